@@ -1,0 +1,130 @@
+"""Generate the golden vectors under tests/golden/ from the REFERENCE itself (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports the reference's torch-only modules by file path from /root/reference (``import torch_em`` fails in
+this image: imageio/skimage/bioimage_cpp are absent), runs them on seeded inputs in fp32 on CPU and stores
+inputs, weights, outputs, losses and gradients as small .npz fixtures.  /root/reference does not exist on the
+GPU box, so the tests only ever read the .npz files.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference/torch_em"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _np(sd):
+    return {k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def unet_case(ref_unet, ref_dice, name, ctor, kwargs, shape, seed):
+    torch.manual_seed(seed)
+    net = getattr(ref_unet, ctor)(**kwargs)
+    if kwargs.get("norm") == "GroupNorm":  # make the affine params non-trivial
+        with torch.no_grad():
+            for k, p in net.named_parameters():
+                if p.dim() == 1 and (".block.0." in k or ".block.3." in k):
+                    p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(*shape)
+    t = (torch.rand(shape[0], kwargs["out_channels"], *shape[2:]) > 0.5).float()
+    y = net(x)
+    loss = ref_dice.DiceLoss()(y, t)
+    loss.backward()
+    out = {"x": x.numpy(), "t": t.numpy(), "y": y.detach().numpy(), "loss": loss.detach().numpy()}
+    for k, v in net.state_dict().items():
+        out["w:" + k] = v.numpy()
+    for k, p in net.named_parameters():
+        out["g:" + k] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "loss", float(loss), "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
+def main():
+    torch.set_num_threads(4)
+    ref_unet = _load("ref_unet", "model/unet.py")
+    ref_dice = _load("ref_dice", "loss/dice.py")
+    ref_wrap = _load("ref_wrap", "loss/wrapper.py")
+
+    unet_case(ref_unet, ref_dice, "unet3d_d2_f4_instnorm", "UNet3d",
+              dict(in_channels=1, out_channels=2, depth=2, initial_features=4, final_activation="Sigmoid"),
+              (2, 1, 16, 16, 16), 0)
+    unet_case(ref_unet, ref_dice, "unet3d_d2_f8_groupnorm", "UNet3d",
+              dict(in_channels=2, out_channels=3, depth=2, initial_features=8, final_activation="Sigmoid",
+                   norm="GroupNorm"),
+              (1, 2, 8, 16, 16), 1)
+    unet_case(ref_unet, ref_dice, "unet3d_d1_f4_nonorm", "UNet3d",
+              dict(in_channels=1, out_channels=1, depth=1, initial_features=4, final_activation=None, norm=None),
+              (1, 1, 8, 8, 8), 2)
+    unet_case(ref_unet, ref_dice, "aniso_f4_anisokernel", "AnisotropicUNet",
+              dict(in_channels=1, out_channels=3, scale_factors=[[1, 2, 2], [2, 2, 2]], initial_features=4,
+                   final_activation="Sigmoid", anisotropic_kernel=True),
+              (1, 1, 4, 16, 16), 3)
+    unet_case(ref_unet, ref_dice, "aniso_f4_isokernel", "AnisotropicUNet",
+              dict(in_channels=1, out_channels=2, scale_factors=[[1, 2, 2], [2, 2, 2]], initial_features=4,
+                   final_activation="Sigmoid", anisotropic_kernel=False),
+              (1, 1, 4, 16, 16), 4)
+
+    # Dice + masked Dice (LossWrapper(DiceLoss(), ApplyAndRemoveMask("multiply"))) with gradients
+    torch.manual_seed(5)
+    p = torch.rand(2, 3, 4, 8, 8, requires_grad=True)
+    t = (torch.rand(2, 3, 4, 8, 8) > 0.5).float()
+    m = (torch.rand(2, 3, 4, 8, 8) > 0.3).float()
+    out = {"p": p.detach().numpy(), "t": t.numpy(), "m": m.numpy()}
+    for red in ("sum", "mean", "max", "min"):
+        p.grad = None
+        l = ref_dice.DiceLoss(reduce_channel=red)(p, t)
+        l.backward()
+        out[f"loss_{red}"] = l.detach().numpy()
+        out[f"grad_{red}"] = p.grad.numpy().copy()
+    p.grad = None
+    l = ref_dice.DiceLoss(channelwise=False)(p, t)
+    l.backward()
+    out["loss_pooled"], out["grad_pooled"] = l.detach().numpy(), p.grad.numpy().copy()
+    p.grad = None
+    wrapped = ref_wrap.LossWrapper(ref_dice.DiceLoss(), transform=ref_wrap.ApplyAndRemoveMask("multiply"))
+    l = wrapped(p, torch.cat([t, m], 1))
+    l.backward()
+    out["loss_masked"], out["grad_masked"] = l.detach().numpy(), p.grad.numpy().copy()
+    out["loss_ones_ones"] = ref_dice.DiceLoss()(torch.ones(1, 1, 8, 8), torch.ones(1, 1, 8, 8)).numpy()
+    out["loss_ones_zeros"] = ref_dice.DiceLoss()(torch.ones(1, 1, 8, 8), torch.zeros(1, 1, 8, 8)).numpy()
+    np.savez_compressed(os.path.join(HERE, "dice.npz"), **out)
+    print("dice", {k: float(v) for k, v in out.items() if k.startswith("loss")})
+
+    # Affinity / boundary targets: the reference's arithmetic lives in absent third-party code; the fixture is
+    # generated with the brute-force functions restated from the reference's own test (oracle/labels.py).
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import labels as L
+    rng = np.random.default_rng(7)
+    seg2 = rng.integers(1, 6, size=(64, 64)).astype("int64")
+    seg2z = seg2.copy(); seg2z[rng.random(seg2.shape) < 0.25] = 0
+    offs2 = [[-1, 0], [0, -1], [-3, 0], [0, -3], [4, 5], [-3, 2]]          # test_label_transforms.py:70-72
+    seg3 = rng.integers(1, 5, size=(6, 10, 12)).astype("int64"); seg3[rng.random(seg3.shape) < 0.2] = 0
+    offs3 = [[-1, 0, 0], [0, -1, 0], [0, 0, -1], [-2, 0, 0], [0, -3, 0], [0, 0, -3],
+             [-3, 0, 0], [0, -9, 0], [0, 0, -9], [-4, 0, 0], [0, -27, 0], [0, 0, -27], [1, 2, -3]]
+    out = {"seg2": seg2, "seg2z": seg2z, "offs2": np.array(offs2), "seg3": seg3, "offs3": np.array(offs3)}
+    out["affs2"] = L.affs_brute_force(seg2, offs2)
+    a, m_ = L.affs_brute_force_with_mask(seg2z, offs2, True); out["affs2z"], out["mask2z"] = a, m_
+    a, m_ = L.affs_brute_force_with_mask(seg2z, offs2, False); out["affs2z_it"], out["mask2z_it"] = a, m_
+    out["affs3"] = L.affs_brute_force(seg3, offs3)
+    a, m_ = L.affs_brute_force_with_mask(seg3, offs3, True); out["affs3z"], out["mask3z"] = a, m_
+    a, m_ = L.affs_brute_force_with_mask(seg3, offs3, False); out["affs3z_it"], out["mask3z_it"] = a, m_
+    out["bound3"] = L.boundary_targets_scipy(seg3)
+    np.savez_compressed(os.path.join(HERE, "labels.npz"), **out)
+    print("labels ok")
+
+
+if __name__ == "__main__":
+    main()
