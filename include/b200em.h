@@ -1,0 +1,162 @@
+/*
+ * b200em.h -- C ABI of libb200em.so: the B200 (sm_100a) kernels behind torch-em's 3D U-Net train step.
+ *
+ * The reference (constantinpape/torch-em) is pure Python over torch.nn; it has no FFI of its own.  Its
+ * "plugin API" for this path is nn.Module duck-typing.  This header is the boundary a
+ * maintainer would bind instead of the torch.nn calls listed beside each entry point: plain pointers and sizes,
+ * a cudaStream_t passed as void*, int status returns (0 = ok, message via b200em_last_error()).  No torch types.
+ * No entry point allocates device memory or synchronises the stream; workspaces are caller-provided.
+ *
+ * Conventions
+ *   - Activations are channels-last "NDHWC": element (n,d,h,w,c) at ((n*D+d)*H+h)*W+w)*ld + c, ld >= C being
+ *     the per-voxel pitch in elements (so a tensor can be a channel slice of a wider concat buffer).
+ *   - dtype codes: B200EM_F32 = 0, B200EM_BF16 = 1.  Statistics / gradients of parameters are always fp32.
+ *   - "sums" buffers are ACCUMULATED into with atomics: the caller zeroes them.
+ *   - Network input / prediction / targets / labels are NCDHW like the reference's tensors.
+ */
+#ifndef B200EM_H_
+#define B200EM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200EM_ABI_VERSION 1
+#define B200EM_F32 0
+#define B200EM_BF16 1
+
+#define B200EM_ACT_NONE 0
+#define B200EM_ACT_SIGMOID 1
+#define B200EM_ACT_RELU 2
+#define B200EM_ACT_TANH 3
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int b200em_abi_version(void);
+const char* b200em_last_error(void);
+/* SM count and compute capability of the current device; umma_ok = 1 iff tcgen05 kernels can run (cc 10.x). */
+int b200em_device_info(int* sm_count, int* cc_major, int* cc_minor, int* umma_ok);
+/* Number of kernel launches issued through this library since the last reset (bench.py "gpu_launches"). */
+int64_t b200em_launch_count(void);
+void b200em_reset_launch_count(void);
+
+/* ---- layout ------------------------------------------------------------------------------------------- */
+/* NCDHW fp32 network input -> NDHWC activations (replaces nothing in the reference: it keeps NCDHW). */
+int b200em_ncdhw_to_ndhwc(const float* x, void* y, int y_dtype, int64_t y_ld, int N, int C, int64_t S, void* stream);
+
+/* ---- convolution weights -------------------------------------------------------------------------------
+ * Re-pack an nn.Conv3d weight (Cout,Cin,kd,kh,kw) fp32 (unet.py:431,435,453,638) into the direct-kernel operand
+ * layouts.  Any output may be NULL.  taps = kd*kh*kw, tap index t = (a*kh+b)*kw+c, flipped tap = taps-1-t.
+ *   w_fwd_f32   [taps][Cin][Cout]            forward
+ *   w_dgrad_f32 [taps][Cout][Cin]  (flipped) data-gradient = forward conv of dY with these ("Cin" <-> "Cout")
+ */
+int b200em_pack_conv_weights(const float* w, int Cout, int Cin, int kd, int kh, int kw,
+                             float* w_fwd_f32, float* w_dgrad_f32, void* stream);
+
+/* ---- convolution: [Norm ->] nn.Conv3d(k, padding=k//2) [-> ReLU]  (unet.py:429-438) and its backward ------- */
+/* Direct (CUDA-core, fp32 accumulate) path: any channel counts, f32 or bf16 activations.  w = w_fwd_f32 layout.
+ *   x_hat = in_scale_shift ? scale[n,c]*x + shift[n,c] : x   on in-bounds voxels, 0 in the padding
+ *   y     = act(conv(x_hat, w) + bias)                       bias may be NULL; relu in {0,1}
+ *   sums (nullable) [N][Cout][2] += (sum y, sum y^2) of the STORED (rounded) outputs: the statistics the next
+ *   InstanceNorm/GroupNorm needs (unet.py:397,402).
+ * The data-gradient is the same call with w = w_dgrad_f32 and Cin/Cout swapped. */
+int b200em_conv3d_direct(const void* x, int64_t x_ld, const float* in_scale_shift, const float* w, const float* bias,
+                         void* y, int64_t y_ld, float* sums, int dtype, int N, int D, int H, int W, int Cin, int Cout,
+                         int kd, int kh, int kw, int relu, void* stream);
+/* dW (Cout,Cin,kd,kh,kw) fp32 += sum_{n,vox} dz[n,vox,co] * x_hat[n,vox+tap,ci]  (torch layout, accumulated). */
+int b200em_conv3d_wgrad_direct(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld,
+                               int dtype, float* dw, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
+                               int kw, void* stream);
+
+/* ---- normalisation: nn.InstanceNorm3d(C) / nn.GroupNorm(min(32,C),C)  (unet.py:391-406) ------------------- */
+/* sums[N][C][2] += (sum x, sum x^2) over the S voxels of each sample. */
+int b200em_channel_sums(const void* x, int64_t x_ld, int dtype, int N, int64_t S, int C, float* sums, void* stream);
+/* sums[N][C][2] += (sum g, sum g*x): the two reductions of the norm backward. */
+int b200em_channel_dot_sums(const void* g, int64_t g_ld, const void* x, int64_t x_ld, int dtype,
+                            int N, int64_t S, int C, float* sums, void* stream);
+/* From per-channel sums make x_hat = scale*x + shift.  groups == C: InstanceNorm (gamma/beta may be NULL);
+ * groups < C: GroupNorm over C/groups consecutive channels with affine gamma/beta.  Biased variance, eps inside
+ * the sqrt.  mean_rstd[N][C][2] is kept for the backward. */
+int b200em_norm_finalize(const float* sums, int N, int C, int64_t S, int groups, const float* gamma,
+                         const float* beta, float eps, float* scale_shift, float* mean_rstd, void* stream);
+/* y = scale[n,c]*x + shift[n,c] */
+int b200em_affine_apply(const void* x, int64_t x_ld, const float* scale_shift, void* y, int64_t y_ld, int dtype,
+                        int N, int64_t S, int C, void* stream);
+/* Backward coefficients: dx = coef0*g + coef1*x + coef2 per (n,c); dgamma/dbeta (nullable) accumulated. */
+int b200em_norm_bwd_finalize(const float* dsums, const float* mean_rstd, const float* gamma, int N, int C,
+                             int64_t S, int groups, float* coef, float* dgamma, float* dbeta, void* stream);
+/* out = (coef0*g + coef1*x + coef2 [+ add]) * (relu_mask ? x > 0 : 1).  coef == NULL means out = g [+ add]. */
+int b200em_norm_bwd_apply(const void* g, int64_t g_ld, const void* x, int64_t x_ld, const float* coef,
+                          const void* add, int64_t add_ld, void* out, int64_t out_ld, int dtype,
+                          int N, int64_t S, int C, int relu_mask, void* stream);
+
+/* ---- nn.MaxPool3d(factor) (unet.py:645, 316) -------------------------------------------------------------- */
+/* (D,H,W) are the INPUT dims; sums (nullable) [N][C][2] += stats of the pooled output. */
+int b200em_maxpool3d_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int dtype, int N, int D, int H, int W,
+                         int C, int fd, int fh, int fw, float* sums, void* stream);
+/* out[hi] = ((hi is the first max of its window ? dp[window] : 0) [+ add[hi]]) * (relu_mask ? x[hi] > 0 : 1) */
+int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp_ld, const void* add, int64_t add_ld,
+                         void* out, int64_t out_ld, int dtype, int N, int D, int H, int W, int C,
+                         int fd, int fh, int fw, int relu_mask, void* stream);
+
+/* ---- F.interpolate(mode="trilinear", align_corners=False), integer scale (unet.py:456) --------------------- */
+/* (D,H,W) are the LOW-resolution dims. */
+int b200em_upsample_trilinear_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int dtype, int N, int D, int H,
+                                  int W, int C, int fd, int fh, int fw, float* sums, void* stream);
+int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int dtype, int N, int D,
+                                  int H, int W, int C, int fd, int fh, int fw, void* stream);
+
+/* ---- out_conv (1x1x1) + final activation (unet.py:202-205, 638, 162-172) ---------------------------------- */
+/* x NDHWC (Cin) -> out NCDHW fp32 (Cout): out = act(W x + b); w is (Cout,Cin) fp32 = the torch weight. */
+int b200em_head_fwd(const void* x, int64_t x_ld, int dtype, const float* w, const float* bias, float* out,
+                    int N, int64_t S, int Cin, int Cout, int act, void* stream);
+/* grad_out, out: NCDHW fp32.  dx NDHWC (nullable), multiplied by [x > 0] when relu_mask (x is then the post-ReLU
+ * output of the last conv block, unet.py:437); dw (Cout,Cin) and db (Cout) accumulated. */
+int b200em_head_bwd(const float* grad_out, const float* out, const void* x, int64_t x_ld, int dtype, const float* w,
+                    void* dx, int64_t dx_ld, float* dw, float* db, int N, int64_t S, int Cin, int Cout, int act,
+                    int relu_mask, void* stream);
+
+/* ---- DiceLoss [+ ApplyAndRemoveMask("multiply")]  (loss/dice.py:34-93, loss/wrapper.py:84-87,129-152) ------- */
+/* pred (N,C,S) fp32 or bf16; target fp32 with sample stride target_nstride (elements): channel c of sample n at
+ * target + n*target_nstride + c*S.  mask (nullable) laid out like target.  sums[C][3] += (sum pm*tm, sum pm^2,
+ * sum tm^2) with pm = p*m, tm = t*m. */
+int b200em_dice_sums(const void* pred, int pred_dtype, const float* target, const float* mask,
+                     int64_t target_nstride, int N, int C, int64_t S, float* sums, void* stream);
+/* loss (device scalar) and backward coefficients coef[C][2] (A_c, B_c): dL/dp = A_c*t*m^2 + B_c*p*m^2.
+ * reduce: 0 sum, 1 mean, 2 max, 3 min, 4 none(per-channel losses written to loss[0..C)); channelwise in {0,1}. */
+int b200em_dice_finalize(const float* sums, int C, float eps, int channelwise, int reduce, float* loss, float* coef,
+                         void* stream);
+/* grad_pred (N,C,S) of grad_dtype = gout[0..] * (A_c t m^2 + B_c p m^2); gout is a device scalar (or C values,
+ * reduce=4). */
+int b200em_dice_bwd(const void* pred, int pred_dtype, const float* target, const float* mask, int64_t target_nstride,
+                    const float* coef, const float* gout, int gout_per_channel, void* grad_pred, int grad_dtype,
+                    int N, int C, int64_t S, void* stream);
+
+/* ---- AffinityTransform / BoundaryTransform (transform/label.py:248-327, 100-129) --------------------------- */
+/* labels (N,D,H,W) int64; offsets: n_off*3 host ints (dz,dy,dx); out (N, channels, D,H,W) fp32 with channel
+ * order [fg?][n_off disaffinities][fg-mask?][n_off masks]  (masks only if add_mask). */
+int b200em_affinity_targets(const int64_t* labels, float* out, int N, int D, int H, int W, const int* offsets,
+                            int n_off, int has_ignore, int64_t ignore_label, int add_binary_target, int add_mask,
+                            int include_ignore_transitions, void* stream);
+/* out (N, 1 or 2, D,H,W) fp32: [foreground?][boundary], boundary = some in-bounds 6-neighbour differs. */
+int b200em_boundary_targets(const int64_t* labels, float* out, int N, int D, int H, int W, int add_binary_target,
+                            void* stream);
+/* Fused target+loss reductions: Dice sums of pred against AffinityTransform(offsets, add_mask=True) targets computed
+ * on the fly from labels (no target tensor in HBM).  Same sums/coef contract as b200em_dice_sums / _bwd. */
+int b200em_affinity_dice_sums(const void* pred, int pred_dtype, const int64_t* labels, int N, int D, int H, int W,
+                              const int* offsets, int n_off, int has_ignore, int64_t ignore_label,
+                              int include_ignore_transitions, float* sums, void* stream);
+int b200em_affinity_dice_bwd(const void* pred, int pred_dtype, const int64_t* labels, int N, int D, int H, int W,
+                             const int* offsets, int n_off, int has_ignore, int64_t ignore_label,
+                             int include_ignore_transitions, const float* coef, const float* gout, void* grad_pred,
+                             int grad_dtype, void* stream);
+
+/* ---- utilities ---------------------------------------------------------------------------------------- */
+/* Write `bytes` bytes of zeros (L2 flush helper for bench.py and buffer clears without a torch launch). */
+int b200em_memset_zero(void* p, int64_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200EM_H_ */

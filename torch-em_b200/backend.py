@@ -1,0 +1,204 @@
+"""The one compute backend of the product: calls into ``libb200em.so`` (hand-written sm_100a CUDA) through the C ABI.
+
+Each method takes torch tensors only to read ``data_ptr()``, shapes and the channel pitch; the arithmetic is in the
+library.  There is no CPU or PyTorch fallback: tensors that are not on a CUDA device raise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT, BF16, F32, call
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"activations must be float32 or bfloat16, got {t.dtype}")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _act(t):
+    """(pointer, pitch) of an NDHWC activation view (N, D, H, W, C) whose base buffer is contiguous."""
+    if t.device.type != "cuda":
+        raise RuntimeError("b200em: tensors must live on a CUDA device (there is no CPU fallback for this path)")
+    assert t.dim() == 5 and t.stride(4) == 1, "NDHWC activation view expected"
+    ld = t.stride(3)
+    N, D, H, W, C = t.shape
+    assert ld >= C and t.stride(2) == W * ld and t.stride(1) == H * W * ld and (N == 1 or t.stride(0) == D * H * W * ld), \
+        "activation view must be a channel slice of a contiguous NDHWC buffer"
+    return _ptr(t), ld
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _f32(t):
+    if t is None:
+        return None
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    return _ptr(t)
+
+
+class WeightPack:
+    """Kernel-operand copies of one conv weight (derived caches; the fp32 nn.Parameter stays the master)."""
+    __slots__ = ("w_fwd_f32", "w_dgrad_f32", "umma_fwd", "umma_dgrad", "version", "ptr", "cout", "cin", "kernel")
+
+
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self, use_umma=True):
+        self.use_umma = use_umma
+        self._pack_cache = {}
+
+    # ---- weights ---------------------------------------------------------------------------------------------
+    def pack(self, key, w):
+        if w.device.type != "cuda":
+            raise RuntimeError("b200em: parameters must live on a CUDA device (there is no CPU fallback for this path)")
+        ver = (w.data_ptr(), w._version, tuple(w.shape), w.device)
+        pk = self._pack_cache.get(key)
+        if pk is not None and pk.version == ver:
+            return pk
+        cout, cin, kd, kh, kw = w.shape
+        wd = w.detach()
+        assert wd.dtype == torch.float32 and wd.is_contiguous()
+        pk = WeightPack()
+        pk.version, pk.cout, pk.cin, pk.kernel = ver, cout, cin, (kd, kh, kw)
+        taps = kd * kh * kw
+        pk.w_fwd_f32 = torch.empty((taps, cin, cout), dtype=torch.float32, device=w.device)
+        pk.w_dgrad_f32 = torch.empty((taps, cout, cin), dtype=torch.float32, device=w.device)
+        pk.umma_fwd = pk.umma_dgrad = None
+        with torch.cuda.device(w.device):
+            call("b200em_pack_conv_weights", _ptr(wd), cout, cin, kd, kh, kw, _ptr(pk.w_fwd_f32), _ptr(pk.w_dgrad_f32),
+                 _stream(w))
+        self._pack_cache[key] = pk
+        return pk
+
+    # ---- layout / statistics ---------------------------------------------------------------------------------
+    def to_ndhwc(self, x, y):
+        N, C, D, H, W = x.shape
+        yp, yld = _act(y)
+        call("b200em_ncdhw_to_ndhwc", _f32(x), yp, _dt(y), yld, N, C, D * H * W, _stream(x))
+
+    def channel_sums(self, x, sums):
+        N, D, H, W, C = x.shape
+        xp, xld = _act(x)
+        call("b200em_channel_sums", xp, xld, _dt(x), N, D * H * W, C, _f32(sums), _stream(x))
+
+    def channel_dot_sums(self, g, x, sums):
+        N, D, H, W, C = x.shape
+        gp, gld = _act(g)
+        xp, xld = _act(x)
+        call("b200em_channel_dot_sums", gp, gld, xp, xld, _dt(x), N, D * H * W, C, _f32(sums), _stream(x))
+
+    def norm_finalize(self, sums, S, groups, gamma, beta, eps):
+        N, C, _ = sums.shape
+        ss = torch.empty((N, C, 2), dtype=torch.float32, device=sums.device)
+        mr = torch.empty((N, C, 2), dtype=torch.float32, device=sums.device)
+        g = gamma.detach() if gamma is not None else None
+        b = beta.detach() if beta is not None else None
+        call("b200em_norm_finalize", _f32(sums), N, C, S, groups, _f32(g), _f32(b), eps, _f32(ss), _f32(mr), _stream(sums))
+        return ss, mr
+
+    def norm_bwd_finalize(self, dsums, mr, gamma, S, groups, dgamma, dbeta):
+        N, C, _ = dsums.shape
+        coef = torch.empty((N, C, 3), dtype=torch.float32, device=dsums.device)
+        g = gamma.detach() if gamma is not None else None
+        call("b200em_norm_bwd_finalize", _f32(dsums), _f32(mr), _f32(g), N, C, S, groups, _f32(coef), _f32(dgamma),
+             _f32(dbeta), _stream(dsums))
+        return coef
+
+    def norm_bwd_apply(self, g, x, coef, add, out, relu_mask):
+        N, D, H, W, C = g.shape
+        gp, gld = _act(g)
+        xp, xld = _act(x)
+        ap, ald = _act(add) if add is not None else (None, 0)
+        op, old = _act(out)
+        call("b200em_norm_bwd_apply", gp, gld, xp, xld, _f32(coef), ap, ald, op, old, _dt(g), N, D * H * W, C,
+             int(relu_mask), _stream(g))
+
+    # ---- convolution -----------------------------------------------------------------------------------------
+    def conv(self, x, in_ss, pack, bias, y, sums, kernel, relu, dgrad):
+        """y = act(conv(norm(x)) + bias).  dgrad=True: the data-gradient (flipped/transposed weights)."""
+        N, D, H, W, Cin = x.shape
+        Cout = y.shape[4]
+        xp, xld = _act(x)
+        yp, yld = _act(y)
+        assert _dt(x) == _dt(y)
+        w = pack.w_dgrad_f32 if dgrad else pack.w_fwd_f32
+        b = bias.detach() if bias is not None else None
+        kd, kh, kw = kernel
+        call("b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, _f32(sums), _dt(x), N, D, H, W, Cin,
+             Cout, kd, kh, kw, int(relu), _stream(x))
+
+    def wgrad(self, x, in_ss, dz, dw, kernel):
+        N, D, H, W, Cin = x.shape
+        Cout = dz.shape[4]
+        xp, xld = _act(x)
+        zp, zld = _act(dz)
+        kd, kh, kw = kernel
+        call("b200em_conv3d_wgrad_direct", xp, xld, _f32(in_ss), zp, zld, _dt(x), _f32(dw), N, D, H, W, Cin, Cout, kd, kh, kw,
+             _stream(x))
+
+    # ---- pool / upsample -------------------------------------------------------------------------------------
+    def maxpool_fwd(self, x, y, f, sums):
+        N, D, H, W, C = x.shape
+        xp, xld = _act(x)
+        yp, yld = _act(y)
+        call("b200em_maxpool3d_fwd", xp, xld, yp, yld, _dt(x), N, D, H, W, C, f[0], f[1], f[2], _f32(sums), _stream(x))
+
+    def maxpool_bwd(self, x, dp, add, out, f, relu_mask):
+        N, D, H, W, C = x.shape
+        xp, xld = _act(x)
+        dpp, dpld = _act(dp)
+        ap, ald = _act(add) if add is not None else (None, 0)
+        op, old = _act(out)
+        call("b200em_maxpool3d_bwd", xp, xld, dpp, dpld, ap, ald, op, old, _dt(x), N, D, H, W, C, f[0], f[1], f[2],
+             int(relu_mask), _stream(x))
+
+    def upsample_fwd(self, x, y, f, sums):
+        N, D, H, W, C = x.shape
+        xp, xld = _act(x)
+        yp, yld = _act(y)
+        call("b200em_upsample_trilinear_fwd", xp, xld, yp, yld, _dt(x), N, D, H, W, C, f[0], f[1], f[2], _f32(sums),
+             _stream(x))
+
+    def upsample_bwd(self, dy, dx, f):
+        N, D, H, W, C = dx.shape
+        yp, yld = _act(dy)
+        xp, xld = _act(dx)
+        call("b200em_upsample_trilinear_bwd", yp, yld, xp, xld, _dt(dx), N, D, H, W, C, f[0], f[1], f[2], _stream(dx))
+
+    # ---- head ------------------------------------------------------------------------------------------------
+    def head_fwd(self, x, w, b, out, act):
+        N, D, H, W, Cin = x.shape
+        Cout = out.shape[1]
+        xp, xld = _act(x)
+        call("b200em_head_fwd", xp, xld, _dt(x), _f32(w.detach().reshape(Cout, Cin)), _f32(b.detach()), _f32(out), N,
+             D * H * W, Cin, Cout, ACT[act], _stream(x))
+
+    def head_bwd(self, grad_out, out, x, w, dx, dw, db, act, relu_mask):
+        N, D, H, W, Cin = x.shape
+        Cout = out.shape[1]
+        xp, xld = _act(x)
+        dxp, dxld = _act(dx) if dx is not None else (None, 0)
+        call("b200em_head_bwd", _f32(grad_out), _f32(out), xp, xld, _dt(x), _f32(w.detach().reshape(Cout, Cin)), dxp, dxld,
+             _f32(dw), _f32(db), N, D * H * W, Cin, Cout, ACT[act], int(relu_mask), _stream(x))
+
+
+_default = None
+
+
+def default_backend():
+    global _default
+    if _default is None:
+        _lib.load()
+        _default = CudaBackend()
+    return _default

@@ -1,0 +1,108 @@
+// Shared helpers for libb200em (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200em.h"
+
+namespace b200em {
+
+// ---- error plumbing -----------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define B2_CHECK_ARG(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            b200em::set_error(__VA_ARGS__);     \
+            return 1;                           \
+        }                                       \
+    } while (0)
+
+#define B2_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            b200em::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return 3;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+#define B2_LAUNCH_CHECK()                                                                     \
+    do {                                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess) {                                                             \
+            b200em::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return 3;                                                                         \
+        }                                                                                     \
+        b200em::count_launch();                                                               \
+    } while (0)
+
+int sm_count();
+
+// ---- scalar conversion ----------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- 16-byte vectors of activations ----------------------------------------------------------------------------
+// VEC elements per thread: 4 (f32) / 8 (bf16) when everything is 16 B aligned, else 1.
+template <typename T, int VEC> struct Vec;
+template <> struct Vec<float, 4> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec<float, 1> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = *p; }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
+};
+template <> struct Vec<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 t = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f = __bfloat1622float2(h[i]);
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint4 t;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = t;
+    }
+};
+template <> struct Vec<__nv_bfloat16, 1> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[1]) { *p = __float2bfloat16_rn(v[0]); }
+};
+
+template <typename T> struct FullVec;
+template <> struct FullVec<float> { static constexpr int value = 4; };
+template <> struct FullVec<__nv_bfloat16> { static constexpr int value = 8; };
+
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Round a stored value the way the activation dtype would (bf16 statistics are taken on the rounded values).
+template <typename T> __device__ __forceinline__ float round_as(float v) { return to_f<T>(from_f<T>(v)); }
+
+// dispatch on dtype code
+#define B2_DISPATCH_DTYPE(dtype, T, ...)                                   \
+    if ((dtype) == B200EM_F32) { using T = float; __VA_ARGS__ }            \
+    else if ((dtype) == B200EM_BF16) { using T = __nv_bfloat16; __VA_ARGS__ } \
+    else { b200em::set_error("bad dtype code %d", (int)(dtype)); return 1; }
+
+}  // namespace b200em

@@ -1,0 +1,623 @@
+// Memory-bound NDHWC kernels of the U-Net block plumbing: layout change, per-channel statistics, the
+// InstanceNorm/GroupNorm apply and backward, max-pool, trilinear upsample.  All are HBM-roofline kernels:
+// one pass over each operand, 16-byte vector accesses along the channel axis, fp32 math.
+//
+// Reference semantics restated (see include/b200em.h for the per-entry citations):
+//   InstanceNorm3d / GroupNorm   unet.py:391-406      MaxPool3d   unet.py:645,316
+//   F.interpolate(trilinear)     unet.py:456          ReLU'       unet.py:433,437
+#include "common.cuh"
+
+namespace b200em {
+
+// Thread layout shared by all kernels here: blockDim = (bx, by); x walks channel vectors (contiguous in
+// memory -> coalesced), y walks voxels.  blockIdx.y = sample, blockIdx.x strides over voxel rows.
+struct Launch2D {
+    dim3 grid, block;
+};
+static Launch2D make_launch(int cvec, int64_t rows, int N, int max_blocks_per_sample = 0) {
+    int bx = cvec < 256 ? cvec : 256;
+    int by = 256 / bx;
+    if (by < 1) by = 1;
+    int64_t need = (rows + by - 1) / by;
+    int64_t cap = max_blocks_per_sample > 0 ? max_blocks_per_sample : (int64_t)sm_count() * 8 / (N > 0 ? N : 1) + 1;
+    if (need > cap) need = cap;
+    if (need < 1) need = 1;
+    Launch2D l;
+    l.grid = dim3((unsigned)need, (unsigned)N, 1);
+    l.block = dim3(bx, by, 1);
+    return l;
+}
+
+template <int VEC, int K>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[VEC][K], float* out_nc, int cv, bool active) {
+    __shared__ float red[256 * VEC * K];
+    const int bx = blockDim.x, by = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
+    float* mine = red + (ty * bx + tx) * (VEC * K);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+        for (int k = 0; k < K; ++k) mine[v * K + k] = acc[v][k];
+    __syncthreads();
+    if (ty == 0 && active) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float s = 0.f;
+                for (int j = 0; j < by; ++j) s += red[(j * bx + tx) * (VEC * K) + v * K + k];
+                atomicAdd(out_nc + (size_t)(cv * VEC + v) * K + k, s);
+            }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// layout: NCDHW fp32 -> NDHWC
+template <typename T>
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t y_ld, int C, int64_t S,
+                                      int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = i % S;
+        int64_t nc = i / S;
+        int c = (int)(nc % C);
+        int64_t n = nc / C;
+        y[(n * S + s) * y_ld + c] = from_f<T>(x[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-(n,c) sums: (sum x, sum x^2)  and  (sum g, sum g*x)
+template <typename T, int VEC, bool DOT>
+__global__ void channel_sums_kernel(const T* __restrict__ a, int64_t a_ld, const T* __restrict__ b, int64_t b_ld,
+                                    int64_t S, int C, float* __restrict__ sums) {
+    const int n = blockIdx.y, cvec = C / VEC;
+    const T* an = a + (size_t)n * S * a_ld;
+    const T* bn = DOT ? b + (size_t)n * S * b_ld : nullptr;
+    for (int cvb = 0; cvb < cvec; cvb += blockDim.x) {
+        const int cv = cvb + threadIdx.x;
+        const bool active = cv < cvec;
+        float acc[VEC][2];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v][0] = acc[v][1] = 0.f;
+        if (active) {
+            for (int64_t s = blockIdx.x * (int64_t)blockDim.y + threadIdx.y; s < S; s += (int64_t)gridDim.x * blockDim.y) {
+                float va[VEC];
+                Vec<T, VEC>::load(an + s * a_ld + cv * VEC, va);
+                if (DOT) {
+                    float vb[VEC];
+                    Vec<T, VEC>::load(bn + s * b_ld + cv * VEC, vb);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { acc[v][0] += va[v]; acc[v][1] += va[v] * vb[v]; }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { acc[v][0] += va[v]; acc[v][1] += va[v] * va[v]; }
+                }
+            }
+        }
+        block_channel_reduce<VEC, 2>(acc, sums + (size_t)n * C * 2, cv, active);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// norm finalize: one thread per (n, group)
+__global__ void norm_finalize_kernel(const float* __restrict__ sums, int N, int C, float S, int groups,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                     float* __restrict__ scale_shift, float* __restrict__ mean_rstd) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * groups) return;
+    int n = i / groups, g = i % groups;
+    int cpg = C / groups;
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+        int c = g * cpg + j;
+        s1 += sums[((size_t)n * C + c) * 2];
+        s2 += sums[((size_t)n * C + c) * 2 + 1];
+    }
+    double cnt = (double)S * cpg;
+    double mean = s1 / cnt;
+    double var = s2 / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    for (int j = 0; j < cpg; ++j) {
+        int c = g * cpg + j;
+        float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+        size_t o = ((size_t)n * C + c) * 2;
+        scale_shift[o] = rstd * ga;
+        scale_shift[o + 1] = be - (float)mean * rstd * ga;
+        mean_rstd[o] = (float)mean;
+        mean_rstd[o + 1] = rstd;
+    }
+}
+
+// norm backward finalize: one thread per (n, group).
+//   x_hat = (x - mean) * rstd;  dxh = gamma * g;  m1 = mean_grp(dxh), m2 = mean_grp(dxh * x_hat)
+//   dx = rstd * (dxh - m1 - x_hat * m2) = coef0 * g + coef1 * x + coef2
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ dsums, const float* __restrict__ mean_rstd,
+                                         const float* __restrict__ gamma, int N, int C, float S, int groups,
+                                         float* __restrict__ coef, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * groups) return;
+    int n = i / groups, g = i % groups;
+    int cpg = C / groups;
+    size_t base = (size_t)n * C + (size_t)g * cpg;
+    float mean = mean_rstd[base * 2], rstd = mean_rstd[base * 2 + 1];
+    double a1 = 0.0, a2 = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+        int c = g * cpg + j;
+        float ga = gamma ? gamma[c] : 1.f;
+        float sg = dsums[(base + j) * 2], sgx = dsums[(base + j) * 2 + 1];
+        float sgxh = rstd * (sgx - mean * sg);  // sum g * x_hat
+        a1 += (double)ga * sg;
+        a2 += (double)ga * sgxh;
+        if (dgamma) atomicAdd(dgamma + c, sgxh);
+        if (dbeta) atomicAdd(dbeta + c, sg);
+    }
+    double cnt = (double)S * cpg;
+    float m1 = (float)(a1 / cnt), m2 = (float)(a2 / cnt);
+    for (int j = 0; j < cpg; ++j) {
+        int c = g * cpg + j;
+        float ga = gamma ? gamma[c] : 1.f;
+        size_t o = (base + j) * 3;
+        coef[o] = rstd * ga;
+        coef[o + 1] = -rstd * rstd * m2;
+        coef[o + 2] = rstd * (mean * rstd * m2 - m1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// y = scale*x + shift
+template <typename T, int VEC>
+__global__ void affine_apply_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ ss,
+                                    T* __restrict__ y, int64_t y_ld, int64_t S, int C, int64_t total) {
+    const int cvec = C / VEC;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cv = (int)(i % cvec);
+        int64_t vox = i / cvec;  // n*S + s
+        int64_t n = vox / S;
+        float v[VEC];
+        Vec<T, VEC>::load(x + vox * x_ld + cv * VEC, v);
+        const float* p = ss + ((size_t)n * C + cv * VEC) * 2;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = fmaf(v[k], p[2 * k], p[2 * k + 1]);
+        Vec<T, VEC>::store(y + vox * y_ld + cv * VEC, v);
+    }
+}
+
+// out = (c0*g + c1*x + c2 [+ add]) * (relu ? x>0 : 1)
+template <typename T, int VEC>
+__global__ void norm_bwd_apply_kernel(const T* __restrict__ g, int64_t g_ld, const T* __restrict__ x, int64_t x_ld,
+                                      const float* __restrict__ coef, const T* __restrict__ add, int64_t add_ld,
+                                      T* __restrict__ out, int64_t out_ld, int64_t S, int C, int relu_mask,
+                                      int64_t total) {
+    const int cvec = C / VEC;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cv = (int)(i % cvec);
+        int64_t vox = i / cvec;
+        int64_t n = vox / S;
+        float vg[VEC], vx[VEC], va[VEC], r[VEC];
+        Vec<T, VEC>::load(g + vox * g_ld + cv * VEC, vg);
+        const bool need_x = (coef != nullptr) || relu_mask;
+        if (need_x) Vec<T, VEC>::load(x + vox * x_ld + cv * VEC, vx);
+        if (add) Vec<T, VEC>::load(add + vox * add_ld + cv * VEC, va);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            float t = vg[k];
+            if (coef) {
+                const float* p = coef + ((size_t)n * C + cv * VEC + k) * 3;
+                t = fmaf(p[0], vg[k], fmaf(p[1], vx[k], p[2]));
+            }
+            if (add) t += va[k];
+            if (relu_mask && !(vx[k] > 0.f)) t = 0.f;
+            r[k] = t;
+        }
+        Vec<T, VEC>::store(out + vox * out_ld + cv * VEC, r);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// max pool forward (+ statistics of the pooled output)
+template <typename T, int VEC>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __restrict__ y, int64_t y_ld, int D, int H,
+                                   int W, int C, int fd, int fh, int fw, float* __restrict__ sums) {
+    const int n = blockIdx.y, cvec = C / VEC;
+    const int Do = D / fd, Ho = H / fh, Wo = W / fw;
+    const int64_t So = (int64_t)Do * Ho * Wo;
+    const T* xn = x + (size_t)n * D * H * W * x_ld;
+    T* yn = y + (size_t)n * So * y_ld;
+    for (int cvb = 0; cvb < cvec; cvb += blockDim.x) {
+        const int cv = cvb + threadIdx.x;
+        const bool active = cv < cvec;
+        float acc[VEC][2];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v][0] = acc[v][1] = 0.f;
+        if (active) {
+            for (int64_t s = blockIdx.x * (int64_t)blockDim.y + threadIdx.y; s < So; s += (int64_t)gridDim.x * blockDim.y) {
+                int wo = (int)(s % Wo), ho = (int)((s / Wo) % Ho), d_o = (int)(s / ((int64_t)Wo * Ho));
+                float m[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) m[v] = -INFINITY;
+                for (int a = 0; a < fd; ++a)
+                    for (int b = 0; b < fh; ++b)
+                        for (int c = 0; c < fw; ++c) {
+                            int64_t vi = ((int64_t)(d_o * fd + a) * H + (ho * fh + b)) * W + (wo * fw + c);
+                            float t[VEC];
+                            Vec<T, VEC>::load(xn + vi * x_ld + cv * VEC, t);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], t[v]);
+                        }
+                Vec<T, VEC>::store(yn + s * y_ld + cv * VEC, m);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { acc[v][0] += m[v]; acc[v][1] += m[v] * m[v]; }
+            }
+        }
+        if (sums) block_channel_reduce<VEC, 2>(acc, sums + (size_t)n * C * 2, cv, active);
+    }
+}
+
+// max pool backward: one thread per (window, channel vector); first maximum in (d,h,w) scan order wins
+// (ATen max_pool3d_with_indices semantics).
+template <typename T, int VEC>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const T* __restrict__ dp, int64_t dp_ld,
+                                   const T* __restrict__ add, int64_t add_ld, T* __restrict__ out, int64_t out_ld,
+                                   int D, int H, int W, int C, int fd, int fh, int fw, int relu_mask, int64_t total) {
+    const int cvec = C / VEC;
+    const int Do = D / fd, Ho = H / fh, Wo = W / fw;
+    const int64_t So = (int64_t)Do * Ho * Wo, Si = (int64_t)D * H * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cv = (int)(i % cvec);
+        int64_t vox = i / cvec;
+        int64_t n = vox / So, s = vox % So;
+        int wo = (int)(s % Wo), ho = (int)((s / Wo) % Ho), d_o = (int)(s / ((int64_t)Wo * Ho));
+        float m[VEC];
+        int arg[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { m[v] = -INFINITY; arg[v] = 0; }
+        int pos = 0;
+        for (int a = 0; a < fd; ++a)
+            for (int b = 0; b < fh; ++b)
+                for (int c = 0; c < fw; ++c, ++pos) {
+                    int64_t vi = n * Si + ((int64_t)(d_o * fd + a) * H + (ho * fh + b)) * W + (wo * fw + c);
+                    float t[VEC];
+                    Vec<T, VEC>::load(x + vi * x_ld + cv * VEC, t);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        if (t[v] > m[v] || pos == 0) { m[v] = t[v]; arg[v] = pos; }
+                }
+        float gp[VEC];
+        Vec<T, VEC>::load(dp + vox * dp_ld + cv * VEC, gp);
+        pos = 0;
+        for (int a = 0; a < fd; ++a)
+            for (int b = 0; b < fh; ++b)
+                for (int c = 0; c < fw; ++c, ++pos) {
+                    int64_t vi = n * Si + ((int64_t)(d_o * fd + a) * H + (ho * fh + b)) * W + (wo * fw + c);
+                    float r[VEC], t[VEC], va[VEC];
+                    if (relu_mask) Vec<T, VEC>::load(x + vi * x_ld + cv * VEC, t);
+                    if (add) Vec<T, VEC>::load(add + vi * add_ld + cv * VEC, va);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        float q = (arg[v] == pos) ? gp[v] : 0.f;
+                        if (add) q += va[v];
+                        if (relu_mask && !(t[v] > 0.f)) q = 0.f;
+                        r[v] = q;
+                    }
+                    Vec<T, VEC>::store(out + vi * out_ld + cv * VEC, r);
+                }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// trilinear, align_corners=False, integer scale f: src = max(0,(o+0.5)/f-0.5); i0=floor(src); i1=min(i0+1,n-1)
+__device__ __forceinline__ void lerp_src(int o, int f, int n, int& i0, int& i1, float& lam) {
+    if (f == 1) { i0 = i1 = o; lam = 0.f; return; }
+    float src = ((float)o + 0.5f) / (float)f - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    i1 = i0 + 1 < n ? i0 + 1 : n - 1;
+    lam = src - (float)i0;
+}
+
+template <typename T, int VEC>
+__global__ void upsample_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __restrict__ y, int64_t y_ld, int D, int H,
+                                    int W, int C, int fd, int fh, int fw, float* __restrict__ sums) {
+    const int n = blockIdx.y, cvec = C / VEC;
+    const int Do = D * fd, Ho = H * fh, Wo = W * fw;
+    const int64_t So = (int64_t)Do * Ho * Wo;
+    const T* xn = x + (size_t)n * D * H * W * x_ld;
+    T* yn = y + (size_t)n * So * y_ld;
+    for (int cvb = 0; cvb < cvec; cvb += blockDim.x) {
+        const int cv = cvb + threadIdx.x;
+        const bool active = cv < cvec;
+        float acc[VEC][2];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v][0] = acc[v][1] = 0.f;
+        if (active) {
+            for (int64_t s = blockIdx.x * (int64_t)blockDim.y + threadIdx.y; s < So; s += (int64_t)gridDim.x * blockDim.y) {
+                int wo = (int)(s % Wo), ho = (int)((s / Wo) % Ho), d_o = (int)(s / ((int64_t)Wo * Ho));
+                int d0, d1, h0, h1, w0, w1;
+                float ld, lh, lw;
+                lerp_src(d_o, fd, D, d0, d1, ld);
+                lerp_src(ho, fh, H, h0, h1, lh);
+                lerp_src(wo, fw, W, w0, w1, lw);
+                float r[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) r[v] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    int dd = (k & 4) ? d1 : d0, hh = (k & 2) ? h1 : h0, ww = (k & 1) ? w1 : w0;
+                    float wt = ((k & 4) ? ld : 1.f - ld) * ((k & 2) ? lh : 1.f - lh) * ((k & 1) ? lw : 1.f - lw);
+                    if (wt != 0.f) {
+                        float t[VEC];
+                        Vec<T, VEC>::load(xn + (((int64_t)dd * H + hh) * W + ww) * x_ld + cv * VEC, t);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) r[v] = fmaf(wt, t[v], r[v]);
+                    }
+                }
+                Vec<T, VEC>::store(yn + s * y_ld + cv * VEC, r);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    float q = round_as<T>(r[v]);
+                    acc[v][0] += q; acc[v][1] += q * q;
+                }
+            }
+        }
+        if (sums) block_channel_reduce<VEC, 2>(acc, sums + (size_t)n * C * 2, cv, active);
+    }
+}
+
+// backward = transpose of the same sparse weights, written as a gather per low-res voxel (no atomics).
+__device__ __forceinline__ float lerp_weight_to(int o, int f, int n, int i) {
+    int i0, i1;
+    float lam;
+    lerp_src(o, f, n, i0, i1, lam);
+    float w = 0.f;
+    if (i0 == i) w += 1.f - lam;
+    if (i1 == i && f != 1) w += lam;
+    return w;
+}
+
+template <typename T, int VEC>
+__global__ void upsample_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, T* __restrict__ dx, int64_t dx_ld, int D,
+                                    int H, int W, int C, int fd, int fh, int fw, int64_t total) {
+    const int cvec = C / VEC;
+    const int Do = D * fd, Ho = H * fh, Wo = W * fw;
+    const int64_t Si = (int64_t)D * H * W, So = (int64_t)Do * Ho * Wo;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cv = (int)(i % cvec);
+        int64_t vox = i / cvec;
+        int64_t n = vox / Si, s = vox % Si;
+        int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+        // candidate outputs o with src(o) in [i-1, i+1]
+        int dlo = fd == 1 ? d : max(0, fd * d - fd), dhi = fd == 1 ? d : min(Do - 1, fd * d + 2 * fd - 1);
+        int hlo = fh == 1 ? h : max(0, fh * h - fh), hhi = fh == 1 ? h : min(Ho - 1, fh * h + 2 * fh - 1);
+        int wlo = fw == 1 ? w : max(0, fw * w - fw), whi = fw == 1 ? w : min(Wo - 1, fw * w + 2 * fw - 1);
+        float r[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = 0.f;
+        for (int od = dlo; od <= dhi; ++od) {
+            float wd = lerp_weight_to(od, fd, D, d);
+            if (wd == 0.f) continue;
+            for (int oh = hlo; oh <= hhi; ++oh) {
+                float wh = lerp_weight_to(oh, fh, H, h);
+                if (wh == 0.f) continue;
+                for (int ow = wlo; ow <= whi; ++ow) {
+                    float ww = lerp_weight_to(ow, fw, W, w);
+                    if (ww == 0.f) continue;
+                    float t[VEC];
+                    Vec<T, VEC>::load(dy + (n * So + ((int64_t)od * Ho + oh) * Wo + ow) * dy_ld + cv * VEC, t);
+                    float wt = wd * wh * ww;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) r[v] = fmaf(wt, t[v], r[v]);
+                }
+            }
+        }
+        Vec<T, VEC>::store(dx + vox * dx_ld + cv * VEC, r);
+    }
+}
+
+static inline int flat_grid(int64_t total, int threads) {
+    int64_t b = (total + threads - 1) / threads;
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+template <typename T>
+static bool can_vec(int C, std::initializer_list<int64_t> lds, std::initializer_list<const void*> ptrs) {
+    const int V = FullVec<T>::value;
+    if (C % V) return false;
+    for (int64_t ld : lds)
+        if (ld % V) return false;
+    for (const void* p : ptrs)
+        if (p && !aligned16(p)) return false;
+    return true;
+}
+
+}  // namespace b200em
+
+using namespace b200em;
+
+extern "C" {
+
+int b200em_ncdhw_to_ndhwc(const float* x, void* y, int y_dtype, int64_t y_ld, int N, int C, int64_t S, void* stream) {
+    B2_CHECK_ARG(x && y && N > 0 && C > 0 && S > 0 && y_ld >= C, "ncdhw_to_ndhwc: bad arguments");
+    int64_t total = (int64_t)N * C * S;
+    B2_DISPATCH_DTYPE(y_dtype, T, {
+        ncdhw_to_ndhwc_kernel<T><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)y, y_ld, C, S, total);
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_channel_sums(const void* x, int64_t x_ld, int dtype, int N, int64_t S, int C, float* sums, void* stream) {
+    B2_CHECK_ARG(x && sums && N > 0 && C > 0 && S > 0 && x_ld >= C, "channel_sums: bad arguments");
+    B2_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = FullVec<T>::value;
+        if (can_vec<T>(C, {x_ld}, {x})) {
+            Launch2D l = make_launch(C / V, S, N);
+            channel_sums_kernel<T, V, false><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, nullptr, 0, S, C, sums);
+        } else {
+            Launch2D l = make_launch(C, S, N);
+            channel_sums_kernel<T, 1, false><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, nullptr, 0, S, C, sums);
+        }
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_channel_dot_sums(const void* g, int64_t g_ld, const void* x, int64_t x_ld, int dtype, int N, int64_t S, int C,
+                            float* sums, void* stream) {
+    B2_CHECK_ARG(g && x && sums && N > 0 && C > 0 && S > 0 && g_ld >= C && x_ld >= C, "channel_dot_sums: bad arguments");
+    B2_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = FullVec<T>::value;
+        if (can_vec<T>(C, {g_ld, x_ld}, {g, x})) {
+            Launch2D l = make_launch(C / V, S, N);
+            channel_sums_kernel<T, V, true><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)g, g_ld, (const T*)x, x_ld, S, C, sums);
+        } else {
+            Launch2D l = make_launch(C, S, N);
+            channel_sums_kernel<T, 1, true><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)g, g_ld, (const T*)x, x_ld, S, C, sums);
+        }
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_norm_finalize(const float* sums, int N, int C, int64_t S, int groups, const float* gamma, const float* beta,
+                         float eps, float* scale_shift, float* mean_rstd, void* stream) {
+    B2_CHECK_ARG(sums && scale_shift && mean_rstd && N > 0 && C > 0 && S > 0, "norm_finalize: bad arguments");
+    B2_CHECK_ARG(groups > 0 && groups <= C && C % groups == 0, "norm_finalize: groups %d does not divide C %d", groups, C);
+    int total = N * groups;
+    norm_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, N, C, (float)S, groups, gamma, beta, eps,
+                                                                                  scale_shift, mean_rstd);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_norm_bwd_finalize(const float* dsums, const float* mean_rstd, const float* gamma, int N, int C, int64_t S,
+                             int groups, float* coef, float* dgamma, float* dbeta, void* stream) {
+    B2_CHECK_ARG(dsums && mean_rstd && coef && N > 0 && C > 0 && S > 0, "norm_bwd_finalize: bad arguments");
+    B2_CHECK_ARG(groups > 0 && groups <= C && C % groups == 0, "norm_bwd_finalize: groups %d does not divide C %d", groups, C);
+    int total = N * groups;
+    norm_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dsums, mean_rstd, gamma, N, C, (float)S,
+                                                                                      groups, coef, dgamma, dbeta);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_affine_apply(const void* x, int64_t x_ld, const float* scale_shift, void* y, int64_t y_ld, int dtype, int N,
+                        int64_t S, int C, void* stream) {
+    B2_CHECK_ARG(x && y && scale_shift && N > 0 && C > 0 && S > 0 && x_ld >= C && y_ld >= C, "affine_apply: bad arguments");
+    B2_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = FullVec<T>::value;
+        if (can_vec<T>(C, {x_ld, y_ld}, {x, y})) {
+            int64_t total = (int64_t)N * S * (C / V);
+            affine_apply_kernel<T, V><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, scale_shift, (T*)y, y_ld, S, C, total);
+        } else {
+            int64_t total = (int64_t)N * S * C;
+            affine_apply_kernel<T, 1><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, scale_shift, (T*)y, y_ld, S, C, total);
+        }
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_norm_bwd_apply(const void* g, int64_t g_ld, const void* x, int64_t x_ld, const float* coef, const void* add,
+                          int64_t add_ld, void* out, int64_t out_ld, int dtype, int N, int64_t S, int C, int relu_mask,
+                          void* stream) {
+    B2_CHECK_ARG(g && out && N > 0 && C > 0 && S > 0 && g_ld >= C && out_ld >= C, "norm_bwd_apply: bad arguments");
+    B2_CHECK_ARG(x || (!coef && !relu_mask), "norm_bwd_apply: x is required with coef or relu_mask");
+    B2_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = FullVec<T>::value;
+        if (can_vec<T>(C, {g_ld, x ? x_ld : (int64_t)V, add ? add_ld : (int64_t)V, out_ld}, {g, x, add, out})) {
+            int64_t total = (int64_t)N * S * (C / V);
+            norm_bwd_apply_kernel<T, V><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                (const T*)g, g_ld, (const T*)x, x_ld, coef, (const T*)add, add_ld, (T*)out, out_ld, S, C, relu_mask, total);
+        } else {
+            int64_t total = (int64_t)N * S * C;
+            norm_bwd_apply_kernel<T, 1><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                (const T*)g, g_ld, (const T*)x, x_ld, coef, (const T*)add, add_ld, (T*)out, out_ld, S, C, relu_mask, total);
+        }
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_maxpool3d_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int dtype, int N, int D, int H, int W, int C,
+                         int fd, int fh, int fw, float* sums, void* stream) {
+    B2_CHECK_ARG(x && y && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "maxpool3d_fwd: bad arguments");
+    B2_CHECK_ARG(D % fd == 0 && H % fh == 0 && W % fw == 0, "maxpool3d_fwd: (%d,%d,%d) not divisible by (%d,%d,%d)", D, H, W, fd, fh, fw);
+    int64_t So = (int64_t)(D / fd) * (H / fh) * (W / fw);
+    B2_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = FullVec<T>::value;
+        if (can_vec<T>(C, {x_ld, y_ld}, {x, y})) {
+            Launch2D l = make_launch(C / V, So, N);
+            maxpool_fwd_kernel<T, V><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);
+        } else {
+            Launch2D l = make_launch(C, So, N);
+            maxpool_fwd_kernel<T, 1><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);
+        }
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp_ld, const void* add, int64_t add_ld,
+                         void* out, int64_t out_ld, int dtype, int N, int D, int H, int W, int C, int fd, int fh, int fw,
+                         int relu_mask, void* stream) {
+    B2_CHECK_ARG(x && dp && out && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "maxpool3d_bwd: bad arguments");
+    B2_CHECK_ARG(D % fd == 0 && H % fh == 0 && W % fw == 0, "maxpool3d_bwd: dims not divisible by factors");
+    int64_t So = (int64_t)(D / fd) * (H / fh) * (W / fw);
+    B2_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = FullVec<T>::value;
+        if (can_vec<T>(C, {x_ld, dp_ld, add ? add_ld : (int64_t)V, out_ld}, {x, dp, add, out})) {
+            int64_t total = (int64_t)N * So * (C / V);
+            maxpool_bwd_kernel<T, V><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, (T*)out, out_ld, D, H, W, C, fd, fh, fw, relu_mask, total);
+        } else {
+            int64_t total = (int64_t)N * So * C;
+            maxpool_bwd_kernel<T, 1><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, (T*)out, out_ld, D, H, W, C, fd, fh, fw, relu_mask, total);
+        }
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_upsample_trilinear_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int dtype, int N, int D, int H, int W,
+                                  int C, int fd, int fh, int fw, float* sums, void* stream) {
+    B2_CHECK_ARG(x && y && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "upsample_fwd: bad arguments");
+    int64_t So = (int64_t)D * fd * H * fh * W * fw;
+    B2_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = FullVec<T>::value;
+        if (can_vec<T>(C, {x_ld, y_ld}, {x, y})) {
+            Launch2D l = make_launch(C / V, So, N);
+            upsample_fwd_kernel<T, V><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);
+        } else {
+            Launch2D l = make_launch(C, So, N);
+            upsample_fwd_kernel<T, 1><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);
+        }
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int dtype, int N, int D, int H,
+                                  int W, int C, int fd, int fh, int fw, void* stream) {
+    B2_CHECK_ARG(dy && dx && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "upsample_bwd: bad arguments");
+    int64_t Si = (int64_t)D * H * W;
+    B2_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = FullVec<T>::value;
+        if (can_vec<T>(C, {dy_ld, dx_ld}, {dy, dx})) {
+            int64_t total = (int64_t)N * Si * (C / V);
+            upsample_bwd_kernel<T, V><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, fd, fh, fw, total);
+        } else {
+            int64_t total = (int64_t)N * Si * C;
+            upsample_bwd_kernel<T, 1><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, fd, fh, fw, total);
+        }
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+// Network head: out_conv (1x1x1 nn.Conv3d, unet.py:638,202-203) + final activation (unet.py:162-172,204-205),
+// fused with the NDHWC -> NCDHW layout change, forward and backward.  HBM-bound (AI ~ 2-9 FLOP/B):
+// one pass over x, one coalesced write of the fp32 NCDHW prediction.
+#include "common.cuh"
+
+namespace b200em {
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+    if (act == B200EM_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    if (act == B200EM_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == B200EM_ACT_TANH) return tanhf(v);
+    return v;
+}
+// derivative expressed through the OUTPUT of the activation (what the forward keeps)
+__device__ __forceinline__ float act_bwd(float out, int act) {
+    if (act == B200EM_ACT_SIGMOID) return out * (1.f - out);
+    if (act == B200EM_ACT_RELU) return out > 0.f ? 1.f : 0.f;
+    if (act == B200EM_ACT_TANH) return 1.f - out * out;
+    return 1.f;
+}
+
+constexpr int HEAD_COB = 8;  // output channels per register pass
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ w, const float* __restrict__ bias,
+                float* __restrict__ out, int64_t S, int Cin, int Cout, int act, int64_t total) {
+    for (int64_t vox = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; vox < total; vox += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = vox / S, s = vox % S;
+        const T* xp = x + vox * x_ld;
+        for (int co0 = 0; co0 < Cout; co0 += HEAD_COB) {
+            float acc[HEAD_COB];
+#pragma unroll
+            for (int j = 0; j < HEAD_COB; ++j) acc[j] = (bias && co0 + j < Cout) ? __ldg(bias + co0 + j) : 0.f;
+            for (int c = 0; c < Cin; c += VEC) {
+                float xv[VEC];
+                Vec<T, VEC>::load(xp + c, xv);
+#pragma unroll
+                for (int j = 0; j < HEAD_COB; ++j) {
+                    if (co0 + j < Cout) {
+                        const float* wr = w + (size_t)(co0 + j) * Cin + c;
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) acc[j] = fmaf(__ldg(wr + k), xv[k], acc[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < HEAD_COB; ++j)
+                if (co0 + j < Cout) out[((size_t)n * Cout + co0 + j) * S + s] = act_fwd(acc[j], act);
+        }
+    }
+}
+
+constexpr int HB_MAXCO = 32;   // output channels handled per call
+constexpr int HB_TILE = 256;   // voxels per tile (= threads)
+
+// grad_out/out: (N, Cout_total, S) fp32; this call handles channels [co_begin, co_begin+Cout).
+template <typename T, int VEC, int MAXP>
+__global__ void __launch_bounds__(HB_TILE)
+head_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, const T* __restrict__ x, int64_t x_ld,
+                const float* __restrict__ w, T* __restrict__ dx, int64_t dx_ld, float* __restrict__ dw,
+                float* __restrict__ db, int64_t S, int Cin, int Cout_total, int co_begin, int Cout, int act,
+                int accumulate, int relu_mask, int64_t total) {
+    __shared__ float dzs[HB_MAXCO][HB_TILE];
+    const int tid = threadIdx.x;
+    float accp[MAXP];
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) accp[i] = 0.f;
+    float accb_slots[HB_MAXCO / 8];  // warp w accumulates db for co = w, w+8, ...
+#pragma unroll
+    for (int i = 0; i < HB_MAXCO / 8; ++i) accb_slots[i] = 0.f;
+    const int npairs = Cout * Cin;
+    const int64_t ntiles = (total + HB_TILE - 1) / HB_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t vox = tile * HB_TILE + tid;
+        const bool live = vox < total;
+        const int64_t n = live ? vox / S : 0, s = live ? vox % S : 0;
+        float dz[HB_MAXCO];
+#pragma unroll
+        for (int j = 0; j < HB_MAXCO; ++j) {
+            float v = 0.f;
+            if (live && j < Cout) {
+                size_t o = ((size_t)n * Cout_total + co_begin + j) * S + s;
+                v = grad_out[o] * act_bwd(out[o], act);
+            }
+            dz[j] = v;
+            dzs[j][tid] = v;
+        }
+        // dx = W^T dz
+        if (live && dx) {
+            T* dxp = dx + vox * dx_ld;
+            for (int c = 0; c < Cin; c += VEC) {
+                float r[VEC], xv[VEC];
+                if (relu_mask) Vec<T, VEC>::load(x + vox * x_ld + c, xv);
+                if (accumulate) Vec<T, VEC>::load(dxp + c, r);
+                else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) r[k] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < HB_MAXCO; ++j) {
+                    if (j < Cout) {
+                        const float* wr = w + (size_t)(co_begin + j) * Cin + c;
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) r[k] = fmaf(__ldg(wr + k), dz[j], r[k]);
+                    }
+                }
+                if (relu_mask) {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k)
+                        if (!(xv[k] > 0.f)) r[k] = 0.f;
+                }
+                Vec<T, VEC>::store(dxp + c, r);
+            }
+        }
+        __syncthreads();
+        // dw[co][ci] partial over this tile: thread p handles pairs p, p+256, ...
+        const int64_t v0 = tile * HB_TILE;
+        const int nv = (int)((total - v0) < HB_TILE ? (total - v0) : HB_TILE);
+#pragma unroll
+        for (int i = 0; i < MAXP; ++i) {
+            const int p = tid + i * HB_TILE;
+            if (p < npairs) {
+                const int co = p / Cin, ci = p % Cin;
+                const T* xc = x + v0 * x_ld + ci;
+                float a = 0.f;
+                for (int v = 0; v < nv; ++v) a = fmaf(dzs[co][v], to_f<T>(xc[(size_t)v * x_ld]), a);
+                accp[i] += a;
+            }
+        }
+        // db: warp wi sums rows co = wi + 8*k
+        {
+            const int wi = tid >> 5, lane = tid & 31;
+#pragma unroll
+            for (int k = 0; k < HB_MAXCO / 8; ++k) {
+                const int co = wi + 8 * k;
+                if (co < Cout) {
+                    float a = 0.f;
+                    for (int v = lane; v < HB_TILE; v += 32) a += dzs[co][v];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    accb_slots[k] += a;
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        const int p = tid + i * HB_TILE;
+        if (p < npairs) atomicAdd(dw + (size_t)(co_begin + p / Cin) * Cin + p % Cin, accp[i]);
+    }
+    if (db && (tid & 31) == 0) {
+        const int wi = tid >> 5;
+#pragma unroll
+        for (int k = 0; k < HB_MAXCO / 8; ++k) {
+            const int co = wi + 8 * k;
+            if (co < Cout) atomicAdd(db + co_begin + co, accb_slots[k]);
+        }
+    }
+}
+
+}  // namespace b200em
+
+using namespace b200em;
+
+template <typename T>
+static void launch_head_bwd(unsigned blocks, cudaStream_t st, const float* grad_out, const float* out, const void* x,
+                            int64_t x_ld, const float* w, void* dx, int64_t dx_ld, float* dw, float* db, int64_t S, int Cin,
+                            int Cout, int co0, int cob, int act, int relu_mask, int64_t total) {
+    constexpr int V = FullVec<T>::value;
+    const bool vec = Cin % V == 0 && x_ld % V == 0 && aligned16(x) && (!dx || (dx_ld % V == 0 && aligned16(dx)));
+    const int maxp = (cob * Cin + HB_TILE - 1) / HB_TILE;
+    const int acc = co0 > 0 ? 1 : 0;
+#define B2_HEAD_BWD(VV, MP)                                                                                          \
+    head_bwd_kernel<T, VV, MP><<<blocks, HB_TILE, 0, st>>>(grad_out, out, (const T*)x, x_ld, w, (T*)dx, dx_ld, dw, db, S, \
+                                                           Cin, Cout, co0, cob, act, acc, relu_mask, total)
+    if (vec) {
+        if (maxp <= 4) B2_HEAD_BWD(V, 4);
+        else if (maxp <= 16) B2_HEAD_BWD(V, 16);
+        else B2_HEAD_BWD(V, 64);
+    } else {
+        if (maxp <= 4) B2_HEAD_BWD(1, 4);
+        else if (maxp <= 16) B2_HEAD_BWD(1, 16);
+        else B2_HEAD_BWD(1, 64);
+    }
+#undef B2_HEAD_BWD
+}
+
+
+extern "C" {
+
+int b200em_head_fwd(const void* x, int64_t x_ld, int dtype, const float* w, const float* bias, float* out, int N,
+                    int64_t S, int Cin, int Cout, int act, void* stream) {
+    B2_CHECK_ARG(x && w && out && N > 0 && S > 0 && Cin > 0 && Cout > 0 && x_ld >= Cin, "head_fwd: bad arguments");
+    B2_CHECK_ARG(act >= 0 && act <= 3, "head_fwd: unknown activation code %d", act);
+    int64_t total = (int64_t)N * S;
+    int64_t blocks = (total + 255) / 256;
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    B2_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = FullVec<T>::value;
+        if (Cin % V == 0 && x_ld % V == 0 && aligned16(x))
+            head_fwd_kernel<T, V><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, w, bias, out, S, Cin, Cout, act, total);
+        else
+            head_fwd_kernel<T, 1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, w, bias, out, S, Cin, Cout, act, total);
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_head_bwd(const float* grad_out, const float* out, const void* x, int64_t x_ld, int dtype, const float* w,
+                    void* dx, int64_t dx_ld, float* dw, float* db, int N, int64_t S, int Cin, int Cout, int act,
+                    int relu_mask, void* stream) {
+    B2_CHECK_ARG(grad_out && out && x && w && dw && N > 0 && S > 0 && Cin > 0 && Cout > 0 && x_ld >= Cin, "head_bwd: bad arguments");
+    B2_CHECK_ARG(!dx || dx_ld >= Cin, "head_bwd: dx pitch smaller than Cin");
+    B2_CHECK_ARG(act >= 0 && act <= 3, "head_bwd: unknown activation code %d", act);
+    B2_CHECK_ARG(Cin <= 512, "head_bwd: Cin %d > 512 not supported", Cin);
+    int64_t total = (int64_t)N * S;
+    int64_t ntiles = (total + HB_TILE - 1) / HB_TILE;
+    int64_t blocks = (int64_t)sm_count() * 4;
+    if (blocks > ntiles) blocks = ntiles;
+    for (int co0 = 0; co0 < Cout; co0 += HB_MAXCO) {
+        int cob = Cout - co0 < HB_MAXCO ? Cout - co0 : HB_MAXCO;
+        B2_DISPATCH_DTYPE(dtype, T, {
+            launch_head_bwd<T>((unsigned)blocks, (cudaStream_t)stream, grad_out, out, x, x_ld, w, dx, dx_ld, dw, db, S, Cin, Cout,
+                               co0, cob, act, relu_mask, total);
+        })
+        B2_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // extern "C"

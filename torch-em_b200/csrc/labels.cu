@@ -1,0 +1,280 @@
+// Instance labels -> affinity / boundary training targets, and the fused "target + masked Dice" reductions.
+//
+// Reference restated: AffinityTransform.__call__ (transform/label.py:290-327; arithmetic pinned by the brute force in
+// test/transform/test_label_transforms.py:5-55) and BoundaryTransform (label.py:100-129, find_boundaries "thick").
+// In the reference these run on CPU inside the dataloader and the 2C-channel fp32 target is shipped host->device
+// every step (805 MB at cfg3); here they are integer stencils over the int64 label volume already on the GPU, and
+// the fused variants never write the target tensor at all (HBM traffic: labels + prediction only).
+//
+//   q = p + offset_c;  oob = q outside the volume
+//   no ignore label :  disaff = oob ? 1 : [lab[p] != lab[q]];                         mask = !oob
+//   ignore label L  :  k = [lab[p]==L] + [lab[q]==L]
+//                      oob or k==2 or (k==1 and !include_ignore_transitions) -> disaff = 1, mask = 0
+//                      k==1 and include_ignore_transitions                   -> disaff = 1, mask = 1
+//                      else                                                   -> disaff = [lab[p]!=lab[q]], mask = 1
+#include "common.cuh"
+
+namespace b200em {
+
+constexpr int MAX_OFFSETS = 64;
+struct OffsetTable {
+    int n;
+    int d[MAX_OFFSETS], h[MAX_OFFSETS], w[MAX_OFFSETS];
+};
+
+struct AffRule {
+    int has_ignore;
+    long long ignore_label;
+    int include_ignore_transitions;
+};
+
+__device__ __forceinline__ void aff_eval(const long long* __restrict__ lab, long long lp, int d, int h, int w, int D, int H,
+                                         int W, int od, int oh, int ow, const AffRule& r, float& disaff, float& msk) {
+    const int qd = d + od, qh = h + oh, qw = w + ow;
+    if (qd < 0 || qd >= D || qh < 0 || qh >= H || qw < 0 || qw >= W) { disaff = 1.f; msk = 0.f; return; }
+    const long long lq = lab[((size_t)qd * H + qh) * W + qw];
+    if (r.has_ignore) {
+        const int k = (lp == r.ignore_label) + (lq == r.ignore_label);
+        if (k == 2 || (k == 1 && !r.include_ignore_transitions)) { disaff = 1.f; msk = 0.f; return; }
+        if (k == 1) { disaff = 1.f; msk = 1.f; return; }
+    }
+    disaff = lp != lq ? 1.f : 0.f;
+    msk = 1.f;
+}
+
+// out (N, channels, D,H,W): [fg?][n disaff][fg-mask?][n masks]
+__global__ void __launch_bounds__(256)
+affinity_targets_kernel(const long long* __restrict__ labels, float* __restrict__ out, int D, int H, int W, OffsetTable offs,
+                        AffRule rule, int add_binary_target, int add_mask) {
+    const int n = blockIdx.y;
+    const int64_t S = (int64_t)D * H * W;
+    const int noff = offs.n;
+    const int channels = (noff + (add_binary_target ? 1 : 0)) * (add_mask ? 2 : 1);
+    const long long* lab = labels + (size_t)n * S;
+    float* o = out + (size_t)n * channels * S;
+    const int c_aff = add_binary_target ? 1 : 0;
+    const int c_mask = c_aff + noff + (add_binary_target ? 1 : 0);
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+        const long long lp = lab[s];
+        if (add_binary_target) {
+            o[s] = lp != 0 ? 1.f : 0.f;
+            if (add_mask) o[(size_t)(c_aff + noff) * S + s] = (rule.has_ignore && lp == rule.ignore_label) ? 0.f : 1.f;
+        }
+        for (int c = 0; c < noff; ++c) {
+            float a, m;
+            aff_eval(lab, lp, d, h, w, D, H, W, offs.d[c], offs.h[c], offs.w[c], rule, a, m);
+            o[(size_t)(c_aff + c) * S + s] = a;
+            if (add_mask) o[(size_t)(c_mask + c) * S + s] = m;
+        }
+    }
+}
+
+// out (N, 1|2, D,H,W): [foreground?][boundary]; boundary = some in-bounds 6-neighbour carries a different label
+__global__ void __launch_bounds__(256)
+boundary_targets_kernel(const long long* __restrict__ labels, float* __restrict__ out, int D, int H, int W,
+                        int add_binary_target) {
+    const int n = blockIdx.y;
+    const int64_t S = (int64_t)D * H * W;
+    const long long* lab = labels + (size_t)n * S;
+    float* o = out + (size_t)n * (add_binary_target ? 2 : 1) * S;
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+        const long long lp = lab[s];
+        bool b = false;
+        if (w > 0) b |= lab[s - 1] != lp;
+        if (w < W - 1) b |= lab[s + 1] != lp;
+        if (h > 0) b |= lab[s - W] != lp;
+        if (h < H - 1) b |= lab[s + W] != lp;
+        if (d > 0) b |= lab[s - (int64_t)W * H] != lp;
+        if (d < D - 1) b |= lab[s + (int64_t)W * H] != lp;
+        if (add_binary_target) {
+            o[s] = lp != 0 ? 1.f : 0.f;
+            o[S + s] = b ? 1.f : 0.f;
+        } else {
+            o[s] = b ? 1.f : 0.f;
+        }
+    }
+}
+
+constexpr int AD_PER_THREAD = 8;                       // voxels per thread
+constexpr int AD_CHUNK = 256 * AD_PER_THREAD;          // voxels per block
+
+// Fused: Dice sums of pred (N, n_off, S) against AffinityTransform(offsets, add_mask=True) targets, target and mask
+// computed on the fly.  grid = (chunks, N).  sums[c][3] += (sum pm*tm, sum pm^2, sum tm^2).
+template <typename TP>
+__global__ void __launch_bounds__(256)
+affinity_dice_sums_kernel(const TP* __restrict__ pred, const long long* __restrict__ labels, int D, int H, int W,
+                          OffsetTable offs, AffRule rule, float* __restrict__ sums) {
+    __shared__ float sh[3][8];
+    const int n = blockIdx.y;
+    const int64_t S = (int64_t)D * H * W;
+    const long long* lab = labels + (size_t)n * S;
+    const int noff = offs.n;
+    long long lp[AD_PER_THREAD];
+    int pd[AD_PER_THREAD], ph[AD_PER_THREAD], pw[AD_PER_THREAD];
+    const int64_t base = (int64_t)blockIdx.x * AD_CHUNK + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < AD_PER_THREAD; ++k) {
+        const int64_t s = base + (int64_t)k * 256;
+        if (s < S) {
+            lp[k] = lab[s];
+            pw[k] = (int)(s % W); ph[k] = (int)((s / W) % H); pd[k] = (int)(s / ((int64_t)W * H));
+        } else {
+            lp[k] = 0; pw[k] = ph[k] = pd[k] = 0;
+        }
+    }
+    for (int c = 0; c < noff; ++c) {
+        const TP* p = pred + ((size_t)n * noff + c) * S;
+        float a_pt = 0.f, a_pp = 0.f, a_tt = 0.f;
+#pragma unroll
+        for (int k = 0; k < AD_PER_THREAD; ++k) {
+            const int64_t s = base + (int64_t)k * 256;
+            if (s < S) {
+                float t, m;
+                aff_eval(lab, lp[k], pd[k], ph[k], pw[k], D, H, W, offs.d[c], offs.h[c], offs.w[c], rule, t, m);
+                const float pm = to_f<TP>(p[s]) * m, tm = t * m;
+                a_pt = fmaf(pm, tm, a_pt);
+                a_pp = fmaf(pm, pm, a_pp);
+                a_tt = fmaf(tm, tm, a_tt);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a_pt += __shfl_xor_sync(0xffffffffu, a_pt, o);
+            a_pp += __shfl_xor_sync(0xffffffffu, a_pp, o);
+            a_tt += __shfl_xor_sync(0xffffffffu, a_tt, o);
+        }
+        const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        __syncthreads();
+        if (lane == 0) { sh[0][wi] = a_pt; sh[1][wi] = a_pp; sh[2][wi] = a_tt; }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            float r = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r += sh[threadIdx.x][j];
+            atomicAdd(sums + c * 3 + threadIdx.x, r);
+        }
+    }
+}
+
+template <typename TP, typename TG>
+__global__ void __launch_bounds__(256)
+affinity_dice_bwd_kernel(const TP* __restrict__ pred, const long long* __restrict__ labels, int D, int H, int W,
+                         OffsetTable offs, AffRule rule, const float* __restrict__ coef, const float* __restrict__ gout,
+                         TG* __restrict__ grad) {
+    const int n = blockIdx.y;
+    const int64_t S = (int64_t)D * H * W;
+    const long long* lab = labels + (size_t)n * S;
+    const int noff = offs.n;
+    const float go = gout[0];
+    long long lp[AD_PER_THREAD];
+    int pd[AD_PER_THREAD], ph[AD_PER_THREAD], pw[AD_PER_THREAD];
+    const int64_t base = (int64_t)blockIdx.x * AD_CHUNK + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < AD_PER_THREAD; ++k) {
+        const int64_t s = base + (int64_t)k * 256;
+        if (s < S) {
+            lp[k] = lab[s];
+            pw[k] = (int)(s % W); ph[k] = (int)((s / W) % H); pd[k] = (int)(s / ((int64_t)W * H));
+        } else {
+            lp[k] = 0; pw[k] = ph[k] = pd[k] = 0;
+        }
+    }
+    for (int c = 0; c < noff; ++c) {
+        const float A = coef[2 * c] * go, B = coef[2 * c + 1] * go;
+        const TP* p = pred + ((size_t)n * noff + c) * S;
+        TG* g = grad + ((size_t)n * noff + c) * S;
+#pragma unroll
+        for (int k = 0; k < AD_PER_THREAD; ++k) {
+            const int64_t s = base + (int64_t)k * 256;
+            if (s < S) {
+                float t, m;
+                aff_eval(lab, lp[k], pd[k], ph[k], pw[k], D, H, W, offs.d[c], offs.h[c], offs.w[c], rule, t, m);
+                g[s] = from_f<TG>((A * t + B * to_f<TP>(p[s])) * m * m);
+            }
+        }
+    }
+}
+
+static int fill_offsets(OffsetTable& t, const int* offsets, int n_off) {
+    if (!offsets || n_off <= 0 || n_off > MAX_OFFSETS) {
+        set_error("affinity: need 1..%d offsets, got %d", MAX_OFFSETS, n_off);
+        return 1;
+    }
+    t.n = n_off;
+    for (int i = 0; i < n_off; ++i) { t.d[i] = offsets[3 * i]; t.h[i] = offsets[3 * i + 1]; t.w[i] = offsets[3 * i + 2]; }
+    return 0;
+}
+
+static inline unsigned flat_blocks(int64_t S, int N) {
+    int64_t b = (S + 255) / 256;
+    int64_t cap = (int64_t)sm_count() * 16 / (N > 0 ? N : 1) + 1;
+    if (b > cap) b = cap;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+}  // namespace b200em
+
+using namespace b200em;
+
+extern "C" {
+
+int b200em_affinity_targets(const int64_t* labels, float* out, int N, int D, int H, int W, const int* offsets, int n_off,
+                            int has_ignore, int64_t ignore_label, int add_binary_target, int add_mask,
+                            int include_ignore_transitions, void* stream) {
+    B2_CHECK_ARG(labels && out && N > 0 && D > 0 && H > 0 && W > 0, "affinity_targets: bad arguments");
+    OffsetTable t;
+    if (fill_offsets(t, offsets, n_off)) return 1;
+    AffRule r{has_ignore, (long long)ignore_label, include_ignore_transitions};
+    dim3 grid(flat_blocks((int64_t)D * H * W, N), (unsigned)N);
+    affinity_targets_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, out, D, H, W, t, r, add_binary_target, add_mask);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_boundary_targets(const int64_t* labels, float* out, int N, int D, int H, int W, int add_binary_target,
+                            void* stream) {
+    B2_CHECK_ARG(labels && out && N > 0 && D > 0 && H > 0 && W > 0, "boundary_targets: bad arguments");
+    dim3 grid(flat_blocks((int64_t)D * H * W, N), (unsigned)N);
+    boundary_targets_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, out, D, H, W, add_binary_target);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_affinity_dice_sums(const void* pred, int pred_dtype, const int64_t* labels, int N, int D, int H, int W,
+                              const int* offsets, int n_off, int has_ignore, int64_t ignore_label,
+                              int include_ignore_transitions, float* sums, void* stream) {
+    B2_CHECK_ARG(pred && labels && sums && N > 0 && D > 0 && H > 0 && W > 0, "affinity_dice_sums: bad arguments");
+    OffsetTable t;
+    if (fill_offsets(t, offsets, n_off)) return 1;
+    AffRule r{has_ignore, (long long)ignore_label, include_ignore_transitions};
+    int64_t S = (int64_t)D * H * W;
+    dim3 grid((unsigned)((S + AD_CHUNK - 1) / AD_CHUNK), (unsigned)N);
+    B2_DISPATCH_DTYPE(pred_dtype, TP, {
+        affinity_dice_sums_kernel<TP><<<grid, 256, 0, (cudaStream_t)stream>>>((const TP*)pred, (const long long*)labels, D, H, W, t, r, sums);
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_affinity_dice_bwd(const void* pred, int pred_dtype, const int64_t* labels, int N, int D, int H, int W,
+                             const int* offsets, int n_off, int has_ignore, int64_t ignore_label,
+                             int include_ignore_transitions, const float* coef, const float* gout, void* grad_pred,
+                             int grad_dtype, void* stream) {
+    B2_CHECK_ARG(pred && labels && coef && gout && grad_pred && N > 0 && D > 0 && H > 0 && W > 0, "affinity_dice_bwd: bad arguments");
+    OffsetTable t;
+    if (fill_offsets(t, offsets, n_off)) return 1;
+    AffRule r{has_ignore, (long long)ignore_label, include_ignore_transitions};
+    int64_t S = (int64_t)D * H * W;
+    dim3 grid((unsigned)((S + AD_CHUNK - 1) / AD_CHUNK), (unsigned)N);
+    B2_DISPATCH_DTYPE(pred_dtype, TP, {
+        B2_DISPATCH_DTYPE(grad_dtype, TG, {
+            affinity_dice_bwd_kernel<TP, TG><<<grid, 256, 0, (cudaStream_t)stream>>>((const TP*)pred, (const long long*)labels, D, H, W, t, r, coef, gout, (TG*)grad_pred);
+        })
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+"""Schedule of the fused 3D U-Net train step: which kernel runs on which buffer, forward and backward.
+
+This is the host-side mirror of ``UNetBase._apply_default`` / ``Encoder.forward`` / ``Decoder.forward`` /
+``ConvBlock.forward`` / ``Upsampler.forward`` (unet.py:194-209, 311-321, 375-388, 429-441, 455-458) and of the
+autograd graph PyTorch would build for them -- restated as an explicit list of calls into the C ABI
+(``include/b200em.h``).  PyTorch supplies device memory (the caching allocator), the current stream and the
+``autograd.Function`` hook that calls ``forward_pass`` / ``backward_pass``; no ``torch.nn`` compute op runs here.
+
+Data layout in HBM
+  * activations: channels-last ``(N, D, H, W, C)`` ("NDHWC"), bf16 under bf16 autocast, fp32 otherwise
+  * every decoder level owns ONE concat buffer ``(N, D, H, W, 2C)``: the encoder's second conv writes its output (the
+    skip connection) straight into channels ``[C, 2C)``, the up-sampler writes into ``[0, C)``;
+    ``torch.cat`` (unet.py:372-373) never runs
+  * per-(n, c) statistics ``(sum, sum of squares)`` fp32 ``[N, C, 2]`` are produced by the epilogue of whichever
+    kernel wrote the tensor and turned into ``scale/shift`` by a finalize kernel; the normalisation itself is applied
+    inside the consuming convolution's operand load (padding stays zero in normalised space)
+  * the 1x1x1 sampler conv runs BEFORE the trilinear interpolation (they commute exactly: both linear, interpolation
+    weights sum to one), i.e. on 8x fewer voxels than the reference order (unet.py:455-458)
+
+Reference details restated here: pre-norm block order (unet.py:429-438), GroupNorm(min(32, C), C)
+(unet.py:402), MaxPool3d first-max gradient routing, ReLU'(0) = 0.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+EPS = 1e-5  # nn.InstanceNorm3d / nn.GroupNorm default eps (unet.py:397,402)
+
+
+@dataclass
+class ConvSpec:
+    key: str                      # state-dict prefix, e.g. "encoder.blocks.0.block.1"
+    cin: int
+    cout: int
+    kernel: Tuple[int, int, int]
+
+
+@dataclass
+class BlockSpec:
+    prefix: str                   # e.g. "encoder.blocks.0"
+    conv1: ConvSpec
+    conv2: ConvSpec
+    norm1_key: Optional[str]      # GroupNorm affine parameter prefixes (None unless norm == "GroupNorm")
+    norm2_key: Optional[str]
+
+
+@dataclass
+class Plan:
+    in_channels: int
+    out_channels: int
+    scale_factors: List[List[int]]
+    norm: Optional[str]
+    final_activation: Optional[str]
+    enc: List[BlockSpec] = field(default_factory=list)
+    base: BlockSpec = None
+    dec: List[BlockSpec] = field(default_factory=list)
+    samplers: List[ConvSpec] = field(default_factory=list)
+    out_conv: ConvSpec = None
+
+    @property
+    def depth(self):
+        return len(self.scale_factors)
+
+
+def _as_factor(f):
+    return [f, f, f] if isinstance(f, int) else list(f)
+
+
+def level_kernels(scale_factors, anisotropic_kernel):
+    """Per-level kernel for one encoder / decoder, given ITS scale-factor order (unet.py:256-272, 291-294, 339-342).
+
+    The reference shares one kwargs dict across all levels of an Encoder / Decoder and ``_update_conv_kwargs``
+    mutates it in place, so the first anisotropic factor met fixes the kernel of every level (behaviour is the spec;
+    pinned by tests/golden/aniso_f4_anisokernel.npz)."""
+    k = (3, 3, 3)
+    if anisotropic_kernel:
+        for sf in scale_factors:
+            f = _as_factor(sf)
+            if f.count(f[0]) != len(f):
+                k = tuple(1 if s == 1 else 3 for s in f)
+                break
+    return [k] * len(scale_factors)
+
+
+def make_plan(in_channels, out_channels, scale_factors, initial_features=32, gain=2, norm="InstanceNorm",
+              final_activation=None, anisotropic_kernel=False) -> Plan:
+    sfs = [_as_factor(sf) for sf in scale_factors]
+    depth = len(sfs)
+    enc_f = [in_channels] + [initial_features * gain ** i for i in range(depth)]
+    dec_f = [initial_features * gain ** i for i in range(depth + 1)][::-1]
+    ci = (1, 4) if norm is not None else (0, 2)
+    gn = norm == "GroupNorm"
+
+    def block(prefix, cin, cout, k):
+        return BlockSpec(prefix,
+                         ConvSpec(f"{prefix}.block.{ci[0]}", cin, cout, k),
+                         ConvSpec(f"{prefix}.block.{ci[1]}", cout, cout, k),
+                         f"{prefix}.block.0" if gn else None, f"{prefix}.block.3" if gn else None)
+
+    plan = Plan(in_channels, out_channels, sfs, norm, final_activation)
+    ek = level_kernels(sfs, anisotropic_kernel)
+    plan.enc = [block(f"encoder.blocks.{l}", enc_f[l], enc_f[l + 1], ek[l]) for l in range(depth)]
+    plan.base = block("base", enc_f[-1], enc_f[-1] * gain, (3, 3, 3))
+    dk = level_kernels(sfs[::-1], anisotropic_kernel)
+    plan.dec = [block(f"decoder.blocks.{l}", dec_f[l], dec_f[l + 1], dk[l]) for l in range(depth)]
+    plan.samplers = [ConvSpec(f"decoder.samplers.{l}.conv", dec_f[l], dec_f[l + 1], (1, 1, 1)) for l in range(depth)]
+    if out_channels is not None:
+        plan.out_conv = ConvSpec("out_conv", dec_f[-1], out_channels, (1, 1, 1))
+    return plan
+
+
+def check_shape(spatial, scale_factors):
+    """unet.py:671-680: every spatial axis must be divisible by the product of its scale factors."""
+    factor = [1, 1, 1]
+    for sf in scale_factors:
+        for i in range(3):
+            factor[i] *= sf[i]
+    if len(spatial) != 3:
+        raise ValueError(f"Invalid shape for U-Net: dimensions don't agree {len(spatial)} != 3")
+    if any(sh % fac != 0 for sh, fac in zip(spatial, factor)):
+        raise ValueError(f"Invalid shape for U-Net: {tuple(spatial)} is not divisible by {factor}")
+
+
+def _groups(norm, c):
+    return c if norm == "InstanceNorm" else min(32, c)
+
+
+class _Ctx:
+    """Everything the backward pass needs from one forward pass."""
+
+    def __init__(self):
+        self.blocks = {}
+        self.misc = {}
+
+
+def _run_block(B, plan, P, spec: BlockSpec, x_in, sums_in, out, want_out_sums, ctx, packs):
+    N, D, H, W, _ = x_in.shape
+    S = D * H * W
+    dev = x_in.device
+    norm = plan.norm
+    rec = {"x_in": x_in}
+    ss1 = mr1 = ss2 = mr2 = None
+    c1, c2 = spec.conv1, spec.conv2
+    if norm is not None:
+        g1 = P[spec.norm1_key + ".weight"] if spec.norm1_key else None
+        b1 = P[spec.norm1_key + ".bias"] if spec.norm1_key else None
+        ss1, mr1 = B.norm_finalize(sums_in, S, _groups(norm, c1.cin), g1, b1, EPS)
+    y1 = torch.empty((N, D, H, W, c1.cout), dtype=x_in.dtype, device=dev)
+    sums1 = torch.zeros((N, c1.cout, 2), dtype=torch.float32, device=dev) if norm is not None else None
+    B.conv(x_in, ss1, packs[c1.key], P[c1.key + ".bias"], y1, sums1, c1.kernel, relu=True, dgrad=False)
+    if norm is not None:
+        g2 = P[spec.norm2_key + ".weight"] if spec.norm2_key else None
+        b2 = P[spec.norm2_key + ".bias"] if spec.norm2_key else None
+        ss2, mr2 = B.norm_finalize(sums1, S, _groups(norm, c2.cin), g2, b2, EPS)
+    sums2 = None
+    if want_out_sums and norm is not None:
+        sums2 = torch.zeros((N, c2.cout, 2), dtype=torch.float32, device=dev)
+    B.conv(y1, ss2, packs[c2.key], P[c2.key + ".bias"], out, sums2, c2.kernel, relu=True, dgrad=False)
+    rec.update(ss1=ss1, mr1=mr1, y1=y1, ss2=ss2, mr2=mr2, y2=out)
+    ctx.blocks[spec.prefix] = rec
+    return sums2
+
+
+def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act_dtype, packs):
+    """x: (N, Cin, D, H, W) fp32 NCDHW on the device.  Returns (prediction NCDHW fp32, ctx)."""
+    if x.dim() != 5:
+        raise ValueError(f"Invalid shape for U-Net: dimensions don't agree {x.dim() - 2} != 3")
+    N, Cin, D, H, W = x.shape
+    dev = x.device
+    depth = plan.depth
+    norm = plan.norm
+    ctx = _Ctx()
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+
+    a = torch.empty((N, D, H, W, Cin), dtype=act_dtype, device=dev)
+    B.to_ndhwc(x, a)
+    cur = a
+    cur_sums = None
+    if norm is not None:
+        cur_sums = torch.zeros((N, Cin, 2), dtype=torch.float32, device=dev)
+        B.channel_sums(a, cur_sums)
+    dims = (D, H, W)
+    cats, skip_sums, level_dims = [], [], []
+    for l in range(depth):
+        spec = plan.enc[l]
+        C = spec.conv2.cout
+        cat = torch.empty((N,) + dims + (2 * C,), dtype=act_dtype, device=dev)
+        skip = cat[..., C:]
+        s2 = _run_block(B, plan, P, spec, cur, cur_sums, skip, True, ctx, packs)
+        cats.append(cat)
+        skip_sums.append(s2)
+        level_dims.append(dims)
+        f = plan.scale_factors[l]
+        dims = tuple(d // ff for d, ff in zip(dims, f))
+        pooled = torch.empty((N,) + dims + (C,), dtype=act_dtype, device=dev)
+        psums = torch.zeros((N, C, 2), dtype=torch.float32, device=dev) if norm is not None else None
+        B.maxpool_fwd(skip, pooled, f, psums)
+        cur, cur_sums = pooled, psums
+    spec = plan.base
+    base_out = torch.empty((N,) + dims + (spec.conv2.cout,), dtype=act_dtype, device=dev)
+    _run_block(B, plan, P, spec, cur, cur_sums, base_out, False, ctx, packs)
+    cur = base_out
+    zlows = []
+    for i in range(depth):
+        lvl = depth - 1 - i
+        spec = plan.dec[i]
+        samp = plan.samplers[i]
+        C = samp.cout
+        f = plan.scale_factors[lvl]
+        z_low = torch.empty((N,) + dims + (C,), dtype=act_dtype, device=dev)
+        B.conv(cur, None, packs[samp.key], P[samp.key + ".bias"], z_low, None, samp.kernel, relu=False, dgrad=False)
+        dims = level_dims[lvl]
+        cat = cats[lvl]
+        up = cat[..., :C]
+        up_sums = torch.zeros((N, C, 2), dtype=torch.float32, device=dev) if norm is not None else None
+        B.upsample_fwd(z_low, up, f, up_sums)
+        zlows.append((cur, z_low.shape))
+        cat_sums = torch.cat([up_sums, skip_sums[lvl]], dim=1) if norm is not None else None
+        out = torch.empty((N,) + dims + (spec.conv2.cout,), dtype=act_dtype, device=dev)
+        _run_block(B, plan, P, spec, cat, cat_sums, out, False, ctx, packs)
+        cur = out
+    if plan.out_conv is None:
+        raise NotImplementedError("out_channels=None (feature output) is not on the accelerated path")
+    oc = plan.out_conv
+    pred = torch.empty((N, oc.cout, D, H, W), dtype=torch.float32, device=dev)
+    B.head_fwd(cur, P[oc.key + ".weight"], P[oc.key + ".bias"], pred, plan.final_activation)
+    ctx.misc.update(cats=cats, level_dims=level_dims, sampler_in=zlows, y_last=cur, pred=pred, act_dtype=act_dtype,
+                    first_input=a)
+    return pred, ctx
+
+
+def _bias_grad(B, dz):
+    N, _, _, _, C = dz.shape
+    s = torch.zeros((N, C, 2), dtype=torch.float32, device=dz.device)
+    B.channel_sums(dz, s)
+    return s[:, :, 0].sum(0)
+
+
+def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs):
+    """dz2 = gradient w.r.t. the PRE-ReLU output of conv2 (i.e. already multiplied by [y2 > 0]).
+    Returns the gradient w.r.t. the block input (before any mask of the producer), or None."""
+    norm = plan.norm
+    c1, c2 = spec.conv1, spec.conv2
+    x_in, y1 = rec["x_in"], rec["y1"]
+    N, D, H, W, _ = y1.shape
+    S = D * H * W
+    dev = y1.device
+    f32 = dict(dtype=torch.float32, device=dev)
+
+    def norm_back(g, x, mr, gamma_key, C, out, relu_mask):
+        if norm is None:
+            B.norm_bwd_apply(g, x, None, None, out, relu_mask)
+            return
+        dsums = torch.zeros((N, C, 2), **f32)
+        B.channel_dot_sums(g, x, dsums)
+        gamma = P[gamma_key + ".weight"] if gamma_key else None
+        dgamma = dbeta = None
+        if gamma_key:
+            dgamma = grads.setdefault(gamma_key + ".weight", torch.zeros(C, **f32))
+            dbeta = grads.setdefault(gamma_key + ".bias", torch.zeros(C, **f32))
+        coef = B.norm_bwd_finalize(dsums, mr, gamma, S, _groups(norm, C), dgamma, dbeta)
+        B.norm_bwd_apply(g, x, coef, None, out, relu_mask)
+
+    # conv2
+    grads[c2.key + ".bias"] = _bias_grad(B, dz2)
+    dw2 = torch.zeros((c2.cout, c2.cin) + c2.kernel, **f32)
+    B.wgrad(y1, rec["ss2"], dz2, dw2, c2.kernel)
+    grads[c2.key + ".weight"] = dw2
+    g2 = torch.empty_like(y1)
+    B.conv(dz2, None, packs[c2.key], None, g2, None, c2.kernel, relu=False, dgrad=True)
+    dz1 = torch.empty_like(y1)
+    norm_back(g2, y1, rec["mr2"], spec.norm2_key, c2.cin, dz1, relu_mask=1)
+    del g2
+    # conv1
+    grads[c1.key + ".bias"] = _bias_grad(B, dz1)
+    dw1 = torch.zeros((c1.cout, c1.cin) + c1.kernel, **f32)
+    B.wgrad(x_in, rec["ss1"], dz1, dw1, c1.kernel)
+    grads[c1.key + ".weight"] = dw1
+    if not need_dx:
+        return None
+    g1 = torch.empty(x_in.shape, dtype=x_in.dtype, device=dev)
+    B.conv(dz1, None, packs[c1.key], None, g1, None, c1.kernel, relu=False, dgrad=True)
+    if norm is None:
+        return g1
+    dx = torch.empty_like(g1)
+    norm_back(g1, x_in, rec["mr1"], spec.norm1_key, c1.cin, dx, relu_mask=0)
+    return dx
+
+
+def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pred: torch.Tensor, packs):
+    """Returns {state-dict key: fp32 gradient} for every parameter."""
+    m = ctx.misc
+    depth = plan.depth
+    grads: Dict[str, torch.Tensor] = {}
+    y_last, pred = m["y_last"], m["pred"]
+    dev = y_last.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    grad_pred = grad_pred.contiguous()
+    if grad_pred.dtype != torch.float32:
+        grad_pred = grad_pred.float()
+    oc = plan.out_conv
+    dw = torch.zeros((oc.cout, oc.cin, 1, 1, 1), **f32)
+    db = torch.zeros((oc.cout,), **f32)
+    dz = torch.empty_like(y_last)
+    B.head_bwd(grad_pred, pred, y_last, P[oc.key + ".weight"], dz, dw, db, plan.final_activation, relu_mask=1)
+    grads[oc.key + ".weight"], grads[oc.key + ".bias"] = dw, db
+
+    skip_grads = [None] * depth
+    for i in reversed(range(depth)):
+        lvl = depth - 1 - i
+        spec, samp = plan.dec[i], plan.samplers[i]
+        C = samp.cout
+        d_cat = _block_backward(B, plan, P, spec, ctx.blocks[spec.prefix], dz, True, grads, packs)
+        skip_grads[lvl] = d_cat[..., C:]
+        x_low, zshape = m["sampler_in"][i]
+        d_zlow = torch.empty(zshape, dtype=x_low.dtype, device=dev)
+        B.upsample_bwd(d_cat[..., :C], d_zlow, plan.scale_factors[lvl])
+        grads[samp.key + ".bias"] = _bias_grad(B, d_zlow)
+        dws = torch.zeros((samp.cout, samp.cin, 1, 1, 1), **f32)
+        B.wgrad(x_low, None, d_zlow, dws, samp.kernel)
+        grads[samp.key + ".weight"] = dws
+        g = torch.empty_like(x_low)
+        B.conv(d_zlow, None, packs[samp.key], None, g, None, samp.kernel, relu=False, dgrad=True)
+        # x_low is the post-ReLU output of the block below: apply its ReLU mask in place
+        B.norm_bwd_apply(g, x_low, None, None, g, 1)
+        dz = g
+    need_first_dx = plan.norm == "GroupNorm"      # the first norm's gamma/beta need the gradient w.r.t. its output
+    d_p = _block_backward(B, plan, P, plan.base, ctx.blocks["base"], dz, depth > 0 or need_first_dx, grads, packs)
+    for l in reversed(range(depth)):
+        spec = plan.enc[l]
+        rec = ctx.blocks[spec.prefix]
+        skip = rec["y2"]
+        dz = torch.empty(skip.shape, dtype=skip.dtype, device=dev)
+        B.maxpool_bwd(skip, d_p, skip_grads[l], dz, plan.scale_factors[l], 1)
+        d_p = _block_backward(B, plan, P, spec, rec, dz, l > 0 or need_first_dx, grads, packs)
+    return grads
