@@ -1,0 +1,270 @@
+"""Benchmark of the 3D U-Net train step (BASELINE.json metric: UNet3d train voxels/sec on (B,1,128,128,128)).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one full train step of BASELINE.json configs[1] on one synthetic batch per GPU:
+``UNet3d(1, 2, depth=4, initial_features=32, final_activation="Sigmoid")``, bf16 autocast, (4,1,128,128,128) patches,
+DiceLoss, zero_grad + forward + loss + backward (+ one gradient all-reduce for N > 1) + AdamW step.
+Weak scaling: the per-GPU batch is fixed.  ``value`` = voxels/s of the whole job with inputs resident in HBM;
+``e2e`` = the same with pinned-host inputs copied H2D and the loss read back D2H inside every timed step.
+``--impl reference`` times the reference's CPU arithmetic for this path (the oracle port: /root/reference does not
+exist on the GPU box and is pure Python over torch, so "the reference compiled here" does not apply) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL_KW = dict(in_channels=1, out_channels=2, depth=4, initial_features=32, final_activation="Sigmoid")
+BATCH, PATCH = 4, (128, 128, 128)
+METRIC = "UNet3d train voxels/sec on (B,1,128,128,128)"
+
+
+def synthetic_batch(batch, patch, seed):
+    """Per-sample standardised random volume (like transform/raw.py:40-65) and binary 2-channel targets."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand((batch, 1) + tuple(patch), generator=g)
+    x = (x - x.mean(dim=(1, 2, 3, 4), keepdim=True)) / (x.std(dim=(1, 2, 3, 4), keepdim=True) + 1e-7)
+    t = (torch.rand((batch, 2) + tuple(patch), generator=g) > 0.5).float()
+    return x, t
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nm, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        smax = max((float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_reference_steps(patch, steps, warmup, threads):
+    """The reference's arithmetic for this path on the host cores: oracle U-Net + Dice + AdamW, fp32."""
+    import torch
+    from oracle import dice as odice
+    from oracle import unet as ounet
+    torch.set_num_threads(threads)
+    sd = ounet.init_state_dict(1, 2, [2] * MODEL_KW["depth"], initial_features=MODEL_KW["initial_features"], seed=0)
+    params = [v.requires_grad_(True) for v in sd.values()]
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    x, t = synthetic_batch(1, patch, 0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        y = ounet.unet3d_forward(x, sd, [2] * MODEL_KW["depth"], final_activation="Sigmoid")
+        loss = odice.dice_loss(y, t)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    vox = patch[0] * patch[1] * patch[2]
+    return vox * len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    patch = (64, 64, 64)
+    vps, sec = cpu_reference_steps(patch, args.steps, args.warmup, threads)
+    sample = f"one (1,1,{patch[0]},{patch[1]},{patch[2]}) patch of the same model per step, fp32, torch CPU oracle"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": vps, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "UNet3d(1,2,depth=4,initial_features=32)+DiceLoss+AdamW train step, configs[1]", "sample": sample},
+        "cpu_baseline": {"value": vps, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": vps, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import torch_em_b200 as tb
+    from torch_em_b200.backend import default_backend
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    batch, patch = args.batch, tuple(args.patch)
+    torch.manual_seed(0)
+    model = tb.UNet3d(**MODEL_KW).to(dev)
+    loss_fn = tb.DiceLoss()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    if world > 1:
+        tb.distributed.broadcast_parameters(model)
+        tb.distributed.sync_gradients(model)
+    xh, th = synthetic_batch(batch, patch, seed=1 + rank)
+    xh, th = xh.pin_memory(), th.pin_memory()
+    xd, td = xh.to(dev), th.to(dev)
+
+    def step(x, t):
+        opt.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = model(x)
+            loss = loss_fn(pred, t)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(xd, td)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    tb.reset_launch_count()
+    ms = timed(lambda: step(xd, td), args.steps)
+    launches = tb.launch_count() // args.steps
+
+    def e2e_step():
+        x = xh.to(dev, non_blocking=True)
+        t = th.to(dev, non_blocking=True)
+        return step(x, t).item()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.finish() if sampler else None
+
+    # per-kernel-family device time (CUDA events around every conv launch) for the roofline of the dominant kernel
+    B = default_backend()
+    B.start_timing()
+    nroof = 2
+    for _ in range(nroof):
+        step(xd, td)
+    torch.cuda.synchronize()
+    fam = B.stop_timing()
+
+    vox = batch * patch[0] * patch[1] * patch[2]
+    value = world * vox / (ms * 1e-3)
+    e2e = world * vox / (ms_e2e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    roofline = None
+    if fam:
+        top = max(fam, key=lambda k: fam[k][1])
+        n, tot_ms, work = fam[top]
+        achieved = work / (tot_ms * 1e-3) / 1e12
+        step_share = tot_ms / nroof / ms
+        roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": tens_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tens_peak, "traffic": None, "launches_per_step": n // nroof,
+                    "avg_launch_ms": tot_ms / n, "share_of_step": step_share, "peak_source": peak_src,
+                    "families_ms_per_step": {k: v[1] / nroof for k, v in fam.items()}}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpatch = (64, 64, 64)
+        vps, sec = cpu_reference_steps(cpatch, 3, 1, threads)
+        cpu = {"value": vps, "unit": "voxels/s", "cores": threads, "kind": "port",
+               "sample": f"3 train steps of the same model on one (1,1,{cpatch[0]},{cpatch[1]},{cpatch[2]}) patch, fp32 torch-CPU oracle, {sec:.2f} s/step"}
+    from oracle.unet import conv_flops_train
+    flops = conv_flops_train(1, 2, [2] * MODEL_KW["depth"], patch, batch, MODEL_KW["initial_features"])
+    line = {
+        "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"UNet3d(1,2,depth=4,initial_features=32,Sigmoid)+DiceLoss+AdamW train step, ({batch},1,{patch[0]},{patch[1]},{patch[2]}) per GPU (configs[1])",
+                   "global_batch": batch * world, "parallelism": f"dp{world}", "l2": "inputs and activations larger than L2 (no flush needed)",
+                   "conv_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12},
+        "e2e": {"value": e2e, "unit": "voxels/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": (xh.numel() + th.numel()) * 4,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--patch", type=int, nargs=3, default=list(PATCH))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

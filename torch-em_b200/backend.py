@@ -57,6 +57,29 @@ class CudaBackend:
     def __init__(self, use_umma=True):
         self.use_umma = use_umma
         self._pack_cache = {}
+        self.timing = None          # {family: [(start_event, end_event, work), ...]} while bench.py measures
+
+    # ---- per-kernel timing (bench.py roofline leg) -----------------------------------------------------------
+    def start_timing(self):
+        self.timing = {}
+
+    def stop_timing(self):
+        """-> {family: (launches, total ms, total work)}; call after torch.cuda.synchronize()."""
+        out = {}
+        for fam, evs in (self.timing or {}).items():
+            out[fam] = (len(evs), sum(a.elapsed_time(b) for a, b, _ in evs), sum(w for _, _, w in evs))
+        self.timing = None
+        return out
+
+    def _timed(self, family, work, fn):
+        if self.timing is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        self.timing.setdefault(family, []).append((a, b, work))
+        return r
 
     # ---- weights ---------------------------------------------------------------------------------------------
     def pack(self, key, w):
@@ -135,8 +158,10 @@ class CudaBackend:
         w = pack.w_dgrad_f32 if dgrad else pack.w_fwd_f32
         b = bias.detach() if bias is not None else None
         kd, kh, kw = kernel
-        call("b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, _f32(sums), _dt(x), N, D, H, W, Cin,
-             Cout, kd, kh, kw, int(relu), _stream(x))
+        flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
+        self._timed("conv_direct_dgrad" if dgrad else "conv_direct_fwd", flops, lambda: call(
+            "b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, _f32(sums), _dt(x), N, D, H, W, Cin,
+            Cout, kd, kh, kw, int(relu), _stream(x)))
 
     def wgrad(self, x, in_ss, dz, dw, kernel):
         N, D, H, W, Cin = x.shape
@@ -144,8 +169,10 @@ class CudaBackend:
         xp, xld = _act(x)
         zp, zld = _act(dz)
         kd, kh, kw = kernel
-        call("b200em_conv3d_wgrad_direct", xp, xld, _f32(in_ss), zp, zld, _dt(x), _f32(dw), N, D, H, W, Cin, Cout, kd, kh, kw,
-             _stream(x))
+        flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
+        self._timed("conv_direct_wgrad", flops, lambda: call(
+            "b200em_conv3d_wgrad_direct", xp, xld, _f32(in_ss), zp, zld, _dt(x), _f32(dw), N, D, H, W, Cin, Cout, kd, kh, kw,
+            _stream(x)))
 
     # ---- pool / upsample -------------------------------------------------------------------------------------
     def maxpool_fwd(self, x, y, f, sums):

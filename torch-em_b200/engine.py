@@ -259,16 +259,13 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
         gamma = P[gamma_key + ".weight"] if gamma_key else None
         dgamma = dbeta = None
         if gamma_key:
-            dgamma = grads.setdefault(gamma_key + ".weight", torch.zeros(C, **f32))
-            dbeta = grads.setdefault(gamma_key + ".bias", torch.zeros(C, **f32))
+            dgamma, dbeta = grads[gamma_key + ".weight"], grads[gamma_key + ".bias"]
         coef = B.norm_bwd_finalize(dsums, mr, gamma, S, _groups(norm, C), dgamma, dbeta)
         B.norm_bwd_apply(g, x, coef, None, out, relu_mask)
 
     # conv2
     grads[c2.key + ".bias"] = _bias_grad(B, dz2)
-    dw2 = torch.zeros((c2.cout, c2.cin) + c2.kernel, **f32)
-    B.wgrad(y1, rec["ss2"], dz2, dw2, c2.kernel)
-    grads[c2.key + ".weight"] = dw2
+    B.wgrad(y1, rec["ss2"], dz2, grads[c2.key + ".weight"], c2.kernel)
     g2 = torch.empty_like(y1)
     B.conv(dz2, None, packs[c2.key], None, g2, None, c2.kernel, relu=False, dgrad=True)
     dz1 = torch.empty_like(y1)
@@ -276,9 +273,7 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
     del g2
     # conv1
     grads[c1.key + ".bias"] = _bias_grad(B, dz1)
-    dw1 = torch.zeros((c1.cout, c1.cin) + c1.kernel, **f32)
-    B.wgrad(x_in, rec["ss1"], dz1, dw1, c1.kernel)
-    grads[c1.key + ".weight"] = dw1
+    B.wgrad(x_in, rec["ss1"], dz1, grads[c1.key + ".weight"], c1.kernel)
     if not need_dx:
         return None
     g1 = torch.empty(x_in.shape, dtype=x_in.dtype, device=dev)
@@ -290,11 +285,32 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
     return dx
 
 
+class FlatGrads(dict):
+    """Parameter gradients as views of ONE contiguous fp32 buffer (``.flat``): the weight-gradient kernels accumulate
+    straight into it and the data-parallel exchange is a single all-reduce over it."""
+
+    def __init__(self, P: Dict[str, torch.Tensor]):
+        super().__init__()
+        total = sum(p.numel() for p in P.values())
+        dev = next(iter(P.values())).device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for k, p in P.items():
+            dict.__setitem__(self, k, self.flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+
+    def __setitem__(self, k, v):
+        self[k].copy_(v.reshape(self[k].shape))
+
+    def setdefault(self, k, default=None):
+        return self[k]
+
+
 def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pred: torch.Tensor, packs):
-    """Returns {state-dict key: fp32 gradient} for every parameter."""
+    """Returns {state-dict key: fp32 gradient} (a FlatGrads) for every parameter."""
     m = ctx.misc
     depth = plan.depth
-    grads: Dict[str, torch.Tensor] = {}
+    grads = FlatGrads(P)
     y_last, pred = m["y_last"], m["pred"]
     dev = y_last.device
     f32 = dict(dtype=torch.float32, device=dev)
@@ -302,11 +318,9 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
     if grad_pred.dtype != torch.float32:
         grad_pred = grad_pred.float()
     oc = plan.out_conv
-    dw = torch.zeros((oc.cout, oc.cin, 1, 1, 1), **f32)
-    db = torch.zeros((oc.cout,), **f32)
     dz = torch.empty_like(y_last)
-    B.head_bwd(grad_pred, pred, y_last, P[oc.key + ".weight"], dz, dw, db, plan.final_activation, relu_mask=1)
-    grads[oc.key + ".weight"], grads[oc.key + ".bias"] = dw, db
+    B.head_bwd(grad_pred, pred, y_last, P[oc.key + ".weight"], dz, grads[oc.key + ".weight"], grads[oc.key + ".bias"],
+               plan.final_activation, relu_mask=1)
 
     skip_grads = [None] * depth
     for i in reversed(range(depth)):
@@ -319,9 +333,7 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
         d_zlow = torch.empty(zshape, dtype=x_low.dtype, device=dev)
         B.upsample_bwd(d_cat[..., :C], d_zlow, plan.scale_factors[lvl])
         grads[samp.key + ".bias"] = _bias_grad(B, d_zlow)
-        dws = torch.zeros((samp.cout, samp.cin, 1, 1, 1), **f32)
-        B.wgrad(x_low, None, d_zlow, dws, samp.kernel)
-        grads[samp.key + ".weight"] = dws
+        B.wgrad(x_low, None, d_zlow, grads[samp.key + ".weight"], samp.kernel)
         g = torch.empty_like(x_low)
         B.conv(d_zlow, None, packs[samp.key], None, g, None, samp.kernel, relu=False, dgrad=True)
         # x_low is the post-ReLU output of the block below: apply its ReLU mask in place

@@ -148,6 +148,8 @@ class _UNetFunction(torch.autograd.Function):
         B = model._backend()
         with _device_ctx(grad_pred.device):
             grads = engine.backward_pass(B, model._plan, ctx.P, ctx.fctx, grad_pred, ctx.packs)
+            if model.grad_sync is not None:
+                model.grad_sync(grads.flat)      # ONE collective over the flat gradient buffer (distributed.py)
         ctx.fctx = None
         out = [None, None, None]
         for name in model._param_names:
@@ -221,6 +223,7 @@ class AnisotropicUNet(nn.Module):
                                       anisotropic_kernel)
         self._param_names = [n for n, _ in self.named_parameters()]
         self._backend_override = None
+        self.grad_sync = None       # callable(flat fp32 gradient buffer); set by torch_em_b200.distributed.sync_gradients
         self.compute_dtype = None   # None: follow torch.autocast (bf16) / fp32 otherwise; or torch.bfloat16 / torch.float32
 
     # ---- reference surface ----------------------------------------------------------------------------------
