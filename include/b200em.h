@@ -69,6 +69,20 @@ int b200em_conv3d_wgrad_direct(const void* x, int64_t x_ld, const float* in_scal
                                int dtype, float* dw, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
                                int kw, void* stream);
 
+/* tcgen05 implicit-GEMM path: bf16 activations and weights, fp32 accumulation in TMEM (csrc/conv_umma.cu).
+ * Same fused prologue / epilogue contract as b200em_conv3d_direct.  Takes Cin % 16 == 0, Cout % 16 == 0
+ * (Cout <= 256 or Cout % 256 == 0); b200em_conv3d_umma_supported() says so, and the other entry points return
+ * 2 ("unsupported shape") otherwise so that the caller can take the direct kernel.
+ * Weights are pre-packed once per optimizer step by b200em_conv3d_umma_pack into Cout*Cin*taps bf16:
+ *   dgrad = 0: forward operand;  dgrad = 1: transposed, tap-flipped operand -- the data gradient is then
+ *   b200em_conv3d_umma(dz, ..., Cin := conv's Cout, Cout := conv's Cin). */
+int b200em_conv3d_umma_supported(int Cin, int Cout, int kd, int kh, int kw);
+int b200em_conv3d_umma_pack(const float* w, int Cout, int Cin, int kd, int kh, int kw, int dgrad, void* packed,
+                            void* stream);
+int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+                       void* y, int64_t y_ld, float* sums, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
+                       int kw, int relu, void* stream);
+
 /* ---- normalisation: nn.InstanceNorm3d(C) / nn.GroupNorm(min(32,C),C)  (unet.py:391-406) ------------------- */
 /* sums[N][C][2] += (sum x, sum x^2) over the S voxels of each sample. */
 int b200em_channel_sums(const void* x, int64_t x_ld, int dtype, int N, int64_t S, int C, float* sums, void* stream);

@@ -1,0 +1,77 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution (csrc/conv_umma.cu) against the plain-PyTorch contract
+(tests/emu_backend.py) with the SAME bf16-rounded operands, so the only differences are fp32 accumulation order and
+the final bf16 rounding of the stored output (one bf16 ulp = 2^-8 relative)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.emu_backend import TorchEmuBackend
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+EMU = TorchEmuBackend()
+
+
+class P:
+    def __init__(self, w):
+        self.w = w
+
+
+@pytest.fixture(scope="module")
+def B():
+    from torch_em_b200.backend import default_backend
+    return default_backend()
+
+
+CASES = [
+    (1, 4, 16, 8, 32, 32, (1, 1, 1)),
+    (1, 4, 16, 8, 32, 32, (3, 3, 3)),
+    (2, 5, 20, 13, 32, 64, (3, 3, 3)),
+    (1, 6, 16, 16, 16, 16, (3, 3, 3)),
+    (1, 3, 16, 8, 64, 32, (1, 3, 3)),
+    (1, 9, 33, 17, 48, 80, (3, 3, 3)),
+    (1, 4, 8, 8, 128, 256, (3, 3, 3)),
+    (1, 2, 8, 8, 256, 512, (3, 3, 3)),
+    (3, 8, 32, 32, 32, 32, (3, 3, 3)),
+]
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_umma_conv_forward_and_dgrad(B, case):
+    from torch_em_b200 import _lib
+    N, D, H, W, Cin, Cout, k = case
+    assert _lib.load().b200em_conv3d_umma_supported(Cin, Cout, *k)
+    x = rnd((N, D, H, W, Cin), 1).bfloat16()
+    w = rnd((Cout, Cin) + k, 2, scale=(Cin * k[0] * k[1] * k[2]) ** -0.5)
+    wq = w.bfloat16().float()                       # the operand the tensor cores see
+    b = rnd((Cout,), 3)
+    ss = torch.stack([1 + 0.1 * rnd((N, Cin), 4), 0.1 * rnd((N, Cin), 5)], -1).contiguous()
+    pk = B.pack(("umma-test", case), w.to(DEV))
+    assert pk.umma_fwd is not None and pk.umma_dgrad is not None
+    for in_ss, relu, bias in ((None, False, None), (ss, True, b)):
+        y_ref = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16)
+        s_ref = torch.zeros((N, Cout, 2))
+        xin = x
+        if in_ss is not None:                       # the loader rounds the normalised operand to bf16
+            xin = (x.float() * in_ss[:, None, None, None, :, 0] + in_ss[:, None, None, None, :, 1]).bfloat16()
+        EMU.conv(xin, None, P(wq), bias, y_ref, s_ref, k, relu, False)
+        ybuf = torch.zeros((N, D, H, W, Cout + 16), dtype=torch.bfloat16, device=DEV)
+        y = ybuf[..., 16:]
+        s = torch.zeros((N, Cout, 2), device=DEV)
+        B.conv(x.to(DEV), None if in_ss is None else in_ss.to(DEV), pk, None if bias is None else bias.to(DEV), y, s, k, relu, False)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(y.float().cpu().numpy(), y_ref.float().numpy(), rtol=1e-2, atol=1e-2)
+        np.testing.assert_allclose(s.cpu().numpy(), s_ref.numpy(), rtol=5e-3, atol=0.5)
+        assert float(ybuf[..., :16].abs().max()) == 0.0
+    dz = rnd((N, D, H, W, Cout), 6).bfloat16()
+    g_ref = torch.empty((N, D, H, W, Cin), dtype=torch.bfloat16)
+    EMU.conv(dz, None, P(wq), None, g_ref, None, k, False, True)
+    g = torch.empty((N, D, H, W, Cin), dtype=torch.bfloat16, device=DEV)
+    B.conv(dz.to(DEV), None, pk, None, g, None, k, False, True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(g.float().cpu().numpy(), g_ref.float().numpy(), rtol=1e-2, atol=1e-2)

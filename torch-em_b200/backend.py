@@ -98,9 +98,16 @@ class CudaBackend:
         pk.w_fwd_f32 = torch.empty((taps, cin, cout), dtype=torch.float32, device=w.device)
         pk.w_dgrad_f32 = torch.empty((taps, cout, cin), dtype=torch.float32, device=w.device)
         pk.umma_fwd = pk.umma_dgrad = None
+        lib = _lib.load()
         with torch.cuda.device(w.device):
             call("b200em_pack_conv_weights", _ptr(wd), cout, cin, kd, kh, kw, _ptr(pk.w_fwd_f32), _ptr(pk.w_dgrad_f32),
                  _stream(w))
+            if self.use_umma and lib.b200em_conv3d_umma_supported(cin, cout, kd, kh, kw):
+                pk.umma_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
+                call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.umma_fwd), _stream(w))
+            if self.use_umma and lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
+                pk.umma_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
+                call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.umma_dgrad), _stream(w))
         self._pack_cache[key] = pk
         return pk
 
@@ -159,6 +166,13 @@ class CudaBackend:
         b = bias.detach() if bias is not None else None
         kd, kh, kw = kernel
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
+        wu = pack.umma_dgrad if dgrad else pack.umma_fwd
+        if wu is not None and x.dtype == torch.bfloat16 and xld % 8 == 0 and yld % 8 == 0 and \
+                x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
+            self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
+                "b200em_conv3d_umma", xp, xld, _f32(in_ss), _ptr(wu), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cin, Cout,
+                kd, kh, kw, int(relu), _stream(x)))
+            return
         self._timed("conv_direct_dgrad" if dgrad else "conv_direct_fwd", flops, lambda: call(
             "b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, _f32(sums), _dt(x), N, D, H, W, Cin,
             Cout, kd, kh, kw, int(relu), _stream(x)))

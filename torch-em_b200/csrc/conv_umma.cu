@@ -1,0 +1,418 @@
+// Implicit-GEMM 3-D convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), bf16
+// operands, fp32 accumulation.  Forward ([Norm ->] Conv3d -> bias -> ReLU, unet.py:429-438) and, with flipped /
+// transposed weights, the data gradient.  im2col-free: the A operand of every filter tap is the SAME haloed NDHWC
+// tile in shared memory, addressed through the shared-memory matrix descriptor (start address + tap offset).
+//
+// Work item (one per CTA iteration, persistent grid = #SMs):  R consecutive depth slabs of a 16 (h) x 8 (w) voxel tile
+//   -> R accumulators of 128 voxels x NP output channels in TMEM (double buffered when 2*R*NP <= 512 columns).
+// K loop:  for each 32(16)-channel chunk of Cin:  for each filter tap:  for each slab r:  K/16 MMAs of 128 x NP x 16.
+//
+// Shared-memory operand layout (SWIZZLE_NONE K-major canonical form, 8-row x 16-byte core matrices):
+//   A: [slice s = 0..R+kd-2][plane j = 8-channel group][hp = 0..17][wp = 0..9][8 bf16]   (PLANE bytes per plane)
+//      GEMM row m = 8*hl + wl of slab r, tap (a,b,c) lives at slice r+a, row hp = hl+b(+1-ph), column wp = wl+c(+1-pw):
+//      rows of one 8-group are 16 B apart, 8-groups are 10*16 B apart (SBO), the two K-chunks PLANE apart (LBO).
+//   B: [tap in stage][plane j][n = 0..NP-1][8 bf16], filled by cp.async.bulk (TMA engine) from the pre-packed weights.
+//
+// Warp roles (320 threads): warps 0-3 epilogue (TMEM -> bias/ReLU -> bf16 store + per-(n,c) statistics for the next
+// norm), warps 4-7 operand loaders (global -> [scale*x+shift of the preceding norm] -> shared; padding is written as
+// zeros, i.e. in normalised space like the reference), warp 8 weight loader (one elected thread), warp 9 MMA issuer
+// (one elected thread).  All hand-offs are mbarriers; the accumulator hand-off is tcgen05.commit.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b200em {
+
+using namespace umma;
+
+namespace {
+constexpr int TH = 16, TW = 8;             // voxel tile (h, w) = 128 GEMM rows
+constexpr int HP = TH + 2, WP = TW + 2;     // haloed tile
+constexpr int PLANE = HP * WP * 16 + 16;    // bytes per (slice, 8-channel group) plane; +16 staggers banks
+constexpr int NSTAGE = 4;                   // weight ring depth
+constexpr int THREADS = 320;
+constexpr int MAX_SMEM = 227 * 1024;
+}  // namespace
+
+struct ConvUmmaParams {
+    const __nv_bfloat16* x; long long x_ld;
+    const float* in_ss;
+    const __nv_bfloat16* w;
+    const float* bias;
+    __nv_bfloat16* y; long long y_ld;
+    float* sums;
+    int N, D, H, W, Cin, Cout;
+    int kd, kh, kw, relu;
+    int R, NP, CC, nchunks, G, acc_bufs;
+    int tiles_w, tiles_h, tiles_d;
+    long long items;
+    int a_bytes, b_stage_bytes;
+};
+
+__device__ __forceinline__ void item_coords(const ConvUmmaParams& p, long long item, int& n, int& d0, int& h0, int& w0) {
+    int tw = (int)(item % p.tiles_w); item /= p.tiles_w;
+    int th = (int)(item % p.tiles_h); item /= p.tiles_h;
+    int td = (int)(item % p.tiles_d); item /= p.tiles_d;
+    n = (int)item; d0 = td * p.R; h0 = th * TH; w0 = tw * TW;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // carve: A[2] | B[NSTAGE] | bias[NP] | sums[2*NP] | barriers | tmem ptr
+    uint8_t* smA = smem;
+    uint8_t* smB = smA + 2 * p.a_bytes;
+    float* s_bias = reinterpret_cast<float*>(smB + NSTAGE * p.b_stage_bytes);
+    float* s_sums = s_bias + p.NP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sums + 2 * p.NP);
+    uint64_t* a_full = bars;             // [2]   128 loader arrivals
+    uint64_t* a_empty = bars + 2;        // [2]   tcgen05.commit
+    uint64_t* b_full = bars + 4;         // [NSTAGE] expect_tx
+    uint64_t* b_empty = bars + 4 + NSTAGE;
+    uint64_t* acc_full = bars + 4 + 2 * NSTAGE;   // [2] tcgen05.commit
+    uint64_t* acc_empty = acc_full + 2;           // [2] 128 epilogue arrivals
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblk = blockIdx.y;                    // 256-wide output-channel block (Cout > 256)
+    const int J = p.CC / 8;                         // planes per slice per chunk
+    const int kc = p.CC / 16;                       // K=16 MMA steps per chunk
+    const int taps = p.kd * p.kh * p.kw;
+    const int ngroups = taps / p.G;
+    const int nslices = p.R + p.kd - 1;
+    const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
+    const uint32_t acc_cols = (uint32_t)(p.R * p.NP);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < acc_cols * p.acc_bufs) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc(s_tmem, tmem_cols);
+    for (int i = threadIdx.x; i < p.NP; i += THREADS) {
+        const int co = nblk * 256 + i;
+        s_bias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
+        s_sums[2 * i] = 0.f;
+        s_sums[2 * i + 1] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp >= 4 && warp < 8) {
+        // ===================== operand loaders =====================
+        const int t = threadIdx.x - 128;             // 0..127
+        const int j = t % J;                         // fixed 8-channel group of this thread (128 % J == 0)
+        const int units = nslices * HP * WP;         // voxels of the haloed tile per chunk
+        uint32_t fill = 0;
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+            int n, d0, h0, w0;
+            item_coords(p, item, n, d0, h0, w0);
+            for (int c = 0; c < p.nchunks; ++c, ++fill) {
+                const int buf = fill & 1;
+                mbar_wait(&a_empty[buf], ((fill >> 1) & 1) ^ 1);
+                const int ch0 = c * p.CC + j * 8;
+                float sc[8], sh[8];
+                if (p.in_ss) {
+                    const float* q = p.in_ss + ((size_t)n * p.Cin + ch0) * 2;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
+                }
+                uint8_t* dstbase = smA + buf * p.a_bytes + j * PLANE;
+                const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
+                for (int v = t / J; v < units; v += 128 / J) {
+                    const int wp_ = v % WP, hp_ = (v / WP) % HP, s = v / (WP * HP);
+                    const int gd = d0 + s - pd, gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
+                    uint4 val = make_uint4(0, 0, 0, 0);
+                    if (gd >= 0 && gd < p.D && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
+                        val = *reinterpret_cast<const uint4*>(xn + (((size_t)gd * p.H + gh) * p.W + gw) * p.x_ld);
+                        if (p.in_ss) {
+                            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 f = __bfloat1622float2(h2[e]);
+                                f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
+                                f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+                                h2[e] = __floats2bfloat162_rn(f.x, f.y);
+                            }
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(dstbase + (size_t)s * J * PLANE + (hp_ * WP + wp_) * 16) = val;
+                }
+                fence_proxy_async();
+                mbar_arrive(&a_full[buf]);
+            }
+        }
+    } else if (warp == 8) {
+        // ===================== weight loader =====================
+        if (elect_one()) {
+            const uint32_t bytes = (uint32_t)p.b_stage_bytes;
+            const size_t tap_elems = (size_t)J * p.NP * 8;
+            const __nv_bfloat16* wblk = p.w + (size_t)nblk * p.nchunks * taps * tap_elems;
+            uint32_t cnt = 0;
+            for (long long item = blockIdx.x; item < p.items; item += gridDim.x)
+                for (int c = 0; c < p.nchunks; ++c)
+                    for (int g = 0; g < ngroups; ++g, ++cnt) {
+                        const int st = cnt % NSTAGE;
+                        mbar_wait(&b_empty[st], ((cnt / NSTAGE) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&b_full[st], bytes);
+                        bulk_g2s(smB + st * p.b_stage_bytes, wblk + ((size_t)c * taps + (size_t)g * p.G) * tap_elems, bytes, &b_full[st]);
+                    }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(128, p.NP);
+            const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
+            const uint32_t b_tap_bytes = (uint32_t)(J * p.NP * 16);
+            uint32_t fill = 0, cnt = 0, it = 0;
+            for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+                int n, d0, h0, w0;
+                item_coords(p, item, n, d0, h0, w0);
+                const int slot = (p.acc_bufs == 2) ? (it & 1) : 0;
+                const uint32_t use = (p.acc_bufs == 2) ? (it >> 1) : it;
+                mbar_wait(&acc_empty[slot], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + slot * acc_cols;
+                const int rmax = min(p.R, p.D - d0);
+                for (int c = 0; c < p.nchunks; ++c, ++fill) {
+                    const int buf = fill & 1;
+                    mbar_wait(&a_full[buf], (fill >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t abuf = a_base + buf * p.a_bytes;
+                    for (int g = 0; g < ngroups; ++g, ++cnt) {
+                        const int st = cnt % NSTAGE;
+                        mbar_wait(&b_full[st], (cnt / NSTAGE) & 1);
+                        tc_fence_after();
+                        for (int tg = 0; tg < p.G; ++tg) {
+                            const int tap = g * p.G + tg;
+                            const int a = tap / (p.kh * p.kw), b = (tap / p.kw) % p.kh, cc = tap % p.kw;
+                            const uint32_t aoff = (uint32_t)(((b + 1 - ph) * WP + (cc + 1 - pw)) * 16);
+                            const uint32_t bsm = b_base + st * p.b_stage_bytes + tg * b_tap_bytes;
+                            for (int r = 0; r < rmax; ++r) {
+                                for (int k = 0; k < kc; ++k) {
+                                    const uint64_t adesc = make_desc(abuf + (uint32_t)(((r + a) * J + 2 * k) * PLANE) + aoff, PLANE, WP * 16);
+                                    const uint64_t bdesc = make_desc(bsm + (uint32_t)(2 * k * p.NP * 16), (uint32_t)(p.NP * 16), 128);
+                                    umma_bf16(tacc + r * p.NP, adesc, bdesc, idesc, (c | tap | k) != 0);
+                                }
+                            }
+                        }
+                        umma_commit(&b_empty[st]);
+                    }
+                    umma_commit(&a_empty[buf]);
+                }
+                umma_commit(&acc_full[slot]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 0-3) =====================
+        const int row = warp * 32 + lane;            // GEMM row = TMEM lane
+        const int hl = row / TW, wl = row % TW;
+        uint32_t it = 0;
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+            int n, d0, h0, w0;
+            item_coords(p, item, n, d0, h0, w0);
+            const int slot = (p.acc_bufs == 2) ? (it & 1) : 0;
+            const uint32_t use = (p.acc_bufs == 2) ? (it >> 1) : it;
+            mbar_wait(&acc_full[slot], use & 1);
+            tc_fence_after();
+            const int gh = h0 + hl, gw = w0 + wl;
+            const bool valid_hw = gh < p.H && gw < p.W;
+            const int rmax = min(p.R, p.D - d0);
+            for (int r = 0; r < rmax; ++r) {
+                const int gd = d0 + r;
+                __nv_bfloat16* yp = p.y + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.y_ld + nblk * 256;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * acc_cols + r * p.NP;
+                for (int cb = 0; cb < p.NP; cb += 32) {
+                    if (p.NP - cb >= 32) {
+                        uint32_t raw[32];
+                        tmem_ld32(taddr + cb, raw);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float f = __uint_as_float(raw[i]) + s_bias[cb + i];
+                            if (p.relu) f = fmaxf(f, 0.f);
+                            v[i] = __bfloat162float(__float2bfloat16_rn(f));
+                        }
+                        if (valid_hw) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 o;
+                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+                                *reinterpret_cast<uint4*>(yp + cb + 8 * q) = o;
+                            }
+                        }
+                        if (p.sums) {
+                            float s1[32], s2[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+                            const float a1 = warp_column_sums<32>(s1, lane);
+                            const float a2 = warp_column_sums<32>(s2, lane);
+                            atomicAdd(&s_sums[2 * (cb + lane)], a1);
+                            atomicAdd(&s_sums[2 * (cb + lane) + 1], a2);
+                        }
+                    } else {   // 16-column tail (NP % 32 == 16)
+                        uint32_t raw[16];
+                        tmem_ld16(taddr + cb, raw);
+                        tmem_ld_wait();
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float f = __uint_as_float(raw[i]) + s_bias[cb + i];
+                            if (p.relu) f = fmaxf(f, 0.f);
+                            v[i] = __bfloat162float(__float2bfloat16_rn(f));
+                        }
+                        if (valid_hw) {
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                uint4 o;
+                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+                                *reinterpret_cast<uint4*>(yp + cb + 8 * q) = o;
+                            }
+                        }
+                        if (p.sums) {
+                            float s1[16], s2[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+                            const float a1 = warp_column_sums<16>(s1, lane);   // column = lane >> 1 (held twice)
+                            const float a2 = warp_column_sums<16>(s2, lane);
+                            if ((lane & 1) == 0) {
+                                atomicAdd(&s_sums[2 * (cb + (lane >> 1))], a1);
+                                atomicAdd(&s_sums[2 * (cb + (lane >> 1)) + 1], a2);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[slot]);
+            if (p.sums) {
+                // flush this item's per-channel partial sums (n may change with the next item)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = threadIdx.x; i < 2 * p.NP; i += 128) {
+                    const int co = nblk * 256 + (i >> 1);
+                    if (co < p.Cout) atomicAdd(p.sums + ((size_t)n * p.Cout + co) * 2 + (i & 1), s_sums[i]);
+                    s_sums[i] = 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing: torch (Cout, Cin, taps) fp32 -> bf16 [nblk][chunk][tap][plane j][NPb][8]
+// dgrad = 1 packs the transposed, tap-flipped filter: "Cout" of the packed operand is the conv's Cin and vice versa.
+__global__ void pack_umma_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int dgrad, int CC, int NPb,
+                                         __nv_bfloat16* __restrict__ out) {
+    const int64_t total = (int64_t)Cout * Cin * taps;
+    const int Kc = dgrad ? Cout : Cin;               // reduction channels of the packed operand
+    const int nchunks = Kc / CC, J = CC / 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tp = (int)(i % taps);
+        const int ci = (int)((i / taps) % Cin);
+        const int co = (int)(i / ((int64_t)taps * Cin));
+        const int n_ = dgrad ? ci : co, k_ = dgrad ? co : ci, t_ = dgrad ? taps - 1 - tp : tp;
+        const int nb = n_ / NPb, nn = n_ % NPb, chunk = k_ / CC, j = (k_ % CC) / 8, e = k_ % 8;
+        out[((((size_t)(nb * nchunks + chunk) * taps + t_) * J + j) * NPb + nn) * 8 + e] = __float2bfloat16_rn(w[i]);
+    }
+}
+
+struct UmmaShape {
+    int CC, NP, nblk, R, G, acc_bufs, a_bytes, b_stage_bytes, smem_bytes;
+};
+
+// Channel counts the tensor-core path takes; everything else goes to the direct kernel.
+static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s) {
+    if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16) return false;
+    if (Cout > 256 && Cout % 256) return false;
+    s.CC = (Cin % 32 == 0) ? 32 : 16;
+    s.NP = Cout > 256 ? 256 : Cout;
+    s.nblk = Cout > 256 ? Cout / 256 : 1;
+    const int taps = kd * kh * kw;
+    s.G = (taps % 3 == 0 && s.NP <= 64) ? 3 : 1;
+    const int J = s.CC / 8;
+    s.b_stage_bytes = s.G * J * s.NP * 16;
+    for (int R = 4; R >= 1; R >>= 1) {
+        if (R * s.NP > 512) continue;
+        s.R = R;
+        s.acc_bufs = (2 * R * s.NP <= 512) ? 2 : 1;
+        s.a_bytes = (R + kd - 1) * J * PLANE;
+        s.smem_bytes = 2 * s.a_bytes + NSTAGE * s.b_stage_bytes + s.NP * 4 * 3 + 16 * 8 + 16 + 128;
+        if (s.smem_bytes <= MAX_SMEM) return true;
+    }
+    return false;
+}
+
+}  // namespace b200em
+
+using namespace b200em;
+
+extern "C" {
+
+int b200em_conv3d_umma_supported(int Cin, int Cout, int kd, int kh, int kw) {
+    UmmaShape s;
+    return umma_shape(Cin, Cout, kd, kh, kw, s) ? 1 : 0;
+}
+
+int b200em_conv3d_umma_pack(const float* w, int Cout, int Cin, int kd, int kh, int kw, int dgrad, void* packed, void* stream) {
+    B2_CHECK_ARG(w && packed && Cout > 0 && Cin > 0, "conv3d_umma_pack: bad arguments");
+    UmmaShape s;
+    const int n_ = dgrad ? Cin : Cout, k_ = dgrad ? Cout : Cin;
+    if (!umma_shape(k_, n_, kd, kh, kw, s)) {
+        set_error("conv3d_umma_pack: channel counts (%d -> %d) not supported by the tcgen05 path", k_, n_);
+        return 2;
+    }
+    const int taps = kd * kh * kw;
+    int64_t total = (int64_t)Cout * Cin * taps;
+    int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    pack_umma_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, taps, dgrad, s.CC, s.NP, (__nv_bfloat16*)packed);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+                       void* y, int64_t y_ld, float* sums, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
+                       int kw, int relu, void* stream) {
+    B2_CHECK_ARG(x && w_packed && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma: bad arguments");
+    B2_CHECK_ARG((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv3d_umma: kernel dims must be 1 or 3");
+    UmmaShape s;
+    if (!umma_shape(Cin, Cout, kd, kh, kw, s)) {
+        set_error("conv3d_umma: channel counts (%d -> %d) not supported by the tcgen05 path", Cin, Cout);
+        return 2;
+    }
+    B2_CHECK_ARG(x_ld % 8 == 0 && y_ld % 8 == 0 && aligned16(x) && aligned16(y), "conv3d_umma: activations must be 16-byte aligned with pitch % 8 == 0");
+    B2_CHECK_ARG(x_ld >= Cin && y_ld >= Cout, "conv3d_umma: pitch smaller than channel count");
+    ConvUmmaParams p;
+    p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.w = (const __nv_bfloat16*)w_packed; p.bias = bias;
+    p.y = (__nv_bfloat16*)y; p.y_ld = y_ld; p.sums = sums;
+    p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.relu = relu;
+    p.R = s.R; p.NP = s.NP; p.CC = s.CC; p.nchunks = Cin / s.CC; p.G = s.G; p.acc_bufs = s.acc_bufs;
+    p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + s.R - 1) / s.R;
+    p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    p.a_bytes = s.a_bytes; p.b_stage_bytes = s.b_stage_bytes;
+    B2_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    long long gx = p.items < sm_count() / s.nblk ? p.items : sm_count() / s.nblk;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)s.nblk, 1);
+    conv3d_umma_kernel<<<grid, THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"
