@@ -83,6 +83,14 @@ int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift,
                        void* y, int64_t y_ld, float* sums, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
                        int kw, int relu, void* stream);
 
+/* Weight gradient on the tensor cores (bf16 operands, fp32 accumulation in TMEM, fp32 atomics into dw).
+ * dw (Cout,Cin,kd,kh,kw) fp32 += sum dz * x_hat (same contract as b200em_conv3d_wgrad_direct); db (nullable)
+ * (Cout) fp32 += sum dz -- the bias gradient, fused into the dz operand load.  Takes Cin % 32 == 0, Cout % 16 == 0. */
+int b200em_conv3d_wgrad_umma_supported(int Cin, int Cout, int kd, int kh, int kw);
+int b200em_conv3d_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld,
+                             float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw,
+                             void* stream);
+
 /* ---- normalisation: nn.InstanceNorm3d(C) / nn.GroupNorm(min(32,C),C)  (unet.py:391-406) ------------------- */
 /* sums[N][C][2] += (sum x, sum x^2) over the S voxels of each sample. */
 int b200em_channel_sums(const void* x, int64_t x_ld, int dtype, int N, int64_t S, int C, float* sums, void* stream);

@@ -102,10 +102,12 @@ class TorchEmuBackend:
         if sums is not None:
             self.channel_sums(y, sums)
 
-    def wgrad(self, x, in_ss, dz, dw, kernel):
+    def wgrad(self, x, in_ss, dz, dw, db, kernel):
         pad = tuple(k // 2 for k in kernel)
         xh = self._xhat(x, in_ss).contiguous()
         dw += torch.nn.grad.conv3d_weight(xh, dw.shape, _ncdhw(dz.float()).contiguous(), padding=pad)
+        if db is not None:
+            db += dz.float().sum((0, 1, 2, 3))
 
     def maxpool_fwd(self, x, y, f, sums):
         r = F.max_pool3d(_ncdhw(x.float()), kernel_size=list(f), stride=list(f))

@@ -18,8 +18,10 @@ DEV = "cuda:0"
 
 @pytest.fixture(scope="module")
 def B():
-    from torch_em_b200.backend import default_backend
-    return default_backend()
+    from torch_em_b200 import _lib
+    from torch_em_b200.backend import CudaBackend
+    _lib.load()
+    return CudaBackend(use_umma=False)      # this module pins the direct / elementwise kernels; tcgen05: test_gpu_umma.py
 
 
 EMU = TorchEmuBackend()
@@ -86,11 +88,12 @@ def test_conv_forward_dgrad_wgrad(B, case, dtype):
     B.conv(dz.to(DEV), None, pk, None, g, None, k, False, True)
     close(g, g_ref, **tol(dtype))
     # weight gradient (with the fused norm apply on x)
-    dw_ref = torch.zeros_like(w)
-    EMU.wgrad(x, ss, dz, dw_ref, k)
-    dw = torch.zeros_like(wd)
-    B.wgrad(x.to(DEV), ss.to(DEV), dz.to(DEV), dw, k)
+    dw_ref, db_ref = torch.zeros_like(w), torch.zeros(Cout)
+    EMU.wgrad(x, ss, dz, dw_ref, db_ref, k)
+    dw, db = torch.zeros_like(wd), torch.zeros(Cout, device=DEV)
+    B.wgrad(x.to(DEV), ss.to(DEV), dz.to(DEV), dw, db, k)
     close(dw, dw_ref, rtol=1e-3, atol=1e-3 * float(dw_ref.abs().max()))
+    close(db, db_ref, rtol=1e-3, atol=1e-3 * float(db_ref.abs().max()))
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

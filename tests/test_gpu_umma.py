@@ -75,3 +75,34 @@ def test_umma_conv_forward_and_dgrad(B, case):
     B.conv(dz.to(DEV), None, pk, None, g, None, k, False, True)
     torch.cuda.synchronize()
     np.testing.assert_allclose(g.float().cpu().numpy(), g_ref.float().numpy(), rtol=1e-2, atol=1e-2)
+
+
+WG_CASES = [
+    (1, 2, 16, 8, 32, 32, (1, 1, 1)),
+    (1, 2, 16, 8, 32, 32, (3, 3, 3)),
+    (2, 5, 20, 13, 32, 64, (3, 3, 3)),
+    (1, 3, 16, 8, 64, 32, (1, 3, 3)),
+    (1, 7, 33, 17, 96, 48, (3, 3, 3)),
+    (1, 4, 8, 8, 128, 256, (3, 3, 3)),
+    (3, 8, 32, 32, 32, 32, (3, 3, 3)),
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_umma_wgrad(B, case):
+    from torch_em_b200 import _lib
+    N, D, H, W, Cin, Cout, k = case
+    assert _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, *k)
+    x = rnd((N, D, H, W, Cin), 11).bfloat16()
+    dz = rnd((N, D, H, W, Cout), 12).bfloat16()
+    ss = torch.stack([1 + 0.1 * rnd((N, Cin), 13), 0.1 * rnd((N, Cin), 14)], -1).contiguous()
+    for in_ss in (None, ss):
+        xin = x if in_ss is None else (x.float() * in_ss[:, None, None, None, :, 0] + in_ss[:, None, None, None, :, 1]).bfloat16()
+        dw_ref, db_ref = torch.zeros((Cout, Cin) + k), torch.zeros(Cout)
+        EMU.wgrad(xin, None, dz, dw_ref, db_ref, k)
+        dw = torch.full((Cout, Cin) + k, 0.5, device=DEV)          # accumulate semantics: += on top of existing values
+        db = torch.full((Cout,), -1.0, device=DEV)
+        B.wgrad(x.to(DEV), None if in_ss is None else in_ss.to(DEV), dz.to(DEV), dw, db, k)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(dw.cpu().numpy() - 0.5, dw_ref.numpy(), rtol=2e-3, atol=2e-3 * float(dw_ref.abs().max()))
+        np.testing.assert_allclose(db.cpu().numpy() + 1.0, db_ref.numpy(), rtol=2e-3, atol=2e-3 * float(db_ref.abs().max()))

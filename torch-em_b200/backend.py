@@ -177,16 +177,27 @@ class CudaBackend:
             "b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, _f32(sums), _dt(x), N, D, H, W, Cin,
             Cout, kd, kh, kw, int(relu), _stream(x)))
 
-    def wgrad(self, x, in_ss, dz, dw, kernel):
+    def wgrad(self, x, in_ss, dz, dw, db, kernel):
+        """dw += sum dz * norm(x) shifted by the taps;  db (nullable) += sum dz  (weight and bias gradient)."""
         N, D, H, W, Cin = x.shape
         Cout = dz.shape[4]
         xp, xld = _act(x)
         zp, zld = _act(dz)
         kd, kh, kw = kernel
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
+        if self.use_umma and x.dtype == torch.bfloat16 and xld % 8 == 0 and zld % 8 == 0 and x.data_ptr() % 16 == 0 and \
+                dz.data_ptr() % 16 == 0 and _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw):
+            self._timed("conv_umma_wgrad", flops, lambda: call(
+                "b200em_conv3d_wgrad_umma", xp, xld, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cin, Cout, kd, kh,
+                kw, _stream(x)))
+            return
         self._timed("conv_direct_wgrad", flops, lambda: call(
             "b200em_conv3d_wgrad_direct", xp, xld, _f32(in_ss), zp, zld, _dt(x), _f32(dw), N, D, H, W, Cin, Cout, kd, kh, kw,
             _stream(x)))
+        if db is not None:
+            s = torch.zeros((N, Cout, 2), dtype=torch.float32, device=dz.device)
+            self.channel_sums(dz, s)
+            db += s[:, :, 0].sum(0)
 
     # ---- pool / upsample -------------------------------------------------------------------------------------
     def maxpool_fwd(self, x, y, f, sums):

@@ -359,6 +359,223 @@ static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s) 
     return false;
 }
 
+
+// ===============================================================================================================
+// Weight gradient on the tensor cores:  dW[co][ci][tap] += sum_{n,vox} dz[n,vox,co] * x_hat[n,vox+tap,ci]
+//
+// GEMM view per (32-channel chunk of Cin, NB-channel block of Cout):  K = voxels (16 per MMA: two 8-voxel w-rows),
+//   A (MN-major) = x_hat: M = 128 rows = 16 consecutive planes of the haloed tile = 4 depth slices x 32 channels
+//       -> rows [0,96) are the three depth taps a = 0,1,2 of slab r; rows [96,128) (slice r+3) are computed and ignored
+//   B (MN-major) = dz slab: N = NB output channels
+//   D[tap9 = (b,c)] in TMEM: 9 accumulators x NB columns, kept resident over ALL work items of the CTA;
+//   one epilogue at the end adds them into the fp32 dW (torch layout) with atomics.
+// The haloed x_hat tile is the same shared-memory image the forward kernel builds (and the same fused norm apply);
+// the (b,c) tap shift is again just a start-address offset of the descriptor.
+namespace {
+constexpr int WG_R = 2;                        // depth slabs per work item
+constexpr int WG_DZ_PLANE = TH * TW * 16;      // bytes per 8-channel plane of a dz slab
+}  // namespace
+
+struct WgradUmmaParams {
+    const __nv_bfloat16* x; long long x_ld;
+    const float* in_ss;
+    const __nv_bfloat16* dz; long long dz_ld;
+    float* dw;
+    float* db;
+    int N, D, H, W, Cin, Cout;
+    int kd, kh, kw;
+    int NB, nco;                               // Cout block, number of Cout blocks
+    int tiles_w, tiles_h, tiles_d;
+    long long items;
+    int x_bytes, dz_bytes;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const WgradUmmaParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // carve: X[2] | pad slice | DZ[2] | db sums[NB] | barriers | tmem ptr
+    constexpr int J = 4;                                       // 32-channel chunk = 4 planes
+    const int nslices = WG_R + p.kd - 1;
+    uint8_t* smX = smem;
+    uint8_t* smZ = smX + 2 * p.x_bytes + 4 * J * PLANE;        // room for the "slice r+3" over-read of the last slab
+    float* s_db = reinterpret_cast<float*>(smZ + 2 * p.dz_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_db + p.NB);
+    uint64_t* full = bars;            // [2] 128 loader arrivals
+    uint64_t* empty = bars + 2;       // [2] tcgen05.commit
+    uint64_t* acc_full = bars + 4;    // [1]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = blockIdx.y / p.nco, cob = blockIdx.y % p.nco;
+    const int JO = p.NB / 8;
+    const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
+    const int tap9 = p.kh * p.kw;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(tap9 * p.NB)) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc(s_tmem, tmem_cols);
+    for (int i = threadIdx.x; i < p.NB; i += THREADS) s_db[i] = 0.f;
+    // the over-read region must hold finite-or-not garbage only in rows that are ignored; zero it once anyway
+    for (int i = threadIdx.x; i < 4 * J * PLANE / 16; i += THREADS)
+        reinterpret_cast<uint4*>(smX + 2 * p.x_bytes)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    auto coords = [&](long long item, int& n, int& d0, int& h0, int& w0) {
+        int tw = (int)(item % p.tiles_w); item /= p.tiles_w;
+        int th = (int)(item % p.tiles_h); item /= p.tiles_h;
+        int td = (int)(item % p.tiles_d); item /= p.tiles_d;
+        n = (int)item; d0 = td * WG_R; h0 = th * TH; w0 = tw * TW;
+    };
+
+    if (warp >= 4 && warp < 8) {
+        // ===================== loaders: x_hat haloed tile + dz slabs =====================
+        const int t = threadIdx.x - 128;
+        const int j = t % J, jo = t % JO;
+        const int xunits = nslices * HP * WP, zunits = WG_R * TH * TW;
+        float dbacc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dbacc[e] = 0.f;
+        uint32_t fill = 0;
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++fill) {
+            int n, d0, h0, w0;
+            coords(item, n, d0, h0, w0);
+            const int buf = fill & 1;
+            mbar_wait(&empty[buf], ((fill >> 1) & 1) ^ 1);
+            const int ch0 = chunk * 32 + j * 8;
+            float sc[8], sh[8];
+            if (p.in_ss) {
+                const float* q = p.in_ss + ((size_t)n * p.Cin + ch0) * 2;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
+            }
+            uint8_t* xdst = smX + buf * p.x_bytes + j * PLANE;
+            const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
+            for (int v = t / J; v < xunits; v += 128 / J) {
+                const int wp_ = v % WP, hp_ = (v / WP) % HP, s = v / (WP * HP);
+                const int gd = d0 + s - pd, gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
+                uint4 val = make_uint4(0, 0, 0, 0);
+                if (gd >= 0 && gd < p.D && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
+                    val = *reinterpret_cast<const uint4*>(xn + (((size_t)gd * p.H + gh) * p.W + gw) * p.x_ld);
+                    if (p.in_ss) {
+                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 f = __bfloat1622float2(h2[e]);
+                            f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
+                            f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+                            h2[e] = __floats2bfloat162_rn(f.x, f.y);
+                        }
+                    }
+                }
+                *reinterpret_cast<uint4*>(xdst + (size_t)s * J * PLANE + (hp_ * WP + wp_) * 16) = val;
+            }
+            uint8_t* zdst = smZ + buf * p.dz_bytes + jo * WG_DZ_PLANE;
+            const __nv_bfloat16* zn = p.dz + (size_t)n * p.D * p.H * p.W * p.dz_ld + cob * p.NB + jo * 8;
+            for (int v = t / JO; v < zunits; v += 128 / JO) {
+                const int wl = v % TW, hl = (v / TW) % TH, r = v / (TW * TH);
+                const int gd = d0 + r, gh = h0 + hl, gw = w0 + wl;
+                uint4 val = make_uint4(0, 0, 0, 0);
+                if (gd < p.D && gh < p.H && gw < p.W) {
+                    val = *reinterpret_cast<const uint4*>(zn + (((size_t)gd * p.H + gh) * p.W + gw) * p.dz_ld);
+                    if (p.db && chunk == 0) {
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 f = __bfloat1622float2(h2[e]);
+                            dbacc[2 * e] += f.x;
+                            dbacc[2 * e + 1] += f.y;
+                        }
+                    }
+                }
+                *reinterpret_cast<uint4*>(zdst + (size_t)r * JO * WG_DZ_PLANE + (hl * TW + wl) * 16) = val;
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[buf]);
+        }
+        if (p.db && chunk == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_db[jo * 8 + e], dbacc[e]);
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (t < p.NB) atomicAdd(p.db + cob * p.NB + t, s_db[t]);
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(128, p.NB, 1, 1);      // both operands MN-major
+            const uint32_t x_base = smem_u32(smX), z_base = smem_u32(smZ);
+            uint32_t fill = 0;
+            for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++fill) {
+                int n, d0, h0, w0;
+                coords(item, n, d0, h0, w0);
+                const int buf = fill & 1;
+                mbar_wait(&full[buf], (fill >> 1) & 1);
+                tc_fence_after();
+                const int rmax = min(WG_R, p.D - d0);
+                for (int r = 0; r < rmax; ++r) {
+                    const uint32_t xs = x_base + buf * p.x_bytes + (uint32_t)(r * J * PLANE);
+                    const uint32_t zs = z_base + buf * p.dz_bytes + (uint32_t)(r * JO * WG_DZ_PLANE);
+                    for (int tp = 0; tp < tap9; ++tp) {
+                        const int b = tp / p.kw, cc = tp % p.kw;
+                        for (int ks = 0; ks < TH / 2; ++ks) {
+                            // K step = voxel rows hl = 2ks, 2ks+1 (8 voxels each)
+                            const uint32_t aaddr = xs + (uint32_t)(((2 * ks + b + 1 - ph) * WP + (cc + 1 - pw)) * 16);
+                            const uint64_t adesc = make_desc(aaddr, WP * 16, PLANE);          // LBO: next 8 voxels, SBO: next 8 channels
+                            const uint64_t bdesc = make_desc(zs + (uint32_t)(2 * ks * TW * 16), TW * 16, WG_DZ_PLANE);
+                            umma_bf16(tmem_base + tp * p.NB, adesc, bdesc, idesc, (fill | (uint32_t)r | (uint32_t)ks) != 0);
+                        }
+                    }
+                }
+                umma_commit(&empty[buf]);
+            }
+            umma_commit(acc_full);
+        }
+    } else if (warp < 4) {
+        // ===================== epilogue: TMEM -> atomics into dW =====================
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int a = warp;                              // depth tap of this warp's 32 lanes (a == 3: ignored rows)
+        const int taps = p.kd * tap9;
+        if (a < p.kd) {
+            const int ci = chunk * 32 + lane;
+            for (int tp = 0; tp < tap9; ++tp) {
+                const int tap = a * tap9 + tp;
+                for (int cb = 0; cb < p.NB; cb += 16) {
+                    uint32_t raw[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + tp * p.NB + cb, raw);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int co = cob * p.NB + cb + i;
+                        atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * taps + tap, __uint_as_float(raw[i]));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+static bool wgrad_umma_shape(int Cin, int Cout, int& NB) {
+    if (Cin % 32 || Cout % 16 || Cin < 32 || Cout < 16) return false;
+    NB = (Cout % 32 == 0) ? 32 : 16;
+    return true;
+}
+
 }  // namespace b200em
 
 using namespace b200em;
@@ -411,6 +628,43 @@ int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift,
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)s.nblk, 1);
     conv3d_umma_kernel<<<grid, THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_conv3d_wgrad_umma_supported(int Cin, int Cout, int kd, int kh, int kw) {
+    int NB;
+    return wgrad_umma_shape(Cin, Cout, NB) ? 1 : 0;
+}
+
+int b200em_conv3d_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw,
+                             float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream) {
+    B2_CHECK_ARG(x && dz && dw && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_wgrad_umma: bad arguments");
+    B2_CHECK_ARG((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv3d_wgrad_umma: kernel dims must be 1 or 3");
+    int NB;
+    if (!wgrad_umma_shape(Cin, Cout, NB)) {
+        set_error("conv3d_wgrad_umma: channel counts (%d -> %d) not supported by the tcgen05 path", Cin, Cout);
+        return 2;
+    }
+    B2_CHECK_ARG(x_ld % 8 == 0 && dz_ld % 8 == 0 && aligned16(x) && aligned16(dz), "conv3d_wgrad_umma: activations must be 16-byte aligned with pitch % 8 == 0");
+    WgradUmmaParams p;
+    p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.dz = (const __nv_bfloat16*)dz; p.dz_ld = dz_ld;
+    p.dw = dw; p.db = db;
+    p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
+    p.NB = NB; p.nco = Cout / NB;
+    p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + WG_R - 1) / WG_R;
+    p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    p.x_bytes = (WG_R + kd - 1) * 4 * PLANE;
+    p.dz_bytes = WG_R * (NB / 8) * WG_DZ_PLANE;
+    const int smem_bytes = 2 * p.x_bytes + 4 * 4 * PLANE + 2 * p.dz_bytes + NB * 4 + 8 * 8 + 16 + 128;
+    B2_CHECK_ARG(smem_bytes <= MAX_SMEM, "conv3d_wgrad_umma: shared memory budget exceeded");
+    B2_CUDA(cudaFuncSetAttribute(conv3d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    const int pairs = (Cin / 32) * p.nco;
+    long long splits = sm_count() / pairs;
+    if (splits < 1) splits = 1;
+    if (splits > p.items) splits = p.items;
+    dim3 grid((unsigned)splits, (unsigned)pairs, 1);
+    conv3d_wgrad_umma_kernel<<<grid, THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
     B2_LAUNCH_CHECK();
     return 0;
 }

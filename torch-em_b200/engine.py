@@ -232,13 +232,6 @@ def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act
     return pred, ctx
 
 
-def _bias_grad(B, dz):
-    N, _, _, _, C = dz.shape
-    s = torch.zeros((N, C, 2), dtype=torch.float32, device=dz.device)
-    B.channel_sums(dz, s)
-    return s[:, :, 0].sum(0)
-
-
 def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs):
     """dz2 = gradient w.r.t. the PRE-ReLU output of conv2 (i.e. already multiplied by [y2 > 0]).
     Returns the gradient w.r.t. the block input (before any mask of the producer), or None."""
@@ -264,16 +257,14 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
         B.norm_bwd_apply(g, x, coef, None, out, relu_mask)
 
     # conv2
-    grads[c2.key + ".bias"] = _bias_grad(B, dz2)
-    B.wgrad(y1, rec["ss2"], dz2, grads[c2.key + ".weight"], c2.kernel)
+    B.wgrad(y1, rec["ss2"], dz2, grads[c2.key + ".weight"], grads[c2.key + ".bias"], c2.kernel)
     g2 = torch.empty_like(y1)
     B.conv(dz2, None, packs[c2.key], None, g2, None, c2.kernel, relu=False, dgrad=True)
     dz1 = torch.empty_like(y1)
     norm_back(g2, y1, rec["mr2"], spec.norm2_key, c2.cin, dz1, relu_mask=1)
     del g2
     # conv1
-    grads[c1.key + ".bias"] = _bias_grad(B, dz1)
-    B.wgrad(x_in, rec["ss1"], dz1, grads[c1.key + ".weight"], c1.kernel)
+    B.wgrad(x_in, rec["ss1"], dz1, grads[c1.key + ".weight"], grads[c1.key + ".bias"], c1.kernel)
     if not need_dx:
         return None
     g1 = torch.empty(x_in.shape, dtype=x_in.dtype, device=dev)
@@ -332,8 +323,7 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
         x_low, zshape = m["sampler_in"][i]
         d_zlow = torch.empty(zshape, dtype=x_low.dtype, device=dev)
         B.upsample_bwd(d_cat[..., :C], d_zlow, plan.scale_factors[lvl])
-        grads[samp.key + ".bias"] = _bias_grad(B, d_zlow)
-        B.wgrad(x_low, None, d_zlow, grads[samp.key + ".weight"], samp.kernel)
+        B.wgrad(x_low, None, d_zlow, grads[samp.key + ".weight"], grads[samp.key + ".bias"], samp.kernel)
         g = torch.empty_like(x_low)
         B.conv(d_zlow, None, packs[samp.key], None, g, None, samp.kernel, relu=False, dgrad=True)
         # x_low is the post-ReLU output of the block below: apply its ReLU mask in place
