@@ -69,6 +69,12 @@ int b200em_conv3d_wgrad_direct(const void* x, int64_t x_ld, const float* in_scal
                                int dtype, float* dw, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
                                int kw, void* stream);
 
+/* Weight + bias gradient of the network's first conv (1 <= Cin <= 4; HBM-bound: one pass over dz and x).
+ * dw (Cout,Cin,kd,kh,kw) += ..., db (nullable) (Cout) += sum dz. */
+int b200em_conv3d_wgrad_smallcin(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld,
+                                 int dtype, float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
+                                 int kw, void* stream);
+
 /* tcgen05 implicit-GEMM path: bf16 activations and weights, fp32 accumulation in TMEM (csrc/conv_umma.cu).
  * Same fused prologue / epilogue contract as b200em_conv3d_direct.  Takes Cin % 16 == 0, Cout % 16 == 0
  * (Cout <= 256 or Cout % 256 == 0); b200em_conv3d_umma_supported() says so, and the other entry points return

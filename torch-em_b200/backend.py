@@ -191,6 +191,11 @@ class CudaBackend:
                 "b200em_conv3d_wgrad_umma", xp, xld, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cin, Cout, kd, kh,
                 kw, _stream(x)))
             return
+        if Cin <= 4:
+            self._timed("conv_smallcin_wgrad", flops, lambda: call(
+                "b200em_conv3d_wgrad_smallcin", xp, xld, _f32(in_ss), zp, zld, _dt(x), _f32(dw), _f32(db), N, D, H, W, Cin, Cout,
+                kd, kh, kw, _stream(x)))
+            return
         self._timed("conv_direct_wgrad", flops, lambda: call(
             "b200em_conv3d_wgrad_direct", xp, xld, _f32(in_ss), zp, zld, _dt(x), _f32(dw), N, D, H, W, Cin, Cout, kd, kh, kw,
             _stream(x)))

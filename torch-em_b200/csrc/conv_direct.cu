@@ -13,19 +13,20 @@ namespace b200em {
 
 namespace {
 constexpr int TD = 4, TH = 8, TW = 8;   // output voxels per block (256 threads, one voxel each)
-constexpr int CK = 4, CKP = 5;           // input channels staged per round (+1 pad: conflict-free voxel stride)
+// input channels staged per round: CK = 4 (+1 pad: conflict-free voxel stride), CK = 1 for the network's first conv
 constexpr int COT = 32;                  // output channels per block
 constexpr int MAXHALO = (TD + 2) * (TH + 2) * (TW + 2);
 }  // namespace
 
-template <typename T>
+template <typename T, int CK>
 __global__ void __launch_bounds__(256)
 conv3d_direct_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ in_ss,
                      const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ y, int64_t y_ld,
                      float* __restrict__ sums, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw,
                      int relu, int tiles_w, int tiles_h) {
+    constexpr int CKP = CK == 1 ? 1 : CK + 1;
     __shared__ float xs[MAXHALO * CKP];
-    __shared__ float ws[27 * CK * COT];
+    __shared__ __align__(16) float ws[27 * CK * COT];
     __shared__ float red[COT * 2];
 
     const int tid = threadIdx.x;
@@ -251,6 +252,104 @@ conv3d_wgrad_direct_kernel(const T* __restrict__ x, int64_t x_ld, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// weight (+ bias) gradient of the network's FIRST conv (Cin <= 4): 27*Cin*Cout outputs reduced over all voxels.
+// HBM-bound: one pass over dz (Cout channels) and x (Cin channels).  Block = 4x8x8 voxel tile, persistent over tiles;
+// thread (co = tid % 32, slot group = tid / 32) owns the (tap, ci) slots {tid/32 + 8k}; dz is staged as fp32 in
+// shared memory (lanes read consecutive co: conflict-free), x_hat values are warp-broadcast reads of the haloed tile.
+namespace {
+constexpr int SC_MAXCIN = 4;
+constexpr int SC_MAXQ = (27 * SC_MAXCIN + 7) / 8;   // slots per thread
+constexpr int SC_VOX = TD * TH * TW;                 // 256
+}  // namespace
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv3d_wgrad_smallcin_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ in_ss,
+                             const T* __restrict__ dz, int64_t dz_ld, float* __restrict__ dw, float* __restrict__ db,
+                             int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
+    __shared__ float xs[MAXHALO * SC_MAXCIN];
+    __shared__ float ds[SC_VOX * COT];
+    const int tid = threadIdx.x;
+    const int co_l = tid & 31, grp = tid >> 5;
+    const int co0 = blockIdx.y * COT;
+    const int pd = kd / 2, ph = kh / 2, pw = kw / 2;
+    const int HH = TH + kh - 1, HW = TW + kw - 1, HD = TD + kd - 1;
+    const int taps = kd * kh * kw;
+    const int nslots = taps * Cin;
+    const int tw_n = (W + TW - 1) / TW, th_n = (H + TH - 1) / TH, td_n = (D + TD - 1) / TD;
+    const int64_t tiles = (int64_t)N * td_n * th_n * tw_n;
+
+    float acc[SC_MAXQ];
+    int off[SC_MAXQ];                                  // haloed-tile element offset of slot k relative to the voxel
+#pragma unroll
+    for (int k = 0; k < SC_MAXQ; ++k) {
+        acc[k] = 0.f;
+        const int q = grp + 8 * k;
+        int o = 0;
+        if (q < nslots) {
+            const int tp = q / Cin, ci = q % Cin;
+            const int a = tp / (kh * kw), b = (tp / kw) % kh, c = tp % kw;
+            o = ((a * HH + b) * HW + c) * Cin + ci;
+        }
+        off[k] = o;
+    }
+    float dbacc = 0.f;
+
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int64_t t = tile;
+        const int w0 = (int)(t % tw_n) * TW; t /= tw_n;
+        const int h0 = (int)(t % th_n) * TH; t /= th_n;
+        const int d0 = (int)(t % td_n) * TD; t /= td_n;
+        const int n = (int)t;
+        const T* xn = x + (size_t)n * D * H * W * x_ld;
+        const T* dn = dz + (size_t)n * D * H * W * dz_ld;
+        __syncthreads();
+        for (int i = tid; i < HD * HH * HW * Cin; i += 256) {
+            const int ci = i % Cin, hv = i / Cin;
+            const int hx = hv % HW, hy = (hv / HW) % HH, hz = hv / (HW * HH);
+            const int gd = d0 + hz - pd, gh = h0 + hy - ph, gw = w0 + hx - pw;
+            float v = 0.f;
+            if (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
+                v = to_f<T>(xn[(((size_t)gd * H + gh) * W + gw) * x_ld + ci]);
+                if (in_ss) {
+                    const float* p = in_ss + ((size_t)n * Cin + ci) * 2;
+                    v = fmaf(v, p[0], p[1]);
+                }
+            }
+            xs[i] = v;
+        }
+        for (int i = tid; i < SC_VOX * COT; i += 256) {
+            const int co = i % COT, v = i / COT;
+            const int vx = v % TW, vy = (v / TW) % TH, vz = v / (TW * TH);
+            const int gd = d0 + vz, gh = h0 + vy, gw = w0 + vx;
+            float g = 0.f;
+            if (co0 + co < Cout && gd < D && gh < H && gw < W)
+                g = to_f<T>(dn[(((size_t)gd * H + gh) * W + gw) * dz_ld + co0 + co]);
+            ds[i] = g;
+        }
+        __syncthreads();
+        for (int v = 0; v < SC_VOX; ++v) {
+            const int vx = v % TW, vy = (v / TW) % TH, vz = v / (TW * TH);
+            const float g = ds[v * COT + co_l];
+            const float* xb = xs + ((vz * HH + vy) * HW + vx) * Cin;
+            if (grp == 0) dbacc += g;
+#pragma unroll
+            for (int k = 0; k < SC_MAXQ; ++k)
+                if (grp + 8 * k < nslots) acc[k] = fmaf(g, xb[off[k]], acc[k]);
+        }
+    }
+    const int co = co0 + co_l;
+    if (co < Cout) {
+#pragma unroll
+        for (int k = 0; k < SC_MAXQ; ++k) {
+            const int q = grp + 8 * k;
+            if (q < nslots) atomicAdd(dw + ((size_t)co * Cin + q % Cin) * taps + q / Cin, acc[k]);
+        }
+        if (db && grp == 0) atomicAdd(db + co, dbacc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // weight re-packing: torch (Cout,Cin,taps) fp32 -> operand layouts
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, float* __restrict__ wf,
                                     float* __restrict__ wd) {
@@ -291,8 +390,31 @@ int b200em_conv3d_direct(const void* x, int64_t x_ld, const float* in_scale_shif
     int tw = (W + TW - 1) / TW, th = (H + TH - 1) / TH, td = (D + TD - 1) / TD;
     dim3 grid((unsigned)(tw * th * td), (unsigned)((Cout + COT - 1) / COT), (unsigned)N);
     B2_DISPATCH_DTYPE(dtype, T, {
-        conv3d_direct_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, in_scale_shift, w, bias, (T*)y, y_ld,
-                                                                         sums, D, H, W, Cin, Cout, kd, kh, kw, relu, tw, th);
+        if (Cin < 4)
+            conv3d_direct_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, in_scale_shift, w, bias, (T*)y, y_ld,
+                                                                                sums, D, H, W, Cin, Cout, kd, kh, kw, relu, tw, th);
+        else
+            conv3d_direct_kernel<T, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, in_scale_shift, w, bias, (T*)y, y_ld,
+                                                                                sums, D, H, W, Cin, Cout, kd, kh, kw, relu, tw, th);
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_conv3d_wgrad_smallcin(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld,
+                                 int dtype, float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
+                                 int kw, void* stream) {
+    B2_CHECK_ARG(x && dz && dw && N > 0 && D > 0 && H > 0 && W > 0 && Cout > 0, "conv3d_wgrad_smallcin: bad arguments");
+    B2_CHECK_ARG(Cin >= 1 && Cin <= SC_MAXCIN, "conv3d_wgrad_smallcin: Cin must be in [1, %d], got %d", SC_MAXCIN, Cin);
+    B2_CHECK_ARG((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv3d_wgrad_smallcin: kernel dims must be 1 or 3");
+    int co_tiles = (Cout + COT - 1) / COT;
+    int64_t tiles = (int64_t)N * ((D + TD - 1) / TD) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+    int64_t per = (int64_t)sm_count() * 4 / co_tiles + 1;
+    if (per > tiles) per = tiles;
+    dim3 grid((unsigned)per, (unsigned)co_tiles, 1);
+    B2_DISPATCH_DTYPE(dtype, T, {
+        conv3d_wgrad_smallcin_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, in_scale_shift, (const T*)dz, dz_ld,
+                                                                                 dw, db, N, D, H, W, Cin, Cout, kd, kh, kw);
     })
     B2_LAUNCH_CHECK();
     return 0;

@@ -33,6 +33,53 @@ constexpr int THREADS = 320;
 constexpr int MAX_SMEM = 227 * 1024;
 }  // namespace
 
+
+// Haloed-tile operand load for 8-channel group `j`: voxels v = v0, v0+step, ... of an (nslices x HP x WP) tile.
+// Loads are issued in batches of LD_BATCH before any is consumed, so each thread keeps LD_BATCH 16-byte requests in
+// flight (the tile load is latency-bound otherwise: one dependent global load per iteration).
+constexpr int LD_BATCH = 8;
+
+__device__ __forceinline__ void load_halo_tile(const __nv_bfloat16* __restrict__ xn, long long x_ld, const float* sc, const float* sh,
+                                               bool affine, uint8_t* dst, int slice_stride_bytes, int v0, int step, int units,
+                                               int d0, int h0, int w0, int pd, int D, int H, int W) {
+    for (int vb = v0; vb < units; vb += LD_BATCH * step) {
+        uint4 val[LD_BATCH];
+        int off[LD_BATCH];
+        uint32_t inb = 0;
+#pragma unroll
+        for (int i = 0; i < LD_BATCH; ++i) {
+            const int v = vb + i * step;
+            val[i] = make_uint4(0, 0, 0, 0);
+            off[i] = -1;
+            if (v < units) {
+                const int wp_ = v % WP, hp_ = (v / WP) % HP, s = v / (WP * HP);
+                const int gd = d0 + s - pd, gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
+                off[i] = s * slice_stride_bytes + (hp_ * WP + wp_) * 16;
+                if (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
+                    val[i] = __ldg(reinterpret_cast<const uint4*>(xn + (((size_t)gd * H + gh) * W + gw) * x_ld));
+                    inb |= 1u << i;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < LD_BATCH; ++i) {
+            if (off[i] >= 0) {
+                if (affine && ((inb >> i) & 1)) {
+                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val[i]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float2 f = __bfloat1622float2(h2[e]);
+                        f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
+                        f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+                        h2[e] = __floats2bfloat162_rn(f.x, f.y);
+                    }
+                }
+                *reinterpret_cast<uint4*>(dst + off[i]) = val[i];
+            }
+        }
+    }
+}
+
 struct ConvUmmaParams {
     const __nv_bfloat16* x; long long x_ld;
     const float* in_ss;
@@ -70,6 +117,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
     uint64_t* acc_full = bars + 4 + 2 * NSTAGE;   // [2] tcgen05.commit
     uint64_t* acc_empty = acc_full + 2;           // [2] 128 epilogue arrivals
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint32_t* s_tap = s_tmem + 2;                   // [27] operand start offset of each tap, in 16-byte units
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = blockIdx.y;                    // 256-wide output-channel block (Cout > 256)
@@ -90,6 +138,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
         fence_mbar_init();
     }
     if (warp == 9) tmem_alloc(s_tmem, tmem_cols);
+    if (threadIdx.x < taps) {
+        const int tap = threadIdx.x;
+        const int a = tap / (p.kh * p.kw), b = (tap / p.kw) % p.kh, cc = tap % p.kw;
+        s_tap[tap] = (uint32_t)((a * J * PLANE + ((b + 1 - ph) * WP + (cc + 1 - pw)) * 16) >> 4);
+    }
     for (int i = threadIdx.x; i < p.NP; i += THREADS) {
         const int co = nblk * 256 + i;
         s_bias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
@@ -122,25 +175,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                 }
                 uint8_t* dstbase = smA + buf * p.a_bytes + j * PLANE;
                 const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
-                for (int v = t / J; v < units; v += 128 / J) {
-                    const int wp_ = v % WP, hp_ = (v / WP) % HP, s = v / (WP * HP);
-                    const int gd = d0 + s - pd, gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
-                    uint4 val = make_uint4(0, 0, 0, 0);
-                    if (gd >= 0 && gd < p.D && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
-                        val = *reinterpret_cast<const uint4*>(xn + (((size_t)gd * p.H + gh) * p.W + gw) * p.x_ld);
-                        if (p.in_ss) {
-                            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float2 f = __bfloat1622float2(h2[e]);
-                                f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
-                                f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
-                                h2[e] = __floats2bfloat162_rn(f.x, f.y);
-                            }
-                        }
-                    }
-                    *reinterpret_cast<uint4*>(dstbase + (size_t)s * J * PLANE + (hp_ * WP + wp_) * 16) = val;
-                }
+                load_halo_tile(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * PLANE, t / J, 128 / J, units, d0, h0, w0, pd,
+                               p.D, p.H, p.W);
                 fence_proxy_async();
                 mbar_arrive(&a_full[buf]);
             }
@@ -163,10 +199,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
+        // One thread issues every MMA, so the per-MMA instruction count is what bounds small-N layers: descriptors
+        // are built once and only their 14-bit start-address field is bumped (independent adds, fully unrolled).
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(128, p.NP);
-            const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
-            const uint32_t b_tap_bytes = (uint32_t)(J * p.NP * 16);
+            const uint32_t a_hi = (uint32_t)(make_desc(0, PLANE, WP * 16) >> 32);
+            const uint32_t b_hi = (uint32_t)(make_desc(0, (uint32_t)(p.NP * 16), 128) >> 32);
+            const uint32_t a_lo_c = (uint32_t)(make_desc(0, PLANE, WP * 16) & 0xFFFFFFFFu);   // LBO field (bits 16..29)
+            const uint32_t b_lo_c = (uint32_t)(make_desc(0, (uint32_t)(p.NP * 16), 128) & 0xFFFFFFFFu);
+            const uint32_t a_base16 = smem_u32(smA) >> 4, b_base16 = smem_u32(smB) >> 4;
+            const uint32_t b_tap16 = (uint32_t)(J * p.NP);
+            const uint32_t slab16 = (uint32_t)(J * (PLANE / 16)), k16 = (uint32_t)(2 * (PLANE / 16));
+            const uint32_t np = (uint32_t)p.NP;
             uint32_t fill = 0, cnt = 0, it = 0;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
                 int n, d0, h0, w0;
@@ -181,21 +225,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                     const int buf = fill & 1;
                     mbar_wait(&a_full[buf], (fill >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t abuf = a_base + buf * p.a_bytes;
+                    const uint32_t abuf16 = a_base16 + (uint32_t)((buf * p.a_bytes) >> 4);
                     for (int g = 0; g < ngroups; ++g, ++cnt) {
                         const int st = cnt % NSTAGE;
                         mbar_wait(&b_full[st], (cnt / NSTAGE) & 1);
                         tc_fence_after();
+                        const uint32_t bst16 = b_base16 + (uint32_t)((st * p.b_stage_bytes) >> 4);
                         for (int tg = 0; tg < p.G; ++tg) {
                             const int tap = g * p.G + tg;
-                            const int a = tap / (p.kh * p.kw), b = (tap / p.kw) % p.kh, cc = tap % p.kw;
-                            const uint32_t aoff = (uint32_t)(((b + 1 - ph) * WP + (cc + 1 - pw)) * 16);
-                            const uint32_t bsm = b_base + st * p.b_stage_bytes + tg * b_tap_bytes;
-                            for (int r = 0; r < rmax; ++r) {
-                                for (int k = 0; k < kc; ++k) {
-                                    const uint64_t adesc = make_desc(abuf + (uint32_t)(((r + a) * J + 2 * k) * PLANE) + aoff, PLANE, WP * 16);
-                                    const uint64_t bdesc = make_desc(bsm + (uint32_t)(2 * k * p.NP * 16), (uint32_t)(p.NP * 16), 128);
-                                    umma_bf16(tacc + r * p.NP, adesc, bdesc, idesc, (c | tap | k) != 0);
+                            const uint32_t a0 = a_lo_c + abuf16 + s_tap[tap];
+                            const uint32_t b0 = b_lo_c + bst16 + tg * b_tap16;
+                            const uint32_t acc0 = (uint32_t)(c | tap);
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                if (r < rmax) {
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k) {
+                                        if (k < kc) {
+                                            const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a0 + r * slab16 + k * k16);
+                                            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b0 + k * 2 * np);
+                                            umma_bf16(tacc + r * np, adesc, bdesc, idesc, acc0 | (uint32_t)k);
+                                        }
+                                    }
                                 }
                             }
                         }
@@ -353,7 +404,7 @@ static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s) 
         s.R = R;
         s.acc_bufs = (2 * R * s.NP <= 512) ? 2 : 1;
         s.a_bytes = (R + kd - 1) * J * PLANE;
-        s.smem_bytes = 2 * s.a_bytes + NSTAGE * s.b_stage_bytes + s.NP * 4 * 3 + 16 * 8 + 16 + 128;
+        s.smem_bytes = 2 * s.a_bytes + NSTAGE * s.b_stage_bytes + s.NP * 4 * 3 + 16 * 8 + 16 + 27 * 4 + 128;
         if (s.smem_bytes <= MAX_SMEM) return true;
     }
     return false;
@@ -403,6 +454,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
     uint64_t* empty = bars + 2;       // [2] tcgen05.commit
     uint64_t* acc_full = bars + 4;    // [1]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
+    uint32_t* s_tap9 = s_tmem + 2;    // [9] (b, c) tap offset within the haloed tile, 16-byte units
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.y / p.nco, cob = blockIdx.y % p.nco;
@@ -418,6 +470,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
         fence_mbar_init();
     }
     if (warp == 9) tmem_alloc(s_tmem, tmem_cols);
+    if (threadIdx.x < tap9) {
+        const int b = threadIdx.x / p.kw, cc = threadIdx.x % p.kw;
+        s_tap9[threadIdx.x] = (uint32_t)((b + 1 - ph) * WP + (cc + 1 - pw));
+    }
     for (int i = threadIdx.x; i < p.NB; i += THREADS) s_db[i] = 0.f;
     // the over-read region must hold finite-or-not garbage only in rows that are ignored; zero it once anyway
     for (int i = threadIdx.x; i < 4 * J * PLANE / 16; i += THREADS)
@@ -458,44 +514,42 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
             }
             uint8_t* xdst = smX + buf * p.x_bytes + j * PLANE;
             const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
-            for (int v = t / J; v < xunits; v += 128 / J) {
-                const int wp_ = v % WP, hp_ = (v / WP) % HP, s = v / (WP * HP);
-                const int gd = d0 + s - pd, gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
-                uint4 val = make_uint4(0, 0, 0, 0);
-                if (gd >= 0 && gd < p.D && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
-                    val = *reinterpret_cast<const uint4*>(xn + (((size_t)gd * p.H + gh) * p.W + gw) * p.x_ld);
-                    if (p.in_ss) {
-                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float2 f = __bfloat1622float2(h2[e]);
-                            f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
-                            f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
-                            h2[e] = __floats2bfloat162_rn(f.x, f.y);
-                        }
-                    }
-                }
-                *reinterpret_cast<uint4*>(xdst + (size_t)s * J * PLANE + (hp_ * WP + wp_) * 16) = val;
-            }
+            load_halo_tile(xn, p.x_ld, sc, sh, p.in_ss != nullptr, xdst, J * PLANE, t / J, 128 / J, xunits, d0, h0, w0, pd,
+                           p.D, p.H, p.W);
             uint8_t* zdst = smZ + buf * p.dz_bytes + jo * WG_DZ_PLANE;
             const __nv_bfloat16* zn = p.dz + (size_t)n * p.D * p.H * p.W * p.dz_ld + cob * p.NB + jo * 8;
-            for (int v = t / JO; v < zunits; v += 128 / JO) {
-                const int wl = v % TW, hl = (v / TW) % TH, r = v / (TW * TH);
-                const int gd = d0 + r, gh = h0 + hl, gw = w0 + wl;
-                uint4 val = make_uint4(0, 0, 0, 0);
-                if (gd < p.D && gh < p.H && gw < p.W) {
-                    val = *reinterpret_cast<const uint4*>(zn + (((size_t)gd * p.H + gh) * p.W + gw) * p.dz_ld);
-                    if (p.db && chunk == 0) {
-                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+            const int zstep = 128 / JO;
+            for (int vb = t / JO; vb < zunits; vb += LD_BATCH * zstep) {
+                uint4 val[LD_BATCH];
+                int off[LD_BATCH];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float2 f = __bfloat1622float2(h2[e]);
-                            dbacc[2 * e] += f.x;
-                            dbacc[2 * e + 1] += f.y;
-                        }
+                for (int i = 0; i < LD_BATCH; ++i) {
+                    const int v = vb + i * zstep;
+                    val[i] = make_uint4(0, 0, 0, 0);
+                    off[i] = -1;
+                    if (v < zunits) {
+                        const int wl = v % TW, hl = (v / TW) % TH, r = v / (TW * TH);
+                        const int gd = d0 + r, gh = h0 + hl, gw = w0 + wl;
+                        off[i] = r * JO * WG_DZ_PLANE + (hl * TW + wl) * 16;
+                        if (gd < p.D && gh < p.H && gw < p.W)
+                            val[i] = __ldg(reinterpret_cast<const uint4*>(zn + (((size_t)gd * p.H + gh) * p.W + gw) * p.dz_ld));
                     }
                 }
-                *reinterpret_cast<uint4*>(zdst + (size_t)r * JO * WG_DZ_PLANE + (hl * TW + wl) * 16) = val;
+#pragma unroll
+                for (int i = 0; i < LD_BATCH; ++i) {
+                    if (off[i] >= 0) {
+                        if (p.db && chunk == 0) {
+                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val[i]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 f = __bfloat1622float2(h2[e]);
+                                dbacc[2 * e] += f.x;
+                                dbacc[2 * e + 1] += f.y;
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(zdst + off[i]) = val[i];
+                    }
+                }
             }
             fence_proxy_async();
             mbar_arrive(&full[buf]);
@@ -510,7 +564,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
         // ===================== MMA issuer =====================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(128, p.NB, 1, 1);      // both operands MN-major
-            const uint32_t x_base = smem_u32(smX), z_base = smem_u32(smZ);
+            // A: LBO = next 8 voxels (next tile row), SBO = next 8 channels (next plane); B likewise on the dz slab
+            const uint64_t ad = make_desc(0, WP * 16, PLANE), bd = make_desc(0, TW * 16, WG_DZ_PLANE);
+            const uint32_t a_hi = (uint32_t)(ad >> 32), a_lo_c = (uint32_t)(ad & 0xFFFFFFFFu);
+            const uint32_t b_hi = (uint32_t)(bd >> 32), b_lo_c = (uint32_t)(bd & 0xFFFFFFFFu);
+            const uint32_t x_base16 = smem_u32(smX) >> 4, z_base16 = smem_u32(smZ) >> 4;
+            const uint32_t nb = (uint32_t)p.NB;
             uint32_t fill = 0;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++fill) {
                 int n, d0, h0, w0;
@@ -520,16 +579,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
                 tc_fence_after();
                 const int rmax = min(WG_R, p.D - d0);
                 for (int r = 0; r < rmax; ++r) {
-                    const uint32_t xs = x_base + buf * p.x_bytes + (uint32_t)(r * J * PLANE);
-                    const uint32_t zs = z_base + buf * p.dz_bytes + (uint32_t)(r * JO * WG_DZ_PLANE);
+                    const uint32_t xs = a_lo_c + x_base16 + (uint32_t)((buf * p.x_bytes + r * J * PLANE) >> 4);
+                    const uint32_t zs = b_lo_c + z_base16 + (uint32_t)((buf * p.dz_bytes + r * JO * WG_DZ_PLANE) >> 4);
+                    const uint32_t acc0 = fill | (uint32_t)r;
                     for (int tp = 0; tp < tap9; ++tp) {
-                        const int b = tp / p.kw, cc = tp % p.kw;
+                        const uint32_t a0 = xs + s_tap9[tp];
+                        const uint32_t tacc = tmem_base + tp * nb;
+#pragma unroll
                         for (int ks = 0; ks < TH / 2; ++ks) {
                             // K step = voxel rows hl = 2ks, 2ks+1 (8 voxels each)
-                            const uint32_t aaddr = xs + (uint32_t)(((2 * ks + b + 1 - ph) * WP + (cc + 1 - pw)) * 16);
-                            const uint64_t adesc = make_desc(aaddr, WP * 16, PLANE);          // LBO: next 8 voxels, SBO: next 8 channels
-                            const uint64_t bdesc = make_desc(zs + (uint32_t)(2 * ks * TW * 16), TW * 16, WG_DZ_PLANE);
-                            umma_bf16(tmem_base + tp * p.NB, adesc, bdesc, idesc, (fill | (uint32_t)r | (uint32_t)ks) != 0);
+                            const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a0 + ks * 2 * WP);
+                            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(zs + ks * 2 * TW);
+                            umma_bf16(tacc, adesc, bdesc, idesc, acc0 | (uint32_t)ks);
                         }
                     }
                 }
@@ -656,7 +717,7 @@ int b200em_conv3d_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
     p.x_bytes = (WG_R + kd - 1) * 4 * PLANE;
     p.dz_bytes = WG_R * (NB / 8) * WG_DZ_PLANE;
-    const int smem_bytes = 2 * p.x_bytes + 4 * 4 * PLANE + 2 * p.dz_bytes + NB * 4 + 8 * 8 + 16 + 128;
+    const int smem_bytes = 2 * p.x_bytes + 4 * 4 * PLANE + 2 * p.dz_bytes + NB * 4 + 8 * 8 + 16 + 9 * 4 + 128;
     B2_CHECK_ARG(smem_bytes <= MAX_SMEM, "conv3d_wgrad_umma: shared memory budget exceeded");
     B2_CUDA(cudaFuncSetAttribute(conv3d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     const int pairs = (Cin / 32) * p.nco;
