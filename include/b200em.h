@@ -97,6 +97,11 @@ int b200em_conv3d_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_
                              float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw,
                              void* stream);
 
+/* im2col of the first conv (thin K = taps*Cin): out (N,D,H,W,Kp) bf16 with out[vox][tap*Cin+ci] = x_hat[vox+tap][ci], zero in
+ * the padding and for channels >= taps*Cin.  The conv is then a 1x1x1 conv with Kp input channels on the tcgen05 path. */
+int b200em_im2col_taps(const void* x, int64_t x_ld, const float* in_scale_shift, int dtype, void* out, int N, int D, int H,
+                       int W, int Cin, int kd, int kh, int kw, int Kp, void* stream);
+
 /* ---- normalisation: nn.InstanceNorm3d(C) / nn.GroupNorm(min(32,C),C)  (unet.py:391-406) ------------------- */
 /* sums[N][C][2] += (sum x, sum x^2) over the S voxels of each sample. */
 int b200em_channel_sums(const void* x, int64_t x_ld, int dtype, int N, int64_t S, int C, float* sums, void* stream);

@@ -106,3 +106,31 @@ def test_umma_wgrad(B, case):
         torch.cuda.synchronize()
         np.testing.assert_allclose(dw.cpu().numpy() - 0.5, dw_ref.numpy(), rtol=2e-3, atol=2e-3 * float(dw_ref.abs().max()))
         np.testing.assert_allclose(db.cpu().numpy() + 1.0, db_ref.numpy(), rtol=2e-3, atol=2e-3 * float(db_ref.abs().max()))
+
+
+@pytest.mark.parametrize("case", [(2, 6, 20, 13, 1, 32, (3, 3, 3)), (1, 4, 16, 16, 2, 16, (3, 3, 3)), (1, 3, 18, 9, 1, 64, (1, 3, 3))])
+def test_thin_k_first_conv(B, case):
+    """First conv (Cin <= 4): im2col + 1x1x1 tcgen05 conv, forward and weight gradient."""
+    N, D, H, W, Cin, Cout, k = case
+    x = rnd((N, D, H, W, Cin), 21).bfloat16()
+    w = rnd((Cout, Cin) + k, 22, scale=0.2)
+    b = rnd((Cout,), 23)
+    ss = torch.stack([1 + 0.1 * rnd((N, Cin), 24), 0.1 * rnd((N, Cin), 25)], -1).contiguous()
+    pk = B.pack(("thin-test", case), w.to(DEV))
+    assert pk.thin is not None
+    xin = (x.float() * ss[:, None, None, None, :, 0] + ss[:, None, None, None, :, 1]).bfloat16()
+    y_ref = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16); s_ref = torch.zeros((N, Cout, 2))
+    EMU.conv(xin, None, P(w.bfloat16().float()), b, y_ref, s_ref, k, True, False)
+    y = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=DEV); s = torch.zeros((N, Cout, 2), device=DEV)
+    B.conv(x.to(DEV), ss.to(DEV), pk, b.to(DEV), y, s, k, True, False)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(y.float().cpu().numpy(), y_ref.float().numpy(), rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(s.cpu().numpy(), s_ref.numpy(), rtol=5e-3, atol=0.5)
+    dz = rnd((N, D, H, W, Cout), 26).bfloat16()
+    dw_ref, db_ref = torch.zeros((Cout, Cin) + k), torch.zeros(Cout)
+    EMU.wgrad(xin, None, dz, dw_ref, db_ref, k)
+    dw, db = torch.zeros((Cout, Cin) + k, device=DEV), torch.zeros(Cout, device=DEV)
+    B.wgrad(x.to(DEV), ss.to(DEV), dz.to(DEV), dw, db, k)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(dw.cpu().numpy(), dw_ref.numpy(), rtol=2e-3, atol=2e-3 * float(dw_ref.abs().max()))
+    np.testing.assert_allclose(db.cpu().numpy(), db_ref.numpy(), rtol=2e-3, atol=2e-3 * float(db_ref.abs().max()))

@@ -48,7 +48,8 @@ def _f32(t):
 
 class WeightPack:
     """Kernel-operand copies of one conv weight (derived caches; the fp32 nn.Parameter stays the master)."""
-    __slots__ = ("w_fwd_f32", "w_dgrad_f32", "umma_fwd", "umma_dgrad", "version", "ptr", "cout", "cin", "kernel")
+    __slots__ = ("w_fwd_f32", "w_dgrad_f32", "umma_fwd", "umma_dgrad", "version", "ptr", "cout", "cin", "kernel", "thin",
+                 "thin_kp")
 
 
 class CudaBackend:
@@ -97,7 +98,8 @@ class CudaBackend:
         taps = kd * kh * kw
         pk.w_fwd_f32 = torch.empty((taps, cin, cout), dtype=torch.float32, device=w.device)
         pk.w_dgrad_f32 = torch.empty((taps, cout, cin), dtype=torch.float32, device=w.device)
-        pk.umma_fwd = pk.umma_dgrad = None
+        pk.umma_fwd = pk.umma_dgrad = pk.thin = None
+        pk.thin_kp = 0
         lib = _lib.load()
         with torch.cuda.device(w.device):
             call("b200em_pack_conv_weights", _ptr(wd), cout, cin, kd, kh, kw, _ptr(pk.w_fwd_f32), _ptr(pk.w_dgrad_f32),
@@ -108,6 +110,14 @@ class CudaBackend:
             if self.use_umma and lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
                 pk.umma_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.umma_dgrad), _stream(w))
+            kp = -(-taps * cin // 32) * 32
+            if self.use_umma and cin <= 4 and lib.b200em_conv3d_umma_supported(kp, cout, 1, 1, 1):
+                # thin-K first conv: W'[co][tap*Cin+ci] = W[co][ci][tap], zero padded to Kp channels (im2col layout)
+                wt = torch.zeros((cout, kp), dtype=torch.float32, device=w.device)
+                wt[:, :taps * cin] = wd.reshape(cout, cin, taps).permute(0, 2, 1).reshape(cout, taps * cin)
+                pk.thin = torch.empty(cout * kp, dtype=torch.bfloat16, device=w.device)
+                pk.thin_kp = kp
+                call("b200em_conv3d_umma_pack", _ptr(wt), cout, kp, 1, 1, 1, 0, _ptr(pk.thin), _stream(w))
         self._pack_cache[key] = pk
         return pk
 
@@ -166,6 +176,12 @@ class CudaBackend:
         b = bias.detach() if bias is not None else None
         kd, kh, kw = kernel
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
+        if (not dgrad) and pack.thin is not None and x.dtype == torch.bfloat16 and yld % 8 == 0 and y.data_ptr() % 16 == 0:
+            cols = self.im2col(x, in_ss, kernel, pack.thin_kp)
+            self._timed("conv_umma_fwd", flops, lambda: call(
+                "b200em_conv3d_umma", _ptr(cols), pack.thin_kp, None, _ptr(pack.thin), _f32(b), yp, yld, _f32(sums), N, D, H, W,
+                pack.thin_kp, Cout, 1, 1, 1, int(relu), _stream(x)))
+            return
         wu = pack.umma_dgrad if dgrad else pack.umma_fwd
         if wu is not None and x.dtype == torch.bfloat16 and xld % 8 == 0 and yld % 8 == 0 and \
                 x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
@@ -177,6 +193,15 @@ class CudaBackend:
             "b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, _f32(sums), _dt(x), N, D, H, W, Cin,
             Cout, kd, kh, kw, int(relu), _stream(x)))
 
+    def im2col(self, x, in_ss, kernel, kp):
+        """(N,D,H,W,Cin<=4) -> (N,D,H,W,kp) bf16 im2col of the first conv's taps, with the norm apply fused."""
+        N, D, H, W, Cin = x.shape
+        xp, xld = _act(x)
+        cols = torch.empty((N, D, H, W, kp), dtype=torch.bfloat16, device=x.device)
+        kd, kh, kw = kernel
+        call("b200em_im2col_taps", xp, xld, _f32(in_ss), _dt(x), _ptr(cols), N, D, H, W, Cin, kd, kh, kw, kp, _stream(x))
+        return cols
+
     def wgrad(self, x, in_ss, dz, dw, db, kernel):
         """dw += sum dz * norm(x) shifted by the taps;  db (nullable) += sum dz  (weight and bias gradient)."""
         N, D, H, W, Cin = x.shape
@@ -185,6 +210,17 @@ class CudaBackend:
         zp, zld = _act(dz)
         kd, kh, kw = kernel
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
+        taps = kd * kh * kw
+        kp = -(-taps * Cin // 32) * 32
+        if self.use_umma and Cin <= 4 and x.dtype == torch.bfloat16 and zld % 8 == 0 and dz.data_ptr() % 16 == 0 and \
+                _lib.load().b200em_conv3d_wgrad_umma_supported(kp, Cout, 1, 1, 1):
+            cols = self.im2col(x, in_ss, kernel, kp)
+            dwt = torch.zeros((Cout, kp), dtype=torch.float32, device=x.device)
+            self._timed("conv_umma_wgrad", flops, lambda: call(
+                "b200em_conv3d_wgrad_umma", _ptr(cols), kp, None, zp, zld, _f32(dwt), _f32(db), N, D, H, W, kp, Cout, 1, 1, 1,
+                _stream(x)))
+            dw += dwt[:, :taps * Cin].reshape(Cout, taps, Cin).permute(0, 2, 1).reshape(dw.shape)
+            return
         if self.use_umma and x.dtype == torch.bfloat16 and xld % 8 == 0 and zld % 8 == 0 and x.data_ptr() % 16 == 0 and \
                 dz.data_ptr() % 16 == 0 and _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw):
             self._timed("conv_umma_wgrad", flops, lambda: call(

@@ -415,6 +415,46 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, T* 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// im2col of the network's first conv (Cin <= 4): out[vox][tap*Cin + ci] = x_hat[vox + tap][ci] (0 in the padding and in
+// the channels >= taps*Cin), bf16, Kp channels per voxel.  Turns the K = 27*Cin conv -- too thin for an implicit GEMM
+// -- into a 1x1x1 conv with K = Kp that the tcgen05 kernels take (forward AND weight gradient).  HBM-bound: reads x
+// once (neighbours hit L1/L2), writes Kp bf16 per voxel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_taps_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ in_ss, __nv_bfloat16* __restrict__ out,
+                   int D, int H, int W, int Cin, int kd, int kh, int kw, int Kp, int64_t total) {
+    const int pd = kd / 2, ph = kh / 2, pw = kw / 2;
+    const int64_t S = (int64_t)D * H * W;
+    const int groups = Kp / 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const int64_t vox = i / groups;
+        const int64_t n = vox / S, s = vox % S;
+        const int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = g * 8 + e;
+            float r = 0.f;
+            if (k < kd * kh * kw * Cin) {
+                const int ci = k % Cin, tp = k / Cin;
+                const int a = tp / (kh * kw), b = (tp / kw) % kh, c = tp % kw;
+                const int gd = d + a - pd, gh = h + b - ph, gw = w + c - pw;
+                if (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
+                    r = to_f<T>(x[((n * D + gd) * H + gh) * (int64_t)W * x_ld + (int64_t)gw * x_ld + ci]);
+                    if (in_ss) {
+                        const float* p = in_ss + ((size_t)n * Cin + ci) * 2;
+                        r = fmaf(r, p[0], p[1]);
+                    }
+                }
+            }
+            v[e] = r;
+        }
+        Vec<__nv_bfloat16, 8>::store(out + vox * Kp + g * 8, v);
+    }
+}
+
 static inline int flat_grid(int64_t total, int threads) {
     int64_t b = (total + threads - 1) / threads;
     int64_t cap = (int64_t)sm_count() * 16;
@@ -615,6 +655,20 @@ int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, void* dx, int64
             int64_t total = (int64_t)N * Si * C;
             upsample_bwd_kernel<T, 1><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, fd, fh, fw, total);
         }
+    })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_im2col_taps(const void* x, int64_t x_ld, const float* in_scale_shift, int dtype, void* out, int N, int D, int H, int W,
+                       int Cin, int kd, int kh, int kw, int Kp, void* stream) {
+    B2_CHECK_ARG(x && out && N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0, "im2col_taps: bad arguments");
+    B2_CHECK_ARG(Kp % 8 == 0 && Kp >= kd * kh * kw * Cin, "im2col_taps: Kp must be a multiple of 8 and >= taps*Cin");
+    B2_CHECK_ARG(aligned16(out), "im2col_taps: output must be 16-byte aligned");
+    int64_t total = (int64_t)N * D * H * W * (Kp / 8);
+    B2_DISPATCH_DTYPE(dtype, T, {
+        im2col_taps_kernel<T><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, in_scale_shift,
+                                                                                       (__nv_bfloat16*)out, D, H, W, Cin, kd, kh, kw, Kp, total);
     })
     B2_LAUNCH_CHECK();
     return 0;
