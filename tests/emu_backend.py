@@ -101,8 +101,9 @@ class TorchEmuBackend:
         y.copy_(r.permute(0, 2, 3, 4, 1))
         if sums is not None:
             self.channel_sums(y, sums)
+        return None
 
-    def wgrad(self, x, in_ss, dz, dw, db, kernel):
+    def wgrad(self, x, in_ss, dz, dw, db, kernel, aux=None):
         pad = tuple(k // 2 for k in kernel)
         xh = self._xhat(x, in_ss).contiguous()
         dw += torch.nn.grad.conv3d_weight(xh, dw.shape, _ncdhw(dz.float()).contiguous(), padding=pad)

@@ -42,8 +42,9 @@ def test_fp32_matches_reference_golden(golden_dir, name):
 def test_bf16_autocast_no_worse_than_reference_autocast(norm):
     """bf16 has no exact answer: the yardstick is the fp32 oracle, and the bar is the error the reference's OWN bf16
     autocast run (same functional graph through cuDNN/ATen on this GPU) makes against it.  Ours must be within
-    1.25x of that error on the prediction; per parameter gradient (those not identically ~0) the error ratio
-    ours / reference-autocast must have a median <= 1.1 and a maximum <= 2 (both are bf16 rounding noise)."""
+    1.25x of that error on the prediction; per parameter gradient the absolute error must be <= 2x the reference
+    autocast's (+ a floor of 5e-3 of the largest gradient norm: we keep the network input in bf16, the
+    reference's first norm sees it in fp32) and the median error ratio <= 1.1."""
     torch.manual_seed(0)
     kw = dict(in_channels=1, out_channels=2, depth=3, initial_features=16, final_activation="Sigmoid", norm=norm)
     net = tb.UNet3d(**kw).to(DEV)
@@ -68,17 +69,21 @@ def test_bf16_autocast_no_worse_than_reference_autocast(norm):
     assert rel(y, y_ref) < 2e-2                                   # relative L2 <= 1e-2..2e-2
     assert rel(y, y_ref) <= 1.25 * rel(y_ac, y_ref) + 1e-3
     assert abs(loss.item() - l_ref.item()) < 1e-2 * abs(l_ref.item())
+    # Per parameter: absolute error (L2) against the fp32 gradient, in units of the largest parameter-gradient norm.
+    # (Relative error is meaningless for gradients that are differences of large terms -- e.g. a conv bias or a norm
+    # scale sitting in front of conv -> norm is ~0 in exact arithmetic.)
     gmax = max(float(v.grad.norm()) for v in sd.values())
+
+    def err(a, b):
+        return float((a.detach().float().cpu() - b.detach()).norm()) / gmax
+
     ratios = {}
     for k, p in net.named_parameters():
-        ref = sd[k].grad
-        if float(ref.norm()) < 1e-3 * gmax:                       # e.g. a conv bias in front of InstanceNorm: exactly 0
-            continue
-        ratios[k] = (rel(p.grad, ref), rel(sdg[k].grad, ref))
-    r = sorted(a / (b + 1e-2) for a, b in ratios.values())
+        e_ours, e_ref = err(p.grad, sd[k].grad), err(sdg[k].grad, sd[k].grad)
+        ratios[k] = (e_ours, e_ref)
+        assert e_ours <= 2.0 * e_ref + 5e-3, (k, e_ours, e_ref)
+    r = sorted(a / (b + 1e-4) for a, b in ratios.values())
     assert r[len(r) // 2] <= 1.1, ("median error ratio vs reference autocast", r[len(r) // 2])
-    worst = max(ratios, key=lambda k: ratios[k][0] / (ratios[k][1] + 1e-2))
-    assert r[-1] <= 2.0, (worst, ratios[worst])
 
 
 def test_fp16_autocast_is_refused():

@@ -181,14 +181,14 @@ class CudaBackend:
             self._timed("conv_umma_fwd", flops, lambda: call(
                 "b200em_conv3d_umma", _ptr(cols), pack.thin_kp, None, _ptr(pack.thin), _f32(b), yp, yld, _f32(sums), N, D, H, W,
                 pack.thin_kp, Cout, 1, 1, 1, int(relu), _stream(x)))
-            return
+            return cols       # kept by the schedule for the weight gradient of the same conv
         wu = pack.umma_dgrad if dgrad else pack.umma_fwd
         if wu is not None and x.dtype == torch.bfloat16 and xld % 8 == 0 and yld % 8 == 0 and \
                 x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
             self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
                 "b200em_conv3d_umma", xp, xld, _f32(in_ss), _ptr(wu), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cin, Cout,
                 kd, kh, kw, int(relu), _stream(x)))
-            return
+            return None
         self._timed("conv_direct_dgrad" if dgrad else "conv_direct_fwd", flops, lambda: call(
             "b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, _f32(sums), _dt(x), N, D, H, W, Cin,
             Cout, kd, kh, kw, int(relu), _stream(x)))
@@ -202,8 +202,9 @@ class CudaBackend:
         call("b200em_im2col_taps", xp, xld, _f32(in_ss), _dt(x), _ptr(cols), N, D, H, W, Cin, kd, kh, kw, kp, _stream(x))
         return cols
 
-    def wgrad(self, x, in_ss, dz, dw, db, kernel):
-        """dw += sum dz * norm(x) shifted by the taps;  db (nullable) += sum dz  (weight and bias gradient)."""
+    def wgrad(self, x, in_ss, dz, dw, db, kernel, aux=None):
+        """dw += sum dz * norm(x) shifted by the taps;  db (nullable) += sum dz  (weight and bias gradient).
+        aux: what conv() returned for the same (x, in_ss) in the forward pass (the first conv's im2col), or None."""
         N, D, H, W, Cin = x.shape
         Cout = dz.shape[4]
         xp, xld = _act(x)
@@ -214,7 +215,7 @@ class CudaBackend:
         kp = -(-taps * Cin // 32) * 32
         if self.use_umma and Cin <= 4 and x.dtype == torch.bfloat16 and zld % 8 == 0 and dz.data_ptr() % 16 == 0 and \
                 _lib.load().b200em_conv3d_wgrad_umma_supported(kp, Cout, 1, 1, 1):
-            cols = self.im2col(x, in_ss, kernel, kp)
+            cols = aux if aux is not None else self.im2col(x, in_ss, kernel, kp)
             dwt = torch.zeros((Cout, kp), dtype=torch.float32, device=x.device)
             self._timed("conv_umma_wgrad", flops, lambda: call(
                 "b200em_conv3d_wgrad_umma", _ptr(cols), kp, None, zp, zld, _f32(dwt), _f32(db), N, D, H, W, kp, Cout, 1, 1, 1,

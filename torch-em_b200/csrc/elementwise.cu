@@ -420,30 +420,38 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, T* 
 // the channels >= taps*Cin), bf16, Kp channels per voxel.  Turns the K = 27*Cin conv -- too thin for an implicit GEMM
 // -- into a 1x1x1 conv with K = Kp that the tcgen05 kernels take (forward AND weight gradient).  HBM-bound: reads x
 // once (neighbours hit L1/L2), writes Kp bf16 per voxel.
-template <typename T>
+// CIN/KD/KH/KW > 0: compile-time filter shape (tap decode becomes constant division); 0: runtime values.
+template <typename T, int CIN, int KD, int KH, int KW>
 __global__ void __launch_bounds__(256)
 im2col_taps_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ in_ss, __nv_bfloat16* __restrict__ out,
-                   int D, int H, int W, int Cin, int kd, int kh, int kw, int Kp, int64_t total) {
+                   int D, int H, int W, int Cin_, int kd_, int kh_, int kw_, int Kp, int64_t total) {
+    const int Cin = CIN > 0 ? CIN : Cin_, kd = KD > 0 ? KD : kd_, kh = KH > 0 ? KH : kh_, kw = KW > 0 ? KW : kw_;
     const int pd = kd / 2, ph = kh / 2, pw = kw / 2;
     const int64_t S = (int64_t)D * H * W;
     const int groups = Kp / 8;
+    const int kmax = kd * kh * kw * Cin;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int g = (int)(i % groups);
         const int64_t vox = i / groups;
         const int64_t n = vox / S, s = vox % S;
         const int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+        const T* xn = x + n * S * x_ld;
+        float sc = 1.f, sh = 0.f;
+        if (CIN == 1 && in_ss) { sc = in_ss[n * 2]; sh = in_ss[n * 2 + 1]; }
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int k = g * 8 + e;
             float r = 0.f;
-            if (k < kd * kh * kw * Cin) {
+            if (k < kmax) {
                 const int ci = k % Cin, tp = k / Cin;
                 const int a = tp / (kh * kw), b = (tp / kw) % kh, c = tp % kw;
                 const int gd = d + a - pd, gh = h + b - ph, gw = w + c - pw;
                 if (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
-                    r = to_f<T>(x[((n * D + gd) * H + gh) * (int64_t)W * x_ld + (int64_t)gw * x_ld + ci]);
-                    if (in_ss) {
+                    r = to_f<T>(xn[(((int64_t)gd * H + gh) * W + gw) * x_ld + ci]);
+                    if (CIN == 1) {
+                        r = fmaf(r, sc, sh);
+                    } else if (in_ss) {
                         const float* p = in_ss + ((size_t)n * Cin + ci) * 2;
                         r = fmaf(r, p[0], p[1]);
                     }
@@ -667,8 +675,14 @@ int b200em_im2col_taps(const void* x, int64_t x_ld, const float* in_scale_shift,
     B2_CHECK_ARG(aligned16(out), "im2col_taps: output must be 16-byte aligned");
     int64_t total = (int64_t)N * D * H * W * (Kp / 8);
     B2_DISPATCH_DTYPE(dtype, T, {
-        im2col_taps_kernel<T><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, in_scale_shift,
-                                                                                       (__nv_bfloat16*)out, D, H, W, Cin, kd, kh, kw, Kp, total);
+        const int grid = flat_grid(total, 256);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (Cin == 1 && kd == 3 && kh == 3 && kw == 3)
+            im2col_taps_kernel<T, 1, 3, 3, 3><<<grid, 256, 0, st>>>((const T*)x, x_ld, in_scale_shift, (__nv_bfloat16*)out, D, H, W, Cin, kd, kh, kw, Kp, total);
+        else if (Cin == 1 && kd == 1 && kh == 3 && kw == 3)
+            im2col_taps_kernel<T, 1, 1, 3, 3><<<grid, 256, 0, st>>>((const T*)x, x_ld, in_scale_shift, (__nv_bfloat16*)out, D, H, W, Cin, kd, kh, kw, Kp, total);
+        else
+            im2col_taps_kernel<T, 0, 0, 0, 0><<<grid, 256, 0, st>>>((const T*)x, x_ld, in_scale_shift, (__nv_bfloat16*)out, D, H, W, Cin, kd, kh, kw, Kp, total);
     })
     B2_LAUNCH_CHECK();
     return 0;

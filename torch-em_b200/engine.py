@@ -148,7 +148,7 @@ def _run_block(B, plan, P, spec: BlockSpec, x_in, sums_in, out, want_out_sums, c
         ss1, mr1 = B.norm_finalize(sums_in, S, _groups(norm, c1.cin), g1, b1, EPS)
     y1 = torch.empty((N, D, H, W, c1.cout), dtype=x_in.dtype, device=dev)
     sums1 = torch.zeros((N, c1.cout, 2), dtype=torch.float32, device=dev) if norm is not None else None
-    B.conv(x_in, ss1, packs[c1.key], P[c1.key + ".bias"], y1, sums1, c1.kernel, relu=True, dgrad=False)
+    aux1 = B.conv(x_in, ss1, packs[c1.key], P[c1.key + ".bias"], y1, sums1, c1.kernel, relu=True, dgrad=False)
     if norm is not None:
         g2 = P[spec.norm2_key + ".weight"] if spec.norm2_key else None
         b2 = P[spec.norm2_key + ".bias"] if spec.norm2_key else None
@@ -157,7 +157,7 @@ def _run_block(B, plan, P, spec: BlockSpec, x_in, sums_in, out, want_out_sums, c
     if want_out_sums and norm is not None:
         sums2 = torch.zeros((N, c2.cout, 2), dtype=torch.float32, device=dev)
     B.conv(y1, ss2, packs[c2.key], P[c2.key + ".bias"], out, sums2, c2.kernel, relu=True, dgrad=False)
-    rec.update(ss1=ss1, mr1=mr1, y1=y1, ss2=ss2, mr2=mr2, y2=out)
+    rec.update(ss1=ss1, mr1=mr1, y1=y1, ss2=ss2, mr2=mr2, y2=out, aux1=aux1)
     ctx.blocks[spec.prefix] = rec
     return sums2
 
@@ -264,7 +264,7 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
     norm_back(g2, y1, rec["mr2"], spec.norm2_key, c2.cin, dz1, relu_mask=1)
     del g2
     # conv1
-    B.wgrad(x_in, rec["ss1"], dz1, grads[c1.key + ".weight"], grads[c1.key + ".bias"], c1.kernel)
+    B.wgrad(x_in, rec["ss1"], dz1, grads[c1.key + ".weight"], grads[c1.key + ".bias"], c1.kernel, aux=rec.get("aux1"))
     if not need_dx:
         return None
     g1 = torch.empty(x_in.shape, dtype=x_in.dtype, device=dev)
