@@ -89,6 +89,16 @@ int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift,
                        void* y, int64_t y_ld, float* sums, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
                        int kw, int relu, void* stream);
 
+/* "w-stacked" tcgen05 variant for layers with few output channels (Cout <= 80, kw == 3): the three w-taps share one
+ * operand fetch (N = 3*Cout), shifted sum in the epilogue (csrc/conv_umma_s3.cu).  Same contract and arguments as
+ * b200em_conv3d_umma; its own packed weight layout (b200em_conv3d_umma_s3_pack, Cout*Cin*taps bf16). */
+int b200em_conv3d_umma_s3_supported(int Cin, int Cout, int kd, int kh, int kw);
+int b200em_conv3d_umma_s3_pack(const float* w, int Cout, int Cin, int kd, int kh, int kw, int dgrad, void* packed,
+                               void* stream);
+int b200em_conv3d_umma_s3(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+                          void* y, int64_t y_ld, float* sums, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
+                          int kw, int relu, void* stream);
+
 /* Weight gradient on the tensor cores (bf16 operands, fp32 accumulation in TMEM, fp32 atomics into dw).
  * dw (Cout,Cin,kd,kh,kw) fp32 += sum dz * x_hat (same contract as b200em_conv3d_wgrad_direct); db (nullable)
  * (Cout) fp32 += sum dz -- the bias gradient, fused into the dz operand load.  Takes Cin % 32 == 0, Cout % 16 == 0. */

@@ -17,10 +17,13 @@ class P:
         self.w = w
 
 
-@pytest.fixture(scope="module")
-def B():
-    from torch_em_b200.backend import default_backend
-    return default_backend()
+@pytest.fixture(scope="module", params=["stacked", "plain"])
+def B(request):
+    """Both tensor-core conv variants: the w-stacked kernel (conv_umma_s3.cu, taken when Cout <= 80) and the plain one."""
+    from torch_em_b200 import _lib
+    from torch_em_b200.backend import CudaBackend
+    _lib.load()
+    return CudaBackend(use_s3=request.param == "stacked")
 
 
 CASES = [
@@ -33,6 +36,9 @@ CASES = [
     (1, 4, 8, 8, 128, 256, (3, 3, 3)),
     (1, 2, 8, 8, 256, 512, (3, 3, 3)),
     (3, 8, 32, 32, 32, 32, (3, 3, 3)),
+    (1, 5, 9, 30, 64, 64, (3, 3, 3)),
+    (2, 3, 17, 14, 32, 16, (1, 3, 3)),
+    (1, 4, 24, 43, 16, 80, (3, 3, 3)),
 ]
 
 
@@ -53,6 +59,8 @@ def test_umma_conv_forward_and_dgrad(B, case):
     ss = torch.stack([1 + 0.1 * rnd((N, Cin), 4), 0.1 * rnd((N, Cin), 5)], -1).contiguous()
     pk = B.pack(("umma-test", case), w.to(DEV))
     assert pk.umma_fwd is not None and pk.umma_dgrad is not None
+    if B.use_s3 and k[2] == 3 and Cout <= 80:
+        assert pk.s3_fwd is not None
     for in_ss, relu, bias in ((None, False, None), (ss, True, b)):
         y_ref = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16)
         s_ref = torch.zeros((N, Cout, 2))

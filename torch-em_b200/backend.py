@@ -49,14 +49,15 @@ def _f32(t):
 class WeightPack:
     """Kernel-operand copies of one conv weight (derived caches; the fp32 nn.Parameter stays the master)."""
     __slots__ = ("w_fwd_f32", "w_dgrad_f32", "umma_fwd", "umma_dgrad", "version", "ptr", "cout", "cin", "kernel", "thin",
-                 "thin_kp")
+                 "thin_kp", "s3_fwd", "s3_dgrad")
 
 
 class CudaBackend:
     name = "cuda"
 
-    def __init__(self, use_umma=True):
+    def __init__(self, use_umma=True, use_s3=True):
         self.use_umma = use_umma
+        self.use_s3 = use_s3 and use_umma
         self._pack_cache = {}
         self.timing = None          # {family: [(start_event, end_event, work), ...]} while bench.py measures
 
@@ -98,7 +99,7 @@ class CudaBackend:
         taps = kd * kh * kw
         pk.w_fwd_f32 = torch.empty((taps, cin, cout), dtype=torch.float32, device=w.device)
         pk.w_dgrad_f32 = torch.empty((taps, cout, cin), dtype=torch.float32, device=w.device)
-        pk.umma_fwd = pk.umma_dgrad = pk.thin = None
+        pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.s3_fwd = pk.s3_dgrad = None
         pk.thin_kp = 0
         lib = _lib.load()
         with torch.cuda.device(w.device):
@@ -110,6 +111,12 @@ class CudaBackend:
             if self.use_umma and lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
                 pk.umma_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.umma_dgrad), _stream(w))
+            if self.use_s3 and lib.b200em_conv3d_umma_s3_supported(cin, cout, kd, kh, kw):
+                pk.s3_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
+                call("b200em_conv3d_umma_s3_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.s3_fwd), _stream(w))
+            if self.use_s3 and lib.b200em_conv3d_umma_s3_supported(cout, cin, kd, kh, kw):
+                pk.s3_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
+                call("b200em_conv3d_umma_s3_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.s3_dgrad), _stream(w))
             kp = -(-taps * cin // 32) * 32
             if self.use_umma and cin <= 4 and lib.b200em_conv3d_umma_supported(kp, cout, 1, 1, 1):
                 # thin-K first conv: W'[co][tap*Cin+ci] = W[co][ci][tap], zero padded to Kp channels (im2col layout)
@@ -182,6 +189,13 @@ class CudaBackend:
                 "b200em_conv3d_umma", _ptr(cols), pack.thin_kp, None, _ptr(pack.thin), _f32(b), yp, yld, _f32(sums), N, D, H, W,
                 pack.thin_kp, Cout, 1, 1, 1, int(relu), _stream(x)))
             return cols       # kept by the schedule for the weight gradient of the same conv
+        ok16 = x.dtype == torch.bfloat16 and xld % 8 == 0 and yld % 8 == 0 and x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0
+        ws3 = pack.s3_dgrad if dgrad else pack.s3_fwd
+        if ws3 is not None and ok16:
+            self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
+                "b200em_conv3d_umma_s3", xp, xld, _f32(in_ss), _ptr(ws3), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cin, Cout,
+                kd, kh, kw, int(relu), _stream(x)))
+            return None
         wu = pack.umma_dgrad if dgrad else pack.umma_fwd
         if wu is not None and x.dtype == torch.bfloat16 and xld % 8 == 0 and yld % 8 == 0 and \
                 x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:

@@ -19,6 +19,7 @@
 // (one elected thread).  All hand-offs are mbarriers; the accumulator hand-off is tcgen05.commit.
 #include "common.cuh"
 #include "umma.cuh"
+#include "halo_tile.cuh"
 
 namespace b200em {
 
@@ -33,52 +34,6 @@ constexpr int THREADS = 320;
 constexpr int MAX_SMEM = 227 * 1024;
 }  // namespace
 
-
-// Haloed-tile operand load for 8-channel group `j`: voxels v = v0, v0+step, ... of an (nslices x HP x WP) tile.
-// Loads are issued in batches of LD_BATCH before any is consumed, so each thread keeps LD_BATCH 16-byte requests in
-// flight (the tile load is latency-bound otherwise: one dependent global load per iteration).
-constexpr int LD_BATCH = 8;
-
-__device__ __forceinline__ void load_halo_tile(const __nv_bfloat16* __restrict__ xn, long long x_ld, const float* sc, const float* sh,
-                                               bool affine, uint8_t* dst, int slice_stride_bytes, int v0, int step, int units,
-                                               int d0, int h0, int w0, int pd, int D, int H, int W) {
-    for (int vb = v0; vb < units; vb += LD_BATCH * step) {
-        uint4 val[LD_BATCH];
-        int off[LD_BATCH];
-        uint32_t inb = 0;
-#pragma unroll
-        for (int i = 0; i < LD_BATCH; ++i) {
-            const int v = vb + i * step;
-            val[i] = make_uint4(0, 0, 0, 0);
-            off[i] = -1;
-            if (v < units) {
-                const int wp_ = v % WP, hp_ = (v / WP) % HP, s = v / (WP * HP);
-                const int gd = d0 + s - pd, gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
-                off[i] = s * slice_stride_bytes + (hp_ * WP + wp_) * 16;
-                if (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
-                    val[i] = __ldg(reinterpret_cast<const uint4*>(xn + (((size_t)gd * H + gh) * W + gw) * x_ld));
-                    inb |= 1u << i;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < LD_BATCH; ++i) {
-            if (off[i] >= 0) {
-                if (affine && ((inb >> i) & 1)) {
-                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val[i]);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float2 f = __bfloat1622float2(h2[e]);
-                        f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
-                        f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
-                        h2[e] = __floats2bfloat162_rn(f.x, f.y);
-                    }
-                }
-                *reinterpret_cast<uint4*>(dst + off[i]) = val[i];
-            }
-        }
-    }
-}
 
 struct ConvUmmaParams {
     const __nv_bfloat16* x; long long x_ld;
@@ -175,7 +130,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                 }
                 uint8_t* dstbase = smA + buf * p.a_bytes + j * PLANE;
                 const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
-                load_halo_tile(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * PLANE, t / J, 128 / J, units, d0, h0, w0, pd,
+                load_halo_tile<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * PLANE, t / J, 128 / J, units, d0, h0, w0, pd,
                                p.D, p.H, p.W);
                 fence_proxy_async();
                 mbar_arrive(&a_full[buf]);
@@ -514,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
             }
             uint8_t* xdst = smX + buf * p.x_bytes + j * PLANE;
             const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
-            load_halo_tile(xn, p.x_ld, sc, sh, p.in_ss != nullptr, xdst, J * PLANE, t / J, 128 / J, xunits, d0, h0, w0, pd,
+            load_halo_tile<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, xdst, J * PLANE, t / J, 128 / J, xunits, d0, h0, w0, pd,
                            p.D, p.H, p.W);
             uint8_t* zdst = smZ + buf * p.dz_bytes + jo * WG_DZ_PLANE;
             const __nv_bfloat16* zn = p.dz + (size_t)n * p.D * p.H * p.W * p.dz_ld + cob * p.NB + jo * 8;

@@ -1,0 +1,389 @@
+// "w-stacked" variant of the tcgen05 implicit-GEMM convolution for layers with few output channels (Cout <= 80).
+//
+// Why: with both operands in shared memory, tcgen05.mma fetches the A operand (128 rows x 16 K x 2 B = 4 KB) at
+// ~64 B/clk (measured: profiles/r01_fwd_L0_32x32_ncu_full.csv), so one M=128 x N x K=16 MMA holds the tensor pipe for
+// max(64, N/2) cycles: a layer with N = Cout = 32 runs at <= 25 % of the tensor peak however well it is fed.  Here the
+// three w-taps of a filter row share ONE operand fetch: the B operand stacks them along N (N = 3*Cout),
+//     P[v][(c, co)] = sum_ci W[co][ci][a,b,c] * x_hat[v + (a,b)][ci]          (v = INPUT voxel, no w shift)
+// and the epilogue forms  y[u] = P[u-1][c=0] + P[u][c=1] + P[u+1][c=2]  with two warp shuffles per channel
+// (u-1 / u+1 are the neighbouring TMEM lanes = neighbouring threads of the same warp).
+// 9 (a,b) MMAs-groups instead of 27 per K step, each with 3x the work per operand byte.
+//
+// Tile: GEMM rows = 8 (h) x 16 (w') voxels where w' spans [w0-1, w0+14]: the w halo is INSIDE the row set, 14 output
+// columns per tile.  Shared-memory image [slice][8-ch plane][hp = 0..9][w' = 0..15][8 bf16]: 8-row groups are 128 B
+// apart (SBO), the (a,b) tap is a start-address offset of whole 256-byte rows.  Everything else (warp roles, mbarrier
+// pipelines, fused norm-apply prologue, bias/ReLU/statistics epilogue, persistent grid) is as in conv_umma.cu.
+#include "common.cuh"
+#include "halo_tile.cuh"
+#include "umma.cuh"
+
+namespace b200em {
+
+using namespace umma;
+
+namespace {
+constexpr int S3_TH = 8, S3_TWR = 16;          // tile rows: 8 x 16 voxels (w' includes the two halo columns)
+constexpr int S3_WOUT = S3_TWR - 2;             // output columns per tile
+constexpr int S3_HP = S3_TH + 2, S3_WP = S3_TWR;
+constexpr int S3_PLANE = S3_HP * S3_WP * 16 + 32;   // +32 B: staggers the 8-channel planes across banks for the loader's stores
+constexpr int S3_NSTAGE = 4;
+constexpr int S3_THREADS = 320;
+constexpr int S3_MAX_SMEM = 227 * 1024;
+}  // namespace
+
+struct ConvS3Params {
+    const __nv_bfloat16* x; long long x_ld;
+    const float* in_ss;
+    const __nv_bfloat16* w;          // [chunk][ab][plane j][3*Cout][8]
+    const float* bias;
+    __nv_bfloat16* y; long long y_ld;
+    float* sums;
+    int N, D, H, W, Cin, Cout;
+    int kd, kh, relu;
+    int R, CC, nchunks, acc_bufs;
+    int tiles_w, tiles_h, tiles_d;
+    long long items;
+    int a_bytes, b_stage_bytes;
+};
+
+__device__ __forceinline__ void s3_coords(const ConvS3Params& p, long long item, int& n, int& d0, int& h0, int& w0) {
+    int tw = (int)(item % p.tiles_w); item /= p.tiles_w;
+    int th = (int)(item % p.tiles_h); item /= p.tiles_h;
+    int td = (int)(item % p.tiles_d); item /= p.tiles_d;
+    n = (int)item; d0 = td * p.R; h0 = th * S3_TH; w0 = tw * S3_WOUT;
+}
+
+// One NV-wide block of output channels of one slab: shifted sum of the three w-tap partials, bias, ReLU, bf16 store,
+// per-channel statistics.  taddr = TMEM address of this thread's lane at column (slab base + cb).
+template <int NV>
+__device__ __forceinline__ void s3_epilogue_block(uint32_t taddr, int cout, const float* __restrict__ bias_s, int relu, bool valid,
+                                                  __nv_bfloat16* __restrict__ yp, float* __restrict__ s_sums_blk, bool want_sums,
+                                                  int lane) {
+    uint32_t raw[NV];
+    float v[NV];
+    auto ld = [&](uint32_t a) {
+        if constexpr (NV == 32) tmem_ld32(a, raw); else tmem_ld16(a, raw);
+        tmem_ld_wait();
+    };
+    ld(taddr);                                         // c = 0 partial of this row: wanted by the row to the right
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[i]), 1);
+    ld(taddr + cout);                                  // c = 1: own row
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __uint_as_float(raw[i]);
+    ld(taddr + 2 * cout);                              // c = 2 partial: wanted by the row to the left
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(raw[i]), 1);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float f = v[i] + bias_s[i];
+        if (relu) f = fmaxf(f, 0.f);
+        v[i] = __bfloat162float(__float2bfloat16_rn(f));
+    }
+    if (valid) {
+#pragma unroll
+        for (int q = 0; q < NV / 8; ++q) {
+            uint4 o;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(yp + 8 * q) = o;
+        }
+    }
+    if (want_sums) {
+        float s2[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { v[i] = valid ? v[i] : 0.f; s2[i] = v[i] * v[i]; }
+        const float a1 = warp_column_sums<NV>(v, lane);
+        const float a2 = warp_column_sums<NV>(s2, lane);
+        if (NV == 32) {
+            atomicAdd(&s_sums_blk[2 * lane], a1);
+            atomicAdd(&s_sums_blk[2 * lane + 1], a2);
+        } else if ((lane & 1) == 0) {                  // NV == 16: column = lane >> 1, held by both lanes of a pair
+            atomicAdd(&s_sums_blk[2 * (lane >> 1)], a1);
+            atomicAdd(&s_sums_blk[2 * (lane >> 1) + 1], a2);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const ConvS3Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int N3 = 3 * p.Cout;
+    uint8_t* smA = smem;
+    uint8_t* smB = smA + 2 * p.a_bytes;
+    float* s_bias = reinterpret_cast<float*>(smB + S3_NSTAGE * p.b_stage_bytes);
+    float* s_sums = s_bias + p.Cout;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sums + 2 * p.Cout);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + 2;
+    uint64_t* b_full = bars + 4;
+    uint64_t* b_empty = bars + 4 + S3_NSTAGE;
+    uint64_t* acc_full = bars + 4 + 2 * S3_NSTAGE;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint32_t* s_tap = s_tmem + 2;                   // [9] start offset of each (a,b) tap, 16-byte units
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int J = p.CC / 8, kc = p.CC / 16;
+    const int ntap = p.kd * p.kh;
+    const int nslices = p.R + p.kd - 1;
+    const int pd = p.kd / 2, ph = p.kh / 2;
+    const uint32_t acc_cols = (uint32_t)(p.R * N3);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < acc_cols * p.acc_bufs) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < S3_NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc(s_tmem, tmem_cols);
+    if (threadIdx.x < ntap) {
+        const int a = threadIdx.x / p.kh, b = threadIdx.x % p.kh;
+        s_tap[threadIdx.x] = (uint32_t)((a * J * S3_PLANE + (b + 1 - ph) * S3_WP * 16) >> 4);
+    }
+    for (int i = threadIdx.x; i < p.Cout; i += S3_THREADS) {
+        s_bias[i] = p.bias ? p.bias[i] : 0.f;
+        s_sums[2 * i] = 0.f;
+        s_sums[2 * i + 1] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp >= 4 && warp < 8) {
+        // ===================== operand loaders =====================
+        const int t = threadIdx.x - 128;
+        const int j = t % J;
+        const int units = nslices * S3_HP * S3_WP;
+        uint32_t fill = 0;
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+            int n, d0, h0, w0;
+            s3_coords(p, item, n, d0, h0, w0);
+            for (int c = 0; c < p.nchunks; ++c, ++fill) {
+                const int buf = fill & 1;
+                mbar_wait(&a_empty[buf], ((fill >> 1) & 1) ^ 1);
+                const int ch0 = c * p.CC + j * 8;
+                float sc[8], sh[8];
+                if (p.in_ss) {
+                    const float* q = p.in_ss + ((size_t)n * p.Cin + ch0) * 2;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
+                }
+                uint8_t* dstbase = smA + buf * p.a_bytes + j * S3_PLANE;
+                const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
+                load_halo_tile<S3_HP, S3_WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * S3_PLANE, t / J, 128 / J, units,
+                                             d0, h0, w0, pd, p.D, p.H, p.W);
+                fence_proxy_async();
+                mbar_arrive(&a_full[buf]);
+            }
+        }
+    } else if (warp == 8) {
+        // ===================== weight loader: one (a,b) tap (all three w-taps stacked) per stage =====================
+        if (elect_one()) {
+            const uint32_t bytes = (uint32_t)p.b_stage_bytes;
+            const size_t tap_elems = (size_t)J * N3 * 8;
+            uint32_t cnt = 0;
+            for (long long item = blockIdx.x; item < p.items; item += gridDim.x)
+                for (int c = 0; c < p.nchunks; ++c)
+                    for (int g = 0; g < ntap; ++g, ++cnt) {
+                        const int st = cnt % S3_NSTAGE;
+                        mbar_wait(&b_empty[st], ((cnt / S3_NSTAGE) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&b_full[st], bytes);
+                        bulk_g2s(smB + st * p.b_stage_bytes, p.w + ((size_t)c * ntap + g) * tap_elems, bytes, &b_full[st]);
+                    }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(128, N3);
+            const uint64_t ad = make_desc(0, S3_PLANE, 128), bd = make_desc(0, (uint32_t)(N3 * 16), 128);
+            const uint32_t a_hi = (uint32_t)(ad >> 32), a_lo_c = (uint32_t)(ad & 0xFFFFFFFFu);
+            const uint32_t b_hi = (uint32_t)(bd >> 32), b_lo_c = (uint32_t)(bd & 0xFFFFFFFFu);
+            const uint32_t a_base16 = smem_u32(smA) >> 4, b_base16 = smem_u32(smB) >> 4;
+            const uint32_t slab16 = (uint32_t)(J * (S3_PLANE / 16)), k16 = (uint32_t)(2 * (S3_PLANE / 16));
+            const uint32_t n3 = (uint32_t)N3;
+            uint32_t fill = 0, cnt = 0, it = 0;
+            for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+                int n, d0, h0, w0;
+                s3_coords(p, item, n, d0, h0, w0);
+                const int slot = (p.acc_bufs == 2) ? (it & 1) : 0;
+                const uint32_t use = (p.acc_bufs == 2) ? (it >> 1) : it;
+                mbar_wait(&acc_empty[slot], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + slot * acc_cols;
+                const int rmax = min(p.R, p.D - d0);
+                for (int c = 0; c < p.nchunks; ++c, ++fill) {
+                    const int buf = fill & 1;
+                    mbar_wait(&a_full[buf], (fill >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t abuf16 = a_base16 + (uint32_t)((buf * p.a_bytes) >> 4);
+                    for (int g = 0; g < ntap; ++g, ++cnt) {
+                        const int st = cnt % S3_NSTAGE;
+                        mbar_wait(&b_full[st], (cnt / S3_NSTAGE) & 1);
+                        tc_fence_after();
+                        const uint32_t a0 = a_lo_c + abuf16 + s_tap[g];
+                        const uint32_t b0 = b_lo_c + b_base16 + (uint32_t)((st * p.b_stage_bytes) >> 4);
+                        const uint32_t acc0 = (uint32_t)(c | g);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (r < rmax) {
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) {
+                                    if (k < kc) {
+                                        const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a0 + r * slab16 + k * k16);
+                                        const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b0 + k * 2 * n3);
+                                        umma_bf16(tacc + r * n3, adesc, bdesc, idesc, acc0 | (uint32_t)k);
+                                    }
+                                }
+                            }
+                        }
+                        umma_commit(&b_empty[st]);
+                    }
+                    umma_commit(&a_empty[buf]);
+                }
+                umma_commit(&acc_full[slot]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 0-3) =====================
+        const int row = warp * 32 + lane;
+        const int hl = row / S3_TWR, wr = row % S3_TWR;      // wr = w' (0 and 15 are halo rows: no output)
+        uint32_t it = 0;
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+            int n, d0, h0, w0;
+            s3_coords(p, item, n, d0, h0, w0);
+            const int slot = (p.acc_bufs == 2) ? (it & 1) : 0;
+            const uint32_t use = (p.acc_bufs == 2) ? (it >> 1) : it;
+            mbar_wait(&acc_full[slot], use & 1);
+            tc_fence_after();
+            const int gh = h0 + hl, gw = w0 + wr - 1;
+            const bool valid = wr >= 1 && wr <= S3_WOUT && gh < p.H && gw < p.W;
+            const int rmax = min(p.R, p.D - d0);
+            for (int r = 0; r < rmax; ++r) {
+                const int gd = d0 + r;
+                __nv_bfloat16* yp = p.y + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.y_ld;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * acc_cols + r * N3;
+                for (int cb = 0; cb < p.Cout; cb += 32) {
+                    if (p.Cout - cb >= 32)
+                        s3_epilogue_block<32>(taddr + cb, p.Cout, s_bias + cb, p.relu, valid, yp + cb, s_sums + 2 * cb, p.sums != nullptr, lane);
+                    else
+                        s3_epilogue_block<16>(taddr + cb, p.Cout, s_bias + cb, p.relu, valid, yp + cb, s_sums + 2 * cb, p.sums != nullptr, lane);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[slot]);
+            if (p.sums) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = threadIdx.x; i < 2 * p.Cout; i += 128) {
+                    atomicAdd(p.sums + ((size_t)n * p.Cout + (i >> 1)) * 2 + (i & 1), s_sums[i]);
+                    s_sums[i] = 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// torch (Cout, Cin, kd, kh, 3) fp32 -> bf16 [chunk][ab][plane j][c*Cout + n][8]; dgrad = 1: transposed, tap-flipped.
+__global__ void pack_s3_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int kd, int kh, int dgrad, int CC,
+                                       __nv_bfloat16* __restrict__ out) {
+    const int taps = kd * kh * 3;
+    const int64_t total = (int64_t)Cout * Cin * taps;
+    const int Nc = dgrad ? Cin : Cout;               // output channels of the packed operand
+    const int J = CC / 8, ntap = kd * kh;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tp = (int)(i % taps);
+        const int ci = (int)((i / taps) % Cin);
+        const int co = (int)(i / ((int64_t)taps * Cin));
+        const int n_ = dgrad ? ci : co, k_ = dgrad ? co : ci, t_ = dgrad ? taps - 1 - tp : tp;
+        const int ab = t_ / 3, c = t_ % 3;
+        const int chunk = k_ / CC, j = (k_ % CC) / 8, e = k_ % 8;
+        out[((((size_t)chunk * ntap + ab) * J + j) * (3 * Nc) + (size_t)c * Nc + n_) * 8 + e] = __float2bfloat16_rn(w[i]);
+    }
+}
+
+struct S3Shape {
+    int CC, R, acc_bufs, a_bytes, b_stage_bytes, smem_bytes;
+};
+
+static bool s3_shape(int Cin, int Cout, int kd, int kh, int kw, S3Shape& s) {
+    if (kw != 3 || (kh != 3 && kh != 1) || (kd != 3 && kd != 1)) return false;
+    if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16 || Cout > 80) return false;
+    s.CC = (Cin % 32 == 0) ? 32 : 16;
+    const int J = s.CC / 8, N3 = 3 * Cout;
+    s.b_stage_bytes = J * N3 * 16;
+    for (int R = 4; R >= 1; R >>= 1) {
+        if (2 * R * N3 > 512 && !(R == 1 && N3 <= 512)) continue;
+        s.R = R;
+        s.acc_bufs = (2 * R * N3 <= 512) ? 2 : 1;
+        s.a_bytes = (R + kd - 1) * J * S3_PLANE;
+        s.smem_bytes = 2 * s.a_bytes + S3_NSTAGE * s.b_stage_bytes + Cout * 4 * 3 + 16 * 8 + 16 + 9 * 4 + 128;
+        if (s.smem_bytes <= S3_MAX_SMEM) return true;
+    }
+    return false;
+}
+
+}  // namespace b200em
+
+using namespace b200em;
+
+extern "C" {
+
+int b200em_conv3d_umma_s3_supported(int Cin, int Cout, int kd, int kh, int kw) {
+    S3Shape s;
+    return s3_shape(Cin, Cout, kd, kh, kw, s) ? 1 : 0;
+}
+
+int b200em_conv3d_umma_s3_pack(const float* w, int Cout, int Cin, int kd, int kh, int kw, int dgrad, void* packed, void* stream) {
+    B2_CHECK_ARG(w && packed && Cout > 0 && Cin > 0, "conv3d_umma_s3_pack: bad arguments");
+    S3Shape s;
+    const int n_ = dgrad ? Cin : Cout, k_ = dgrad ? Cout : Cin;
+    if (!s3_shape(k_, n_, kd, kh, kw, s)) {
+        set_error("conv3d_umma_s3_pack: shape (%d -> %d, %dx%dx%d) not supported by the stacked tcgen05 path", k_, n_, kd, kh, kw);
+        return 2;
+    }
+    int64_t total = (int64_t)Cout * Cin * kd * kh * kw;
+    int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    pack_s3_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, kd, kh, dgrad, s.CC, (__nv_bfloat16*)packed);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_conv3d_umma_s3(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+                          void* y, int64_t y_ld, float* sums, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
+                          int kw, int relu, void* stream) {
+    B2_CHECK_ARG(x && w_packed && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_s3: bad arguments");
+    S3Shape s;
+    if (!s3_shape(Cin, Cout, kd, kh, kw, s)) {
+        set_error("conv3d_umma_s3: shape (%d -> %d, %dx%dx%d) not supported by the stacked tcgen05 path", Cin, Cout, kd, kh, kw);
+        return 2;
+    }
+    B2_CHECK_ARG(x_ld % 8 == 0 && y_ld % 8 == 0 && aligned16(x) && aligned16(y), "conv3d_umma_s3: activations must be 16-byte aligned with pitch % 8 == 0");
+    B2_CHECK_ARG(x_ld >= Cin && y_ld >= Cout, "conv3d_umma_s3: pitch smaller than channel count");
+    ConvS3Params p;
+    p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.w = (const __nv_bfloat16*)w_packed; p.bias = bias;
+    p.y = (__nv_bfloat16*)y; p.y_ld = y_ld; p.sums = sums;
+    p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.relu = relu;
+    p.R = s.R; p.CC = s.CC; p.nchunks = Cin / s.CC; p.acc_bufs = s.acc_bufs;
+    p.tiles_w = (W + S3_WOUT - 1) / S3_WOUT; p.tiles_h = (H + S3_TH - 1) / S3_TH; p.tiles_d = (D + s.R - 1) / s.R;
+    p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    p.a_bytes = s.a_bytes; p.b_stage_bytes = s.b_stage_bytes;
+    B2_CUDA(cudaFuncSetAttribute(conv3d_umma_s3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_MAX_SMEM));
+    long long gx = p.items < sm_count() ? p.items : sm_count();
+    conv3d_umma_s3_kernel<<<(unsigned)gx, S3_THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"
