@@ -59,7 +59,7 @@ def test_umma_conv_forward_and_dgrad(B, case):
     ss = torch.stack([1 + 0.1 * rnd((N, Cin), 4), 0.1 * rnd((N, Cin), 5)], -1).contiguous()
     pk = B.pack(("umma-test", case), w.to(DEV))
     assert pk.umma_fwd is not None and pk.umma_dgrad is not None
-    if B.use_s3 and k[2] == 3 and Cout <= 80:
+    if B.use_s3 and _lib.load().b200em_conv3d_umma_s3_supported(Cin, Cout, *k):
         assert pk.s3_fwd is not None
     for in_ss, relu, bias in ((None, False, None), (ss, True, b)):
         y_ref = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16)

@@ -55,7 +55,7 @@ class WeightPack:
 class CudaBackend:
     name = "cuda"
 
-    def __init__(self, use_umma=True, use_s3=True):
+    def __init__(self, use_umma=True, use_s3=False):
         self.use_umma = use_umma
         self.use_s3 = use_s3 and use_umma
         self._pack_cache = {}

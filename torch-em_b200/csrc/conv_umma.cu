@@ -13,10 +13,12 @@
 //      rows of one 8-group are 16 B apart, 8-groups are 10*16 B apart (SBO), the two K-chunks PLANE apart (LBO).
 //   B: [tap in stage][plane j][n = 0..NP-1][8 bf16], filled by cp.async.bulk (TMA engine) from the pre-packed weights.
 //
-// Warp roles (320 threads): warps 0-3 epilogue (TMEM -> bias/ReLU -> bf16 store + per-(n,c) statistics for the next
-// norm), warps 4-7 operand loaders (global -> [scale*x+shift of the preceding norm] -> shared; padding is written as
-// zeros, i.e. in normalised space like the reference), warp 8 weight loader (one elected thread), warp 9 MMA issuer
+// Warp roles (448 threads): warps 0-3 epilogue (TMEM -> bias/ReLU -> bf16 store + per-(n,c) statistics for the next
+// norm), warps 4-11 operand loaders (global -> [scale*x+shift of the preceding norm] -> shared; padding is written as
+// zeros, i.e. in normalised space like the reference), warp 12 weight loader (one elected thread), warp 13 MMA issuer
 // (one elected thread).  All hand-offs are mbarriers; the accumulator hand-off is tcgen05.commit.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 #include "halo_tile.cuh"
@@ -30,7 +32,9 @@ constexpr int TH = 16, TW = 8;             // voxel tile (h, w) = 128 GEMM rows
 constexpr int HP = TH + 2, WP = TW + 2;     // haloed tile
 constexpr int PLANE = HP * WP * 16 + 16;    // bytes per (slice, 8-channel group) plane; +16 staggers banks
 constexpr int NSTAGE = 4;                   // weight ring depth
-constexpr int THREADS = 320;
+constexpr int NLOAD = 256;                  // operand-loader threads (8 warps): the tile load is latency-bound, more threads = more bytes in flight
+constexpr int THREADS = 128 + NLOAD + 64;   // 4 epilogue warps | 8 loader warps | weight-loader warp | MMA warp
+constexpr int W_WLOAD = (128 + NLOAD) / 32, W_MMA = W_WLOAD + 1;
 constexpr int MAX_SMEM = 227 * 1024;
 }  // namespace
 
@@ -87,12 +91,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
     while (tmem_cols < acc_cols * p.acc_bufs) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], NLOAD); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(s_tmem, tmem_cols);
+    if (warp == W_MMA) tmem_alloc(s_tmem, tmem_cols);
     if (threadIdx.x < taps) {
         const int tap = threadIdx.x;
         const int a = tap / (p.kh * p.kw), b = (tap / p.kw) % p.kh, cc = tap % p.kw;
@@ -109,9 +113,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < W_WLOAD) {
         // ===================== operand loaders =====================
-        const int t = threadIdx.x - 128;             // 0..127
+        const int t = threadIdx.x - 128;             // 0..NLOAD-1
         const int j = t % J;                         // fixed 8-channel group of this thread (128 % J == 0)
         const int units = nslices * HP * WP;         // voxels of the haloed tile per chunk
         uint32_t fill = 0;
@@ -130,13 +134,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                 }
                 uint8_t* dstbase = smA + buf * p.a_bytes + j * PLANE;
                 const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
-                load_halo_tile<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * PLANE, t / J, 128 / J, units, d0, h0, w0, pd,
+                load_halo_tile_async<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * PLANE, t / J, NLOAD / J, units, d0, h0, w0, pd,
                                p.D, p.H, p.W);
                 fence_proxy_async();
                 mbar_arrive(&a_full[buf]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == W_WLOAD) {
         // ===================== weight loader =====================
         if (elect_one()) {
             const uint32_t bytes = (uint32_t)p.b_stage_bytes;
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         bulk_g2s(smB + st * p.b_stage_bytes, wblk + ((size_t)c * taps + (size_t)g * p.G) * tap_elems, bytes, &b_full[st]);
                     }
         }
-    } else if (warp == 9) {
+    } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
         // One thread issues every MMA, so the per-MMA instruction count is what bounds small-N layers: descriptors
         // are built once and only their 14-bit start-address field is bumped (independent adds, fully unrolled).
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == W_MMA) {
         __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
@@ -394,6 +398,7 @@ struct WgradUmmaParams {
     int tiles_w, tiles_h, tiles_d;
     long long items;
     int x_bytes, dz_bytes;
+    int debug;                                 // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 4 no MMAs, 8 no epilogue atomics
 };
 
 __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const WgradUmmaParams p) {
@@ -420,11 +425,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
     while (tmem_cols < (uint32_t)(tap9 * p.NB)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], NLOAD); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(s_tmem, tmem_cols);
+    if (warp == W_MMA) tmem_alloc(s_tmem, tmem_cols);
     if (threadIdx.x < tap9) {
         const int b = threadIdx.x / p.kw, cc = threadIdx.x % p.kw;
         s_tap9[threadIdx.x] = (uint32_t)((b + 1 - ph) * WP + (cc + 1 - pw));
@@ -446,7 +451,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
         n = (int)item; d0 = td * WG_R; h0 = th * TH; w0 = tw * TW;
     };
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < W_WLOAD) {
         // ===================== loaders: x_hat haloed tile + dz slabs =====================
         const int t = threadIdx.x - 128;
         const int j = t % J, jo = t % JO;
@@ -469,40 +474,35 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
             }
             uint8_t* xdst = smX + buf * p.x_bytes + j * PLANE;
             const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
-            load_halo_tile<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, xdst, J * PLANE, t / J, 128 / J, xunits, d0, h0, w0, pd,
-                           p.D, p.H, p.W);
+            if (!(p.debug & 1))
+                load_halo_tile_async<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, xdst, J * PLANE, t / J, NLOAD / J, xunits, d0, h0, w0, pd,
+                                       p.D, p.H, p.W);
             uint8_t* zdst = smZ + buf * p.dz_bytes + jo * WG_DZ_PLANE;
             const __nv_bfloat16* zn = p.dz + (size_t)n * p.D * p.H * p.W * p.dz_ld + cob * p.NB + jo * 8;
-            const int zstep = 128 / JO;
-            for (int vb = t / JO; vb < zunits; vb += LD_BATCH * zstep) {
-                uint4 val[LD_BATCH];
-                int off[LD_BATCH];
-#pragma unroll
-                for (int i = 0; i < LD_BATCH; ++i) {
-                    const int v = vb + i * zstep;
-                    val[i] = make_uint4(0, 0, 0, 0);
-                    off[i] = -1;
-                    if (v < zunits) {
-                        const int wl = v % TW, hl = (v / TW) % TH, r = v / (TW * TH);
-                        const int gd = d0 + r, gh = h0 + hl, gw = w0 + wl;
-                        off[i] = r * JO * WG_DZ_PLANE + (hl * TW + wl) * 16;
-                        if (gd < p.D && gh < p.H && gw < p.W)
-                            val[i] = __ldg(reinterpret_cast<const uint4*>(zn + (((size_t)gd * p.H + gh) * p.W + gw) * p.dz_ld));
-                    }
+            const int zstep = NLOAD / JO;
+            {
+                const uint32_t z32 = smem_u32(zdst);
+                for (int v = t / JO; v < ((p.debug & 1) ? 0 : zunits); v += zstep) {
+                    const int wl = v % TW, hl = (v / TW) % TH, r = v / (TW * TH);
+                    const int gd = d0 + r, gh = h0 + hl, gw = w0 + wl;
+                    const bool in = gd < p.D && gh < p.H && gw < p.W;
+                    const __nv_bfloat16* src = in ? zn + (((size_t)gd * p.H + gh) * p.W + gw) * p.dz_ld : zn;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(z32 + (uint32_t)(r * JO * WG_DZ_PLANE + (hl * TW + wl) * 16)),
+                                 "l"(src), "r"(in ? 16 : 0)
+                                 : "memory");
                 }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                if (p.db && chunk == 0) {
+                    for (int v = t / JO; v < zunits; v += zstep) {
+                        const int wl = v % TW, hl = (v / TW) % TH, r = v / (TW * TH);
+                        const uint4 val = *reinterpret_cast<const uint4*>(zdst + r * JO * WG_DZ_PLANE + (hl * TW + wl) * 16);
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
 #pragma unroll
-                for (int i = 0; i < LD_BATCH; ++i) {
-                    if (off[i] >= 0) {
-                        if (p.db && chunk == 0) {
-                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val[i]);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float2 f = __bfloat1622float2(h2[e]);
-                                dbacc[2 * e] += f.x;
-                                dbacc[2 * e + 1] += f.y;
-                            }
+                        for (int e = 0; e < 4; ++e) {
+                            float2 f = __bfloat1622float2(h2[e]);
+                            dbacc[2 * e] += f.x;
+                            dbacc[2 * e + 1] += f.y;
                         }
-                        *reinterpret_cast<uint4*>(zdst + off[i]) = val[i];
                     }
                 }
             }
@@ -512,10 +512,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
         if (p.db && chunk == 0) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) atomicAdd(&s_db[jo * 8 + e], dbacc[e]);
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(NLOAD) : "memory");
             if (t < p.NB) atomicAdd(p.db + cob * p.NB + t, s_db[t]);
         }
-    } else if (warp == 9) {
+    } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(128, p.NB, 1, 1);      // both operands MN-major
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
                             // K step = voxel rows hl = 2ks, 2ks+1 (8 voxels each)
                             const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a0 + ks * 2 * WP);
                             const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(zs + ks * 2 * TW);
-                            umma_bf16(tacc, adesc, bdesc, idesc, acc0 | (uint32_t)ks);
+                            if (!(p.debug & 4)) umma_bf16(tacc, adesc, bdesc, idesc, acc0 | (uint32_t)ks);
                         }
                     }
                 }
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
         tc_fence_after();
         const int a = warp;                              // depth tap of this warp's 32 lanes (a == 3: ignored rows)
         const int taps = p.kd * tap9;
-        if (a < p.kd) {
+        if (a < p.kd && !(p.debug & 8)) {
             const int ci = chunk * 32 + lane;
             for (int tp = 0; tp < tap9; ++tp) {
                 const int tap = a * tap9 + tp;
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == W_MMA) {
         __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
@@ -672,6 +672,7 @@ int b200em_conv3d_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
     p.x_bytes = (WG_R + kd - 1) * 4 * PLANE;
     p.dz_bytes = WG_R * (NB / 8) * WG_DZ_PLANE;
+    { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
     const int smem_bytes = 2 * p.x_bytes + 4 * 4 * PLANE + 2 * p.dz_bytes + NB * 4 + 8 * 8 + 16 + 9 * 4 + 128;
     B2_CHECK_ARG(smem_bytes <= MAX_SMEM, "conv3d_wgrad_umma: shared memory budget exceeded");
     B2_CUDA(cudaFuncSetAttribute(conv3d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));

@@ -13,6 +13,8 @@
 // columns per tile.  Shared-memory image [slice][8-ch plane][hp = 0..9][w' = 0..15][8 bf16]: 8-row groups are 128 B
 // apart (SBO), the (a,b) tap is a start-address offset of whole 256-byte rows.  Everything else (warp roles, mbarrier
 // pipelines, fused norm-apply prologue, bias/ReLU/statistics epilogue, persistent grid) is as in conv_umma.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "halo_tile.cuh"
 #include "umma.cuh"
@@ -44,6 +46,8 @@ struct ConvS3Params {
     int tiles_w, tiles_h, tiles_d;
     long long items;
     int a_bytes, b_stage_bytes;
+    int resident;                    // 1: the whole packed filter stays in shared memory for the CTA's lifetime
+    int debug;                       // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 2 no epilogue math, 4 no MMAs
 };
 
 __device__ __forceinline__ void s3_coords(const ConvS3Params& p, long long item, int& n, int& d0, int& h0, int& w0) {
@@ -55,10 +59,12 @@ __device__ __forceinline__ void s3_coords(const ConvS3Params& p, long long item,
 
 // One NV-wide block of output channels of one slab: shifted sum of the three w-tap partials, bias, ReLU, bf16 store,
 // per-channel statistics.  taddr = TMEM address of this thread's lane at column (slab base + cb).
-template <int NV>
+// ACC: statistics go to per-thread accumulators (acc_s/acc_q, flushed when the sample changes); otherwise they are
+// reduced over the warp's rows right away and added to the shared-memory sums (s_sums_blk).
+template <int NV, bool ACC>
 __device__ __forceinline__ void s3_epilogue_block(uint32_t taddr, int cout, const float* __restrict__ bias_s, int relu, bool valid,
-                                                  __nv_bfloat16* __restrict__ yp, float* __restrict__ s_sums_blk, bool want_sums,
-                                                  int lane) {
+                                                  __nv_bfloat16* __restrict__ yp, float* acc_s, float* acc_q,
+                                                  float* __restrict__ s_sums_blk, bool want_sums, int lane) {
     uint32_t raw[NV];
     float v[NV];
     auto ld = [&](uint32_t a) {
@@ -90,7 +96,12 @@ __device__ __forceinline__ void s3_epilogue_block(uint32_t taddr, int cout, cons
             *reinterpret_cast<uint4*>(yp + 8 * q) = o;
         }
     }
-    if (want_sums) {
+    if (ACC) {
+        if (want_sums && valid) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) { acc_s[i] += v[i]; acc_q[i] = fmaf(v[i], v[i], acc_q[i]); }
+        }
+    } else if (want_sums) {
         float s2[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) { v[i] = valid ? v[i] : 0.f; s2[i] = v[i] * v[i]; }
@@ -99,19 +110,39 @@ __device__ __forceinline__ void s3_epilogue_block(uint32_t taddr, int cout, cons
         if (NV == 32) {
             atomicAdd(&s_sums_blk[2 * lane], a1);
             atomicAdd(&s_sums_blk[2 * lane + 1], a2);
-        } else if ((lane & 1) == 0) {                  // NV == 16: column = lane >> 1, held by both lanes of a pair
+        } else if ((lane & 1) == 0) {
             atomicAdd(&s_sums_blk[2 * (lane >> 1)], a1);
             atomicAdd(&s_sums_blk[2 * (lane >> 1) + 1], a2);
         }
     }
 }
 
+// Flush one NV-wide block of per-thread statistics: column sums over the warp's 32 rows, then shared-memory atomics.
+template <int NV>
+__device__ __forceinline__ void s3_flush_stats(float* acc_s, float* acc_q, float* __restrict__ s_sums_blk, int lane) {
+    float a[NV], q[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { a[i] = acc_s[i]; q[i] = acc_q[i]; acc_s[i] = 0.f; acc_q[i] = 0.f; }
+    const float a1 = warp_column_sums<NV>(a, lane);
+    const float a2 = warp_column_sums<NV>(q, lane);
+    if (NV == 32) {
+        atomicAdd(&s_sums_blk[2 * lane], a1);
+        atomicAdd(&s_sums_blk[2 * lane + 1], a2);
+    } else if ((lane & 1) == 0) {                  // NV == 16: column = lane >> 1, held by both lanes of a pair
+        atomicAdd(&s_sums_blk[2 * (lane >> 1)], a1);
+        atomicAdd(&s_sums_blk[2 * (lane >> 1) + 1], a2);
+    }
+}
+
+// CO = Cout (16..80, multiple of 16): compile-time so that the epilogue's channel blocks and accumulators are static.
+template <int CO>
 __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const ConvS3Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int N3 = 3 * p.Cout;
     uint8_t* smA = smem;
     uint8_t* smB = smA + 2 * p.a_bytes;
-    float* s_bias = reinterpret_cast<float*>(smB + S3_NSTAGE * p.b_stage_bytes);
+    const int b_region = p.resident ? p.nchunks * p.kd * p.kh * p.b_stage_bytes : S3_NSTAGE * p.b_stage_bytes;
+    float* s_bias = reinterpret_cast<float*>(smB + b_region);
     float* s_sums = s_bias + p.Cout;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_sums + 2 * p.Cout);
     uint64_t* a_full = bars;
@@ -174,8 +205,9 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
                 }
                 uint8_t* dstbase = smA + buf * p.a_bytes + j * S3_PLANE;
                 const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
-                load_halo_tile<S3_HP, S3_WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * S3_PLANE, t / J, 128 / J, units,
-                                             d0, h0, w0, pd, p.D, p.H, p.W);
+                if (!(p.debug & 1))
+                    load_halo_tile<S3_HP, S3_WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * S3_PLANE, t / J, 128 / J, units,
+                                                 d0, h0, w0, pd, p.D, p.H, p.W);
                 fence_proxy_async();
                 mbar_arrive(&a_full[buf]);
             }
@@ -185,15 +217,22 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
         if (elect_one()) {
             const uint32_t bytes = (uint32_t)p.b_stage_bytes;
             const size_t tap_elems = (size_t)J * N3 * 8;
-            uint32_t cnt = 0;
-            for (long long item = blockIdx.x; item < p.items; item += gridDim.x)
-                for (int c = 0; c < p.nchunks; ++c)
-                    for (int g = 0; g < ntap; ++g, ++cnt) {
-                        const int st = cnt % S3_NSTAGE;
-                        mbar_wait(&b_empty[st], ((cnt / S3_NSTAGE) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&b_full[st], bytes);
-                        bulk_g2s(smB + st * p.b_stage_bytes, p.w + ((size_t)c * ntap + g) * tap_elems, bytes, &b_full[st]);
-                    }
+            if (p.resident) {
+                // the whole filter fits: load it once, it stays for every work item of this CTA
+                const int nst = p.nchunks * ntap;
+                mbar_arrive_expect_tx(&b_full[0], bytes * nst);
+                for (int g = 0; g < nst; ++g) bulk_g2s(smB + (size_t)g * bytes, p.w + (size_t)g * tap_elems, bytes, &b_full[0]);
+            } else {
+                uint32_t cnt = 0;
+                for (long long item = blockIdx.x; item < p.items; item += gridDim.x)
+                    for (int c = 0; c < p.nchunks; ++c)
+                        for (int g = 0; g < ntap; ++g, ++cnt) {
+                            const int st = cnt % S3_NSTAGE;
+                            mbar_wait(&b_empty[st], ((cnt / S3_NSTAGE) & 1) ^ 1);
+                            mbar_arrive_expect_tx(&b_full[st], bytes);
+                            bulk_g2s(smB + st * p.b_stage_bytes, p.w + ((size_t)c * ntap + g) * tap_elems, bytes, &b_full[st]);
+                        }
+            }
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
@@ -206,6 +245,10 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
             const uint32_t slab16 = (uint32_t)(J * (S3_PLANE / 16)), k16 = (uint32_t)(2 * (S3_PLANE / 16));
             const uint32_t n3 = (uint32_t)N3;
             uint32_t fill = 0, cnt = 0, it = 0;
+            if (p.resident) {
+                mbar_wait(&b_full[0], 0);
+                tc_fence_after();
+            }
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
                 int n, d0, h0, w0;
                 s3_coords(p, item, n, d0, h0, w0);
@@ -221,9 +264,11 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
                     tc_fence_after();
                     const uint32_t abuf16 = a_base16 + (uint32_t)((buf * p.a_bytes) >> 4);
                     for (int g = 0; g < ntap; ++g, ++cnt) {
-                        const int st = cnt % S3_NSTAGE;
-                        mbar_wait(&b_full[st], (cnt / S3_NSTAGE) & 1);
-                        tc_fence_after();
+                        const int st = p.resident ? c * ntap + g : (int)(cnt % S3_NSTAGE);
+                        if (!p.resident) {
+                            mbar_wait(&b_full[st], (cnt / S3_NSTAGE) & 1);
+                            tc_fence_after();
+                        }
                         const uint32_t a0 = a_lo_c + abuf16 + s_tap[g];
                         const uint32_t b0 = b_lo_c + b_base16 + (uint32_t)((st * p.b_stage_bytes) >> 4);
                         const uint32_t acc0 = (uint32_t)(c | g);
@@ -232,7 +277,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
                             if (r < rmax) {
 #pragma unroll
                                 for (int k = 0; k < 2; ++k) {
-                                    if (k < kc) {
+                                    if (k < kc && !(p.debug & 4)) {
                                         const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a0 + r * slab16 + k * k16);
                                         const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b0 + k * 2 * n3);
                                         umma_bf16(tacc + r * n3, adesc, bdesc, idesc, acc0 | (uint32_t)k);
@@ -240,7 +285,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
                                 }
                             }
                         }
-                        umma_commit(&b_empty[st]);
+                        if (!p.resident) umma_commit(&b_empty[st]);
                     }
                     umma_commit(&a_empty[buf]);
                 }
@@ -251,39 +296,61 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
         // ===================== epilogue (warps 0-3) =====================
         const int row = warp * 32 + lane;
         const int hl = row / S3_TWR, wr = row % S3_TWR;      // wr = w' (0 and 15 are halo rows: no output)
+        // Statistics: Cout <= 32 keeps per-thread accumulators over all of this thread's rows (2*Cout registers) and
+        // reduces them across the warp only when the sample changes; wider layers reduce per slab into shared memory.
+        constexpr bool kAcc = CO <= 32;
+        constexpr int NA = kAcc ? CO : 1;
+        float acc_s[NA], acc_q[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
+        int cur_n = -1;
+        auto flush = [&](int n_) {
+            if constexpr (kAcc) s3_flush_stats<CO>(acc_s, acc_q, s_sums, lane);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x; i < 2 * CO; i += 128) {
+                atomicAdd(p.sums + ((size_t)n_ * CO + (i >> 1)) * 2 + (i & 1), s_sums[i]);
+                s_sums[i] = 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
         uint32_t it = 0;
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
             int n, d0, h0, w0;
             s3_coords(p, item, n, d0, h0, w0);
             const int slot = (p.acc_bufs == 2) ? (it & 1) : 0;
             const uint32_t use = (p.acc_bufs == 2) ? (it >> 1) : it;
+            if (p.sums && n != cur_n) {
+                if (cur_n >= 0) flush(cur_n);
+                cur_n = n;
+            }
             mbar_wait(&acc_full[slot], use & 1);
             tc_fence_after();
             const int gh = h0 + hl, gw = w0 + wr - 1;
             const bool valid = wr >= 1 && wr <= S3_WOUT && gh < p.H && gw < p.W;
             const int rmax = min(p.R, p.D - d0);
-            for (int r = 0; r < rmax; ++r) {
+            for (int r = 0; r < ((p.debug & 2) ? 0 : rmax); ++r) {
                 const int gd = d0 + r;
                 __nv_bfloat16* yp = p.y + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.y_ld;
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * acc_cols + r * N3;
-                for (int cb = 0; cb < p.Cout; cb += 32) {
-                    if (p.Cout - cb >= 32)
-                        s3_epilogue_block<32>(taddr + cb, p.Cout, s_bias + cb, p.relu, valid, yp + cb, s_sums + 2 * cb, p.sums != nullptr, lane);
-                    else
-                        s3_epilogue_block<16>(taddr + cb, p.Cout, s_bias + cb, p.relu, valid, yp + cb, s_sums + 2 * cb, p.sums != nullptr, lane);
+                const bool ws = p.sums != nullptr;
+                if constexpr (CO == 16) {
+                    s3_epilogue_block<16, true>(taddr, CO, s_bias, p.relu, valid, yp, acc_s, acc_q, s_sums, ws, lane);
+                } else if constexpr (CO == 32) {
+                    s3_epilogue_block<32, true>(taddr, CO, s_bias, p.relu, valid, yp, acc_s, acc_q, s_sums, ws, lane);
+                } else {
+                    s3_epilogue_block<32, false>(taddr, CO, s_bias, p.relu, valid, yp, acc_s, acc_q, s_sums, ws, lane);
+                    if constexpr (CO >= 64)
+                        s3_epilogue_block<32, false>(taddr + 32, CO, s_bias + 32, p.relu, valid, yp + 32, acc_s, acc_q, s_sums + 64, ws, lane);
+                    if constexpr (CO == 48)
+                        s3_epilogue_block<16, false>(taddr + 32, CO, s_bias + 32, p.relu, valid, yp + 32, acc_s, acc_q, s_sums + 64, ws, lane);
+                    if constexpr (CO == 80)
+                        s3_epilogue_block<16, false>(taddr + 64, CO, s_bias + 64, p.relu, valid, yp + 64, acc_s, acc_q, s_sums + 128, ws, lane);
                 }
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[slot]);
-            if (p.sums) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = threadIdx.x; i < 2 * p.Cout; i += 128) {
-                    atomicAdd(p.sums + ((size_t)n * p.Cout + (i >> 1)) * 2 + (i & 1), s_sums[i]);
-                    s_sums[i] = 0.f;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
         }
+        if (p.sums && cur_n >= 0) flush(cur_n);
     }
 
     tc_fence_before();
@@ -314,7 +381,7 @@ __global__ void pack_s3_weights_kernel(const float* __restrict__ w, int Cout, in
 }
 
 struct S3Shape {
-    int CC, R, acc_bufs, a_bytes, b_stage_bytes, smem_bytes;
+    int CC, R, acc_bufs, a_bytes, b_stage_bytes, smem_bytes, resident;
 };
 
 static bool s3_shape(int Cin, int Cout, int kd, int kh, int kw, S3Shape& s) {
@@ -328,7 +395,12 @@ static bool s3_shape(int Cin, int Cout, int kd, int kh, int kw, S3Shape& s) {
         s.R = R;
         s.acc_bufs = (2 * R * N3 <= 512) ? 2 : 1;
         s.a_bytes = (R + kd - 1) * J * S3_PLANE;
-        s.smem_bytes = 2 * s.a_bytes + S3_NSTAGE * s.b_stage_bytes + Cout * 4 * 3 + 16 * 8 + 16 + 9 * 4 + 128;
+        const int misc = Cout * 4 * 3 + 16 * 8 + 16 + 9 * 4 + 128;
+        // the stacked kernel only pays off when the whole filter stays resident in shared memory: streaming it per work
+        // item (R is small here) is bound by the ~1 us latency of the bulk copies (measured), not by the tensor pipe
+        const int wbytes = (Cin / s.CC) * kd * kh * s.b_stage_bytes;
+        s.resident = 1;
+        s.smem_bytes = 2 * s.a_bytes + wbytes + misc;
         if (s.smem_bytes <= S3_MAX_SMEM) return true;
     }
     return false;
@@ -378,10 +450,25 @@ int b200em_conv3d_umma_s3(const void* x, int64_t x_ld, const float* in_scale_shi
     p.R = s.R; p.CC = s.CC; p.nchunks = Cin / s.CC; p.acc_bufs = s.acc_bufs;
     p.tiles_w = (W + S3_WOUT - 1) / S3_WOUT; p.tiles_h = (H + S3_TH - 1) / S3_TH; p.tiles_d = (D + s.R - 1) / s.R;
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
-    p.a_bytes = s.a_bytes; p.b_stage_bytes = s.b_stage_bytes;
-    B2_CUDA(cudaFuncSetAttribute(conv3d_umma_s3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_MAX_SMEM));
+    p.a_bytes = s.a_bytes; p.b_stage_bytes = s.b_stage_bytes; p.resident = s.resident;
+    { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
     long long gx = p.items < sm_count() ? p.items : sm_count();
-    conv3d_umma_s3_kernel<<<(unsigned)gx, S3_THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);
+#define B2_S3_LAUNCH(CO_)                                                                                                   \
+    case CO_:                                                                                                               \
+        B2_CUDA(cudaFuncSetAttribute(conv3d_umma_s3_kernel<CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_MAX_SMEM)); \
+        conv3d_umma_s3_kernel<CO_><<<(unsigned)gx, S3_THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                     \
+        break;
+    switch (Cout) {
+        B2_S3_LAUNCH(16)
+        B2_S3_LAUNCH(32)
+        B2_S3_LAUNCH(48)
+        B2_S3_LAUNCH(64)
+        B2_S3_LAUNCH(80)
+        default:
+            set_error("conv3d_umma_s3: Cout %d not instantiated", Cout);
+            return 2;
+    }
+#undef B2_S3_LAUNCH
     B2_LAUNCH_CHECK();
     return 0;
 }
