@@ -85,9 +85,11 @@ int b200em_conv3d_wgrad_smallcin(const void* x, int64_t x_ld, const float* in_sc
 int b200em_conv3d_umma_supported(int Cin, int Cout, int kd, int kh, int kw);
 int b200em_conv3d_umma_pack(const float* w, int Cout, int Cin, int kd, int kh, int kw, int dgrad, void* packed,
                             void* stream);
+/* dot_x (nullable, NDHWC bf16 with pitch dot_ld, Cout channels): when given, sums += (sum y, sum y*dot_x) instead of
+ * (sum y, sum y^2) -- the two reductions of the InstanceNorm/GroupNorm backward, fused into the data-gradient conv. */
 int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
-                       void* y, int64_t y_ld, float* sums, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
-                       int kw, int relu, void* stream);
+                       void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
+                       int Cout, int kd, int kh, int kw, int relu, void* stream);
 
 /* "w-stacked" tcgen05 variant for layers with few output channels (Cout <= 80, kw == 3): the three w-taps share one
  * operand fetch (N = 3*Cout), shifted sum in the epilogue (csrc/conv_umma_s3.cu).  Same contract and arguments as

@@ -89,7 +89,7 @@ class TorchEmuBackend:
             xf = xf * _bcast(in_ss[..., 0]) + _bcast(in_ss[..., 1])
         return _ncdhw(xf)
 
-    def conv(self, x, in_ss, pack, bias, y, sums, kernel, relu, dgrad):
+    def conv(self, x, in_ss, pack, bias, y, sums, kernel, relu, dgrad, dot_x=None):
         pad = tuple(k // 2 for k in kernel)
         xh = self._xhat(x, in_ss)
         if dgrad:
@@ -100,7 +100,10 @@ class TorchEmuBackend:
             r = F.relu(r)
         y.copy_(r.permute(0, 2, 3, 4, 1))
         if sums is not None:
-            self.channel_sums(y, sums)
+            if dot_x is not None:
+                self.channel_dot_sums(y, dot_x, sums)
+            else:
+                self.channel_sums(y, sums)
         return None
 
     def wgrad(self, x, in_ss, dz, dw, db, kernel, aux=None):

@@ -83,6 +83,13 @@ def test_umma_conv_forward_and_dgrad(B, case):
     B.conv(dz.to(DEV), None, pk, None, g, None, k, False, True)
     torch.cuda.synchronize()
     np.testing.assert_allclose(g.float().cpu().numpy(), g_ref.float().numpy(), rtol=1e-2, atol=1e-2)
+    # data gradient with the fused norm-backward reductions: sums = (sum g, sum g * x) over the stored g
+    d_ref = torch.zeros((N, Cin, 2))
+    EMU.channel_dot_sums(g_ref, x, d_ref)
+    d = torch.zeros((N, Cin, 2), device=DEV)
+    B.conv(dz.to(DEV), None, pk, None, g, d, k, False, True, dot_x=x.to(DEV))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(d.cpu().numpy(), d_ref.numpy(), rtol=1e-2, atol=2e-2 * float(d_ref.abs().max()))
 
 
 WG_CASES = [

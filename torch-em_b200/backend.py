@@ -172,8 +172,9 @@ class CudaBackend:
              int(relu_mask), _stream(g))
 
     # ---- convolution -----------------------------------------------------------------------------------------
-    def conv(self, x, in_ss, pack, bias, y, sums, kernel, relu, dgrad):
-        """y = act(conv(norm(x)) + bias).  dgrad=True: the data-gradient (flipped/transposed weights)."""
+    def conv(self, x, in_ss, pack, bias, y, sums, kernel, relu, dgrad, dot_x=None):
+        """y = act(conv(norm(x)) + bias).  dgrad=True: the data-gradient (flipped/transposed weights).
+        sums += (sum y, sum y^2) per (n, channel), or (sum y, sum y * dot_x) when dot_x is given (norm backward)."""
         N, D, H, W, Cin = x.shape
         Cout = y.shape[4]
         xp, xld = _act(x)
@@ -185,13 +186,14 @@ class CudaBackend:
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
         if (not dgrad) and pack.thin is not None and x.dtype == torch.bfloat16 and yld % 8 == 0 and y.data_ptr() % 16 == 0:
             cols = self.im2col(x, in_ss, kernel, pack.thin_kp)
+            assert dot_x is None
             self._timed("conv_umma_fwd", flops, lambda: call(
-                "b200em_conv3d_umma", _ptr(cols), pack.thin_kp, None, _ptr(pack.thin), _f32(b), yp, yld, _f32(sums), N, D, H, W,
-                pack.thin_kp, Cout, 1, 1, 1, int(relu), _stream(x)))
+                "b200em_conv3d_umma", _ptr(cols), pack.thin_kp, None, _ptr(pack.thin), _f32(b), yp, yld, _f32(sums), None, 0, N, D, H,
+                W, pack.thin_kp, Cout, 1, 1, 1, int(relu), _stream(x)))
             return cols       # kept by the schedule for the weight gradient of the same conv
         ok16 = x.dtype == torch.bfloat16 and xld % 8 == 0 and yld % 8 == 0 and x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0
         ws3 = pack.s3_dgrad if dgrad else pack.s3_fwd
-        if ws3 is not None and ok16:
+        if ws3 is not None and ok16 and dot_x is None:
             self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
                 "b200em_conv3d_umma_s3", xp, xld, _f32(in_ss), _ptr(ws3), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cin, Cout,
                 kd, kh, kw, int(relu), _stream(x)))
@@ -199,13 +201,18 @@ class CudaBackend:
         wu = pack.umma_dgrad if dgrad else pack.umma_fwd
         if wu is not None and x.dtype == torch.bfloat16 and xld % 8 == 0 and yld % 8 == 0 and \
                 x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
-            self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
-                "b200em_conv3d_umma", xp, xld, _f32(in_ss), _ptr(wu), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cin, Cout,
-                kd, kh, kw, int(relu), _stream(x)))
-            return None
+            dp, dld = _act(dot_x) if dot_x is not None else (None, 0)
+            if dot_x is None or (dld % 8 == 0 and dot_x.data_ptr() % 16 == 0):
+                self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
+                    "b200em_conv3d_umma", xp, xld, _f32(in_ss), _ptr(wu), _f32(b), yp, yld, _f32(sums), dp, dld, N, D, H, W, Cin,
+                    Cout, kd, kh, kw, int(relu), _stream(x)))
+                return None
         self._timed("conv_direct_dgrad" if dgrad else "conv_direct_fwd", flops, lambda: call(
-            "b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, _f32(sums), _dt(x), N, D, H, W, Cin,
-            Cout, kd, kh, kw, int(relu), _stream(x)))
+            "b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, None if dot_x is not None else _f32(sums),
+            _dt(x), N, D, H, W, Cin, Cout, kd, kh, kw, int(relu), _stream(x)))
+        if dot_x is not None:
+            self.channel_dot_sums(y, dot_x, sums)
+        return None
 
     def im2col(self, x, in_ss, kernel, kp):
         """(N,D,H,W,Cin<=4) -> (N,D,H,W,kp) bf16 im2col of the first conv's taps, with the norm apply fused."""

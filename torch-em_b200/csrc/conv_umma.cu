@@ -46,6 +46,7 @@ struct ConvUmmaParams {
     const float* bias;
     __nv_bfloat16* y; long long y_ld;
     float* sums;
+    const __nv_bfloat16* dot_x; long long dot_ld;   // non-null: sums = (sum y, sum y * dot_x) -- the norm-backward reductions
     int N, D, H, W, Cin, Cout;
     int kd, kh, kw, relu;
     int R, NP, CC, nchunks, G, acc_bufs;
@@ -259,8 +260,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         }
                         if (p.sums) {
                             float s1[32], s2[32];
+                            if (p.dot_x) {
+                                const __nv_bfloat16* xq = p.dot_x + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * 256 + cb;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+                                for (int q = 0; q < 4; ++q) {
+                                    uint4 xv = valid_hw ? __ldg(reinterpret_cast<const uint4*>(xq + 8 * q)) : make_uint4(0, 0, 0, 0);
+                                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 f = __bfloat1622float2(h2[e]);
+                                        s2[8 * q + 2 * e] = f.x;
+                                        s2[8 * q + 2 * e + 1] = f.y;
+                                    }
+                                }
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] *= s1[i]; }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+                            }
                             const float a1 = warp_column_sums<32>(s1, lane);
                             const float a2 = warp_column_sums<32>(s2, lane);
                             atomicAdd(&s_sums[2 * (cb + lane)], a1);
@@ -289,8 +307,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         }
                         if (p.sums) {
                             float s1[16], s2[16];
+                            if (p.dot_x) {
+                                const __nv_bfloat16* xq = p.dot_x + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * 256 + cb;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+                                for (int q = 0; q < 2; ++q) {
+                                    uint4 xv = valid_hw ? __ldg(reinterpret_cast<const uint4*>(xq + 8 * q)) : make_uint4(0, 0, 0, 0);
+                                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 f = __bfloat1622float2(h2[e]);
+                                        s2[8 * q + 2 * e] = f.x;
+                                        s2[8 * q + 2 * e + 1] = f.y;
+                                    }
+                                }
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] *= s1[i]; }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+                            }
                             const float a1 = warp_column_sums<16>(s1, lane);   // column = lane >> 1 (held twice)
                             const float a2 = warp_column_sums<16>(s2, lane);
                             if ((lane & 1) == 0) {
@@ -620,8 +655,8 @@ int b200em_conv3d_umma_pack(const float* w, int Cout, int Cin, int kd, int kh, i
 }
 
 int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
-                       void* y, int64_t y_ld, float* sums, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
-                       int kw, int relu, void* stream) {
+                       void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
+                       int Cout, int kd, int kh, int kw, int relu, void* stream) {
     B2_CHECK_ARG(x && w_packed && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma: bad arguments");
     B2_CHECK_ARG((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv3d_umma: kernel dims must be 1 or 3");
     UmmaShape s;
@@ -634,6 +669,8 @@ int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift,
     ConvUmmaParams p;
     p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.w = (const __nv_bfloat16*)w_packed; p.bias = bias;
     p.y = (__nv_bfloat16*)y; p.y_ld = y_ld; p.sums = sums;
+    p.dot_x = (const __nv_bfloat16*)dot_x; p.dot_ld = dot_ld;
+    B2_CHECK_ARG(!dot_x || (sums && dot_ld % 8 == 0 && aligned16(dot_x) && dot_ld >= Cout), "conv3d_umma: dot_x needs sums, 16-byte alignment and pitch >= Cout");
     p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.relu = relu;
     p.R = s.R; p.NP = s.NP; p.CC = s.CC; p.nchunks = Cin / s.CC; p.G = s.G; p.acc_bufs = s.acc_bufs;
     p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + s.R - 1) / s.R;

@@ -80,12 +80,12 @@ __global__ void channel_sums_kernel(const T* __restrict__ a, int64_t a_ld, const
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[v][0] = acc[v][1] = 0.f;
         if (active) {
-            for (int64_t s = blockIdx.x * (int64_t)blockDim.y + threadIdx.y; s < S; s += (int64_t)gridDim.x * blockDim.y) {
+            for (unsigned s = blockIdx.x * blockDim.y + threadIdx.y; s < (unsigned)S; s += gridDim.x * blockDim.y) {
                 float va[VEC];
-                Vec<T, VEC>::load(an + s * a_ld + cv * VEC, va);
+                Vec<T, VEC>::load(an + (size_t)s * a_ld + cv * VEC, va);
                 if (DOT) {
                     float vb[VEC];
-                    Vec<T, VEC>::load(bn + s * b_ld + cv * VEC, vb);
+                    Vec<T, VEC>::load(bn + (size_t)s * b_ld + cv * VEC, vb);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) { acc[v][0] += va[v]; acc[v][1] += va[v] * vb[v]; }
                 } else {
@@ -170,11 +170,11 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ dsums, const 
 template <typename T, int VEC>
 __global__ void affine_apply_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ ss,
                                     T* __restrict__ y, int64_t y_ld, int64_t S, int C, int64_t total) {
-    const int cvec = C / VEC;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned cvec = C / VEC;
+    const int64_t n = blockIdx.y;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
         int cv = (int)(i % cvec);
-        int64_t vox = i / cvec;  // n*S + s
-        int64_t n = vox / S;
+        int64_t vox = n * S + i / cvec;
         float v[VEC];
         Vec<T, VEC>::load(x + vox * x_ld + cv * VEC, v);
         const float* p = ss + ((size_t)n * C + cv * VEC) * 2;
@@ -190,11 +190,11 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ g, int64_t g_ld, con
                                       const float* __restrict__ coef, const T* __restrict__ add, int64_t add_ld,
                                       T* __restrict__ out, int64_t out_ld, int64_t S, int C, int relu_mask,
                                       int64_t total) {
-    const int cvec = C / VEC;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned cvec = C / VEC;
+    const int64_t n = blockIdx.y;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
         int cv = (int)(i % cvec);
-        int64_t vox = i / cvec;
-        int64_t n = vox / S;
+        int64_t vox = n * S + i / cvec;
         float vg[VEC], vx[VEC], va[VEC], r[VEC];
         Vec<T, VEC>::load(g + vox * g_ld + cv * VEC, vg);
         const bool need_x = (coef != nullptr) || relu_mask;
@@ -232,8 +232,8 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __r
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[v][0] = acc[v][1] = 0.f;
         if (active) {
-            for (int64_t s = blockIdx.x * (int64_t)blockDim.y + threadIdx.y; s < So; s += (int64_t)gridDim.x * blockDim.y) {
-                int wo = (int)(s % Wo), ho = (int)((s / Wo) % Ho), d_o = (int)(s / ((int64_t)Wo * Ho));
+            for (unsigned s = blockIdx.x * blockDim.y + threadIdx.y; s < (unsigned)So; s += gridDim.x * blockDim.y) {
+                int wo = (int)(s % (unsigned)Wo), ho = (int)((s / (unsigned)Wo) % (unsigned)Ho), d_o = (int)(s / (unsigned)(Wo * Ho));
                 float m[VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) m[v] = -INFINITY;
@@ -246,7 +246,7 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __r
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], t[v]);
                         }
-                Vec<T, VEC>::store(yn + s * y_ld + cv * VEC, m);
+                Vec<T, VEC>::store(yn + (size_t)s * y_ld + cv * VEC, m);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) { acc[v][0] += m[v]; acc[v][1] += m[v] * m[v]; }
             }
@@ -261,14 +261,15 @@ template <typename T, int VEC>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const T* __restrict__ dp, int64_t dp_ld,
                                    const T* __restrict__ add, int64_t add_ld, T* __restrict__ out, int64_t out_ld,
                                    int D, int H, int W, int C, int fd, int fh, int fw, int relu_mask, int64_t total) {
-    const int cvec = C / VEC;
+    const unsigned cvec = C / VEC;
     const int Do = D / fd, Ho = H / fh, Wo = W / fw;
     const int64_t So = (int64_t)Do * Ho * Wo, Si = (int64_t)D * H * W;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = blockIdx.y;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
         int cv = (int)(i % cvec);
-        int64_t vox = i / cvec;
-        int64_t n = vox / So, s = vox % So;
-        int wo = (int)(s % Wo), ho = (int)((s / Wo) % Ho), d_o = (int)(s / ((int64_t)Wo * Ho));
+        const unsigned s = i / cvec;
+        int64_t vox = n * So + s;
+        int wo = (int)(s % (unsigned)Wo), ho = (int)((s / (unsigned)Wo) % (unsigned)Ho), d_o = (int)(s / (unsigned)(Wo * Ho));
         float m[VEC];
         int arg[VEC];
 #pragma unroll
@@ -332,8 +333,8 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[v][0] = acc[v][1] = 0.f;
         if (active) {
-            for (int64_t s = blockIdx.x * (int64_t)blockDim.y + threadIdx.y; s < So; s += (int64_t)gridDim.x * blockDim.y) {
-                int wo = (int)(s % Wo), ho = (int)((s / Wo) % Ho), d_o = (int)(s / ((int64_t)Wo * Ho));
+            for (unsigned s = blockIdx.x * blockDim.y + threadIdx.y; s < (unsigned)So; s += gridDim.x * blockDim.y) {
+                int wo = (int)(s % (unsigned)Wo), ho = (int)((s / (unsigned)Wo) % (unsigned)Ho), d_o = (int)(s / (unsigned)(Wo * Ho));
                 int d0, d1, h0, h1, w0, w1;
                 float ld, lh, lw;
                 lerp_src(d_o, fd, D, d0, d1, ld);
@@ -353,7 +354,7 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __
                         for (int v = 0; v < VEC; ++v) r[v] = fmaf(wt, t[v], r[v]);
                     }
                 }
-                Vec<T, VEC>::store(yn + s * y_ld + cv * VEC, r);
+                Vec<T, VEC>::store(yn + (size_t)s * y_ld + cv * VEC, r);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
                     float q = round_as<T>(r[v]);
@@ -379,14 +380,15 @@ __device__ __forceinline__ float lerp_weight_to(int o, int f, int n, int i) {
 template <typename T, int VEC>
 __global__ void upsample_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, T* __restrict__ dx, int64_t dx_ld, int D,
                                     int H, int W, int C, int fd, int fh, int fw, int64_t total) {
-    const int cvec = C / VEC;
+    const unsigned cvec = C / VEC;
     const int Do = D * fd, Ho = H * fh, Wo = W * fw;
     const int64_t Si = (int64_t)D * H * W, So = (int64_t)Do * Ho * Wo;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = blockIdx.y;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
         int cv = (int)(i % cvec);
-        int64_t vox = i / cvec;
-        int64_t n = vox / Si, s = vox % Si;
-        int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+        const unsigned s = i / cvec;
+        int64_t vox = n * Si + s;
+        int w = (int)(s % (unsigned)W), h = (int)((s / (unsigned)W) % (unsigned)H), d = (int)(s / (unsigned)(W * H));
         // candidate outputs o with src(o) in [i-1, i+1]
         int dlo = fd == 1 ? d : max(0, fd * d - fd), dhi = fd == 1 ? d : min(Do - 1, fd * d + 2 * fd - 1);
         int hlo = fh == 1 ? h : max(0, fh * h - fh), hhi = fh == 1 ? h : min(Ho - 1, fh * h + 2 * fh - 1);
@@ -430,11 +432,12 @@ im2col_taps_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restric
     const int64_t S = (int64_t)D * H * W;
     const int groups = Kp / 8;
     const int kmax = kd * kh * kw * Cin;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i % groups);
-        const int64_t vox = i / groups;
-        const int64_t n = vox / S, s = vox % S;
-        const int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+    const int64_t n = blockIdx.y;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
+        const int g = (int)(i % (unsigned)groups);
+        const unsigned s = i / (unsigned)groups;
+        const int64_t vox = n * S + s;
+        const int w = (int)(s % (unsigned)W), h = (int)((s / (unsigned)W) % (unsigned)H), d = (int)(s / (unsigned)(W * H));
         const T* xn = x + n * S * x_ld;
         float sc = 1.f, sh = 0.f;
         if (CIN == 1 && in_ss) { sc = in_ss[n * 2]; sh = in_ss[n * 2 + 1]; }
@@ -463,9 +466,9 @@ im2col_taps_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restric
     }
 }
 
-static inline int flat_grid(int64_t total, int threads) {
+static inline int flat_grid(int64_t total, int threads, int N = 1) {
     int64_t b = (total + threads - 1) / threads;
-    int64_t cap = (int64_t)sm_count() * 16;
+    int64_t cap = (int64_t)sm_count() * 16 / (N > 0 ? N : 1) + 1;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (int)b;
@@ -559,11 +562,11 @@ int b200em_affine_apply(const void* x, int64_t x_ld, const float* scale_shift, v
     B2_DISPATCH_DTYPE(dtype, T, {
         constexpr int V = FullVec<T>::value;
         if (can_vec<T>(C, {x_ld, y_ld}, {x, y})) {
-            int64_t total = (int64_t)N * S * (C / V);
-            affine_apply_kernel<T, V><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, scale_shift, (T*)y, y_ld, S, C, total);
+            int64_t total = S * (C / V);
+            affine_apply_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, scale_shift, (T*)y, y_ld, S, C, total);
         } else {
-            int64_t total = (int64_t)N * S * C;
-            affine_apply_kernel<T, 1><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, scale_shift, (T*)y, y_ld, S, C, total);
+            int64_t total = S * C;
+            affine_apply_kernel<T, 1><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, scale_shift, (T*)y, y_ld, S, C, total);
         }
     })
     B2_LAUNCH_CHECK();
@@ -574,16 +577,18 @@ int b200em_norm_bwd_apply(const void* g, int64_t g_ld, const void* x, int64_t x_
                           int64_t add_ld, void* out, int64_t out_ld, int dtype, int N, int64_t S, int C, int relu_mask,
                           void* stream) {
     B2_CHECK_ARG(g && out && N > 0 && C > 0 && S > 0 && g_ld >= C && out_ld >= C, "norm_bwd_apply: bad arguments");
+    B2_CHECK_ARG(S * C < (1LL << 31) && N <= 65535, "norm_bwd_apply: sample too large for 32-bit indexing");
+    B2_CHECK_ARG(S * C < (1LL << 31) && N <= 65535, "norm_bwd_apply: sample too large for 32-bit indexing");
     B2_CHECK_ARG(x || (!coef && !relu_mask), "norm_bwd_apply: x is required with coef or relu_mask");
     B2_DISPATCH_DTYPE(dtype, T, {
         constexpr int V = FullVec<T>::value;
         if (can_vec<T>(C, {g_ld, x ? x_ld : (int64_t)V, add ? add_ld : (int64_t)V, out_ld}, {g, x, add, out})) {
-            int64_t total = (int64_t)N * S * (C / V);
-            norm_bwd_apply_kernel<T, V><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            int64_t total = S * (C / V);
+            norm_bwd_apply_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
                 (const T*)g, g_ld, (const T*)x, x_ld, coef, (const T*)add, add_ld, (T*)out, out_ld, S, C, relu_mask, total);
         } else {
-            int64_t total = (int64_t)N * S * C;
-            norm_bwd_apply_kernel<T, 1><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            int64_t total = S * C;
+            norm_bwd_apply_kernel<T, 1><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
                 (const T*)g, g_ld, (const T*)x, x_ld, coef, (const T*)add, add_ld, (T*)out, out_ld, S, C, relu_mask, total);
         }
     })
@@ -615,16 +620,17 @@ int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp
                          int relu_mask, void* stream) {
     B2_CHECK_ARG(x && dp && out && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "maxpool3d_bwd: bad arguments");
     B2_CHECK_ARG(D % fd == 0 && H % fh == 0 && W % fw == 0, "maxpool3d_bwd: dims not divisible by factors");
+    B2_CHECK_ARG((int64_t)D * H * W * C < (1LL << 31) && N <= 65535, "maxpool3d_bwd: sample too large for 32-bit indexing");
     int64_t So = (int64_t)(D / fd) * (H / fh) * (W / fw);
     B2_DISPATCH_DTYPE(dtype, T, {
         constexpr int V = FullVec<T>::value;
         if (can_vec<T>(C, {x_ld, dp_ld, add ? add_ld : (int64_t)V, out_ld}, {x, dp, add, out})) {
-            int64_t total = (int64_t)N * So * (C / V);
-            maxpool_bwd_kernel<T, V><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            int64_t total = So * (C / V);
+            maxpool_bwd_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
                 (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, (T*)out, out_ld, D, H, W, C, fd, fh, fw, relu_mask, total);
         } else {
-            int64_t total = (int64_t)N * So * C;
-            maxpool_bwd_kernel<T, 1><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            int64_t total = So * C;
+            maxpool_bwd_kernel<T, 1><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
                 (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, (T*)out, out_ld, D, H, W, C, fd, fh, fw, relu_mask, total);
         }
     })
@@ -654,14 +660,15 @@ int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, void* dx, int64
                                   int W, int C, int fd, int fh, int fw, void* stream) {
     B2_CHECK_ARG(dy && dx && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "upsample_bwd: bad arguments");
     int64_t Si = (int64_t)D * H * W;
+    B2_CHECK_ARG(Si * fd * fh * fw * C < (1LL << 31) && N <= 65535, "upsample_bwd: sample too large for 32-bit indexing");
     B2_DISPATCH_DTYPE(dtype, T, {
         constexpr int V = FullVec<T>::value;
         if (can_vec<T>(C, {dy_ld, dx_ld}, {dy, dx})) {
-            int64_t total = (int64_t)N * Si * (C / V);
-            upsample_bwd_kernel<T, V><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, fd, fh, fw, total);
+            int64_t total = Si * (C / V);
+            upsample_bwd_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, fd, fh, fw, total);
         } else {
-            int64_t total = (int64_t)N * Si * C;
-            upsample_bwd_kernel<T, 1><<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, fd, fh, fw, total);
+            int64_t total = Si * C;
+            upsample_bwd_kernel<T, 1><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, fd, fh, fw, total);
         }
     })
     B2_LAUNCH_CHECK();
@@ -673,9 +680,10 @@ int b200em_im2col_taps(const void* x, int64_t x_ld, const float* in_scale_shift,
     B2_CHECK_ARG(x && out && N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0, "im2col_taps: bad arguments");
     B2_CHECK_ARG(Kp % 8 == 0 && Kp >= kd * kh * kw * Cin, "im2col_taps: Kp must be a multiple of 8 and >= taps*Cin");
     B2_CHECK_ARG(aligned16(out), "im2col_taps: output must be 16-byte aligned");
-    int64_t total = (int64_t)N * D * H * W * (Kp / 8);
+    int64_t total = (int64_t)D * H * W * (Kp / 8);
+    B2_CHECK_ARG(total < (1LL << 31), "im2col_taps: sample too large for 32-bit indexing");
     B2_DISPATCH_DTYPE(dtype, T, {
-        const int grid = flat_grid(total, 256);
+        const dim3 grid(flat_grid(total, 256, N), N);
         cudaStream_t st = (cudaStream_t)stream;
         if (Cin == 1 && kd == 3 && kh == 3 && kw == 3)
             im2col_taps_kernel<T, 1, 3, 3, 3><<<grid, 256, 0, st>>>((const T*)x, x_ld, in_scale_shift, (__nv_bfloat16*)out, D, H, W, Cin, kd, kh, kw, Kp, total);

@@ -70,6 +70,8 @@ head_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ ou
 #pragma unroll
     for (int i = 0; i < HB_MAXCO / 8; ++i) accb_slots[i] = 0.f;
     const int npairs = Cout * Cin;
+    int rep = 1;
+    while (rep * 2 * npairs <= HB_TILE) rep *= 2;
     const int64_t ntiles = (total + HB_TILE - 1) / HB_TILE;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t vox = tile * HB_TILE + tid;
@@ -114,18 +116,30 @@ head_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ ou
             }
         }
         __syncthreads();
-        // dw[co][ci] partial over this tile: thread p handles pairs p, p+256, ...
+        // dw[co][ci] partial over this tile: thread p handles pairs p, p+256, ...; when there are fewer pairs than
+        // threads, `rep` threads share a pair and split the tile's voxels (all 256 threads stay busy)
         const int64_t v0 = tile * HB_TILE;
         const int nv = (int)((total - v0) < HB_TILE ? (total - v0) : HB_TILE);
-#pragma unroll
-        for (int i = 0; i < MAXP; ++i) {
-            const int p = tid + i * HB_TILE;
-            if (p < npairs) {
+        if (rep > 1) {
+            if (tid < rep * npairs) {
+                const int p = tid % npairs, sub = tid / npairs;
                 const int co = p / Cin, ci = p % Cin;
                 const T* xc = x + v0 * x_ld + ci;
                 float a = 0.f;
-                for (int v = 0; v < nv; ++v) a = fmaf(dzs[co][v], to_f<T>(xc[(size_t)v * x_ld]), a);
-                accp[i] += a;
+                for (int v = sub; v < nv; v += rep) a = fmaf(dzs[co][v], to_f<T>(xc[(size_t)v * x_ld]), a);
+                accp[0] += a;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < MAXP; ++i) {
+                const int p = tid + i * HB_TILE;
+                if (p < npairs) {
+                    const int co = p / Cin, ci = p % Cin;
+                    const T* xc = x + v0 * x_ld + ci;
+                    float a = 0.f;
+                    for (int v = 0; v < nv; ++v) a = fmaf(dzs[co][v], to_f<T>(xc[(size_t)v * x_ld]), a);
+                    accp[i] += a;
+                }
             }
         }
         // db: warp wi sums rows co = wi + 8*k
@@ -145,10 +159,17 @@ head_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ ou
         }
         __syncthreads();
     }
+    if (rep > 1) {
+        if (tid < rep * npairs) {
+            const int p = tid % npairs;
+            atomicAdd(dw + (size_t)(co_begin + p / Cin) * Cin + p % Cin, accp[0]);
+        }
+    } else {
 #pragma unroll
-    for (int i = 0; i < MAXP; ++i) {
-        const int p = tid + i * HB_TILE;
-        if (p < npairs) atomicAdd(dw + (size_t)(co_begin + p / Cin) * Cin + p % Cin, accp[i]);
+        for (int i = 0; i < MAXP; ++i) {
+            const int p = tid + i * HB_TILE;
+            if (p < npairs) atomicAdd(dw + (size_t)(co_begin + p / Cin) * Cin + p % Cin, accp[i]);
+        }
     }
     if (db && (tid & 31) == 0) {
         const int wi = tid >> 5;

@@ -243,37 +243,37 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
     dev = y1.device
     f32 = dict(dtype=torch.float32, device=dev)
 
-    def norm_back(g, x, mr, gamma_key, C, out, relu_mask):
+    def dgrad_and_norm_back(dz, conv, x, mr, gamma_key, out, relu_mask):
+        """g = dgrad(dz) (gradient w.r.t. the norm OUTPUT), then the norm backward (+ the producer's ReLU mask) -> out.
+        The two norm-backward reductions (sum g, sum g*x) come out of the dgrad kernel's epilogue."""
+        C = conv.cin
+        g = torch.empty(x.shape, dtype=x.dtype, device=dev)
         if norm is None:
+            B.conv(dz, None, packs[conv.key], None, g, None, conv.kernel, relu=False, dgrad=True)
+            if out is None:
+                return g
             B.norm_bwd_apply(g, x, None, None, out, relu_mask)
-            return
+            return out
         dsums = torch.zeros((N, C, 2), **f32)
-        B.channel_dot_sums(g, x, dsums)
+        B.conv(dz, None, packs[conv.key], None, g, dsums, conv.kernel, relu=False, dgrad=True, dot_x=x)
         gamma = P[gamma_key + ".weight"] if gamma_key else None
         dgamma = dbeta = None
         if gamma_key:
             dgamma, dbeta = grads[gamma_key + ".weight"], grads[gamma_key + ".bias"]
         coef = B.norm_bwd_finalize(dsums, mr, gamma, S, _groups(norm, C), dgamma, dbeta)
+        if out is None:
+            out = torch.empty_like(g)
         B.norm_bwd_apply(g, x, coef, None, out, relu_mask)
+        return out
 
     # conv2
     B.wgrad(y1, rec["ss2"], dz2, grads[c2.key + ".weight"], grads[c2.key + ".bias"], c2.kernel)
-    g2 = torch.empty_like(y1)
-    B.conv(dz2, None, packs[c2.key], None, g2, None, c2.kernel, relu=False, dgrad=True)
-    dz1 = torch.empty_like(y1)
-    norm_back(g2, y1, rec["mr2"], spec.norm2_key, c2.cin, dz1, relu_mask=1)
-    del g2
+    dz1 = dgrad_and_norm_back(dz2, c2, y1, rec["mr2"], spec.norm2_key, torch.empty_like(y1), relu_mask=1)
     # conv1
     B.wgrad(x_in, rec["ss1"], dz1, grads[c1.key + ".weight"], grads[c1.key + ".bias"], c1.kernel, aux=rec.get("aux1"))
     if not need_dx:
         return None
-    g1 = torch.empty(x_in.shape, dtype=x_in.dtype, device=dev)
-    B.conv(dz1, None, packs[c1.key], None, g1, None, c1.kernel, relu=False, dgrad=True)
-    if norm is None:
-        return g1
-    dx = torch.empty_like(g1)
-    norm_back(g1, x_in, rec["mr1"], spec.norm1_key, c1.cin, dx, relu_mask=0)
-    return dx
+    return dgrad_and_norm_back(dz1, c1, x_in, rec["mr1"], spec.norm1_key, None, relu_mask=0)
 
 
 class FlatGrads(dict):
