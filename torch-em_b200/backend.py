@@ -315,5 +315,6 @@ def default_backend():
     global _default
     if _default is None:
         _lib.load()
-        _default = CudaBackend()
+        import os
+        _default = CudaBackend(use_s3=os.environ.get("B200EM_S3", "0") == "1")
     return _default

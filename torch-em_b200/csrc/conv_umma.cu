@@ -55,13 +55,19 @@ struct ConvUmmaParams {
     int a_bytes, b_stage_bytes;
 };
 
-__device__ __forceinline__ void item_coords(const ConvUmmaParams& p, long long item, int& n, int& d0, int& h0, int& w0) {
-    int tw = (int)(item % p.tiles_w); item /= p.tiles_w;
-    int th = (int)(item % p.tiles_h); item /= p.tiles_h;
-    int td = (int)(item % p.tiles_d); item /= p.tiles_d;
-    n = (int)item; d0 = td * p.R; h0 = th * TH; w0 = tw * TW;
+// 32-bit arithmetic on purpose: 64-bit division is a ~100-instruction software routine and this runs per work item in
+// every warp role.
+__device__ __forceinline__ void item_coords(const ConvUmmaParams& p, long long item_, int& n, int& d0, int& h0, int& w0) {
+    unsigned item = (unsigned)item_;
+    const unsigned tw = item % (unsigned)p.tiles_w; item /= (unsigned)p.tiles_w;
+    const unsigned th = item % (unsigned)p.tiles_h; item /= (unsigned)p.tiles_h;
+    const unsigned td = item % (unsigned)p.tiles_d; item /= (unsigned)p.tiles_d;
+    n = (int)item; d0 = (int)td * p.R; h0 = (int)th * TH; w0 = (int)tw * TW;
 }
 
+// R_ = depth slabs per work item, KC_ = K=16 steps per channel chunk: compile-time so that the single-thread MMA issue
+// loop is straight-line code with immediate operand offsets (it bounds the small-N layers otherwise).
+template <int R_, int KC_>
 __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     // carve: A[2] | B[NSTAGE] | bias[NP] | sums[2*NP] | barriers | tmem ptr
@@ -81,8 +87,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = blockIdx.y;                    // 256-wide output-channel block (Cout > 256)
-    const int J = p.CC / 8;                         // planes per slice per chunk
-    const int kc = p.CC / 16;                       // K=16 MMA steps per chunk
+    constexpr int J = KC_ * 2;                      // 8-channel planes per slice per chunk
     const int taps = p.kd * p.kh * p.kw;
     const int ngroups = taps / p.G;
     const int nslices = p.R + p.kd - 1;
@@ -92,9 +97,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
     while (tmem_cols < acc_cols * p.acc_bufs) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], NLOAD); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], NLOAD / 32); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_mbar_init();
     }
     if (warp == W_MMA) tmem_alloc(s_tmem, tmem_cols);
@@ -138,7 +143,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                 load_halo_tile_async<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * PLANE, t / J, NLOAD / J, units, d0, h0, w0, pd,
                                p.D, p.H, p.W);
                 fence_proxy_async();
-                mbar_arrive(&a_full[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[buf]);
             }
         }
     } else if (warp == W_WLOAD) {
@@ -159,54 +165,53 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
-        // One thread issues every MMA, so the per-MMA instruction count is what bounds small-N layers: descriptors
-        // are built once and only their 14-bit start-address field is bumped (independent adds, fully unrolled).
+        // One thread issues every MMA, so the per-MMA instruction count is what bounds small-N layers: descriptors are
+        // built once, only their 14-bit start-address field changes, and with R_/KC_ known at compile time the per-tap
+        // body is R_*KC_ MMAs whose operand offsets are immediates.
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(128, p.NP);
-            const uint32_t a_hi = (uint32_t)(make_desc(0, PLANE, WP * 16) >> 32);
-            const uint32_t b_hi = (uint32_t)(make_desc(0, (uint32_t)(p.NP * 16), 128) >> 32);
-            const uint32_t a_lo_c = (uint32_t)(make_desc(0, PLANE, WP * 16) & 0xFFFFFFFFu);   // LBO field (bits 16..29)
-            const uint32_t b_lo_c = (uint32_t)(make_desc(0, (uint32_t)(p.NP * 16), 128) & 0xFFFFFFFFu);
-            const uint32_t a_base16 = smem_u32(smA) >> 4, b_base16 = smem_u32(smB) >> 4;
-            const uint32_t b_tap16 = (uint32_t)(J * p.NP);
-            const uint32_t slab16 = (uint32_t)(J * (PLANE / 16)), k16 = (uint32_t)(2 * (PLANE / 16));
-            const uint32_t np = (uint32_t)p.NP;
+            const uint64_t ad = make_desc(0, PLANE, WP * 16), bd = make_desc(0, (uint32_t)(p.NP * 16), 128);
+            const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
+            const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
+            const uint32_t b_lo_base = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smB) >> 4);
+            constexpr uint32_t SLAB16 = J * (PLANE / 16), K16 = 2 * (PLANE / 16);
+            const uint32_t np = (uint32_t)p.NP, b_tap16 = (uint32_t)(J * p.NP), bk16 = 2 * np;
+            const uint32_t a_bytes16 = (uint32_t)(p.a_bytes >> 4), bstage16 = (uint32_t)(p.b_stage_bytes >> 4);
             uint32_t fill = 0, cnt = 0, it = 0;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-                int n, d0, h0, w0;
-                item_coords(p, item, n, d0, h0, w0);
                 const int slot = (p.acc_bufs == 2) ? (it & 1) : 0;
                 const uint32_t use = (p.acc_bufs == 2) ? (it >> 1) : it;
                 mbar_wait(&acc_empty[slot], (use & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + slot * acc_cols;
-                const int rmax = min(p.R, p.D - d0);
+                uint32_t tcol[R_];
+#pragma unroll
+                for (int r = 0; r < R_; ++r) tcol[r] = tmem_base + slot * acc_cols + r * np;
                 for (int c = 0; c < p.nchunks; ++c, ++fill) {
                     const int buf = fill & 1;
                     mbar_wait(&a_full[buf], (fill >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t abuf16 = a_base16 + (uint32_t)((buf * p.a_bytes) >> 4);
+                    const uint32_t abuf = a_lo_base + buf * a_bytes16;
                     for (int g = 0; g < ngroups; ++g, ++cnt) {
                         const int st = cnt % NSTAGE;
                         mbar_wait(&b_full[st], (cnt / NSTAGE) & 1);
                         tc_fence_after();
-                        const uint32_t bst16 = b_base16 + (uint32_t)((st * p.b_stage_bytes) >> 4);
+                        const uint32_t bst = b_lo_base + st * bstage16;
                         for (int tg = 0; tg < p.G; ++tg) {
                             const int tap = g * p.G + tg;
-                            const uint32_t a0 = a_lo_c + abuf16 + s_tap[tap];
-                            const uint32_t b0 = b_lo_c + bst16 + tg * b_tap16;
-                            const uint32_t acc0 = (uint32_t)(c | tap);
+                            const uint32_t a0 = abuf + s_tap[tap];
+                            const uint32_t b0 = bst + tg * b_tap16;
+                            // slabs beyond the volume (d0 + r >= D) read zero-filled slices: computed, never stored
+                            if ((c | tap) == 0) {
 #pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                if (r < rmax) {
+                                for (int r = 0; r < R_; ++r) {
+                                    umma_bf16_c<false>(tcol[r], a0 + r * SLAB16, a_hi, b0, b_hi, idesc);
+                                    if (KC_ == 2) umma_bf16_c<true>(tcol[r], a0 + r * SLAB16 + K16, a_hi, b0 + bk16, b_hi, idesc);
+                                }
+                            } else {
 #pragma unroll
-                                    for (int k = 0; k < 2; ++k) {
-                                        if (k < kc) {
-                                            const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a0 + r * slab16 + k * k16);
-                                            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b0 + k * 2 * np);
-                                            umma_bf16(tacc + r * np, adesc, bdesc, idesc, acc0 | (uint32_t)k);
-                                        }
-                                    }
+                                for (int r = 0; r < R_; ++r) {
+                                    umma_bf16_c<true>(tcol[r], a0 + r * SLAB16, a_hi, b0, b_hi, idesc);
+                                    if (KC_ == 2) umma_bf16_c<true>(tcol[r], a0 + r * SLAB16 + K16, a_hi, b0 + bk16, b_hi, idesc);
                                 }
                             }
                         }
@@ -337,7 +342,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[slot]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[slot]);
             if (p.sums) {
                 // flush this item's per-channel partial sums (n may change with the next item)
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -460,7 +466,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
     while (tmem_cols < (uint32_t)(tap9 * p.NB)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], NLOAD); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], NLOAD / 32); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
@@ -479,11 +485,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    auto coords = [&](long long item, int& n, int& d0, int& h0, int& w0) {
-        int tw = (int)(item % p.tiles_w); item /= p.tiles_w;
-        int th = (int)(item % p.tiles_h); item /= p.tiles_h;
-        int td = (int)(item % p.tiles_d); item /= p.tiles_d;
-        n = (int)item; d0 = td * WG_R; h0 = th * TH; w0 = tw * TW;
+    auto coords = [&](long long item_, int& n, int& d0, int& h0, int& w0) {      // 32-bit: see item_coords
+        unsigned item = (unsigned)item_;
+        const unsigned tw = item % (unsigned)p.tiles_w; item /= (unsigned)p.tiles_w;
+        const unsigned th = item % (unsigned)p.tiles_h; item /= (unsigned)p.tiles_h;
+        const unsigned td = item % (unsigned)p.tiles_d; item /= (unsigned)p.tiles_d;
+        n = (int)item; d0 = (int)td * WG_R; h0 = (int)th * TH; w0 = (int)tw * TW;
     };
 
     if (warp >= 4 && warp < W_WLOAD) {
@@ -491,9 +498,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
         const int t = threadIdx.x - 128;
         const int j = t % J, jo = t % JO;
         const int xunits = nslices * HP * WP, zunits = WG_R * TH * TW;
-        float dbacc[8];
+        float dbacc[8], sc[8], sh[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dbacc[e] = 0.f;
+        for (int e = 0; e < 8; ++e) { dbacc[e] = 0.f; sc[e] = 1.f; sh[e] = 0.f; }
+        int cur_n = -1;
         uint32_t fill = 0;
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++fill) {
             int n, d0, h0, w0;
@@ -501,23 +509,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
             const int buf = fill & 1;
             mbar_wait(&empty[buf], ((fill >> 1) & 1) ^ 1);
             const int ch0 = chunk * 32 + j * 8;
-            float sc[8], sh[8];
-            if (p.in_ss) {
+            if (p.in_ss && n != cur_n) {           // scale/shift of this thread's 8 channels: reload only when the sample changes
                 const float* q = p.in_ss + ((size_t)n * p.Cin + ch0) * 2;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
+                cur_n = n;
             }
             uint8_t* xdst = smX + buf * p.x_bytes + j * PLANE;
             const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
-            if (!(p.debug & 1))
-                load_halo_tile_async<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, xdst, J * PLANE, t / J, NLOAD / J, xunits, d0, h0, w0, pd,
-                                       p.D, p.H, p.W);
             uint8_t* zdst = smZ + buf * p.dz_bytes + jo * WG_DZ_PLANE;
             const __nv_bfloat16* zn = p.dz + (size_t)n * p.D * p.H * p.W * p.dz_ld + cob * p.NB + jo * 8;
             const int zstep = NLOAD / JO;
-            {
+            if (!(p.debug & 1)) {
+                // dz slabs: plain copies, issued first; the wait inside load_halo_tile_async covers them as well
                 const uint32_t z32 = smem_u32(zdst);
-                for (int v = t / JO; v < ((p.debug & 1) ? 0 : zunits); v += zstep) {
+                for (int v = t / JO; v < zunits; v += zstep) {
                     const int wl = v % TW, hl = (v / TW) % TH, r = v / (TW * TH);
                     const int gd = d0 + r, gh = h0 + hl, gw = w0 + wl;
                     const bool in = gd < p.D && gh < p.H && gw < p.W;
@@ -526,7 +532,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
                                  "l"(src), "r"(in ? 16 : 0)
                                  : "memory");
                 }
-                asm volatile("cp.async.wait_all;" ::: "memory");
+                load_halo_tile_async<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, xdst, J * PLANE, t / J, NLOAD / J, xunits, d0, h0, w0, pd,
+                                             p.D, p.H, p.W);
                 if (p.db && chunk == 0) {
                     for (int v = t / JO; v < zunits; v += zstep) {
                         const int wl = v % TW, hl = (v / TW) % TH, r = v / (TW * TH);
@@ -542,7 +549,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
                 }
             }
             fence_proxy_async();
-            mbar_arrive(&full[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[buf]);
         }
         if (p.db && chunk == 0) {
 #pragma unroll
@@ -571,17 +579,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
                 for (int r = 0; r < rmax; ++r) {
                     const uint32_t xs = a_lo_c + x_base16 + (uint32_t)((buf * p.x_bytes + r * J * PLANE) >> 4);
                     const uint32_t zs = b_lo_c + z_base16 + (uint32_t)((buf * p.dz_bytes + r * JO * WG_DZ_PLANE) >> 4);
-                    const uint32_t acc0 = fill | (uint32_t)r;
+                    const bool first = (fill | (uint32_t)r) == 0;      // very first slab of this CTA: overwrite the accumulators
+                    if (p.debug & 4) continue;
                     for (int tp = 0; tp < tap9; ++tp) {
                         const uint32_t a0 = xs + s_tap9[tp];
                         const uint32_t tacc = tmem_base + tp * nb;
+                        // K step ks = voxel rows hl = 2ks, 2ks+1 (8 voxels each); offsets are immediates
+                        if (first) umma_bf16_c<false>(tacc, a0, a_hi, zs, b_hi, idesc);
+                        else umma_bf16_c<true>(tacc, a0, a_hi, zs, b_hi, idesc);
 #pragma unroll
-                        for (int ks = 0; ks < TH / 2; ++ks) {
-                            // K step = voxel rows hl = 2ks, 2ks+1 (8 voxels each)
-                            const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a0 + ks * 2 * WP);
-                            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(zs + ks * 2 * TW);
-                            if (!(p.debug & 4)) umma_bf16(tacc, adesc, bdesc, idesc, acc0 | (uint32_t)ks);
-                        }
+                        for (int ks = 1; ks < TH / 2; ++ks)
+                            umma_bf16_c<true>(tacc, a0 + ks * 2 * WP, a_hi, zs + ks * 2 * TW, b_hi, idesc);
                     }
                 }
                 umma_commit(&empty[buf]);
@@ -675,12 +683,24 @@ int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift,
     p.R = s.R; p.NP = s.NP; p.CC = s.CC; p.nchunks = Cin / s.CC; p.G = s.G; p.acc_bufs = s.acc_bufs;
     p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + s.R - 1) / s.R;
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
     p.a_bytes = s.a_bytes; p.b_stage_bytes = s.b_stage_bytes;
-    B2_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     long long gx = p.items < sm_count() / s.nblk ? p.items : sm_count() / s.nblk;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)s.nblk, 1);
-    conv3d_umma_kernel<<<grid, THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);
+#define B2_UMMA_LAUNCH(R_, KC_)                                                                                             \
+    do {                                                                                                                    \
+        B2_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<R_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));    \
+        conv3d_umma_kernel<R_, KC_><<<grid, THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                                \
+    } while (0)
+    const int kc = s.CC / 16;
+    if (s.R == 4 && kc == 2) B2_UMMA_LAUNCH(4, 2);
+    else if (s.R == 4) B2_UMMA_LAUNCH(4, 1);
+    else if (s.R == 2 && kc == 2) B2_UMMA_LAUNCH(2, 2);
+    else if (s.R == 2) B2_UMMA_LAUNCH(2, 1);
+    else if (kc == 2) B2_UMMA_LAUNCH(1, 2);
+    else B2_UMMA_LAUNCH(1, 1);
+#undef B2_UMMA_LAUNCH
     B2_LAUNCH_CHECK();
     return 0;
 }
@@ -707,6 +727,7 @@ int b200em_conv3d_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_
     p.NB = NB; p.nco = Cout / NB;
     p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + WG_R - 1) / WG_R;
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
     p.x_bytes = (WG_R + kd - 1) * 4 * PLANE;
     p.dz_bytes = WG_R * (NB / 8) * WG_DZ_PLANE;
     { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }

@@ -29,7 +29,9 @@ constexpr int S3_WOUT = S3_TWR - 2;             // output columns per tile
 constexpr int S3_HP = S3_TH + 2, S3_WP = S3_TWR;
 constexpr int S3_PLANE = S3_HP * S3_WP * 16 + 32;   // +32 B: staggers the 8-channel planes across banks for the loader's stores
 constexpr int S3_NSTAGE = 4;
-constexpr int S3_THREADS = 320;
+constexpr int S3_NLOAD = 256;                    // operand-loader threads (8 warps)
+constexpr int S3_THREADS = 128 + S3_NLOAD + 64;
+constexpr int S3_W_WLOAD = (128 + S3_NLOAD) / 32, S3_W_MMA = S3_W_WLOAD + 1;
 constexpr int S3_MAX_SMEM = 227 * 1024;
 }  // namespace
 
@@ -50,11 +52,14 @@ struct ConvS3Params {
     int debug;                       // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 2 no epilogue math, 4 no MMAs
 };
 
-__device__ __forceinline__ void s3_coords(const ConvS3Params& p, long long item, int& n, int& d0, int& h0, int& w0) {
-    int tw = (int)(item % p.tiles_w); item /= p.tiles_w;
-    int th = (int)(item % p.tiles_h); item /= p.tiles_h;
-    int td = (int)(item % p.tiles_d); item /= p.tiles_d;
-    n = (int)item; d0 = td * p.R; h0 = th * S3_TH; w0 = tw * S3_WOUT;
+// 32-bit arithmetic on purpose: 64-bit division is a ~100-instruction software routine and this runs per work item in
+// every warp role (it was the largest fixed cost of the pipeline).
+__device__ __forceinline__ void s3_coords(const ConvS3Params& p, long long item_, int& n, int& d0, int& h0, int& w0) {
+    unsigned item = (unsigned)item_;
+    const unsigned tw = item % (unsigned)p.tiles_w; item /= (unsigned)p.tiles_w;
+    const unsigned th = item % (unsigned)p.tiles_h; item /= (unsigned)p.tiles_h;
+    const unsigned td = item % (unsigned)p.tiles_d; item /= (unsigned)p.tiles_d;
+    n = (int)item; d0 = (int)td * p.R; h0 = (int)th * S3_TH; w0 = (int)tw * S3_WOUT;
 }
 
 // One NV-wide block of output channels of one slab: shifted sum of the three w-tap partials, bias, ReLU, bf16 store,
@@ -135,10 +140,13 @@ __device__ __forceinline__ void s3_flush_stats(float* acc_s, float* acc_q, float
 }
 
 // CO = Cout (16..80, multiple of 16): compile-time so that the epilogue's channel blocks and accumulators are static.
-template <int CO>
+// KC_ = K=16 steps per channel chunk (1 or 2); the slab count R follows from CO (TMEM budget) -- all compile-time so
+// the single-thread MMA issue loop is straight-line code with immediate operand offsets.
+template <int CO, int KC_>
 __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const ConvS3Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int N3 = 3 * p.Cout;
+    constexpr int N3 = 3 * CO;
+    constexpr int R_ = (2 * 4 * N3 <= 512) ? 4 : (2 * 2 * N3 <= 512) ? 2 : 1;     // must match s3_shape()
     uint8_t* smA = smem;
     uint8_t* smB = smA + 2 * p.a_bytes;
     const int b_region = p.resident ? p.nchunks * p.kd * p.kh * p.b_stage_bytes : S3_NSTAGE * p.b_stage_bytes;
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
     uint32_t* s_tap = s_tmem + 2;                   // [9] start offset of each (a,b) tap, 16-byte units
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int J = p.CC / 8, kc = p.CC / 16;
+    constexpr int J = KC_ * 2;
     const int ntap = p.kd * p.kh;
     const int nslices = p.R + p.kd - 1;
     const int pd = p.kd / 2, ph = p.kh / 2;
@@ -164,12 +172,12 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
     while (tmem_cols < acc_cols * p.acc_bufs) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], S3_NLOAD / 32); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < S3_NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);   }
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(s_tmem, tmem_cols);
+    if (warp == S3_W_MMA) tmem_alloc(s_tmem, tmem_cols);
     if (threadIdx.x < ntap) {
         const int a = threadIdx.x / p.kh, b = threadIdx.x % p.kh;
         s_tap[threadIdx.x] = (uint32_t)((a * J * S3_PLANE + (b + 1 - ph) * S3_WP * 16) >> 4);
@@ -184,18 +192,21 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < S3_W_WLOAD) {
         // ===================== operand loaders =====================
         const int t = threadIdx.x - 128;
         const int j = t % J;
         const int units = nslices * S3_HP * S3_WP;
         uint32_t fill = 0;
+        long long prof_wait = 0, prof_t0 = clock64();
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
             int n, d0, h0, w0;
             s3_coords(p, item, n, d0, h0, w0);
             for (int c = 0; c < p.nchunks; ++c, ++fill) {
                 const int buf = fill & 1;
+                const long long tq0 = clock64();
                 mbar_wait(&a_empty[buf], ((fill >> 1) & 1) ^ 1);
+                prof_wait += clock64() - tq0;
                 const int ch0 = c * p.CC + j * 8;
                 float sc[8], sh[8];
                 if (p.in_ss) {
@@ -206,13 +217,16 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
                 uint8_t* dstbase = smA + buf * p.a_bytes + j * S3_PLANE;
                 const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
                 if (!(p.debug & 1))
-                    load_halo_tile<S3_HP, S3_WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * S3_PLANE, t / J, 128 / J, units,
+                    load_halo_tile_async<S3_HP, S3_WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * S3_PLANE, t / J, S3_NLOAD / J, units,
                                                  d0, h0, w0, pd, p.D, p.H, p.W);
                 fence_proxy_async();
-                mbar_arrive(&a_full[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[buf]);
             }
         }
-    } else if (warp == 8) {
+        if ((p.debug & 8) && blockIdx.x == 0 && t == 0)
+            printf("[s3 prof] loader: total %lld cyc, waiting a_empty %lld, fills %u\n", clock64() - prof_t0, prof_wait, fill);
+    } else if (warp == S3_W_WLOAD) {
         // ===================== weight loader: one (a,b) tap (all three w-taps stacked) per stage =====================
         if (elect_one()) {
             const uint32_t bytes = (uint32_t)p.b_stage_bytes;
@@ -234,54 +248,53 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
                         }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == S3_W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(128, N3);
+            constexpr uint32_t idesc = make_idesc_bf16(128, N3);
             const uint64_t ad = make_desc(0, S3_PLANE, 128), bd = make_desc(0, (uint32_t)(N3 * 16), 128);
-            const uint32_t a_hi = (uint32_t)(ad >> 32), a_lo_c = (uint32_t)(ad & 0xFFFFFFFFu);
-            const uint32_t b_hi = (uint32_t)(bd >> 32), b_lo_c = (uint32_t)(bd & 0xFFFFFFFFu);
-            const uint32_t a_base16 = smem_u32(smA) >> 4, b_base16 = smem_u32(smB) >> 4;
-            const uint32_t slab16 = (uint32_t)(J * (S3_PLANE / 16)), k16 = (uint32_t)(2 * (S3_PLANE / 16));
-            const uint32_t n3 = (uint32_t)N3;
+            const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
+            const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
+            const uint32_t b_lo_base = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smB) >> 4);
+            constexpr uint32_t SLAB16 = J * (S3_PLANE / 16), K16 = 2 * (S3_PLANE / 16), BK16 = 2 * N3;
+            const uint32_t a_bytes16 = (uint32_t)(p.a_bytes >> 4), bstage16 = (uint32_t)(p.b_stage_bytes >> 4);
             uint32_t fill = 0, cnt = 0, it = 0;
             if (p.resident) {
                 mbar_wait(&b_full[0], 0);
                 tc_fence_after();
             }
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-                int n, d0, h0, w0;
-                s3_coords(p, item, n, d0, h0, w0);
                 const int slot = (p.acc_bufs == 2) ? (it & 1) : 0;
                 const uint32_t use = (p.acc_bufs == 2) ? (it >> 1) : it;
                 mbar_wait(&acc_empty[slot], (use & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + slot * acc_cols;
-                const int rmax = min(p.R, p.D - d0);
                 for (int c = 0; c < p.nchunks; ++c, ++fill) {
                     const int buf = fill & 1;
                     mbar_wait(&a_full[buf], (fill >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t abuf16 = a_base16 + (uint32_t)((buf * p.a_bytes) >> 4);
+                    const uint32_t abuf = a_lo_base + buf * a_bytes16;
                     for (int g = 0; g < ntap; ++g, ++cnt) {
                         const int st = p.resident ? c * ntap + g : (int)(cnt % S3_NSTAGE);
                         if (!p.resident) {
                             mbar_wait(&b_full[st], (cnt / S3_NSTAGE) & 1);
                             tc_fence_after();
                         }
-                        const uint32_t a0 = a_lo_c + abuf16 + s_tap[g];
-                        const uint32_t b0 = b_lo_c + b_base16 + (uint32_t)((st * p.b_stage_bytes) >> 4);
-                        const uint32_t acc0 = (uint32_t)(c | g);
+                        const uint32_t a0 = abuf + s_tap[g];
+                        const uint32_t b0 = b_lo_base + st * bstage16;
+                        if (!(p.debug & 4)) {
+                            // slabs beyond the volume (d0 + r >= D) read zero-filled slices: computed, never stored
+                            if ((c | g) == 0) {
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            if (r < rmax) {
+                                for (int r = 0; r < R_; ++r) {
+                                    umma_bf16_c<false>(tacc + r * N3, a0 + r * SLAB16, a_hi, b0, b_hi, idesc);
+                                    if (KC_ == 2) umma_bf16_c<true>(tacc + r * N3, a0 + r * SLAB16 + K16, a_hi, b0 + BK16, b_hi, idesc);
+                                }
+                            } else {
 #pragma unroll
-                                for (int k = 0; k < 2; ++k) {
-                                    if (k < kc && !(p.debug & 4)) {
-                                        const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(a0 + r * slab16 + k * k16);
-                                        const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b0 + k * 2 * n3);
-                                        umma_bf16(tacc + r * n3, adesc, bdesc, idesc, acc0 | (uint32_t)k);
-                                    }
+                                for (int r = 0; r < R_; ++r) {
+                                    umma_bf16_c<true>(tacc + r * N3, a0 + r * SLAB16, a_hi, b0, b_hi, idesc);
+                                    if (KC_ == 2) umma_bf16_c<true>(tacc + r * N3, a0 + r * SLAB16 + K16, a_hi, b0 + BK16, b_hi, idesc);
                                 }
                             }
                         }
@@ -314,6 +327,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
             asm volatile("bar.sync 1, 128;" ::: "memory");
         };
         uint32_t it = 0;
+        long long pe_wait = 0, pe_t0 = clock64();
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
             int n, d0, h0, w0;
             s3_coords(p, item, n, d0, h0, w0);
@@ -323,7 +337,9 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
                 if (cur_n >= 0) flush(cur_n);
                 cur_n = n;
             }
+            const long long tq = clock64();
             mbar_wait(&acc_full[slot], use & 1);
+            pe_wait += clock64() - tq;
             tc_fence_after();
             const int gh = h0 + hl, gw = w0 + wr - 1;
             const bool valid = wr >= 1 && wr <= S3_WOUT && gh < p.H && gw < p.W;
@@ -348,14 +364,17 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv3d_umma_s3_kernel(const Con
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[slot]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[slot]);
         }
         if (p.sums && cur_n >= 0) flush(cur_n);
+        if ((p.debug & 8) && blockIdx.x == 0 && threadIdx.x == 0)
+            printf("[s3 prof] epilogue: total %lld cyc, waiting acc_full %lld, items %u\n", clock64() - pe_t0, pe_wait, it);
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == S3_W_MMA) {
         __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
@@ -450,13 +469,24 @@ int b200em_conv3d_umma_s3(const void* x, int64_t x_ld, const float* in_scale_shi
     p.R = s.R; p.CC = s.CC; p.nchunks = Cin / s.CC; p.acc_bufs = s.acc_bufs;
     p.tiles_w = (W + S3_WOUT - 1) / S3_WOUT; p.tiles_h = (H + S3_TH - 1) / S3_TH; p.tiles_d = (D + s.R - 1) / s.R;
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
     p.a_bytes = s.a_bytes; p.b_stage_bytes = s.b_stage_bytes; p.resident = s.resident;
     { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
     long long gx = p.items < sm_count() ? p.items : sm_count();
-#define B2_S3_LAUNCH(CO_)                                                                                                   \
-    case CO_:                                                                                                               \
-        B2_CUDA(cudaFuncSetAttribute(conv3d_umma_s3_kernel<CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_MAX_SMEM)); \
-        conv3d_umma_s3_kernel<CO_><<<(unsigned)gx, S3_THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                     \
+    {
+        const int N3 = 3 * Cout;
+        const int r_expected = (2 * 4 * N3 <= 512) ? 4 : (2 * 2 * N3 <= 512) ? 2 : 1;
+        B2_CHECK_ARG(s.R == r_expected, "conv3d_umma_s3: internal slab-count mismatch (%d vs %d)", s.R, r_expected);
+    }
+#define B2_S3_LAUNCH(CO_)                                                                                                          \
+    case CO_:                                                                                                                      \
+        if (s.CC == 32) {                                                                                                          \
+            B2_CUDA(cudaFuncSetAttribute(conv3d_umma_s3_kernel<CO_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_MAX_SMEM)); \
+            conv3d_umma_s3_kernel<CO_, 2><<<(unsigned)gx, S3_THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                     \
+        } else {                                                                                                                   \
+            B2_CUDA(cudaFuncSetAttribute(conv3d_umma_s3_kernel<CO_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_MAX_SMEM)); \
+            conv3d_umma_s3_kernel<CO_, 1><<<(unsigned)gx, S3_THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                     \
+        }                                                                                                                          \
         break;
     switch (Cout) {
         B2_S3_LAUNCH(16)

@@ -78,6 +78,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
+// Same, accumulate flag known at compile time (no setp from a register in the single-thread issue loop).
+template <bool ACC>
+__device__ __forceinline__ void umma_bf16_c(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    if (ACC) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.eq.u32 p, 1, 1;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.u32 p, 1, 1;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+            : "memory");
+    }
+}
+
 // Shared-memory matrix descriptor, SWIZZLE_NONE ("interleave"), version 1 (Blackwell).
 // K-major operand: 8-row x 16-byte core matrices, each 128 contiguous bytes (row r of the core matrix at +16*r);
 //   lbo = byte distance between the two 16-byte K-chunks of one K=16 step, sbo = byte distance between 8-row groups.
