@@ -101,6 +101,19 @@ int b200em_conv3d_umma_s3(const void* x, int64_t x_ld, const float* in_scale_shi
                           void* y, int64_t y_ld, float* sums, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
                           int kw, int relu, void* stream);
 
+/* "depth-stacked" tcgen05 variant for 3 x kh x kw filters with few output channels (Cout <= 80) whose packed filter
+ * fits in shared memory: the three depth taps share one operand fetch (N = 3*Cout) and land in the accumulators of
+ * three consecutive output slices (a ring of TMEM column blocks); every input slice is staged once per column of
+ * output slices (csrc/conv_umma_ds.cu).  Replaces nn.Conv3d forward / autograd dgrad of the shallow wide levels
+ * (unet.py:429-438).  Same contract and arguments as b200em_conv3d_umma (incl. dot_x); its own packed weight layout
+ * (b200em_conv3d_umma_ds_pack, Cout*Cin*taps bf16). */
+int b200em_conv3d_umma_ds_supported(int Cin, int Cout, int kd, int kh, int kw);
+int b200em_conv3d_umma_ds_pack(const float* w, int Cout, int Cin, int kd, int kh, int kw, int dgrad, void* packed,
+                               void* stream);
+int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+                          void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W,
+                          int Cin, int Cout, int kd, int kh, int kw, int relu, void* stream);
+
 /* Weight gradient on the tensor cores (bf16 operands, fp32 accumulation in TMEM, fp32 atomics into dw).
  * dw (Cout,Cin,kd,kh,kw) fp32 += sum dz * x_hat (same contract as b200em_conv3d_wgrad_direct); db (nullable)
  * (Cout) fp32 += sum dz -- the bias gradient, fused into the dz operand load.  Takes Cin % 32 == 0, Cout % 16 == 0. */

@@ -12,7 +12,7 @@ __device__ __forceinline__ uint64_t mk(uint32_t saddr, uint32_t lbo, uint32_t sb
 }
 
 // layout: 0 none, 2 sw128, 4 sw64, 6 sw32
-__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int layout, int nacc, int iters, int amode, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int layout, int nacc, int iters, int amode, long long* out, int a_shift16 = 0, int sbo_a_override = 0) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem;
@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int layout, int nac
         else if (layout == 2) { lbo_a = 16; sbo_a = 1024; lbo_b = 16; sbo_b = 1024; kadv = 32; }
         else if (layout == 4) { lbo_a = 16; sbo_a = 512; lbo_b = 16; sbo_b = 512; kadv = 32; }
         else { lbo_a = 16; sbo_a = 256; lbo_b = 16; sbo_b = 256; kadv = 0; }
-        const uint64_t ad0 = mk(a_addr, lbo_a, sbo_a, layout), bd0 = mk(b_addr, lbo_b, sbo_b, layout);
+        if (sbo_a_override) sbo_a = sbo_a_override;
+        const uint64_t ad0 = mk(a_addr + 16 * a_shift16, lbo_a, sbo_a, layout), bd0 = mk(b_addr, lbo_b, sbo_b, layout);
         const long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
 #pragma unroll
@@ -63,9 +64,9 @@ int main() {
     const char* names[4] = {"none", "sw32", "sw64", "sw128"};
     int Ns[5] = {32, 64, 96, 128, 256};
     printf("cycles per MMA (M=128,K=16,bf16,cta_group::1), all 148 SMs busy; ideal = N/2\n");
-    for (int amode = 0; amode < 2; ++amode)
-        for (int li = 0; li < 4; ++li)
-            for (int nacc = 1; nacc <= 4; nacc *= 2)
+    for (int amode = 0; amode < 1; ++amode)
+        for (int li = 0; li < 1; ++li)
+            for (int nacc = 1; nacc <= 1; nacc *= 2)
                 for (int ni = 0; ni < 5; ++ni) {
                     int N = Ns[ni];
                     if (nacc * N > 512) continue;
@@ -75,5 +76,17 @@ int main() {
                     long long c; cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
                     printf("amode %d layout %-5s nacc %d N %3d : %7.1f cycles/MMA\n", amode, names[li], nacc, N, (double)c / (iters * 8));
                 }
+    // alignment of the 8-row x 16-byte core matrices of A (SWIZZLE_NONE): start shifted by k*16 B, 8-row-group pitch 128 / 160 B
+    printf("A core-matrix alignment (layout none): shift16 = start offset in 16-B units, sbo = 8-row group pitch\n");
+    for (int sbo = 128; sbo <= 160; sbo += 32)
+        for (int sh = 0; sh < 8; ++sh)
+            for (int ni = 0; ni < 4; ++ni) {
+                int N = Ns[ni];
+                rate_kernel<<<148, 128, 200 * 1024>>>(N, 0, 1, iters, 0, d, sh, sbo);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+                long long c; cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+                printf("sbo %3d shift16 %d N %3d : %7.1f cycles/MMA\n", sbo, sh, N, (double)c / (iters * 8));
+            }
     return 0;
 }

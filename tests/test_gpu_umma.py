@@ -17,13 +17,14 @@ class P:
         self.w = w
 
 
-@pytest.fixture(scope="module", params=["stacked", "plain"])
+@pytest.fixture(scope="module", params=["dstacked", "stacked", "plain"])
 def B(request):
-    """Both tensor-core conv variants: the w-stacked kernel (conv_umma_s3.cu, taken when Cout <= 80) and the plain one."""
+    """The tensor-core conv variants: depth-stacked (conv_umma_ds.cu, Cout <= 80 with a resident filter), w-stacked
+    (conv_umma_s3.cu, Cout <= 80) and the plain one."""
     from torch_em_b200 import _lib
     from torch_em_b200.backend import CudaBackend
     _lib.load()
-    return CudaBackend(use_s3=request.param == "stacked")
+    return CudaBackend(use_s3=request.param == "stacked", use_ds=request.param == "dstacked")
 
 
 CASES = [
@@ -39,6 +40,11 @@ CASES = [
     (1, 5, 9, 30, 64, 64, (3, 3, 3)),
     (2, 3, 17, 14, 32, 16, (1, 3, 3)),
     (1, 4, 24, 43, 16, 80, (3, 3, 3)),
+    (2, 37, 16, 16, 32, 32, (3, 3, 3)),
+    (1, 70, 17, 9, 64, 32, (3, 3, 3)),
+    (1, 21, 16, 8, 32, 64, (3, 3, 1)),
+    (1, 19, 20, 11, 16, 48, (3, 1, 3)),
+    (1, 15, 16, 8, 16, 80, (3, 3, 3)),
 ]
 
 
@@ -61,6 +67,8 @@ def test_umma_conv_forward_and_dgrad(B, case):
     assert pk.umma_fwd is not None and pk.umma_dgrad is not None
     if B.use_s3 and _lib.load().b200em_conv3d_umma_s3_supported(Cin, Cout, *k):
         assert pk.s3_fwd is not None
+    if B.use_ds and _lib.load().b200em_conv3d_umma_ds_supported(Cin, Cout, *k):
+        assert pk.ds_fwd is not None
     for in_ss, relu, bias in ((None, False, None), (ss, True, b)):
         y_ref = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16)
         s_ref = torch.zeros((N, Cout, 2))
@@ -89,6 +97,46 @@ def test_umma_conv_forward_and_dgrad(B, case):
     d = torch.zeros((N, Cin, 2), device=DEV)
     B.conv(dz.to(DEV), None, pk, None, g, d, k, False, True, dot_x=x.to(DEV))
     torch.cuda.synchronize()
+    np.testing.assert_allclose(d.cpu().numpy(), d_ref.numpy(), rtol=1e-2, atol=2e-2 * float(d_ref.abs().max()))
+
+
+@pytest.mark.parametrize("case", [(2, 24, 48, 40, 64, 32, (3, 3, 3)), (2, 24, 48, 40, 32, 32, (3, 3, 3))])
+def test_dstacked_many_items_per_cta(case, monkeypatch):
+    """Depth-stacked kernel with more work items than SMs (short depth segments forced): the operand ring, the accumulator
+    ring and the dot_x prefetch ring all wrap many times per CTA, and the dgrad runs with fewer ring stages than loader warps."""
+    from torch_em_b200 import _lib
+    from torch_em_b200.backend import CudaBackend
+    monkeypatch.setenv("B200EM_DS_DR", "3")
+    N, D, H, W, Cin, Cout, k = case
+    Bd = CudaBackend(use_ds=True)
+    assert _lib.load().b200em_conv3d_umma_ds_supported(Cin, Cout, *k) and _lib.load().b200em_conv3d_umma_ds_supported(Cout, Cin, *k)
+    x = rnd((N, D, H, W, Cin), 31).bfloat16()
+    w = rnd((Cout, Cin) + k, 32, scale=(Cin * 27) ** -0.5)
+    wq = w.bfloat16().float()
+    b = rnd((Cout,), 33)
+    ss = torch.stack([1 + 0.1 * rnd((N, Cin), 34), 0.1 * rnd((N, Cin), 35)], -1).contiguous()
+    pk = Bd.pack(("ds-many", case), w.to(DEV))
+    xin = (x.float() * ss[:, None, None, None, :, 0] + ss[:, None, None, None, :, 1]).bfloat16()
+    y_ref = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16); s_ref = torch.zeros((N, Cout, 2))
+    EMU.conv(xin, None, P(wq), b, y_ref, s_ref, k, True, False)
+    y = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=DEV); s = torch.zeros((N, Cout, 2), device=DEV)
+    for _ in range(3):                              # repeated launches: a ring race shows up as a mismatch or a trapped kernel
+        s.zero_()
+        Bd.conv(x.to(DEV), ss.to(DEV), pk, b.to(DEV), y, s, k, True, False)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(y.float().cpu().numpy(), y_ref.float().numpy(), rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(s.cpu().numpy(), s_ref.numpy(), rtol=5e-3, atol=0.5)
+    dz = rnd((N, D, H, W, Cout), 36).bfloat16()
+    g_ref = torch.empty((N, D, H, W, Cin), dtype=torch.bfloat16)
+    EMU.conv(dz, None, P(wq), None, g_ref, None, k, False, True)
+    d_ref = torch.zeros((N, Cin, 2))
+    EMU.channel_dot_sums(g_ref, x, d_ref)
+    g = torch.empty((N, D, H, W, Cin), dtype=torch.bfloat16, device=DEV); d = torch.zeros((N, Cin, 2), device=DEV)
+    for _ in range(3):
+        d.zero_()
+        Bd.conv(dz.to(DEV), None, pk, None, g, d, k, False, True, dot_x=x.to(DEV))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(g.float().cpu().numpy(), g_ref.float().numpy(), rtol=1e-2, atol=1e-2)
     np.testing.assert_allclose(d.cpu().numpy(), d_ref.numpy(), rtol=1e-2, atol=2e-2 * float(d_ref.abs().max()))
 
 

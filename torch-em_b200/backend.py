@@ -49,15 +49,16 @@ def _f32(t):
 class WeightPack:
     """Kernel-operand copies of one conv weight (derived caches; the fp32 nn.Parameter stays the master)."""
     __slots__ = ("w_fwd_f32", "w_dgrad_f32", "umma_fwd", "umma_dgrad", "version", "ptr", "cout", "cin", "kernel", "thin",
-                 "thin_kp", "s3_fwd", "s3_dgrad")
+                 "thin_kp", "s3_fwd", "s3_dgrad", "ds_fwd", "ds_dgrad")
 
 
 class CudaBackend:
     name = "cuda"
 
-    def __init__(self, use_umma=True, use_s3=False):
+    def __init__(self, use_umma=True, use_s3=False, use_ds=True):
         self.use_umma = use_umma
         self.use_s3 = use_s3 and use_umma
+        self.use_ds = use_ds and use_umma
         self._pack_cache = {}
         self.timing = None          # {family: [(start_event, end_event, work), ...]} while bench.py measures
 
@@ -99,7 +100,7 @@ class CudaBackend:
         taps = kd * kh * kw
         pk.w_fwd_f32 = torch.empty((taps, cin, cout), dtype=torch.float32, device=w.device)
         pk.w_dgrad_f32 = torch.empty((taps, cout, cin), dtype=torch.float32, device=w.device)
-        pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.s3_fwd = pk.s3_dgrad = None
+        pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.s3_fwd = pk.s3_dgrad = pk.ds_fwd = pk.ds_dgrad = None
         pk.thin_kp = 0
         lib = _lib.load()
         with torch.cuda.device(w.device):
@@ -117,6 +118,12 @@ class CudaBackend:
             if self.use_s3 and lib.b200em_conv3d_umma_s3_supported(cout, cin, kd, kh, kw):
                 pk.s3_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_s3_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.s3_dgrad), _stream(w))
+            if self.use_ds and lib.b200em_conv3d_umma_ds_supported(cin, cout, kd, kh, kw):
+                pk.ds_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
+                call("b200em_conv3d_umma_ds_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.ds_fwd), _stream(w))
+            if self.use_ds and lib.b200em_conv3d_umma_ds_supported(cout, cin, kd, kh, kw):
+                pk.ds_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
+                call("b200em_conv3d_umma_ds_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.ds_dgrad), _stream(w))
             kp = -(-taps * cin // 32) * 32
             if self.use_umma and cin <= 4 and lib.b200em_conv3d_umma_supported(kp, cout, 1, 1, 1):
                 # thin-K first conv: W'[co][tap*Cin+ci] = W[co][ci][tap], zero padded to Kp channels (im2col layout)
@@ -192,6 +199,14 @@ class CudaBackend:
                 W, pack.thin_kp, Cout, 1, 1, 1, int(relu), _stream(x)))
             return cols       # kept by the schedule for the weight gradient of the same conv
         ok16 = x.dtype == torch.bfloat16 and xld % 8 == 0 and yld % 8 == 0 and x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0
+        wds = pack.ds_dgrad if dgrad else pack.ds_fwd
+        if wds is not None and ok16:
+            dp, dld = _act(dot_x) if dot_x is not None else (None, 0)
+            if dot_x is None or (dld % 8 == 0 and dot_x.data_ptr() % 16 == 0):
+                self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
+                    "b200em_conv3d_umma_ds", xp, xld, _f32(in_ss), _ptr(wds), _f32(b), yp, yld, _f32(sums), dp, dld, N, D, H, W,
+                    Cin, Cout, kd, kh, kw, int(relu), _stream(x)))
+                return None
         ws3 = pack.s3_dgrad if dgrad else pack.s3_fwd
         if ws3 is not None and ok16 and dot_x is None:
             self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
@@ -316,5 +331,5 @@ def default_backend():
     if _default is None:
         _lib.load()
         import os
-        _default = CudaBackend(use_s3=os.environ.get("B200EM_S3", "0") == "1")
+        _default = CudaBackend(use_s3=os.environ.get("B200EM_S3", "0") == "1", use_ds=os.environ.get("B200EM_DS", "1") == "1")
     return _default

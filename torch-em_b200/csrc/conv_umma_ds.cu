@@ -1,0 +1,697 @@
+// "depth-stacked" tcgen05 implicit-GEMM convolution for 3 x kh x kw filters with few output channels (Cout <= 80).
+//
+// Why (measured, scripts/ubench/umma_rate.cu on B200): one M=128 x N x K=16 bf16 tcgen05.mma with both operands in
+// shared memory takes max(N/2, ~57 + N/8) cycles -- the A-operand fetch is a fixed ~57-cycle cost -- so a layer issued
+// with N = Cout = 32 (64) runs at 26 % (49 %) of the tensor peak however well it is fed, while N = 96 reaches 70 % and
+// N = 192 the full rate.  Here the three DEPTH taps of the filter share one operand fetch: for an input slice s the
+// MMA computes, for every (b, c) tap,
+//     [ y[s+1] | y[s] | y[s-1] ]  +=  x_hat[s][v + (b, c)]  *  [ W[a=0,b,c] | W[a=1,b,c] | W[a=2,b,c] ]
+// i.e. N = 3*Cout, and the three N-blocks land in the accumulators of three consecutive OUTPUT slices, which are
+// contiguous TMEM column blocks of a ring (block of output d = NA-1 - (d mod NA)).  No shifted sums, no shuffles: the
+// epilogue is the plain one.  Each input slice is staged in shared memory ONCE per work item (a column of DR output
+// slices needs DR + 2 input slices), the whole packed filter stays resident in shared memory.
+//
+// Work item = 16 (h) x 8 (w) voxel tile x DR output depth slices; persistent grid = #SMs.
+// Shared-memory operand layout as in conv_umma.cu (SWIZZLE_NONE K-major core matrices):
+//   A stage = one input slice x one 32(16)-channel chunk: [plane j = 8-ch group][hp 0..17][wp 0..9][8 bf16]
+//   B       = [chunk][tap (b,c)][plane j][n = a*Cout + co][8 bf16]   (resident, loaded once by cp.async.bulk)
+// Warp roles (448 threads): warps 0-3 epilogue, warps 4-11 operand loaders (each warp owns every 8th stage, so eight
+// stage loads are in flight), warp 12 weight loader, warp 13 MMA issuer.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b200em {
+
+using namespace umma;
+
+namespace {
+constexpr int DS_TH = 16, DS_TW = 8;
+constexpr int DS_HP = DS_TH + 2, DS_WP = DS_TW + 2;
+constexpr int DS_PLANE = DS_HP * DS_WP * 16 + 16;   // +16 B staggers the planes across banks
+constexpr int DS_NLW = 8;                           // operand-loader warps
+constexpr int DS_THREADS = 128 + DS_NLW * 32 + 64;
+constexpr int DS_W_WLOAD = 4 + DS_NLW, DS_W_MMA = DS_W_WLOAD + 1;
+constexpr int DS_MAX_SMEM = 227 * 1024;
+constexpr int DS_MAX_NS = 12;                       // A ring depth cap
+constexpr int DS_MAX_NA = 16;                       // accumulator ring blocks cap
+}  // namespace
+
+struct ConvDsParams {
+    const __nv_bfloat16* x; long long x_ld;
+    const float* in_ss;
+    const __nv_bfloat16* w;
+    const float* bias;
+    __nv_bfloat16* y; long long y_ld;
+    float* sums;
+    const __nv_bfloat16* dot_x; long long dot_ld;   // non-null: sums = (sum y, sum y * dot_x) -- the norm-backward reductions
+    int N, D, H, W, Cin, Cout;
+    int kh, kw, relu;
+    int DR, NS, CC, nchunks;
+    int nlw;                         // active operand-loader warps = min(8, NS): a loader may never run two ring phases ahead
+    int tiles_w, tiles_h, tiles_d;
+    long long items;
+    int wbytes;
+    int xdepth;                      // dot_x prefetch ring depth (output slices in flight per epilogue thread), 0 without dot_x
+    int debug;                       // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 2 no epilogue math, 4 no MMAs, 16 no norm apply
+};
+
+__device__ __forceinline__ void ds_coords(const ConvDsParams& p, long long item_, int& n, int& d0, int& h0, int& w0) {
+    unsigned item = (unsigned)item_;                 // 32-bit on purpose (64-bit division is a software routine)
+    const unsigned tw = item % (unsigned)p.tiles_w; item /= (unsigned)p.tiles_w;
+    const unsigned th = item % (unsigned)p.tiles_h; item /= (unsigned)p.tiles_h;
+    const unsigned td = item % (unsigned)p.tiles_d; item /= (unsigned)p.tiles_d;
+    n = (int)item; d0 = (int)td * p.DR; h0 = (int)th * DS_TH; w0 = (int)tw * DS_TW;
+}
+
+// One NV-wide block of output channels of one output slice: bias, ReLU, bf16 store, statistics.
+// ACC: statistics go to per-thread accumulators (flushed once per work item); otherwise they are reduced over the
+// warp's 32 rows right away and added to the shared-memory sums.
+template <int NV, bool ACC>
+__device__ __forceinline__ void ds_epilogue_block(uint32_t taddr, const float* __restrict__ bias_s, int relu, bool valid,
+                                                  __nv_bfloat16* __restrict__ yp, const uint4* xv, bool has_x, float* acc_s,
+                                                  float* acc_q, float* __restrict__ s_sums_blk, bool want_sums, int lane) {
+    // xv: this row's dot_x values for these NV channels, already in registers (prefetched one slice ahead; zeros if !valid)
+    uint32_t raw[NV];
+    if constexpr (NV == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+    tmem_ld_wait();
+    float v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float f = __uint_as_float(raw[i]) + bias_s[i];
+        if (relu) f = fmaxf(f, 0.f);
+        v[i] = __bfloat162float(__float2bfloat16_rn(f));
+    }
+    if (valid) {
+#pragma unroll
+        for (int q = 0; q < NV / 8; ++q) {
+            uint4 o;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(yp + 8 * q) = o;
+        }
+    }
+    if (!want_sums) return;
+    if constexpr (ACC) {
+        // per-thread accumulators, 8 channels at a time (keeps the live register set small)
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < NV / 8; ++q) {
+                float m[8];
+                if (has_x) {                           // second statistic = sum y * dot_x
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xv[q]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(h2[e]);
+                        m[2 * e] = f.x;
+                        m[2 * e + 1] = f.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) m[e] = v[8 * q + e];
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    acc_s[8 * q + e] += v[8 * q + e];
+                    acc_q[8 * q + e] = fmaf(v[8 * q + e], m[e], acc_q[8 * q + e]);
+                }
+            }
+        }
+        return;
+    }
+    float s2[NV];
+    if (has_x) {
+#pragma unroll
+        for (int q = 0; q < NV / 8; ++q) {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xv[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                s2[8 * q + 2 * e] = f.x;
+                s2[8 * q + 2 * e + 1] = f.y;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { v[i] = valid ? v[i] : 0.f; s2[i] *= v[i]; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { v[i] = valid ? v[i] : 0.f; s2[i] = v[i] * v[i]; }
+    }
+    const float a1 = warp_column_sums<NV>(v, lane);
+    const float a2 = warp_column_sums<NV>(s2, lane);
+    if (NV == 32) {
+        atomicAdd(&s_sums_blk[2 * lane], a1);
+        atomicAdd(&s_sums_blk[2 * lane + 1], a2);
+    } else if ((lane & 1) == 0) {
+        atomicAdd(&s_sums_blk[2 * (lane >> 1)], a1);
+        atomicAdd(&s_sums_blk[2 * (lane >> 1) + 1], a2);
+    }
+}
+
+template <int NV>
+__device__ __forceinline__ void ds_flush_stats(float* acc_s, float* acc_q, float* __restrict__ s_sums_blk, int lane) {
+    float a[NV], q[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { a[i] = acc_s[i]; q[i] = acc_q[i]; acc_s[i] = 0.f; acc_q[i] = 0.f; }
+    const float a1 = warp_column_sums<NV>(a, lane);
+    const float a2 = warp_column_sums<NV>(q, lane);
+    if (NV == 32) {
+        atomicAdd(&s_sums_blk[2 * lane], a1);
+        atomicAdd(&s_sums_blk[2 * lane + 1], a2);
+    } else if ((lane & 1) == 0) {
+        atomicAdd(&s_sums_blk[2 * (lane >> 1)], a1);
+        atomicAdd(&s_sums_blk[2 * (lane >> 1) + 1], a2);
+    }
+}
+
+// CO = Cout (16..80, multiple of 16), KC_ = K=16 steps per channel chunk (1 or 2): compile-time so that the epilogue's
+// channel blocks are static and the single-thread MMA issue loop has immediate operand offsets.
+template <int CO, int KC_>
+__global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const ConvDsParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int N3 = 3 * CO;
+    constexpr int J = KC_ * 2;                                  // 8-channel planes per stage
+    constexpr int A_STAGE = J * DS_PLANE;
+    constexpr int NA = (512 / CO) < DS_MAX_NA ? (512 / CO) : DS_MAX_NA;   // accumulator ring blocks (CO columns each)
+    uint8_t* smA = smem;
+    uint8_t* smB = smA + p.NS * A_STAGE;
+    float* s_bias = reinterpret_cast<float*>(smB + p.wbytes);
+    float* s_sums = s_bias + CO;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sums + 2 * CO);
+    uint64_t* a_full = bars;                          // [NS]  one loader-warp arrival
+    uint64_t* a_empty = a_full + DS_MAX_NS;           // [NS]  tcgen05.commit
+    uint64_t* acc_full = a_empty + DS_MAX_NS;         // [NA]  tcgen05.commit
+    uint64_t* acc_empty = acc_full + DS_MAX_NA;       // [NA]  4 epilogue-warp arrivals
+    uint64_t* b_full = acc_empty + DS_MAX_NA;         // [1]   expect_tx (resident filter)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(b_full + 1);
+    uint32_t* s_tap = s_tmem + 2;                     // [9] operand start offset of each (b, c) tap, 16-byte units
+    uint8_t* s_xring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_tap + 9) + 15) & ~(uintptr_t)15);   // [xdepth][128 rows][CO bf16]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntap = p.kh * p.kw;
+    const int ph = p.kh / 2, pw = p.kw / 2;
+    const int DR = p.DR, NS = p.NS;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        mbar_init(b_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == DS_W_MMA) tmem_alloc(s_tmem, 512);
+    if (threadIdx.x < ntap) {
+        const int b = threadIdx.x / p.kw, cc = threadIdx.x % p.kw;
+        s_tap[threadIdx.x] = (uint32_t)((((b + 1 - ph) * DS_WP + (cc + 1 - pw)) * 16) >> 4);
+    }
+    for (int i = threadIdx.x; i < CO; i += DS_THREADS) {
+        s_bias[i] = p.bias ? p.bias[i] : 0.f;
+        s_sums[2 * i] = 0.f;
+        s_sums[2 * i + 1] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp >= 4 && warp < DS_W_WLOAD) {
+        // ===================== operand loaders: warp w8 owns the stages q = w8 (mod nlw) =====================
+        // nlw <= NS: the ring's parity waits are only valid while a waiter is at most one phase ahead of its barrier, which
+        // holds when a warp's next stage (q + nlw) reuses a slot whose previous use (q + nlw - NS) precedes q.
+        // Per work item each lane precomputes the in-slice element offset of its units once (only the slice changes from
+        // stage to stage); the norm apply is a short in-place shared-memory pass.
+        const int w8 = warp - 4;
+        constexpr int UNITS = DS_HP * DS_WP * J;       // 16-byte units per stage
+        constexpr int NU = (UNITS + 31) / 32;          // per lane
+        constexpr int VSTEP = 32 / J;                  // voxels per 32 units
+        const int j = lane % J;                        // this lane's 8-channel plane (32 % J == 0)
+        const int vl = lane / J;
+        float sc[8], sh[8];
+        int cur_n = -1, cur_c = -1;
+        uint32_t slot = 0, phase = 1;                  // ring position of the current stage (phase = parity to wait for on a_empty)
+        int owner = 0;                                 // loader warp that owns the current stage (round robin over p.nlw warps)
+        const size_t slice_elems = (size_t)p.H * p.W * p.x_ld;
+        const bool prof = (p.debug & 8) != 0;
+        long long pf_wait = 0, pf_load = 0, pf_norm = 0, pf_t0 = clock64(), pf_n = 0;
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+            int n, d0, h0, w0;
+            ds_coords(p, item, n, d0, h0, w0);
+            int goff[NU];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+                const int v = vl + VSTEP * i;
+                const int hp_ = v / DS_WP, wp_ = v % DS_WP;
+                const int gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
+                const bool in = v < DS_HP * DS_WP && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
+                goff[i] = in ? (int)((gh * p.W + gw) * p.x_ld) : -1;
+            }
+            for (int s = 0; s < DR + 2; ++s) {
+                const int gd = d0 - 1 + s;
+                const bool in_d = gd >= 0 && gd < p.D;
+                const __nv_bfloat16* xs = p.x + ((size_t)n * p.D + (in_d ? gd : 0)) * slice_elems + j * 8;
+                for (int c = 0; c < p.nchunks; ++c) {
+                    const uint32_t my_slot = slot, my_phase = phase;
+                    const bool mine = owner == w8;
+                    if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1; }
+                    if (++owner == p.nlw) owner = 0;
+                    if (!mine) continue;
+                    long long pf_a = 0, pf_b = 0, pf_c = 0;
+                    if (prof) pf_a = clock64();
+                    mbar_wait(&a_empty[my_slot], my_phase);
+                    if (prof) pf_b = clock64();
+                    uint8_t* dst = smA + my_slot * A_STAGE + j * DS_PLANE + vl * 16;
+                    const uint32_t dst32 = smem_u32(dst);
+                    const __nv_bfloat16* xc = xs + c * p.CC;
+                    if (!(p.debug & 1)) {
+#pragma unroll
+                        for (int i = 0; i < NU; ++i) {
+                            if (vl + VSTEP * i < DS_HP * DS_WP) {
+                                const bool in = in_d && goff[i] >= 0;
+                                const __nv_bfloat16* src = in ? xc + goff[i] : p.x;
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst32 + (uint32_t)(VSTEP * i * 16)),
+                                             "l"(src), "r"(in ? 16 : 0)
+                                             : "memory");
+                            }
+                        }
+                    }
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    if (prof) pf_c = clock64();
+                    if (p.in_ss && in_d && !(p.debug & 16)) {
+                        if (n != cur_n || c != cur_c) {
+                            const float* qq = p.in_ss + ((size_t)n * p.Cin + c * p.CC + j * 8) * 2;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { sc[e] = qq[2 * e]; sh[e] = qq[2 * e + 1]; }
+                            cur_n = n; cur_c = c;
+                        }
+#pragma unroll
+                        for (int i = 0; i < NU; ++i) {
+                            if (goff[i] < 0) continue;
+                            uint4* qd = reinterpret_cast<uint4*>(dst + VSTEP * i * 16);
+                            uint4 val = *qd;
+                            uint32_t* w32 = reinterpret_cast<uint32_t*>(&val);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {       // fp32 math on the unpacked pair, one rounding to bf16
+                                const float lo = fmaf(__uint_as_float(w32[e] << 16), sc[2 * e], sh[2 * e]);
+                                const float hi = fmaf(__uint_as_float(w32[e] & 0xffff0000u), sc[2 * e + 1], sh[2 * e + 1]);
+                                const __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+                                w32[e] = *reinterpret_cast<const uint32_t*>(&r);
+                            }
+                            *qd = val;
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[my_slot]);
+                    if (prof) { pf_wait += pf_b - pf_a; pf_load += pf_c - pf_b; pf_norm += clock64() - pf_c; ++pf_n; }
+                }
+            }
+        }
+        if (prof && blockIdx.x == 0 && lane == 0 && w8 < 2)
+            printf("[ds prof] loader warp %d: total %lld cyc, %lld stages: wait a_empty %lld, load %lld, norm+arrive %lld\n", w8,
+                   clock64() - pf_t0, pf_n, pf_wait, pf_load, pf_norm);
+    } else if (warp == DS_W_WLOAD) {
+        // ===================== weight loader: the whole packed filter, once =====================
+        if (elect_one()) {
+            mbar_arrive_expect_tx(b_full, (uint32_t)p.wbytes);
+            const uint32_t piece = (uint32_t)(J * N3 * 16);              // one (chunk, tap) block
+            const int npieces = p.nchunks * ntap;
+            for (int g = 0; g < npieces; ++g)
+                bulk_g2s(smB + (size_t)g * piece, reinterpret_cast<const uint8_t*>(p.w) + (size_t)g * piece, piece, b_full);
+        }
+    } else if (warp == DS_W_MMA) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc1 = make_idesc_bf16(128, CO), idesc2 = make_idesc_bf16(128, 2 * CO), idesc3 = make_idesc_bf16(128, N3);
+            const uint64_t ad = make_desc(0, DS_PLANE, DS_WP * 16), bd = make_desc(0, (uint32_t)(N3 * 16), 128);
+            const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
+            const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
+            const uint32_t b_lo_base = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smB) >> 4);
+            constexpr uint32_t K16 = 2 * (DS_PLANE / 16), BK16 = 2 * N3, BTAP16 = J * N3, ASTAGE16 = A_STAGE / 16;
+            auto idesc_of = [&](int nb) { return nb == 1 ? idesc1 : (nb == 2 ? idesc2 : idesc3); };
+            uint32_t tapo[9];                            // (b, c) tap start offsets in registers: the issue loop is fully unrolled
+#pragma unroll
+            for (int t = 0; t < 9; ++t) tapo[t] = t < ntap ? s_tap[t] : 0u;
+            const int DRq = DR / NA, DRr = DR % NA;
+            mbar_wait(b_full, 0);
+            tc_fence_after();
+            // Ring bookkeeping is incremental (no divisions in the issue loop): (slot, fph) = A stage and its a_full parity;
+            // (r0, w0) = (oc % NA, (oc / NA) & 1) of the item's first output slice; the block of output counter oc is NA-1 - oc % NA.
+            uint32_t slot = 0, fph = 0;
+            int r0 = 0;
+            uint32_t w0 = 0;
+            const bool prof = (p.debug & 8) != 0;
+            long long pf_wa = 0, pf_wacc = 0, pf_t0 = clock64(), pf_n = 0;
+            for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+                int r = r0;                              // ring position of output od = s (the newest output slice s feeds)
+                uint32_t wpar = w0;
+                for (int s = 0; s < DR + 2; ++s) {
+                    const int a_lo = s - (DR - 1) > 0 ? s - (DR - 1) : 0;
+                    const int nblk = (s < 2 ? s : 2) - a_lo + 1;
+                    int rf = r - a_lo;                   // ring position of the first (a = a_lo) output this slice feeds
+                    if (rf < 0) rf += NA;
+                    const int k0 = NA - 1 - rf;          // a ascending = columns ascending
+                    if (a_lo == 0) {                     // a new accumulator (output od = s) starts with this slice
+                        long long t_ = 0;
+                        if (prof) t_ = clock64();
+                        mbar_wait(&acc_empty[k0], wpar ^ 1);
+                        if (prof) pf_wacc += clock64() - t_;
+                        tc_fence_after();
+                    }
+                    // segments of consecutive ring blocks: [k0, k0+n1) and, past the wrap, [0, n2)
+                    const int n1 = nblk < NA - k0 ? nblk : NA - k0;
+                    const int n2 = nblk - n1;
+                    const uint32_t col1 = tmem_base + (uint32_t)(k0 * CO), col2 = tmem_base;
+                    const uint32_t id1 = idesc_of(n1), id2 = idesc_of(n2 > 0 ? n2 : 1);
+                    const uint32_t boff2 = (uint32_t)(n1 * CO);
+                    uint32_t bch = b_lo_base + (uint32_t)(a_lo * CO);     // 16-byte units: n rows are 16 B apart
+                    for (int c = 0; c < p.nchunks; ++c, bch += (uint32_t)ntap * BTAP16) {
+                        long long t_ = 0;
+                        if (prof) t_ = clock64();
+                        mbar_wait(&a_full[slot], fph);
+                        if (prof) { pf_wa += clock64() - t_; ++pf_n; }
+                        tc_fence_after();
+                        const uint32_t abuf = a_lo_base + slot * ASTAGE16;
+                        if (!(p.debug & 4)) {
+                            const bool fresh = c == 0 && a_lo == 0;       // block k0 (a = 0) is overwritten by its very first MMA
+                            if (fresh) {
+                                const uint32_t a0 = abuf + tapo[0];
+                                umma_bf16_c<false>(col1, a0, a_hi, bch, b_hi, idesc1);
+                                if (nblk > 1) {
+                                    // the other blocks a = 1..  accumulate; they start at ring block k0+1 (may wrap)
+                                    const int rr = nblk - 1;
+                                    const int kk = (k0 + 1 == NA) ? 0 : k0 + 1;
+                                    const int r1 = rr < NA - kk ? rr : NA - kk;
+                                    umma_bf16_c<true>(tmem_base + (uint32_t)(kk * CO), a0, a_hi, bch + CO, b_hi, idesc_of(r1));
+                                    if (rr - r1 > 0)
+                                        umma_bf16_c<true>(tmem_base, a0, a_hi, bch + CO + (uint32_t)(r1 * CO), b_hi, idesc_of(rr - r1));
+                                }
+                                if (KC_ == 2) {
+                                    umma_bf16_c<true>(col1, a0 + K16, a_hi, bch + BK16, b_hi, id1);
+                                    if (n2 > 0) umma_bf16_c<true>(col2, a0 + K16, a_hi, bch + BK16 + boff2, b_hi, id2);
+                                }
+                            }
+                            if (n2 == 0) {
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) {
+                                    if (t < ntap && !(t == 0 && fresh)) {
+                                        umma_bf16_c<true>(col1, abuf + tapo[t], a_hi, bch + t * BTAP16, b_hi, id1);
+                                        if (KC_ == 2) umma_bf16_c<true>(col1, abuf + tapo[t] + K16, a_hi, bch + t * BTAP16 + BK16, b_hi, id1);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) {
+                                    if (t < ntap && !(t == 0 && fresh)) {
+                                        umma_bf16_c<true>(col1, abuf + tapo[t], a_hi, bch + t * BTAP16, b_hi, id1);
+                                        umma_bf16_c<true>(col2, abuf + tapo[t], a_hi, bch + t * BTAP16 + boff2, b_hi, id2);
+                                        if (KC_ == 2) {
+                                            umma_bf16_c<true>(col1, abuf + tapo[t] + K16, a_hi, bch + t * BTAP16 + BK16, b_hi, id1);
+                                            umma_bf16_c<true>(col2, abuf + tapo[t] + K16, a_hi, bch + t * BTAP16 + BK16 + boff2, b_hi, id2);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        umma_commit(&a_empty[slot]);
+                        if (++slot == (uint32_t)NS) { slot = 0; fph ^= 1; }
+                    }
+                    if (s >= 2) {                        // output od = s - 2 has received its last contribution
+                        int r2 = r - 2;
+                        if (r2 < 0) r2 += NA;
+                        umma_commit(&acc_full[NA - 1 - r2]);
+                    }
+                    if (++r == NA) { r = 0; wpar ^= 1; }
+                }
+                r0 += DRr; w0 ^= (uint32_t)(DRq & 1);
+                if (r0 >= NA) { r0 -= NA; w0 ^= 1; }
+            }
+            if (prof && blockIdx.x == 0)
+                printf("[ds prof] mma: total %lld cyc, %lld stages: wait a_full %lld, wait acc_empty %lld\n", clock64() - pf_t0, pf_n, pf_wa, pf_wacc);
+        }
+    } else {
+        // ===================== epilogue (warps 0-3) =====================
+        const int row = warp * 32 + lane;            // GEMM row = TMEM lane
+        const int hl = row / DS_TW, wl = row % DS_TW;
+        constexpr bool kAcc = CO <= 32;
+        constexpr int NAcc = kAcc ? CO : 1;
+        float acc_s[NAcc], acc_q[NAcc];
+#pragma unroll
+        for (int i = 0; i < NAcc; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
+        const bool ws = p.sums != nullptr;
+        const bool has_x = p.dot_x != nullptr;
+        constexpr int XV = CO / 8;                   // 16-byte vectors of dot_x per row
+        const int XD = p.xdepth;
+        const uint32_t xs_row = smem_u32(s_xring) + (uint32_t)row * (CO * 2);
+        int r = 0;                                   // (oc % NA, (oc / NA) & 1) of the next output slice
+        uint32_t wpar = 0;
+        const bool prof = (p.debug & 8) != 0;
+        long long pf_w = 0, pf_t0 = clock64(), pf_n = 0;
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+            int n, d0, h0, w0;
+            ds_coords(p, item, n, d0, h0, w0);
+            const int gh = h0 + hl, gw = w0 + wl;
+            const bool valid_hw = gh < p.H && gw < p.W;
+            // this row's voxel in slice d0 (clamped when the row is outside the volume: never dereferenced then)
+            const size_t vox0 = (((size_t)n * p.D + d0) * p.H + (valid_hw ? gh : 0)) * p.W + (valid_hw ? gw : 0);
+            const size_t hw = (size_t)p.H * p.W;
+            uint4 xcur[XV];
+            // dot_x rows are prefetched XD output slices ahead with cp.async into a PRIVATE shared-memory slot per thread
+            // (each thread reads back only what it copied itself: no barrier, just cp.async groups); a global load issued
+            // when the accumulator is ready would expose its full latency on every slice.
+            auto issue_x = [&](int od_) {
+                if (has_x) {
+                    const bool ok = valid_hw && od_ < DR && d0 + od_ < p.D;
+                    const __nv_bfloat16* q_ = ok ? p.dot_x + (vox0 + (size_t)od_ * hw) * p.dot_ld : p.dot_x;
+                    const uint32_t dst = xs_row + (uint32_t)(od_ % XD) * (128u * CO * 2u);
+#pragma unroll
+                    for (int i = 0; i < XV; ++i)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16u * (uint32_t)((i + row) % XV)), "l"(q_ + 8 * i),
+                                     "r"(ok ? 16 : 0)
+                                     : "memory");
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+            };
+            for (int i = 0; i < XD - 1; ++i) issue_x(i);
+            for (int od = 0; od < DR; ++od) {
+                const int blk = NA - 1 - r;
+                long long t_ = 0;
+                if (prof) t_ = clock64();
+                mbar_wait(&acc_full[blk], wpar);
+                if (prof) { pf_w += clock64() - t_; ++pf_n; }
+                tc_fence_after();
+                if (has_x) {
+                    issue_x(od + XD - 1);
+                    // all but the XD-1 most recent groups have landed -> slice od is in its slot
+                    if (XD == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+                    else if (XD == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+                    else asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    const uint8_t* src = s_xring + (size_t)(od % XD) * (128 * CO * 2) + (size_t)row * (CO * 2);
+#pragma unroll
+                    for (int i = 0; i < XV; ++i) xcur[i] = *reinterpret_cast<const uint4*>(src + 16 * ((i + row) % XV));
+                }
+                const int gd = d0 + od;
+                const bool valid = valid_hw && gd < p.D;
+                __nv_bfloat16* yp = p.y + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(blk * CO);
+                if (p.debug & 2) {
+                } else if constexpr (CO == 16) {
+                    ds_epilogue_block<16, true>(taddr, s_bias, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sums, ws, lane);
+                } else if constexpr (CO == 32) {
+                    // two 16-column passes: half the live registers of one 32-column pass (the 64 statistics accumulators stay)
+                    ds_epilogue_block<16, true>(taddr, s_bias, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sums, ws, lane);
+                    ds_epilogue_block<16, true>(taddr + 16, s_bias + 16, p.relu, valid, yp + 16, xcur + 2, has_x, acc_s + 16, acc_q + 16,
+                                                s_sums, ws, lane);
+                } else {
+                    ds_epilogue_block<32, false>(taddr, s_bias, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sums, ws, lane);
+                    if constexpr (CO >= 64)
+                        ds_epilogue_block<32, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
+                                                     s_sums + 64, ws, lane);
+                    if constexpr (CO == 48)
+                        ds_epilogue_block<16, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
+                                                     s_sums + 64, ws, lane);
+                    if constexpr (CO == 80)
+                        ds_epilogue_block<16, false>(taddr + 64, s_bias + 64, p.relu, valid, yp + 64, xcur + 8, has_x, acc_s, acc_q,
+                                                     s_sums + 128, ws, lane);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[blk]);
+                if (++r == NA) { r = 0; wpar ^= 1; }
+            }
+            if (has_x) asm volatile("cp.async.wait_all;" ::: "memory");
+            if (ws) {
+                // flush this item's per-channel partial sums (the sample n may change with the next item)
+                if constexpr (CO == 32) {
+                    ds_flush_stats<16>(acc_s, acc_q, s_sums, lane);
+                    ds_flush_stats<16>(acc_s + 16, acc_q + 16, s_sums + 32, lane);
+                } else if constexpr (kAcc) {
+                    ds_flush_stats<CO>(acc_s, acc_q, s_sums, lane);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = threadIdx.x; i < 2 * CO; i += 128) {
+                    atomicAdd(p.sums + ((size_t)n * CO + (i >> 1)) * 2 + (i & 1), s_sums[i]);
+                    s_sums[i] = 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+        if (prof && blockIdx.x == 0 && threadIdx.x == 0)
+            printf("[ds prof] epilogue: total %lld cyc, %lld slabs: wait acc_full %lld\n", clock64() - pf_t0, pf_n, pf_w);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == DS_W_MMA) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// torch (Cout, Cin, 3, kh, kw) fp32 -> bf16 [chunk][tap (b,c)][plane j][a*Nc + n][8]; dgrad = 1: transposed, tap-flipped.
+__global__ void pack_ds_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw, int dgrad, int CC,
+                                       __nv_bfloat16* __restrict__ out) {
+    const int thw = kh * kw, taps = 3 * thw;
+    const int64_t total = (int64_t)Cout * Cin * taps;
+    const int Nc = dgrad ? Cin : Cout;               // output channels of the packed operand
+    const int J = CC / 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tp = (int)(i % taps);
+        const int ci = (int)((i / taps) % Cin);
+        const int co = (int)(i / ((int64_t)taps * Cin));
+        const int n_ = dgrad ? ci : co, k_ = dgrad ? co : ci, t_ = dgrad ? taps - 1 - tp : tp;
+        const int a = t_ / thw, bc = t_ % thw;
+        const int chunk = k_ / CC, j = (k_ % CC) / 8, e = k_ % 8;
+        out[((((size_t)chunk * thw + bc) * J + j) * (3 * Nc) + (size_t)a * Nc + n_) * 8 + e] = __float2bfloat16_rn(w[i]);
+    }
+}
+
+struct DsShape {
+    int CC, NS, wbytes, smem_bytes, xdepth;
+};
+
+static bool ds_shape(int Cin, int Cout, int kd, int kh, int kw, DsShape& s, bool with_dot = false) {
+    if (kd != 3 || (kh != 3 && kh != 1) || (kw != 3 && kw != 1)) return false;
+    if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16 || Cout > 80) return false;
+    s.CC = (Cin % 32 == 0) ? 32 : 16;
+    const int J = s.CC / 8;
+    s.wbytes = 3 * kh * kw * Cin * Cout * 2;
+    const int misc = Cout * 4 * 3 + (2 * DS_MAX_NS + 2 * DS_MAX_NA + 1) * 8 + 8 + 9 * 4 + 128;
+    const int stage = J * DS_PLANE;
+    int ns = (DS_MAX_SMEM - s.wbytes - misc) / stage;
+    if (ns > DS_MAX_NS) ns = DS_MAX_NS;
+    if (ns < 6) return false;                        // the filter must stay resident next to a useful operand ring
+    s.xdepth = 0;
+    int xring = 0;
+    if (with_dot) {
+        // room for the dot_x prefetch ring: as deep as possible while the operand ring keeps >= 5 stages
+        for (int xd = 4; xd >= 2; --xd) {
+            xring = xd * 128 * Cout * 2 + 16;
+            const int ns2 = (DS_MAX_SMEM - s.wbytes - misc - xring) / stage;
+            if (ns2 >= 5 || xd == 2) { s.xdepth = xd; ns = ns2 < ns ? ns2 : ns; break; }
+        }
+        if (ns < 3) return false;
+    }
+    s.NS = ns;
+    s.smem_bytes = ns * stage + s.wbytes + misc + xring;
+    return true;
+}
+
+// Output slices per work item: few enough items per SM that the last wave is full, many enough slices that the DR + 2
+// input slices (4 of them issued with a narrower N) amortise.
+static int ds_pick_dr(int N, int D, int H, int W, int sms) {
+    const long long cols = (long long)N * ((H + DS_TH - 1) / DS_TH) * ((W + DS_TW - 1) / DS_TW);
+    int best = 1;
+    double best_cost = 1e30;
+    for (int dr = 1; dr <= (D < 64 ? D : 64); ++dr) {
+        const long long items = cols * ((D + dr - 1) / dr);
+        const long long waves = (items + sms - 1) / sms;
+        const double cost = (double)waves * (dr + 1.8);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = dr; }
+    }
+    return best;
+}
+
+}  // namespace b200em
+
+using namespace b200em;
+
+extern "C" {
+
+int b200em_conv3d_umma_ds_supported(int Cin, int Cout, int kd, int kh, int kw) {
+    DsShape s;
+    return (ds_shape(Cin, Cout, kd, kh, kw, s, false) && ds_shape(Cin, Cout, kd, kh, kw, s, true)) ? 1 : 0;
+}
+
+int b200em_conv3d_umma_ds_pack(const float* w, int Cout, int Cin, int kd, int kh, int kw, int dgrad, void* packed, void* stream) {
+    B2_CHECK_ARG(w && packed && Cout > 0 && Cin > 0, "conv3d_umma_ds_pack: bad arguments");
+    DsShape s;
+    const int n_ = dgrad ? Cin : Cout, k_ = dgrad ? Cout : Cin;
+    if (!ds_shape(k_, n_, kd, kh, kw, s)) {
+        set_error("conv3d_umma_ds_pack: shape (%d -> %d, %dx%dx%d) not supported by the depth-stacked tcgen05 path", k_, n_, kd, kh, kw);
+        return 2;
+    }
+    int64_t total = (int64_t)Cout * Cin * kd * kh * kw;
+    int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    pack_ds_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, kh, kw, dgrad, s.CC, (__nv_bfloat16*)packed);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+                          void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W,
+                          int Cin, int Cout, int kd, int kh, int kw, int relu, void* stream) {
+    B2_CHECK_ARG(x && w_packed && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_ds: bad arguments");
+    DsShape s;
+    if (!ds_shape(Cin, Cout, kd, kh, kw, s, dot_x != nullptr)) {
+        set_error("conv3d_umma_ds: shape (%d -> %d, %dx%dx%d) not supported by the depth-stacked tcgen05 path", Cin, Cout, kd, kh, kw);
+        return 2;
+    }
+    B2_CHECK_ARG(x_ld % 8 == 0 && y_ld % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(w_packed),
+                 "conv3d_umma_ds: activations must be 16-byte aligned with pitch % 8 == 0");
+    B2_CHECK_ARG(x_ld >= Cin && y_ld >= Cout, "conv3d_umma_ds: pitch smaller than channel count");
+    B2_CHECK_ARG((long long)H * W * x_ld < (1LL << 31), "conv3d_umma_ds: slice too large for 32-bit in-slice offsets");
+    B2_CHECK_ARG(!dot_x || (sums && dot_ld % 8 == 0 && aligned16(dot_x) && dot_ld >= Cout), "conv3d_umma_ds: dot_x needs sums, 16-byte alignment and pitch >= Cout");
+    ConvDsParams p;
+    p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.w = (const __nv_bfloat16*)w_packed; p.bias = bias;
+    p.y = (__nv_bfloat16*)y; p.y_ld = y_ld; p.sums = sums; p.dot_x = (const __nv_bfloat16*)dot_x; p.dot_ld = dot_ld;
+    p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.relu = relu;
+    p.CC = s.CC; p.nchunks = Cin / s.CC; p.NS = s.NS; p.wbytes = s.wbytes; p.xdepth = s.xdepth;
+    p.nlw = s.NS < DS_NLW ? s.NS : DS_NLW;
+    { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    {
+        const char* e = getenv("B200EM_DS_DR");
+        p.DR = e ? atoi(e) : ds_pick_dr(N, D, H, W, sm_count());
+        if (p.DR < 1) p.DR = 1;
+    }
+    p.tiles_w = (W + DS_TW - 1) / DS_TW; p.tiles_h = (H + DS_TH - 1) / DS_TH; p.tiles_d = (D + p.DR - 1) / p.DR;
+    p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
+    long long gx = p.items < sm_count() ? p.items : sm_count();
+#define B2_DS_LAUNCH(CO_)                                                                                                          \
+    case CO_:                                                                                                                      \
+        if (s.CC == 32) {                                                                                                          \
+            B2_CUDA(cudaFuncSetAttribute(conv3d_umma_ds_kernel<CO_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
+            conv3d_umma_ds_kernel<CO_, 2><<<(unsigned)gx, DS_THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                     \
+        } else {                                                                                                                   \
+            B2_CUDA(cudaFuncSetAttribute(conv3d_umma_ds_kernel<CO_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
+            conv3d_umma_ds_kernel<CO_, 1><<<(unsigned)gx, DS_THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                     \
+        }                                                                                                                          \
+        break;
+    switch (Cout) {
+        B2_DS_LAUNCH(16)
+        B2_DS_LAUNCH(32)
+        B2_DS_LAUNCH(48)
+        B2_DS_LAUNCH(64)
+        B2_DS_LAUNCH(80)
+        default:
+            set_error("conv3d_umma_ds: Cout %d not instantiated", Cout);
+            return 2;
+    }
+#undef B2_DS_LAUNCH
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"
