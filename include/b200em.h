@@ -122,6 +122,14 @@ int b200em_conv3d_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_
                              float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw,
                              void* stream);
 
+/* "w-stacked", depth-streamed tcgen05 weight gradient for 3 x kh x 3 filters (Cin % 32 == 0, Cout % 32 == 0): the three
+ * w-taps share one MMA (N = 3*32 from three shifted shared-memory copies of dz), every x slice is staged once per
+ * column of output slices (csrc/conv_wgrad_cs.cu).  Same contract and arguments as b200em_conv3d_wgrad_umma. */
+int b200em_conv3d_wgrad_cs_supported(int Cin, int Cout, int kd, int kh, int kw);
+int b200em_conv3d_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld,
+                           float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw,
+                           void* stream);
+
 /* im2col of the first conv (thin K = taps*Cin): out (N,D,H,W,Kp) bf16 with out[vox][tap*Cin+ci] = x_hat[vox+tap][ci], zero in
  * the padding and for channels >= taps*Cin.  The conv is then a 1x1x1 conv with Kp input channels on the tcgen05 path. */
 int b200em_im2col_taps(const void* x, int64_t x_ld, const float* in_scale_shift, int dtype, void* out, int N, int D, int H,

@@ -24,7 +24,7 @@ def B(request):
     from torch_em_b200 import _lib
     from torch_em_b200.backend import CudaBackend
     _lib.load()
-    return CudaBackend(use_s3=request.param == "stacked", use_ds=request.param == "dstacked")
+    return CudaBackend(use_s3=request.param == "stacked", use_ds=request.param == "dstacked", use_cs=request.param == "dstacked")
 
 
 CASES = [
@@ -148,6 +148,10 @@ WG_CASES = [
     (1, 7, 33, 17, 96, 48, (3, 3, 3)),
     (1, 4, 8, 8, 128, 256, (3, 3, 3)),
     (3, 8, 32, 32, 32, 32, (3, 3, 3)),
+    (2, 37, 16, 16, 32, 32, (3, 3, 3)),
+    (1, 21, 20, 11, 64, 64, (3, 1, 3)),
+    (2, 24, 48, 40, 64, 32, (3, 3, 3)),
+    (1, 9, 33, 17, 96, 64, (3, 3, 3)),
 ]
 
 
@@ -169,6 +173,29 @@ def test_umma_wgrad(B, case):
         torch.cuda.synchronize()
         np.testing.assert_allclose(dw.cpu().numpy() - 0.5, dw_ref.numpy(), rtol=2e-3, atol=2e-3 * float(dw_ref.abs().max()))
         np.testing.assert_allclose(db.cpu().numpy() + 1.0, db_ref.numpy(), rtol=2e-3, atol=2e-3 * float(db_ref.abs().max()))
+
+
+@pytest.mark.parametrize("dr", ["2", "5"])
+def test_wgrad_cs_many_items_per_cta(dr, monkeypatch):
+    """w-stacked weight gradient with short depth segments forced: several work items per CTA, the stage ring and its
+    mirrored slots wrap many times; repeated launches must give the same answer."""
+    from torch_em_b200.backend import CudaBackend
+    monkeypatch.setenv("B200EM_CS_DR", dr)
+    N, D, H, W, Cin, Cout, k = 2, 24, 48, 40, 64, 32, (3, 3, 3)
+    Bc = CudaBackend(use_cs=True)
+    x = rnd((N, D, H, W, Cin), 41).bfloat16()
+    dz = rnd((N, D, H, W, Cout), 42).bfloat16()
+    ss = torch.stack([1 + 0.1 * rnd((N, Cin), 43), 0.1 * rnd((N, Cin), 44)], -1).contiguous()
+    xin = (x.float() * ss[:, None, None, None, :, 0] + ss[:, None, None, None, :, 1]).bfloat16()
+    dw_ref, db_ref = torch.zeros((Cout, Cin) + k), torch.zeros(Cout)
+    EMU.wgrad(xin, None, dz, dw_ref, db_ref, k)
+    for _ in range(3):
+        dw = torch.zeros((Cout, Cin) + k, device=DEV)
+        db = torch.zeros((Cout,), device=DEV)
+        Bc.wgrad(x.to(DEV), ss.to(DEV), dz.to(DEV), dw, db, k)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(dw.cpu().numpy(), dw_ref.numpy(), rtol=2e-3, atol=2e-3 * float(dw_ref.abs().max()))
+        np.testing.assert_allclose(db.cpu().numpy(), db_ref.numpy(), rtol=2e-3, atol=2e-3 * float(db_ref.abs().max()))
 
 
 @pytest.mark.parametrize("case", [(2, 6, 20, 13, 1, 32, (3, 3, 3)), (1, 4, 16, 16, 2, 16, (3, 3, 3)), (1, 3, 18, 9, 1, 64, (1, 3, 3))])

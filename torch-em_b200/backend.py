@@ -55,10 +55,11 @@ class WeightPack:
 class CudaBackend:
     name = "cuda"
 
-    def __init__(self, use_umma=True, use_s3=False, use_ds=True):
+    def __init__(self, use_umma=True, use_s3=False, use_ds=True, use_cs=True):
         self.use_umma = use_umma
         self.use_s3 = use_s3 and use_umma
         self.use_ds = use_ds and use_umma
+        self.use_cs = use_cs and use_umma
         self._pack_cache = {}
         self.timing = None          # {family: [(start_event, end_event, work), ...]} while bench.py measures
 
@@ -258,6 +259,12 @@ class CudaBackend:
                 _stream(x)))
             dw += dwt[:, :taps * Cin].reshape(Cout, taps, Cin).permute(0, 2, 1).reshape(dw.shape)
             return
+        ok16 = x.dtype == torch.bfloat16 and xld % 8 == 0 and zld % 8 == 0 and x.data_ptr() % 16 == 0 and dz.data_ptr() % 16 == 0
+        if self.use_umma and self.use_cs and ok16 and _lib.load().b200em_conv3d_wgrad_cs_supported(Cin, Cout, kd, kh, kw):
+            self._timed("conv_umma_wgrad", flops, lambda: call(
+                "b200em_conv3d_wgrad_cs", xp, xld, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cin, Cout, kd, kh,
+                kw, _stream(x)))
+            return
         if self.use_umma and x.dtype == torch.bfloat16 and xld % 8 == 0 and zld % 8 == 0 and x.data_ptr() % 16 == 0 and \
                 dz.data_ptr() % 16 == 0 and _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw):
             self._timed("conv_umma_wgrad", flops, lambda: call(
@@ -331,5 +338,6 @@ def default_backend():
     if _default is None:
         _lib.load()
         import os
-        _default = CudaBackend(use_s3=os.environ.get("B200EM_S3", "0") == "1", use_ds=os.environ.get("B200EM_DS", "1") == "1")
+        _default = CudaBackend(use_s3=os.environ.get("B200EM_S3", "0") == "1", use_ds=os.environ.get("B200EM_DS", "1") == "1",
+                               use_cs=os.environ.get("B200EM_CS", "1") == "1")
     return _default

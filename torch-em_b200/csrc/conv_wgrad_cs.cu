@@ -1,0 +1,382 @@
+// Weight gradient of the 3 x 3 x 3 convolutions on the tensor cores, "h-stacked" and depth-streamed:
+//     dW[co][ci][a,b,c] += sum_{n,v} dz[n,v,co] * x_hat[n, v + (a-1, b-1, c-1), ci]        (+ db[co] += sum dz)
+//
+// GEMM view per (32-channel chunk of Cin, 32-channel block of Cout), K = voxels (16 per MMA: two 8-voxel w-rows H, H+1):
+//   A (MN-major) = x_hat:  M = 128 rows = 4 consecutive depth slices x 32 channels at tile row H, w shifted by the tap c
+//       (descriptor start address) -> rows [0,96) are the depth taps a = 0,1,2 of output slice r; rows [96,128) are ignored
+//   B (MN-major) = dz:     N = 96 = 3 h-taps x 32 output channels.  The haloed dz slice is stored [row hp][8-ch group jo]
+//       [w][8 ch]: N-group g = 4*b' + jo at stride 128 B is then 8-ch group jo of row hp + b' -- the three h-shifted
+//       operands are ONE buffer, no copies (tap b = 2 - b').  One tcgen05.mma covers three taps: an MMA instruction costs
+//       max(N/2, ~57 + N/8) cycles whatever N is, so N = 96 instead of 32 is 2.7x fewer tensor-pipe cycles per FLOP.
+//   D[c] in TMEM: 3 accumulators x 96 columns, resident over ALL work items of the CTA; one epilogue at the end adds
+//       them into the fp32 dW (torch layout) with atomics.
+// Depth streaming: a work item is a 16 x 8 (h, w) tile x DR consecutive depth slices; stage t of an item holds input
+// slice d0-1+t of x_hat (4 planes of 8 channels, loaded ONCE per item) and dz slice d0+t.  The x parts of consecutive
+// ring slots are contiguous in shared memory and the first three slots are mirrored behind the last one, so the
+// 4-slice operand window of any output slice is one contiguous block (descriptor stride = plane).
+// Warp roles: warps 0-3 epilogue (once, at the end), warps 4-11 loaders (each warp owns every nlw-th stage), warp 12
+// MMA issuer.  Replaces the autograd weight/bias gradient of nn.Conv3d (unet.py:429-438) for the 3x3x3 layers.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b200em {
+
+using namespace umma;
+
+namespace {
+constexpr int CS_TH = 16, CS_TW = 8;
+constexpr int CS_HP = CS_TH + 2, CS_WP = CS_TW + 2;
+constexpr int CS_XVOX = CS_TH * CS_WP;                 // x tile: 16 rows x 10 columns (w halo only)
+constexpr int CS_PLANE = CS_XVOX * 16 + 16;            // bytes per 8-channel plane of an x slice (+16 staggers banks)
+constexpr int CS_XSLOT = 4 * CS_PLANE;                 // one x slice of a 32-channel chunk
+constexpr int CS_NB = 32;                              // output channels per CTA
+constexpr int CS_ZROW = (CS_NB / 8) * CS_TW * 16;      // one haloed dz row: [jo][w][8 ch] = 512 B
+constexpr int CS_ZSLOT = CS_HP * CS_ZROW;              // one dz slice with its h halo
+constexpr int CS_NLW = 8;
+constexpr int CS_THREADS = 128 + CS_NLW * 32 + 32;
+constexpr int CS_W_MMA = 4 + CS_NLW;
+constexpr int CS_MAX_NS = 8;
+constexpr int CS_MAX_SMEM = 227 * 1024;
+}  // namespace
+
+struct WgradCsParams {
+    const __nv_bfloat16* x; long long x_ld;
+    const float* in_ss;
+    const __nv_bfloat16* dz; long long dz_ld;
+    float* dw;
+    float* db;
+    int N, D, H, W, Cin, Cout;
+    int nco;                                   // number of 32-wide Cout blocks
+    int DR, NS, nlw;
+    int tiles_w, tiles_h, tiles_d;
+    long long items;
+    int debug;                                 // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 4 no MMAs, 8 profile printf
+};
+
+__global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const WgradCsParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // carve: X[NS + 3] (slots 0..2 mirrored at NS..NS+2) | Z[NS] | db sums[32] | barriers | tmem ptr
+    const int NS = p.NS, DR = p.DR;
+    uint8_t* smX = smem;
+    uint8_t* smZ = smX + (NS + 3) * CS_XSLOT;
+    float* s_db = reinterpret_cast<float*>(smZ + NS * CS_ZSLOT);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_db + CS_NB);
+    uint64_t* full = bars;                     // [NS] one loader-warp arrival
+    uint64_t* empty = bars + CS_MAX_NS;        // [NS] tcgen05.commit
+    uint64_t* acc_full = bars + 2 * CS_MAX_NS; // [1]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = blockIdx.y / p.nco, cob = blockIdx.y % p.nco;
+    constexpr int N3 = 3 * CS_NB;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == CS_W_MMA) tmem_alloc(s_tmem, 512);
+    for (int i = threadIdx.x; i < CS_NB; i += CS_THREADS) s_db[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    auto coords = [&](long long item_, int& n, int& d0, int& h0, int& w0) {      // 32-bit: 64-bit division is a software routine
+        unsigned item = (unsigned)item_;
+        const unsigned tw = item % (unsigned)p.tiles_w; item /= (unsigned)p.tiles_w;
+        const unsigned th = item % (unsigned)p.tiles_h; item /= (unsigned)p.tiles_h;
+        const unsigned td = item % (unsigned)p.tiles_d; item /= (unsigned)p.tiles_d;
+        n = (int)item; d0 = (int)td * DR; h0 = (int)th * CS_TH; w0 = (int)tw * CS_TW;
+    };
+
+    if (warp >= 4 && warp < CS_W_MMA) {
+        // ===================== loaders =====================
+        const int w8 = warp - 4;
+        constexpr int XU = CS_XVOX * 4 / 32;                 // x units (16 B) per lane and stage: 20
+        constexpr int ZU = CS_HP * CS_TW * 4 / 32;           // dz units per lane and stage: 18 (unit i = haloed row i)
+        const int j = lane & 3, vl = lane >> 2;              // 8-channel group of this lane, first voxel
+        float sc[8], sh[8];
+        float dbacc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { dbacc[e] = 0.f; sc[e] = 1.f; sh[e] = 0.f; }
+        int cur_n = -1;
+        uint32_t slot = 0, phase = 1;
+        int owner = 0;
+        const size_t xslice = (size_t)p.H * p.W * p.x_ld, zslice = (size_t)p.H * p.W * p.dz_ld;
+        const bool want_db = p.db != nullptr && chunk == 0;
+        const bool prof = (p.debug & 8) != 0;
+        long long pf_wait = 0, pf_load = 0, pf_rest = 0, pf_n = 0, pf_t0 = clock64();
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+            int n, d0, h0, w0;
+            coords(item, n, d0, h0, w0);
+            int goff[XU];                            // in-slice element offset of this lane's x units, -1 = outside the volume
+#pragma unroll
+            for (int i = 0; i < XU; ++i) {
+                const int v = vl + 8 * i;
+                const int hl = v / CS_WP, wp_ = v % CS_WP;
+                const int gh = h0 + hl, gw = w0 + wp_ - 1;
+                goff[i] = (gh < p.H && gw >= 0 && gw < p.W) ? (int)((gh * p.W + gw) * p.x_ld) : -1;
+            }
+            // dz unit i of this lane = haloed row hp = i (global row h0 + i - 1), column w0 + vl
+            const int zgw = w0 + vl;
+            const int zoff0 = (int)(((h0 - 1) * p.W + zgw) * p.dz_ld), zrow = (int)(p.W * p.dz_ld);
+            uint32_t zmask = 0;                      // row i inside the volume (and the column)
+#pragma unroll
+            for (int i = 0; i < ZU; ++i) {
+                const int gh = h0 + i - 1;
+                if (gh >= 0 && gh < p.H && zgw < p.W) zmask |= 1u << i;
+            }
+            if (p.in_ss && n != cur_n) {
+                const float* q = p.in_ss + ((size_t)n * p.Cin + chunk * 32 + j * 8) * 2;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
+                cur_n = n;
+            }
+            for (int t = 0; t < DR + 2; ++t) {
+                const uint32_t my_slot = slot, my_phase = phase;
+                const bool mine = owner == w8;
+                if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1; }
+                if (++owner == p.nlw) owner = 0;
+                if (!mine) continue;
+                long long pa = 0, pb = 0, pc = 0;
+                if (prof) pa = clock64();
+                mbar_wait(&empty[my_slot], my_phase);
+                if (prof) pb = clock64();
+                const int gd = d0 - 1 + t;
+                const bool in_d = gd >= 0 && gd < p.D;
+                const int gz = d0 + t;
+                const bool z_on = t < DR && gz < p.D;
+                const __nv_bfloat16* xs = p.x + ((size_t)n * p.D + (in_d ? gd : 0)) * xslice + chunk * 32 + j * 8;
+                const __nv_bfloat16* zs = p.dz + ((size_t)n * p.D + (z_on ? gz : 0)) * zslice + cob * CS_NB + j * 8;
+                uint8_t* xdst = smX + my_slot * CS_XSLOT + j * CS_PLANE + vl * 16;
+                uint8_t* zdst = smZ + my_slot * CS_ZSLOT + j * (CS_TW * 16) + vl * 16;
+                const uint32_t xd32 = smem_u32(xdst), zd32 = smem_u32(zdst);
+                const uint32_t mirror = my_slot < 3 ? (uint32_t)(NS * CS_XSLOT) : 0u;
+                if (!(p.debug & 1)) {
+#pragma unroll
+                    for (int i = 0; i < ZU; ++i) {
+                        const bool in = z_on && ((zmask >> i) & 1);
+                        const __nv_bfloat16* src = in ? zs + zoff0 + i * zrow : p.dz;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(zd32 + (uint32_t)(i * CS_ZROW)), "l"(src),
+                                     "r"(in ? 16 : 0)
+                                     : "memory");
+                    }
+#pragma unroll
+                    for (int i = 0; i < XU; ++i) {
+                        const bool in = in_d && goff[i] >= 0;
+                        const __nv_bfloat16* src = in ? xs + goff[i] : p.x;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xd32 + (uint32_t)(8 * i * 16)), "l"(src),
+                                     "r"(in ? 16 : 0)
+                                     : "memory");
+                    }
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                if (prof) pc = clock64();
+                if (in_d && (p.in_ss || mirror)) {
+                    // norm apply in place (fp32 math, one rounding to bf16) and the mirror copy of the first three slots
+#pragma unroll
+                    for (int i = 0; i < XU; ++i) {
+                        uint4* qd = reinterpret_cast<uint4*>(xdst + 8 * i * 16);
+                        uint4 val = *qd;
+                        if (p.in_ss && goff[i] >= 0) {
+                            uint32_t* w32 = reinterpret_cast<uint32_t*>(&val);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float lo = fmaf(__uint_as_float(w32[e] << 16), sc[2 * e], sh[2 * e]);
+                                const float hi = fmaf(__uint_as_float(w32[e] & 0xffff0000u), sc[2 * e + 1], sh[2 * e + 1]);
+                                const __nv_bfloat162 r2 = __floats2bfloat162_rn(lo, hi);
+                                w32[e] = *reinterpret_cast<const uint32_t*>(&r2);
+                            }
+                            *qd = val;
+                        }
+                        if (mirror) *reinterpret_cast<uint4*>(xdst + mirror + 8 * i * 16) = val;
+                    }
+                } else if (mirror) {                 // slice outside the volume: zeros in the mirror slot as well
+#pragma unroll
+                    for (int i = 0; i < XU; ++i) *reinterpret_cast<uint4*>(xdst + mirror + 8 * i * 16) = make_uint4(0, 0, 0, 0);
+                }
+                if (want_db && z_on) {               // bias gradient from the tile's own rows (hp = 1..16): every in-volume dz element once
+#pragma unroll
+                    for (int i = 1; i <= CS_TH; ++i) {
+                        const uint4 val = *reinterpret_cast<const uint4*>(zdst + i * CS_ZROW);
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __bfloat1622float2(h2[e]);
+                            dbacc[2 * e] += f.x;
+                            dbacc[2 * e + 1] += f.y;
+                        }
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[my_slot]);
+                if (prof) { pf_wait += pb - pa; pf_load += pc - pb; pf_rest += clock64() - pc; ++pf_n; }
+            }
+        }
+        if (want_db) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_db[j * 8 + e], dbacc[e]);
+            asm volatile("bar.sync 2, %0;" ::"n"(CS_NLW * 32) : "memory");
+            const int t = threadIdx.x - 128;
+            if (t < CS_NB) atomicAdd(p.db + cob * CS_NB + t, s_db[t]);
+        }
+        if (prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && w8 == 0)
+            printf("[cs prof] loader warp 0: total %lld cyc, %lld stages: wait empty %lld, load %lld, norm/db/arrive %lld\n", clock64() - pf_t0,
+                   pf_n, pf_wait, pf_load, pf_rest);
+    } else if (warp == CS_W_MMA) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, N3, 1, 1);      // both operands MN-major
+            // A: LBO = next 8 voxels (next tile row), SBO = next 8 channels (next plane; slices are consecutive planes)
+            // B: LBO = next 8 voxels (next dz row), SBO = 128 B = next 8 output channels, and after four of them the next row
+            const uint64_t ad = make_desc(0, CS_WP * 16, CS_PLANE), bd = make_desc(0, CS_ZROW, CS_TW * 16);
+            const uint32_t a_hi = (uint32_t)(ad >> 32), a_lo_c = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smX) >> 4);
+            const uint32_t b_hi = (uint32_t)(bd >> 32), b_lo_c = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smZ) >> 4);
+            uint32_t slot = 0, fph = 0;              // ring position of the next stage to wait for
+            uint32_t rslot = 0;                      // ring position of the output slice being issued (= its first x slice)
+            bool first = true;                       // very first MMAs of this CTA overwrite the accumulators
+            const bool prof = (p.debug & 8) != 0;
+            long long pf_w = 0, pf_t0 = clock64(), pf_n = 0;
+            for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+                for (int t = 0; t < DR + 2; ++t) {
+                    long long t_ = 0;
+                    if (prof) t_ = clock64();
+                    mbar_wait(&full[slot], fph);
+                    if (prof) { pf_w += clock64() - t_; ++pf_n; }
+                    tc_fence_after();
+                    if (++slot == (uint32_t)NS) { slot = 0; fph ^= 1; }
+                    if (t < 2) continue;
+                    // output slice r = t - 2: x slices r, r+1, r+2 (+ one ignored) start at ring slot rslot, dz copies in slot rslot
+                    const uint32_t xs = a_lo_c + rslot * (CS_XSLOT / 16);
+                    const uint32_t zs = b_lo_c + rslot * (CS_ZSLOT / 16);
+                    if (!(p.debug & 4)) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {        // w tap: start column of the haloed x rows
+                            const uint32_t a0 = xs + (uint32_t)c;
+                            const uint32_t tacc = tmem_base + (uint32_t)(c * N3);
+                            if (first) umma_bf16_c<false>(tacc, a0, a_hi, zs, b_hi, idesc);
+                            else umma_bf16_c<true>(tacc, a0, a_hi, zs, b_hi, idesc);
+#pragma unroll
+                            for (int ks = 1; ks < CS_TH / 2; ++ks)
+                                umma_bf16_c<true>(tacc, a0 + ks * 2 * CS_WP, a_hi, zs + ks * 2 * (CS_ZROW / 16), b_hi, idesc);
+                        }
+                        first = false;
+                    }
+                    umma_commit(&empty[rslot]);      // x slice r and dz slice r are free once these MMAs have completed
+                    if (++rslot == (uint32_t)NS) rslot = 0;
+                }
+                // the item's last two x slices were only ever read as depth taps a = 1, 2: release their stages as well
+                umma_commit(&empty[rslot]);
+                if (++rslot == (uint32_t)NS) rslot = 0;
+                umma_commit(&empty[rslot]);
+                if (++rslot == (uint32_t)NS) rslot = 0;
+            }
+            umma_commit(acc_full);
+            if (prof && blockIdx.x == 0 && blockIdx.y == 0)
+                printf("[cs prof] mma: total %lld cyc, %lld stages: wait full %lld\n", clock64() - pf_t0, pf_n, pf_w);
+        }
+    } else if (warp < 4) {
+        // ===================== epilogue: TMEM -> atomics into dW =====================
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int a = warp;                              // depth tap of this warp's 32 lanes (a == 3: ignored rows)
+        const int taps = 27;
+        if (a < 3) {
+            const int ci = chunk * 32 + lane;
+            for (int c = 0; c < 3; ++c) {
+                for (int bq = 0; bq < 3; ++bq) {             // N block b' = h shift of the dz rows: tap b = 2 - b'
+                    const int tap = (a * 3 + (2 - bq)) * 3 + c;
+                    for (int cb = 0; cb < CS_NB; cb += 16) {
+                        uint32_t raw[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * N3 + bq * CS_NB + cb), raw);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int co = cob * CS_NB + cb + i;
+                            atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * taps + tap, __uint_as_float(raw[i]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == CS_W_MMA) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static bool wgrad_cs_shape(int Cin, int Cout, int kd, int kh, int kw) {
+    return kd == 3 && kw == 3 && kh == 3 && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32;
+}
+
+}  // namespace b200em
+
+using namespace b200em;
+
+extern "C" {
+
+int b200em_conv3d_wgrad_cs_supported(int Cin, int Cout, int kd, int kh, int kw) { return wgrad_cs_shape(Cin, Cout, kd, kh, kw) ? 1 : 0; }
+
+int b200em_conv3d_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw,
+                           float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream) {
+    B2_CHECK_ARG(x && dz && dw && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_wgrad_cs: bad arguments");
+    if (!wgrad_cs_shape(Cin, Cout, kd, kh, kw)) {
+        set_error("conv3d_wgrad_cs: shape (%d -> %d, %dx%dx%d) not supported by the w-stacked tcgen05 weight gradient", Cin, Cout, kd, kh, kw);
+        return 2;
+    }
+    B2_CHECK_ARG(x_ld % 8 == 0 && dz_ld % 8 == 0 && aligned16(x) && aligned16(dz), "conv3d_wgrad_cs: activations must be 16-byte aligned with pitch % 8 == 0");
+    B2_CHECK_ARG(x_ld >= Cin && dz_ld >= Cout, "conv3d_wgrad_cs: pitch smaller than channel count");
+    B2_CHECK_ARG((long long)H * W * x_ld < (1LL << 31) && (long long)H * W * dz_ld < (1LL << 31), "conv3d_wgrad_cs: slice too large for 32-bit in-slice offsets");
+    WgradCsParams p;
+    p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.dz = (const __nv_bfloat16*)dz; p.dz_ld = dz_ld;
+    p.dw = dw; p.db = db;
+    p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+    p.nco = Cout / CS_NB;
+    const int misc = CS_NB * 4 + (2 * CS_MAX_NS + 1) * 8 + 8 + 128;
+    int ns = (CS_MAX_SMEM - misc - 3 * CS_XSLOT) / (CS_XSLOT + CS_ZSLOT);
+    if (ns > CS_MAX_NS) ns = CS_MAX_NS;
+    B2_CHECK_ARG(ns >= 4, "conv3d_wgrad_cs: shared memory budget exceeded");
+    p.NS = ns;
+    p.nlw = ns < CS_NLW ? ns : CS_NLW;
+    const int smem_bytes = (ns + 3) * CS_XSLOT + ns * CS_ZSLOT + misc;
+    const int pairs = (Cin / 32) * p.nco;
+    long long splits = sm_count() / pairs;
+    if (splits < 1) splits = 1;
+    // depth slices per work item: enough items that every split has the same number of them, long enough that the two
+    // extra input slices of an item amortise
+    const long long cols = (long long)N * ((H + CS_TH - 1) / CS_TH) * ((W + CS_TW - 1) / CS_TW);
+    {
+        const char* e = getenv("B200EM_CS_DR");
+        int best = 1;
+        double best_cost = 1e30;
+        for (int dr = 1; dr <= (D < 64 ? D : 64); ++dr) {
+            const long long items = cols * ((D + dr - 1) / dr);
+            const long long waves = (items + splits - 1) / splits;
+            const double cost = (double)waves * (dr + 2.0);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = dr; }
+        }
+        p.DR = e ? atoi(e) : best;
+        if (p.DR < 1) p.DR = 1;
+    }
+    p.tiles_w = (W + CS_TW - 1) / CS_TW; p.tiles_h = (H + CS_TH - 1) / CS_TH; p.tiles_d = (D + p.DR - 1) / p.DR;
+    p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
+    if (splits > p.items) splits = p.items;
+    { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    B2_CUDA(cudaFuncSetAttribute(conv3d_wgrad_cs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_MAX_SMEM));
+    dim3 grid((unsigned)splits, (unsigned)pairs, 1);
+    conv3d_wgrad_cs_kernel<<<grid, CS_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"
