@@ -49,7 +49,7 @@ def _f32(t):
 class WeightPack:
     """Kernel-operand copies of one conv weight (derived caches; the fp32 nn.Parameter stays the master)."""
     __slots__ = ("w_fwd_f32", "w_dgrad_f32", "umma_fwd", "umma_dgrad", "version", "ptr", "cout", "cin", "kernel", "thin",
-                 "thin_kp", "s3_fwd", "s3_dgrad", "ds_fwd", "ds_dgrad")
+                 "thin_kp", "s3_fwd", "s3_dgrad", "ds_fwd", "ds_dgrad", "master")
 
 
 class CudaBackend:
@@ -99,18 +99,19 @@ class CudaBackend:
         pk = WeightPack()
         pk.version, pk.cout, pk.cin, pk.kernel = ver, cout, cin, (kd, kh, kw)
         taps = kd * kh * kw
-        pk.w_fwd_f32 = torch.empty((taps, cin, cout), dtype=torch.float32, device=w.device)
-        pk.w_dgrad_f32 = torch.empty((taps, cout, cin), dtype=torch.float32, device=w.device)
+        pk.w_fwd_f32 = pk.w_dgrad_f32 = None         # fp32 operands of the direct kernels: packed on first use (f32_operands)
+        pk.master = wd
         pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.s3_fwd = pk.s3_dgrad = pk.ds_fwd = pk.ds_dgrad = None
         pk.thin_kp = 0
         lib = _lib.load()
         with torch.cuda.device(w.device):
-            call("b200em_pack_conv_weights", _ptr(wd), cout, cin, kd, kh, kw, _ptr(pk.w_fwd_f32), _ptr(pk.w_dgrad_f32),
-                 _stream(w))
-            if self.use_umma and lib.b200em_conv3d_umma_supported(cin, cout, kd, kh, kw):
+            # one packed operand per direction: the depth-stacked layout where that kernel takes the layer, else the plain one
+            ds_f = self.use_ds and lib.b200em_conv3d_umma_ds_supported(cin, cout, kd, kh, kw)
+            ds_d = self.use_ds and lib.b200em_conv3d_umma_ds_supported(cout, cin, kd, kh, kw)
+            if self.use_umma and not ds_f and lib.b200em_conv3d_umma_supported(cin, cout, kd, kh, kw):
                 pk.umma_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.umma_fwd), _stream(w))
-            if self.use_umma and lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
+            if self.use_umma and not ds_d and lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
                 pk.umma_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.umma_dgrad), _stream(w))
             if self.use_s3 and lib.b200em_conv3d_umma_s3_supported(cin, cout, kd, kh, kw):
@@ -119,10 +120,10 @@ class CudaBackend:
             if self.use_s3 and lib.b200em_conv3d_umma_s3_supported(cout, cin, kd, kh, kw):
                 pk.s3_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_s3_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.s3_dgrad), _stream(w))
-            if self.use_ds and lib.b200em_conv3d_umma_ds_supported(cin, cout, kd, kh, kw):
+            if ds_f:
                 pk.ds_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_ds_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.ds_fwd), _stream(w))
-            if self.use_ds and lib.b200em_conv3d_umma_ds_supported(cout, cin, kd, kh, kw):
+            if ds_d:
                 pk.ds_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_ds_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.ds_dgrad), _stream(w))
             kp = -(-taps * cin // 32) * 32
@@ -135,6 +136,20 @@ class CudaBackend:
                 call("b200em_conv3d_umma_pack", _ptr(wt), cout, kp, 1, 1, 1, 0, _ptr(pk.thin), _stream(w))
         self._pack_cache[key] = pk
         return pk
+
+    def f32_operands(self, pk):
+        """fp32 (taps, Cin, Cout) / (taps, Cout, Cin) operands of the direct CUDA-core kernels, packed on first use."""
+        if pk.w_fwd_f32 is None:
+            cout, cin = pk.cout, pk.cin
+            kd, kh, kw = pk.kernel
+            taps = kd * kh * kw
+            wd = pk.master
+            pk.w_fwd_f32 = torch.empty((taps, cin, cout), dtype=torch.float32, device=wd.device)
+            pk.w_dgrad_f32 = torch.empty((taps, cout, cin), dtype=torch.float32, device=wd.device)
+            with torch.cuda.device(wd.device):
+                call("b200em_pack_conv_weights", _ptr(wd), cout, cin, kd, kh, kw, _ptr(pk.w_fwd_f32), _ptr(pk.w_dgrad_f32),
+                     _stream(wd))
+        return pk.w_fwd_f32, pk.w_dgrad_f32
 
     # ---- layout / statistics ---------------------------------------------------------------------------------
     def to_ndhwc(self, x, y):
@@ -188,7 +203,6 @@ class CudaBackend:
         xp, xld = _act(x)
         yp, yld = _act(y)
         assert _dt(x) == _dt(y)
-        w = pack.w_dgrad_f32 if dgrad else pack.w_fwd_f32
         b = bias.detach() if bias is not None else None
         kd, kh, kw = kernel
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
@@ -223,6 +237,7 @@ class CudaBackend:
                     "b200em_conv3d_umma", xp, xld, _f32(in_ss), _ptr(wu), _f32(b), yp, yld, _f32(sums), dp, dld, N, D, H, W, Cin,
                     Cout, kd, kh, kw, int(relu), _stream(x)))
                 return None
+        w = self.f32_operands(pack)[1 if dgrad else 0]
         self._timed("conv_direct_dgrad" if dgrad else "conv_direct_fwd", flops, lambda: call(
             "b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, None if dot_x is not None else _f32(sums),
             _dt(x), N, D, H, W, Cin, Cout, kd, kh, kw, int(relu), _stream(x)))

@@ -582,6 +582,98 @@ upsample2_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __restrict__ y, i
     }
 }
 
+// Forward, output-centric variant (the one launched for factors (2|1, 2, 2)): one thread per (output d, output h, LOW-res
+// w, 8-channel vector) produces the two outputs along w.  With clamped neighbour indices the weights are uniform
+// (out[2i] = .25 x[i-1] + .75 x[i], out[2i+1] = .75 x[i] + .25 x[i+1]; the clamp turns the edge samples into the exact
+// copies align_corners=False prescribes), so the 2 (d) x 2 (h) x 3 (w) neighbourhood is folded into three running
+// vectors as it is loaded: 12 loads, 24 accumulators, no 27-vector register tile.  HBM-bound: reads hit L1/L2.
+template <typename T, int VEC, int FD>
+__global__ void __launch_bounds__(256)
+upsample2_fwd_pair_kernel(const T* __restrict__ x, int64_t x_ld, T* __restrict__ y, int64_t y_ld, int D, int H, int W, int C,
+                          float* __restrict__ sums, unsigned total) {
+    __shared__ float red[256 * 2];
+    const int cvec = C / VEC;
+    const int n = blockIdx.y;
+    const int Do = D * FD, Ho = H * 2, Wo = W * 2;
+    const T* xn = x + (size_t)n * D * H * W * x_ld;
+    T* yn = y + (size_t)n * Do * Ho * Wo * y_ld;
+    float acc[VEC][2];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v][0] = acc[v][1] = 0.f;
+    // blockDim.x * gridDim.x is a multiple of cvec, so a thread keeps its channel vector over the grid-stride loop
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        unsigned t = idx;
+        const int cv = (int)(t % (unsigned)cvec); t /= (unsigned)cvec;
+        const int w = (int)(t % (unsigned)W); t /= (unsigned)W;
+        const int oh = (int)(t % (unsigned)Ho); t /= (unsigned)Ho;
+        const int od = (int)t;
+        // the two source rows along d and h and their weights
+        int d_a, d_b; float wd_a, wd_b;
+        if (FD == 2) {
+            const int i = od >> 1;
+            if (od & 1) { d_a = i; d_b = min(i + 1, D - 1); wd_a = 0.75f; wd_b = 0.25f; }
+            else { d_a = max(i - 1, 0); d_b = i; wd_a = 0.25f; wd_b = 0.75f; }
+        } else { d_a = d_b = od; wd_a = 1.f; wd_b = 0.f; }
+        int h_a, h_b; float wh_a, wh_b;
+        {
+            const int i = oh >> 1;
+            if (oh & 1) { h_a = i; h_b = min(i + 1, H - 1); wh_a = 0.75f; wh_b = 0.25f; }
+            else { h_a = max(i - 1, 0); h_b = i; wh_a = 0.25f; wh_b = 0.75f; }
+        }
+        const int wm = max(w - 1, 0), wp = min(w + 1, W - 1);
+        float am[VEC], a0[VEC], ap[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) am[v] = a0[v] = ap[v] = 0.f;
+#pragma unroll
+        for (int q = 0; q < (FD == 2 ? 4 : 2); ++q) {
+            const int dd = (q & 2) ? d_b : d_a, hh = (q & 1) ? h_b : h_a;
+            const float wt = ((q & 2) ? wd_b : wd_a) * ((q & 1) ? wh_b : wh_a);
+            const T* row = xn + ((size_t)dd * H + hh) * W * x_ld + cv * VEC;
+            float r[VEC];
+            Vec<T, VEC>::load(row + (size_t)wm * x_ld, r);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) am[v] = fmaf(wt, r[v], am[v]);
+            Vec<T, VEC>::load(row + (size_t)w * x_ld, r);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) a0[v] = fmaf(wt, r[v], a0[v]);
+            Vec<T, VEC>::load(row + (size_t)wp * x_ld, r);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) ap[v] = fmaf(wt, r[v], ap[v]);
+        }
+        float lo[VEC], hi[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            lo[v] = fmaf(0.25f, am[v], 0.75f * a0[v]);
+            hi[v] = fmaf(0.25f, ap[v], 0.75f * a0[v]);
+        }
+        T* yo = yn + (((size_t)od * Ho + oh) * Wo + 2 * w) * y_ld + cv * VEC;
+        Vec<T, VEC>::store(yo, lo);
+        Vec<T, VEC>::store(yo + y_ld, hi);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const float q0 = round_as<T>(lo[v]), q1 = round_as<T>(hi[v]);
+            acc[v][0] += q0 + q1;
+            acc[v][1] += q0 * q0 + q1 * q1;
+        }
+    }
+    if (sums) {
+        const int cvt = threadIdx.x % cvec;          // blockDim.x % cvec == 0
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            red[threadIdx.x * 2] = acc[v][0];
+            red[threadIdx.x * 2 + 1] = acc[v][1];
+            __syncthreads();
+            if ((int)threadIdx.x < cvec) {
+                float s1 = 0.f, s2 = 0.f;
+                for (int j = threadIdx.x; j < 256; j += cvec) { s1 += red[j * 2]; s2 += red[j * 2 + 1]; }
+                atomicAdd(sums + ((size_t)n * C + cvt * VEC + v) * 2, s1);
+                atomicAdd(sums + ((size_t)n * C + cvt * VEC + v) * 2 + 1, s2);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // Backward (transpose of the same weights): dx[i] = .25 g[2i-1] + a g[2i] + b g[2i+1] + .25 g[2i+2] per axis with
 // a = (i == 0 ? 1 : .75), b = (i == n-1 ? 1 : .75) and the out-of-range taps dropped.  Separable: w, then h, then d.
 template <typename T, int VEC, int FD, int FH, int FW>
@@ -820,12 +912,24 @@ int b200em_upsample_trilinear_fwd(const void* x, int64_t x_ld, void* y, int64_t 
         constexpr int V = FullVec<T>::value;
         const int cvec_ = C / V;
         if (can_vec<T>(C, {x_ld, y_ld}, {x, y}) && cvec_ <= 256 && 256 % cvec_ == 0 && fd <= 2 && fh == 2 && fw == 2) {
-            const int th = (H + UP_BH - 1) / UP_BH, tw = (W + UP_BW - 1) / UP_BW, td = (D + UP_BD - 1) / UP_BD;
-            dim3 grid((unsigned)(td * th * tw), 1, (unsigned)N);
-            if (fd == 2)
-                upsample2_fwd_kernel<T, V, 2, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, th, tw);
-            else
-                upsample2_fwd_kernel<T, V, 1, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, th, tw);
+            const int64_t tot = (int64_t)D * fd * H * 2 * W * cvec_;
+            if (tot < (1LL << 31) && N <= 65535) {
+                int64_t blocks = (tot + 255) / 256;
+                const int64_t cap = (int64_t)sm_count() * 16;
+                if (blocks > cap) blocks = cap;
+                dim3 grid((unsigned)blocks, (unsigned)N, 1);
+                if (fd == 2)
+                    upsample2_fwd_pair_kernel<T, V, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, (unsigned)tot);
+                else
+                    upsample2_fwd_pair_kernel<T, V, 1><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, (unsigned)tot);
+            } else {
+                const int th = (H + UP_BH - 1) / UP_BH, tw = (W + UP_BW - 1) / UP_BW, td = (D + UP_BD - 1) / UP_BD;
+                dim3 grid((unsigned)(td * th * tw), 1, (unsigned)N);
+                if (fd == 2)
+                    upsample2_fwd_kernel<T, V, 2, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, th, tw);
+                else
+                    upsample2_fwd_kernel<T, V, 1, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, th, tw);
+            }
         } else if (can_vec<T>(C, {x_ld, y_ld}, {x, y})) {
             Launch2D l = make_launch(C / V, So, N);
             upsample_fwd_kernel<T, V><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);

@@ -181,6 +181,114 @@ head_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ ou
     }
 }
 
+// ---- small heads (Cin <= 32, Cout <= 2: the U-Net's out_conv on the first feature level) -------------------------------
+// One thread per voxel, the Cout x Cin filter and the per-thread dW partials live in registers, x is read ONCE (it also
+// carries the ReLU mask of the block below), dx is written once; dW / db are reduced over the block at the end.
+template <typename T, int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+head_fwd_small_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ out, int64_t S, int act, int64_t total) {
+    constexpr int V = FullVec<T>::value;
+    float wr[COUT][CIN], br[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+        br[j] = bias ? bias[j] : 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) wr[j][c] = w[j * CIN + c];
+    }
+    for (int64_t vox = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; vox < total; vox += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = vox / S, s_ = vox % S;
+        const T* xp = x + vox * x_ld;
+        float acc[COUT];
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) acc[j] = br[j];
+#pragma unroll
+        for (int c = 0; c < CIN; c += V) {
+            float xv[V];
+            Vec<T, V>::load(xp + c, xv);
+#pragma unroll
+            for (int j = 0; j < COUT; ++j)
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc[j] = fmaf(wr[j][c + k], xv[k], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) out[((size_t)n * COUT + j) * S + s_] = act_fwd(acc[j], act);
+    }
+}
+
+template <typename T, int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+head_bwd_small_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, const T* __restrict__ x, int64_t x_ld,
+                      const float* __restrict__ w, T* __restrict__ dx, int64_t dx_ld, float* __restrict__ dw,
+                      float* __restrict__ db, int64_t S, int act, int relu_mask, int64_t total) {
+    constexpr int V = FullVec<T>::value;
+    __shared__ float red[8][COUT * CIN + COUT];
+    float wr[COUT][CIN], aw[COUT][CIN], ab[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+        ab[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) { wr[j][c] = w[j * CIN + c]; aw[j][c] = 0.f; }
+    }
+    for (int64_t vox = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; vox < total; vox += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = vox / S, s_ = vox % S;
+        float dz[COUT];
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) {
+            const size_t o = ((size_t)n * COUT + j) * S + s_;
+            dz[j] = grad_out[o] * act_bwd(out[o], act);
+            ab[j] += dz[j];
+        }
+        const T* xp = x + vox * x_ld;
+#pragma unroll
+        for (int c = 0; c < CIN; c += V) {
+            float xv[V], r[V];
+            Vec<T, V>::load(xp + c, xv);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                float g = 0.f;
+#pragma unroll
+                for (int j = 0; j < COUT; ++j) {
+                    g = fmaf(wr[j][c + k], dz[j], g);
+                    aw[j][c + k] = fmaf(dz[j], xv[k], aw[j][c + k]);
+                }
+                r[k] = (relu_mask && !(xv[k] > 0.f)) ? 0.f : g;
+            }
+            if (dx) Vec<T, V>::store(dx + vox * dx_ld + c, r);
+        }
+    }
+    // block reduction: warp shuffles, then one row per warp in shared memory, then COUT*CIN + COUT atomics per block
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            float a = aw[j][c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) red[wi][j * CIN + c] = a;
+        }
+        float b = ab[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) red[wi][COUT * CIN + j] = b;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * CIN + COUT; i += blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a += red[q][i];
+        if (i < COUT * CIN) atomicAdd(dw + i, a);
+        else if (db) atomicAdd(db + (i - COUT * CIN), a);
+    }
+}
+
+template <typename T>
+static bool head_small_ok(const void* x, int64_t x_ld, const void* dx, int64_t dx_ld, int Cin, int Cout) {
+    constexpr int V = FullVec<T>::value;
+    return (Cin == 16 || Cin == 32) && (Cout == 1 || Cout == 2) && x_ld % V == 0 && aligned16(x) && (!dx || (dx_ld % V == 0 && aligned16(dx)));
+}
+
 }  // namespace b200em
 
 using namespace b200em;
@@ -209,6 +317,31 @@ static void launch_head_bwd(unsigned blocks, cudaStream_t st, const float* grad_
 }
 
 
+template <typename T>
+static void launch_head_fwd_small(unsigned blocks, cudaStream_t st, const void* x, int64_t x_ld, const float* w, const float* bias,
+                                  float* out, int64_t S, int Cin, int Cout, int act, int64_t total) {
+#define B2_HEAD_FWD_SMALL(CI, CO) head_fwd_small_kernel<T, CI, CO><<<blocks, 256, 0, st>>>((const T*)x, x_ld, w, bias, out, S, act, total)
+    if (Cin == 32 && Cout == 2) B2_HEAD_FWD_SMALL(32, 2);
+    else if (Cin == 32) B2_HEAD_FWD_SMALL(32, 1);
+    else if (Cout == 2) B2_HEAD_FWD_SMALL(16, 2);
+    else B2_HEAD_FWD_SMALL(16, 1);
+#undef B2_HEAD_FWD_SMALL
+}
+
+template <typename T>
+static void launch_head_bwd_small(unsigned blocks, cudaStream_t st, const float* grad_out, const float* out, const void* x,
+                                  int64_t x_ld, const float* w, void* dx, int64_t dx_ld, float* dw, float* db, int64_t S, int Cin,
+                                  int Cout, int act, int relu_mask, int64_t total) {
+#define B2_HEAD_BWD_SMALL(CI, CO)                                                                                             \
+    head_bwd_small_kernel<T, CI, CO><<<blocks, 256, 0, st>>>(grad_out, out, (const T*)x, x_ld, w, (T*)dx, dx_ld, dw, db, S, act, \
+                                                             relu_mask, total)
+    if (Cin == 32 && Cout == 2) B2_HEAD_BWD_SMALL(32, 2);
+    else if (Cin == 32) B2_HEAD_BWD_SMALL(32, 1);
+    else if (Cout == 2) B2_HEAD_BWD_SMALL(16, 2);
+    else B2_HEAD_BWD_SMALL(16, 1);
+#undef B2_HEAD_BWD_SMALL
+}
+
 extern "C" {
 
 int b200em_head_fwd(const void* x, int64_t x_ld, int dtype, const float* w, const float* bias, float* out, int N,
@@ -221,7 +354,9 @@ int b200em_head_fwd(const void* x, int64_t x_ld, int dtype, const float* w, cons
     if (blocks > cap) blocks = cap;
     B2_DISPATCH_DTYPE(dtype, T, {
         constexpr int V = FullVec<T>::value;
-        if (Cin % V == 0 && x_ld % V == 0 && aligned16(x))
+        if (head_small_ok<T>(x, x_ld, nullptr, 0, Cin, Cout)) {
+            launch_head_fwd_small<T>((unsigned)blocks, (cudaStream_t)stream, x, x_ld, w, bias, out, S, Cin, Cout, act, total);
+        } else if (Cin % V == 0 && x_ld % V == 0 && aligned16(x))
             head_fwd_kernel<T, V><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, w, bias, out, S, Cin, Cout, act, total);
         else
             head_fwd_kernel<T, 1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, w, bias, out, S, Cin, Cout, act, total);
@@ -241,6 +376,20 @@ int b200em_head_bwd(const float* grad_out, const float* out, const void* x, int6
     int64_t ntiles = (total + HB_TILE - 1) / HB_TILE;
     int64_t blocks = (int64_t)sm_count() * 4;
     if (blocks > ntiles) blocks = ntiles;
+    {
+        bool done = false;
+        B2_DISPATCH_DTYPE(dtype, T, {
+            if (head_small_ok<T>(x, x_ld, dx, dx_ld, Cin, Cout)) {
+                launch_head_bwd_small<T>((unsigned)blocks, (cudaStream_t)stream, grad_out, out, x, x_ld, w, dx, dx_ld, dw, db, S, Cin, Cout,
+                                         act, relu_mask, total);
+                done = true;
+            }
+        })
+        if (done) {
+            B2_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     for (int co0 = 0; co0 < Cout; co0 += HB_MAXCO) {
         int cob = Cout - co0 < HB_MAXCO ? Cout - co0 : HB_MAXCO;
         B2_DISPATCH_DTYPE(dtype, T, {
