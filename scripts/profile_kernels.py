@@ -1,0 +1,61 @@
+"""One launch of each hot kernel on its cfg2 L0 shape between cudaProfilerStart/Stop (for `ncu --set full`).
+
+    ncu --set full --import-source on --clock-control none --profile-from-start off -o gpurun_out/r01_kernels python scripts/profile_kernels.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from torch_em_b200.backend import default_backend
+
+dev = "cuda:0"
+B = default_backend()
+N, S = 4, 128
+which = set((os.environ.get("KERNELS") or "ds_fwd,ds_dgrad,cs_wgrad,plain_fwd,upsample_fwd,upsample_bwd,maxpool_bwd,im2col").split(","))
+torch.manual_seed(0)
+x = torch.randn((N, S, S, S, 32), device=dev).bfloat16()
+dz = torch.randn((N, S, S, S, 32), device=dev).bfloat16()
+w = torch.randn((32, 32, 3, 3, 3), device=dev) * 0.03
+b = torch.zeros(32, device=dev)
+ss = torch.ones((N, 32, 2), device=dev)
+pk = B.pack(("prof", 32), w)
+y = torch.empty_like(x)
+g = torch.empty_like(x)
+sums = torch.zeros((N, 32, 2), device=dev)
+dw = torch.zeros_like(w)
+db = torch.zeros(32, device=dev)
+x2 = torch.randn((N, 32, 32, 32, 128), device=dev).bfloat16()
+w2 = torch.randn((128, 128, 3, 3, 3), device=dev) * 0.03
+pk2 = B.pack(("prof", 128), w2)
+y2 = torch.empty_like(x2)
+s2 = torch.zeros((N, 128, 2), device=dev)
+ss2 = torch.ones((N, 128, 2), device=dev)
+lo = torch.randn((N, S // 2, S // 2, S // 2, 32), device=dev).bfloat16()
+cat = torch.empty((N, S, S, S, 64), device=dev, dtype=torch.bfloat16)
+dlo = torch.empty_like(lo)
+x1 = torch.randn((N, S, S, S, 1), device=dev).bfloat16()
+ss1 = torch.ones((N, 1, 2), device=dev)
+
+runs = {
+    "ds_fwd": lambda: B.conv(x, ss, pk, b, y, sums, (3, 3, 3), True, False),
+    "ds_dgrad": lambda: B.conv(dz, None, pk, None, g, sums, (3, 3, 3), False, True, dot_x=x),
+    "cs_wgrad": lambda: B.wgrad(x, ss, dz, dw, db, (3, 3, 3)),
+    "plain_fwd": lambda: B.conv(x2, ss2, pk2, torch.zeros(128, device=dev), y2, s2, (3, 3, 3), True, False),
+    "upsample_fwd": lambda: B.upsample_fwd(lo, cat[..., :32], (2, 2, 2), sums),
+    "upsample_bwd": lambda: B.upsample_bwd(cat[..., :32], dlo, (2, 2, 2)),
+    "maxpool_bwd": lambda: B.maxpool_bwd(cat[..., 32:], lo, cat[..., :32], y, (2, 2, 2), 1),
+    "im2col": lambda: B.im2col(x1, ss1, (3, 3, 3), 32),
+}
+for k, fn in runs.items():
+    if k in which:
+        fn(); fn()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+for k, fn in runs.items():
+    if k in which:
+        fn()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("done")

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
             const uint32_t np = (uint32_t)p.NP, b_tap16 = (uint32_t)(J * p.NP), bk16 = 2 * np;
             const uint32_t a_bytes16 = (uint32_t)(p.a_bytes >> 4), bstage16 = (uint32_t)(p.b_stage_bytes >> 4);
             uint32_t fill = 0, cnt = 0, it = 0;
+            bool a_ok = false, b_ok = false;             // results of the early probes of the next a_full / b_full barriers
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
                 const int slot = (p.acc_bufs == 2) ? (it & 1) : 0;
                 const uint32_t use = (p.acc_bufs == 2) ? (it >> 1) : it;
@@ -188,13 +189,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                 for (int r = 0; r < R_; ++r) tcol[r] = tmem_base + slot * acc_cols + r * np;
                 for (int c = 0; c < p.nchunks; ++c, ++fill) {
                     const int buf = fill & 1;
-                    mbar_wait(&a_full[buf], (fill >> 1) & 1);
+                    if (!a_ok) mbar_wait(&a_full[buf], (fill >> 1) & 1);
                     tc_fence_after();
+                    a_ok = mbar_test_wait(&a_full[(fill + 1) & 1], ((fill + 1) >> 1) & 1);
                     const uint32_t abuf = a_lo_base + buf * a_bytes16;
                     for (int g = 0; g < ngroups; ++g, ++cnt) {
                         const int st = cnt % NSTAGE;
-                        mbar_wait(&b_full[st], (cnt / NSTAGE) & 1);
+                        if (!b_ok) mbar_wait(&b_full[st], (cnt / NSTAGE) & 1);
                         tc_fence_after();
+                        // early probe of the next weight stage: a probe costs ~200 cycles of latency even when the barrier is
+                        // complete, so it is issued before this stage's MMAs and consumed after them
+                        b_ok = mbar_test_wait(&b_full[(cnt + 1) % NSTAGE], ((cnt + 1) / NSTAGE) & 1);
                         const uint32_t bst = b_lo_base + st * bstage16;
                         for (int tg = 0; tg < p.G; ++tg) {
                             const int tap = g * p.G + tg;

@@ -340,11 +340,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const Con
             uint32_t slot = 0, fph = 0;
             int r0 = 0;
             uint32_t w0 = 0;
+            bool a_ok = false, acc_ok = false;           // results of the early probes of the next a_full / acc_empty barriers
             const bool prof = (p.debug & 8) != 0;
             long long pf_wa = 0, pf_wacc = 0, pf_t0 = clock64(), pf_n = 0;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
                 int r = r0;                              // ring position of output od = s (the newest output slice s feeds)
                 uint32_t wpar = w0;
+                acc_ok = false;
                 for (int s = 0; s < DR + 2; ++s) {
                     const int a_lo = s - (DR - 1) > 0 ? s - (DR - 1) : 0;
                     const int nblk = (s < 2 ? s : 2) - a_lo + 1;
@@ -354,9 +356,16 @@ __global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const Con
                     if (a_lo == 0) {                     // a new accumulator (output od = s) starts with this slice
                         long long t_ = 0;
                         if (prof) t_ = clock64();
-                        mbar_wait(&acc_empty[k0], wpar ^ 1);
+                        if (!acc_ok) mbar_wait(&acc_empty[k0], wpar ^ 1);
                         if (prof) pf_wacc += clock64() - t_;
                         tc_fence_after();
+                    }
+                    // probe the NEXT slice's new accumulator now; the answer is consumed after this slice's MMAs were issued
+                    acc_ok = false;
+                    if (s + 1 <= DR - 1) {
+                        const int rn = r + 1 == NA ? 0 : r + 1;
+                        const uint32_t wn = r + 1 == NA ? wpar ^ 1u : wpar;
+                        acc_ok = mbar_test_wait(&acc_empty[NA - 1 - rn], wn ^ 1u);
                     }
                     // segments of consecutive ring blocks: [k0, k0+n1) and, past the wrap, [0, n2)
                     const int n1 = nblk < NA - k0 ? nblk : NA - k0;
@@ -368,10 +377,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const Con
                     for (int c = 0; c < p.nchunks; ++c, bch += (uint32_t)ntap * BTAP16) {
                         long long t_ = 0;
                         if (prof) t_ = clock64();
-                        mbar_wait(&a_full[slot], fph);
+                        if (!a_ok) mbar_wait(&a_full[slot], fph);
                         if (prof) { pf_wa += clock64() - t_; ++pf_n; }
                         tc_fence_after();
                         const uint32_t abuf = a_lo_base + slot * ASTAGE16;
+                        {   // probe the next stage's barrier before this stage's MMAs are issued
+                            const uint32_t ns_ = slot + 1 == (uint32_t)NS ? 0u : slot + 1;
+                            const uint32_t np_ = slot + 1 == (uint32_t)NS ? fph ^ 1u : fph;
+                            a_ok = mbar_test_wait(&a_full[ns_], np_);
+                        }
                         if (!(p.debug & 4)) {
                             const bool fresh = c == 0 && a_lo == 0;       // block k0 (a = 0) is overwritten by its very first MMA
                             if (fresh) {

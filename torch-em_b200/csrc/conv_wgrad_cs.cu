@@ -239,16 +239,18 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
             uint32_t slot = 0, fph = 0;              // ring position of the next stage to wait for
             uint32_t rslot = 0;                      // ring position of the output slice being issued (= its first x slice)
             bool first = true;                       // very first MMAs of this CTA overwrite the accumulators
+            bool f_ok = false;
             const bool prof = (p.debug & 8) != 0;
             long long pf_w = 0, pf_t0 = clock64(), pf_n = 0;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
                 for (int t = 0; t < DR + 2; ++t) {
                     long long t_ = 0;
                     if (prof) t_ = clock64();
-                    mbar_wait(&full[slot], fph);
+                    if (!f_ok) mbar_wait(&full[slot], fph);
                     if (prof) { pf_w += clock64() - t_; ++pf_n; }
                     tc_fence_after();
                     if (++slot == (uint32_t)NS) { slot = 0; fph ^= 1; }
+                    f_ok = mbar_test_wait(&full[slot], fph);      // early probe of the next stage (a probe costs ~200 cycles of latency)
                     if (t < 2) continue;
                     // output slice r = t - 2: x slices r, r+1, r+2 (+ one ignored) start at ring slot rslot, dz copies in slot rslot
                     const uint32_t xs = a_lo_c + rslot * (CS_XSLOT / 16);

@@ -914,8 +914,9 @@ int b200em_upsample_trilinear_fwd(const void* x, int64_t x_ld, void* y, int64_t 
         if (can_vec<T>(C, {x_ld, y_ld}, {x, y}) && cvec_ <= 256 && 256 % cvec_ == 0 && fd <= 2 && fh == 2 && fw == 2) {
             const int64_t tot = (int64_t)D * fd * H * 2 * W * cvec_;
             if (tot < (1LL << 31) && N <= 65535) {
-                int64_t blocks = (tot + 255) / 256;
-                const int64_t cap = (int64_t)sm_count() * 16;
+                // >= 16 outputs pairs per thread: the per-block statistics reduction and its atomics amortise
+                int64_t blocks = (tot + 256 * 16 - 1) / (256 * 16);
+                const int64_t cap = (int64_t)sm_count() * 8;
                 if (blocks > cap) blocks = cap;
                 dim3 grid((unsigned)blocks, (unsigned)N, 1);
                 if (fd == 2)
