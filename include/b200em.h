@@ -114,6 +114,16 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
                           void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W,
                           int Cin, int Cout, int kd, int kh, int kw, int relu, void* stream);
 
+/* First convolution of the network (Cin = 1, 3x3x3, Cout in {16,32,48,64}; unet.py:412-438 first block): the im2col rows
+ * (K = 27 padded to 32) are built on the fly in shared memory and fed to tcgen05.mma; same fused prologue (norm apply on
+ * the 1-channel input, x: (N,D,H,W,1) bf16) and epilogue (bias, ReLU, statistics) as b200em_conv3d_umma.  w / dw are the
+ * torch-layout fp32 parameter (Cout,1,3,3,3) and its gradient (accumulated); db (nullable) += sum dz. */
+int b200em_conv3d_first_supported(int Cin, int Cout, int kd, int kh, int kw);
+int b200em_conv3d_first(const void* x, const float* in_scale_shift, const float* w, const float* bias, void* y, int64_t y_ld,
+                        float* sums, int N, int D, int H, int W, int Cout, int relu, void* stream);
+int b200em_conv3d_first_wgrad(const void* x, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw, float* db,
+                              int N, int D, int H, int W, int Cout, void* stream);
+
 /* Weight gradient on the tensor cores (bf16 operands, fp32 accumulation in TMEM, fp32 atomics into dw).
  * dw (Cout,Cin,kd,kh,kw) fp32 += sum dz * x_hat (same contract as b200em_conv3d_wgrad_direct); db (nullable)
  * (Cout) fp32 += sum dz -- the bias gradient, fused into the dz operand load.  Takes Cin % 32 == 0, Cout % 16 == 0. */

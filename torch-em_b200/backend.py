@@ -127,7 +127,8 @@ class CudaBackend:
                 pk.ds_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_ds_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.ds_dgrad), _stream(w))
             kp = -(-taps * cin // 32) * 32
-            if self.use_umma and cin <= 4 and lib.b200em_conv3d_umma_supported(kp, cout, 1, 1, 1):
+            first = self.use_ds and lib.b200em_conv3d_first_supported(cin, cout, kd, kh, kw)
+            if self.use_umma and cin <= 4 and not first and lib.b200em_conv3d_umma_supported(kp, cout, 1, 1, 1):
                 # thin-K first conv: W'[co][tap*Cin+ci] = W[co][ci][tap], zero padded to Kp channels (im2col layout)
                 wt = torch.zeros((cout, kp), dtype=torch.float32, device=w.device)
                 wt[:, :taps * cin] = wd.reshape(cout, cin, taps).permute(0, 2, 1).reshape(cout, taps * cin)
@@ -206,6 +207,13 @@ class CudaBackend:
         b = bias.detach() if bias is not None else None
         kd, kh, kw = kernel
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
+        if (not dgrad) and self.use_ds and Cin == 1 and xld == 1 and x.dtype == torch.bfloat16 and yld % 8 == 0 and \
+                y.data_ptr() % 16 == 0 and dot_x is None and _lib.load().b200em_conv3d_first_supported(Cin, Cout, kd, kh, kw):
+            # first conv of the network: im2col rows built on the fly in shared memory, straight from the fp32 parameter
+            self._timed("conv_umma_fwd", flops, lambda: call(
+                "b200em_conv3d_first", xp, _f32(in_ss), _f32(pack.master), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cout,
+                int(relu), _stream(x)))
+            return None
         if (not dgrad) and pack.thin is not None and x.dtype == torch.bfloat16 and yld % 8 == 0 and y.data_ptr() % 16 == 0:
             cols = self.im2col(x, in_ss, kernel, pack.thin_kp)
             assert dot_x is None
@@ -265,6 +273,11 @@ class CudaBackend:
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
         taps = kd * kh * kw
         kp = -(-taps * Cin // 32) * 32
+        if self.use_umma and self.use_ds and Cin == 1 and xld == 1 and x.dtype == torch.bfloat16 and zld % 8 == 0 and \
+                dz.data_ptr() % 16 == 0 and _lib.load().b200em_conv3d_first_supported(Cin, Cout, kd, kh, kw):
+            self._timed("conv_umma_wgrad", flops, lambda: call(
+                "b200em_conv3d_first_wgrad", xp, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cout, _stream(x)))
+            return
         if self.use_umma and Cin <= 4 and x.dtype == torch.bfloat16 and zld % 8 == 0 and dz.data_ptr() % 16 == 0 and \
                 _lib.load().b200em_conv3d_wgrad_umma_supported(kp, Cout, 1, 1, 1):
             cols = aux if aux is not None else self.im2col(x, in_ss, kernel, kp)

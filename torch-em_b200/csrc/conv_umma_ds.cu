@@ -581,6 +581,402 @@ __global__ void pack_ds_weights_kernel(const float* __restrict__ w, int Cout, in
     }
 }
 
+
+// ===============================================================================================================
+// First convolution of the network (Cin = 1, 3x3x3: K = 27, too thin for the implicit GEMM above).  The im2col rows
+// are built ON THE FLY in shared memory -- 27 neighbours of each voxel gathered from a small haloed 1-channel tile,
+// zero-padded to K = 32 -- and consumed by two tcgen05.mma (K = 16 each) per 128-voxel slab; nothing but the input
+// (2 B/voxel) is read and nothing but the output is written.  Same epilogue as the kernels above.  The weight-gradient
+// kernel below builds the identical shared-memory image and uses it MN-major (K = voxels).
+namespace {
+constexpr int F1_NLW = 8;
+constexpr int F1_THREADS = 128 + F1_NLW * 32 + 32;
+constexpr int F1_W_MMA = 4 + F1_NLW;
+constexpr int F1_NS = 8;                              // A ring depth (8 KB per stage)
+constexpr int F1_ASTAGE = 4 * 128 * 16;               // [4 k-groups of 8 taps][128 voxels][8 bf16]
+constexpr int F1_SCR = 3 * DS_HP * DS_WP;             // per-warp scratch: haloed 1-channel tile of three slices (bf16)
+}  // namespace
+
+struct ConvFirstParams {
+    const __nv_bfloat16* x;                           // (N, D, H, W, 1)
+    const float* in_ss;                               // (N, 1, 2) or null
+    const float* w;                                   // torch (Cout, 1, 3, 3, 3) fp32
+    const float* bias;
+    __nv_bfloat16* y; long long y_ld;
+    float* sums;
+    const __nv_bfloat16* dz; long long dz_ld;         // weight-gradient kernel only
+    float* dw; float* db;
+    int N, D, H, W, Cout, relu, DR;
+    int tiles_w, tiles_h, tiles_d;
+    long long items;
+};
+
+__device__ __forceinline__ void f1_coords(const ConvFirstParams& p, long long item_, int& n, int& d0, int& h0, int& w0) {
+    unsigned item = (unsigned)item_;
+    const unsigned tw = item % (unsigned)p.tiles_w; item /= (unsigned)p.tiles_w;
+    const unsigned th = item % (unsigned)p.tiles_h; item /= (unsigned)p.tiles_h;
+    const unsigned td = item % (unsigned)p.tiles_d; item /= (unsigned)p.tiles_d;
+    n = (int)item; d0 = (int)td * p.DR; h0 = (int)th * DS_TH; w0 = (int)tw * DS_TW;
+}
+
+// One loader warp builds the im2col image of one 128-voxel slab (output slice gd, tile origin h0, w0) at `dst`:
+// [k-group j][voxel m = 8*hl + wl][8 taps], tap k = (a*3 + b)*3 + c, k >= 27 zero.  scr = this warp's scratch.
+__device__ __forceinline__ void f1_build_slab(const ConvFirstParams& p, int n, int gd, int h0, int w0, float sc, float sh,
+                                              __nv_bfloat16* scr, uint8_t* dst, int lane) {
+    const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W;
+    for (int i = lane; i < F1_SCR; i += 32) {
+        const int wp_ = i % DS_WP, hp_ = (i / DS_WP) % DS_HP, a = i / (DS_WP * DS_HP);
+        const int sd = gd + a - 1, gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
+        float v = 0.f;
+        if (sd >= 0 && sd < p.D && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W)
+            v = fmaf(__bfloat162float(xn[((size_t)sd * p.H + gh) * p.W + gw]), sc, sh);
+        scr[i] = __float2bfloat16_rn(v);
+    }
+    __syncwarp();
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(scr);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int m = lane + 32 * q;
+        const int hl = m / DS_TW, wl = m % DS_TW;
+        uint32_t pk[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+            uint32_t lo = 0, hi = 0;
+            const int k0 = 2 * k2, k1 = 2 * k2 + 1;
+            if (k0 < 27) lo = s16[((k0 / 9) * DS_HP + hl + (k0 / 3) % 3) * DS_WP + wl + k0 % 3];
+            if (k1 < 27) hi = s16[((k1 / 9) * DS_HP + hl + (k1 / 3) % 3) * DS_WP + wl + k1 % 3];
+            pk[k2] = lo | (hi << 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(dst + j * (128 * 16) + m * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+    __syncwarp();                                     // scratch is reused by this warp's next slab
+}
+
+template <int CO>
+__global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvFirstParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int NA = (512 / CO) < DS_MAX_NA ? (512 / CO) : DS_MAX_NA;
+    uint8_t* smA = smem;                                              // [F1_NS][F1_ASTAGE]
+    uint8_t* smB = smA + F1_NS * F1_ASTAGE;                           // [4 k-groups][CO][8 bf16]
+    __nv_bfloat16* s_scr = reinterpret_cast<__nv_bfloat16*>(smB + 4 * CO * 16);   // [F1_NLW][F1_SCR]
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_scr) + ((F1_NLW * F1_SCR * 2 + 15) & ~15));
+    float* s_sums = s_bias + CO;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sums + 2 * CO);
+    uint64_t* a_full = bars;                          // [F1_NS]
+    uint64_t* a_empty = a_full + F1_NS;               // [F1_NS]
+    uint64_t* acc_full = a_empty + F1_NS;             // [NA]
+    uint64_t* acc_empty = acc_full + DS_MAX_NA;       // [NA]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + DS_MAX_NA);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int DR = p.DR;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < F1_NS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_mbar_init();
+    }
+    if (warp == F1_W_MMA) tmem_alloc(s_tmem, 512);
+    // weight operand straight from the fp32 parameter: B[k-group j][co][8 taps], taps >= 27 zero
+    for (int i = threadIdx.x; i < 4 * CO * 8; i += F1_THREADS) {
+        const int e = i % 8, co = (i / 8) % CO, j = i / (8 * CO);
+        const int k = j * 8 + e;
+        reinterpret_cast<__nv_bfloat16*>(smB)[i] = __float2bfloat16_rn(k < 27 ? p.w[co * 27 + k] : 0.f);
+    }
+    for (int i = threadIdx.x; i < CO; i += F1_THREADS) {
+        s_bias[i] = p.bias ? p.bias[i] : 0.f;
+        s_sums[2 * i] = 0.f;
+        s_sums[2 * i + 1] = 0.f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp >= 4 && warp < F1_W_MMA) {
+        // ===================== loaders: warp w8 builds every 8th slab =====================
+        const int w8 = warp - 4;
+        __nv_bfloat16* scr = s_scr + w8 * F1_SCR;
+        uint32_t slot = 0, phase = 1;
+        int owner = 0;
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+            int n, d0, h0, w0;
+            f1_coords(p, item, n, d0, h0, w0);
+            const float sc = p.in_ss ? p.in_ss[n * 2] : 1.f, sh = p.in_ss ? p.in_ss[n * 2 + 1] : 0.f;
+            for (int od = 0; od < DR; ++od) {
+                const uint32_t my_slot = slot, my_phase = phase;
+                const bool mine = owner == w8;
+                if (++slot == F1_NS) { slot = 0; phase ^= 1; }
+                if (++owner == F1_NLW) owner = 0;
+                if (!mine) continue;
+                mbar_wait(&a_empty[my_slot], my_phase);
+                f1_build_slab(p, n, d0 + od, h0, w0, sc, sh, scr, smA + my_slot * F1_ASTAGE, lane);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[my_slot]);
+            }
+        }
+    } else if (warp == F1_W_MMA) {
+        // ===================== MMA issuer: two K = 16 MMAs per slab =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, CO);
+            const uint64_t ad = make_desc(0, 128 * 16, 128), bd = make_desc(0, (uint32_t)(CO * 16), 128);
+            const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
+            const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
+            const uint32_t b_lo = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smB) >> 4);
+            uint32_t slot = 0, fph = 0;
+            int r = 0;
+            uint32_t wpar = 0;
+            for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+                for (int od = 0; od < DR; ++od) {
+                    mbar_wait(&acc_empty[r], wpar ^ 1);
+                    mbar_wait(&a_full[slot], fph);
+                    tc_fence_after();
+                    const uint32_t a0 = a_lo_base + slot * (F1_ASTAGE / 16);
+                    const uint32_t tacc = tmem_base + (uint32_t)(r * CO);
+                    umma_bf16_c<false>(tacc, a0, a_hi, b_lo, b_hi, idesc);
+                    umma_bf16_c<true>(tacc, a0 + 2 * 128, a_hi, b_lo + 2 * CO, b_hi, idesc);
+                    umma_commit(&a_empty[slot]);
+                    umma_commit(&acc_full[r]);
+                    if (++slot == F1_NS) { slot = 0; fph ^= 1; }
+                    if (++r == NA) { r = 0; wpar ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 0-3) =====================
+        const int row = warp * 32 + lane;
+        const int hl = row / DS_TW, wl = row % DS_TW;
+        constexpr bool kAcc = CO <= 32;
+        constexpr int NAcc = kAcc ? CO : 1;
+        float acc_s[NAcc], acc_q[NAcc];
+#pragma unroll
+        for (int i = 0; i < NAcc; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
+        const bool ws = p.sums != nullptr;
+        int r = 0;
+        uint32_t wpar = 0;
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+            int n, d0, h0, w0;
+            f1_coords(p, item, n, d0, h0, w0);
+            const int gh = h0 + hl, gw = w0 + wl;
+            const bool valid_hw = gh < p.H && gw < p.W;
+            const size_t vox0 = (((size_t)n * p.D + d0) * p.H + (valid_hw ? gh : 0)) * p.W + (valid_hw ? gw : 0);
+            const size_t hw = (size_t)p.H * p.W;
+            for (int od = 0; od < DR; ++od) {
+                mbar_wait(&acc_full[r], wpar);
+                tc_fence_after();
+                const int gd = d0 + od;
+                const bool valid = valid_hw && gd < p.D;
+                __nv_bfloat16* yp = p.y + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(r * CO);
+                if constexpr (CO == 16) {
+                    ds_epilogue_block<16, true>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
+                } else if constexpr (CO == 32) {
+                    ds_epilogue_block<16, true>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
+                    ds_epilogue_block<16, true>(taddr + 16, s_bias + 16, p.relu, valid, yp + 16, nullptr, false, acc_s + 16, acc_q + 16, s_sums,
+                                                ws, lane);
+                } else {
+                    ds_epilogue_block<32, false>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
+                    if constexpr (CO == 64)
+                        ds_epilogue_block<32, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, nullptr, false, acc_s, acc_q, s_sums + 64,
+                                                     ws, lane);
+                    if constexpr (CO == 48)
+                        ds_epilogue_block<16, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, nullptr, false, acc_s, acc_q, s_sums + 64,
+                                                     ws, lane);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[r]);
+                if (++r == NA) { r = 0; wpar ^= 1; }
+            }
+            if (ws) {
+                if constexpr (CO == 32) {
+                    ds_flush_stats<16>(acc_s, acc_q, s_sums, lane);
+                    ds_flush_stats<16>(acc_s + 16, acc_q + 16, s_sums + 32, lane);
+                } else if constexpr (kAcc) {
+                    ds_flush_stats<CO>(acc_s, acc_q, s_sums, lane);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = threadIdx.x; i < 2 * CO; i += 128) {
+                    atomicAdd(p.sums + ((size_t)n * CO + (i >> 1)) * 2 + (i & 1), s_sums[i]);
+                    s_sums[i] = 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == F1_W_MMA) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// Weight (and bias) gradient of the first convolution: dW[co][tap] += sum_v dz[v][co] * x_hat[v + tap].
+// A (MN-major) = the im2col image above, M = taps (32 rows used of 128: the rows beyond read whatever follows in shared
+// memory and are ignored), B (MN-major) = the dz slab, N = Cout, K = the slab's 128 voxels (8 MMAs); one accumulator
+// resident in TMEM for the CTA's whole life, one atomic epilogue.
+template <int CO>
+__global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_wgrad_kernel(const ConvFirstParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int ZSTAGE = (CO / 8) * 128 * 16;                       // [jo][128 voxels][8 bf16]
+    uint8_t* smA = smem;                                              // [F1_NS][F1_ASTAGE]
+    uint8_t* smZ = smA + F1_NS * F1_ASTAGE;                           // [F1_NS][ZSTAGE]  (>= 24 KB: absorbs the M = 128 over-read)
+    __nv_bfloat16* s_scr = reinterpret_cast<__nv_bfloat16*>(smZ + F1_NS * ZSTAGE);
+    float* s_db = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_scr) + ((F1_NLW * F1_SCR * 2 + 15) & ~15));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_db + CO);
+    uint64_t* full = bars;                            // [F1_NS]
+    uint64_t* empty = full + F1_NS;                   // [F1_NS]
+    uint64_t* acc_full = empty + F1_NS;               // [1]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int DR = p.DR;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < F1_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == F1_W_MMA) tmem_alloc(s_tmem, 512);
+    for (int i = threadIdx.x; i < CO; i += F1_THREADS) s_db[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp >= 4 && warp < F1_W_MMA) {
+        const int w8 = warp - 4;
+        __nv_bfloat16* scr = s_scr + w8 * F1_SCR;
+        constexpr int JO = CO / 8;
+        float dbacc[JO][8];                            // this lane's voxels (m = lane + 32 q), all channels: reduced at the end
+#pragma unroll
+        for (int j = 0; j < JO; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dbacc[j][e] = 0.f;
+        uint32_t slot = 0, phase = 1;
+        int owner = 0;
+        for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+            int n, d0, h0, w0;
+            f1_coords(p, item, n, d0, h0, w0);
+            const float sc = p.in_ss ? p.in_ss[n * 2] : 1.f, sh = p.in_ss ? p.in_ss[n * 2 + 1] : 0.f;
+            for (int od = 0; od < DR; ++od) {
+                const uint32_t my_slot = slot, my_phase = phase;
+                const bool mine = owner == w8;
+                if (++slot == F1_NS) { slot = 0; phase ^= 1; }
+                if (++owner == F1_NLW) owner = 0;
+                if (!mine) continue;
+                mbar_wait(&empty[my_slot], my_phase);
+                const int gd = d0 + od;
+                uint8_t* zdst = smZ + my_slot * ZSTAGE;
+                const uint32_t z32 = smem_u32(zdst);
+                // dz slab: plain copies (zero outside the volume), issued first so they fly while the im2col image is built
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int m = lane + 32 * q;
+                    const int gh = h0 + m / DS_TW, gw = w0 + m % DS_TW;
+                    const bool in = gd < p.D && gh < p.H && gw < p.W;
+                    const __nv_bfloat16* src = in ? p.dz + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dz_ld : p.dz;
+#pragma unroll
+                    for (int j = 0; j < JO; ++j)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(z32 + (uint32_t)(j * 128 * 16 + m * 16)), "l"(src + 8 * j),
+                                     "r"(in ? 16 : 0)
+                                     : "memory");
+                }
+                f1_build_slab(p, n, gd < p.D ? gd : p.D + 1, h0, w0, sc, sh, scr, smA + my_slot * F1_ASTAGE, lane);
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                if (p.db) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int m = lane + 32 * q;
+#pragma unroll
+                        for (int j = 0; j < JO; ++j) {
+                            const uint4 val = *reinterpret_cast<const uint4*>(zdst + j * 128 * 16 + m * 16);
+                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __bfloat1622float2(h2[e]);
+                                dbacc[j][2 * e] += f.x;
+                                dbacc[j][2 * e + 1] += f.y;
+                            }
+                        }
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[my_slot]);
+            }
+        }
+        if (p.db) {
+#pragma unroll
+            for (int j = 0; j < JO; ++j)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float a = dbacc[j][e];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    if (lane == 0) atomicAdd(&s_db[j * 8 + e], a);
+                }
+            asm volatile("bar.sync 2, %0;" ::"n"(F1_NLW * 32) : "memory");
+            const int t = threadIdx.x - 128;
+            if (t < CO) atomicAdd(p.db + t, s_db[t]);
+        }
+    } else if (warp == F1_W_MMA) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, CO, 1, 1);
+            // MN-major: LBO = next 8 voxels (128 B), SBO = next 8 taps / channels (one 2 KB plane)
+            const uint64_t ad = make_desc(0, 128, 128 * 16), bd = make_desc(0, 128, 128 * 16);
+            const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
+            const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
+            const uint32_t b_lo_base = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smZ) >> 4);
+            uint32_t slot = 0, fph = 0;
+            bool first = true;
+            for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+                for (int od = 0; od < DR; ++od) {
+                    mbar_wait(&full[slot], fph);
+                    tc_fence_after();
+                    const uint32_t a0 = a_lo_base + slot * (F1_ASTAGE / 16), b0 = b_lo_base + slot * (ZSTAGE / 16);
+                    if (first) umma_bf16_c<false>(tmem_base, a0, a_hi, b0, b_hi, idesc);
+                    else umma_bf16_c<true>(tmem_base, a0, a_hi, b0, b_hi, idesc);
+                    first = false;
+#pragma unroll
+                    for (int ks = 1; ks < 8; ++ks) umma_bf16_c<true>(tmem_base, a0 + ks * 16, a_hi, b0 + ks * 16, b_hi, idesc);
+                    umma_commit(&empty[slot]);
+                    if (++slot == F1_NS) { slot = 0; fph ^= 1; }
+                }
+            }
+            umma_commit(acc_full);
+        }
+    } else if (warp == 0) {
+        // epilogue: accumulator rows 0..26 = taps (TMEM lanes of warp 0), columns = output channels
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        for (int cb = 0; cb < CO; cb += 16) {
+            uint32_t raw[16];
+            tmem_ld16(tmem_base + (uint32_t)cb, raw);
+            tmem_ld_wait();
+            if (lane < 27) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) atomicAdd(p.dw + (size_t)(cb + i) * 27 + lane, __uint_as_float(raw[i]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == F1_W_MMA) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static bool first_shape(int Cin, int Cout, int kd, int kh, int kw) {
+    return Cin == 1 && kd == 3 && kh == 3 && kw == 3 && (Cout == 16 || Cout == 32 || Cout == 48 || Cout == 64);
+}
+
 struct DsShape {
     int CC, NS, wbytes, smem_bytes, xdepth;
 };
@@ -704,6 +1100,67 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
             return 2;
     }
 #undef B2_DS_LAUNCH
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_conv3d_first_supported(int Cin, int Cout, int kd, int kh, int kw) { return first_shape(Cin, Cout, kd, kh, kw) ? 1 : 0; }
+
+static int first_setup(ConvFirstParams& p, int N, int D, int H, int W, int Cout, int splits) {
+    p.N = N; p.D = D; p.H = H; p.W = W; p.Cout = Cout;
+    const char* e = getenv("B200EM_DS_DR");
+    p.DR = e ? atoi(e) : ds_pick_dr(N, D, H, W, splits);
+    if (p.DR < 1) p.DR = 1;
+    p.tiles_w = (W + DS_TW - 1) / DS_TW; p.tiles_h = (H + DS_TH - 1) / DS_TH; p.tiles_d = (D + p.DR - 1) / p.DR;
+    p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    return 0;
+}
+
+int b200em_conv3d_first(const void* x, const float* in_scale_shift, const float* w, const float* bias, void* y, int64_t y_ld,
+                        float* sums, int N, int D, int H, int W, int Cout, int relu, void* stream) {
+    B2_CHECK_ARG(x && w && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_first: bad arguments");
+    B2_CHECK_ARG(first_shape(1, Cout, 3, 3, 3), "conv3d_first: Cout %d not supported", Cout);
+    B2_CHECK_ARG(y_ld % 8 == 0 && aligned16(y) && y_ld >= Cout, "conv3d_first: output must be 16-byte aligned with pitch % 8 == 0");
+    ConvFirstParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = (const __nv_bfloat16*)x; p.in_ss = in_scale_shift; p.w = w; p.bias = bias; p.y = (__nv_bfloat16*)y; p.y_ld = y_ld;
+    p.sums = sums; p.relu = relu;
+    first_setup(p, N, D, H, W, Cout, sm_count());
+    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
+    const long long gx = p.items < sm_count() ? p.items : sm_count();
+    const int smem_bytes = F1_NS * F1_ASTAGE + 4 * Cout * 16 + ((F1_NLW * F1_SCR * 2 + 15) & ~15) + Cout * 12 + (2 * F1_NS + 2 * DS_MAX_NA) * 8 + 16 + 128;
+#define B2_F1(CO_)                                                                                                     \
+    case CO_:                                                                                                          \
+        B2_CUDA(cudaFuncSetAttribute(conv3d_first_kernel<CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
+        conv3d_first_kernel<CO_><<<(unsigned)gx, F1_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);                     \
+        break;
+    switch (Cout) { B2_F1(16) B2_F1(32) B2_F1(48) B2_F1(64) default: set_error("conv3d_first: Cout %d not instantiated", Cout); return 2; }
+#undef B2_F1
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_conv3d_first_wgrad(const void* x, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw, float* db, int N,
+                              int D, int H, int W, int Cout, void* stream) {
+    B2_CHECK_ARG(x && dz && dw && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_first_wgrad: bad arguments");
+    B2_CHECK_ARG(first_shape(1, Cout, 3, 3, 3), "conv3d_first_wgrad: Cout %d not supported", Cout);
+    B2_CHECK_ARG(dz_ld % 8 == 0 && aligned16(dz) && dz_ld >= Cout, "conv3d_first_wgrad: dz must be 16-byte aligned with pitch % 8 == 0");
+    ConvFirstParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = (const __nv_bfloat16*)x; p.in_ss = in_scale_shift; p.dz = (const __nv_bfloat16*)dz; p.dz_ld = dz_ld; p.dw = dw; p.db = db;
+    first_setup(p, N, D, H, W, Cout, sm_count());
+    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
+    const long long gx = p.items < sm_count() ? p.items : sm_count();
+    const int zstage = (Cout / 8) * 128 * 16;
+    const int smem_bytes = F1_NS * F1_ASTAGE + F1_NS * zstage + ((F1_NLW * F1_SCR * 2 + 15) & ~15) + Cout * 4 + (2 * F1_NS + 1) * 8 + 16 + 128;
+    B2_CHECK_ARG(F1_NS * zstage >= 24 * 1024 && smem_bytes <= DS_MAX_SMEM, "conv3d_first_wgrad: shared memory layout");
+#define B2_F1W(CO_)                                                                                                          \
+    case CO_:                                                                                                                \
+        B2_CUDA(cudaFuncSetAttribute(conv3d_first_wgrad_kernel<CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
+        conv3d_first_wgrad_kernel<CO_><<<(unsigned)gx, F1_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);                     \
+        break;
+    switch (Cout) { B2_F1W(16) B2_F1W(32) B2_F1W(48) B2_F1W(64) default: set_error("conv3d_first_wgrad: Cout %d not instantiated", Cout); return 2; }
+#undef B2_F1W
     B2_LAUNCH_CHECK();
     return 0;
 }
