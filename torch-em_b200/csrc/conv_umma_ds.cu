@@ -30,9 +30,6 @@ namespace {
 constexpr int DS_TH = 16, DS_TW = 8;
 constexpr int DS_HP = DS_TH + 2, DS_WP = DS_TW + 2;
 constexpr int DS_PLANE = DS_HP * DS_WP * 16 + 16;   // +16 B staggers the planes across banks
-constexpr int DS_NLW = 8;                           // operand-loader warps
-constexpr int DS_THREADS = 128 + DS_NLW * 32 + 64;
-constexpr int DS_W_WLOAD = 4 + DS_NLW, DS_W_MMA = DS_W_WLOAD + 1;
 constexpr int DS_MAX_SMEM = 227 * 1024;
 constexpr int DS_MAX_NS = 12;                       // A ring depth cap
 constexpr int DS_MAX_NA = 16;                       // accumulator ring blocks cap
@@ -168,9 +165,22 @@ __device__ __forceinline__ void ds_flush_stats(float* acc_s, float* acc_q, float
 
 // CO = Cout (16..80, multiple of 16), KC_ = K=16 steps per channel chunk (1 or 2): compile-time so that the epilogue's
 // channel blocks are static and the single-thread MMA issue loop has immediate operand offsets.
+// Warp roles: CO == 64 splits the epilogue over two groups of four warps (columns [0,32) and [32,64), each with per-thread
+// statistics accumulators like the CO = 32 epilogue) and runs six loader warps; every other CO has four epilogue warps and
+// eight loader warps.  16 resp. 14 warps, so 128 registers per thread either way.
+template <int CO> struct DsRoles {
+    static constexpr int NEPI = CO == 64 ? 8 : 4;          // epilogue warps
+    static constexpr int NLW = CO == 64 ? 6 : 8;           // loader warps
+    static constexpr int W_WLOAD = NEPI + NLW, W_MMA = W_WLOAD + 1;
+    static constexpr int THREADS = (W_MMA + 1) * 32;
+    static constexpr int CPT = CO == 64 ? 32 : CO;         // output columns per epilogue thread
+};
+
 template <int CO, int KC_>
-__global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const ConvDsParams p) {
+__global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel(const ConvDsParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    using RL = DsRoles<CO>;
+    constexpr int DS_THREADS = RL::THREADS, DS_W_WLOAD = RL::W_WLOAD, DS_W_MMA = RL::W_MMA;
     constexpr int N3 = 3 * CO;
     constexpr int J = KC_ * 2;                                  // 8-channel planes per stage
     constexpr int A_STAGE = J * DS_PLANE;
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const Con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < NA; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], RL::NEPI); }
         mbar_init(b_full, 1);
         fence_mbar_init();
     }
@@ -215,13 +225,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const Con
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp >= 4 && warp < DS_W_WLOAD) {
+    if (warp >= RL::NEPI && warp < DS_W_WLOAD) {
         // ===================== operand loaders: warp w8 owns the stages q = w8 (mod nlw) =====================
         // nlw <= NS: the ring's parity waits are only valid while a waiter is at most one phase ahead of its barrier, which
         // holds when a warp's next stage (q + nlw) reuses a slot whose previous use (q + nlw - NS) precedes q.
         // Per work item each lane precomputes the in-slice element offset of its units once (only the slice changes from
         // stage to stage); the norm apply is a short in-place shared-memory pass.
-        const int w8 = warp - 4;
+        const int w8 = warp - RL::NEPI;
         constexpr int UNITS = DS_HP * DS_WP * J;       // 16-byte units per stage
         constexpr int NU = (UNITS + 31) / 32;          // per lane
         constexpr int VSTEP = 32 / J;                  // voxels per 32 units
@@ -444,19 +454,22 @@ __global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const Con
                 printf("[ds prof] mma: total %lld cyc, %lld stages: wait a_full %lld, wait acc_empty %lld\n", clock64() - pf_t0, pf_n, pf_wa, pf_wacc);
         }
     } else {
-        // ===================== epilogue (warps 0-3) =====================
-        const int row = warp * 32 + lane;            // GEMM row = TMEM lane
+        // ===================== epilogue (warps 0..NEPI-1; warp % 4 = TMEM lane quadrant, warp / 4 = column group) ============
+        const int wq = warp & 3, grp = warp >> 2;
+        const int row = wq * 32 + lane;              // GEMM row = TMEM lane
         const int hl = row / DS_TW, wl = row % DS_TW;
-        constexpr bool kAcc = CO <= 32;
-        constexpr int NAcc = kAcc ? CO : 1;
+        constexpr int CPT = RL::CPT;
+        const int col0 = grp * CPT;                  // first output column of this thread
+        constexpr bool kAcc = CPT <= 32;
+        constexpr int NAcc = kAcc ? CPT : 1;
         float acc_s[NAcc], acc_q[NAcc];
 #pragma unroll
         for (int i = 0; i < NAcc; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
         const bool ws = p.sums != nullptr;
         const bool has_x = p.dot_x != nullptr;
-        constexpr int XV = CO / 8;                   // 16-byte vectors of dot_x per row
+        constexpr int XV = CPT / 8;                  // 16-byte vectors of dot_x per thread
         const int XD = p.xdepth;
-        const uint32_t xs_row = smem_u32(s_xring) + (uint32_t)row * (CO * 2);
+        const uint32_t xs_row = smem_u32(s_xring) + (uint32_t)row * (CO * 2) + (uint32_t)col0 * 2;
         int r = 0;                                   // (oc % NA, (oc / NA) & 1) of the next output slice
         uint32_t wpar = 0;
         const bool prof = (p.debug & 8) != 0;
@@ -476,7 +489,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const Con
             auto issue_x = [&](int od_) {
                 if (has_x) {
                     const bool ok = valid_hw && od_ < DR && d0 + od_ < p.D;
-                    const __nv_bfloat16* q_ = ok ? p.dot_x + (vox0 + (size_t)od_ * hw) * p.dot_ld : p.dot_x;
+                    const __nv_bfloat16* q_ = ok ? p.dot_x + (vox0 + (size_t)od_ * hw) * p.dot_ld + col0 : p.dot_x;
                     const uint32_t dst = xs_row + (uint32_t)(od_ % XD) * (128u * CO * 2u);
 #pragma unroll
                     for (int i = 0; i < XV; ++i)
@@ -500,33 +513,35 @@ __global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const Con
                     if (XD == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
                     else if (XD == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
                     else asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    const uint8_t* src = s_xring + (size_t)(od % XD) * (128 * CO * 2) + (size_t)row * (CO * 2);
+                    const uint8_t* src = s_xring + (size_t)(od % XD) * (128 * CO * 2) + (size_t)row * (CO * 2) + col0 * 2;
 #pragma unroll
                     for (int i = 0; i < XV; ++i) xcur[i] = *reinterpret_cast<const uint4*>(src + 16 * ((i + row) % XV));
                 }
                 const int gd = d0 + od;
                 const bool valid = valid_hw && gd < p.D;
-                __nv_bfloat16* yp = p.y + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(blk * CO);
+                __nv_bfloat16* yp = p.y + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld + col0;
+                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(blk * CO + col0);
+                const float* s_biasg = s_bias + col0;
+                float* s_sumsg = s_sums + 2 * col0;
                 if (p.debug & 2) {
-                } else if constexpr (CO == 16) {
-                    ds_epilogue_block<16, true>(taddr, s_bias, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sums, ws, lane);
-                } else if constexpr (CO == 32) {
+                } else if constexpr (CPT == 16) {
+                    ds_epilogue_block<16, true>(taddr, s_biasg, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sumsg, ws, lane);
+                } else if constexpr (CPT == 32) {
                     // two 16-column passes: half the live registers of one 32-column pass (the 64 statistics accumulators stay)
-                    ds_epilogue_block<16, true>(taddr, s_bias, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sums, ws, lane);
-                    ds_epilogue_block<16, true>(taddr + 16, s_bias + 16, p.relu, valid, yp + 16, xcur + 2, has_x, acc_s + 16, acc_q + 16,
-                                                s_sums, ws, lane);
+                    ds_epilogue_block<16, true>(taddr, s_biasg, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sumsg, ws, lane);
+                    ds_epilogue_block<16, true>(taddr + 16, s_biasg + 16, p.relu, valid, yp + 16, xcur + 2, has_x, acc_s + 16, acc_q + 16,
+                                                s_sumsg, ws, lane);
                 } else {
                     ds_epilogue_block<32, false>(taddr, s_bias, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sums, ws, lane);
-                    if constexpr (CO >= 64)
-                        ds_epilogue_block<32, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
-                                                     s_sums + 64, ws, lane);
                     if constexpr (CO == 48)
                         ds_epilogue_block<16, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
                                                      s_sums + 64, ws, lane);
-                    if constexpr (CO == 80)
+                    if constexpr (CO == 80) {
+                        ds_epilogue_block<32, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
+                                                     s_sums + 64, ws, lane);
                         ds_epilogue_block<16, false>(taddr + 64, s_bias + 64, p.relu, valid, yp + 64, xcur + 8, has_x, acc_s, acc_q,
                                                      s_sums + 128, ws, lane);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -536,18 +551,20 @@ __global__ void __launch_bounds__(DS_THREADS, 1) conv3d_umma_ds_kernel(const Con
             if (has_x) asm volatile("cp.async.wait_all;" ::: "memory");
             if (ws) {
                 // flush this item's per-channel partial sums (the sample n may change with the next item)
-                if constexpr (CO == 32) {
-                    ds_flush_stats<16>(acc_s, acc_q, s_sums, lane);
-                    ds_flush_stats<16>(acc_s + 16, acc_q + 16, s_sums + 32, lane);
+                if constexpr (CPT == 32) {
+                    ds_flush_stats<16>(acc_s, acc_q, s_sums + 2 * col0, lane);
+                    ds_flush_stats<16>(acc_s + 16, acc_q + 16, s_sums + 2 * col0 + 32, lane);
                 } else if constexpr (kAcc) {
-                    ds_flush_stats<CO>(acc_s, acc_q, s_sums, lane);
+                    ds_flush_stats<CPT>(acc_s, acc_q, s_sums + 2 * col0, lane);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = threadIdx.x; i < 2 * CO; i += 128) {
-                    atomicAdd(p.sums + ((size_t)n * CO + (i >> 1)) * 2 + (i & 1), s_sums[i]);
-                    s_sums[i] = 0.f;
+                // each column group flushes its own channels behind its own named barrier (ids 1 and 3)
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+                for (int i = (int)(threadIdx.x & 127); i < 2 * CPT; i += 128) {
+                    const int ii = 2 * col0 + i;
+                    atomicAdd(p.sums + ((size_t)n * CO + (ii >> 1)) * 2 + (ii & 1), s_sums[ii]);
+                    s_sums[ii] = 0.f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
             }
         }
         if (prof && blockIdx.x == 0 && threadIdx.x == 0)
@@ -751,6 +768,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
         const int hl = row / DS_TW, wl = row % DS_TW;
         constexpr bool kAcc = CO <= 32;
         constexpr int NAcc = kAcc ? CO : 1;
+        constexpr int CPT = CO;                       // one column group: every epilogue thread owns all CO columns
+        const int col0 = 0, grp = 0;
         float acc_s[NAcc], acc_q[NAcc];
 #pragma unroll
         for (int i = 0; i < NAcc; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
@@ -792,18 +811,20 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
                 if (++r == NA) { r = 0; wpar ^= 1; }
             }
             if (ws) {
-                if constexpr (CO == 32) {
-                    ds_flush_stats<16>(acc_s, acc_q, s_sums, lane);
-                    ds_flush_stats<16>(acc_s + 16, acc_q + 16, s_sums + 32, lane);
+                if constexpr (CPT == 32) {
+                    ds_flush_stats<16>(acc_s, acc_q, s_sums + 2 * col0, lane);
+                    ds_flush_stats<16>(acc_s + 16, acc_q + 16, s_sums + 2 * col0 + 32, lane);
                 } else if constexpr (kAcc) {
-                    ds_flush_stats<CO>(acc_s, acc_q, s_sums, lane);
+                    ds_flush_stats<CPT>(acc_s, acc_q, s_sums + 2 * col0, lane);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = threadIdx.x; i < 2 * CO; i += 128) {
-                    atomicAdd(p.sums + ((size_t)n * CO + (i >> 1)) * 2 + (i & 1), s_sums[i]);
-                    s_sums[i] = 0.f;
+                // each column group flushes its own channels behind its own named barrier (ids 1 and 3)
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+                for (int i = (int)(threadIdx.x & 127); i < 2 * CPT; i += 128) {
+                    const int ii = 2 * col0 + i;
+                    atomicAdd(p.sums + ((size_t)n * CO + (ii >> 1)) * 2 + (ii & 1), s_sums[ii]);
+                    s_sums[ii] = 0.f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
             }
         }
     }
@@ -1068,7 +1089,7 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
     p.y = (__nv_bfloat16*)y; p.y_ld = y_ld; p.sums = sums; p.dot_x = (const __nv_bfloat16*)dot_x; p.dot_ld = dot_ld;
     p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.relu = relu;
     p.CC = s.CC; p.nchunks = Cin / s.CC; p.NS = s.NS; p.wbytes = s.wbytes; p.xdepth = s.xdepth;
-    p.nlw = s.NS < DS_NLW ? s.NS : DS_NLW;
+    { const int nlw_max = Cout == 64 ? 6 : 8; p.nlw = s.NS < nlw_max ? s.NS : nlw_max; }
     { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
     {
         const char* e = getenv("B200EM_DS_DR");
@@ -1083,10 +1104,10 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
     case CO_:                                                                                                                      \
         if (s.CC == 32) {                                                                                                          \
             B2_CUDA(cudaFuncSetAttribute(conv3d_umma_ds_kernel<CO_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
-            conv3d_umma_ds_kernel<CO_, 2><<<(unsigned)gx, DS_THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                     \
+            conv3d_umma_ds_kernel<CO_, 2><<<(unsigned)gx, DsRoles<CO_>::THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                    \
         } else {                                                                                                                   \
             B2_CUDA(cudaFuncSetAttribute(conv3d_umma_ds_kernel<CO_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
-            conv3d_umma_ds_kernel<CO_, 1><<<(unsigned)gx, DS_THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                     \
+            conv3d_umma_ds_kernel<CO_, 1><<<(unsigned)gx, DsRoles<CO_>::THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                    \
         }                                                                                                                          \
         break;
     switch (Cout) {
