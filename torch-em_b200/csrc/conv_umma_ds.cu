@@ -165,15 +165,16 @@ __device__ __forceinline__ void ds_flush_stats(float* acc_s, float* acc_q, float
 
 // CO = Cout (16..80, multiple of 16), KC_ = K=16 steps per channel chunk (1 or 2): compile-time so that the epilogue's
 // channel blocks are static and the single-thread MMA issue loop has immediate operand offsets.
-// Warp roles: CO == 64 splits the epilogue over two groups of four warps (columns [0,32) and [32,64), each with per-thread
+// Warp roles: CO == 64 / 32 splits the epilogue over two groups of four warps (columns [0,32) and [32,64), each with per-thread
 // statistics accumulators like the CO = 32 epilogue) and runs six loader warps; every other CO has four epilogue warps and
 // eight loader warps.  16 resp. 14 warps, so 128 registers per thread either way.
 template <int CO> struct DsRoles {
-    static constexpr int NEPI = CO == 64 ? 8 : 4;          // epilogue warps
-    static constexpr int NLW = CO == 64 ? 6 : 8;           // loader warps
+    static constexpr bool SPLIT = CO == 64 || CO == 32;    // two epilogue column groups
+    static constexpr int NEPI = SPLIT ? 8 : 4;             // epilogue warps
+    static constexpr int NLW = SPLIT ? 6 : 8;              // loader warps
     static constexpr int W_WLOAD = NEPI + NLW, W_MMA = W_WLOAD + 1;
     static constexpr int THREADS = (W_MMA + 1) * 32;
-    static constexpr int CPT = CO == 64 ? 32 : CO;         // output columns per epilogue thread
+    static constexpr int CPT = SPLIT ? CO / 2 : CO;        // output columns per epilogue thread
 };
 
 template <int CO, int KC_>
@@ -1089,7 +1090,7 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
     p.y = (__nv_bfloat16*)y; p.y_ld = y_ld; p.sums = sums; p.dot_x = (const __nv_bfloat16*)dot_x; p.dot_ld = dot_ld;
     p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.relu = relu;
     p.CC = s.CC; p.nchunks = Cin / s.CC; p.NS = s.NS; p.wbytes = s.wbytes; p.xdepth = s.xdepth;
-    { const int nlw_max = Cout == 64 ? 6 : 8; p.nlw = s.NS < nlw_max ? s.NS : nlw_max; }
+    { const int nlw_max = (Cout == 64 || Cout == 32) ? 6 : 8; p.nlw = s.NS < nlw_max ? s.NS : nlw_max; }
     { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
     {
         const char* e = getenv("B200EM_DS_DR");
