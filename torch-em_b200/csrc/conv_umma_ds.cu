@@ -191,10 +191,10 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
     float* s_bias = reinterpret_cast<float*>(smB + p.wbytes);
     float* s_sums = s_bias + CO;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_sums + 2 * CO);
-    uint64_t* a_full = bars;                          // [NS]  one loader-warp arrival
+    uint64_t* a_full = bars;                          // [NS]  plain flags: fill number of the slot (flag_store / flag_wait_eq)
     uint64_t* a_empty = a_full + DS_MAX_NS;           // [NS]  tcgen05.commit
     uint64_t* acc_full = a_empty + DS_MAX_NS;         // [NA]  tcgen05.commit
-    uint64_t* acc_empty = acc_full + DS_MAX_NA;       // [NA]  4 epilogue-warp arrivals
+    uint64_t* acc_empty = acc_full + DS_MAX_NA;       // [NA] plain counters: epilogue-warp completions per ring block (counter_add / counter_wait_ge)
     uint64_t* b_full = acc_empty + DS_MAX_NA;         // [1]   expect_tx (resident filter)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(b_full + 1);
     uint32_t* s_tap = s_tmem + 2;                     // [9] operand start offset of each (b, c) tap, 16-byte units
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
     const int DR = p.DR, NS = p.NS;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < NA; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], RL::NEPI); }
+        for (int i = 0; i < NS; ++i) { flag_init(&a_full[i]); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&acc_full[i], 1); flag_init(&acc_empty[i]); }
         mbar_init(b_full, 1);
         fence_mbar_init();
     }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
         const int vl = lane / J;
         float sc[8], sh[8];
         int cur_n = -1, cur_c = -1;
-        uint32_t slot = 0, phase = 1;                  // ring position of the current stage (phase = parity to wait for on a_empty)
+        uint32_t slot = 0, phase = 1, lap = 1;         // ring position of the current stage (phase = parity to wait for on a_empty, lap = fill number)
         int owner = 0;                                 // loader warp that owns the current stage (round robin over p.nlw warps)
         const size_t slice_elems = (size_t)p.H * p.W * p.x_ld;
         const bool prof = (p.debug & 8) != 0;
@@ -262,9 +262,9 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                 const bool in_d = gd >= 0 && gd < p.D;
                 const __nv_bfloat16* xs = p.x + ((size_t)n * p.D + (in_d ? gd : 0)) * slice_elems + j * 8;
                 for (int c = 0; c < p.nchunks; ++c) {
-                    const uint32_t my_slot = slot, my_phase = phase;
+                    const uint32_t my_slot = slot, my_phase = phase, my_lap = lap;
                     const bool mine = owner == w8;
-                    if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1; }
+                    if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1; ++lap; }
                     if (++owner == p.nlw) owner = 0;
                     if (!mine) continue;
                     long long pf_a = 0, pf_b = 0, pf_c = 0;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_full[my_slot]);
+                    if (lane == 0) flag_store(&a_full[my_slot], my_lap);
                     if (prof) { pf_wait += pf_b - pf_a; pf_load += pf_c - pf_b; pf_norm += clock64() - pf_c; ++pf_n; }
                 }
             }
@@ -340,24 +340,21 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
             const uint32_t b_lo_base = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smB) >> 4);
             constexpr uint32_t K16 = 2 * (DS_PLANE / 16), BK16 = 2 * N3, BTAP16 = J * N3, ASTAGE16 = A_STAGE / 16;
             auto idesc_of = [&](int nb) { return nb == 1 ? idesc1 : (nb == 2 ? idesc2 : idesc3); };
-            uint32_t tapo[9];                            // (b, c) tap start offsets in registers: the issue loop is fully unrolled
-#pragma unroll
-            for (int t = 0; t < 9; ++t) tapo[t] = t < ntap ? s_tap[t] : 0u;
+            auto TAPO = [](int t) { return (uint32_t)((t / 3) * DS_WP + (t % 3)); };   // (b, c) tap start offset, 16-byte units (3 x 3 taps)
             const int DRq = DR / NA, DRr = DR % NA;
             mbar_wait(b_full, 0);
             tc_fence_after();
-            // Ring bookkeeping is incremental (no divisions in the issue loop): (slot, fph) = A stage and its a_full parity;
+            // Ring bookkeeping is incremental (no divisions in the issue loop): (slot, lap) = A stage and its fill number;
             // (r0, w0) = (oc % NA, (oc / NA) & 1) of the item's first output slice; the block of output counter oc is NA-1 - oc % NA.
-            uint32_t slot = 0, fph = 0;
+            uint32_t slot = 0, lap = 1;
             int r0 = 0;
             uint32_t w0 = 0;
-            bool a_ok = false, acc_ok = false;           // results of the early probes of the next a_full / acc_empty barriers
+            uint32_t started = 0;                        // output slices this CTA has started accumulating
             const bool prof = (p.debug & 8) != 0;
             long long pf_wa = 0, pf_wacc = 0, pf_t0 = clock64(), pf_n = 0;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
                 int r = r0;                              // ring position of output od = s (the newest output slice s feeds)
                 uint32_t wpar = w0;
-                acc_ok = false;
                 for (int s = 0; s < DR + 2; ++s) {
                     const int a_lo = s - (DR - 1) > 0 ? s - (DR - 1) : 0;
                     const int nblk = (s < 2 ? s : 2) - a_lo + 1;
@@ -367,16 +364,11 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                     if (a_lo == 0) {                     // a new accumulator (output od = s) starts with this slice
                         long long t_ = 0;
                         if (prof) t_ = clock64();
-                        if (!acc_ok) mbar_wait(&acc_empty[k0], wpar ^ 1);
+                        // its ring block is free once every epilogue warp is done with the block's previous use
+                        if (started >= (uint32_t)NA) counter_wait_ge(&acc_empty[k0], (uint32_t)RL::NEPI * (started / (uint32_t)NA));
+                        ++started;
                         if (prof) pf_wacc += clock64() - t_;
                         tc_fence_after();
-                    }
-                    // probe the NEXT slice's new accumulator now; the answer is consumed after this slice's MMAs were issued
-                    acc_ok = false;
-                    if (s + 1 <= DR - 1) {
-                        const int rn = r + 1 == NA ? 0 : r + 1;
-                        const uint32_t wn = r + 1 == NA ? wpar ^ 1u : wpar;
-                        acc_ok = mbar_test_wait(&acc_empty[NA - 1 - rn], wn ^ 1u);
                     }
                     // segments of consecutive ring blocks: [k0, k0+n1) and, past the wrap, [0, n2)
                     const int n1 = nblk < NA - k0 ? nblk : NA - k0;
@@ -388,19 +380,14 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                     for (int c = 0; c < p.nchunks; ++c, bch += (uint32_t)ntap * BTAP16) {
                         long long t_ = 0;
                         if (prof) t_ = clock64();
-                        if (!a_ok) mbar_wait(&a_full[slot], fph);
+                        flag_wait_eq(&a_full[slot], lap);
                         if (prof) { pf_wa += clock64() - t_; ++pf_n; }
                         tc_fence_after();
                         const uint32_t abuf = a_lo_base + slot * ASTAGE16;
-                        {   // probe the next stage's barrier before this stage's MMAs are issued
-                            const uint32_t ns_ = slot + 1 == (uint32_t)NS ? 0u : slot + 1;
-                            const uint32_t np_ = slot + 1 == (uint32_t)NS ? fph ^ 1u : fph;
-                            a_ok = mbar_test_wait(&a_full[ns_], np_);
-                        }
                         if (!(p.debug & 4)) {
-                            const bool fresh = c == 0 && a_lo == 0;       // block k0 (a = 0) is overwritten by its very first MMA
-                            if (fresh) {
-                                const uint32_t a0 = abuf + tapo[0];
+                            // (t = 0, k = 0) first: it overwrites block k0 when this slice starts a new accumulator
+                            const uint32_t a0 = abuf + TAPO(0);
+                            if (c == 0 && a_lo == 0) {
                                 umma_bf16_c<false>(col1, a0, a_hi, bch, b_hi, idesc1);
                                 if (nblk > 1) {
                                     // the other blocks a = 1..  accumulate; they start at ring block k0+1 (may wrap)
@@ -411,35 +398,32 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                                     if (rr - r1 > 0)
                                         umma_bf16_c<true>(tmem_base, a0, a_hi, bch + CO + (uint32_t)(r1 * CO), b_hi, idesc_of(rr - r1));
                                 }
-                                if (KC_ == 2) {
-                                    umma_bf16_c<true>(col1, a0 + K16, a_hi, bch + BK16, b_hi, id1);
-                                    if (n2 > 0) umma_bf16_c<true>(col2, a0 + K16, a_hi, bch + BK16 + boff2, b_hi, id2);
-                                }
+                            } else {
+                                umma_bf16_c<true>(col1, a0, a_hi, bch, b_hi, id1);
+                                if (n2 > 0) umma_bf16_c<true>(col2, a0, a_hi, bch + boff2, b_hi, id2);
                             }
+                            // the rest of the stage is branch-free straight-line code with immediate operand offsets: the descriptor
+                            // halves, instruction descriptors and TMEM columns then stay in uniform registers across the burst
+                            // (every branch inside the burst costs a re-materialisation of ~8 R2UR per tap, ~40 cycles per MMA)
                             if (n2 == 0) {
 #pragma unroll
-                                for (int t = 0; t < 9; ++t) {
-                                    if (t < ntap && !(t == 0 && fresh)) {
-                                        umma_bf16_c<true>(col1, abuf + tapo[t], a_hi, bch + t * BTAP16, b_hi, id1);
-                                        if (KC_ == 2) umma_bf16_c<true>(col1, abuf + tapo[t] + K16, a_hi, bch + t * BTAP16 + BK16, b_hi, id1);
-                                    }
-                                }
+                                for (int t = 0; t < 9; ++t)
+#pragma unroll
+                                    for (int k = 0; k < KC_; ++k)
+                                        if (t + k > 0) umma_bf16_c<true>(col1, abuf + TAPO(t) + k * K16, a_hi, bch + t * BTAP16 + k * BK16, b_hi, id1);
                             } else {
 #pragma unroll
-                                for (int t = 0; t < 9; ++t) {
-                                    if (t < ntap && !(t == 0 && fresh)) {
-                                        umma_bf16_c<true>(col1, abuf + tapo[t], a_hi, bch + t * BTAP16, b_hi, id1);
-                                        umma_bf16_c<true>(col2, abuf + tapo[t], a_hi, bch + t * BTAP16 + boff2, b_hi, id2);
-                                        if (KC_ == 2) {
-                                            umma_bf16_c<true>(col1, abuf + tapo[t] + K16, a_hi, bch + t * BTAP16 + BK16, b_hi, id1);
-                                            umma_bf16_c<true>(col2, abuf + tapo[t] + K16, a_hi, bch + t * BTAP16 + BK16 + boff2, b_hi, id2);
+                                for (int t = 0; t < 9; ++t)
+#pragma unroll
+                                    for (int k = 0; k < KC_; ++k)
+                                        if (t + k > 0) {
+                                            umma_bf16_c<true>(col1, abuf + TAPO(t) + k * K16, a_hi, bch + t * BTAP16 + k * BK16, b_hi, id1);
+                                            umma_bf16_c<true>(col2, abuf + TAPO(t) + k * K16, a_hi, bch + t * BTAP16 + k * BK16 + boff2, b_hi, id2);
                                         }
-                                    }
-                                }
                             }
                         }
                         umma_commit(&a_empty[slot]);
-                        if (++slot == (uint32_t)NS) { slot = 0; fph ^= 1; }
+                        if (++slot == (uint32_t)NS) { slot = 0; ++lap; }
                     }
                     if (s >= 2) {                        // output od = s - 2 has received its last contribution
                         int r2 = r - 2;
@@ -546,7 +530,7 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[blk]);
+                if (lane == 0) counter_add(&acc_empty[blk]);
                 if (++r == NA) { r = 0; wpar ^= 1; }
             }
             if (has_x) asm volatile("cp.async.wait_all;" ::: "memory");
@@ -691,8 +675,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int DR = p.DR;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < F1_NS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < NA; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < F1_NS; ++i) { flag_init(&a_full[i]); mbar_init(&a_empty[i], 1); }      // a_full: plain fill-number flags
+        for (int i = 0; i < NA; ++i) { mbar_init(&acc_full[i], 1); flag_init(&acc_empty[i]); }    // acc_empty: plain completion counters
         fence_mbar_init();
     }
     if (warp == F1_W_MMA) tmem_alloc(s_tmem, 512);
@@ -717,23 +701,23 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
         // ===================== loaders: warp w8 builds every 8th slab =====================
         const int w8 = warp - 4;
         __nv_bfloat16* scr = s_scr + w8 * F1_SCR;
-        uint32_t slot = 0, phase = 1;
+        uint32_t slot = 0, phase = 1, lap = 1;
         int owner = 0;
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
             int n, d0, h0, w0;
             f1_coords(p, item, n, d0, h0, w0);
             const float sc = p.in_ss ? p.in_ss[n * 2] : 1.f, sh = p.in_ss ? p.in_ss[n * 2 + 1] : 0.f;
             for (int od = 0; od < DR; ++od) {
-                const uint32_t my_slot = slot, my_phase = phase;
+                const uint32_t my_slot = slot, my_phase = phase, my_lap = lap;
                 const bool mine = owner == w8;
-                if (++slot == F1_NS) { slot = 0; phase ^= 1; }
+                if (++slot == F1_NS) { slot = 0; phase ^= 1; ++lap; }
                 if (++owner == F1_NLW) owner = 0;
                 if (!mine) continue;
                 mbar_wait(&a_empty[my_slot], my_phase);
                 f1_build_slab(p, n, d0 + od, h0, w0, sc, sh, scr, smA + my_slot * F1_ASTAGE, lane);
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[my_slot]);
+                if (lane == 0) flag_store(&a_full[my_slot], my_lap);
             }
         }
     } else if (warp == F1_W_MMA) {
@@ -744,13 +728,13 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
             const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
             const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
             const uint32_t b_lo = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smB) >> 4);
-            uint32_t slot = 0, fph = 0;
+            uint32_t slot = 0, lap = 1, started = 0;
             int r = 0;
-            uint32_t wpar = 0;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
                 for (int od = 0; od < DR; ++od) {
-                    mbar_wait(&acc_empty[r], wpar ^ 1);
-                    mbar_wait(&a_full[slot], fph);
+                    if (started >= (uint32_t)NA) counter_wait_ge(&acc_empty[r], 4u * (started / (uint32_t)NA));
+                    ++started;
+                    flag_wait_eq(&a_full[slot], lap);
                     tc_fence_after();
                     const uint32_t a0 = a_lo_base + slot * (F1_ASTAGE / 16);
                     const uint32_t tacc = tmem_base + (uint32_t)(r * CO);
@@ -758,8 +742,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
                     umma_bf16_c<true>(tacc, a0 + 2 * 128, a_hi, b_lo + 2 * CO, b_hi, idesc);
                     umma_commit(&a_empty[slot]);
                     umma_commit(&acc_full[r]);
-                    if (++slot == F1_NS) { slot = 0; fph ^= 1; }
-                    if (++r == NA) { r = 0; wpar ^= 1; }
+                    if (++slot == F1_NS) { slot = 0; ++lap; }
+                    if (++r == NA) r = 0;
                 }
             }
         }
@@ -808,7 +792,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[r]);
+                if (lane == 0) counter_add(&acc_empty[r]);
                 if (++r == NA) { r = 0; wpar ^= 1; }
             }
             if (ws) {
@@ -859,7 +843,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_wgrad_kernel(const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int DR = p.DR;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < F1_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < F1_NS; ++i) { flag_init(&full[i]); mbar_init(&empty[i], 1); }          // full: plain fill-number flags
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
@@ -879,16 +863,16 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_wgrad_kernel(const
         for (int j = 0; j < JO; ++j)
 #pragma unroll
             for (int e = 0; e < 8; ++e) dbacc[j][e] = 0.f;
-        uint32_t slot = 0, phase = 1;
+        uint32_t slot = 0, phase = 1, lap = 1;
         int owner = 0;
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
             int n, d0, h0, w0;
             f1_coords(p, item, n, d0, h0, w0);
             const float sc = p.in_ss ? p.in_ss[n * 2] : 1.f, sh = p.in_ss ? p.in_ss[n * 2 + 1] : 0.f;
             for (int od = 0; od < DR; ++od) {
-                const uint32_t my_slot = slot, my_phase = phase;
+                const uint32_t my_slot = slot, my_phase = phase, my_lap = lap;
                 const bool mine = owner == w8;
-                if (++slot == F1_NS) { slot = 0; phase ^= 1; }
+                if (++slot == F1_NS) { slot = 0; phase ^= 1; ++lap; }
                 if (++owner == F1_NLW) owner = 0;
                 if (!mine) continue;
                 mbar_wait(&empty[my_slot], my_phase);
@@ -929,7 +913,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_wgrad_kernel(const
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[my_slot]);
+                if (lane == 0) flag_store(&full[my_slot], my_lap);
             }
         }
         if (p.db) {
@@ -954,11 +938,11 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_wgrad_kernel(const
             const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
             const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
             const uint32_t b_lo_base = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smZ) >> 4);
-            uint32_t slot = 0, fph = 0;
+            uint32_t slot = 0, lap = 1;
             bool first = true;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
                 for (int od = 0; od < DR; ++od) {
-                    mbar_wait(&full[slot], fph);
+                    flag_wait_eq(&full[slot], lap);
                     tc_fence_after();
                     const uint32_t a0 = a_lo_base + slot * (F1_ASTAGE / 16), b0 = b_lo_base + slot * (ZSTAGE / 16);
                     if (first) umma_bf16_c<false>(tmem_base, a0, a_hi, b0, b_hi, idesc);
@@ -967,7 +951,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_wgrad_kernel(const
 #pragma unroll
                     for (int ks = 1; ks < 8; ++ks) umma_bf16_c<true>(tmem_base, a0 + ks * 16, a_hi, b0 + ks * 16, b_hi, idesc);
                     umma_commit(&empty[slot]);
-                    if (++slot == F1_NS) { slot = 0; fph ^= 1; }
+                    if (++slot == F1_NS) { slot = 0; ++lap; }
                 }
             }
             umma_commit(acc_full);
@@ -1004,7 +988,7 @@ struct DsShape {
 };
 
 static bool ds_shape(int Cin, int Cout, int kd, int kh, int kw, DsShape& s, bool with_dot = false) {
-    if (kd != 3 || (kh != 3 && kh != 1) || (kw != 3 && kw != 1)) return false;
+    if (kd != 3 || kh != 3 || kw != 3) return false;   // the MMA burst is compiled for the 3 x 3 (h, w) taps
     if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16 || Cout > 80) return false;
     s.CC = (Cin % 32 == 0) ? 32 : 16;
     const int J = s.CC / 8;

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
     uint8_t* smZ = smX + (NS + 3) * CS_XSLOT;
     float* s_db = reinterpret_cast<float*>(smZ + NS * CS_ZSLOT);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_db + CS_NB);
-    uint64_t* full = bars;                     // [NS] one loader-warp arrival
+    uint64_t* full = bars;                     // [NS] plain flags: fill number of the slot
     uint64_t* empty = bars + CS_MAX_NS;        // [NS] tcgen05.commit
     uint64_t* acc_full = bars + 2 * CS_MAX_NS; // [1]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
     constexpr int N3 = 3 * CS_NB;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NS; ++i) { flag_init(&full[i]); mbar_init(&empty[i], 1); }   // full: plain fill-number flags (umma.cuh)
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
 #pragma unroll
         for (int e = 0; e < 8; ++e) { dbacc[e] = 0.f; sc[e] = 1.f; sh[e] = 0.f; }
         int cur_n = -1;
-        uint32_t slot = 0, phase = 1;
+        uint32_t slot = 0, phase = 1, lap = 1;
         int owner = 0;
         const size_t xslice = (size_t)p.H * p.W * p.x_ld, zslice = (size_t)p.H * p.W * p.dz_ld;
         const bool want_db = p.db != nullptr && chunk == 0;
@@ -136,9 +136,9 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
                 cur_n = n;
             }
             for (int t = 0; t < DR + 2; ++t) {
-                const uint32_t my_slot = slot, my_phase = phase;
+                const uint32_t my_slot = slot, my_phase = phase, my_lap = lap;
                 const bool mine = owner == w8;
-                if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1; }
+                if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1; ++lap; }
                 if (++owner == p.nlw) owner = 0;
                 if (!mine) continue;
                 long long pa = 0, pb = 0, pc = 0;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[my_slot]);
+                if (lane == 0) flag_store(&full[my_slot], my_lap);
                 if (prof) { pf_wait += pb - pa; pf_load += pc - pb; pf_rest += clock64() - pc; ++pf_n; }
             }
         }
@@ -236,21 +236,19 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
             const uint64_t ad = make_desc(0, CS_WP * 16, CS_PLANE), bd = make_desc(0, CS_ZROW, CS_TW * 16);
             const uint32_t a_hi = (uint32_t)(ad >> 32), a_lo_c = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smX) >> 4);
             const uint32_t b_hi = (uint32_t)(bd >> 32), b_lo_c = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smZ) >> 4);
-            uint32_t slot = 0, fph = 0;              // ring position of the next stage to wait for
+            uint32_t slot = 0, lap = 1;              // ring position and fill number of the next stage to wait for
             uint32_t rslot = 0;                      // ring position of the output slice being issued (= its first x slice)
             bool first = true;                       // very first MMAs of this CTA overwrite the accumulators
-            bool f_ok = false;
             const bool prof = (p.debug & 8) != 0;
             long long pf_w = 0, pf_t0 = clock64(), pf_n = 0;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
                 for (int t = 0; t < DR + 2; ++t) {
                     long long t_ = 0;
                     if (prof) t_ = clock64();
-                    if (!f_ok) mbar_wait(&full[slot], fph);
+                    flag_wait_eq(&full[slot], lap);
                     if (prof) { pf_w += clock64() - t_; ++pf_n; }
                     tc_fence_after();
-                    if (++slot == (uint32_t)NS) { slot = 0; fph ^= 1; }
-                    f_ok = mbar_test_wait(&full[slot], fph);      // early probe of the next stage (a probe costs ~200 cycles of latency)
+                    if (++slot == (uint32_t)NS) { slot = 0; ++lap; }
                     if (t < 2) continue;
                     // output slice r = t - 2: x slices r, r+1, r+2 (+ one ignored) start at ring slot rslot, dz copies in slot rslot
                     const uint32_t xs = a_lo_c + rslot * (CS_XSLOT / 16);

@@ -54,6 +54,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---- plain shared-memory flags / counters for the hand-offs INTO the single-thread MMA issue loop ----------------------
+// An mbarrier probe costs the issuing thread ~200 cycles even when the barrier is already complete (measured,
+// scripts/ubench/umma_commit.cu) and the MMA thread cannot hide that; a volatile shared-memory load is ~30.  Producers
+// that are ordinary threads (operand loaders, epilogue warps) therefore publish with a plain store / atomic add after a
+// block-level fence, and only the hardware-signalled hand-offs (tcgen05.commit, cp.async.bulk) stay mbarriers.
+// The storage is an 8-byte slot of the barrier array, zero-initialised instead of mbarrier.init.
+__device__ __forceinline__ void flag_init(uint64_t* f) { *reinterpret_cast<volatile uint64_t*>(f) = 0ull; }
+__device__ __forceinline__ void flag_store(uint64_t* f, uint32_t v) {
+    __threadfence_block();
+    *reinterpret_cast<volatile uint32_t*>(f) = v;
+}
+__device__ __forceinline__ void counter_add(uint64_t* f) {
+    __threadfence_block();
+    atomicAdd(reinterpret_cast<unsigned int*>(f), 1u);
+}
+__device__ __forceinline__ void flag_wait_eq(uint64_t* f, uint32_t v) {
+    const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(f);
+    if (*q == v) return;
+    const long long t0 = clock64();
+    while (*q != v) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void counter_wait_ge(uint64_t* f, uint32_t v) {
+    const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(f);
+    if (*q >= v) return;
+    const long long t0 = clock64();
+    while (*q < v) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
 // ---- proxies / bulk copy -----------------------------------------------------------------------------------
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
