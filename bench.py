@@ -233,6 +233,21 @@ def run_ours(args):
         pass
     tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    def ncu_traffic(kernel_substr):
+        """DRAM bytes (read + write) of one launch of the kernel from the committed `ncu --set full` capture, or None."""
+        try:
+            import csv
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01_kernels_ncu_full.csv"))))
+            hdr, units = rows[0], rows[1]
+            ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for r in rows[2:]:
+                if kernel_substr in r[ik]:
+                    return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+        except Exception:
+            pass
+        return None
+
     roofline = None
     if fam:
         top = max(fam, key=lambda k: fam[k][1])
@@ -240,7 +255,12 @@ def run_ours(args):
         achieved = work / (tot_ms * 1e-3) / 1e12
         step_share = tot_ms / nroof / ms
         roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": tens_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tens_peak, "traffic": None, "launches_per_step": n // nroof,
+                    "frac": achieved / tens_peak,
+                    # per-launch DRAM traffic from the committed ncu capture of the family's largest launch (L0 32->32 on
+                    # (4,128^3): algorithmic bytes = x + dz read once = 1.074e9); achieved / avg_launch_ms average all launches
+                    "traffic": ncu_traffic("wgrad_cs") if top == "conv_umma_wgrad" else None,
+                    "traffic_launch": "conv3d_wgrad_cs_kernel, 32->32 @ (4,128,128,128), algorithmic 1.074e9 B" if top == "conv_umma_wgrad" else None,
+                    "launches_per_step": n // nroof,
                     "avg_launch_ms": tot_ms / n, "share_of_step": step_share, "peak_source": peak_src,
                     "families_ms_per_step": {k: v[1] / nroof for k, v in fam.items()}}
     cpu = None

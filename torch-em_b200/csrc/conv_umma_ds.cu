@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
         constexpr int UNITS = DS_HP * DS_WP * J;       // 16-byte units per stage
         constexpr int NU = (UNITS + 31) / 32;          // per lane
         constexpr int VSTEP = 32 / J;                  // voxels per 32 units
-        const int j = lane % J;                        // this lane's 8-channel plane (32 % J == 0)
-        const int vl = lane / J;
+        const int j = lane / VSTEP;                    // this lane's 8-channel plane: a quarter (half) warp = consecutive voxels of
+        const int vl = lane % VSTEP;                   // ONE plane = whole 128-byte shared-memory lines
         float sc[8], sh[8];
         int cur_n = -1, cur_c = -1;
         uint32_t slot = 0, phase = 1, lap = 1;         // ring position of the current stage (phase = parity to wait for on a_empty, lap = fill number)

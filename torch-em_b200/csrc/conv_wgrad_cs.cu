@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
         const int w8 = warp - 4;
         constexpr int XU = CS_XVOX * 4 / 32;                 // x units (16 B) per lane and stage: 20
         constexpr int ZU = CS_HP * CS_TW * 4 / 32;           // dz units per lane and stage: 18 (unit i = haloed row i)
-        const int j = lane & 3, vl = lane >> 2;              // 8-channel group of this lane, first voxel
+        const int j = lane >> 3, vl = lane & 7;              // 8-channel group of this lane, first voxel: a quarter warp = 8 consecutive voxels of one plane = one 128-byte shared-memory line
         float sc[8], sh[8];
         float dbacc[8];
 #pragma unroll
