@@ -217,9 +217,11 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ g, int64_t g_ld, con
 
 // ---------------------------------------------------------------------------------------------------------------
 // max pool forward (+ statistics of the pooled output)
-template <typename T, int VEC>
+// F2 = 1: factor (2,2,2) or (1,2,2) known at compile time (FDC = depth factor): the window loads are unrolled and in flight together
+template <typename T, int VEC, int F2 = 0, int FDC = 0>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __restrict__ y, int64_t y_ld, int D, int H,
-                                   int W, int C, int fd, int fh, int fw, float* __restrict__ sums) {
+                                   int W, int C, int fd_, int fh_, int fw_, float* __restrict__ sums) {
+    const int fd = F2 ? FDC : fd_, fh = F2 ? 2 : fh_, fw = F2 ? 2 : fw_;
     const int n = blockIdx.y, cvec = C / VEC;
     const int Do = D / fd, Ho = H / fh, Wo = W / fw;
     const int64_t So = (int64_t)Do * Ho * Wo;
@@ -237,15 +239,29 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __r
                 float m[VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) m[v] = -INFINITY;
-                for (int a = 0; a < fd; ++a)
-                    for (int b = 0; b < fh; ++b)
-                        for (int c = 0; c < fw; ++c) {
-                            int64_t vi = ((int64_t)(d_o * fd + a) * H + (ho * fh + b)) * W + (wo * fw + c);
-                            float t[VEC];
-                            Vec<T, VEC>::load(xn + vi * x_ld + cv * VEC, t);
+                if (F2) {
+                    float t[FDC ? FDC * 4 : 1][VEC];
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], t[v]);
-                        }
+                    for (int q = 0; q < FDC * 4; ++q) {
+                        const int a = q >> 2, b = (q >> 1) & 1, c = q & 1;
+                        const int64_t vi = ((int64_t)(d_o * FDC + a) * H + (ho * 2 + b)) * W + (wo * 2 + c);
+                        Vec<T, VEC>::load(xn + vi * x_ld + cv * VEC, t[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < FDC * 4; ++q)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], t[q][v]);
+                } else {
+                    for (int a = 0; a < fd; ++a)
+                        for (int b = 0; b < fh; ++b)
+                            for (int c = 0; c < fw; ++c) {
+                                int64_t vi = ((int64_t)(d_o * fd + a) * H + (ho * fh + b)) * W + (wo * fw + c);
+                                float t[VEC];
+                                Vec<T, VEC>::load(xn + vi * x_ld + cv * VEC, t);
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) m[v] = fmaxf(m[v], t[v]);
+                            }
+                }
                 Vec<T, VEC>::store(yn + (size_t)s * y_ld + cv * VEC, m);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) { acc[v][0] += m[v]; acc[v][1] += m[v] * m[v]; }
@@ -871,7 +887,12 @@ int b200em_maxpool3d_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int
         constexpr int V = FullVec<T>::value;
         if (can_vec<T>(C, {x_ld, y_ld}, {x, y})) {
             Launch2D l = make_launch(C / V, So, N);
-            maxpool_fwd_kernel<T, V><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);
+            if (fd == 2 && fh == 2 && fw == 2)
+                maxpool_fwd_kernel<T, V, 1, 2><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);
+            else if (fd == 1 && fh == 2 && fw == 2)
+                maxpool_fwd_kernel<T, V, 1, 1><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);
+            else
+                maxpool_fwd_kernel<T, V><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);
         } else {
             Launch2D l = make_launch(C, So, N);
             maxpool_fwd_kernel<T, 1><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);

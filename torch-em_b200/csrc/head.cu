@@ -217,19 +217,23 @@ head_fwd_small_kernel(const T* __restrict__ x, int64_t x_ld, const float* __rest
 }
 
 template <typename T, int CIN, int COUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_bwd_small_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, const T* __restrict__ x, int64_t x_ld,
                       const float* __restrict__ w, T* __restrict__ dx, int64_t dx_ld, float* __restrict__ dw,
                       float* __restrict__ db, int64_t S, int act, int relu_mask, int64_t total) {
     constexpr int V = FullVec<T>::value;
     __shared__ float red[8][COUT * CIN + COUT];
-    float wr[COUT][CIN], aw[COUT][CIN], ab[COUT];
+    __shared__ float wr_s[COUT * CIN];               // filter in shared memory (broadcast reads): two blocks per SM fit the register file
+    float aw[COUT][CIN], ab[COUT];
+    for (int i = threadIdx.x; i < COUT * CIN; i += blockDim.x) wr_s[i] = w[i];
 #pragma unroll
     for (int j = 0; j < COUT; ++j) {
         ab[j] = 0.f;
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) { wr[j][c] = w[j * CIN + c]; aw[j][c] = 0.f; }
+        for (int c = 0; c < CIN; ++c) aw[j][c] = 0.f;
     }
+    __syncthreads();
+    const float (*wr)[CIN] = reinterpret_cast<const float (*)[CIN]>(wr_s);
     for (int64_t vox = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; vox < total; vox += (int64_t)gridDim.x * blockDim.x) {
         const int64_t n = vox / S, s_ = vox % S;
         float dz[COUT];
