@@ -17,6 +17,7 @@
 //   B       = [chunk][tap (b,c)][plane j][n = a*Cout + co][8 bf16]   (resident, loaded once by cp.async.bulk)
 // Warp roles (448 threads): warps 0-3 epilogue, warps 4-11 operand loaders (each warp owns every 8th stage, so eight
 // stage loads are in flight), warp 12 weight loader, warp 13 MMA issuer.
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,7 +30,7 @@ using namespace umma;
 namespace {
 constexpr int DS_TH = 16, DS_TW = 8;
 constexpr int DS_HP = DS_TH + 2, DS_WP = DS_TW + 2;
-constexpr int DS_PLANE = DS_HP * DS_WP * 16 + 16;   // +16 B staggers the planes across banks
+constexpr int DS_PLANE = 2944;                      // 18 x 10 voxels x 16 B = 2880, padded to a multiple of 128 B (TMA destination alignment)
 constexpr int DS_MAX_SMEM = 227 * 1024;
 constexpr int DS_MAX_NS = 12;                       // A ring depth cap
 constexpr int DS_MAX_NA = 16;                       // accumulator ring blocks cap
@@ -50,6 +51,7 @@ struct ConvDsParams {
     int tiles_w, tiles_h, tiles_d;
     long long items;
     int wbytes;
+    int use_tma;                     // 1: the haloed tile planes are loaded by cp.async.bulk.tensor (5-D tiled tensor map over x), else cp.async
     int xdepth;                      // dot_x prefetch ring depth (output slices in flight per epilogue thread), 0 without dot_x
     int debug;                       // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 2 no epilogue math, 4 no MMAs, 16 no norm apply
 };
@@ -178,7 +180,7 @@ template <int CO> struct DsRoles {
 };
 
 template <int CO, int KC_>
-__global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel(const ConvDsParams p) {
+__global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel(const ConvDsParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     using RL = DsRoles<CO>;
     constexpr int DS_THREADS = RL::THREADS, DS_W_WLOAD = RL::W_WLOAD, DS_W_MMA = RL::W_MMA;
@@ -196,7 +198,8 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
     uint64_t* acc_full = a_empty + DS_MAX_NS;         // [NA]  tcgen05.commit
     uint64_t* acc_empty = acc_full + DS_MAX_NA;       // [NA] plain counters: epilogue-warp completions per ring block (counter_add / counter_wait_ge)
     uint64_t* b_full = acc_empty + DS_MAX_NA;         // [1]   expect_tx (resident filter)
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(b_full + 1);
+    uint64_t* t_full = b_full + 1;                    // [NS]  TMA tile loads (expect_tx)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_full + DS_MAX_NS);
     uint32_t* s_tap = s_tmem + 2;                     // [9] operand start offset of each (b, c) tap, 16-byte units
     uint8_t* s_xring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_tap + 9) + 15) & ~(uintptr_t)15);   // [xdepth][128 rows][CO bf16]
 
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
     const int DR = p.DR, NS = p.NS;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NS; ++i) { flag_init(&a_full[i]); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NS; ++i) { flag_init(&a_full[i]); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); }
         for (int i = 0; i < NA; ++i) { mbar_init(&acc_full[i], 1); flag_init(&acc_empty[i]); }
         mbar_init(b_full, 1);
         fence_mbar_init();
@@ -274,19 +277,36 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                     uint8_t* dst = smA + my_slot * A_STAGE + j * DS_PLANE + vl * 16;
                     const uint32_t dst32 = smem_u32(dst);
                     const __nv_bfloat16* xc = xs + c * p.CC;
-                    if (!(p.debug & 1)) {
+                    if (p.use_tma) {
+                        // one tiled TMA load per 8-channel plane: box (8 ch, 10 w, 18 h, 1 d, 1 n) lands as [hp][wp][8 ch];
+                        // coordinates outside the volume (halo, slices d0-1 / beyond D) are zero-filled by the TMA unit
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(&t_full[my_slot], (uint32_t)(J * DS_HP * DS_WP * 16));
+                            const uint32_t bar32 = smem_u32(&t_full[my_slot]);
 #pragma unroll
-                        for (int i = 0; i < NU; ++i) {
-                            if (vl + VSTEP * i < DS_HP * DS_WP) {
-                                const bool in = in_d && goff[i] >= 0;
-                                const __nv_bfloat16* src = in ? xc + goff[i] : p.x;
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst32 + (uint32_t)(VSTEP * i * 16)),
-                                             "l"(src), "r"(in ? 16 : 0)
-                                             : "memory");
+                            for (int jj = 0; jj < J; ++jj)
+                                asm volatile(
+                                    "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::
+                                        "r"(smem_u32(smA + my_slot * A_STAGE + jj * DS_PLANE)),
+                                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c * p.CC + jj * 8), "r"(w0 - 1), "r"(h0 - 1), "r"(gd), "r"(n), "r"(bar32)
+                                    : "memory");
+                        }
+                        mbar_wait(&t_full[my_slot], (my_lap - 1) & 1);
+                    } else {
+                        if (!(p.debug & 1)) {
+#pragma unroll
+                            for (int i = 0; i < NU; ++i) {
+                                if (vl + VSTEP * i < DS_HP * DS_WP) {
+                                    const bool in = in_d && goff[i] >= 0;
+                                    const __nv_bfloat16* src = in ? xc + goff[i] : p.x;
+                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst32 + (uint32_t)(VSTEP * i * 16)),
+                                                 "l"(src), "r"(in ? 16 : 0)
+                                                 : "memory");
+                                }
                             }
                         }
+                        asm volatile("cp.async.wait_all;" ::: "memory");
                     }
-                    asm volatile("cp.async.wait_all;" ::: "memory");
                     if (prof) pf_c = clock64();
                     if (p.in_ss && in_d && !(p.debug & 16)) {
                         if (n != cur_n || c != cur_c) {
@@ -993,7 +1013,7 @@ static bool ds_shape(int Cin, int Cout, int kd, int kh, int kw, DsShape& s, bool
     s.CC = (Cin % 32 == 0) ? 32 : 16;
     const int J = s.CC / 8;
     s.wbytes = 3 * kh * kw * Cin * Cout * 2;
-    const int misc = Cout * 4 * 3 + (2 * DS_MAX_NS + 2 * DS_MAX_NA + 1) * 8 + 8 + 9 * 4 + 128;
+    const int misc = Cout * 4 * 3 + (3 * DS_MAX_NS + 2 * DS_MAX_NA + 1) * 8 + 8 + 9 * 4 + 128;
     const int stage = J * DS_PLANE;
     int ns = (DS_MAX_SMEM - s.wbytes - misc) / stage;
     if (ns > DS_MAX_NS) ns = DS_MAX_NS;
@@ -1085,14 +1105,48 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
     B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
     long long gx = p.items < sm_count() ? p.items : sm_count();
+    // tiled tensor map over x: dims (C, W, H, D, N), box (8, 10, 18, 1, 1) -> one TMA load per 8-channel plane of a stage
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    p.use_tma = 0;
+    {
+        const char* e = getenv("B200EM_DS_TMA");
+        if (!(e && atoi(e) == 0)) {
+            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            static EncodeFn encode = nullptr;
+            static bool looked = false;
+            if (!looked) {
+                looked = true;
+                void* fn = nullptr;
+                cudaDriverEntryPointQueryResult qres;
+                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+                    encode = (EncodeFn)fn;
+                else
+                    (void)cudaGetLastError();
+            }
+            if (encode) {
+                const cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+                const cuuint64_t gstr[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2,
+                                            (cuuint64_t)D * H * W * x_ld * 2};
+                const cuuint32_t box[5] = {8, (cuuint32_t)DS_WP, (cuuint32_t)DS_HP, 1, 1};
+                const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r == CUDA_SUCCESS) p.use_tma = 1;
+            }
+        }
+    }
 #define B2_DS_LAUNCH(CO_)                                                                                                          \
     case CO_:                                                                                                                      \
         if (s.CC == 32) {                                                                                                          \
             B2_CUDA(cudaFuncSetAttribute(conv3d_umma_ds_kernel<CO_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
-            conv3d_umma_ds_kernel<CO_, 2><<<(unsigned)gx, DsRoles<CO_>::THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                    \
+            conv3d_umma_ds_kernel<CO_, 2><<<(unsigned)gx, DsRoles<CO_>::THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p, tmap);                    \
         } else {                                                                                                                   \
             B2_CUDA(cudaFuncSetAttribute(conv3d_umma_ds_kernel<CO_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
-            conv3d_umma_ds_kernel<CO_, 1><<<(unsigned)gx, DsRoles<CO_>::THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                    \
+            conv3d_umma_ds_kernel<CO_, 1><<<(unsigned)gx, DsRoles<CO_>::THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p, tmap);                    \
         }                                                                                                                          \
         break;
     switch (Cout) {

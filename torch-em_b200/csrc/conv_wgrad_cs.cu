@@ -254,15 +254,16 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
                     const uint32_t xs = a_lo_c + rslot * (CS_XSLOT / 16);
                     const uint32_t zs = b_lo_c + rslot * (CS_ZSLOT / 16);
                     if (!(p.debug & 4)) {
+                        // K step outermost, w tap innermost: consecutive MMAs share the B operand (the dz rows of this K step)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {        // w tap: start column of the haloed x rows
-                            const uint32_t a0 = xs + (uint32_t)c;
-                            const uint32_t tacc = tmem_base + (uint32_t)(c * N3);
-                            if (first) umma_bf16_c<false>(tacc, a0, a_hi, zs, b_hi, idesc);
-                            else umma_bf16_c<true>(tacc, a0, a_hi, zs, b_hi, idesc);
+                        for (int ks = 0; ks < CS_TH / 2; ++ks) {
 #pragma unroll
-                            for (int ks = 1; ks < CS_TH / 2; ++ks)
-                                umma_bf16_c<true>(tacc, a0 + ks * 2 * CS_WP, a_hi, zs + ks * 2 * (CS_ZROW / 16), b_hi, idesc);
+                            for (int c = 0; c < 3; ++c) {    // w tap: start column of the haloed x rows
+                                const uint32_t a0 = xs + (uint32_t)c + ks * 2 * CS_WP;
+                                const uint32_t tacc = tmem_base + (uint32_t)(c * N3);
+                                if (ks == 0 && first) umma_bf16_c<false>(tacc, a0, a_hi, zs, b_hi, idesc);
+                                else umma_bf16_c<true>(tacc, a0, a_hi, zs + ks * 2 * (CS_ZROW / 16), b_hi, idesc);
+                            }
                         }
                         first = false;
                     }
