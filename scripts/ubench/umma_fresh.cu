@@ -34,14 +34,20 @@ __global__ void __launch_bounds__(128, 1) fresh_kernel(int N, int layout, int fr
         uint32_t lbo_a, sbo_a, lbo_b, sbo_b, a_step, b_step;
         if (layout == 0) { lbo_a = 2944; sbo_a = 160; lbo_b = N * 16; sbo_b = 128; a_step = 2944 * 2; b_step = N * 32; }
         else { lbo_a = 16; sbo_a = 1024; lbo_b = 16; sbo_b = 1024; a_step = 128 * 128; b_step = N * 128; }   // one 64-wide K block per step
+        // descriptors precomputed: the timed loop only issues
+        uint64_t ad[16], bd[16];
+        const int nb = layout == 0 ? 16 : (96 * 1024 / (N * 128) > 16 ? 16 : 96 * 1024 / (N * 128));
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const uint32_t ao = (fresh & 1) ? (uint32_t)(u % (layout == 0 ? 16 : 5)) * a_step : 0u;
+            const uint32_t bo = (fresh & 2) ? (uint32_t)(u % nb) * b_step : 0u;
+            ad[u] = mk(a_addr + ao, lbo_a, sbo_a, layout);
+            bd[u] = mk(b_addr + bo, lbo_b, sbo_b, layout);
+        }
         const long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const uint32_t ao = (fresh & 1) ? (uint32_t)(u % (layout == 0 ? 16 : 5)) * a_step : 0u;
-                const uint32_t bo = (fresh & 2) ? (uint32_t)(u % (layout == 0 ? 16 : (96 * 1024 / (N * 128) > 16 ? 16 : 96 * 1024 / (N * 128)))) * b_step : 0u;
-                umma_bf16(tbase + (u & 3) * N, mk(a_addr + ao, lbo_a, sbo_a, layout), mk(b_addr + bo, lbo_b, sbo_b, layout), idesc, 1);
-            }
+            for (int u = 0; u < 16; ++u) umma_bf16(tbase + (u & 3) * N, ad[u], bd[u], idesc, 1);
         }
         umma_commit(&bar);
         mbar_wait(&bar, 0);
