@@ -376,6 +376,37 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                 int r = r0;                              // ring position of output od = s (the newest output slice s feeds)
                 uint32_t wpar = w0;
                 for (int s = 0; s < DR + 2; ++s) {
+                    // ---- fast path: an interior slice (feeds three outputs, starts a new one) whose three ring blocks do not wrap.
+                    // The issuing thread's bookkeeping is NOT hidden behind the MMAs, so the common case is kept to
+                    // a handful of instructions: one counter probe, one flag probe and one fence per stage, constants elsewhere.
+                    if (s >= 2 && s <= DR - 1 && r >= 2 && !prof && !(p.debug & 4)) {
+                        const int k0 = NA - 1 - r;       // blocks k0, k0+1, k0+2 = outputs s, s-1, s-2
+                        if (started >= (uint32_t)NA) counter_wait_ge(&acc_empty[k0], (uint32_t)RL::NEPI * (started / (uint32_t)NA));
+                        ++started;
+                        const uint32_t col1 = tmem_base + (uint32_t)(k0 * CO);
+                        uint32_t bch = b_lo_base;
+                        for (int c = 0; c < p.nchunks; ++c, bch += 9u * BTAP16) {
+                            flag_wait_eq(&a_full[slot], lap);
+                            tc_fence_after();
+                            const uint32_t abuf = a_lo_base + slot * ASTAGE16;
+                            if (c == 0) {
+                                umma_bf16_c<false>(col1, abuf + TAPO(0), a_hi, bch, b_hi, idesc1);
+                                umma_bf16_c<true>(col1 + CO, abuf + TAPO(0), a_hi, bch + CO, b_hi, idesc2);
+                            } else {
+                                umma_bf16_c<true>(col1, abuf + TAPO(0), a_hi, bch, b_hi, idesc3);
+                            }
+#pragma unroll
+                            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                                for (int k = 0; k < KC_; ++k)
+                                    if (t + k > 0) umma_bf16_c<true>(col1, abuf + TAPO(t) + k * K16, a_hi, bch + t * BTAP16 + k * BK16, b_hi, idesc3);
+                            umma_commit(&a_empty[slot]);
+                            if (++slot == (uint32_t)NS) { slot = 0; ++lap; }
+                        }
+                        umma_commit(&acc_full[k0 + 2]);  // output s - 2 = ring position r - 2
+                        if (++r == NA) { r = 0; wpar ^= 1; }
+                        continue;
+                    }
                     const int a_lo = s - (DR - 1) > 0 ? s - (DR - 1) : 0;
                     const int nblk = (s < 2 ? s : 2) - a_lo + 1;
                     int rf = r - a_lo;                   // ring position of the first (a = a_lo) output this slice feeds
