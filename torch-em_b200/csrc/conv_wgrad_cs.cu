@@ -16,6 +16,7 @@
 // 4-slice operand window of any output slice is one contiguous block (descriptor stride = plane).
 // Warp roles: warps 0-3 epilogue (once, at the end), warps 4-11 loaders (each warp owns every nlw-th stage), warp 12
 // MMA issuer.  Replaces the autograd weight/bias gradient of nn.Conv3d (unet.py:429-438) for the 3x3x3 layers.
+#include <cuda.h>      // CUtensorMap (types only; the encoder comes from cudaGetDriverEntryPoint)
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,7 +30,7 @@ namespace {
 constexpr int CS_TH = 16, CS_TW = 8;
 constexpr int CS_HP = CS_TH + 2, CS_WP = CS_TW + 2;
 constexpr int CS_XVOX = CS_TH * CS_WP;                 // x tile: 16 rows x 10 columns (w halo only)
-constexpr int CS_PLANE = CS_XVOX * 16 + 16;            // bytes per 8-channel plane of an x slice (+16 staggers banks)
+constexpr int CS_PLANE = CS_XVOX * 16;                 // bytes per 8-channel plane of an x slice: 2560 = 20 x 128 (TMA destination alignment)
 constexpr int CS_XSLOT = 4 * CS_PLANE;                 // one x slice of a 32-channel chunk
 constexpr int CS_NB = 32;                              // output channels per CTA
 constexpr int CS_ZROW = (CS_NB / 8) * CS_TW * 16;      // one haloed dz row: [jo][w][8 ch] = 512 B
@@ -52,10 +53,12 @@ struct WgradCsParams {
     int DR, NS, nlw;
     int tiles_w, tiles_h, tiles_d;
     long long items;
+    int use_tma;                               // 1: tiles loaded by cp.async.bulk.tensor (tensor maps over x and dz), else cp.async
     int debug;                                 // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 4 no MMAs, 8 profile printf
 };
 
-__global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const WgradCsParams p) {
+__global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const WgradCsParams p, const __grid_constant__ CUtensorMap tmx,
+                                                                       const __grid_constant__ CUtensorMap tmz) {
     extern __shared__ __align__(128) uint8_t smem[];
     // carve: X[NS + 3] (slots 0..2 mirrored at NS..NS+2) | Z[NS] | db sums[32] | barriers | tmem ptr
     const int NS = p.NS, DR = p.DR;
@@ -66,14 +69,15 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
     uint64_t* full = bars;                     // [NS] plain flags: fill number of the slot
     uint64_t* empty = bars + CS_MAX_NS;        // [NS] tcgen05.commit
     uint64_t* acc_full = bars + 2 * CS_MAX_NS; // [1]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint64_t* t_full = acc_full + 1;           // [NS] TMA tile loads (expect_tx)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_full + CS_MAX_NS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.y / p.nco, cob = blockIdx.y % p.nco;
     constexpr int N3 = 3 * CS_NB;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NS; ++i) { flag_init(&full[i]); mbar_init(&empty[i], 1); }   // full: plain fill-number flags (umma.cuh)
+        for (int i = 0; i < NS; ++i) { flag_init(&full[i]); mbar_init(&empty[i], 1); mbar_init(&t_full[i], 1); }   // full: plain fill-number flags (umma.cuh)
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
@@ -155,7 +159,33 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
                 uint8_t* zdst = smZ + my_slot * CS_ZSLOT + j * (CS_TW * 16) + vl * 16;
                 const uint32_t xd32 = smem_u32(xdst), zd32 = smem_u32(zdst);
                 const uint32_t mirror = my_slot < 3 ? (uint32_t)(NS * CS_XSLOT) : 0u;
-                if (!(p.debug & 1)) {
+                if (p.use_tma) {
+                    // x slice: one tiled load per 8-channel plane, box (8 ch, 10 w, 16 h, 1 d, 1 n); dz slice: ONE load, box
+                    // (8 ch, 8 w, 4 groups, 18 h, 1) over the view (8, W, Cout/8, H, N*D) -> lands as [row][group][w][8 ch];
+                    // halo rows / columns and out-of-volume x slices are zero-filled by the TMA unit
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&t_full[my_slot], (uint32_t)(CS_XSLOT + (z_on ? CS_ZSLOT : 0)));
+                        const uint32_t bar32 = smem_u32(&t_full[my_slot]);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            asm volatile(
+                                "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::
+                                    "r"(smem_u32(smX + my_slot * CS_XSLOT + jj * CS_PLANE)),
+                                "l"(reinterpret_cast<uint64_t>(&tmx)), "r"(chunk * 32 + jj * 8), "r"(w0 - 1), "r"(h0), "r"(gd), "r"(n), "r"(bar32)
+                                : "memory");
+                        if (z_on)
+                            asm volatile(
+                                "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::
+                                    "r"(smem_u32(smZ + my_slot * CS_ZSLOT)),
+                                "l"(reinterpret_cast<uint64_t>(&tmz)), "r"(0), "r"(w0), "r"(cob * (CS_NB / 8)), "r"(h0 - 1), "r"(n * p.D + gz), "r"(bar32)
+                                : "memory");
+                    }
+                    if (!z_on && t < DR) {           // dz slice beyond the volume (D % DR != 0): zeros
+#pragma unroll
+                        for (int i = 0; i < ZU; ++i) *reinterpret_cast<uint4*>(zdst + i * CS_ZROW) = make_uint4(0, 0, 0, 0);
+                    }
+                    mbar_wait(&t_full[my_slot], (my_lap - 1) & 1);
+                } else if (!(p.debug & 1)) {
 #pragma unroll
                     for (int i = 0; i < ZU; ++i) {
                         const bool in = z_on && ((zmask >> i) & 1);
@@ -173,7 +203,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
                                      : "memory");
                     }
                 }
-                asm volatile("cp.async.wait_all;" ::: "memory");
+                if (!p.use_tma) asm volatile("cp.async.wait_all;" ::: "memory");
                 if (prof) pc = clock64();
                 if (in_d && (p.in_ss || mirror)) {
                     // norm apply in place (fp32 math, one rounding to bf16) and the mirror copy of the first three slots
@@ -342,7 +372,7 @@ int b200em_conv3d_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_sh
     p.dw = dw; p.db = db;
     p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
     p.nco = Cout / CS_NB;
-    const int misc = CS_NB * 4 + (2 * CS_MAX_NS + 1) * 8 + 8 + 128;
+    const int misc = CS_NB * 4 + (3 * CS_MAX_NS + 1) * 8 + 8 + 128;
     int ns = (CS_MAX_SMEM - misc - 3 * CS_XSLOT) / (CS_XSLOT + CS_ZSLOT);
     if (ns > CS_MAX_NS) ns = CS_MAX_NS;
     B2_CHECK_ARG(ns >= 4, "conv3d_wgrad_cs: shared memory budget exceeded");
@@ -375,7 +405,47 @@ int b200em_conv3d_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_sh
     { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
     B2_CUDA(cudaFuncSetAttribute(conv3d_wgrad_cs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_MAX_SMEM));
     dim3 grid((unsigned)splits, (unsigned)pairs, 1);
-    conv3d_wgrad_cs_kernel<<<grid, CS_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    // tensor maps: x as (C, W, H, D, N) with box (8, 10, 16, 1, 1); dz as (8, W, Cout/8, H, N*D) with box (8, 8, 4, 18, 1)
+    CUtensorMap tmx, tmz;
+    memset(&tmx, 0, sizeof(tmx));
+    memset(&tmz, 0, sizeof(tmz));
+    p.use_tma = 0;
+    {
+        const char* e = getenv("B200EM_CS_TMA");
+        if (!(e && atoi(e) == 0)) {
+            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            static EncodeFn encode = nullptr;
+            static bool looked = false;
+            if (!looked) {
+                looked = true;
+                void* fn = nullptr;
+                cudaDriverEntryPointQueryResult qres;
+                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+                    encode = (EncodeFn)fn;
+                else
+                    (void)cudaGetLastError();
+            }
+            if (encode) {
+                const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                const cuuint64_t xdim[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+                const cuuint64_t xstr[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2, (cuuint64_t)D * H * W * x_ld * 2};
+                const cuuint32_t xbox[5] = {8, (cuuint32_t)CS_WP, (cuuint32_t)CS_TH, 1, 1};
+                const cuuint64_t zdim[5] = {8, (cuuint64_t)W, (cuuint64_t)(Cout / 8), (cuuint64_t)H, (cuuint64_t)N * D};
+                const cuuint64_t zstr[4] = {(cuuint64_t)dz_ld * 2, 16, (cuuint64_t)W * dz_ld * 2, (cuuint64_t)H * W * dz_ld * 2};
+                const cuuint32_t zbox[5] = {8, (cuuint32_t)CS_TW, (cuuint32_t)(CS_NB / 8), (cuuint32_t)CS_HP, 1};
+                const CUresult r1 = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), xdim, xstr, xbox, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                const CUresult r2 = encode(&tmz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dz), zdim, zstr, zbox, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) p.use_tma = 1;
+            }
+        }
+    }
+    conv3d_wgrad_cs_kernel<<<grid, CS_THREADS, smem_bytes, (cudaStream_t)stream>>>(p, tmx, tmz);
     B2_LAUNCH_CHECK();
     return 0;
 }
