@@ -201,7 +201,6 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
     uint64_t* t_full = b_full + 1;                    // [NS]  TMA tile loads (expect_tx)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_full + DS_MAX_NS);
     uint32_t* s_tap = s_tmem + 2;                     // [9] operand start offset of each (b, c) tap, 16-byte units
-    uint8_t* s_xring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_tap + 9) + 15) & ~(uintptr_t)15);   // [xdepth][128 rows][CO bf16]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntap = p.kh * p.kw;
@@ -504,8 +503,6 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
         const bool ws = p.sums != nullptr;
         const bool has_x = p.dot_x != nullptr;
         constexpr int XV = CPT / 8;                  // 16-byte vectors of dot_x per thread
-        const int XD = p.xdepth;
-        const uint32_t xs_row = smem_u32(s_xring) + (uint32_t)row * (CO * 2) + (uint32_t)col0 * 2;
         int r = 0;                                   // (oc % NA, (oc / NA) & 1) of the next output slice
         uint32_t wpar = 0;
         const bool prof = (p.debug & 8) != 0;
@@ -518,41 +515,25 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
             // this row's voxel in slice d0 (clamped when the row is outside the volume: never dereferenced then)
             const size_t vox0 = (((size_t)n * p.D + d0) * p.H + (valid_hw ? gh : 0)) * p.W + (valid_hw ? gw : 0);
             const size_t hw = (size_t)p.H * p.W;
-            uint4 xcur[XV];
-            // dot_x rows are prefetched XD output slices ahead with cp.async into a PRIVATE shared-memory slot per thread
-            // (each thread reads back only what it copied itself: no barrier, just cp.async groups); a global load issued
-            // when the accumulator is ready would expose its full latency on every slice.
-            auto issue_x = [&](int od_) {
-                if (has_x) {
-                    const bool ok = valid_hw && od_ < DR && d0 + od_ < p.D;
-                    const __nv_bfloat16* q_ = ok ? p.dot_x + (vox0 + (size_t)od_ * hw) * p.dot_ld + col0 : p.dot_x;
-                    const uint32_t dst = xs_row + (uint32_t)(od_ % XD) * (128u * CO * 2u);
+            // dot_x rows are prefetched into registers two output slices ahead (one when a thread owns 32 columns or more:
+            // register budget): a load issued when the accumulator is ready would expose its full latency on every slice, and
+            // staging them through shared memory costs LSU wavefronts (8x the ideal for this 16-byte scatter) that the tensor
+            // pipe's operand fetch needs.
+            constexpr bool DBL = XV <= 2;
+            uint4 xa[XV], xb[DBL ? XV : 1];
+            auto load_x = [&](uint4* dst, int od_) {
+                const bool ok = has_x && valid_hw && od_ < DR && d0 + od_ < p.D;
+                const __nv_bfloat16* q_ = p.dot_x + (vox0 + (size_t)od_ * hw) * p.dot_ld + col0;
 #pragma unroll
-                    for (int i = 0; i < XV; ++i)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16u * (uint32_t)((i + row) % XV)), "l"(q_ + 8 * i),
-                                     "r"(ok ? 16 : 0)
-                                     : "memory");
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                }
+                for (int i = 0; i < XV; ++i) dst[i] = ok ? __ldg(reinterpret_cast<const uint4*>(q_ + 8 * i)) : make_uint4(0, 0, 0, 0);
             };
-            for (int i = 0; i < XD - 1; ++i) issue_x(i);
-            for (int od = 0; od < DR; ++od) {
+            auto process = [&](int od, const uint4* xcur) {
                 const int blk = NA - 1 - r;
                 long long t_ = 0;
                 if (prof) t_ = clock64();
                 mbar_wait(&acc_full[blk], wpar);
                 if (prof) { pf_w += clock64() - t_; ++pf_n; }
                 tc_fence_after();
-                if (has_x) {
-                    issue_x(od + XD - 1);
-                    // all but the XD-1 most recent groups have landed -> slice od is in its slot
-                    if (XD == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
-                    else if (XD == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
-                    else asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    const uint8_t* src = s_xring + (size_t)(od % XD) * (128 * CO * 2) + (size_t)row * (CO * 2) + col0 * 2;
-#pragma unroll
-                    for (int i = 0; i < XV; ++i) xcur[i] = *reinterpret_cast<const uint4*>(src + 16 * ((i + row) % XV));
-                }
                 const int gd = d0 + od;
                 const bool valid = valid_hw && gd < p.D;
                 __nv_bfloat16* yp = p.y + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld + col0;
@@ -583,8 +564,19 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                 __syncwarp();
                 if (lane == 0) counter_add(&acc_empty[blk]);
                 if (++r == NA) { r = 0; wpar ^= 1; }
+            };
+            load_x(xa, 0);
+            if constexpr (DBL) load_x(xb, 1);
+            for (int od = 0; od < DR; od += (DBL ? 2 : 1)) {
+                process(od, xa);
+                load_x(xa, od + (DBL ? 2 : 1));
+                if constexpr (DBL) {
+                    if (od + 1 < DR) {
+                        process(od + 1, xb);
+                        load_x(xb, od + 3);
+                    }
+                }
             }
-            if (has_x) asm volatile("cp.async.wait_all;" ::: "memory");
             if (ws) {
                 // flush this item's per-channel partial sums (the sample n may change with the next item)
                 if constexpr (CPT == 32) {
@@ -1050,16 +1042,8 @@ static bool ds_shape(int Cin, int Cout, int kd, int kh, int kw, DsShape& s, bool
     if (ns > DS_MAX_NS) ns = DS_MAX_NS;
     if (ns < 6) return false;                        // the filter must stay resident next to a useful operand ring
     s.xdepth = 0;
-    int xring = 0;
-    if (with_dot) {
-        // room for the dot_x prefetch ring: as deep as possible while the operand ring keeps >= 5 stages
-        for (int xd = 4; xd >= 2; --xd) {
-            xring = xd * 128 * Cout * 2 + 16;
-            const int ns2 = (DS_MAX_SMEM - s.wbytes - misc - xring) / stage;
-            if (ns2 >= 5 || xd == 2) { s.xdepth = xd; ns = ns2 < ns ? ns2 : ns; break; }
-        }
-        if (ns < 3) return false;
-    }
+    const int xring = 0;                             // dot_x is prefetched into registers (no shared-memory ring)
+    (void)with_dot;
     s.NS = ns;
     s.smem_bytes = ns * stage + s.wbytes + misc + xring;
     return true;
