@@ -1,10 +1,10 @@
-// "depth-stacked" tcgen05 implicit-GEMM convolution for 3 x kh x kw filters with few output channels (Cout <= 80).
+// "depth-stacked" tcgen05 implicit-GEMM convolution for 3 x 3 x 3 filters with few output channels (Cout <= 80).
 //
-// Why (measured, scripts/ubench/umma_rate.cu on B200): one M=128 x N x K=16 bf16 tcgen05.mma with both operands in
-// shared memory takes max(N/2, ~57 + N/8) cycles -- the A-operand fetch is a fixed ~57-cycle cost -- so a layer issued
-// with N = Cout = 32 (64) runs at 26 % (49 %) of the tensor peak however well it is fed, while N = 96 reaches 70 % and
-// N = 192 the full rate.  Here the three DEPTH taps of the filter share one operand fetch: for an input slice s the
-// MMA computes, for every (b, c) tap,
+// Why (measured, scripts/ubench/umma_fresh.cu / umma_rate.cu on B200): one M=128 x N x K=16 bf16 tcgen05.mma
+// with both operands in shared memory costs max(N/2, 32 + N/4) tensor-pipe cycles and ~60-70 cycles of the single issuing
+// thread, so a layer issued with N = Cout = 32 (64) runs at <= 40 % (67 %) of the tensor peak however well it is fed, while
+// N = 96 reaches 86 % and N >= 128 the full rate.  Here the three DEPTH taps of the filter share one MMA: for an input
+// slice s it computes, for every (b, c) tap,
 //     [ y[s+1] | y[s] | y[s-1] ]  +=  x_hat[s][v + (b, c)]  *  [ W[a=0,b,c] | W[a=1,b,c] | W[a=2,b,c] ]
 // i.e. N = 3*Cout, and the three N-blocks land in the accumulators of three consecutive OUTPUT slices, which are
 // contiguous TMEM column blocks of a ring (block of output d = NA-1 - (d mod NA)).  No shifted sums, no shuffles: the
@@ -13,10 +13,13 @@
 //
 // Work item = 16 (h) x 8 (w) voxel tile x DR output depth slices; persistent grid = #SMs.
 // Shared-memory operand layout as in conv_umma.cu (SWIZZLE_NONE K-major core matrices):
-//   A stage = one input slice x one 32(16)-channel chunk: [plane j = 8-ch group][hp 0..17][wp 0..9][8 bf16]
+//   A stage = one input slice x one 32(16)-channel chunk: [plane j = 8-ch group][hp 0..17][wp 0..9][8 bf16], each plane one
+//             TMA tiled load (cp.async.bulk.tensor 5-D; halo outside the volume zero-filled by the TMA unit)
 //   B       = [chunk][tap (b,c)][plane j][n = a*Cout + co][8 bf16]   (resident, loaded once by cp.async.bulk)
-// Warp roles (448 threads): warps 0-3 epilogue, warps 4-11 operand loaders (each warp owns every 8th stage, so eight
-// stage loads are in flight), warp 12 weight loader, warp 13 MMA issuer.
+// Warp roles (DsRoles): 4 epilogue warps + 8 loader warps, or for Cout = 32 / 64 two epilogue column groups (8 warps) + 6
+// loader warps; each loader warp owns every nlw-th stage (issue the TMA loads, wait, norm apply in place, publish the
+// stage with a plain shared-memory flag); one weight-loader warp; one MMA-issuing thread (branch-free burst per stage).
+// The first convolution of the network (Cin = 1) and its weight gradient live at the end of this file.
 #include <cuda.h>      // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include <stdlib.h>
 
