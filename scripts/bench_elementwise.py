@@ -51,3 +51,12 @@ for C, S in ((32, 128), (64, 64)):
 x1 = torch.randn((N, 128, 128, 128, 1), device=dev).bfloat16()
 ss = torch.ones((N, 1, 2), device=dev)
 timeit("im2col 1->32 taps S=128", lambda: B.im2col(x1, ss, (3, 3, 3), 32), N * 128 ** 3 * (2 + 64))
+w1 = torch.randn((32, 1, 3, 3, 3), device=dev) * 0.2
+pk1 = B.pack(("bench-first",), w1)
+y1 = torch.empty((N, 128, 128, 128, 32), device=dev, dtype=torch.bfloat16)
+s1 = torch.zeros((N, 32, 2), device=dev)
+b1 = torch.zeros(32, device=dev)
+timeit("first conv fwd 1->32 S=128", lambda: B.conv(x1, ss, pk1, b1, y1, s1, (3, 3, 3), True, False), N * 128 ** 3 * (2 + 64))
+dw1 = torch.zeros_like(w1)
+db1 = torch.zeros(32, device=dev)
+timeit("first conv wgrad 1->32 S=128", lambda: B.wgrad(x1, ss, y1, dw1, db1, (3, 3, 3)), N * 128 ** 3 * (2 + 64))

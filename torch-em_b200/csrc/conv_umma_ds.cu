@@ -672,13 +672,22 @@ __device__ __forceinline__ void f1_coords(const ConvFirstParams& p, long long it
 __device__ __forceinline__ void f1_build_slab(const ConvFirstParams& p, int n, int gd, int h0, int w0, float sc, float sh,
                                               __nv_bfloat16* scr, uint8_t* dst, int lane) {
     const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W;
-    for (int i = lane; i < F1_SCR; i += 32) {
+    // all of the lane's loads are issued before the first one is consumed (one global latency per slab, not 17)
+    constexpr int NF = (F1_SCR + 31) / 32;
+    __nv_bfloat16 raw[NF];
+    bool inb[NF];
+#pragma unroll
+    for (int q = 0; q < NF; ++q) {
+        const int i = lane + 32 * q;
         const int wp_ = i % DS_WP, hp_ = (i / DS_WP) % DS_HP, a = i / (DS_WP * DS_HP);
         const int sd = gd + a - 1, gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
-        float v = 0.f;
-        if (sd >= 0 && sd < p.D && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W)
-            v = fmaf(__bfloat162float(xn[((size_t)sd * p.H + gh) * p.W + gw]), sc, sh);
-        scr[i] = __float2bfloat16_rn(v);
+        inb[q] = i < F1_SCR && sd >= 0 && sd < p.D && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
+        raw[q] = inb[q] ? xn[((size_t)sd * p.H + gh) * p.W + gw] : __float2bfloat16_rn(0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < NF; ++q) {
+        const int i = lane + 32 * q;
+        if (i < F1_SCR) scr[i] = __float2bfloat16_rn(inb[q] ? fmaf(__bfloat162float(raw[q]), sc, sh) : 0.f);
     }
     __syncwarp();
     const uint16_t* s16 = reinterpret_cast<const uint16_t*>(scr);
