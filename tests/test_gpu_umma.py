@@ -101,13 +101,15 @@ def test_umma_conv_forward_and_dgrad(B, case):
     np.testing.assert_allclose(d.cpu().numpy(), d_ref.numpy(), rtol=1e-2, atol=2e-2 * float(d_ref.abs().max()))
 
 
+@pytest.mark.parametrize("tma", ["1", "0"])
 @pytest.mark.parametrize("case", [(2, 24, 48, 40, 64, 32, (3, 3, 3)), (2, 24, 48, 40, 32, 32, (3, 3, 3))])
-def test_dstacked_many_items_per_cta(case, monkeypatch):
+def test_dstacked_many_items_per_cta(case, tma, monkeypatch):
     """Depth-stacked kernel with more work items than SMs (short depth segments forced): the operand ring, the accumulator
     ring and the dot_x prefetch ring all wrap many times per CTA, and the dgrad runs with fewer ring stages than loader warps."""
     from torch_em_b200 import _lib
     from torch_em_b200.backend import CudaBackend
     monkeypatch.setenv("B200EM_DS_DR", "3")
+    monkeypatch.setenv("B200EM_DS_TMA", tma)         # "0": the cp.async fallback of the tile loader
     N, D, H, W, Cin, Cout, k = case
     Bd = CudaBackend(use_ds=True)
     assert _lib.load().b200em_conv3d_umma_ds_supported(Cin, Cout, *k) and _lib.load().b200em_conv3d_umma_ds_supported(Cout, Cin, *k)
@@ -176,12 +178,14 @@ def test_umma_wgrad(B, case):
         np.testing.assert_allclose(db.cpu().numpy() + 1.0, db_ref.numpy(), rtol=2e-3, atol=2e-3 * float(db_ref.abs().max()))
 
 
+@pytest.mark.parametrize("tma", ["1", "0"])
 @pytest.mark.parametrize("dr", ["2", "5"])
-def test_wgrad_cs_many_items_per_cta(dr, monkeypatch):
+def test_wgrad_cs_many_items_per_cta(dr, tma, monkeypatch):
     """w-stacked weight gradient with short depth segments forced: several work items per CTA, the stage ring and its
     mirrored slots wrap many times; repeated launches must give the same answer."""
     from torch_em_b200.backend import CudaBackend
     monkeypatch.setenv("B200EM_CS_DR", dr)
+    monkeypatch.setenv("B200EM_CS_TMA", tma)         # "0": the cp.async fallback of the tile loader
     N, D, H, W, Cin, Cout, k = 2, 24, 48, 40, 64, 32, (3, 3, 3)
     Bc = CudaBackend(use_cs=True)
     x = rnd((N, D, H, W, Cin), 41).bfloat16()
