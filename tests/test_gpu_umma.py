@@ -45,6 +45,8 @@ CASES = [
     (1, 21, 16, 8, 32, 64, (3, 3, 1)),
     (1, 19, 20, 11, 16, 48, (3, 1, 3)),
     (1, 15, 16, 8, 16, 80, (3, 3, 3)),
+    (1, 11, 18, 12, 32, 48, (3, 3, 3)),
+    (2, 9, 16, 24, 48, 16, (3, 3, 3)),
 ]
 
 
