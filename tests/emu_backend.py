@@ -23,7 +23,7 @@ def _ncdhw(t):
 class TorchEmuBackend:
     name = "torch-emulation"
 
-    def pack(self, key, w):
+    def pack(self, key, w, lazy_dgrad=False):
         p = _Pack()
         p.w = w.detach()
         return p

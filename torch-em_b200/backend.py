@@ -49,7 +49,7 @@ def _f32(t):
 class WeightPack:
     """Kernel-operand copies of one conv weight (derived caches; the fp32 nn.Parameter stays the master)."""
     __slots__ = ("w_fwd_f32", "w_dgrad_f32", "umma_fwd", "umma_dgrad", "version", "ptr", "cout", "cin", "kernel", "thin",
-                 "thin_kp", "s3_fwd", "s3_dgrad", "ds_fwd", "ds_dgrad", "master")
+                 "thin_kp", "s3_fwd", "s3_dgrad", "ds_fwd", "ds_dgrad", "master", "dgrad_ready")
 
 
 class CudaBackend:
@@ -86,12 +86,17 @@ class CudaBackend:
         return r
 
     # ---- weights ---------------------------------------------------------------------------------------------
-    def pack(self, key, w):
+    def pack(self, key, w, lazy_dgrad=False):
+        """Operand images of one conv weight.  lazy_dgrad=True defers the data-gradient operands to the first dgrad call
+        (ensure_dgrad): the schedule then issues each pack right before the kernel that needs it instead of ~40 small
+        launches in front of the first conv of a step."""
         if w.device.type != "cuda":
             raise RuntimeError("b200em: parameters must live on a CUDA device (there is no CPU fallback for this path)")
         ver = (w.data_ptr(), w._version, tuple(w.shape), w.device)
         pk = self._pack_cache.get(key)
         if pk is not None and pk.version == ver:
+            if not lazy_dgrad:
+                self.ensure_dgrad(pk)
             return pk
         cout, cin, kd, kh, kw = w.shape
         wd = w.detach()
@@ -103,29 +108,20 @@ class CudaBackend:
         pk.master = wd
         pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.s3_fwd = pk.s3_dgrad = pk.ds_fwd = pk.ds_dgrad = None
         pk.thin_kp = 0
+        pk.dgrad_ready = False
         lib = _lib.load()
         with torch.cuda.device(w.device):
             # one packed operand per direction: the depth-stacked layout where that kernel takes the layer, else the plain one
             ds_f = self.use_ds and lib.b200em_conv3d_umma_ds_supported(cin, cout, kd, kh, kw)
-            ds_d = self.use_ds and lib.b200em_conv3d_umma_ds_supported(cout, cin, kd, kh, kw)
             if self.use_umma and not ds_f and lib.b200em_conv3d_umma_supported(cin, cout, kd, kh, kw):
                 pk.umma_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.umma_fwd), _stream(w))
-            if self.use_umma and not ds_d and lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
-                pk.umma_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
-                call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.umma_dgrad), _stream(w))
             if self.use_s3 and lib.b200em_conv3d_umma_s3_supported(cin, cout, kd, kh, kw):
                 pk.s3_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_s3_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.s3_fwd), _stream(w))
-            if self.use_s3 and lib.b200em_conv3d_umma_s3_supported(cout, cin, kd, kh, kw):
-                pk.s3_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
-                call("b200em_conv3d_umma_s3_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.s3_dgrad), _stream(w))
             if ds_f:
                 pk.ds_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
                 call("b200em_conv3d_umma_ds_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.ds_fwd), _stream(w))
-            if ds_d:
-                pk.ds_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
-                call("b200em_conv3d_umma_ds_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.ds_dgrad), _stream(w))
             kp = -(-taps * cin // 32) * 32
             first = self.use_ds and lib.b200em_conv3d_first_supported(cin, cout, kd, kh, kw)
             if self.use_umma and cin <= 4 and not first and lib.b200em_conv3d_umma_supported(kp, cout, 1, 1, 1):
@@ -136,7 +132,31 @@ class CudaBackend:
                 pk.thin_kp = kp
                 call("b200em_conv3d_umma_pack", _ptr(wt), cout, kp, 1, 1, 1, 0, _ptr(pk.thin), _stream(w))
         self._pack_cache[key] = pk
+        if not lazy_dgrad:
+            self.ensure_dgrad(pk)
         return pk
+
+    def ensure_dgrad(self, pk):
+        """Data-gradient operands (transposed, tap-flipped filter) of a pack, built on first use."""
+        if pk.dgrad_ready:
+            return
+        pk.dgrad_ready = True
+        cout, cin = pk.cout, pk.cin
+        kd, kh, kw = pk.kernel
+        taps = kd * kh * kw
+        wd = pk.master
+        lib = _lib.load()
+        with torch.cuda.device(wd.device):
+            ds_d = self.use_ds and lib.b200em_conv3d_umma_ds_supported(cout, cin, kd, kh, kw)
+            if self.use_umma and not ds_d and lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
+                pk.umma_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=wd.device)
+                call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.umma_dgrad), _stream(wd))
+            if self.use_s3 and lib.b200em_conv3d_umma_s3_supported(cout, cin, kd, kh, kw):
+                pk.s3_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=wd.device)
+                call("b200em_conv3d_umma_s3_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.s3_dgrad), _stream(wd))
+            if ds_d:
+                pk.ds_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=wd.device)
+                call("b200em_conv3d_umma_ds_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.ds_dgrad), _stream(wd))
 
     def f32_operands(self, pk):
         """fp32 (taps, Cin, Cout) / (taps, Cout, Cin) operands of the direct CUDA-core kernels, packed on first use."""
@@ -207,6 +227,8 @@ class CudaBackend:
         b = bias.detach() if bias is not None else None
         kd, kh, kw = kernel
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
+        if dgrad:
+            self.ensure_dgrad(pack)
         if (not dgrad) and self.use_ds and Cin == 1 and xld == 1 and x.dtype == torch.bfloat16 and yld % 8 == 0 and \
                 y.data_ptr() % 16 == 0 and dot_x is None and _lib.load().b200em_conv3d_first_supported(Cin, Cout, kd, kh, kw):
             # first conv of the network: im2col rows built on the fly in shared memory, straight from the fp32 parameter

@@ -125,6 +125,16 @@ def _device_ctx(device):
     return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
 
 
+class _LazyPacks:
+    """Mapping key -> WeightPack that packs on first access (see AnisotropicUNet._packs)."""
+
+    def __init__(self, model, B, P):
+        self._model_id, self._B, self._P = id(model), B, P
+
+    def __getitem__(self, key):
+        return self._B.pack((self._model_id, key), self._P[key + ".weight"], lazy_dgrad=True)
+
+
 class _UNetFunction(torch.autograd.Function):
     """The whole network as one autograd node: forward_pass / backward_pass are explicit kernel schedules."""
 
@@ -268,9 +278,10 @@ class AnisotropicUNet(nn.Module):
         return self._backend_override if self._backend_override is not None else default_backend()
 
     def _packs(self, B, P):
-        plan = self._plan
-        convs = [c for b in plan.enc + [plan.base] + plan.dec for c in (b.conv1, b.conv2)] + plan.samplers
-        return {c.key: B.pack((id(self), c.key), P[c.key + ".weight"]) for c in convs}
+        """Weight operand images, built on demand: each pack is issued right before the kernel that consumes it (forward
+        operand at the layer's forward conv, data-gradient operand at its dgrad) instead of ~40 small launches in front of
+        the first conv of every step (which leave the GPU idle whenever the host starts a step with an empty queue)."""
+        return _LazyPacks(self, B, P)
 
     def _activation_dtype(self, x):
         if self.compute_dtype is not None:
