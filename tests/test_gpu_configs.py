@@ -1,0 +1,165 @@
+"""End-to-end parity of the BASELINE.json *models* (configs[0..3]) on the code path that is benchmarked.
+
+The golden-vector nets of tests/test_gpu_unet.py are small (f = 4 / 8) and therefore run on the exact-fp32 CUDA-core
+kernels.  Here the real channel widths (32 ... 512) go through the tcgen05 kernels -- depth-stacked (ds), plain implicit
+GEMM, first conv, h-stacked (cs) and plain weight gradient -- in ONE graph, at spatial sizes the fp32 CPU oracle finishes in
+seconds, and the test asserts that each of those kernels really was launched.
+
+Yardstick for bf16 (there is no exact answer): the fp32 oracle on the CPU, and as the bar the error that the reference's
+OWN bf16 autocast (the same functional graph through cuDNN / ATen on this GPU) makes against it:
+  * prediction: relative L2 <= 2e-2 and <= 1.25 x the reference-autocast error (+1e-3)
+  * loss: within 1 % of the fp32 loss
+  * every parameter gradient: cosine similarity with the fp32 gradient >= 0.999, or (gradients that are differences of
+    large terms -- e.g. a conv bias in front of an InstanceNorm is exactly 0 in exact arithmetic) an absolute L2 error no
+    larger than 2 x the reference autocast's + 5e-3 of the largest gradient norm.
+fp32 (cfg1, exact CUDA-core path): rtol 1e-4 / atol 1e-4 on the prediction (the reference's own batched-vs-unbatched bound,
+test/util/test_prediction.py:358-382), gradients rtol 2e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+import torch_em_b200 as tb
+from oracle import dice as odice
+from oracle import labels as olabels
+from oracle import unet as ounet
+from torch_em_b200.backend import default_backend
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+CREMI_OFFSETS = [[-1, 0, 0], [0, -1, 0], [0, 0, -1], [-2, 0, 0], [0, -3, 0], [0, 0, -3],
+                 [-3, 0, 0], [0, -9, 0], [0, 0, -9], [-4, 0, 0], [0, -27, 0], [0, 0, -27]]
+
+
+def _rel(a, b):
+    return float((a.detach().float().cpu() - b.detach().float().cpu()).norm() / (b.detach().float().norm() + 1e-30))
+
+
+def _cos(a, b):
+    a, b = a.detach().float().cpu().flatten(), b.detach().float().cpu().flatten()
+    return float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _bf16_parity(net, sf, x, run_loss_ours, run_loss_oracle, norm="InstanceNorm", anisotropic_kernel=False,
+                 expect_kernels=()):
+    """net: our model on DEV; run_loss_*: callables (pred) -> loss for ours / for the oracle arms (cpu and cuda)."""
+    act = "Sigmoid"
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    y_ref = ounet.unet3d_forward(x, sd, sf, norm=norm, final_activation=act, anisotropic_kernel=anisotropic_kernel)
+    l_ref = run_loss_oracle(y_ref, "cpu")
+    l_ref.backward()
+    # the reference's arithmetic under its own bf16 autocast on this GPU (cuDNN / ATen)
+    sdg = {k: v.detach().to(DEV).clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y_ac = ounet.unet3d_forward(x.to(DEV), sdg, sf, norm=norm, final_activation=act, anisotropic_kernel=anisotropic_kernel)
+        run_loss_oracle(y_ac, DEV).backward()
+    B = default_backend()
+    B.calls.clear()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = net(x.to(DEV))
+        loss = run_loss_ours(y)
+    loss.backward()
+    torch.cuda.synchronize()
+    for k in expect_kernels:
+        assert B.calls.get(k, 0) > 0, (k, dict(B.calls))
+    assert not any(k.startswith("direct:") for k in B.calls), dict(B.calls)      # nothing fell to the CUDA-core path
+
+    e_y, e_ac = _rel(y, y_ref), _rel(y_ac, y_ref)
+    assert e_y < 2e-2, e_y
+    assert e_y <= 1.25 * e_ac + 1e-3, (e_y, e_ac)
+    assert abs(loss.item() - l_ref.item()) < 1e-2 * abs(l_ref.item()), (loss.item(), l_ref.item())
+    gmax = max(float(v.grad.norm()) for v in sd.values())
+    bad = []
+    for k, p in net.named_parameters():
+        g_ref = sd[k].grad
+        c = _cos(p.grad, g_ref)
+        e_ours = float((p.grad.detach().float().cpu() - g_ref).norm()) / gmax
+        e_refac = float((sdg[k].grad.detach().float().cpu() - g_ref).norm()) / gmax
+        if not (c >= 0.999 or e_ours <= 2.0 * e_refac + 5e-3):
+            bad.append((k, c, e_ours, e_refac))
+    assert not bad, bad
+    return dict(B.calls)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 64, 64, 64), (2, 1, 32, 32, 32)])
+def test_cfg2_model_bf16_vs_oracle(shape):
+    """configs[1]: UNet3d(1, 2, depth=4, initial_features=32, Sigmoid) + DiceLoss under bf16 autocast."""
+    torch.manual_seed(0)
+    net = tb.UNet3d(1, 2, depth=4, initial_features=32, final_activation="Sigmoid").to(DEV)
+    x = torch.randn(*shape)
+    t = (torch.rand(shape[0], 2, *shape[2:]) > 0.5).float()
+    calls = _bf16_parity(net, [2] * 4, x, lambda y: tb.DiceLoss()(y, t.to(DEV)), lambda y, dev: odice.dice_loss(y, t.to(dev)),
+                         expect_kernels=("first:fwd", "first:wgrad", "ds:fwd", "ds:dgrad", "plain:fwd", "plain:dgrad",
+                                         "cs:wgrad", "umma:wgrad"))
+    # 18 3x3x3 convs + 4 samplers forward; every conv except the first has a data gradient
+    assert sum(v for k, v in calls.items() if k.endswith(":fwd")) == 22
+    assert sum(v for k, v in calls.items() if k.endswith(":dgrad")) == 21
+    assert sum(v for k, v in calls.items() if k.endswith(":wgrad")) == 22
+
+
+@pytest.mark.parametrize("anisotropic_kernel", [False, True])
+def test_cfg3_model_bf16_vs_oracle(anisotropic_kernel):
+    """configs[2]: AnisotropicUNet(1, 12, [[1,2,2],[1,2,2],[2,2,2],[2,2,2]], f=32) with the 12 long-range offsets; the loss
+    is the reference's affinity idiom (cli.py:263-267): masked Dice on AffinityTransform(add_mask=True) targets -- ours
+    computes target and mask inside the loss kernels from the integer labels."""
+    torch.manual_seed(1)
+    sf = [[1, 2, 2], [1, 2, 2], [2, 2, 2], [2, 2, 2]]
+    shape = (1, 1, 16, 64, 64)
+    net = tb.AnisotropicUNet(1, 12, scale_factors=sf, initial_features=32, final_activation="Sigmoid",
+                             anisotropic_kernel=anisotropic_kernel).to(DEV)
+    x = torch.randn(*shape)
+    labels = olabels.synthetic_labels(shape[2:], n_seeds=30, zero_fraction=0.1, seed=3)
+    target = torch.from_numpy(olabels.affinity_targets(labels, CREMI_OFFSETS, ignore_label=0, add_mask=True))[None]
+    lab_t = torch.from_numpy(labels.astype("int64"))[None].to(DEV)
+    loss_fn = tb.AffinityLoss(CREMI_OFFSETS, ignore_label=0)
+    expect = ["first:fwd", "ds:fwd", "plain:fwd", "plain:dgrad", "umma:wgrad"] if not anisotropic_kernel else ["plain:fwd", "umma:wgrad"]
+    _bf16_parity(net, sf, x, lambda y: loss_fn(y, lab_t), lambda y, dev: odice.masked_dice_loss(y, target.to(dev)),
+                 anisotropic_kernel=anisotropic_kernel, expect_kernels=expect)
+
+
+def test_cfg2_groupnorm_model_bf16_vs_oracle():
+    """GroupNorm with 2 / 4 / 8 / 16 channels per group (64 ... 512 channels) through the tensor-core path."""
+    torch.manual_seed(2)
+    net = tb.UNet3d(1, 2, depth=4, initial_features=32, final_activation="Sigmoid", norm="GroupNorm").to(DEV)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if p.dim() == 1 and (".block.0." in k or ".block.3." in k):
+                p.add_(0.1 * torch.randn_like(p))
+    shape = (1, 1, 32, 32, 32)
+    x = torch.randn(*shape)
+    t = (torch.rand(1, 2, *shape[2:]) > 0.5).float()
+    _bf16_parity(net, [2] * 4, x, lambda y: tb.DiceLoss()(y, t.to(DEV)), lambda y, dev: odice.dice_loss(y, t.to(dev)),
+                 norm="GroupNorm", expect_kernels=("ds:fwd", "plain:fwd", "cs:wgrad"))
+
+
+def test_cfg1_model_fp32_vs_oracle():
+    """configs[0]: UNet3d(1, 2, depth=3, initial_features=16) forward + DiceLoss on one (1,1,64,64,64) volume, fp32."""
+    torch.manual_seed(0)
+    net = tb.UNet3d(1, 2, depth=3, initial_features=16, final_activation="Sigmoid").to(DEV)
+    x = torch.randn(1, 1, 64, 64, 64)
+    t = (torch.rand(1, 2, 64, 64, 64) > 0.5).float()
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    y_ref = ounet.unet3d_forward(x, sd, [2] * 3, final_activation="Sigmoid")
+    l_ref = odice.dice_loss(y_ref, t)
+    l_ref.backward()
+    y = net(x.to(DEV))
+    loss = tb.DiceLoss()(y, t.to(DEV))
+    loss.backward()
+    assert y.dtype == torch.float32
+    np.testing.assert_allclose(y.detach().cpu().numpy(), y_ref.detach().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(loss.item(), l_ref.item(), rtol=1e-4)
+    for k, p in net.named_parameters():
+        g = sd[k].grad.numpy()
+        np.testing.assert_allclose(p.grad.cpu().numpy(), g, rtol=2e-3, atol=2e-6 + 1e-4 * np.abs(g).max(), err_msg=k)
+
+
+def test_cfg4_model_shape_bf16_vs_oracle():
+    """configs[3] topology (depth 5) at half width: UNet3d(1, 2, depth=5, initial_features=32) on 32^3 -- five pooling
+    levels down to 1^3 at the base (1024 channels), where InstanceNorm over one voxel has zero variance."""
+    torch.manual_seed(4)
+    net = tb.UNet3d(1, 2, depth=5, initial_features=32, final_activation="Sigmoid").to(DEV)
+    shape = (1, 1, 32, 32, 32)
+    x = torch.randn(*shape)
+    t = (torch.rand(1, 2, *shape[2:]) > 0.5).float()
+    _bf16_parity(net, [2] * 5, x, lambda y: tb.DiceLoss()(y, t.to(DEV)), lambda y, dev: odice.dice_loss(y, t.to(dev)),
+                 expect_kernels=("plain:fwd", "umma:wgrad"))

@@ -3,6 +3,7 @@
 Each method takes torch tensors only to read ``data_ptr()``, shapes and the channel pitch; the arithmetic is in the
 library.  There is no CPU or PyTorch fallback: tensors that are not on a CUDA device raise.
 """
+import collections
 import ctypes
 
 import torch
@@ -62,6 +63,7 @@ class CudaBackend:
         self.use_cs = use_cs and use_umma
         self._pack_cache = {}
         self.timing = None          # {family: [(start_event, end_event, work), ...]} while bench.py measures
+        self.calls = collections.Counter()   # conv launches per "<kernel>:<direction>" (tests assert which kernels ran)
 
     # ---- per-kernel timing (bench.py roofline leg) -----------------------------------------------------------
     def start_timing(self):
@@ -76,6 +78,7 @@ class CudaBackend:
         return out
 
     def _timed(self, family, work, fn):
+        self.calls[family] += 1
         if self.timing is None:
             return fn()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -232,14 +235,14 @@ class CudaBackend:
         if (not dgrad) and self.use_ds and Cin == 1 and xld == 1 and x.dtype == torch.bfloat16 and yld % 8 == 0 and \
                 y.data_ptr() % 16 == 0 and dot_x is None and _lib.load().b200em_conv3d_first_supported(Cin, Cout, kd, kh, kw):
             # first conv of the network: im2col rows built on the fly in shared memory, straight from the fp32 parameter
-            self._timed("conv_umma_fwd", flops, lambda: call(
+            self._timed("first:fwd", flops, lambda: call(
                 "b200em_conv3d_first", xp, _f32(in_ss), _f32(pack.master), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cout,
                 int(relu), _stream(x)))
             return None
         if (not dgrad) and pack.thin is not None and x.dtype == torch.bfloat16 and yld % 8 == 0 and y.data_ptr() % 16 == 0:
             cols = self.im2col(x, in_ss, kernel, pack.thin_kp)
             assert dot_x is None
-            self._timed("conv_umma_fwd", flops, lambda: call(
+            self._timed("thin:fwd", flops, lambda: call(
                 "b200em_conv3d_umma", _ptr(cols), pack.thin_kp, None, _ptr(pack.thin), _f32(b), yp, yld, _f32(sums), None, 0, N, D, H,
                 W, pack.thin_kp, Cout, 1, 1, 1, int(relu), _stream(x)))
             return cols       # kept by the schedule for the weight gradient of the same conv
@@ -248,13 +251,13 @@ class CudaBackend:
         if wds is not None and ok16:
             dp, dld = _act(dot_x) if dot_x is not None else (None, 0)
             if dot_x is None or (dld % 8 == 0 and dot_x.data_ptr() % 16 == 0):
-                self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
+                self._timed("ds:dgrad" if dgrad else "ds:fwd", flops, lambda: call(
                     "b200em_conv3d_umma_ds", xp, xld, _f32(in_ss), _ptr(wds), _f32(b), yp, yld, _f32(sums), dp, dld, N, D, H, W,
                     Cin, Cout, kd, kh, kw, int(relu), _stream(x)))
                 return None
         ws3 = pack.s3_dgrad if dgrad else pack.s3_fwd
         if ws3 is not None and ok16 and dot_x is None:
-            self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
+            self._timed("s3:dgrad" if dgrad else "s3:fwd", flops, lambda: call(
                 "b200em_conv3d_umma_s3", xp, xld, _f32(in_ss), _ptr(ws3), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cin, Cout,
                 kd, kh, kw, int(relu), _stream(x)))
             return None
@@ -263,12 +266,12 @@ class CudaBackend:
                 x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
             dp, dld = _act(dot_x) if dot_x is not None else (None, 0)
             if dot_x is None or (dld % 8 == 0 and dot_x.data_ptr() % 16 == 0):
-                self._timed("conv_umma_dgrad" if dgrad else "conv_umma_fwd", flops, lambda: call(
+                self._timed("plain:dgrad" if dgrad else "plain:fwd", flops, lambda: call(
                     "b200em_conv3d_umma", xp, xld, _f32(in_ss), _ptr(wu), _f32(b), yp, yld, _f32(sums), dp, dld, N, D, H, W, Cin,
                     Cout, kd, kh, kw, int(relu), _stream(x)))
                 return None
         w = self.f32_operands(pack)[1 if dgrad else 0]
-        self._timed("conv_direct_dgrad" if dgrad else "conv_direct_fwd", flops, lambda: call(
+        self._timed("direct:dgrad" if dgrad else "direct:fwd", flops, lambda: call(
             "b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, None if dot_x is not None else _f32(sums),
             _dt(x), N, D, H, W, Cin, Cout, kd, kh, kw, int(relu), _stream(x)))
         if dot_x is not None:
@@ -297,36 +300,36 @@ class CudaBackend:
         kp = -(-taps * Cin // 32) * 32
         if self.use_umma and self.use_ds and Cin == 1 and xld == 1 and x.dtype == torch.bfloat16 and zld % 8 == 0 and \
                 dz.data_ptr() % 16 == 0 and _lib.load().b200em_conv3d_first_supported(Cin, Cout, kd, kh, kw):
-            self._timed("conv_umma_wgrad", flops, lambda: call(
+            self._timed("first:wgrad", flops, lambda: call(
                 "b200em_conv3d_first_wgrad", xp, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cout, _stream(x)))
             return
         if self.use_umma and Cin <= 4 and x.dtype == torch.bfloat16 and zld % 8 == 0 and dz.data_ptr() % 16 == 0 and \
                 _lib.load().b200em_conv3d_wgrad_umma_supported(kp, Cout, 1, 1, 1):
             cols = aux if aux is not None else self.im2col(x, in_ss, kernel, kp)
             dwt = torch.zeros((Cout, kp), dtype=torch.float32, device=x.device)
-            self._timed("conv_umma_wgrad", flops, lambda: call(
+            self._timed("thin:wgrad", flops, lambda: call(
                 "b200em_conv3d_wgrad_umma", _ptr(cols), kp, None, zp, zld, _f32(dwt), _f32(db), N, D, H, W, kp, Cout, 1, 1, 1,
                 _stream(x)))
             dw += dwt[:, :taps * Cin].reshape(Cout, taps, Cin).permute(0, 2, 1).reshape(dw.shape)
             return
         ok16 = x.dtype == torch.bfloat16 and xld % 8 == 0 and zld % 8 == 0 and x.data_ptr() % 16 == 0 and dz.data_ptr() % 16 == 0
         if self.use_umma and self.use_cs and ok16 and _lib.load().b200em_conv3d_wgrad_cs_supported(Cin, Cout, kd, kh, kw):
-            self._timed("conv_umma_wgrad", flops, lambda: call(
+            self._timed("cs:wgrad", flops, lambda: call(
                 "b200em_conv3d_wgrad_cs", xp, xld, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cin, Cout, kd, kh,
                 kw, _stream(x)))
             return
         if self.use_umma and x.dtype == torch.bfloat16 and xld % 8 == 0 and zld % 8 == 0 and x.data_ptr() % 16 == 0 and \
                 dz.data_ptr() % 16 == 0 and _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw):
-            self._timed("conv_umma_wgrad", flops, lambda: call(
+            self._timed("umma:wgrad", flops, lambda: call(
                 "b200em_conv3d_wgrad_umma", xp, xld, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cin, Cout, kd, kh,
                 kw, _stream(x)))
             return
         if Cin <= 4:
-            self._timed("conv_smallcin_wgrad", flops, lambda: call(
+            self._timed("smallcin:wgrad", flops, lambda: call(
                 "b200em_conv3d_wgrad_smallcin", xp, xld, _f32(in_ss), zp, zld, _dt(x), _f32(dw), _f32(db), N, D, H, W, Cin, Cout,
                 kd, kh, kw, _stream(x)))
             return
-        self._timed("conv_direct_wgrad", flops, lambda: call(
+        self._timed("direct:wgrad", flops, lambda: call(
             "b200em_conv3d_wgrad_direct", xp, xld, _f32(in_ss), zp, zld, _dt(x), _f32(dw), N, D, H, W, Cin, Cout, kd, kh, kw,
             _stream(x)))
         if db is not None:

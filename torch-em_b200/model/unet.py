@@ -295,8 +295,13 @@ class AnisotropicUNet(nn.Module):
             return dt
         return torch.float32
 
+    @torch.compiler.disable
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """(N, in_channels, D, H, W) -> (N, out_channels, D, H, W) fp32 (unet.py:237-253)."""
+        """(N, in_channels, D, H, W) -> (N, out_channels, D, H, W) fp32 (unet.py:237-253).
+
+        Opted out of Dynamo tracing: ``DefaultTrainer`` wraps the model in ``torch.compile`` by default
+        (default_trainer.py:541, util/util.py:38-74); the network already is one hand-scheduled autograd node, so the
+        compiled wrapper simply calls this method eagerly."""
         if getattr(self, "check_shape", True):
             self._check_shape(x)
         params = [p for _, p in self.named_parameters()]
