@@ -53,6 +53,11 @@ def unet_case(ref_unet, ref_dice, name, ctor, kwargs, shape, seed):
 
 
 def main():
+    only = sys.argv[1:]                      # optional: names of the U-Net cases to (re)generate
+    global unet_case
+    if only:
+        _all = unet_case
+        unet_case = lambda a, b, name, *r: _all(a, b, name, *r) if name in only else None
     torch.set_num_threads(4)
     ref_unet = _load("ref_unet", "model/unet.py")
     ref_dice = _load("ref_dice", "loss/dice.py")
@@ -65,6 +70,12 @@ def main():
               dict(in_channels=2, out_channels=3, depth=2, initial_features=8, final_activation="Sigmoid",
                    norm="GroupNorm"),
               (1, 2, 8, 16, 16), 1)
+    # GroupNorm with MORE than one channel per group: GroupNorm(min(32, C), C) has 2 channels per group at 64 channels
+    # (base block and the decoder block's first norm); batch 2 pins the per-sample statistics
+    unet_case(ref_unet, ref_dice, "unet3d_d1_f32_groupnorm", "UNet3d",
+              dict(in_channels=1, out_channels=2, depth=1, initial_features=32, final_activation="Sigmoid",
+                   norm="GroupNorm"),
+              (2, 1, 8, 16, 16), 6)
     unet_case(ref_unet, ref_dice, "unet3d_d1_f4_nonorm", "UNet3d",
               dict(in_channels=1, out_channels=1, depth=1, initial_features=4, final_activation=None, norm=None),
               (1, 1, 8, 8, 8), 2)
@@ -77,6 +88,8 @@ def main():
                    final_activation="Sigmoid", anisotropic_kernel=False),
               (1, 1, 4, 16, 16), 4)
 
+    if only:
+        return
     # Dice + masked Dice (LossWrapper(DiceLoss(), ApplyAndRemoveMask("multiply"))) with gradients
     torch.manual_seed(5)
     p = torch.rand(2, 3, 4, 8, 8, requires_grad=True)

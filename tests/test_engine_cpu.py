@@ -17,6 +17,8 @@ CASES = {
                                              final_activation="Sigmoid")),
     "unet3d_d2_f8_groupnorm": ("UNet3d", dict(in_channels=2, out_channels=3, depth=2, initial_features=8,
                                               final_activation="Sigmoid", norm="GroupNorm")),
+    "unet3d_d1_f32_groupnorm": ("UNet3d", dict(in_channels=1, out_channels=2, depth=1, initial_features=32,
+                                               final_activation="Sigmoid", norm="GroupNorm")),
     "unet3d_d1_f4_nonorm": ("UNet3d", dict(in_channels=1, out_channels=1, depth=1, initial_features=4,
                                            final_activation=None, norm=None)),
     "aniso_f4_anisokernel": ("AnisotropicUNet", dict(in_channels=1, out_channels=3,

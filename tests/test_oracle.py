@@ -12,6 +12,7 @@ from oracle import unet as ounet
 UNET_CASES = {
     "unet3d_d2_f4_instnorm": dict(scale_factors=[2, 2], norm="InstanceNorm", final_activation="Sigmoid"),
     "unet3d_d2_f8_groupnorm": dict(scale_factors=[2, 2], norm="GroupNorm", final_activation="Sigmoid"),
+    "unet3d_d1_f32_groupnorm": dict(scale_factors=[2], norm="GroupNorm", final_activation="Sigmoid"),
     "unet3d_d1_f4_nonorm": dict(scale_factors=[2], norm=None, final_activation=None),
     "aniso_f4_anisokernel": dict(scale_factors=[[1, 2, 2], [2, 2, 2]], norm="InstanceNorm",
                                  final_activation="Sigmoid", anisotropic_kernel=True),
