@@ -42,6 +42,26 @@ class SyntheticPatches(torch.utils.data.Dataset):
         return self.raw[i], self.labels[i]
 
 
+LOSS_LOG = []
+
+
+class RecordingDiceLoss(tb.DiceLoss):
+    """Module-level (the trainer pickles the loss by dotted class path into the checkpoint)."""
+
+    def forward(self, p, t):
+        v = super().forward(p, t)
+        LOSS_LOG.append(float(v.detach()))
+        return v
+
+
+if torch_em is not None:
+    class RecordingRefDiceLoss(torch_em.loss.DiceLoss):
+        def forward(self, p, t):
+            v = super().forward(p, t)
+            LOSS_LOG.append(float(v.detach()))
+            return v
+
+
 def _loaders():
     from torch_em.segmentation import get_data_loader
     ds = SyntheticPatches()
@@ -129,18 +149,11 @@ def test_real_trainer_default_compile_setting_cpu(tmp_path, monkeypatch):
 @pytest.mark.parametrize("compile_model", [False, None])
 def test_real_trainer_gpu_bf16(tmp_path, compile_model):
     dev = "cuda:0"
-    loss_vals = []
-    loss = tb.DiceLoss()
-
-    class Recording(tb.DiceLoss):
-        def forward(self, p, t):
-            v = super().forward(p, t)
-            loss_vals.append(float(v.detach()))
-            return v
-
+    LOSS_LOG.clear()
     tb.reset_launch_count()
-    trainer, folder = _run_trainer(tmp_path, dev, Recording(), loss, compile_model=compile_model, mixed_precision=True,
-                                   mixed_precision_dtype="bfloat16")
+    trainer, folder = _run_trainer(tmp_path, dev, RecordingDiceLoss(), tb.DiceLoss(), compile_model=compile_model,
+                                   mixed_precision=True, mixed_precision_dtype="bfloat16")
+    loss_vals = list(LOSS_LOG)
     assert tb.launch_count() > 100, "the CUDA kernels of libb200em did not run"
     assert not trainer.scaler.is_enabled()
     assert loss_vals[-1] < loss_vals[0], loss_vals
@@ -162,16 +175,10 @@ def test_real_trainer_gpu_fp32_matches_reference_model_trajectory(tmp_path):
         if flavour == "reference":
             model = RefUNet3d(**MODEL_KW)
             model.load_state_dict(ours.state_dict())
-            base_loss = torch_em.loss.DiceLoss
+            base_loss, rec_loss = torch_em.loss.DiceLoss, RecordingRefDiceLoss
         else:
-            model, base_loss = ours, tb.DiceLoss
-        vals = []
-
-        class Recording(base_loss):
-            def forward(self, p, t):
-                v = super().forward(p, t)
-                vals.append(float(v.detach()))
-                return v
+            model, base_loss, rec_loss = ours, tb.DiceLoss, RecordingDiceLoss
+        LOSS_LOG.clear()
 
         torch.manual_seed(1)
         ds = SyntheticPatches()
@@ -181,10 +188,10 @@ def test_real_trainer_gpu_fp32_matches_reference_model_trajectory(tmp_path):
         torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
         try:
             trainer = torch_em.default_segmentation_trainer(
-                name=f"traj_{flavour}", model=model, train_loader=train, val_loader=train, loss=Recording(), metric=base_loss(),
+                name=f"traj_{flavour}", model=model, train_loader=train, val_loader=train, loss=rec_loss(), metric=base_loss(),
                 device=dev, logger=None, compile_model=False, mixed_precision=False, save_root=str(tmp_path))
             trainer.fit(iterations=10)
         finally:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
-        curves.append(list(vals))
+        curves.append(list(LOSS_LOG))
     np.testing.assert_allclose(curves[1], curves[0], rtol=2e-3)

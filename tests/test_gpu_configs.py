@@ -62,7 +62,10 @@ def _bf16_parity(net, sf, x, run_loss_ours, run_loss_oracle, norm="InstanceNorm"
     torch.cuda.synchronize()
     for k in expect_kernels:
         assert B.calls.get(k, 0) > 0, (k, dict(B.calls))
-    assert not any(k.startswith("direct:") for k in B.calls), dict(B.calls)      # nothing fell to the CUDA-core path
+    # nothing falls to the CUDA-core path -- except the data gradient INTO the 1-channel network input, which only GroupNorm
+    # needs (for the first norm's gamma / beta)
+    direct = {k: v for k, v in B.calls.items() if k.startswith("direct:")}
+    assert direct == ({"direct:dgrad": 1} if norm == "GroupNorm" else {}), dict(B.calls)
 
     e_y, e_ac = _rel(y, y_ref), _rel(y_ac, y_ref)
     assert e_y < 2e-2, e_y
@@ -133,32 +136,56 @@ def test_cfg2_groupnorm_model_bf16_vs_oracle():
 
 
 def test_cfg1_model_fp32_vs_oracle():
-    """configs[0]: UNet3d(1, 2, depth=3, initial_features=16) forward + DiceLoss on one (1,1,64,64,64) volume, fp32."""
+    """configs[0]: UNet3d(1, 2, depth=3, initial_features=16) forward + DiceLoss on one (1,1,64,64,64) volume, fp32.
+
+    Truth is the oracle in float64.  The prediction and the loss are held to the reference's own bound (rtol 1e-4 / atol 1e-4).
+    For the gradients fp32 arithmetic itself is noisy at this size (random targets behind InstanceNorm make every weight
+    gradient a small difference of large terms: the fp32 CPU oracle AND the same graph in fp32 on the GPU through cuDNN are
+    each off by 1e-3 .. 1e-2 of a tensor's largest entry against float64, scripts/diag_fp32.py), so the bar per parameter
+    tensor is relative to that noise: our L2 error against float64 <= 4 x the larger of the two fp32 references' L2 errors
+    + 1e-3 of the tensor's norm."""
     torch.manual_seed(0)
     net = tb.UNet3d(1, 2, depth=3, initial_features=16, final_activation="Sigmoid").to(DEV)
     x = torch.randn(1, 1, 64, 64, 64)
     t = (torch.rand(1, 2, 64, 64, 64) > 0.5).float()
-    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
-    y_ref = ounet.unet3d_forward(x, sd, [2] * 3, final_activation="Sigmoid")
-    l_ref = odice.dice_loss(y_ref, t)
-    l_ref.backward()
+
+    def oracle(dtype, dev="cpu"):
+        sd = {k: v.detach().to(dev).to(dtype).clone().requires_grad_(True) for k, v in net.state_dict().items()}
+        y_ = ounet.unet3d_forward(x.to(dev).to(dtype), sd, [2] * 3, final_activation="Sigmoid")
+        l_ = odice.dice_loss(y_, t.to(dev).to(dtype))
+        l_.backward()
+        return y_.detach().cpu(), l_.item(), {k: v.grad.cpu() for k, v in sd.items()}
+
+    y64, l64, g64 = oracle(torch.float64)
+    y32, l32, g32 = oracle(torch.float32)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        _, _, g32g = oracle(torch.float32, DEV)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     y = net(x.to(DEV))
     loss = tb.DiceLoss()(y, t.to(DEV))
     loss.backward()
     assert y.dtype == torch.float32
-    np.testing.assert_allclose(y.detach().cpu().numpy(), y_ref.detach().numpy(), rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(loss.item(), l_ref.item(), rtol=1e-4)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), y64.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(loss.item(), l64, rtol=1e-4)
     for k, p in net.named_parameters():
-        g = sd[k].grad.numpy()
-        np.testing.assert_allclose(p.grad.cpu().numpy(), g, rtol=2e-3, atol=2e-6 + 1e-4 * np.abs(g).max(), err_msg=k)
+        truth = g64[k]
+        e_ours = float((p.grad.cpu().double() - truth).norm())
+        e_ref = max(float((g32[k].double() - truth).norm()), float((g32g[k].double() - truth).norm()))
+        assert e_ours <= 4.0 * e_ref + 1e-3 * float(truth.norm()) + 1e-12, (k, e_ours, e_ref, float(truth.norm()))
 
 
 def test_cfg4_model_shape_bf16_vs_oracle():
     """configs[3] topology (depth 5) at half width: UNet3d(1, 2, depth=5, initial_features=32) on 32^3 -- five pooling
-    levels down to 1^3 at the base (1024 channels), where InstanceNorm over one voxel has zero variance."""
+    levels down to 2^3 at the base (1024 channels).  (1^3 at the base is refused like the reference: InstanceNorm3d raises
+    "Expected more than 1 spatial element when training".)"""
     torch.manual_seed(4)
     net = tb.UNet3d(1, 2, depth=5, initial_features=32, final_activation="Sigmoid").to(DEV)
-    shape = (1, 1, 32, 32, 32)
+    with pytest.raises(ValueError, match="more than 1 spatial element"):
+        net(torch.zeros(1, 1, 32, 32, 32, device=DEV))
+    shape = (1, 1, 64, 64, 64)
     x = torch.randn(*shape)
     t = (torch.rand(1, 2, *shape[2:]) > 0.5).float()
     _bf16_parity(net, [2] * 5, x, lambda y: tb.DiceLoss()(y, t.to(DEV)), lambda y, dev: odice.dice_loss(y, t.to(dev)),

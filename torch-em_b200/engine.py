@@ -142,6 +142,10 @@ def _run_block(B, plan, P, spec: BlockSpec, x_in, sums_in, out, want_out_sums, c
     rec = {"x_in": x_in}
     ss1 = mr1 = ss2 = mr2 = None
     c1, c2 = spec.conv1, spec.conv2
+    if norm == "InstanceNorm" and S == 1:
+        # F.instance_norm refuses a single spatial element when it uses the input statistics (torch/nn/functional.py
+        # _verify_spatial_size) -- nn.InstanceNorm3d without running stats always does, also in eval mode
+        raise ValueError(f"Expected more than 1 spatial element when training, got input size {(N, c1.cin, D, H, W)}")
     if norm is not None:
         g1 = P[spec.norm1_key + ".weight"] if spec.norm1_key else None
         b1 = P[spec.norm1_key + ".bias"] if spec.norm1_key else None
