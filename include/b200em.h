@@ -91,16 +91,6 @@ int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift,
                        void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
                        int Cout, int kd, int kh, int kw, int relu, void* stream);
 
-/* "w-stacked" tcgen05 variant for layers with few output channels (Cout <= 80, kw == 3): the three w-taps share one
- * operand fetch (N = 3*Cout), shifted sum in the epilogue (csrc/conv_umma_s3.cu).  Same contract and arguments as
- * b200em_conv3d_umma; its own packed weight layout (b200em_conv3d_umma_s3_pack, Cout*Cin*taps bf16). */
-int b200em_conv3d_umma_s3_supported(int Cin, int Cout, int kd, int kh, int kw);
-int b200em_conv3d_umma_s3_pack(const float* w, int Cout, int Cin, int kd, int kh, int kw, int dgrad, void* packed,
-                               void* stream);
-int b200em_conv3d_umma_s3(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
-                          void* y, int64_t y_ld, float* sums, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
-                          int kw, int relu, void* stream);
-
 /* "depth-stacked" tcgen05 variant for 3 x kh x kw filters with few output channels (Cout <= 80) whose packed filter
  * fits in shared memory: the three depth taps share one operand fetch (N = 3*Cout) and land in the accumulators of
  * three consecutive output slices (a ring of TMEM column blocks); every input slice is staged once per column of
@@ -113,6 +103,25 @@ int b200em_conv3d_umma_ds_pack(const float* w, int Cout, int Cin, int kd, int kh
 int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
                           void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W,
                           int Cin, int Cout, int kd, int kh, int kw, int relu, void* stream);
+
+/* Batched packing: the bf16 operand images of EVERY conv weight of a model in one launch (csrc/pack.cu).  The fp32
+ * nn.Parameter (unet.py:431,435,453) stays the master; the images are rebuilt at the start of every forward / backward pass,
+ * so no in-place parameter update can leave a stale operand behind.  The caller fills w, packed (Cout*Cin*taps bf16, 16-byte
+ * aligned), the filter shape, dgrad and layout of each job; b200em_pack_batch_prepare (host) validates them and fills the
+ * derived fields; the table is then copied to the device once and b200em_pack_batch launches over it. */
+#define B200EM_PACK_PLAIN 0          /* operand of b200em_conv3d_umma */
+#define B200EM_PACK_DEPTH_STACKED 1  /* operand of b200em_conv3d_umma_ds */
+typedef struct b200em_pack_job {
+    const float* w;    /* torch (Cout, Cin, kd, kh, kw) fp32, device */
+    void* packed;      /* bf16 operand image, device */
+    int32_t Cout, Cin, kd, kh, kw;
+    int32_t dgrad;     /* 1: transposed, tap-flipped operand (data gradient) */
+    int32_t layout;    /* B200EM_PACK_* */
+    int32_t CC, NPb, block_begin;   /* filled by b200em_pack_batch_prepare */
+    int32_t reserved[2];
+} b200em_pack_job;     /* 64 bytes */
+int b200em_pack_batch_prepare(b200em_pack_job* jobs, int njobs, int* total_blocks);
+int b200em_pack_batch(const b200em_pack_job* jobs_device, int njobs, int total_blocks, void* stream);
 
 /* First convolution of the network (Cin = 1, 3x3x3, Cout in {16,32,48,64}; unet.py:412-438 first block): the im2col rows
  * (K = 27 padded to 32) are built on the fly in shared memory and fed to tcgen05.mma; same fused prologue (norm apply on

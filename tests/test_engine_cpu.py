@@ -109,3 +109,22 @@ def test_eval_no_grad_keeps_nothing(golden_dir):
         y = net(torch.from_numpy(z["x"]))
     assert not y.requires_grad
     np.testing.assert_allclose(y.numpy(), z["y"], rtol=1e-4, atol=1e-5)
+
+
+def test_autograd_contract(golden_dir):
+    """(1) no silent None gradient for an input that requires grad, (2) an accurate error on a second backward,
+    (3) an in-place edit of the returned prediction is caught by autograd's version check (the head's backward reads it)."""
+    z, net = build(golden_dir, "unet3d_d2_f4_instnorm")
+    net._backend_override = TorchEmuBackend()
+    x = torch.from_numpy(z["x"])
+    with pytest.raises(NotImplementedError, match="gradient w.r.t. its input"):
+        net(x.clone().requires_grad_(True))
+    y = net(x)
+    loss = y.sum()
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second backward"):
+        loss.backward()
+    y = net(x)
+    y.clamp_(0.1, 0.9)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        y.sum().backward()

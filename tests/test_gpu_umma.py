@@ -17,14 +17,13 @@ class P:
         self.w = w
 
 
-@pytest.fixture(scope="module", params=["dstacked", "stacked", "plain"])
+@pytest.fixture(scope="module", params=["dstacked", "plain"])
 def B(request):
-    """The tensor-core conv variants: depth-stacked (conv_umma_ds.cu, Cout <= 80 with a resident filter), w-stacked
-    (conv_umma_s3.cu, Cout <= 80) and the plain one."""
+    """The tensor-core conv variants: depth-stacked (conv_umma_ds.cu, Cout <= 80 with a resident filter) and the plain one."""
     from torch_em_b200 import _lib
     from torch_em_b200.backend import CudaBackend
     _lib.load()
-    return CudaBackend(use_s3=request.param == "stacked", use_ds=request.param == "dstacked", use_cs=request.param == "dstacked")
+    return CudaBackend(use_ds=request.param == "dstacked", use_cs=request.param == "dstacked")
 
 
 CASES = [
@@ -68,8 +67,6 @@ def test_umma_conv_forward_and_dgrad(B, case):
     pk = B.pack(("umma-test", case), w.to(DEV))
     assert pk.umma_fwd is not None or pk.ds_fwd is not None
     assert pk.umma_dgrad is not None or pk.ds_dgrad is not None
-    if B.use_s3 and _lib.load().b200em_conv3d_umma_s3_supported(Cin, Cout, *k):
-        assert pk.s3_fwd is not None
     if B.use_ds and _lib.load().b200em_conv3d_umma_ds_supported(Cin, Cout, *k):
         assert pk.ds_fwd is not None
     for in_ss, relu, bias in ((None, False, None), (ss, True, b)):

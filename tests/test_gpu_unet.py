@@ -117,3 +117,43 @@ def test_train_steps_reduce_loss_and_match_oracle_trajectory():
         ref.append(lr.item())
     assert ours[-1] < ours[0]
     np.testing.assert_allclose(ours, ref, rtol=2e-3)
+
+
+def test_weight_update_through_data_is_seen():
+    """In-place parameter updates that do not bump the tensor version (``p.data.mul_()``: EMA, clamping, old-style
+    optimizers) must reach the packed bf16 operand images: they are rebuilt at the start of every pass."""
+    torch.manual_seed(0)
+    net = tb.UNet3d(1, 2, depth=2, initial_features=32, final_activation="Sigmoid").to(DEV)
+    x = torch.randn(1, 1, 16, 16, 16, device=DEV)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y0 = net(x).clone()
+        v0 = [p._version for p in net.parameters()]
+        for p in net.parameters():
+            p.data.mul_(0.5)                                   # invisible to p._version
+        assert [p._version for p in net.parameters()] == v0
+        y1 = net(x).clone()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    y_ref = ounet.unet3d_forward(x.cpu(), sd, [2, 2], final_activation="Sigmoid")
+    assert float((y1 - y0).abs().max()) > 1e-3                   # the output moved ...
+    assert float((y1.cpu() - y_ref).norm() / y_ref.norm()) < 2e-2   # ... to where the NEW weights put it
+
+
+def test_replica_on_moved_storage():
+    """``model.to()`` / ``load_state_dict`` / ``copy.deepcopy`` (predict_with_halo, prediction.py:188-192): the pack set
+    follows the parameters' storage and is not shared between copies."""
+    import copy
+    torch.manual_seed(0)
+    net = tb.UNet3d(1, 2, depth=2, initial_features=32, final_activation="Sigmoid").to(DEV)
+    x = torch.randn(1, 1, 16, 16, 16, device=DEV)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y0 = net(x).clone()
+        twin = copy.deepcopy(net)
+        assert "_pack_store" not in twin.__dict__
+        for p in twin.parameters():
+            p.data.zero_()
+        yt = twin(x).clone()
+        y1 = net(x).clone()
+        net.cpu().to(DEV)                                       # new storage, same values
+        y2 = net(x).clone()
+    assert float((y1 - y0).abs().max()) < 1e-2 and float((y2 - y0).abs().max()) < 1e-2     # (fp32 atomics in the statistics)
+    assert float((yt - 0.5).abs().max()) < 1e-6                   # all-zero weights: sigmoid(0)

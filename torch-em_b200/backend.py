@@ -48,20 +48,149 @@ def _f32(t):
 
 
 class WeightPack:
-    """Kernel-operand copies of one conv weight (derived caches; the fp32 nn.Parameter stays the master)."""
-    __slots__ = ("w_fwd_f32", "w_dgrad_f32", "umma_fwd", "umma_dgrad", "version", "ptr", "cout", "cin", "kernel", "thin",
-                 "thin_kp", "s3_fwd", "s3_dgrad", "ds_fwd", "ds_dgrad", "master", "dgrad_ready")
+    """Kernel-operand copies of one conv weight (derived data; the fp32 nn.Parameter stays the master)."""
+    __slots__ = ("w_fwd_f32", "w_dgrad_f32", "f32_stale", "umma_fwd", "umma_dgrad", "cout", "cin", "kernel", "thin", "thin_kp",
+                 "ds_fwd", "ds_dgrad", "master")
+
+
+class _PackJob(ctypes.Structure):
+    """struct b200em_pack_job of include/b200em.h (64 bytes)."""
+    _fields_ = [("w", ctypes.c_void_p), ("packed", ctypes.c_void_p),
+                ("Cout", ctypes.c_int32), ("Cin", ctypes.c_int32), ("kd", ctypes.c_int32), ("kh", ctypes.c_int32),
+                ("kw", ctypes.c_int32), ("dgrad", ctypes.c_int32), ("layout", ctypes.c_int32),
+                ("CC", ctypes.c_int32), ("NPb", ctypes.c_int32), ("block_begin", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 2)]
+
+
+PACK_PLAIN, PACK_DEPTH_STACKED = 0, 1
+
+
+class PackSet:
+    """The operand images of ALL conv weights of one model on one device, rebuilt by ONE launch per direction.
+
+    ``refresh_fwd()`` runs at the start of every forward pass, ``refresh_dgrad()`` at the start of every backward pass
+    (csrc/pack.cu).  Rebuilding unconditionally instead of caching by ``tensor._version`` means that in-place updates the
+    version counter does not see (``p.data.mul_()``, EMA, old-style optimizers, ``load_state_dict``) can never leave a stale
+    operand behind.  The job table lives on the device and is rebuilt only when a parameter's storage moves.
+    The set is owned by the model (``model._pack_store``), so it dies with it."""
+
+    def __init__(self, backend, weights):
+        self.B = backend
+        self.sig = None
+        self.packs = {}
+        self._build(weights)
+
+    @staticmethod
+    def signature(weights):
+        return tuple((k, w.data_ptr(), tuple(w.shape), str(w.device)) for k, w in weights.items())
+
+    def _build(self, weights):
+        lib = _lib.load()
+        B = self.B
+        self.sig = self.signature(weights)
+        self.packs = {}
+        self.device = None
+        plan = {0: [], 1: []}                         # direction -> [(pack, attr, layout, elems)]
+        for key, w in weights.items():
+            if w.device.type != "cuda":
+                raise RuntimeError("b200em: parameters must live on a CUDA device (there is no CPU fallback for this path)")
+            self.device = w.device
+            cout, cin, kd, kh, kw = w.shape
+            wd = w.detach()
+            assert wd.dtype == torch.float32 and wd.is_contiguous()
+            pk = WeightPack()
+            pk.cout, pk.cin, pk.kernel, pk.master = cout, cin, (kd, kh, kw), wd
+            pk.w_fwd_f32 = pk.w_dgrad_f32 = None
+            pk.f32_stale = True
+            pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.ds_fwd = pk.ds_dgrad = None
+            pk.thin_kp = 0
+            n = cout * cin * kd * kh * kw
+            if B.use_umma:
+                # one packed operand per direction: the depth-stacked layout where that kernel takes the layer, else the plain one
+                if B.use_ds and lib.b200em_conv3d_umma_ds_supported(cin, cout, kd, kh, kw):
+                    plan[0].append((pk, "ds_fwd", PACK_DEPTH_STACKED, n))
+                elif lib.b200em_conv3d_umma_supported(cin, cout, kd, kh, kw):
+                    plan[0].append((pk, "umma_fwd", PACK_PLAIN, n))
+                if B.use_ds and lib.b200em_conv3d_umma_ds_supported(cout, cin, kd, kh, kw):
+                    plan[1].append((pk, "ds_dgrad", PACK_DEPTH_STACKED, n))
+                elif lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
+                    plan[1].append((pk, "umma_dgrad", PACK_PLAIN, n))
+                kp = -(-kd * kh * kw * cin // 32) * 32
+                first = B.use_ds and lib.b200em_conv3d_first_supported(cin, cout, kd, kh, kw)
+                if cin <= 4 and not first and lib.b200em_conv3d_umma_supported(kp, cout, 1, 1, 1):
+                    pk.thin_kp = kp                   # thin-K first conv (im2col layout), packed by refresh_fwd
+            self.packs[key] = pk
+        self.tables = {}
+        for d in (0, 1):
+            if not plan[d]:
+                self.tables[d] = None
+                continue
+            total = sum(-(-n // 8) * 8 for _, _, _, n in plan[d])
+            flat = torch.empty(total, dtype=torch.bfloat16, device=self.device)
+            jobs = (_PackJob * len(plan[d]))()
+            off = 0
+            for i, (pk, attr, layout, n) in enumerate(plan[d]):
+                buf = flat[off:off + n]
+                off += -(-n // 8) * 8                 # keep every image 16-byte aligned
+                setattr(pk, attr, buf)
+                j = jobs[i]
+                j.w, j.packed = pk.master.data_ptr(), buf.data_ptr()
+                j.Cout, j.Cin = pk.cout, pk.cin
+                j.kd, j.kh, j.kw = pk.kernel
+                j.dgrad, j.layout = d, layout
+            nblocks = ctypes.c_int(0)
+            call("b200em_pack_batch_prepare", ctypes.cast(jobs, ctypes.c_void_p), len(plan[d]), ctypes.byref(nblocks))
+            host = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
+            self.tables[d] = (host.to(self.device), len(plan[d]), nblocks.value, flat)
+
+    def _launch(self, d):
+        t = self.tables[d]
+        if t is None:
+            return
+        table, njobs, nblocks, _ = t
+        with torch.cuda.device(self.device):
+            call("b200em_pack_batch", _ptr(table), njobs, nblocks, ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+
+    def refresh_fwd(self, weights=None, bf16=True):
+        """Rebuild the forward operands from the CURRENT parameter values (one launch).  ``weights``: the model's current
+        {key: weight}; if a parameter's storage moved (``.to()``, re-assignment) the job table is rebuilt first."""
+        if weights is not None and self.signature(weights) != self.sig:
+            self._build(weights)
+        for pk in self.packs.values():
+            pk.f32_stale = True
+        if not bf16:
+            return                                    # fp32 activations run on the direct kernels (lazy fp32 operands)
+        self._launch(0)
+        for pk in self.packs.values():
+            if pk.thin_kp:
+                self._pack_thin(pk)
+
+    def refresh_dgrad(self, bf16=True):
+        if bf16:
+            self._launch(1)
+
+    def _pack_thin(self, pk):
+        # thin-K first conv: W'[co][tap*Cin+ci] = W[co][ci][tap], zero padded to Kp channels (im2col layout)
+        wd, cout, cin = pk.master, pk.cout, pk.cin
+        taps = pk.kernel[0] * pk.kernel[1] * pk.kernel[2]
+        wt = torch.zeros((cout, pk.thin_kp), dtype=torch.float32, device=wd.device)
+        wt[:, :taps * cin] = wd.reshape(cout, cin, taps).permute(0, 2, 1).reshape(cout, taps * cin)
+        if pk.thin is None:
+            pk.thin = torch.empty(cout * pk.thin_kp, dtype=torch.bfloat16, device=wd.device)
+        with torch.cuda.device(wd.device):
+            call("b200em_conv3d_umma_pack", _ptr(wt), cout, pk.thin_kp, 1, 1, 1, 0, _ptr(pk.thin), _stream(wd))
+
+    def __getitem__(self, key):
+        return self.packs[key]
 
 
 class CudaBackend:
     name = "cuda"
 
-    def __init__(self, use_umma=True, use_s3=False, use_ds=True, use_cs=True):
+    def __init__(self, use_umma=True, use_ds=True, use_cs=True):
         self.use_umma = use_umma
-        self.use_s3 = use_s3 and use_umma
         self.use_ds = use_ds and use_umma
         self.use_cs = use_cs and use_umma
-        self._pack_cache = {}
         self.timing = None          # {family: [(start_event, end_event, work), ...]} while bench.py measures
         self.calls = collections.Counter()   # conv launches per "<kernel>:<direction>" (tests assert which kernels ran)
 
@@ -89,87 +218,29 @@ class CudaBackend:
         return r
 
     # ---- weights ---------------------------------------------------------------------------------------------
-    def pack(self, key, w, lazy_dgrad=False):
-        """Operand images of one conv weight.  lazy_dgrad=True defers the data-gradient operands to the first dgrad call
-        (ensure_dgrad): the schedule then issues each pack right before the kernel that needs it instead of ~40 small
-        launches in front of the first conv of a step."""
-        if w.device.type != "cuda":
-            raise RuntimeError("b200em: parameters must live on a CUDA device (there is no CPU fallback for this path)")
-        ver = (w.data_ptr(), w._version, tuple(w.shape), w.device)
-        pk = self._pack_cache.get(key)
-        if pk is not None and pk.version == ver:
-            if not lazy_dgrad:
-                self.ensure_dgrad(pk)
-            return pk
-        cout, cin, kd, kh, kw = w.shape
-        wd = w.detach()
-        assert wd.dtype == torch.float32 and wd.is_contiguous()
-        pk = WeightPack()
-        pk.version, pk.cout, pk.cin, pk.kernel = ver, cout, cin, (kd, kh, kw)
-        taps = kd * kh * kw
-        pk.w_fwd_f32 = pk.w_dgrad_f32 = None         # fp32 operands of the direct kernels: packed on first use (f32_operands)
-        pk.master = wd
-        pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.s3_fwd = pk.s3_dgrad = pk.ds_fwd = pk.ds_dgrad = None
-        pk.thin_kp = 0
-        pk.dgrad_ready = False
-        lib = _lib.load()
-        with torch.cuda.device(w.device):
-            # one packed operand per direction: the depth-stacked layout where that kernel takes the layer, else the plain one
-            ds_f = self.use_ds and lib.b200em_conv3d_umma_ds_supported(cin, cout, kd, kh, kw)
-            if self.use_umma and not ds_f and lib.b200em_conv3d_umma_supported(cin, cout, kd, kh, kw):
-                pk.umma_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
-                call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.umma_fwd), _stream(w))
-            if self.use_s3 and lib.b200em_conv3d_umma_s3_supported(cin, cout, kd, kh, kw):
-                pk.s3_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
-                call("b200em_conv3d_umma_s3_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.s3_fwd), _stream(w))
-            if ds_f:
-                pk.ds_fwd = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=w.device)
-                call("b200em_conv3d_umma_ds_pack", _ptr(wd), cout, cin, kd, kh, kw, 0, _ptr(pk.ds_fwd), _stream(w))
-            kp = -(-taps * cin // 32) * 32
-            first = self.use_ds and lib.b200em_conv3d_first_supported(cin, cout, kd, kh, kw)
-            if self.use_umma and cin <= 4 and not first and lib.b200em_conv3d_umma_supported(kp, cout, 1, 1, 1):
-                # thin-K first conv: W'[co][tap*Cin+ci] = W[co][ci][tap], zero padded to Kp channels (im2col layout)
-                wt = torch.zeros((cout, kp), dtype=torch.float32, device=w.device)
-                wt[:, :taps * cin] = wd.reshape(cout, cin, taps).permute(0, 2, 1).reshape(cout, taps * cin)
-                pk.thin = torch.empty(cout * kp, dtype=torch.bfloat16, device=w.device)
-                pk.thin_kp = kp
-                call("b200em_conv3d_umma_pack", _ptr(wt), cout, kp, 1, 1, 1, 0, _ptr(pk.thin), _stream(w))
-        self._pack_cache[key] = pk
-        if not lazy_dgrad:
-            self.ensure_dgrad(pk)
-        return pk
+    def pack_set(self, weights):
+        """{key: conv weight} -> PackSet (all operand images of a model, one launch per direction)."""
+        return PackSet(self, weights)
 
-    def ensure_dgrad(self, pk):
-        """Data-gradient operands (transposed, tap-flipped filter) of a pack, built on first use."""
-        if pk.dgrad_ready:
-            return
-        pk.dgrad_ready = True
-        cout, cin = pk.cout, pk.cin
-        kd, kh, kw = pk.kernel
-        taps = kd * kh * kw
-        wd = pk.master
-        lib = _lib.load()
-        with torch.cuda.device(wd.device):
-            ds_d = self.use_ds and lib.b200em_conv3d_umma_ds_supported(cout, cin, kd, kh, kw)
-            if self.use_umma and not ds_d and lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
-                pk.umma_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=wd.device)
-                call("b200em_conv3d_umma_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.umma_dgrad), _stream(wd))
-            if self.use_s3 and lib.b200em_conv3d_umma_s3_supported(cout, cin, kd, kh, kw):
-                pk.s3_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=wd.device)
-                call("b200em_conv3d_umma_s3_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.s3_dgrad), _stream(wd))
-            if ds_d:
-                pk.ds_dgrad = torch.empty(cout * cin * taps, dtype=torch.bfloat16, device=wd.device)
-                call("b200em_conv3d_umma_ds_pack", _ptr(wd), cout, cin, kd, kh, kw, 1, _ptr(pk.ds_dgrad), _stream(wd))
+    def pack(self, key, w, lazy_dgrad=False):
+        """Operand images of ONE conv weight, both directions, packed now (tests / stand-alone use of conv())."""
+        ps = PackSet(self, {key: w})
+        ps.refresh_fwd()
+        ps.refresh_dgrad()
+        return ps[key]
 
     def f32_operands(self, pk):
-        """fp32 (taps, Cin, Cout) / (taps, Cout, Cin) operands of the direct CUDA-core kernels, packed on first use."""
-        if pk.w_fwd_f32 is None:
+        """fp32 (taps, Cin, Cout) / (taps, Cout, Cin) operands of the direct CUDA-core kernels, packed on first use after
+        every refresh of the pack set."""
+        if pk.f32_stale:
+            pk.f32_stale = False
             cout, cin = pk.cout, pk.cin
             kd, kh, kw = pk.kernel
             taps = kd * kh * kw
             wd = pk.master
-            pk.w_fwd_f32 = torch.empty((taps, cin, cout), dtype=torch.float32, device=wd.device)
-            pk.w_dgrad_f32 = torch.empty((taps, cout, cin), dtype=torch.float32, device=wd.device)
+            if pk.w_fwd_f32 is None:
+                pk.w_fwd_f32 = torch.empty((taps, cin, cout), dtype=torch.float32, device=wd.device)
+                pk.w_dgrad_f32 = torch.empty((taps, cout, cin), dtype=torch.float32, device=wd.device)
             with torch.cuda.device(wd.device):
                 call("b200em_pack_conv_weights", _ptr(wd), cout, cin, kd, kh, kw, _ptr(pk.w_fwd_f32), _ptr(pk.w_dgrad_f32),
                      _stream(wd))
@@ -230,8 +301,6 @@ class CudaBackend:
         b = bias.detach() if bias is not None else None
         kd, kh, kw = kernel
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
-        if dgrad:
-            self.ensure_dgrad(pack)
         if (not dgrad) and self.use_ds and Cin == 1 and xld == 1 and x.dtype == torch.bfloat16 and yld % 8 == 0 and \
                 y.data_ptr() % 16 == 0 and dot_x is None and _lib.load().b200em_conv3d_first_supported(Cin, Cout, kd, kh, kw):
             # first conv of the network: im2col rows built on the fly in shared memory, straight from the fp32 parameter
@@ -255,12 +324,6 @@ class CudaBackend:
                     "b200em_conv3d_umma_ds", xp, xld, _f32(in_ss), _ptr(wds), _f32(b), yp, yld, _f32(sums), dp, dld, N, D, H, W,
                     Cin, Cout, kd, kh, kw, int(relu), _stream(x)))
                 return None
-        ws3 = pack.s3_dgrad if dgrad else pack.s3_fwd
-        if ws3 is not None and ok16 and dot_x is None:
-            self._timed("s3:dgrad" if dgrad else "s3:fwd", flops, lambda: call(
-                "b200em_conv3d_umma_s3", xp, xld, _f32(in_ss), _ptr(ws3), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cin, Cout,
-                kd, kh, kw, int(relu), _stream(x)))
-            return None
         wu = pack.umma_dgrad if dgrad else pack.umma_fwd
         if wu is not None and x.dtype == torch.bfloat16 and xld % 8 == 0 and yld % 8 == 0 and \
                 x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
@@ -391,6 +454,5 @@ def default_backend():
     if _default is None:
         _lib.load()
         import os
-        _default = CudaBackend(use_s3=os.environ.get("B200EM_S3", "0") == "1", use_ds=os.environ.get("B200EM_DS", "1") == "1",
-                               use_cs=os.environ.get("B200EM_CS", "1") == "1")
+        _default = CudaBackend(use_ds=os.environ.get("B200EM_DS", "1") == "1", use_cs=os.environ.get("B200EM_CS", "1") == "1")
     return _default

@@ -15,6 +15,8 @@ OUT = os.path.join(HERE, "libb200em.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
+if os.environ.get("B200EM_WATCHDOG_CYCLES"):      # 0 compiles the pipeline watchdog out (sanitizer / debugger runs)
+    FLAGS.append("-DB200EM_WATCHDOG_CYCLES=" + os.environ["B200EM_WATCHDOG_CYCLES"])
 
 
 def sources():

@@ -655,6 +655,15 @@ static bool wgrad_umma_shape(int Cin, int Cout, int& NB) {
     return true;
 }
 
+
+// layout parameters of the packed operand (pack.cu: batched packing of every weight of a model in one launch)
+bool umma_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC, int* NP) {
+    UmmaShape s;
+    if (!umma_shape(Cin, Cout, kd, kh, kw, s)) return false;
+    *CC = s.CC; *NP = s.NP;
+    return true;
+}
+
 }  // namespace b200em
 
 using namespace b200em;

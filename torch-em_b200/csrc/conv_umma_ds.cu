@@ -1076,6 +1076,14 @@ static int ds_pick_dr(int N, int D, int H, int W, int sms) {
     return best;
 }
 
+// layout parameter of the packed operand (pack.cu: batched packing of every weight of a model in one launch)
+bool ds_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC) {
+    DsShape s;
+    if (!ds_shape(Cin, Cout, kd, kh, kw, s)) return false;
+    *CC = s.CC;
+    return true;
+}
+
 }  // namespace b200em
 
 using namespace b200em;

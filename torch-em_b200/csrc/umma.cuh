@@ -46,12 +46,20 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a pipeline bug must end as a trapped kernel (launch failure reported to the host), never as a hung GPU.
+// The bound is a build-time constant (-DB200EM_WATCHDOG_CYCLES=n; 0 compiles the watchdog out, e.g. for runs under
+// compute-sanitizer or a debugger whose slowdown could otherwise trip it).  Default: ~20 s at 2 GHz.
+#ifndef B200EM_WATCHDOG_CYCLES
+#define B200EM_WATCHDOG_CYCLES 40000000000LL
+#endif
+__device__ __forceinline__ void watchdog(long long t0) {
+#if B200EM_WATCHDOG_CYCLES > 0
+    if (clock64() - t0 > (long long)B200EM_WATCHDOG_CYCLES) __trap();
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
-    }
+    while (!mbar_try_wait(bar, parity)) watchdog(t0);
 }
 
 // ---- plain shared-memory flags / counters for the hand-offs INTO the single-thread MMA issue loop ----------------------
@@ -73,17 +81,13 @@ __device__ __forceinline__ void flag_wait_eq(uint64_t* f, uint32_t v) {
     const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(f);
     if (*q == v) return;
     const long long t0 = clock64();
-    while (*q != v) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
+    while (*q != v) watchdog(t0);
 }
 __device__ __forceinline__ void counter_wait_ge(uint64_t* f, uint32_t v) {
     const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(f);
     if (*q >= v) return;
     const long long t0 = clock64();
-    while (*q < v) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
+    while (*q < v) watchdog(t0);
 }
 
 // ---- proxies / bulk copy -----------------------------------------------------------------------------------

@@ -126,13 +126,19 @@ def _device_ctx(device):
 
 
 class _LazyPacks:
-    """Mapping key -> WeightPack that packs on first access (see AnisotropicUNet._packs)."""
+    """Mapping key -> pack for backends without a batched pack set (the CPU emulation used by the host-logic tests)."""
 
-    def __init__(self, model, B, P):
-        self._model_id, self._B, self._P = id(model), B, P
+    def __init__(self, B, P):
+        self._B, self._P = B, P
 
     def __getitem__(self, key):
-        return self._B.pack((self._model_id, key), self._P[key + ".weight"], lazy_dgrad=True)
+        return self._B.pack(key, self._P[key + ".weight"])
+
+    def refresh_fwd(self, weights=None, bf16=True):
+        pass
+
+    def refresh_dgrad(self, bf16=True):
+        pass
 
 
 class _UNetFunction(torch.autograd.Function):
@@ -140,27 +146,47 @@ class _UNetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, act_dtype, x, *params):
+        if ctx.needs_input_grad[2]:
+            raise NotImplementedError(
+                "the fused U-Net node does not compute the gradient w.r.t. its input (the reference's trainer never asks for "
+                "it, default_trainer.py:805-831); detach the input or set requires_grad=False")
         names = model._param_names
         P = dict(zip(names, params))
         B = model._backend()
+        bf16 = act_dtype == torch.bfloat16
         with _device_ctx(x.device):
             packs = model._packs(B, P)
+            packs.refresh_fwd({k[:-len(".weight")]: v for k, v in P.items() if v.dim() == 5}, bf16=bf16)
             pred, fctx = engine.forward_pass(B, model._plan, P, x.detach(), act_dtype, packs)
-        ctx.model, ctx.P, ctx.packs = model, P, packs
+        ctx.model, ctx.P, ctx.packs, ctx.bf16 = model, P, packs, bf16
         ctx.fctx = fctx if any(ctx.needs_input_grad) else None   # no_grad / eval inference keeps nothing
+        ctx.ran_backward = False
+        if ctx.fctx is not None:
+            # the head's backward reads the prediction (sigmoid / tanh derivative): saving it through autograd makes an
+            # in-place edit of the returned tensor (pred.clamp_()) raise instead of silently corrupting the gradient
+            ctx.save_for_backward(pred)
+            fctx.misc.pop("pred", None)          # (a direct reference would close a cycle pred -> grad_fn -> ctx -> pred)
         return pred
 
     @staticmethod
     def backward(ctx, grad_pred):
         model = ctx.model
         if ctx.fctx is None:
+            if ctx.ran_backward:
+                raise RuntimeError(
+                    "the fused U-Net node releases its activations after the first backward pass: a second backward through "
+                    "the same forward (retain_graph=True) is not supported -- run the forward again")
             raise RuntimeError("backward through a forward that ran without grad")
+        (pred,) = ctx.saved_tensors
+        ctx.fctx.misc["pred"] = pred
         B = model._backend()
         with _device_ctx(grad_pred.device):
+            ctx.packs.refresh_dgrad(bf16=ctx.bf16)
             grads = engine.backward_pass(B, model._plan, ctx.P, ctx.fctx, grad_pred, ctx.packs)
             if model.grad_sync is not None:
                 model.grad_sync(grads.flat)      # ONE collective over the flat gradient buffer (distributed.py)
         ctx.fctx = None
+        ctx.ran_backward = True
         out = [None, None, None]
         for name in model._param_names:
             g = grads.get(name)
@@ -278,10 +304,16 @@ class AnisotropicUNet(nn.Module):
         return self._backend_override if self._backend_override is not None else default_backend()
 
     def _packs(self, B, P):
-        """Weight operand images, built on demand: each pack is issued right before the kernel that consumes it (forward
-        operand at the layer's forward conv, data-gradient operand at its dgrad) instead of ~40 small launches in front of
-        the first conv of every step (which leave the GPU idle whenever the host starts a step with an empty queue)."""
-        return _LazyPacks(self, B, P)
+        """The model's operand images (backend.PackSet: one pack launch per direction and pass); owned by the model so that
+        they are freed with it.  One set per backend object (tests swap backends on a live model)."""
+        if not hasattr(B, "pack_set"):
+            return _LazyPacks(B, P)
+        store = self.__dict__.get("_pack_store")
+        if store is None or store[0] is not B:
+            weights = {k[:-len(".weight")]: v for k, v in P.items() if v.dim() == 5}
+            store = (B, B.pack_set(weights))
+            self.__dict__["_pack_store"] = store
+        return store[1]
 
     def _activation_dtype(self, x):
         if self.compute_dtype is not None:
@@ -314,6 +346,8 @@ class AnisotropicUNet(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
+            if k == "_pack_store":
+                continue                          # derived data: the copy packs its own operands on its own device
             new.__dict__[k] = v if k == "_backend_override" else copy.deepcopy(v, memo)
         return new
 
