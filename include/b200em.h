@@ -77,7 +77,7 @@ int b200em_conv3d_wgrad_smallcin(const void* x, int64_t x_ld, const float* in_sc
 
 /* tcgen05 implicit-GEMM path: bf16 activations and weights, fp32 accumulation in TMEM (csrc/conv_umma.cu).
  * Same fused prologue / epilogue contract as b200em_conv3d_direct.  Takes Cin % 16 == 0, Cout % 16 == 0
- * (Cout <= 256 or Cout % 256 == 0); b200em_conv3d_umma_supported() says so, and the other entry points return
+ * (Cout <= 256 or Cout % 128 == 0); b200em_conv3d_umma_supported() says so, and the other entry points return
  * 2 ("unsupported shape") otherwise so that the caller can take the direct kernel.
  * Weights are pre-packed once per optimizer step by b200em_conv3d_umma_pack into Cout*Cin*taps bf16:
  *   dgrad = 0: forward operand;  dgrad = 1: transposed, tap-flipped operand -- the data gradient is then

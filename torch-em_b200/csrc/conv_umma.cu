@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
     uint32_t* s_tap = s_tmem + 2;                   // [27] operand start offset of each tap, in 16-byte units
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nblk = blockIdx.y;                    // 256-wide output-channel block (Cout > 256)
+    const int nblk = blockIdx.y;                    // NP-wide output-channel block
     constexpr int J = KC_ * 2;                      // 8-channel planes per slice per chunk
     const int taps = p.kd * p.kh * p.kw;
     const int ngroups = taps / p.G;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
         s_tap[tap] = (uint32_t)((a * J * PLANE + ((b + 1 - ph) * WP + (cc + 1 - pw)) * 16) >> 4);
     }
     for (int i = threadIdx.x; i < p.NP; i += THREADS) {
-        const int co = nblk * 256 + i;
+        const int co = nblk * p.NP + i;
         s_bias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
         s_sums[2 * i] = 0.f;
         s_sums[2 * i + 1] = 0.f;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
             const int rmax = min(p.R, p.D - d0);
             for (int r = 0; r < rmax; ++r) {
                 const int gd = d0 + r;
-                __nv_bfloat16* yp = p.y + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.y_ld + nblk * 256;
+                __nv_bfloat16* yp = p.y + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.y_ld + nblk * p.NP;
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * acc_cols + r * p.NP;
                 for (int cb = 0; cb < p.NP; cb += 32) {
                     if (p.NP - cb >= 32) {
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         if (p.sums) {
                             float s1[32], s2[32];
                             if (p.dot_x) {
-                                const __nv_bfloat16* xq = p.dot_x + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * 256 + cb;
+                                const __nv_bfloat16* xq = p.dot_x + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     uint4 xv = valid_hw ? __ldg(reinterpret_cast<const uint4*>(xq + 8 * q)) : make_uint4(0, 0, 0, 0);
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         if (p.sums) {
                             float s1[16], s2[16];
                             if (p.dot_x) {
-                                const __nv_bfloat16* xq = p.dot_x + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * 256 + cb;
+                                const __nv_bfloat16* xq = p.dot_x + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
 #pragma unroll
                                 for (int q = 0; q < 2; ++q) {
                                     uint4 xv = valid_hw ? __ldg(reinterpret_cast<const uint4*>(xq + 8 * q)) : make_uint4(0, 0, 0, 0);
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                 // flush this item's per-channel partial sums (n may change with the next item)
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int i = threadIdx.x; i < 2 * p.NP; i += 128) {
-                    const int co = nblk * 256 + (i >> 1);
+                    const int co = nblk * p.NP + (i >> 1);
                     if (co < p.Cout) atomicAdd(p.sums + ((size_t)n * p.Cout + co) * 2 + (i & 1), s_sums[i]);
                     s_sums[i] = 0.f;
                 }
@@ -411,10 +411,13 @@ struct UmmaShape {
 // Channel counts the tensor-core path takes; everything else goes to the direct kernel.
 static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s) {
     if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16) return false;
-    if (Cout > 256 && Cout % 256) return false;
+    if (Cout > 256 && Cout % 128) return false;
     s.CC = (Cin % 32 == 0) ? 32 : 16;
-    s.NP = Cout > 256 ? 256 : Cout;
-    s.nblk = Cout > 256 ? Cout / 256 : 1;
+    // Output-channel block of one CTA.  N = 128 already issues at the full tensor rate, so wide layers are cut
+    // into 128-channel blocks: twice the CTAs of a 256-wide block for the deep levels (8^3 / 16^3 volumes have few voxel
+    // tiles), half the weight bytes streamed per CTA, and room for double-buffered accumulators (2 * R * 128 <= 512).
+    s.NP = (Cout % 128 == 0) ? 128 : Cout;
+    s.nblk = Cout / s.NP;
     const int taps = kd * kh * kw;
     s.G = (taps % 3 == 0 && s.NP <= 64) ? 3 : 1;
     const int J = s.CC / 8;
@@ -709,6 +712,33 @@ int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift,
     p.dot_x = (const __nv_bfloat16*)dot_x; p.dot_ld = dot_ld;
     B2_CHECK_ARG(!dot_x || (sums && dot_ld % 8 == 0 && aligned16(dot_x) && dot_ld >= Cout), "conv3d_umma: dot_x needs sums, 16-byte alignment and pitch >= Cout");
     p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.relu = relu;
+    // Depth slabs per work item: the shape admits R <= s.R; fewer slabs = more work items (the deep levels have fewer voxel
+    // tiles than SMs) but the weight block is streamed once per item.  Cost model per CTA (cycles): items per CTA x
+    // max(MMA issue, weight stream at ~48 B/clk from L2) + a fixed pipeline fill per item.
+    {
+        const int taps = kd * kh * kw;
+        const long long cols = (long long)N * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+        const int cta_cap = sm_count() / s.nblk > 0 ? sm_count() / s.nblk : 1;
+        const double mma_cyc = s.NP / 2 > 32 + s.NP / 4 ? s.NP / 2 : 32 + s.NP / 4;
+        const double wts = (double)taps * Cin * s.NP * 2 / 48.0;
+        double best = 1e300;
+        int best_r = s.R;
+        for (int R = s.R; R >= 1; R >>= 1) {
+            const long long items = cols * ((D + R - 1) / R);
+            const long long gx_ = items < cta_cap ? items : cta_cap;
+            const long long per_cta = (items + gx_ - 1) / gx_;
+            const double mma = (double)R * taps * (Cin / 16) * mma_cyc;
+            const double epi = (2 * R * s.NP <= 512) ? 0.0 : (double)R * (s.NP / 32) * 700.0;   // single accumulator set: the epilogue is not overlapped
+            const double cost = per_cta * ((mma > wts ? mma : wts) + epi + 4000.0 + 1500.0 * (R + kd - 1));
+            if (cost < best * 0.97) { best = cost; best_r = R; }
+        }
+        if (best_r != s.R) {
+            s.R = best_r;
+            s.acc_bufs = (2 * s.R * s.NP <= 512) ? 2 : 1;
+            s.a_bytes = (s.R + kd - 1) * (s.CC / 8) * PLANE;
+            s.smem_bytes = 2 * s.a_bytes + NSTAGE * s.b_stage_bytes + s.NP * 4 * 3 + 16 * 8 + 16 + 27 * 4 + 128;
+        }
+    }
     p.R = s.R; p.NP = s.NP; p.CC = s.CC; p.nchunks = Cin / s.CC; p.G = s.G; p.acc_bufs = s.acc_bufs;
     p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + s.R - 1) / s.R;
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
