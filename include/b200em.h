@@ -218,6 +218,24 @@ int b200em_dice_bwd(const void* pred, int pred_dtype, const float* target, const
                     const float* coef, const float* gout, int gout_per_channel, void* grad_pred, int grad_dtype,
                     int N, int C, int64_t S, void* stream);
 
+/* ---- Dice-family losses beyond DiceLoss (csrc/segloss.cu): DiceLossWithLogits, BCEDiceLoss, BCEDiceLossWithLogits
+ * (loss/dice.py:136-256), DistanceLoss / DiceBasedDistanceLoss (loss/distance_based.py:7-69) ---------------------------------
+ * chan[C][4] = (w_dice, w_bce, w_mse, use_mask) per channel selects the terms a channel contributes.  With p = logits ?
+ * sigmoid(x) : x, m = use_mask ? mask : 1 (mask element of (n, c, i) at mask + n*mask_nstride + c*mask_cstride + i; a channel
+ * stride of 0 broadcasts one mask channel), pm = p*m, tm = t*m:
+ *   sums[C][5] += (sum pm*tm, sum pm^2, sum tm^2, sum bce, sum (pm-tm)^2)
+ *   loss = reduce_c w_dice[c]*(1 - 2 num_c/max(den_c, eps)) + sum_c (w_bce[c]*bce_c + w_mse[c]*mse_c) / numel
+ * BCE as ATen: log clamped at -100, gradient (p-t)/max(p(1-p), 1e-12); with logits max(x,0) - x t + log1p(exp(-|x|)).
+ * coef[C][4] = (A_c, B_c, w_bce/numel, w_mse/numel); reduce codes as b200em_dice_finalize. */
+int b200em_segloss_sums(const void* pred, int pred_dtype, const float* target, const float* mask, int64_t target_nstride,
+                        int64_t mask_nstride, int64_t mask_cstride, const float* chan, int logits, int N, int C, int64_t S,
+                        float* sums, void* stream);
+int b200em_segloss_finalize(const float* sums, const float* chan, int C, float eps, int channelwise, int reduce, float numel,
+                            float* loss, float* coef, void* stream);
+int b200em_segloss_bwd(const void* pred, int pred_dtype, const float* target, const float* mask, int64_t target_nstride,
+                       int64_t mask_nstride, int64_t mask_cstride, const float* chan, const float* coef, const float* gout,
+                       int gout_per_channel, int logits, void* grad_pred, int grad_dtype, int N, int C, int64_t S, void* stream);
+
 /* ---- AffinityTransform / BoundaryTransform (transform/label.py:248-327, 100-129) --------------------------- */
 /* labels (N,D,H,W) int64; offsets: n_off*3 host ints (dz,dy,dx); out (N, channels, D,H,W) fp32 with channel
  * order [fg?][n_off disaffinities][fg-mask?][n_off masks]  (masks only if add_mask). */

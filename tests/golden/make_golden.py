@@ -52,6 +52,49 @@ def unet_case(ref_unet, ref_dice, name, ctor, kwargs, shape, seed):
     print(name, "loss", float(loss), "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+def losses_case():
+    """Dice-family losses beyond DiceLoss (loss/dice.py:136-256, combined_loss.py, distance_based.py): values and gradients
+    from the reference classes (package imported through the stub finder of tests/ref_harness.py)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from tests import ref_harness
+    te = ref_harness.import_torch_em()
+    L = te.loss
+    from torch_em.loss.dice import BCEDiceLoss, BCEDiceLossWithLogits, DiceLossWithLogits
+    from torch_em.loss.distance_based import DiceBasedDistanceLoss, DistanceLoss
+    torch.manual_seed(11)
+    shape = (2, 3, 4, 8, 8)
+    x = torch.randn(*shape) * 2.0                       # logits
+    p = torch.rand(*shape) * 0.98 + 0.01                # probabilities
+    t = (torch.rand(*shape) > 0.5).float()
+    out = {"x": x.numpy(), "p": p.numpy(), "t": t.numpy()}
+
+    def record(name, loss_fn, inp, tgt):
+        inp = inp.clone().requires_grad_(True)
+        l = loss_fn(inp, tgt)
+        if l.dim() > 0:
+            l.sum().backward()
+        else:
+            l.backward()
+        out["loss_" + name] = l.detach().numpy()
+        out["grad_" + name] = inp.grad.numpy().copy()
+
+    for red in ("sum", "mean", "max", "min", None):
+        record(f"dice_logits_{red}", DiceLossWithLogits(reduce_channel=red), x, t)
+    record("dice_logits_pooled", DiceLossWithLogits(channelwise=False), x, t)
+    record("bce_dice", BCEDiceLoss(alpha=0.7, beta=1.3), p, t)
+    record("bce_dice_pooled", BCEDiceLoss(alpha=1.0, beta=0.5, channelwise=False), p, t)
+    record("bce_dice_logits", BCEDiceLossWithLogits(alpha=0.7, beta=1.3), x, t)
+    record("combined", L.CombinedLoss(L.DiceLoss(), BCEDiceLoss(), loss_weights=[0.25, 0.75]), p, t)
+    # distance losses: channel 0 = foreground, channels 1, 2 = distances in [0, 1]
+    td = torch.cat([t[:, :1], torch.rand(2, 2, 4, 8, 8)], 1)
+    out["td"] = td.numpy()
+    for m in (True, False):
+        record(f"distance_{m}", DistanceLoss(mask_distances_in_bg=m), p, td)
+        record(f"dice_distance_{m}", DiceBasedDistanceLoss(mask_distances_in_bg=m), p, td)
+    np.savez_compressed(os.path.join(HERE, "losses.npz"), **out)
+    print("losses", {k: np.round(v, 5).tolist() for k, v in out.items() if k.startswith("loss")})
+
+
 def main():
     only = sys.argv[1:]                      # optional: names of the U-Net cases to (re)generate
     global unet_case
@@ -88,6 +131,8 @@ def main():
                    final_activation="Sigmoid", anisotropic_kernel=False),
               (1, 1, 4, 16, 16), 4)
 
+    if only == ["losses"]:
+        losses_case()
     if only:
         return
     # Dice + masked Dice (LossWrapper(DiceLoss(), ApplyAndRemoveMask("multiply"))) with gradients
@@ -115,6 +160,8 @@ def main():
     out["loss_ones_zeros"] = ref_dice.DiceLoss()(torch.ones(1, 1, 8, 8), torch.zeros(1, 1, 8, 8)).numpy()
     np.savez_compressed(os.path.join(HERE, "dice.npz"), **out)
     print("dice", {k: float(v) for k, v in out.items() if k.startswith("loss")})
+
+    losses_case()
 
     # Affinity / boundary targets: the reference's arithmetic lives in absent third-party code; the fixture is
     # generated with the brute-force functions restated from the reference's own test (oracle/labels.py).

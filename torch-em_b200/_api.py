@@ -1,10 +1,12 @@
 """Public surface of ``torch_em_b200``: the torch-em names for the accelerated path."""
 from . import _lib, distributed, util
-from .loss import AffinityLoss, ApplyAndRemoveMask, ApplyMask, DiceLoss, LossWrapper, MaskIgnoreLabel, dice_score
+from .loss import (AffinityLoss, ApplyAndRemoveMask, ApplyMask, BCEDiceLoss, BCEDiceLossWithLogits, CombinedLoss, DiceBasedDistanceLoss,
+                   DiceLoss, DiceLossWithLogits, DistanceLoss, LossWrapper, MaskIgnoreLabel, dice_score)
 from .model import AnisotropicUNet, UNet3d
 from .transform import AffinityTransform, BoundaryTransform
 
-__all__ = ["UNet3d", "AnisotropicUNet", "DiceLoss", "dice_score", "LossWrapper", "ApplyMask", "ApplyAndRemoveMask",
+__all__ = ["UNet3d", "AnisotropicUNet", "DiceLoss", "DiceLossWithLogits", "BCEDiceLoss", "BCEDiceLossWithLogits", "CombinedLoss",
+           "DistanceLoss", "DiceBasedDistanceLoss", "dice_score", "LossWrapper", "ApplyMask", "ApplyAndRemoveMask",
            "MaskIgnoreLabel", "AffinityLoss", "AffinityTransform", "BoundaryTransform", "launch_count",
            "reset_launch_count", "distributed", "util"]
 

@@ -10,7 +10,7 @@ import torch.nn as nn
 from .. import _lib
 from .._lib import BF16, F32, call
 
-__all__ = ["DiceLoss", "dice_score", "masked_dice"]
+__all__ = ["DiceLoss", "DiceLossWithLogits", "BCEDiceLoss", "BCEDiceLossWithLogits", "dice_score", "masked_dice"]
 
 _REDUCE = {"sum": 0, "mean": 1, "max": 2, "min": 3, None: 4}
 
@@ -142,3 +142,56 @@ class DiceLoss(nn.Module):
             raise ValueError(f"Expect input and target of same shape, got: {input_.shape}, {target.shape}.")
         return _DiceFn.apply(_flatten_to_ncs(input_), _flatten_to_ncs(target), _flatten_to_ncs(mask), False,
                              self.channelwise, self.eps, self.reduce_channel if self.channelwise else "sum")
+
+
+def _check_same_shape(input_, target):
+    if input_.shape != target.shape:
+        raise ValueError(f"Expect input and target of same shape, got: {input_.shape}, {target.shape}.")
+
+
+class DiceLossWithLogits(nn.Module):
+    """Dice error between logits and a binary target (torch_em/loss/dice.py:136-173): the sigmoid is applied inside the
+    fused reduction and its derivative inside the fused backward (csrc/segloss.cu)."""
+
+    def __init__(self, channelwise: bool = True, eps: float = 1e-7, reduce_channel: Optional[str] = "sum"):
+        if reduce_channel not in ("sum", "mean", "max", "min", None):
+            raise ValueError(f"Unsupported channel reduction {reduce_channel}")
+        super().__init__()
+        self.channelwise = channelwise
+        self.eps = eps
+        self.reduce_channel = reduce_channel
+        self.init_kwargs = {"channelwise": channelwise, "eps": self.eps, "reduce_channel": self.reduce_channel}
+
+    def forward(self, input_: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        from .segloss import SegLossFn
+        _check_same_shape(input_, target)
+        C = input_.shape[1]
+        return SegLossFn.apply(input_, target, [[1.0, 0.0, 0.0, 0.0]] * C, True, None, self.channelwise, self.eps,
+                               self.reduce_channel if self.channelwise else "sum")
+
+
+class BCEDiceLoss(nn.Module):
+    """alpha * Dice + beta * binary cross entropy between binary inputs and target (torch_em/loss/dice.py:176-214), one
+    fused pass forward and one backward."""
+    _logits = False
+
+    def __init__(self, alpha: float = 1.0, beta: float = 1.0, channelwise: bool = True, eps: float = 1e-7):
+        super().__init__()
+        self.alpha = alpha
+        self.beta = beta
+        self.channelwise = channelwise
+        self.eps = eps
+        self.init_kwargs = {"alpha": alpha, "beta": beta, "channelwise": channelwise, "eps": self.eps}
+
+    def forward(self, input_: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        from .segloss import SegLossFn
+        _check_same_shape(input_, target)
+        C = input_.shape[1]
+        # the BCE is a mean over ALL elements (N*C*S): per-channel weight beta / C on a per-channel mean over N*S
+        chan = [[float(self.alpha), float(self.beta) / C, 0.0, 0.0]] * C
+        return SegLossFn.apply(input_, target, chan, self._logits, None, self.channelwise, self.eps, "sum")
+
+
+class BCEDiceLossWithLogits(BCEDiceLoss):
+    """alpha * Dice(sigmoid(x)) + beta * BCE-with-logits(x) (torch_em/loss/dice.py:217-256)."""
+    _logits = True
