@@ -245,6 +245,17 @@ int b200em_affinity_targets(const int64_t* labels, float* out, int N, int D, int
 /* out (N, 1 or 2, D,H,W) fp32: [foreground?][boundary], boundary = some in-bounds 6-neighbour differs. */
 int b200em_boundary_targets(const int64_t* labels, float* out, int N, int D, int H, int W, int add_binary_target,
                             void* stream);
+/* NoToBackgroundBoundaryTransform (mode 1: aux = mask_label, bg = bg_label; label.py:133-189) and
+ * BoundaryTransformWithIgnoreLabel (mode 2: aux = ignore_label; label.py:192-244): the label boundary, with the boundaries of
+ * [lab != bg] resp. [lab == aux] set to aux; optional channel 0 = [lab != bg] with lab == aux -> aux.  out fp32. */
+int b200em_boundary_targets_masked(const int64_t* labels, float* out, int N, int D, int H, int W, int add_binary_target,
+                                   int mode, int64_t aux_label, int64_t bg_label, void* stream);
+/* OneHotTransform (label.py:330-353): out (N, n_classes, S) fp32 = [labels == class_ids[k]]; class_ids on the device. */
+int b200em_one_hot(const int64_t* labels, const int64_t* class_ids, int n_classes, float* out, int N, int64_t S, void* stream);
+/* segmentation_to_affinities (loss/affinity_side_loss.py:70-89): out (N, n_off, D,H,W) fp32 = [lab[p] == lab[clamp(p+off)]]
+ * (affinities, replication at the border, no mask). */
+int b200em_segmentation_affinities(const int64_t* labels, float* out, int N, int D, int H, int W, const int* offsets, int n_off,
+                                   void* stream);
 /* Fused target+loss reductions: Dice sums of pred against AffinityTransform(offsets, add_mask=True) targets computed
  * on the fly from labels (no target tensor in HBM).  Same sums/coef contract as b200em_dice_sums / _bwd. */
 int b200em_affinity_dice_sums(const void* pred, int pred_dtype, const int64_t* labels, int N, int D, int H, int W,

@@ -143,3 +143,54 @@ def synthetic_labels(shape, n_seeds=40, zero_fraction=0.1, seed=0):
         ids = rng.choice(np.arange(1, n_seeds + 1), size=max(1, int(n_seeds * zero_fraction)), replace=False)
         lab[np.isin(lab, ids)] = 0
     return lab
+
+
+def _find_boundaries_thick(img):
+    """skimage.segmentation.find_boundaries(img, mode='thick') restated (parity unpinned, see the module docstring): bool."""
+    return boundary_targets(np.asarray(img).astype("int64"))[0].astype(bool)
+
+
+def no_to_background_boundary_targets(labels, bg_label=0, mask_label=-1, add_binary_target=False):
+    """NoToBackgroundBoundaryTransform.__call__ (label.py:160-189): float32 restatement of the int8 output."""
+    labels = np.asarray(labels)
+    boundaries = _find_boundaries_thick(labels).astype("float32")
+    boundaries[_find_boundaries_thick(labels != bg_label)] = mask_label
+    if add_binary_target:
+        binary = (labels != bg_label).astype("float32")
+        binary[labels == mask_label] = mask_label
+        return np.stack([binary, boundaries])
+    return boundaries[None]
+
+
+def boundary_targets_with_ignore_label(labels, ignore_label=-1, add_binary_target=False):
+    """BoundaryTransformWithIgnoreLabel.__call__ (label.py:217-244)."""
+    labels = np.asarray(labels)
+    boundaries = _find_boundaries_thick(labels).astype("float32")
+    boundaries[_find_boundaries_thick(labels == ignore_label)] = ignore_label
+    if add_binary_target:
+        binary = (labels != 0).astype("float32")
+        binary[labels == ignore_label] = ignore_label
+        return np.stack([binary, boundaries])
+    return boundaries[None]
+
+
+def one_hot_targets(labels, class_ids=None):
+    """OneHotTransform.__call__ (label.py:339-353)."""
+    labels = np.asarray(labels)
+    ids = list(range(class_ids)) if isinstance(class_ids, int) else class_ids
+    ids = np.unique(labels).tolist() if ids is None else ids
+    return np.stack([(labels == c).astype("float32") for c in ids])
+
+
+def segmentation_to_affinities(segmentation, offsets):
+    """segmentation_to_affinities (loss/affinity_side_loss.py:70-89): (N, 1, *spatial) -> (N, C, *spatial) float32 affinities
+    [seg[p] == seg[clamp(p + offset)]] (replication padding of the shifted copy)."""
+    seg = np.asarray(segmentation)
+    assert seg.shape[1] == 1
+    sp = seg.shape[2:]
+    grids = np.meshgrid(*[np.arange(s) for s in sp], indexing="ij")
+    out = []
+    for off in offsets:
+        idx = tuple(np.clip(g + o, 0, s - 1) for g, o, s in zip(grids, off, sp))
+        out.append((seg[:, 0][(slice(None),) + idx] == seg[:, 0]).astype("float32"))
+    return np.stack(out, 1)

@@ -95,6 +95,47 @@ def losses_case():
     print("losses", {k: np.round(v, 5).tolist() for k, v in out.items() if k.startswith("loss")})
 
 
+def labels2_case():
+    """Label-target family (transform/label.py:133-244, 330-353; loss/affinity_side_loss.py:70-89) from the reference's own
+    classes, imported through the stub finder.  OneHotTransform and segmentation_to_affinities are pure numpy / torch.  The two
+    masked boundary transforms call skimage.segmentation.find_boundaries (absent here): it is substituted by the restatement of
+    oracle/labels.py, so the class logic (which boundaries are masked, channel order, dtype handling) is the reference's while
+    find_boundaries itself stays parity-unpinned."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from tests import ref_harness
+    ref_harness.import_torch_em()
+    import skimage.segmentation
+    from oracle import labels as L
+    import torch_em.transform.label as RL
+    from torch_em.loss.affinity_side_loss import segmentation_to_affinities
+    skimage.segmentation.find_boundaries = lambda img, mode="thick": L._find_boundaries_thick(img)
+    rng = np.random.default_rng(21)
+    seg = L.synthetic_labels((6, 12, 14), n_seeds=12, zero_fraction=0.2, seed=5)
+    segi = seg.copy()
+    segi[rng.random(seg.shape) < 0.1] = -1                      # ignore / mask label
+    seg2 = L.synthetic_labels((16, 18), n_seeds=8, zero_fraction=0.2, seed=6)
+    out = {"seg": seg, "segi": segi, "seg2": seg2}
+    for b in (False, True):
+        out[f"ntb_{b}"] = RL.NoToBackgroundBoundaryTransform(add_binary_target=b)(segi).astype("float32")
+        out[f"ntb_bg2_{b}"] = RL.NoToBackgroundBoundaryTransform(bg_label=2, mask_label=-1, add_binary_target=b)(segi).astype("float32")
+        out[f"bwi_{b}"] = RL.BoundaryTransformWithIgnoreLabel(add_binary_target=b)(segi).astype("float32")
+        out[f"bwi2d_{b}"] = RL.BoundaryTransformWithIgnoreLabel(ignore_label=0, add_binary_target=b)(seg2).astype("float32")
+    sem = rng.integers(0, 5, size=(5, 9, 11)).astype("int64")
+    out["sem"] = sem
+    out["onehot_none"] = RL.OneHotTransform()(sem)
+    out["onehot_4"] = RL.OneHotTransform(class_ids=4)(sem)
+    out["onehot_list"] = RL.OneHotTransform(class_ids=[3, 1, 7])(sem)
+    offs3 = [[-1, 0, 0], [0, -1, 0], [0, 0, -1], [0, -3, 0], [2, 0, 0], [1, 2, -3], [0, 0, 20]]
+    offs2 = [[-1, 0], [0, -1], [3, -2]]
+    segb = np.stack([seg, np.roll(seg, 3, 1)])[:, None]
+    out["segb"], out["offs3"], out["offs2"] = segb, np.array(offs3), np.array(offs2)
+    out["segaffs3"] = segmentation_to_affinities(torch.from_numpy(segb), offs3).numpy()
+    out["segaffs2"] = segmentation_to_affinities(torch.from_numpy(seg2[None, None]), offs2).numpy()
+    out["segaffs3_float"] = segmentation_to_affinities(torch.from_numpy(segb).float(), offs3).numpy()
+    np.savez_compressed(os.path.join(HERE, "labels2.npz"), **out)
+    print("labels2 ok", {k: v.shape for k, v in out.items()})
+
+
 def main():
     only = sys.argv[1:]                      # optional: names of the U-Net cases to (re)generate
     global unet_case
@@ -133,6 +174,8 @@ def main():
 
     if only == ["losses"]:
         losses_case()
+    if only == ["labels2"]:
+        labels2_case()
     if only:
         return
     # Dice + masked Dice (LossWrapper(DiceLoss(), ApplyAndRemoveMask("multiply"))) with gradients
@@ -162,6 +205,7 @@ def main():
     print("dice", {k: float(v) for k, v in out.items() if k.startswith("loss")})
 
     losses_case()
+    labels2_case()
 
     # Affinity / boundary targets: the reference's arithmetic lives in absent third-party code; the fixture is
     # generated with the brute-force functions restated from the reference's own test (oracle/labels.py).

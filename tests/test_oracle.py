@@ -115,3 +115,20 @@ def test_labels_channel_layout():
     assert a.shape == (8, 4, 8, 8) and a.dtype == np.float32        # [fg, 3 affs, fg-mask, 3 masks]
     assert np.array_equal(a[0], (seg != 0).astype("float32"))
     assert np.array_equal(a[4], (seg != 0).astype("float32"))
+
+
+def test_label_family_oracle_matches_reference_classes(golden_dir):
+    """oracle/labels.py restatements vs the goldens produced by the reference's own classes (make_golden.py::labels2_case;
+    find_boundaries itself substituted, see there)."""
+    z = np.load(os.path.join(golden_dir, "labels2.npz"))
+    segi, seg2, sem = z["segi"], z["seg2"], z["sem"]
+    for b in (False, True):
+        np.testing.assert_array_equal(olabels.no_to_background_boundary_targets(segi, add_binary_target=b), z[f"ntb_{b}"])
+        np.testing.assert_array_equal(olabels.no_to_background_boundary_targets(segi, bg_label=2, add_binary_target=b), z[f"ntb_bg2_{b}"])
+        np.testing.assert_array_equal(olabels.boundary_targets_with_ignore_label(segi, add_binary_target=b), z[f"bwi_{b}"])
+        np.testing.assert_array_equal(olabels.boundary_targets_with_ignore_label(seg2, ignore_label=0, add_binary_target=b), z[f"bwi2d_{b}"])
+    np.testing.assert_array_equal(olabels.one_hot_targets(sem), z["onehot_none"])
+    np.testing.assert_array_equal(olabels.one_hot_targets(sem, 4), z["onehot_4"])
+    np.testing.assert_array_equal(olabels.one_hot_targets(sem, [3, 1, 7]), z["onehot_list"])
+    np.testing.assert_array_equal(olabels.segmentation_to_affinities(z["segb"], z["offs3"].tolist()), z["segaffs3"])
+    np.testing.assert_array_equal(olabels.segmentation_to_affinities(seg2[None, None], z["offs2"].tolist()), z["segaffs2"])

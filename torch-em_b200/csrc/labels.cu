@@ -97,6 +97,77 @@ boundary_targets_kernel(const long long* __restrict__ labels, float* __restrict_
     }
 }
 
+// Boundary targets with a masked transition class (label.py:133-244).  A voxel is a boundary of image f iff some in-bounds
+// 6-neighbour q has f(q) != f(p) (find_boundaries "thick" on f).
+//   mode 1  NoToBackgroundBoundaryTransform(bg_label, mask_label):   boundary of [lab != bg_label]  -> mask_label
+//   mode 2  BoundaryTransformWithIgnoreLabel(ignore_label = aux):    boundary of [lab == aux]       -> aux
+//   elsewhere the ordinary label boundary (0 / 1).  Optional channel 0: [lab != bg] with lab == aux -> aux.
+// out (N, 1|2, D,H,W) fp32 holding -1 / 0 / 1 style values (the reference returns int8; targets are consumed as floats).
+__global__ void __launch_bounds__(256)
+boundary_targets_masked_kernel(const long long* __restrict__ labels, float* __restrict__ out, int D, int H, int W,
+                               int add_binary_target, int mode, long long aux, long long bg) {
+    const int n = blockIdx.y;
+    const int64_t S = (int64_t)D * H * W;
+    const long long* lab = labels + (size_t)n * S;
+    float* o = out + (size_t)n * (add_binary_target ? 2 : 1) * S;
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+        const long long lp = lab[s];
+        const bool fp = mode == 1 ? lp != bg : lp == aux;      // the binary image whose boundaries are masked
+        bool b = false, bm = false;
+        auto visit = [&](long long lq) {
+            b |= lq != lp;
+            bm |= (mode == 1 ? lq != bg : lq == aux) != fp;
+        };
+        if (w > 0) visit(lab[s - 1]);
+        if (w < W - 1) visit(lab[s + 1]);
+        if (h > 0) visit(lab[s - W]);
+        if (h < H - 1) visit(lab[s + W]);
+        if (d > 0) visit(lab[s - (int64_t)W * H]);
+        if (d < D - 1) visit(lab[s + (int64_t)W * H]);
+        const float bv = bm ? (float)aux : (b ? 1.f : 0.f);
+        if (add_binary_target) {
+            const float bin = lp == aux ? (float)aux : (lp != (mode == 1 ? bg : 0) ? 1.f : 0.f);
+            o[s] = bin;
+            o[S + s] = bv;
+        } else {
+            o[s] = bv;
+        }
+    }
+}
+
+// OneHotTransform (label.py:330-353): out (N, n_classes, S) fp32, out[n][k][s] = [lab[n][s] == class_ids[k]]
+__global__ void __launch_bounds__(256)
+one_hot_kernel(const long long* __restrict__ labels, const long long* __restrict__ class_ids, int n_classes, int64_t S,
+               float* __restrict__ out) {
+    const int n = blockIdx.y;
+    const long long* lab = labels + (size_t)n * S;
+    float* o = out + (size_t)n * n_classes * S;
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        const long long lp = lab[s];
+        for (int k = 0; k < n_classes; ++k) o[(size_t)k * S + s] = lp == class_ids[k] ? 1.f : 0.f;
+    }
+}
+
+// segmentation_to_affinities (loss/affinity_side_loss.py:70-89): AFFINITIES (1 = same segment) against the segment at
+// p + offset with REPLICATION at the border (the neighbour index is clamped into the volume), no masks.
+__global__ void __launch_bounds__(256)
+segmentation_affinities_kernel(const long long* __restrict__ labels, float* __restrict__ out, int D, int H, int W,
+                               OffsetTable offs) {
+    const int n = blockIdx.y;
+    const int64_t S = (int64_t)D * H * W;
+    const long long* lab = labels + (size_t)n * S;
+    float* o = out + (size_t)n * offs.n * S;
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+        const long long lp = lab[s];
+        for (int c = 0; c < offs.n; ++c) {
+            const int qd = min(max(d + offs.d[c], 0), D - 1), qh = min(max(h + offs.h[c], 0), H - 1), qw = min(max(w + offs.w[c], 0), W - 1);
+            o[(size_t)c * S + s] = lab[((size_t)qd * H + qh) * W + qw] == lp ? 1.f : 0.f;
+        }
+    }
+}
+
 constexpr int AD_PER_THREAD = 8;                       // voxels per thread
 constexpr int AD_CHUNK = 256 * AD_PER_THREAD;          // voxels per block
 
@@ -238,6 +309,36 @@ int b200em_boundary_targets(const int64_t* labels, float* out, int N, int D, int
     B2_CHECK_ARG(labels && out && N > 0 && D > 0 && H > 0 && W > 0, "boundary_targets: bad arguments");
     dim3 grid(flat_blocks((int64_t)D * H * W, N), (unsigned)N);
     boundary_targets_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, out, D, H, W, add_binary_target);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_boundary_targets_masked(const int64_t* labels, float* out, int N, int D, int H, int W, int add_binary_target,
+                                   int mode, int64_t aux_label, int64_t bg_label, void* stream) {
+    B2_CHECK_ARG(labels && out && N > 0 && D > 0 && H > 0 && W > 0, "boundary_targets_masked: bad arguments");
+    B2_CHECK_ARG(mode == 1 || mode == 2, "boundary_targets_masked: mode must be 1 (no-to-background) or 2 (ignore label)");
+    dim3 grid(flat_blocks((int64_t)D * H * W, N), (unsigned)N);
+    boundary_targets_masked_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, out, D, H, W, add_binary_target,
+                                                                            mode, (long long)aux_label, (long long)bg_label);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_one_hot(const int64_t* labels, const int64_t* class_ids, int n_classes, float* out, int N, int64_t S, void* stream) {
+    B2_CHECK_ARG(labels && class_ids && out && N > 0 && S > 0 && n_classes > 0, "one_hot: bad arguments");
+    dim3 grid(flat_blocks(S, N), (unsigned)N);
+    one_hot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, (const long long*)class_ids, n_classes, S, out);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_segmentation_affinities(const int64_t* labels, float* out, int N, int D, int H, int W, const int* offsets, int n_off,
+                                   void* stream) {
+    B2_CHECK_ARG(labels && out && N > 0 && D > 0 && H > 0 && W > 0, "segmentation_affinities: bad arguments");
+    OffsetTable t;
+    if (fill_offsets(t, offsets, n_off)) return 1;
+    dim3 grid(flat_blocks((int64_t)D * H * W, N), (unsigned)N);
+    segmentation_affinities_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, out, D, H, W, t);
     B2_LAUNCH_CHECK();
     return 0;
 }

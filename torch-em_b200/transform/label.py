@@ -14,7 +14,8 @@ import torch
 
 from .._lib import call
 
-__all__ = ["AffinityTransform", "BoundaryTransform", "labels_to_binary"]
+__all__ = ["AffinityTransform", "BoundaryTransform", "NoToBackgroundBoundaryTransform", "BoundaryTransformWithIgnoreLabel",
+           "OneHotTransform", "segmentation_to_affinities", "labels_to_binary"]
 
 
 def _stream(t):
@@ -110,3 +111,100 @@ class BoundaryTransform:
         if ndim == 2:
             out = out[:, :, 0]
         return out if batched else out[0]
+
+
+class _MaskedBoundaryTransform:
+    _mode = 0
+
+    def _run(self, labels, aux, bg):
+        ndim = self.ndim if self.ndim is not None else (labels.dim() if labels.dim() <= 3 else 3)
+        x, batched = _canon_labels(labels, ndim)
+        N, D, H, W = x.shape
+        out = torch.empty((N, 2 if self.add_binary_target else 1, D, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            call("b200em_boundary_targets_masked", _vp(x), _vp(out), N, D, H, W, int(self.add_binary_target), self._mode,
+                 int(aux), int(bg), _stream(x))
+        if ndim == 2:
+            out = out[:, :, 0]
+        return out if batched else out[0]
+
+
+class NoToBackgroundBoundaryTransform(_MaskedBoundaryTransform):
+    """Boundaries, with the boundaries TO the background set to ``mask_label`` (label.py:133-189).  float32 output
+    (the reference returns int8 holding the same -1 / 0 / 1 values)."""
+    _mode = 1
+
+    def __init__(self, bg_label: int = 0, mask_label: int = -1, mode: str = "thick", add_binary_target: bool = False,
+                 ndim: Optional[int] = None):
+        if mode != "thick":
+            raise NotImplementedError("only mode='thick' (the reference default) is implemented on the GPU path")
+        self.bg_label = bg_label
+        self.mask_label = mask_label
+        self.mode = mode
+        self.ndim = ndim
+        self.add_binary_target = add_binary_target
+
+    def __call__(self, labels: torch.Tensor) -> torch.Tensor:
+        return self._run(labels, self.mask_label, self.bg_label)
+
+
+class BoundaryTransformWithIgnoreLabel(_MaskedBoundaryTransform):
+    """Boundaries, with the boundaries of the ignore region set to ``ignore_label`` (label.py:192-244).  float32 output."""
+    _mode = 2
+
+    def __init__(self, ignore_label: int = -1, mode: str = "thick", add_binary_target: bool = False, ndim: Optional[int] = None):
+        if mode != "thick":
+            raise NotImplementedError("only mode='thick' (the reference default) is implemented on the GPU path")
+        self.ignore_label = ignore_label
+        self.mode = mode
+        self.ndim = ndim
+        self.add_binary_target = add_binary_target
+
+    def __call__(self, labels: torch.Tensor) -> torch.Tensor:
+        return self._run(labels, self.ignore_label, 0)
+
+
+class OneHotTransform:
+    """Semantic labels -> one-hot float32 channels (label.py:330-353).  Like the reference, the channel axis is prepended to
+    whatever shape the labels have: ``labels.shape -> (n_classes,) + labels.shape``; ``class_ids=None`` takes the sorted
+    unique labels of the input (one device->host synchronisation, as np.unique is data dependent)."""
+
+    def __init__(self, class_ids=None):
+        self.class_ids = list(range(class_ids)) if isinstance(class_ids, int) else class_ids
+
+    def __call__(self, labels: torch.Tensor) -> torch.Tensor:
+        if not torch.is_tensor(labels) or labels.device.type != "cuda":
+            raise RuntimeError("b200em label transforms take CUDA tensors (the CPU/numpy path is the reference's own)")
+        x = labels.to(torch.int64).contiguous()
+        if self.class_ids is None:
+            ids = torch.unique(x)
+        else:
+            ids = torch.tensor([int(c) for c in self.class_ids], dtype=torch.int64, device=x.device)
+        n_classes, S = int(ids.numel()), x.numel()
+        out = torch.empty((n_classes,) + tuple(x.shape), dtype=torch.float32, device=x.device)
+        if n_classes and S:
+            with torch.cuda.device(x.device):
+                call("b200em_one_hot", _vp(x), _vp(ids), n_classes, _vp(out), 1, S, _stream(x))
+        return out
+
+
+def segmentation_to_affinities(segmentation: torch.Tensor, offsets: List[List[int]]) -> torch.Tensor:
+    """(N, 1, *spatial) segmentation -> (N, len(offsets), *spatial) float32 AFFINITIES (1 = same segment) with replication
+    at the border (torch_em/loss/affinity_side_loss.py:70-89), as one integer stencil pass."""
+    assert segmentation.shape[1] == 1, f"{segmentation.shape}"
+    if segmentation.device.type != "cuda":
+        raise RuntimeError("b200em label transforms take CUDA tensors (the CPU/numpy path is the reference's own)")
+    ndim, c_offsets = offsets_to_3d(offsets)
+    assert segmentation.dim() == ndim + 2
+    seg = segmentation[:, 0]
+    if seg.is_floating_point():
+        seg = (seg.float() + 0.0).contiguous().view(torch.int32)     # equal floats <=> equal bit patterns (-0 folded into +0)
+    x = seg.to(torch.int64)
+    if ndim == 2:
+        x = x[:, None]
+    x = x.contiguous()
+    N, D, H, W = x.shape
+    out = torch.empty((N, len(offsets), D, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        call("b200em_segmentation_affinities", _vp(x), _vp(out), N, D, H, W, c_offsets, len(offsets), _stream(x))
+    return out[:, :, 0] if ndim == 2 else out
