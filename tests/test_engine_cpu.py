@@ -83,9 +83,12 @@ def test_constructor_surface():
         net(torch.zeros(1, 1, 12, 16, 16))
     with pytest.raises(ValueError, match="Invalid activation"):
         tb.UNet3d(1, 1, depth=1, final_activation="NoSuchActivation")
-    for kw in (dict(norm="BatchNorm"), dict(return_side_outputs=True), dict(postprocessing="affinities_to_boundaries3d")):
+    # what cannot be fused is refused loudly instead of falling back silently
+    class MyBlock(torch.nn.Module):
+        pass
+    for kw in (dict(conv_block_impl=MyBlock), dict(out_channels=None), dict(final_activation="Softmax"), dict(kernel_size=5, padding=2)):
         with pytest.raises(NotImplementedError):
-            tb.UNet3d(1, 1, depth=1, **kw)
+            tb.UNet3d(**{**dict(in_channels=1, out_channels=1, depth=1), **kw})
 
 
 def test_no_cpu_fallback():

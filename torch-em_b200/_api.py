@@ -2,11 +2,11 @@
 from . import _lib, distributed, util
 from .loss import (AffinityLoss, ApplyAndRemoveMask, ApplyMask, BCEDiceLoss, BCEDiceLossWithLogits, CombinedLoss, DiceBasedDistanceLoss,
                    DiceLoss, DiceLossWithLogits, DistanceLoss, LossWrapper, MaskIgnoreLabel, dice_score)
-from .model import AnisotropicUNet, UNet3d
+from .model import AnisotropicUNet, UNet2d, UNet3d
 from .transform import (AffinityTransform, BoundaryTransform, BoundaryTransformWithIgnoreLabel, NoToBackgroundBoundaryTransform,
                         OneHotTransform, segmentation_to_affinities)
 
-__all__ = ["UNet3d", "AnisotropicUNet", "DiceLoss", "DiceLossWithLogits", "BCEDiceLoss", "BCEDiceLossWithLogits", "CombinedLoss",
+__all__ = ["UNet2d", "UNet3d", "AnisotropicUNet", "DiceLoss", "DiceLossWithLogits", "BCEDiceLoss", "BCEDiceLossWithLogits", "CombinedLoss",
            "DistanceLoss", "DiceBasedDistanceLoss", "dice_score", "LossWrapper", "ApplyMask", "ApplyAndRemoveMask",
            "MaskIgnoreLabel", "AffinityLoss", "AffinityTransform", "BoundaryTransform", "NoToBackgroundBoundaryTransform",
            "BoundaryTransformWithIgnoreLabel", "OneHotTransform", "segmentation_to_affinities", "launch_count",

@@ -881,7 +881,8 @@ int b200em_norm_bwd_apply(const void* g, int64_t g_ld, const void* x, int64_t x_
 int b200em_maxpool3d_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int dtype, int N, int D, int H, int W, int C,
                          int fd, int fh, int fw, float* sums, void* stream) {
     B2_CHECK_ARG(x && y && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "maxpool3d_fwd: bad arguments");
-    B2_CHECK_ARG(D % fd == 0 && H % fh == 0 && W % fw == 0, "maxpool3d_fwd: (%d,%d,%d) not divisible by (%d,%d,%d)", D, H, W, fd, fh, fw);
+    // like nn.MaxPool3d, trailing voxels that do not fill a window are ignored (output dims = floor(dims / factor))
+    B2_CHECK_ARG(D >= fd && H >= fh && W >= fw, "maxpool3d_fwd: (%d,%d,%d) smaller than the window (%d,%d,%d)", D, H, W, fd, fh, fw);
     int64_t So = (int64_t)(D / fd) * (H / fh) * (W / fw);
     B2_DISPATCH_DTYPE(dtype, T, {
         constexpr int V = FullVec<T>::value;
@@ -906,7 +907,8 @@ int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp
                          void* out, int64_t out_ld, int dtype, int N, int D, int H, int W, int C, int fd, int fh, int fw,
                          int relu_mask, void* stream) {
     B2_CHECK_ARG(x && dp && out && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "maxpool3d_bwd: bad arguments");
-    B2_CHECK_ARG(D % fd == 0 && H % fh == 0 && W % fw == 0, "maxpool3d_bwd: dims not divisible by factors");
+    // voxels beyond the last full window are NOT written (the caller initialises them: they receive no pooled gradient)
+    B2_CHECK_ARG(D >= fd && H >= fh && W >= fw, "maxpool3d_bwd: dims smaller than the window");
     B2_CHECK_ARG((int64_t)D * H * W * C < (1LL << 31) && N <= 65535, "maxpool3d_bwd: sample too large for 32-bit indexing");
     int64_t So = (int64_t)(D / fd) * (H / fh) * (W / fw);
     B2_DISPATCH_DTYPE(dtype, T, {

@@ -57,6 +57,7 @@ class Plan:
     dec: List[BlockSpec] = field(default_factory=list)
     samplers: List[ConvSpec] = field(default_factory=list)
     out_conv: ConvSpec = None
+    side_convs: List[ConvSpec] = None        # return_side_outputs=True: one 1x1x1 head per decoder level (unet.py:211-227)
 
     @property
     def depth(self):
@@ -83,14 +84,21 @@ def level_kernels(scale_factors, anisotropic_kernel):
     return [k] * len(scale_factors)
 
 
+AFFINE_NORMS = ("GroupNorm", "BatchNorm", "InstanceNormTrackStats")     # norms with gamma / beta parameters (unet.py:391-406)
+RUNNING_NORMS = ("BatchNorm", "InstanceNormTrackStats")                 # ... and running statistics used in eval mode
+NORM_MOMENTUM = {"BatchNorm": 0.1, "InstanceNormTrackStats": 0.01}      # nn.BatchNorm3d default / unet.py:398
+
+
 def make_plan(in_channels, out_channels, scale_factors, initial_features=32, gain=2, norm="InstanceNorm",
-              final_activation=None, anisotropic_kernel=False) -> Plan:
+              final_activation=None, anisotropic_kernel=False, side_outputs=False, dim=3) -> Plan:
+    """dim=2: the 2-D U-Net (unet.py:481-563) as the D = 1 special case -- (1,3,3) kernels everywhere (base included),
+    (1,2,2) pooling, and bilinear up-sampling = trilinear with factor 1 along depth."""
     sfs = [_as_factor(sf) for sf in scale_factors]
     depth = len(sfs)
     enc_f = [in_channels] + [initial_features * gain ** i for i in range(depth)]
     dec_f = [initial_features * gain ** i for i in range(depth + 1)][::-1]
     ci = (1, 4) if norm is not None else (0, 2)
-    gn = norm == "GroupNorm"
+    gn = norm in AFFINE_NORMS
 
     def block(prefix, cin, cout, k):
         return BlockSpec(prefix,
@@ -99,13 +107,20 @@ def make_plan(in_channels, out_channels, scale_factors, initial_features=32, gai
                          f"{prefix}.block.0" if gn else None, f"{prefix}.block.3" if gn else None)
 
     plan = Plan(in_channels, out_channels, sfs, norm, final_activation)
-    ek = level_kernels(sfs, anisotropic_kernel)
+    if dim == 2:
+        ek = dk = [(1, 3, 3)] * depth
+        base_k = (1, 3, 3)
+    else:
+        ek = level_kernels(sfs, anisotropic_kernel)
+        dk = level_kernels(sfs[::-1], anisotropic_kernel)
+        base_k = (3, 3, 3)
     plan.enc = [block(f"encoder.blocks.{l}", enc_f[l], enc_f[l + 1], ek[l]) for l in range(depth)]
-    plan.base = block("base", enc_f[-1], enc_f[-1] * gain, (3, 3, 3))
-    dk = level_kernels(sfs[::-1], anisotropic_kernel)
+    plan.base = block("base", enc_f[-1], enc_f[-1] * gain, base_k)
     plan.dec = [block(f"decoder.blocks.{l}", dec_f[l], dec_f[l + 1], dk[l]) for l in range(depth)]
     plan.samplers = [ConvSpec(f"decoder.samplers.{l}.conv", dec_f[l], dec_f[l + 1], (1, 1, 1)) for l in range(depth)]
-    if out_channels is not None:
+    if side_outputs:
+        plan.side_convs = [ConvSpec(f"out_conv.{l}", dec_f[l + 1], out_channels[l], (1, 1, 1)) for l in range(depth)]
+    elif out_channels is not None:
         plan.out_conv = ConvSpec("out_conv", dec_f[-1], out_channels, (1, 1, 1))
     return plan
 
@@ -123,7 +138,7 @@ def check_shape(spatial, scale_factors):
 
 
 def _groups(norm, c):
-    return c if norm == "InstanceNorm" else min(32, c)
+    return min(32, c) if norm == "GroupNorm" else c
 
 
 class _Ctx:
@@ -134,46 +149,119 @@ class _Ctx:
         self.misc = {}
 
 
-def _run_block(B, plan, P, spec: BlockSpec, x_in, sums_in, out, want_out_sums, ctx, packs):
+def _norm_forward(B, plan, P, bufs, key, sums, S, C, training):
+    """Per-(n, c) ``(scale, shift)`` and ``(mean, rstd)`` of one norm layer from the per-(n, c) sums of its input.
+
+    InstanceNorm / GroupNorm: statistics of the sample (identical in train and eval mode).  BatchNorm: statistics of the whole
+    batch in training mode.  BatchNorm / InstanceNormTrackStats additionally keep running statistics (updated here in training
+    mode exactly like ATen: momentum update with the UNBIASED variance) and use them in eval mode (unet.py:391-406).
+    The parameter-sized bookkeeping below (C or N x C floats) is done with torch ops on the device; the per-voxel work is in
+    the kernels."""
+    norm = plan.norm
+    gamma = P[key + ".weight"] if key is not None and norm in AFFINE_NORMS else None
+    beta = P[key + ".bias"] if key is not None and norm in AFFINE_NORMS else None
+    N = sums.shape[0]
+    if norm in RUNNING_NORMS and not training:
+        rm, rv = bufs[key + ".running_mean"], bufs[key + ".running_var"]
+        rstd = torch.rsqrt(rv + EPS)
+        scale = rstd * gamma.detach()
+        ss = torch.stack([scale, beta.detach() - rm * scale], -1)[None].expand(N, C, 2).contiguous()
+        mr = torch.stack([rm, rstd], -1)[None].expand(N, C, 2).contiguous()
+        return ss, mr, "fixed"
+    if norm == "BatchNorm":
+        sums_b = sums.sum(0, keepdim=True).expand(N, C, 2).contiguous()
+        ss, mr = B.norm_finalize(sums_b, N * S, C, gamma, beta, EPS)
+        cnt = N * S
+        mode = "batch"
+    else:
+        ss, mr = B.norm_finalize(sums, S, _groups(norm, C), gamma, beta, EPS)
+        cnt = S
+        mode = "sample"
+    if norm in RUNNING_NORMS:
+        with torch.no_grad():
+            m = NORM_MOMENTUM[norm]
+            mean = mr[..., 0].mean(0)
+            var_b = (1.0 / (mr[..., 1] * mr[..., 1]) - EPS).clamp_(min=0.0)      # biased variance back from rstd
+            var_u = (var_b * (cnt / max(cnt - 1, 1))).mean(0)
+            bufs[key + ".running_mean"].mul_(1 - m).add_(mean, alpha=m)
+            bufs[key + ".running_var"].mul_(1 - m).add_(var_u, alpha=m)
+            if norm == "BatchNorm":                     # nn.InstanceNorm3d keeps the counter but never advances it
+                bufs[key + ".num_batches_tracked"].add_(1)
+    return ss, mr, mode
+
+
+def _norm_backward_coef(B, plan, P, key, dsums, mr, mode, S, C, grads):
+    """coef[n, c] = (c0, c1, c2) with dx = c0 * g + c1 * x + c2, and the gamma / beta gradients accumulated into ``grads``."""
+    norm = plan.norm
+    affine = key is not None and norm in AFFINE_NORMS
+    gamma = P[key + ".weight"] if affine else None
+    dgamma = grads[key + ".weight"] if affine else None
+    dbeta = grads[key + ".bias"] if affine else None
+    N = dsums.shape[0]
+    if mode == "sample":
+        return B.norm_bwd_finalize(dsums, mr, gamma, S, _groups(norm, C), dgamma, dbeta)
+    sg, sgx = dsums[..., 0], dsums[..., 1]
+    mean, rstd = mr[..., 0], mr[..., 1]
+    dgamma += (rstd * (sgx - mean * sg)).sum(0)
+    dbeta += sg.sum(0)
+    if mode == "fixed":                                   # running statistics are constants: dx = gamma * rstd * g
+        c0 = rstd * gamma.detach()
+        return torch.stack([c0, torch.zeros_like(c0), torch.zeros_like(c0)], -1).contiguous()
+    dsums_b = dsums.sum(0, keepdim=True).expand(N, C, 2).contiguous()        # "batch": one statistic over (n, voxels)
+    return B.norm_bwd_finalize(dsums_b, mr, gamma, N * S, C, None, None)
+
+
+def _run_block(B, plan, P, bufs, spec: BlockSpec, x_in, sums_in, out, want_out_sums, ctx, packs, training):
     N, D, H, W, _ = x_in.shape
     S = D * H * W
     dev = x_in.device
     norm = plan.norm
     rec = {"x_in": x_in}
-    ss1 = mr1 = ss2 = mr2 = None
+    ss1 = mr1 = ss2 = mr2 = m1 = m2 = None
     c1, c2 = spec.conv1, spec.conv2
     if norm == "InstanceNorm" and S == 1:
         # F.instance_norm refuses a single spatial element when it uses the input statistics (torch/nn/functional.py
         # _verify_spatial_size) -- nn.InstanceNorm3d without running stats always does, also in eval mode
         raise ValueError(f"Expected more than 1 spatial element when training, got input size {(N, c1.cin, D, H, W)}")
     if norm is not None:
-        g1 = P[spec.norm1_key + ".weight"] if spec.norm1_key else None
-        b1 = P[spec.norm1_key + ".bias"] if spec.norm1_key else None
-        ss1, mr1 = B.norm_finalize(sums_in, S, _groups(norm, c1.cin), g1, b1, EPS)
+        ss1, mr1, m1 = _norm_forward(B, plan, P, bufs, spec.norm1_key, sums_in, S, c1.cin, training)
     y1 = torch.empty((N, D, H, W, c1.cout), dtype=x_in.dtype, device=dev)
     sums1 = torch.zeros((N, c1.cout, 2), dtype=torch.float32, device=dev) if norm is not None else None
     aux1 = B.conv(x_in, ss1, packs[c1.key], P[c1.key + ".bias"], y1, sums1, c1.kernel, relu=True, dgrad=False)
     if norm is not None:
-        g2 = P[spec.norm2_key + ".weight"] if spec.norm2_key else None
-        b2 = P[spec.norm2_key + ".bias"] if spec.norm2_key else None
-        ss2, mr2 = B.norm_finalize(sums1, S, _groups(norm, c2.cin), g2, b2, EPS)
+        ss2, mr2, m2 = _norm_forward(B, plan, P, bufs, spec.norm2_key, sums1, S, c2.cin, training)
     sums2 = None
     if want_out_sums and norm is not None:
         sums2 = torch.zeros((N, c2.cout, 2), dtype=torch.float32, device=dev)
     B.conv(y1, ss2, packs[c2.key], P[c2.key + ".bias"], out, sums2, c2.kernel, relu=True, dgrad=False)
-    rec.update(ss1=ss1, mr1=mr1, y1=y1, ss2=ss2, mr2=mr2, y2=out, aux1=aux1)
+    rec.update(ss1=ss1, mr1=mr1, y1=y1, ss2=ss2, mr2=mr2, y2=out, aux1=aux1, m1=m1, m2=m2)
     ctx.blocks[spec.prefix] = rec
     return sums2
 
 
-def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act_dtype, packs):
-    """x: (N, Cin, D, H, W) fp32 NCDHW on the device.  Returns (prediction NCDHW fp32, ctx)."""
+def _crop_slices(full, target):
+    """Decoder._crop (unet.py:363-366): centre crop of the spatial dims ``full`` to ``target``."""
+    sl = []
+    for f, t in zip(full, target):
+        sd = (f - t) // 2
+        if f - 2 * sd != t:
+            # the reference's crop keeps f - 2*sd voxels, so an ODD difference ends in torch.cat's size error (unet.py:372-373)
+            raise RuntimeError(f"Sizes of tensors must match except in dimension 1. Expected size {t} but got size {f - 2 * sd} "
+                               "for the cropped skip connection (Decoder._crop only handles even size differences)")
+        sl.append(slice(sd, f - sd))
+    return tuple(sl)
+
+
+def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act_dtype, packs, bufs=None, training=True):
+    """x: (N, Cin, D, H, W) fp32 NCDHW on the device.  Returns (list of NCDHW fp32 predictions -- one entry, or the side
+    outputs with the full-resolution one first (unet.py:211-227) --, ctx)."""
     if x.dim() != 5:
         raise ValueError(f"Invalid shape for U-Net: dimensions don't agree {x.dim() - 2} != 3")
     N, Cin, D, H, W = x.shape
     dev = x.device
     depth = plan.depth
     norm = plan.norm
+    bufs = bufs or {}
     ctx = _Ctx()
     x = x.contiguous()
     if x.dtype != torch.float32:
@@ -187,27 +275,47 @@ def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act
         cur_sums = torch.zeros((N, Cin, 2), dtype=torch.float32, device=dev)
         B.channel_sums(a, cur_sums)
     dims = (D, H, W)
-    cats, skip_sums, level_dims = [], [], []
+    # spatial dims on the way down (floor division, like nn.MaxPool3d) and on the way up (x factor): they differ from the
+    # encoder's only for shapes the shape check would refuse (check_shape=False); the skip is then centre-cropped
+    enc_dims = [dims]
+    for l in range(depth):
+        enc_dims.append(tuple(d // ff for d, ff in zip(enc_dims[-1], plan.scale_factors[l])))
+    if any(d < 1 for d in enc_dims[-1]):
+        raise ValueError(f"Invalid shape for U-Net: {(D, H, W)} is too small for {depth} pooling levels")
+    dec_dims = [None] * depth
+    up = enc_dims[depth]
+    for lvl in reversed(range(depth)):
+        up = tuple(d * ff for d, ff in zip(up, plan.scale_factors[lvl]))
+        dec_dims[lvl] = up
+    cats, skip_sums, skips_full = [], [], []
     for l in range(depth):
         spec = plan.enc[l]
         C = spec.conv2.cout
-        cat = torch.empty((N,) + dims + (2 * C,), dtype=act_dtype, device=dev)
-        skip = cat[..., C:]
-        s2 = _run_block(B, plan, P, spec, cur, cur_sums, skip, True, ctx, packs)
+        dims = enc_dims[l]
+        cropped = dec_dims[l] != dims
+        cat = torch.empty((N,) + dec_dims[l] + (2 * C,), dtype=act_dtype, device=dev)
+        skip = torch.empty((N,) + dims + (C,), dtype=act_dtype, device=dev) if cropped else cat[..., C:]
+        s2 = _run_block(B, plan, P, bufs, spec, cur, cur_sums, skip, not cropped, ctx, packs, training)
+        if cropped:
+            sl = _crop_slices(dims, dec_dims[l])
+            cat[..., C:].copy_(skip[(slice(None),) + sl])
+            if norm is not None:
+                s2 = torch.zeros((N, C, 2), dtype=torch.float32, device=dev)
+                B.channel_sums(cat[..., C:], s2)
         cats.append(cat)
         skip_sums.append(s2)
-        level_dims.append(dims)
+        skips_full.append(skip)
         f = plan.scale_factors[l]
-        dims = tuple(d // ff for d, ff in zip(dims, f))
-        pooled = torch.empty((N,) + dims + (C,), dtype=act_dtype, device=dev)
+        pooled = torch.empty((N,) + enc_dims[l + 1] + (C,), dtype=act_dtype, device=dev)
         psums = torch.zeros((N, C, 2), dtype=torch.float32, device=dev) if norm is not None else None
         B.maxpool_fwd(skip, pooled, f, psums)
         cur, cur_sums = pooled, psums
     spec = plan.base
+    dims = enc_dims[depth]
     base_out = torch.empty((N,) + dims + (spec.conv2.cout,), dtype=act_dtype, device=dev)
-    _run_block(B, plan, P, spec, cur, cur_sums, base_out, False, ctx, packs)
+    _run_block(B, plan, P, bufs, spec, cur, cur_sums, base_out, False, ctx, packs, training)
     cur = base_out
-    zlows = []
+    zlows, dec_outs = [], []
     for i in range(depth):
         lvl = depth - 1 - i
         spec = plan.dec[i]
@@ -216,7 +324,7 @@ def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act
         f = plan.scale_factors[lvl]
         z_low = torch.empty((N,) + dims + (C,), dtype=act_dtype, device=dev)
         B.conv(cur, None, packs[samp.key], P[samp.key + ".bias"], z_low, None, samp.kernel, relu=False, dgrad=False)
-        dims = level_dims[lvl]
+        dims = dec_dims[lvl]
         cat = cats[lvl]
         up = cat[..., :C]
         up_sums = torch.zeros((N, C, 2), dtype=torch.float32, device=dev) if norm is not None else None
@@ -224,16 +332,27 @@ def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act
         zlows.append((cur, z_low.shape))
         cat_sums = torch.cat([up_sums, skip_sums[lvl]], dim=1) if norm is not None else None
         out = torch.empty((N,) + dims + (spec.conv2.cout,), dtype=act_dtype, device=dev)
-        _run_block(B, plan, P, spec, cat, cat_sums, out, False, ctx, packs)
+        _run_block(B, plan, P, bufs, spec, cat, cat_sums, out, False, ctx, packs, training)
         cur = out
-    if plan.out_conv is None:
-        raise NotImplementedError("out_channels=None (feature output) is not on the accelerated path")
-    oc = plan.out_conv
-    pred = torch.empty((N, oc.cout, D, H, W), dtype=torch.float32, device=dev)
-    B.head_fwd(cur, P[oc.key + ".weight"], P[oc.key + ".bias"], pred, plan.final_activation)
-    ctx.misc.update(cats=cats, level_dims=level_dims, sampler_in=zlows, y_last=cur, pred=pred, act_dtype=act_dtype,
-                    first_input=a)
-    return pred, ctx
+        dec_outs.append(out)
+    preds = []
+    if plan.side_convs is not None:
+        for i, oc in enumerate(plan.side_convs):
+            y = dec_outs[i]
+            pr = torch.empty((N, oc.cout) + tuple(y.shape[1:4]), dtype=torch.float32, device=dev)
+            B.head_fwd(y, P[oc.key + ".weight"], P[oc.key + ".bias"], pr, plan.final_activation)
+            preds.append(pr)
+        preds = preds[::-1]                               # full-resolution output first (unet.py:226-227)
+    else:
+        if plan.out_conv is None:
+            raise NotImplementedError("out_channels=None (feature output) is not on the accelerated path")
+        oc = plan.out_conv
+        pred = torch.empty((N, oc.cout) + tuple(cur.shape[1:4]), dtype=torch.float32, device=dev)
+        B.head_fwd(cur, P[oc.key + ".weight"], P[oc.key + ".bias"], pred, plan.final_activation)
+        preds = [pred]
+    ctx.misc.update(cats=cats, enc_dims=enc_dims, dec_dims=dec_dims, sampler_in=zlows, dec_outs=dec_outs, act_dtype=act_dtype,
+                    first_input=a, skips_full=skips_full)
+    return preds, ctx
 
 
 def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs):
@@ -247,7 +366,7 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
     dev = y1.device
     f32 = dict(dtype=torch.float32, device=dev)
 
-    def dgrad_and_norm_back(dz, conv, x, mr, gamma_key, out, relu_mask):
+    def dgrad_and_norm_back(dz, conv, x, mr, mode, norm_key, out, relu_mask):
         """g = dgrad(dz) (gradient w.r.t. the norm OUTPUT), then the norm backward (+ the producer's ReLU mask) -> out.
         The two norm-backward reductions (sum g, sum g*x) come out of the dgrad kernel's epilogue."""
         C = conv.cin
@@ -260,11 +379,7 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
             return out
         dsums = torch.zeros((N, C, 2), **f32)
         B.conv(dz, None, packs[conv.key], None, g, dsums, conv.kernel, relu=False, dgrad=True, dot_x=x)
-        gamma = P[gamma_key + ".weight"] if gamma_key else None
-        dgamma = dbeta = None
-        if gamma_key:
-            dgamma, dbeta = grads[gamma_key + ".weight"], grads[gamma_key + ".bias"]
-        coef = B.norm_bwd_finalize(dsums, mr, gamma, S, _groups(norm, C), dgamma, dbeta)
+        coef = _norm_backward_coef(B, plan, P, norm_key, dsums, mr, mode, S, C, grads)
         if out is None:
             out = torch.empty_like(g)
         B.norm_bwd_apply(g, x, coef, None, out, relu_mask)
@@ -272,12 +387,12 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
 
     # conv2
     B.wgrad(y1, rec["ss2"], dz2, grads[c2.key + ".weight"], grads[c2.key + ".bias"], c2.kernel)
-    dz1 = dgrad_and_norm_back(dz2, c2, y1, rec["mr2"], spec.norm2_key, torch.empty_like(y1), relu_mask=1)
+    dz1 = dgrad_and_norm_back(dz2, c2, y1, rec["mr2"], rec["m2"], spec.norm2_key, torch.empty_like(y1), relu_mask=1)
     # conv1
     B.wgrad(x_in, rec["ss1"], dz1, grads[c1.key + ".weight"], grads[c1.key + ".bias"], c1.kernel, aux=rec.get("aux1"))
     if not need_dx:
         return None
-    return dgrad_and_norm_back(dz1, c1, x_in, rec["mr1"], spec.norm1_key, None, relu_mask=0)
+    return dgrad_and_norm_back(dz1, c1, x_in, rec["mr1"], rec["m1"], spec.norm1_key, None, relu_mask=0)
 
 
 class FlatGrads(dict):
@@ -301,21 +416,42 @@ class FlatGrads(dict):
         return self[k]
 
 
-def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pred: torch.Tensor, packs):
-    """Returns {state-dict key: fp32 gradient} (a FlatGrads) for every parameter."""
+def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_preds, packs):
+    """grad_preds: list aligned with the predictions forward_pass returned (entries may be None for unused side outputs).
+    Returns {state-dict key: fp32 gradient} (a FlatGrads) for every parameter."""
     m = ctx.misc
     depth = plan.depth
     grads = FlatGrads(P)
-    y_last, pred = m["y_last"], m["pred"]
-    dev = y_last.device
-    f32 = dict(dtype=torch.float32, device=dev)
-    grad_pred = grad_pred.contiguous()
-    if grad_pred.dtype != torch.float32:
-        grad_pred = grad_pred.float()
-    oc = plan.out_conv
-    dz = torch.empty_like(y_last)
-    B.head_bwd(grad_pred, pred, y_last, P[oc.key + ".weight"], dz, grads[oc.key + ".weight"], grads[oc.key + ".bias"],
-               plan.final_activation, relu_mask=1)
+    preds = m["preds"]
+    dec_outs = m["dec_outs"]
+    dev = dec_outs[-1].device if dec_outs else preds[0].device
+    if torch.is_tensor(grad_preds):
+        grad_preds = [grad_preds]
+
+    def head_back(oc, gp, pred, y, relu_mask):
+        gp = gp.contiguous()
+        if gp.dtype != torch.float32:
+            gp = gp.float()
+        dx = torch.empty_like(y)
+        B.head_bwd(gp, pred, y, P[oc.key + ".weight"], dx, grads[oc.key + ".weight"], grads[oc.key + ".bias"],
+                   plan.final_activation, relu_mask=relu_mask)
+        return dx
+
+    # gradient entering every decoder block's output from ITS head (side outputs) -- the last block always has one
+    side = plan.side_convs is not None
+    head_dx = [None] * depth
+    if side:
+        for i in range(depth):
+            gp = grad_preds[depth - 1 - i]                 # predictions are returned full-resolution first
+            if gp is not None:
+                head_dx[i] = head_back(plan.side_convs[i], gp, preds[depth - 1 - i], dec_outs[i], relu_mask=1)
+    elif depth > 0:
+        head_dx[depth - 1] = head_back(plan.out_conv, grad_preds[0], preds[0], dec_outs[-1], relu_mask=1)
+    if depth == 0:
+        raise NotImplementedError("a U-Net without pooling levels is not on the accelerated path")
+    dz = head_dx[depth - 1]
+    if dz is None:                                         # no gradient reached the full-resolution output
+        dz = torch.zeros_like(dec_outs[-1])
 
     skip_grads = [None] * depth
     for i in reversed(range(depth)):
@@ -330,16 +466,28 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
         B.wgrad(x_low, None, d_zlow, grads[samp.key + ".weight"], grads[samp.key + ".bias"], samp.kernel)
         g = torch.empty_like(x_low)
         B.conv(d_zlow, None, packs[samp.key], None, g, None, samp.kernel, relu=False, dgrad=True)
-        # x_low is the post-ReLU output of the block below: apply its ReLU mask in place
-        B.norm_bwd_apply(g, x_low, None, None, g, 1)
+        # x_low is the post-ReLU output of the block below: add the gradient from that block's own head (side outputs), then
+        # apply its ReLU mask in place
+        add = head_dx[i - 1] if i > 0 else None
+        B.norm_bwd_apply(g, x_low, None, add, g, 1)
         dz = g
-    need_first_dx = plan.norm == "GroupNorm"      # the first norm's gamma/beta need the gradient w.r.t. its output
+    need_first_dx = plan.norm in AFFINE_NORMS          # the first norm's gamma/beta need the gradient w.r.t. its output
     d_p = _block_backward(B, plan, P, plan.base, ctx.blocks["base"], dz, depth > 0 or need_first_dx, grads, packs)
     for l in reversed(range(depth)):
         spec = plan.enc[l]
         rec = ctx.blocks[spec.prefix]
         skip = rec["y2"]
         dz = torch.empty(skip.shape, dtype=skip.dtype, device=dev)
-        B.maxpool_bwd(skip, d_p, skip_grads[l], dz, plan.scale_factors[l], 1)
+        f = plan.scale_factors[l]
+        sg = skip_grads[l]
+        dims, ddims = m["enc_dims"][l], m["dec_dims"][l]
+        if ddims != dims:
+            # check_shape=False with a non-divisible shape: the skip was centre-cropped (Decoder._crop), so its gradient is
+            # zero outside the crop; voxels beyond the last pooling window get no pooled gradient either
+            full = torch.zeros(skip.shape, dtype=skip.dtype, device=dev)
+            full[(slice(None),) + _crop_slices(dims, ddims)] = sg
+            B.norm_bwd_apply(full, skip, None, None, dz, 1)
+            sg = full
+        B.maxpool_bwd(skip, d_p, sg, dz, f, 1)
         d_p = _block_backward(B, plan, P, spec, rec, dz, l > 0 or need_first_dx, grads, packs)
     return grads

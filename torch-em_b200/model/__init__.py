@@ -1,3 +1,3 @@
-from .unet import AnisotropicUNet, UNet3d
+from .unet import AnisotropicUNet, UNet2d, UNet3d
 
-__all__ = ["AnisotropicUNet", "UNet3d"]
+__all__ = ["AnisotropicUNet", "UNet2d", "UNet3d"]
