@@ -266,6 +266,31 @@ int b200em_affinity_dice_bwd(const void* pred, int pred_dtype, const int64_t* la
                              int include_ignore_transitions, const float* coef, const float* gout, void* grad_pred,
                              int grad_dtype, void* stream);
 
+/* ---- tiled inference I/O (csrc/tiling.cu): predict_with_halo's per-block host work on a volume resident in HBM ----------
+ * (util/prediction.py:98-142 _load_block, transform/raw.py:40-65 standardize, prediction.py:287-309 crop + mask + write) */
+#define B200EM_MAX_TILE_BLOCKS 16
+#define B200EM_RAW_U8 0
+#define B200EM_RAW_I8 1
+#define B200EM_RAW_U16 2
+#define B200EM_RAW_I16 3
+#define B200EM_RAW_I32 4
+#define B200EM_RAW_U32 5
+#define B200EM_RAW_F16 6
+#define B200EM_RAW_F32 7
+#define B200EM_RAW_F64 8
+/* vol (C,D,H,W) raw dtype -> out (nblocks, C, bd,bh,bw) fp32: block i covers [begin_i, begin_i + (bd,bh,bw)) (begin = offset -
+ * halo, may be negative), clipped to the volume and completed by reflecting the clipped data (np.pad "reflect").  block_begins:
+ * 3*nblocks host ints.  stats (nullable) [nblocks][2] doubles += (sum, sum of squares) of each block (caller zeroes). */
+int b200em_gather_blocks(const void* vol, int raw_dtype, int C, int D, int H, int W, const int* block_begins, int nblocks, int bd,
+                         int bh, int bw, float* out, double* stats, void* stream);
+/* x (nblocks, per_block) fp32, in place: (x - mean) / (std + eps), population statistics from stats[nblocks][2]. */
+int b200em_standardize_blocks(float* x, int nblocks, int64_t per_block, const double* stats, float eps, void* stream);
+/* pred (nblocks, Cp, bd,bh,bw) fp32 -> out (nc, D,H,W) fp32: out[c, begin_i + v] = pred[i, c0 + c, halo + v] for v in the inner
+ * block shape_i (truncated last blocks), set to 0 where mask (nullable, (D,H,W) bytes) is 0.  begins / shapes: host ints. */
+int b200em_scatter_blocks(const float* pred, int Cp, int bd, int bh, int bw, int hd, int hh, int hw, const int* block_begins,
+                          const int* block_shapes, int nblocks, float* out, int D, int H, int W, int c0, int nc,
+                          const unsigned char* mask, void* stream);
+
 /* ---- utilities ---------------------------------------------------------------------------------------- */
 /* Write `bytes` bytes of zeros (L2 flush helper for bench.py and buffer clears without a torch launch). */
 int b200em_memset_zero(void* p, int64_t bytes, void* stream);

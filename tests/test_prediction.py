@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import prediction as opred
-from torch_em_b200.util import Blocking, predict_with_halo, standardize
+from torch_em_b200.util import Blocking, predict_with_halo, predict_with_halo_pipelined, standardize
 
 
 class TinyNet(torch.nn.Module):
@@ -66,12 +66,105 @@ def test_predict_with_halo_matches_oracle(shape, block_shape, halo):
     np.testing.assert_allclose(buf, ref_c, rtol=1e-4, atol=1e-5)
 
 
-def test_unsupported_arguments_raise():
+def _all_argument_cases(rng, shape):
+    """(name, kwargs for ours, kwargs for the oracle) covering every argument of prediction.py:145-164."""
+    mask = np.zeros(shape, dtype="uint8")
+    mask[2:-3, :shape[1] // 2, 3:] = 1
+    mask[rng.random(shape) < 0.2] = 0
+    return [
+        ("mask", dict(mask=mask), dict(mask=mask)),
+        ("roi", dict(roi=(slice(4, 20), slice(None), slice(8, None))), dict(roi=(slice(4, 20), slice(None), slice(8, None)))),
+        ("iter_list", dict(iter_list=[0, 3, 5]), dict(iter_list=[0, 3, 5])),
+        ("grid_shift", dict(grid_shift=(0.0, 0.25, 0.5)), dict(grid_shift=(0.0, 0.25, 0.5))),
+        ("grid_shift+mask", dict(grid_shift=(0.5, 0.0, 0.25), mask=mask), dict(grid_shift=(0.5, 0.0, 0.25), mask=mask)),
+        ("no preprocess", dict(preprocess=None), dict(preprocess=None)),
+    ]
+
+
+def check_all_arguments(device_ids, net, to_np_net):
+    rng = np.random.default_rng(4)
+    shape, block_shape, halo = (24, 20, 28), (16, 8, 16), (4, 4, 4)
+    vol = rng.random(shape).astype("float32")
+    for name, ours_kw, ref_kw in _all_argument_cases(rng, shape):
+        ref = opred.predict_with_halo(vol, to_np_net, block_shape, halo, n_out=2, **ref_kw)
+        out = predict_with_halo(vol, net, device_ids, block_shape, halo, **ours_kw)
+        assert out.shape == ref.shape, name
+        np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-5, err_msg=name)
+    # list of (array, channel slice) outputs, one of them without a channel axis; pre-filled outputs keep what is not written
+    o1, o2 = np.full((1,) + shape, 7.0, dtype="float32"), np.full(shape, 7.0, dtype="float32")
+    predict_with_halo(vol, net, device_ids, block_shape, halo, output=[(o1, np.s_[0:1]), (o2, 1)], iter_list=[1, 2])
+    r1, r2 = np.full((1,) + shape, 7.0, dtype="float32"), np.full(shape, 7.0, dtype="float32")
+    opred.predict_with_halo(vol, to_np_net, block_shape, halo, n_out=2, output=[(r1, np.s_[0:1]), (r2, 1)], iter_list=[1, 2])
+    np.testing.assert_allclose(o1, r1, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(o2, r2, rtol=1e-4, atol=1e-5)
+    # host callbacks (numpy in, numpy out) take the streaming path with the same results
+    skip = lambda a: bool(a.mean() > 0.505)                                   # noqa: E731
+    post = lambda p: p[:1] * 2.0                                              # noqa: E731
+    ref = opred.predict_with_halo(vol, to_np_net, block_shape, halo, n_out=1, skip_block=skip, postprocess=post,
+                                  output=np.zeros((1,) + shape, dtype="float32"))
+    out = predict_with_halo(vol, net, device_ids, block_shape, halo, skip_block=skip, postprocess=post,
+                            output=np.zeros((1,) + shape, dtype="float32"))
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-5)
+    # pipelined variant: same results, batches of blocks, grid_shift refused like the reference (prediction.py:555-559)
+    ref = opred.predict_with_halo(vol, to_np_net, block_shape, halo, n_out=2)
+    out = predict_with_halo_pipelined(vol, net, device_ids, block_shape, halo, batch_size=3, num_prefetch_workers=2)
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-5)
+    with pytest.raises(NotImplementedError, match="grid_shift"):
+        predict_with_halo_pipelined(vol, net, device_ids, block_shape, halo, grid_shift=(0, 0, 0.5))
+    with pytest.raises(ValueError, match="grid_shift"):
+        predict_with_halo(vol, net, device_ids, block_shape, halo, grid_shift=(0, 0, 0.5), output=np.zeros((2,) + shape, "float32"))
+
+
+def test_every_argument_matches_oracle_streaming_path():
+    net = TinyNet()
+    check_all_arguments(["cpu"], net, np_net(net))
+
+
+def test_argument_validation():
     vol = np.zeros((8, 8, 8), dtype="float32")
-    with pytest.raises(NotImplementedError):
-        predict_with_halo(vol, TinyNet(), ["cpu"], (8, 8, 8), (2, 2, 2), mask=np.ones((8, 8, 8)))
     with pytest.raises(ValueError):
         predict_with_halo(vol, TinyNet(), ["cpu"], (8, 8), (2, 2, 2))
+    with pytest.raises(ValueError):
+        predict_with_halo(vol, TinyNet(), [], (8, 8, 8), (2, 2, 2))
+
+
+@pytest.mark.gpu
+def test_every_argument_matches_oracle_device_path():
+    """The device-resident path (gather / standardize / scatter kernels of csrc/tiling.cu) with a plain torch model on the GPU."""
+    import torch_em_b200 as tb
+    net = TinyNet().to("cuda:0")
+    cpu = TinyNet()
+    tb.reset_launch_count()
+    check_all_arguments([0], net, np_net(cpu))
+    assert tb.launch_count() > 20, "the tiling kernels did not run"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["uint8", "uint16", "int16", "float64", "int64"])
+def test_device_path_raw_dtypes(dtype):
+    """EM volumes are usually uint8 / uint16: the gather kernel converts on the fly (torch has no uint16 index_select)."""
+    rng = np.random.default_rng(5)
+    vol = (rng.random((20, 24, 18)) * 200).astype(dtype)
+    net, cpu = TinyNet().to("cuda:0"), TinyNet()
+    ref = opred.predict_with_halo(vol, np_net(cpu), (8, 16, 16), (3, 2, 4), n_out=2)
+    out = predict_with_halo(vol, net, [0], (8, 16, 16), (3, 2, 4))
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_device_path_2d_and_channels():
+    class Net2d(torch.nn.Module):
+        out_channels = 3
+
+        def forward(self, x):
+            return torch.cat([x.mean(1, keepdim=True), torch.tanh(x[:, :1]), torch.nn.functional.avg_pool2d(x[:, 1:2], 3, 1, 1)], 1)
+
+    rng = np.random.default_rng(6)
+    vol = rng.random((2, 40, 52)).astype("float32")
+    net = Net2d()
+    ref = opred.predict_with_halo(vol, np_net(net), (16, 32), (4, 6), n_out=3, with_channels=True)
+    out = predict_with_halo(vol, net.to("cuda:0"), ["cuda:0"], (16, 32), (4, 6), with_channels=True)
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.gpu

@@ -1,3 +1,3 @@
-from .prediction import Blocking, predict_with_halo, standardize
+from .prediction import Blocking, predict_with_halo, predict_with_halo_pipelined, standardize
 
-__all__ = ["Blocking", "predict_with_halo", "standardize"]
+__all__ = ["Blocking", "predict_with_halo", "predict_with_halo_pipelined", "standardize"]

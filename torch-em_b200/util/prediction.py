@@ -1,30 +1,41 @@
-"""Device-resident tiled prediction: the ``predict_with_halo`` of torch-em (util/prediction.py:145-324) with the volume,
-the haloed blocks, the per-block standardisation and the output kept in HBM.
+"""Tiled prediction with a halo: ``predict_with_halo`` / ``predict_with_halo_pipelined`` with torch-em's signatures
+(util/prediction.py:145-164, 487-510), device-resident.
 
-Reference behaviour that is restated here (SURVEY.md 8f rank 1 -- groundwork, see the scope note at the end):
-  * blocking: a C-order regular grid over the (ROI of the) volume with truncated last blocks -- what
-    ``bioimage_cpp.utils.Blocking(begin, end, block_shape)`` provides at prediction.py:229-234 (``number_of_blocks``,
-    ``get_block(i).begin / .end / .shape``);
-  * ``_load_block`` (prediction.py:98-142): the block [offset - halo, offset + block_shape + halo) clipped to the volume and
-    filled up by ``np.pad(mode="reflect")`` (mirror without repeating the edge voxel);
-  * per block: ``preprocess`` (default ``standardize``, transform/raw.py:40-65: float32, ``x -= mean; x /= (std + 1e-7)``, population
-    std, statistics of the haloed block), ``net(inp)`` under ``no_grad``, first tensor of a list output, inner crop
-    ``[halo, halo + block.shape)``, write to ``output[:, block.begin:block.end]`` (prediction.py:258-309).
+The reference moves every haloed block host -> device and every prediction device -> host (prediction.py:273,279) and does the
+reflect padding, the standardisation, the inner crop and the masking with numpy on the host.  Here, when the volume fits the
+device (the common case: 180 GB of HBM), it is copied to the device ONCE in its raw dtype and every per-block step is a kernel
+of ``csrc/tiling.cu``:
 
-Differences by design: the input is copied to the device ONCE (the reference moves every haloed block H2D and every
-prediction D2H, prediction.py:273,279), blocks are gathered on the device with mirrored index vectors, and the result comes
-back in one D2H copy.  Blocks run in order on one device per call (``gpu_ids`` with several entries assigns block i to device
-i % n like prediction.py:249-250, each device with its own replica and copy of the volume).
+  gather_blocks       ``_load_block`` (prediction.py:98-142): clipped haloed box + np.pad(mode="reflect") of the clipped data,
+                      raw dtype -> fp32, block statistics on the fly
+  standardize_blocks  ``standardize`` (transform/raw.py:40-65) with the statistics of the whole haloed block
+  model forward       ``batch_size`` blocks per forward pass (the caller's autocast context is honoured, also in worker threads)
+  scatter_blocks      inner crop ``[halo, halo + block.shape)``, zero outside ``mask``, write to the device-resident output
 
-Not on this path yet (raise ``NotImplementedError`` rather than silently differ): ``mask``, ``skip_block``, ``roi``, ``iter_list``,
-``grid_shift``, list-of-(array, slice) ``output``, ``postprocess``.  The gather / standardise / crop steps are torch indexing
-and elementwise ops for now; fused CUDA kernels for them and the cfg5 measurement are round-2 work.
+and the result comes back in one device -> host copy through pinned memory.  Every argument of the reference is honoured:
+``mask`` (blocks with an empty inner mask are skipped), ``roi``, ``iter_list``, list-of-(array, channel slice) outputs,
+``grid_shift`` (zero padding + final crop, prediction.py:205-222, 319-322), ``with_channels``, ``prediction_function``, several
+``gpu_ids`` (block i runs on device i % n, prediction.py:249-250, one replica and one thread per device).
+
+Host callbacks that are defined on numpy arrays -- ``skip_block``, ``postprocess``, a ``preprocess`` other than ``standardize`` --
+and inputs that do not fit the device (lazy hdf5 / zarr datasets larger than the memory budget) take the streaming path: the
+reference's own per-block host loop, restated, around the same device model.
 """
+import ctypes
+from concurrent import futures
 from copy import deepcopy
-from typing import Callable, List, Optional, Sequence, Tuple, Union
+from typing import Any, Callable, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
+
+from .._lib import call
+
+__all__ = ["Blocking", "predict_with_halo", "predict_with_halo_pipelined", "standardize"]
+
+MAX_BLOCKS_PER_LAUNCH = 16          # B200EM_MAX_TILE_BLOCKS
+_RAW_CODES = {"uint8": 0, "int8": 1, "uint16": 2, "int16": 3, "int32": 4, "uint32": 5, "float16": 6, "float32": 7, "float64": 8}
+_SAME_BITS = {"uint16": "int16", "uint32": "int32"}      # dtypes torch cannot hold are shipped as their signed twin
 
 
 class Blocking:
@@ -66,36 +77,292 @@ class Blocking:
         return Blocking.Block(begin, end)
 
 
-def standardize(raw: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
-    """transform/raw.py:40-65 on a device tensor: float32, population statistics of the whole block."""
-    raw = raw.to(torch.float32)
-    raw = raw - raw.mean()
-    return raw / (raw.std(unbiased=False) + eps)
+def standardize(raw, eps: float = 1e-7):
+    """transform/raw.py:40-65 (default arguments): float32, population statistics of the whole array.  Accepts a numpy array
+    (host path) or a tensor."""
+    if torch.is_tensor(raw):
+        raw = raw.to(torch.float32)
+        raw = raw - raw.mean()
+        return raw / (raw.std(unbiased=False) + eps)
+    raw = np.asarray(raw).astype("float32")
+    raw -= raw.mean()
+    raw /= (raw.std() + eps)
+    return raw
 
 
-def _mirror_index(start: int, stop: int, n: int, device) -> torch.Tensor:
-    """Indices start..stop-1 into an axis of length n, with what prediction.py:98-142 does outside [0, n): the bounding box is
-    clipped to the volume and the CLIPPED data [lo, hi) are extended by np.pad(mode="reflect") -- a triangular wave of period
-    2*(hi-lo-1) around the clipped range (identical to mirroring the volume unless the pad exceeds the clipped length)."""
-    lo, hi = max(0, start), min(n, stop)
-    length = hi - lo
-    idx = torch.arange(start, stop, device=device) - lo
-    if length == 1:
-        return torch.full_like(idx, lo)
-    period = 2 * (length - 1)
-    idx = idx.remainder(period)
-    return torch.where(idx >= length, period - idx, idx) + lo
+def _is_standardize(fn) -> bool:
+    if fn is standardize:
+        return True
+    return getattr(fn, "__name__", None) == "standardize" and str(getattr(fn, "__module__", "")).endswith("transform.raw")
 
 
-def _load_block(vol: torch.Tensor, offset, block_shape, halo) -> torch.Tensor:
-    """Haloed block of a (C, *spatial) device volume, mirrored at the volume border (prediction.py:98-142).
-    Like the reference the requested extent is offset - halo .. offset + block_shape + halo (the FULL block shape, also for
-    truncated last blocks)."""
-    out = vol
-    for ax, (off, bs, ha) in enumerate(zip(offset, block_shape, halo)):
-        n = vol.shape[ax + 1]
-        out = out.index_select(ax + 1, _mirror_index(off - ha, off + bs + ha, n, vol.device))
-    return out
+# ---- reference-literal host helpers (streaming path) -----------------------------------------------------------------------
+def _load_block_host(input_, offset, block_shape, halo, with_channels=False):
+    """prediction.py:98-142 on an array-like (numpy, hdf5, zarr): slice the clipped box, np.pad(mode="reflect") the rest."""
+    shape = input_.shape[1:] if with_channels else input_.shape
+    starts = [off - ha for off, ha in zip(offset, halo)]
+    stops = [off + bs + ha for off, bs, ha in zip(offset, block_shape, halo)]
+    pad_left = [max(0, -s) for s in starts]
+    pad_right = [max(0, st - sh) for st, sh in zip(stops, shape)]
+    bb = tuple(slice(max(0, s), min(sh, st)) for s, st, sh in zip(starts, stops, shape))
+    data = np.asarray(input_[(slice(None),) + bb] if with_channels else input_[bb])
+    if any(pad_left) or any(pad_right):
+        width = tuple(zip(pad_left, pad_right))
+        data = np.pad(data, (((0, 0),) + width) if with_channels else width, mode="reflect")
+    return data
+
+
+def _write_block_host(prediction, block, output, ndim, mask_block, inner_bb, postprocess):
+    """prediction.py:281-309: postprocess, inner crop, zero outside the mask, write."""
+    if postprocess is not None:
+        prediction = postprocess(prediction)
+    prediction = prediction[((slice(None),) + inner_bb) if prediction.ndim == ndim + 1 else inner_bb]
+    if mask_block is not None:
+        mb = np.broadcast_to(mask_block[None], prediction.shape) if prediction.ndim == ndim + 1 else mask_block
+        prediction[~mb] = 0
+    bb = tuple(slice(beg, end) for beg, end in zip(block.begin, block.end))
+    if isinstance(output, list):
+        for out, channel_slice in output:
+            out[bb if out.ndim == ndim else (slice(None),) + bb] = prediction[channel_slice]
+    else:
+        output[((slice(None),) + bb) if output.ndim == ndim + 1 else bb] = prediction
+
+
+def _first_tensor(pred):
+    return pred[0] if isinstance(pred, (list, tuple)) else pred
+
+
+class _Autocast:
+    """The caller's autocast state, re-entered inside worker threads (autocast is thread-local)."""
+
+    def __init__(self):
+        self.enabled = torch.is_autocast_enabled("cuda")
+        self.dtype = torch.get_autocast_dtype("cuda") if self.enabled else None
+
+    def __call__(self, device):
+        return torch.autocast("cuda", dtype=self.dtype, enabled=self.enabled and device.type == "cuda")
+
+
+# ---- device-resident path ----------------------------------------------------------------------------------------------------
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ints(rows):
+    flat = [int(v) for r in rows for v in r]
+    return (ctypes.c_int * len(flat))(*flat)
+
+
+def _to3(v, ndim, fill):
+    return [fill] * (3 - ndim) + [int(x) for x in v]
+
+
+def _device_worker(net, dev, worker_id, n_workers, vol_np, mask_np, blocks, block_ids, block_shape, halo, ndim, with_channels,
+                   standardize_blocks, prediction_function, batch_size, autocast, n_out_hint):
+    """All blocks of one device: returns (host result (C_out, *spatial) float32 pinned tensor, processed block ids)."""
+    mine = [b for b in block_ids if b % n_workers == worker_id]
+    if not mine:
+        return None, []
+    code = _RAW_CODES[str(vol_np.dtype)]
+    ship = vol_np.view(_SAME_BITS[str(vol_np.dtype)]) if str(vol_np.dtype) in _SAME_BITS else vol_np
+    with torch.cuda.device(dev), torch.no_grad(), autocast(dev):
+        vol = torch.from_numpy(ship).to(dev, non_blocking=True)                  # the volume: ONE host -> device copy
+        C = vol.shape[0]
+        D, H, W = _to3(vol.shape[1:], ndim, 1)
+        spatial = tuple(vol.shape[1:])
+        mask_d = None
+        if mask_np is not None:
+            mask_d = torch.from_numpy(np.ascontiguousarray(mask_np != 0).view(np.uint8)).to(dev)
+            # blocks whose inner mask is empty are skipped (prediction.py:258-262): one reduction per block, ONE synchronisation
+            flags = torch.stack([mask_d[tuple(slice(b, e) for b, e in zip(blocks[i].begin, blocks[i].end))].any() for i in mine])
+            keep = flags.cpu().tolist()
+            mine = [i for i, k in zip(mine, keep) if k]
+            if not mine:
+                return None, []
+        bd, bh, bw = _to3([bs + 2 * ha for bs, ha in zip(block_shape, halo)], ndim, 1)
+        hd, hh, hw = _to3(halo, ndim, 0)
+        out_d = None
+        for s in range(0, len(mine), batch_size):
+            ids = mine[s:s + batch_size]
+            nb = len(ids)
+            begins = [_to3([b - ha for b, ha in zip(blocks[i].begin, halo)], ndim, 0) for i in ids]
+            inp = torch.empty((nb, C, bd, bh, bw), dtype=torch.float32, device=dev)
+            stats = torch.zeros((nb, 2), dtype=torch.float64, device=dev) if standardize_blocks else None
+            for k in range(0, nb, MAX_BLOCKS_PER_LAUNCH):
+                n_ = min(MAX_BLOCKS_PER_LAUNCH, nb - k)
+                call("b200em_gather_blocks", _ptr(vol), code, C, D, H, W, _ints(begins[k:k + n_]), n_, bd, bh, bw, _ptr(inp[k:]),
+                     _ptr(stats[k:]) if stats is not None else None, _stream(dev))
+            if standardize_blocks:
+                call("b200em_standardize_blocks", _ptr(inp), nb, C * bd * bh * bw, _ptr(stats), 1e-7, _stream(dev))
+            x = inp if ndim == 3 else inp[:, :, 0]
+            pred = _first_tensor(net(x) if prediction_function is None else prediction_function(net, x))
+            pred = pred.to(torch.float32)
+            if pred.dim() == ndim + 1:                                          # a model without a channel axis in its output
+                pred = pred[:, None]
+            pred = pred.contiguous()
+            Cp = pred.shape[1]
+            if tuple(pred.shape[2:]) != tuple(x.shape[2:]):
+                raise ValueError(f"predict_with_halo: the model changed the spatial shape {tuple(x.shape[2:])} -> {tuple(pred.shape[2:])}")
+            if out_d is None:
+                out_d = torch.zeros((Cp,) + spatial, dtype=torch.float32, device=dev)
+            obeg = [_to3(blocks[i].begin, ndim, 0) for i in ids]
+            oshp = [_to3(blocks[i].shape, ndim, 1) for i in ids]
+            for k in range(0, nb, MAX_BLOCKS_PER_LAUNCH):
+                n_ = min(MAX_BLOCKS_PER_LAUNCH, nb - k)
+                call("b200em_scatter_blocks", _ptr(pred[k:]), Cp, bd, bh, bw, hd, hh, hw, _ints(obeg[k:k + n_]), _ints(oshp[k:k + n_]), n_,
+                     _ptr(out_d), D, H, W, 0, Cp, _ptr(mask_d) if mask_d is not None else None, _stream(dev))
+        host = torch.empty(out_d.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(out_d, non_blocking=True)                                     # the result: ONE device -> host copy (pinned)
+        torch.cuda.current_stream(dev).synchronize()
+    return host, mine
+
+
+def _device_budget_ok(devices, in_bytes, out_bytes, block_bytes):
+    need = in_bytes + out_bytes + 64 * block_bytes          # volume + output + a generous bound on the activations of one batch
+    for d in devices:
+        free, _ = torch.cuda.mem_get_info(d)
+        if need > 0.85 * free:
+            return False
+    return True
+
+
+def _run(input_, model, gpu_ids, block_shape, halo, output, preprocess, postprocess, with_channels, skip_block, mask, prediction_function,
+         roi, iter_list, grid_shift, batch_size):
+    devices = [torch.device("cuda", g) if isinstance(g, int) else torch.device(g) for g in gpu_ids]
+    if not devices:
+        raise ValueError("gpu_ids must name at least one device")
+    models = [(model if next(model.parameters()).device == d else deepcopy(model).to(d), d) for d in devices]
+    n_workers = len(devices)
+    shape0 = tuple(input_.shape)
+    spatial0 = shape0[1:] if with_channels else shape0
+    ndim = len(spatial0)
+    if not (len(block_shape) == len(halo) == ndim):
+        raise ValueError("block_shape and halo must have one entry per spatial axis")
+
+    # grid_shift: zero padding to the left + final crop (prediction.py:205-222, 241-247, 319-322)
+    input_eff, mask_eff = input_, mask
+    pad_left = (0,) * ndim
+    if grid_shift is not None:
+        assert len(grid_shift) == ndim, "grid_shift must match number of spatial dims"
+        if output is not None:
+            raise ValueError(
+                "grid_shift is not supported together with a user-provided `output`, because grid_shift requires internal "
+                "zero-padding and a final cropping step. Pass `output=None` (let this function allocate the output) or disable "
+                "`grid_shift`. Or pad the input manually beforehand.")
+        if not isinstance(input_eff, np.ndarray):
+            raise TypeError("grid_shift padding currently requires input_ to be a numpy array")
+        pad_left = tuple(int(np.rint(abs(gs) * bs)) for gs, bs in zip(grid_shift, block_shape))
+        width = tuple((p, 0) for p in pad_left)
+        input_eff = np.pad(input_eff, (((0, 0),) + width) if with_channels else width, mode="constant", constant_values=0)
+        if mask_eff is not None:
+            if not isinstance(mask_eff, np.ndarray):
+                raise TypeError("grid_shift padding currently requires mask to be a numpy array")
+            mask_eff = np.pad(mask_eff, width, mode="constant", constant_values=0)
+    spatial = tuple(input_eff.shape[1:] if with_channels else input_eff.shape)
+
+    if roi is None:
+        blocking = Blocking([0] * ndim, list(spatial), list(block_shape))
+    else:
+        assert len(roi) == ndim
+        blocking = Blocking([0 if r.start is None else r.start for r in roi],
+                            [sh if r.stop is None else r.stop for r, sh in zip(roi, spatial)], list(block_shape))
+    n_blocks = blocking.number_of_blocks
+    block_ids = list(range(n_blocks)) if iter_list is None else [int(i) for i in iter_list]
+    blocks = {i: blocking.get_block(i) for i in block_ids}
+
+    own_output = output is None
+    n_out_hint = getattr(models[0][0], "out_channels", None)
+    autocast = _Autocast()
+
+    # ---- which path -------------------------------------------------------------------------------------------------------
+    on_device = (all(d.type == "cuda" for d in devices) and ndim in (2, 3) and skip_block is None and postprocess is None
+                 and (preprocess is None or _is_standardize(preprocess)))
+    vol_np = None
+    if on_device:
+        n_out_est = n_out_hint if isinstance(n_out_hint, int) else (max(n_out_hint) if n_out_hint else 4)
+        n_vox = int(np.prod(spatial))
+        itemsize = np.dtype(input_eff.dtype).itemsize
+        block_bytes = 4 * batch_size * int(np.prod([bs + 2 * ha for bs, ha in zip(block_shape, halo)]))
+        in_ch = shape0[0] if with_channels else 1
+        on_device = _device_budget_ok(devices, n_vox * in_ch * itemsize, 4 * n_out_est * n_vox, block_bytes)
+    if on_device:
+        vol_np = np.asarray(input_eff if isinstance(input_eff, np.ndarray) else input_eff[...])
+        if str(vol_np.dtype) not in _RAW_CODES:
+            vol_np = vol_np.astype("uint8" if vol_np.dtype == bool else "float32")
+        vol_np = np.ascontiguousarray(vol_np if with_channels else vol_np[None])
+        mask_np = None if mask_eff is None else np.asarray(mask_eff if isinstance(mask_eff, np.ndarray) else mask_eff[...])
+
+        def work(w):
+            net, dev = models[w]
+            return _device_worker(net, dev, w, n_workers, vol_np, mask_np, blocks, block_ids, block_shape, halo, ndim, with_channels,
+                                  preprocess is not None, prediction_function, batch_size, autocast, n_out_hint)
+
+        if n_workers == 1:
+            results = [work(0)]
+        else:
+            with futures.ThreadPoolExecutor(n_workers) as tp:
+                results = list(tp.map(work, range(n_workers)))
+        results = [(h, ids) for h, ids in results if h is not None]
+        if own_output and len(results) == 1 and grid_shift is None:
+            return results[0][0].numpy()                     # backed by the pinned buffer of the single device -> host copy
+        if own_output:
+            n_out = results[0][0].shape[0] if results else (n_out_hint if isinstance(n_out_hint, int) else 1)
+            output = np.zeros((n_out,) + spatial, dtype="float32")
+        for host, ids in results:
+            res = host.numpy()
+            for i in ids:                                    # only processed blocks are written, like the reference
+                b = blocks[i]
+                bb = tuple(slice(beg, end) for beg, end in zip(b.begin, b.end))
+                pred = res[(slice(None),) + bb]
+                if isinstance(output, list):
+                    for out, channel_slice in output:
+                        out[bb if out.ndim == ndim else (slice(None),) + bb] = pred[channel_slice]
+                else:
+                    output[((slice(None),) + bb) if output.ndim == ndim + 1 else bb] = pred
+    else:
+        # ---- streaming path: the reference's per-block host loop (prediction.py:249-317) around the device model ----------------
+        if own_output:
+            n_out = n_out_hint if isinstance(n_out_hint, int) else n_out_hint[0]
+            output = np.zeros((n_out,) + spatial, dtype="float32")
+
+        def predict_block(block_id):
+            net, dev = models[block_id % n_workers]
+            block = blocks[block_id]
+            inner_bb = tuple(slice(ha, ha + bs) for ha, bs in zip(halo, block.shape))
+            mask_block = None
+            if mask_eff is not None:
+                mask_block = _load_block_host(mask_eff, block.begin, block_shape, halo)[inner_bb].astype("bool")
+                if mask_block.sum() == 0:
+                    return
+            inp = _load_block_host(input_eff, block.begin, block_shape, halo, with_channels)
+            if skip_block is not None and skip_block(inp):
+                return
+            if preprocess is not None:
+                inp = preprocess(inp)
+            inp = np.ascontiguousarray(inp[None] if with_channels else inp[None, None])
+            if inp.dtype not in (np.float32, np.float64, np.float16):
+                inp = inp.astype("float32")
+            with torch.no_grad(), autocast(dev):
+                x = torch.from_numpy(inp).to(dev)
+                pred = _first_tensor(net(x) if prediction_function is None else prediction_function(net, x))
+                pred = pred.float().cpu().numpy().squeeze(0)
+            _write_block_host(pred, block, output, ndim, mask_block, inner_bb, postprocess)
+
+        if n_workers == 1:
+            for i in block_ids:
+                predict_block(i)
+        else:
+            with futures.ThreadPoolExecutor(n_workers) as tp:
+                list(tp.map(predict_block, block_ids))
+
+    if grid_shift is not None:
+        crop = tuple(slice(p, p + s) for p, s in zip(pad_left, spatial0))
+        output = output[((slice(None),) + crop) if output.ndim == ndim + 1 else crop]
+    return output
 
 
 def predict_with_halo(
@@ -105,71 +372,56 @@ def predict_with_halo(
     block_shape: Tuple[int, ...],
     halo: Tuple[int, ...],
     output=None,
-    preprocess: Optional[Callable[[torch.Tensor], torch.Tensor]] = standardize,
-    postprocess=None,
+    preprocess: Optional[Callable] = standardize,
+    postprocess: Optional[Callable] = None,
     with_channels: bool = False,
-    skip_block=None,
+    skip_block: Optional[Callable[[Any], bool]] = None,
     mask=None,
-    disable_tqdm: bool = True,
+    disable_tqdm: bool = False,
     tqdm_desc: str = "predict with halo",
     prediction_function: Optional[Callable] = None,
-    roi=None,
-    iter_list=None,
-    grid_shift=None,
-) -> np.ndarray:
-    """Block-wise prediction with a halo; same signature as torch_em.util.prediction.predict_with_halo (prediction.py:145-164).
-    Returns the (C_out, *spatial) float32 numpy array the reference returns (or fills ``output`` in place)."""
-    for name, val in (("postprocess", postprocess), ("skip_block", skip_block), ("mask", mask), ("roi", roi), ("iter_list", iter_list),
-                      ("grid_shift", grid_shift)):
-        if val is not None:
-            raise NotImplementedError(f"predict_with_halo: `{name}` is not on the device-resident path yet")
-    if isinstance(output, list):
-        raise NotImplementedError("predict_with_halo: a list of (output, channel slice) is not on the device-resident path yet")
-    shape = tuple(input_.shape)
-    spatial = shape[1:] if with_channels else shape
-    ndim = len(spatial)
-    if not (len(block_shape) == len(halo) == ndim):
-        raise ValueError("block_shape and halo must have one entry per spatial axis")
-    devices = [torch.device(g) if not isinstance(g, int) else torch.device("cuda", g) for g in gpu_ids]
-    if not devices:
-        raise ValueError("gpu_ids must name at least one device")
-    models = [(model if next(model.parameters()).device == d else deepcopy(model).to(d), d) for d in devices]
-    host = torch.as_tensor(np.ascontiguousarray(input_))
-    if not with_channels:
-        host = host[None]
-    vols = [host.to(d, non_blocking=True) for d in devices]                     # the volume: one H2D copy per device
-    blocking = Blocking([0] * ndim, list(spatial), list(block_shape))
-    outs = [None] * len(devices)
-    with torch.no_grad():
-        for block_id in range(blocking.number_of_blocks):
-            w = block_id % len(devices)
-            net, dev = models[w]
-            block = blocking.get_block(block_id)
-            inp = _load_block(vols[w], block.begin, block_shape, halo)
-            if preprocess is not None:
-                inp = preprocess(inp if with_channels else inp[0])
-                if not with_channels:
-                    inp = inp[None]
-            inp = inp.to(torch.float32)[None].contiguous()
-            pred = net(inp) if prediction_function is None else prediction_function(net, inp)
-            if isinstance(pred, (list, tuple)):
-                pred = pred[0]
-            pred = pred[0]
-            inner = (slice(None),) + tuple(slice(ha, ha + bs) for ha, bs in zip(halo, block.shape))
-            if outs[w] is None:
-                outs[w] = torch.zeros((pred.shape[0],) + tuple(spatial), dtype=torch.float32, device=dev)
-            bb = (slice(None),) + tuple(slice(b, e) for b, e in zip(block.begin, block.end))
-            outs[w][bb] = pred[inner].to(torch.float32)
-    result = None
-    for o in outs:                                                              # blocks are disjoint: the per-device outputs add up
-        if o is not None:
-            r = o.cpu()
-            result = r if result is None else result + r
-    result = result.numpy()
-    if output is not None:
-        if output.ndim == ndim:
-            output[...] = result[0]
-        else:
-            output[...] = result
-        return output
-    return result
+    roi: Optional[Tuple[slice]] = None,
+    iter_list: Optional[List[int]] = None,
+    grid_shift: Optional[Tuple[float, ...]] = None,
+):
+    """Block-wise network prediction with a halo; same signature and results as
+    ``torch_em.util.prediction.predict_with_halo`` (prediction.py:145-324).  See the module docstring for what runs where.
+    ``disable_tqdm`` / ``tqdm_desc`` are accepted for compatibility (there is no per-block host loop to report on)."""
+    return _run(input_, model, gpu_ids, block_shape, halo, output, preprocess, postprocess, with_channels, skip_block, mask,
+                prediction_function, roi, iter_list, grid_shift, batch_size=1)
+
+
+def predict_with_halo_pipelined(
+    input_,
+    model: torch.nn.Module,
+    gpu_ids: List[Union[str, int]],
+    block_shape: Tuple[int, ...],
+    halo: Tuple[int, ...],
+    output=None,
+    preprocess: Optional[Callable] = standardize,
+    postprocess: Optional[Callable] = None,
+    with_channels: bool = False,
+    skip_block: Optional[Callable[[Any], bool]] = None,
+    mask=None,
+    disable_tqdm: bool = False,
+    tqdm_desc: str = "predict with halo (pipelined)",
+    prediction_function: Optional[Callable] = None,
+    roi: Optional[Tuple[slice]] = None,
+    iter_list: Optional[List[int]] = None,
+    batch_size: int = 1,
+    num_prefetch_workers: int = 4,
+    queue_size: Optional[int] = None,
+    num_write_workers: int = 1,
+    write_queue_size: Optional[int] = None,
+    grid_shift: Optional[Tuple[float, ...]] = None,
+):
+    """Same signature and results as ``torch_em.util.prediction.predict_with_halo_pipelined`` (prediction.py:487-759).  The
+    reference pipelines host loading, device prediction and host writing through queues; with the volume and the output
+    resident on the device there is nothing left to pipeline, so the queue / worker-count arguments are accepted and unused and
+    ``batch_size`` blocks share one forward pass.  ``prediction_function`` must operate on the leading batch axis."""
+    if grid_shift is not None:
+        raise NotImplementedError(
+            "grid_shift is not supported by predict_with_halo_pipelined. "
+            "Use predict_with_halo for grid_shift, or pre-pad the input and use roi.")
+    return _run(input_, model, gpu_ids, block_shape, halo, output, preprocess, postprocess, with_channels, skip_block, mask,
+                prediction_function, roi, iter_list, None, batch_size=max(1, int(batch_size)))
