@@ -16,8 +16,10 @@ import types
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STUB_ROOTS = ("imageio", "skimage", "bioimage_cpp", "elf", "kornia", "h5py", "matplotlib", "natsort", "tifffile", "mrcfile",
-              "bioimageio", "zarr", "z5py", "napari", "nifty", "vigra", "affogato", "tensorboard", "xarray", "pooch", "cv2",
+              "bioimageio", "zarr", "z5py", "nifty", "vigra", "affogato", "tensorboard", "xarray", "pooch", "cv2",
               "nibabel", "imagecodecs", "torchvision")
+# NOT stubbed although absent: napari -- the reference guards it itself (``try: from napari.utils import progress as tqdm
+# except ImportError: from tqdm import tqdm``, util/prediction.py:13-16) and a stub would shadow the real tqdm.
 
 
 def reference_root():

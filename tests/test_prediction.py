@@ -156,6 +156,10 @@ def test_device_path_2d_and_channels():
     class Net2d(torch.nn.Module):
         out_channels = 3
 
+        def __init__(self):
+            super().__init__()
+            self.dummy = torch.nn.Parameter(torch.zeros(1))       # predict_with_halo reads the device from the parameters
+
         def forward(self, x):
             return torch.cat([x.mean(1, keepdim=True), torch.tanh(x[:, :1]), torch.nn.functional.avg_pool2d(x[:, 1:2], 3, 1, 1)], 1)
 

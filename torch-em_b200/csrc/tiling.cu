@@ -36,38 +36,47 @@ __device__ __forceinline__ float raw_to_f(TI v) { return (float)v; }
 template <>
 __device__ __forceinline__ float raw_to_f<__half>(__half v) { return __half2float(v); }
 
-// vol (C, D, H, W) of TI -> out (nblocks, C, bd, bh, bw) fp32; stats[nblocks][2] += (sum, sum of squares) in double
+// vol (C, D, H, W) of TI -> out (nblocks, C, bd, bh, bw) fp32; stats[nblocks][2] += (sum, sum of squares) in double.
+// One CTA = TILE_ROWS rows (c, d, h) of one block: the row's source (d, h) is resolved once per row, the threads run along w
+// (coalesced loads and stores; only the w reflection is per element).  grid = (row groups, nblocks).
+constexpr int TILE_ROWS = 8;
+
 template <typename TI>
 __global__ void __launch_bounds__(256)
 gather_blocks_kernel(const TI* __restrict__ vol, int C, int D, int H, int W, BlockList bl, int bd, int bh, int bw,
                      float* __restrict__ out, double* __restrict__ stats) {
     __shared__ double sh[8][2];
     const int b = blockIdx.y;
-    const int64_t per_c = (int64_t)bd * bh * bw, total = per_c * C;
+    const int rows = C * bd * bh;
     const int d0 = bl.begin[b][0], h0 = bl.begin[b][1], w0 = bl.begin[b][2];
-    float* o = out + (size_t)b * total;
+    float* o = out + (size_t)b * rows * bw;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 lanes along w, 8 rows per CTA
+    const int row = blockIdx.x * TILE_ROWS + ty;
     float s = 0.f, q = 0.f;
-    double ds = 0.0, dq = 0.0;
-    int since = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int w = (int)(i % bw), h = (int)((i / bw) % bh), d = (int)((i / ((int64_t)bw * bh)) % bd), c = (int)(i / per_c);
-        const int gd = reflect_index(d0 + d, d0, d0 + bd, D), gh = reflect_index(h0 + h, h0, h0 + bh, H),
-                  gw = reflect_index(w0 + w, w0, w0 + bw, W);
-        const float v = raw_to_f<TI>(vol[(((size_t)c * D + gd) * H + gh) * W + gw]);
-        o[i] = v;
-        s += v;
-        q = fmaf(v, v, q);
-        if (++since == 64) { ds += s; dq += q; s = q = 0.f; since = 0; }   // short fp32 runs, double across them
+    if (row < rows) {
+        const int h = row % bh, d = (row / bh) % bd, c = row / (bh * bd);
+        const int gd = reflect_index(d0 + d, d0, d0 + bd, D), gh = reflect_index(h0 + h, h0, h0 + bh, H);
+        const TI* __restrict__ src = vol + (((size_t)c * D + gd) * H + gh) * W;
+        float* __restrict__ dst = o + (size_t)row * bw;
+        // interior of the row (no reflection along w) is a straight copy; the clipped range is [wlo, whi)
+        const int wlo = w0 > 0 ? w0 : 0, whi = w0 + bw < W ? w0 + bw : W;
+        for (int w = tx; w < bw; w += 32) {
+            const int gw0 = w0 + w;
+            const int gw = (gw0 >= wlo && gw0 < whi) ? gw0 : reflect_index(gw0, w0, w0 + bw, W);
+            const float v = raw_to_f<TI>(src[gw]);
+            dst[w] = v;
+            s += v;
+            q = fmaf(v, v, q);
+        }
     }
-    ds += s; dq += q;
     if (stats) {
+        double ds = s, dq = q;                                   // <= bw / 32 fp32 terms per thread, double from here on
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             ds += __shfl_xor_sync(0xffffffffu, ds, off);
             dq += __shfl_xor_sync(0xffffffffu, dq, off);
         }
-        const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (lane == 0) { sh[wi][0] = ds; sh[wi][1] = dq; }
+        if (tx == 0) { sh[ty][0] = ds; sh[ty][1] = dq; }
         __syncthreads();
         if (threadIdx.x < 2) {
             double v = 0.0;
@@ -89,21 +98,27 @@ standardize_blocks_kernel(float* __restrict__ x, int64_t per_block, const double
         p[i] = (p[i] - m) * inv;
 }
 
-// pred (nblocks, Cp, bd, bh, bw) fp32 -> out (Co, D, H, W): channels [c0, c0 + nc) of the inner crop of every block
+// pred (nblocks, Cp, bd, bh, bw) fp32 -> out (Co, D, H, W): channels [c0, c0 + nc) of the inner crop of every block.
+// One CTA = TILE_ROWS rows (c, d, h) of one inner block, threads along w.  grid = (row groups of the largest block, nblocks).
 __global__ void __launch_bounds__(256)
 scatter_blocks_kernel(const float* __restrict__ pred, int Cp, int bd, int bh, int bw, int hd, int hh, int hw, BlockList bl,
                       float* __restrict__ out, int D, int H, int W, int c0, int nc, const unsigned char* __restrict__ mask) {
     const int b = blockIdx.y;
     const int sd = bl.shape[b][0], sh_ = bl.shape[b][1], sw = bl.shape[b][2];
     const int od = bl.begin[b][0], oh = bl.begin[b][1], ow = bl.begin[b][2];
-    const int64_t per_c = (int64_t)sd * sh_ * sw, total = per_c * nc;
-    const float* p = pred + (size_t)b * Cp * bd * bh * bw;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int w = (int)(i % sw), h = (int)((i / sw) % sh_), d = (int)((i / ((int64_t)sw * sh_)) % sd), c = (int)(i / per_c);
-        const size_t dst_vox = ((size_t)(od + d) * H + (oh + h)) * W + (ow + w);
-        float v = p[(((size_t)(c0 + c) * bd + (hd + d)) * bh + (hh + h)) * bw + (hw + w)];
-        if (mask && !mask[dst_vox]) v = 0.f;
-        out[(size_t)c * D * H * W + dst_vox] = v;
+    const int rows = nc * sd * sh_;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int row = blockIdx.x * TILE_ROWS + ty;
+    if (row >= rows) return;
+    const int h = row % sh_, d = (row / sh_) % sd, c = row / (sh_ * sd);
+    const float* __restrict__ src = pred + ((((size_t)b * Cp + (c0 + c)) * bd + (hd + d)) * bh + (hh + h)) * bw + hw;
+    const size_t dst_row = ((size_t)(od + d) * H + (oh + h)) * W + ow;
+    float* __restrict__ dst = out + (size_t)c * D * H * W + dst_row;
+    const unsigned char* __restrict__ m = mask ? mask + dst_row : nullptr;
+    for (int w = tx; w < sw; w += 32) {
+        float v = src[w];
+        if (m && !m[w]) v = 0.f;
+        dst[w] = v;
     }
 }
 
@@ -140,7 +155,8 @@ int b200em_gather_blocks(const void* vol, int raw_dtype, int C, int D, int H, in
     B2_CHECK_ARG(vol && out && block_begins && C > 0 && D > 0 && H > 0 && W > 0 && bd > 0 && bh > 0 && bw > 0, "gather_blocks: bad arguments");
     BlockList bl;
     if (fill_blocks(bl, block_begins, nullptr, nblocks)) return 1;
-    dim3 grid(tile_grid((int64_t)C * bd * bh * bw), (unsigned)nblocks);
+    B2_CHECK_ARG((int64_t)C * bd * bh < (1LL << 31), "gather_blocks: block too large");
+    dim3 grid((unsigned)(((int64_t)C * bd * bh + TILE_ROWS - 1) / TILE_ROWS), (unsigned)nblocks);
 #define B2_GATHER(TI) gather_blocks_kernel<TI><<<grid, 256, 0, (cudaStream_t)stream>>>((const TI*)vol, C, D, H, W, bl, bd, bh, bw, out, stats)
     switch (raw_dtype) {
         case B200EM_RAW_U8: B2_GATHER(uint8_t); break;
@@ -181,10 +197,10 @@ int b200em_scatter_blocks(const float* pred, int Cp, int bd, int bh, int bw, int
                      "scatter_blocks: inner block %d does not fit into the prediction", i);
         B2_CHECK_ARG(b[0] >= 0 && b[1] >= 0 && b[2] >= 0 && b[0] + s[0] <= D && b[1] + s[1] <= H && b[2] + s[2] <= W,
                      "scatter_blocks: block %d leaves the output volume", i);
-        const int64_t t = (int64_t)s[0] * s[1] * s[2] * nc;
+        const int64_t t = (int64_t)s[0] * s[1] * nc;               // rows (c, d, h) of the inner block
         if (t > big) big = t;
     }
-    dim3 grid(tile_grid(big), (unsigned)nblocks);
+    dim3 grid((unsigned)((big + TILE_ROWS - 1) / TILE_ROWS), (unsigned)nblocks);
     scatter_blocks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, Cp, bd, bh, bw, hd, hh, hw, bl, out, D, H, W, c0, nc, mask);
     B2_LAUNCH_CHECK();
     return 0;

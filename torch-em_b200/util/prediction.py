@@ -274,6 +274,12 @@ def _run(input_, model, gpu_ids, block_shape, halo, output, preprocess, postproc
     block_ids = list(range(n_blocks)) if iter_list is None else [int(i) for i in iter_list]
     blocks = {i: blocking.get_block(i) for i in block_ids}
 
+    if batch_size is None:
+        # predict_with_halo has no batch argument (the reference feeds one block per forward pass).  On the device path several
+        # haloed blocks share one forward pass -- the per-block results are identical (the norm layers are per sample) and the
+        # host-side launch overhead of a forward pass is amortised -- unless a user prediction_function could tell the difference.
+        big_vox = int(np.prod([bs + 2 * ha for bs, ha in zip(block_shape, halo)]))
+        batch_size = 1 if prediction_function is not None else max(1, min(4, (32 << 20) // max(big_vox, 1)))
     own_output = output is None
     n_out_hint = getattr(models[0][0], "out_channels", None)
     autocast = _Autocast()
@@ -388,7 +394,7 @@ def predict_with_halo(
     ``torch_em.util.prediction.predict_with_halo`` (prediction.py:145-324).  See the module docstring for what runs where.
     ``disable_tqdm`` / ``tqdm_desc`` are accepted for compatibility (there is no per-block host loop to report on)."""
     return _run(input_, model, gpu_ids, block_shape, halo, output, preprocess, postprocess, with_channels, skip_block, mask,
-                prediction_function, roi, iter_list, grid_shift, batch_size=1)
+                prediction_function, roi, iter_list, grid_shift, batch_size=None)
 
 
 def predict_with_halo_pipelined(
