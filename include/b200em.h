@@ -91,6 +91,18 @@ int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift,
                        void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
                        int Cout, int kd, int kh, int kw, int relu, void* stream);
 
+/* TF32 variants of the two entry points above: fp32 activations and fp32 packed weights (b200em_pack_batch with
+ * B200EM_PACK_PLAIN_TF32), fed to tcgen05.mma.kind::tf32, which reads the upper 19 bits of every operand word -- the arithmetic
+ * torch / cuDNN use for fp32 convolutions by default (torch.backends.cudnn.allow_tf32; the reference's mixed_precision=False
+ * path, default_trainer.py:132-142).  Same contracts, Cin % 16 == 0 (conv) resp. Cin % 32 == 0 (weight gradient). */
+int b200em_conv3d_umma_tf32_supported(int Cin, int Cout, int kd, int kh, int kw);
+int b200em_conv3d_umma_tf32(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+                            void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
+                            int Cout, int kd, int kh, int kw, int relu, void* stream);
+int b200em_conv3d_wgrad_umma_tf32(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld,
+                                  float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw,
+                                  void* stream);
+
 /* "depth-stacked" tcgen05 variant for 3 x kh x kw filters with few output channels (Cout <= 80) whose packed filter
  * fits in shared memory: the three depth taps share one operand fetch (N = 3*Cout) and land in the accumulators of
  * three consecutive output slices (a ring of TMEM column blocks); every input slice is staged once per column of
@@ -111,6 +123,7 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
  * derived fields; the table is then copied to the device once and b200em_pack_batch launches over it. */
 #define B200EM_PACK_PLAIN 0          /* operand of b200em_conv3d_umma */
 #define B200EM_PACK_DEPTH_STACKED 1  /* operand of b200em_conv3d_umma_ds */
+#define B200EM_PACK_PLAIN_TF32 2     /* fp32 operand of b200em_conv3d_umma_tf32 (packed: Cout*Cin*taps fp32) */
 typedef struct b200em_pack_job {
     const float* w;    /* torch (Cout, Cin, kd, kh, kw) fp32, device */
     void* packed;      /* bf16 operand image, device */

@@ -27,3 +27,15 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_by_default():
+    """fp32 activations run on the TF32 tensor-core kernels when torch allows TF32 convolutions (its default, and what the
+    reference's fp32 runs use).  The parity tests want the EXACT fp32 path (CUDA-core kernels here, cuDNN / cuBLAS without TF32
+    on the reference side) unless they opt in (tests/test_gpu_tf32.py)."""
+    import torch
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

@@ -50,7 +50,7 @@ def _f32(t):
 class WeightPack:
     """Kernel-operand copies of one conv weight (derived data; the fp32 nn.Parameter stays the master)."""
     __slots__ = ("w_fwd_f32", "w_dgrad_f32", "f32_stale", "umma_fwd", "umma_dgrad", "cout", "cin", "kernel", "thin", "thin_kp",
-                 "ds_fwd", "ds_dgrad", "master")
+                 "ds_fwd", "ds_dgrad", "master", "tf32_fwd", "tf32_dgrad")
 
 
 class _PackJob(ctypes.Structure):
@@ -62,7 +62,7 @@ class _PackJob(ctypes.Structure):
                 ("reserved", ctypes.c_int32 * 2)]
 
 
-PACK_PLAIN, PACK_DEPTH_STACKED = 0, 1
+PACK_PLAIN, PACK_DEPTH_STACKED, PACK_PLAIN_TF32 = 0, 1, 2
 
 
 class PackSet:
@@ -90,7 +90,9 @@ class PackSet:
         self.sig = self.signature(weights)
         self.packs = {}
         self.device = None
-        plan = {0: [], 1: []}                         # direction -> [(pack, attr, layout, elems)]
+        # table -> [(pack, attr, layout, elems)]: 0 / 1 = bf16 forward / data-gradient operands, 2 / 3 = the fp32 operands of the
+        # TF32 path (allocated and packed only when a pass really runs with fp32 activations and TF32 allowed)
+        plan = {0: [], 1: [], 2: [], 3: []}
         for key, w in weights.items():
             if w.device.type != "cuda":
                 raise RuntimeError("b200em: parameters must live on a CUDA device (there is no CPU fallback for this path)")
@@ -102,7 +104,7 @@ class PackSet:
             pk.cout, pk.cin, pk.kernel, pk.master = cout, cin, (kd, kh, kw), wd
             pk.w_fwd_f32 = pk.w_dgrad_f32 = None
             pk.f32_stale = True
-            pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.ds_fwd = pk.ds_dgrad = None
+            pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.ds_fwd = pk.ds_dgrad = pk.tf32_fwd = pk.tf32_dgrad = None
             pk.thin_kp = 0
             n = cout * cin * kd * kh * kw
             if B.use_umma:
@@ -115,35 +117,47 @@ class PackSet:
                     plan[1].append((pk, "ds_dgrad", PACK_DEPTH_STACKED, n))
                 elif lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
                     plan[1].append((pk, "umma_dgrad", PACK_PLAIN, n))
+                if lib.b200em_conv3d_umma_tf32_supported(cin, cout, kd, kh, kw):
+                    plan[2].append((pk, "tf32_fwd", PACK_PLAIN_TF32, n))
+                if lib.b200em_conv3d_umma_tf32_supported(cout, cin, kd, kh, kw):
+                    plan[3].append((pk, "tf32_dgrad", PACK_PLAIN_TF32, n))
                 kp = -(-kd * kh * kw * cin // 32) * 32
                 first = B.use_ds and lib.b200em_conv3d_first_supported(cin, cout, kd, kh, kw)
                 if cin <= 4 and not first and lib.b200em_conv3d_umma_supported(kp, cout, 1, 1, 1):
                     pk.thin_kp = kp                   # thin-K first conv (im2col layout), packed by refresh_fwd
             self.packs[key] = pk
+        self.plan = plan
         self.tables = {}
         for d in (0, 1):
-            if not plan[d]:
-                self.tables[d] = None
-                continue
-            total = sum(-(-n // 8) * 8 for _, _, _, n in plan[d])
-            flat = torch.empty(total, dtype=torch.bfloat16, device=self.device)
-            jobs = (_PackJob * len(plan[d]))()
-            off = 0
-            for i, (pk, attr, layout, n) in enumerate(plan[d]):
-                buf = flat[off:off + n]
-                off += -(-n // 8) * 8                 # keep every image 16-byte aligned
-                setattr(pk, attr, buf)
-                j = jobs[i]
-                j.w, j.packed = pk.master.data_ptr(), buf.data_ptr()
-                j.Cout, j.Cin = pk.cout, pk.cin
-                j.kd, j.kh, j.kw = pk.kernel
-                j.dgrad, j.layout = d, layout
-            nblocks = ctypes.c_int(0)
-            call("b200em_pack_batch_prepare", ctypes.cast(jobs, ctypes.c_void_p), len(plan[d]), ctypes.byref(nblocks))
-            host = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
-            self.tables[d] = (host.to(self.device), len(plan[d]), nblocks.value, flat)
+            self._build_table(d)
+
+    def _build_table(self, d):
+        plan = self.plan[d]
+        if not plan:
+            self.tables[d] = None
+            return
+        dtype = torch.float32 if d >= 2 else torch.bfloat16
+        total = sum(-(-n // 8) * 8 for _, _, _, n in plan)
+        flat = torch.empty(total, dtype=dtype, device=self.device)
+        jobs = (_PackJob * len(plan))()
+        off = 0
+        for i, (pk, attr, layout, n) in enumerate(plan):
+            buf = flat[off:off + n]
+            off += -(-n // 8) * 8                     # keep every image 16-byte aligned
+            setattr(pk, attr, buf)
+            j = jobs[i]
+            j.w, j.packed = pk.master.data_ptr(), buf.data_ptr()
+            j.Cout, j.Cin = pk.cout, pk.cin
+            j.kd, j.kh, j.kw = pk.kernel
+            j.dgrad, j.layout = d % 2, layout
+        nblocks = ctypes.c_int(0)
+        call("b200em_pack_batch_prepare", ctypes.cast(jobs, ctypes.c_void_p), len(plan), ctypes.byref(nblocks))
+        host = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
+        self.tables[d] = (host.to(self.device), len(plan), nblocks.value, flat)
 
     def _launch(self, d):
+        if d not in self.tables:
+            self._build_table(d)
         t = self.tables[d]
         if t is None:
             return
@@ -159,7 +173,11 @@ class PackSet:
         for pk in self.packs.values():
             pk.f32_stale = True
         if not bf16:
-            return                                    # fp32 activations run on the direct kernels (lazy fp32 operands)
+            # fp32 activations: the TF32 tensor-core path when torch allows TF32 convolutions, else the exact direct kernels
+            # (their fp32 operands are packed lazily, f32_operands)
+            if self.B.tf32_enabled():
+                self._launch(2)
+            return
         self._launch(0)
         for pk in self.packs.values():
             if pk.thin_kp:
@@ -168,6 +186,8 @@ class PackSet:
     def refresh_dgrad(self, bf16=True):
         if bf16:
             self._launch(1)
+        elif self.B.tf32_enabled():
+            self._launch(3)
 
     def _pack_thin(self, pk):
         # thin-K first conv: W'[co][tap*Cin+ci] = W[co][ci][tap], zero padded to Kp channels (im2col layout)
@@ -187,8 +207,9 @@ class PackSet:
 class CudaBackend:
     name = "cuda"
 
-    def __init__(self, use_umma=True, use_ds=True, use_cs=True):
+    def __init__(self, use_umma=True, use_ds=True, use_cs=True, use_tf32=None):
         self.use_umma = use_umma
+        self.use_tf32 = use_tf32    # None: follow torch.backends.cudnn.allow_tf32 (True by default, like the reference's fp32 runs)
         self.use_ds = use_ds and use_umma
         self.use_cs = use_cs and use_umma
         self.timing = None          # {family: [(start_event, end_event, work), ...]} while bench.py measures
@@ -217,6 +238,13 @@ class CudaBackend:
         self.timing.setdefault(family, []).append((a, b, work))
         return r
 
+    def tf32_enabled(self):
+        """fp32 activations take the TF32 tensor-core kernels iff torch would run an fp32 convolution in TF32
+        (``torch.backends.cudnn.allow_tf32``, default True); set it to False for the exact-fp32 CUDA-core kernels."""
+        if not self.use_umma:
+            return False
+        return torch.backends.cudnn.allow_tf32 if self.use_tf32 is None else bool(self.use_tf32)
+
     # ---- weights ---------------------------------------------------------------------------------------------
     def pack_set(self, weights):
         """{key: conv weight} -> PackSet (all operand images of a model, one launch per direction)."""
@@ -227,6 +255,9 @@ class CudaBackend:
         ps = PackSet(self, {key: w})
         ps.refresh_fwd()
         ps.refresh_dgrad()
+        if self.tf32_enabled():
+            ps.refresh_fwd(bf16=False)
+            ps.refresh_dgrad(bf16=False)
         return ps[key]
 
     def f32_operands(self, pk):
@@ -333,6 +364,15 @@ class CudaBackend:
                     "b200em_conv3d_umma", xp, xld, _f32(in_ss), _ptr(wu), _f32(b), yp, yld, _f32(sums), dp, dld, N, D, H, W, Cin,
                     Cout, kd, kh, kw, int(relu), _stream(x)))
                 return None
+        wt = pack.tf32_dgrad if dgrad else pack.tf32_fwd
+        if wt is not None and x.dtype == torch.float32 and self.tf32_enabled() and xld % 4 == 0 and yld % 4 == 0 and \
+                x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
+            dp, dld = _act(dot_x) if dot_x is not None else (None, 0)
+            if dot_x is None or (dld % 4 == 0 and dot_x.data_ptr() % 16 == 0):
+                self._timed("tf32:dgrad" if dgrad else "tf32:fwd", flops, lambda: call(
+                    "b200em_conv3d_umma_tf32", xp, xld, _f32(in_ss), _ptr(wt), _f32(b), yp, yld, _f32(sums), dp, dld, N, D, H, W, Cin,
+                    Cout, kd, kh, kw, int(relu), _stream(x)))
+                return None
         w = self.f32_operands(pack)[1 if dgrad else 0]
         self._timed("direct:dgrad" if dgrad else "direct:fwd", flops, lambda: call(
             "b200em_conv3d_direct", xp, xld, _f32(in_ss), _f32(w), _f32(b), yp, yld, None if dot_x is not None else _f32(sums),
@@ -385,6 +425,12 @@ class CudaBackend:
                 dz.data_ptr() % 16 == 0 and _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw):
             self._timed("umma:wgrad", flops, lambda: call(
                 "b200em_conv3d_wgrad_umma", xp, xld, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cin, Cout, kd, kh,
+                kw, _stream(x)))
+            return
+        if self.tf32_enabled() and x.dtype == torch.float32 and xld % 4 == 0 and zld % 4 == 0 and x.data_ptr() % 16 == 0 and \
+                dz.data_ptr() % 16 == 0 and _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw):
+            self._timed("tf32:wgrad", flops, lambda: call(
+                "b200em_conv3d_wgrad_umma_tf32", xp, xld, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cin, Cout, kd, kh,
                 kw, _stream(x)))
             return
         if Cin <= 4:

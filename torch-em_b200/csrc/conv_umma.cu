@@ -39,14 +39,17 @@ constexpr int MAX_SMEM = 227 * 1024;
 }  // namespace
 
 
+// Activations / packed weights are bf16 (kind::f16 MMAs, K = 16) or fp32 (kind::tf32 MMAs, K = 8: the tensor core reads the upper
+// 19 bits of every fp32 word -- what torch / cuDNN do for fp32 convolutions by default, torch.backends.cudnn.allow_tf32).  Either
+// way a 16-byte shared-memory unit holds EPU = 16 / sizeof(T) channels of one voxel and an MMA K step consumes two units.
 struct ConvUmmaParams {
-    const __nv_bfloat16* x; long long x_ld;
+    const void* x; long long x_ld;
     const float* in_ss;
-    const __nv_bfloat16* w;
+    const void* w;
     const float* bias;
-    __nv_bfloat16* y; long long y_ld;
+    void* y; long long y_ld;
     float* sums;
-    const __nv_bfloat16* dot_x; long long dot_ld;   // non-null: sums = (sum y, sum y * dot_x) -- the norm-backward reductions
+    const void* dot_x; long long dot_ld;   // non-null: sums = (sum y, sum y * dot_x) -- the norm-backward reductions
     int N, D, H, W, Cin, Cout;
     int kd, kh, kw, relu;
     int R, NP, CC, nchunks, G, acc_bufs;
@@ -65,11 +68,52 @@ __device__ __forceinline__ void item_coords(const ConvUmmaParams& p, long long i
     n = (int)item; d0 = (int)td * p.R; h0 = (int)th * TH; w0 = (int)tw * TW;
 }
 
+// NV consecutive channels of one voxel: registers (fp32) <-> global memory in the activation type, 16-byte accesses.
+template <typename T, int NV>
+__device__ __forceinline__ void store_row(T* __restrict__ dst, const float (&v)[NV]) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int q = 0; q < NV / 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NV / 8; ++q) {
+            uint4 o;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(dst + 8 * q) = o;
+        }
+    }
+}
+template <typename T, int NV>
+__device__ __forceinline__ void load_row(const T* __restrict__ src, bool valid, float (&v)[NV]) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int q = 0; q < NV / 4; ++q) {
+            const float4 t = valid ? __ldg(reinterpret_cast<const float4*>(src + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NV / 8; ++q) {
+            const uint4 xv = valid ? __ldg(reinterpret_cast<const uint4*>(src + 8 * q)) : make_uint4(0, 0, 0, 0);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                v[8 * q + 2 * e] = f.x;
+                v[8 * q + 2 * e + 1] = f.y;
+            }
+        }
+    }
+}
+
 // R_ = depth slabs per work item, KC_ = K=16 steps per channel chunk: compile-time so that the single-thread MMA issue
 // loop is straight-line code with immediate operand offsets (it bounds the small-N layers otherwise).
-template <int R_, int KC_>
+template <typename TA, int R_, int KC_>
 __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int EPU = 16 / (int)sizeof(TA);       // channels per 16-byte unit: 8 (bf16) or 4 (fp32 / TF32)
     // carve: A[2] | B[NSTAGE] | bias[NP] | sums[2*NP] | barriers | tmem ptr
     uint8_t* smA = smem;
     uint8_t* smB = smA + 2 * p.a_bytes;
@@ -131,16 +175,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
             for (int c = 0; c < p.nchunks; ++c, ++fill) {
                 const int buf = fill & 1;
                 mbar_wait(&a_empty[buf], ((fill >> 1) & 1) ^ 1);
-                const int ch0 = c * p.CC + j * 8;
-                float sc[8], sh[8];
+                const int ch0 = c * p.CC + j * EPU;
+                float sc[EPU], sh[EPU];
                 if (p.in_ss) {
                     const float* q = p.in_ss + ((size_t)n * p.Cin + ch0) * 2;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
+                    for (int e = 0; e < EPU; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
                 }
                 uint8_t* dstbase = smA + buf * p.a_bytes + j * PLANE;
-                const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
-                load_halo_tile_async<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * PLANE, t / J, NLOAD / J, units, d0, h0, w0, pd,
+                const TA* xn = reinterpret_cast<const TA*>(p.x) + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
+                load_halo_tile_async<HP, WP, TA>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * PLANE, t / J, NLOAD / J, units, d0, h0, w0, pd,
                                p.D, p.H, p.W);
                 fence_proxy_async();
                 __syncwarp();
@@ -151,8 +195,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
         // ===================== weight loader =====================
         if (elect_one()) {
             const uint32_t bytes = (uint32_t)p.b_stage_bytes;
-            const size_t tap_elems = (size_t)J * p.NP * 8;
-            const __nv_bfloat16* wblk = p.w + (size_t)nblk * p.nchunks * taps * tap_elems;
+            const size_t tap_elems = (size_t)J * p.NP * 16;          // BYTES per (chunk, tap) block of the packed operand
+            const uint8_t* wblk = reinterpret_cast<const uint8_t*>(p.w) + (size_t)nblk * p.nchunks * taps * tap_elems;
             uint32_t cnt = 0;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x)
                 for (int c = 0; c < p.nchunks; ++c)
@@ -169,7 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
         // built once, only their 14-bit start-address field changes, and with R_/KC_ known at compile time the per-tap
         // body is R_*KC_ MMAs whose operand offsets are immediates.
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(128, p.NP);
+            const uint32_t idesc = make_idesc<TA>(128, p.NP);
             const uint64_t ad = make_desc(0, PLANE, WP * 16), bd = make_desc(0, (uint32_t)(p.NP * 16), 128);
             const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
             const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
@@ -209,14 +253,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                             if ((c | tap) == 0) {
 #pragma unroll
                                 for (int r = 0; r < R_; ++r) {
-                                    umma_bf16_c<false>(tcol[r], a0 + r * SLAB16, a_hi, b0, b_hi, idesc);
-                                    if (KC_ == 2) umma_bf16_c<true>(tcol[r], a0 + r * SLAB16 + K16, a_hi, b0 + bk16, b_hi, idesc);
+                                    umma_c<TA, false>(tcol[r], a0 + r * SLAB16, a_hi, b0, b_hi, idesc);
+                                    if (KC_ == 2) umma_c<TA, true>(tcol[r], a0 + r * SLAB16 + K16, a_hi, b0 + bk16, b_hi, idesc);
                                 }
                             } else {
 #pragma unroll
                                 for (int r = 0; r < R_; ++r) {
-                                    umma_bf16_c<true>(tcol[r], a0 + r * SLAB16, a_hi, b0, b_hi, idesc);
-                                    if (KC_ == 2) umma_bf16_c<true>(tcol[r], a0 + r * SLAB16 + K16, a_hi, b0 + bk16, b_hi, idesc);
+                                    umma_c<TA, true>(tcol[r], a0 + r * SLAB16, a_hi, b0, b_hi, idesc);
+                                    if (KC_ == 2) umma_c<TA, true>(tcol[r], a0 + r * SLAB16 + K16, a_hi, b0 + bk16, b_hi, idesc);
                                 }
                             }
                         }
@@ -244,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
             const int rmax = min(p.R, p.D - d0);
             for (int r = 0; r < rmax; ++r) {
                 const int gd = d0 + r;
-                __nv_bfloat16* yp = p.y + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.y_ld + nblk * p.NP;
+                TA* yp = reinterpret_cast<TA*>(p.y) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.y_ld + nblk * p.NP;
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * acc_cols + r * p.NP;
                 for (int cb = 0; cb < p.NP; cb += 32) {
                     if (p.NP - cb >= 32) {
@@ -256,33 +300,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         for (int i = 0; i < 32; ++i) {
                             float f = __uint_as_float(raw[i]) + s_bias[cb + i];
                             if (p.relu) f = fmaxf(f, 0.f);
-                            v[i] = __bfloat162float(__float2bfloat16_rn(f));
+                            v[i] = round_as<TA>(f);
                         }
-                        if (valid_hw) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 o;
-                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
-                                *reinterpret_cast<uint4*>(yp + cb + 8 * q) = o;
-                            }
-                        }
+                        if (valid_hw) store_row<TA, 32>(yp + cb, v);
                         if (p.sums) {
                             float s1[32], s2[32];
                             if (p.dot_x) {
-                                const __nv_bfloat16* xq = p.dot_x + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    uint4 xv = valid_hw ? __ldg(reinterpret_cast<const uint4*>(xq + 8 * q)) : make_uint4(0, 0, 0, 0);
-                                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const float2 f = __bfloat1622float2(h2[e]);
-                                        s2[8 * q + 2 * e] = f.x;
-                                        s2[8 * q + 2 * e + 1] = f.y;
-                                    }
-                                }
+                                const TA* xq = reinterpret_cast<const TA*>(p.dot_x) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
+                                load_row<TA, 32>(xq, valid_hw, s2);
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] *= s1[i]; }
                             } else {
@@ -303,33 +328,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         for (int i = 0; i < 16; ++i) {
                             float f = __uint_as_float(raw[i]) + s_bias[cb + i];
                             if (p.relu) f = fmaxf(f, 0.f);
-                            v[i] = __bfloat162float(__float2bfloat16_rn(f));
+                            v[i] = round_as<TA>(f);
                         }
-                        if (valid_hw) {
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                uint4 o;
-                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
-                                *reinterpret_cast<uint4*>(yp + cb + 8 * q) = o;
-                            }
-                        }
+                        if (valid_hw) store_row<TA, 16>(yp + cb, v);
                         if (p.sums) {
                             float s1[16], s2[16];
                             if (p.dot_x) {
-                                const __nv_bfloat16* xq = p.dot_x + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
-#pragma unroll
-                                for (int q = 0; q < 2; ++q) {
-                                    uint4 xv = valid_hw ? __ldg(reinterpret_cast<const uint4*>(xq + 8 * q)) : make_uint4(0, 0, 0, 0);
-                                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const float2 f = __bfloat1622float2(h2[e]);
-                                        s2[8 * q + 2 * e] = f.x;
-                                        s2[8 * q + 2 * e + 1] = f.y;
-                                    }
-                                }
+                                const TA* xq = reinterpret_cast<const TA*>(p.dot_x) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
+                                load_row<TA, 16>(xq, valid_hw, s2);
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] *= s1[i]; }
                             } else {
@@ -409,10 +415,11 @@ struct UmmaShape {
 };
 
 // Channel counts the tensor-core path takes; everything else goes to the direct kernel.
-static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s) {
+static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s, bool f32 = false) {
     if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16) return false;
     if (Cout > 256 && Cout % 128) return false;
-    s.CC = (Cin % 32 == 0) ? 32 : 16;
+    // channels per chunk: four 16-byte planes per slice either way (32 bf16 channels, or 16 fp32 channels for the TF32 path)
+    s.CC = f32 ? 16 : ((Cin % 32 == 0) ? 32 : 16);
     // Output-channel block of one CTA.  N = 128 already issues at the full tensor rate, so wide layers are cut
     // into 128-channel blocks: twice the CTAs of a 256-wide block for the deep levels (8^3 / 16^3 volumes have few voxel
     // tiles), half the weight bytes streamed per CTA, and room for double-buffered accumulators (2 * R * 128 <= 512).
@@ -420,7 +427,7 @@ static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s) 
     s.nblk = Cout / s.NP;
     const int taps = kd * kh * kw;
     s.G = (taps % 3 == 0 && s.NP <= 64) ? 3 : 1;
-    const int J = s.CC / 8;
+    const int J = s.CC / (f32 ? 4 : 8);
     s.b_stage_bytes = s.G * J * s.NP * 16;
     for (int R = 4; R >= 1; R >>= 1) {
         if (R * s.NP > 512) continue;
@@ -446,32 +453,38 @@ static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s) 
 // The haloed x_hat tile is the same shared-memory image the forward kernel builds (and the same fused norm apply);
 // the (b,c) tap shift is again just a start-address offset of the descriptor.
 namespace {
-constexpr int WG_R = 2;                        // depth slabs per work item
-constexpr int WG_DZ_PLANE = TH * TW * 16;      // bytes per 8-channel plane of a dz slab
+constexpr int WG_DZ_PLANE = TH * TW * 16;      // bytes per 16-byte-unit plane (8 bf16 / 4 fp32 channels) of a dz slab
+// depth slabs per work item: 2 with bf16 operands, 1 with fp32 (TF32) operands whose 32-channel chunk is 8 planes per slice
+template <typename TA> struct WgR { static constexpr int value = sizeof(TA) == 4 ? 1 : 2; };
 }  // namespace
 
 struct WgradUmmaParams {
-    const __nv_bfloat16* x; long long x_ld;
+    const void* x; long long x_ld;
     const float* in_ss;
-    const __nv_bfloat16* dz; long long dz_ld;
+    const void* dz; long long dz_ld;
     float* dw;
     float* db;
     int N, D, H, W, Cin, Cout;
     int kd, kh, kw;
     int NB, nco;                               // Cout block, number of Cout blocks
+    int pad_bytes;                             // zeroed shared memory behind the x buffers for the last slab's over-read
     int tiles_w, tiles_h, tiles_d;
     long long items;
     int x_bytes, dz_bytes;
     int debug;                                 // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 4 no MMAs, 8 no epilogue atomics
 };
 
+template <typename TA>
 __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const WgradUmmaParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // carve: X[2] | pad slice | DZ[2] | db sums[NB] | barriers | tmem ptr
-    constexpr int J = 4;                                       // 32-channel chunk = 4 planes
+    // carve: X[2] | pad slices | DZ[2] | db sums[NB] | barriers | tmem ptr
+    constexpr int EPU = 16 / (int)sizeof(TA);                  // channels per 16-byte unit
+    constexpr int J = 32 / EPU;                                // 32-channel chunk = 4 (bf16) or 8 (fp32) planes per slice
+    constexpr int WG_R = WgR<TA>::value;
+    constexpr int KROWS = sizeof(TA) == 4 ? 1 : 2;             // tile rows (8 voxels each) per MMA K step: K = 8 (tf32) or 16
     const int nslices = WG_R + p.kd - 1;
     uint8_t* smX = smem;
-    uint8_t* smZ = smX + 2 * p.x_bytes + 4 * J * PLANE;        // room for the "slice r+3" over-read of the last slab
+    uint8_t* smZ = smX + 2 * p.x_bytes + p.pad_bytes;          // room for the over-read of the last slab (slices r+1 .. r+3)
     float* s_db = reinterpret_cast<float*>(smZ + 2 * p.dz_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_db + p.NB);
     uint64_t* full = bars;            // [2] 128 loader arrivals
@@ -482,7 +495,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.y / p.nco, cob = blockIdx.y % p.nco;
-    const int JO = p.NB / 8;
+    const int JO = p.NB / EPU;
     const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
     const int tap9 = p.kh * p.kw;
     uint32_t tmem_cols = 32;
@@ -500,7 +513,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
     }
     for (int i = threadIdx.x; i < p.NB; i += THREADS) s_db[i] = 0.f;
     // the over-read region must hold finite-or-not garbage only in rows that are ignored; zero it once anyway
-    for (int i = threadIdx.x; i < 4 * J * PLANE / 16; i += THREADS)
+    for (int i = threadIdx.x; i < p.pad_bytes / 16; i += THREADS)
         reinterpret_cast<uint4*>(smX + 2 * p.x_bytes)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
@@ -521,9 +534,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
         const int t = threadIdx.x - 128;
         const int j = t % J, jo = t % JO;
         const int xunits = nslices * HP * WP, zunits = WG_R * TH * TW;
-        float dbacc[8], sc[8], sh[8];
+        float dbacc[EPU], sc[EPU], sh[EPU];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { dbacc[e] = 0.f; sc[e] = 1.f; sh[e] = 0.f; }
+        for (int e = 0; e < EPU; ++e) { dbacc[e] = 0.f; sc[e] = 1.f; sh[e] = 0.f; }
         int cur_n = -1;
         uint32_t fill = 0;
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++fill) {
@@ -531,17 +544,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
             coords(item, n, d0, h0, w0);
             const int buf = fill & 1;
             mbar_wait(&empty[buf], ((fill >> 1) & 1) ^ 1);
-            const int ch0 = chunk * 32 + j * 8;
-            if (p.in_ss && n != cur_n) {           // scale/shift of this thread's 8 channels: reload only when the sample changes
+            const int ch0 = chunk * 32 + j * EPU;
+            if (p.in_ss && n != cur_n) {           // scale/shift of this thread's channels: reload only when the sample changes
                 const float* q = p.in_ss + ((size_t)n * p.Cin + ch0) * 2;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
+                for (int e = 0; e < EPU; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
                 cur_n = n;
             }
             uint8_t* xdst = smX + buf * p.x_bytes + j * PLANE;
-            const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
+            const TA* xn = reinterpret_cast<const TA*>(p.x) + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
             uint8_t* zdst = smZ + buf * p.dz_bytes + jo * WG_DZ_PLANE;
-            const __nv_bfloat16* zn = p.dz + (size_t)n * p.D * p.H * p.W * p.dz_ld + cob * p.NB + jo * 8;
+            const TA* zn = reinterpret_cast<const TA*>(p.dz) + (size_t)n * p.D * p.H * p.W * p.dz_ld + cob * p.NB + jo * EPU;
             const int zstep = NLOAD / JO;
             if (!(p.debug & 1)) {
                 // dz slabs: plain copies, issued first; the wait inside load_halo_tile_async covers them as well
@@ -550,23 +563,29 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
                     const int wl = v % TW, hl = (v / TW) % TH, r = v / (TW * TH);
                     const int gd = d0 + r, gh = h0 + hl, gw = w0 + wl;
                     const bool in = gd < p.D && gh < p.H && gw < p.W;
-                    const __nv_bfloat16* src = in ? zn + (((size_t)gd * p.H + gh) * p.W + gw) * p.dz_ld : zn;
+                    const TA* src = in ? zn + (((size_t)gd * p.H + gh) * p.W + gw) * p.dz_ld : zn;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(z32 + (uint32_t)(r * JO * WG_DZ_PLANE + (hl * TW + wl) * 16)),
                                  "l"(src), "r"(in ? 16 : 0)
                                  : "memory");
                 }
-                load_halo_tile_async<HP, WP>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, xdst, J * PLANE, t / J, NLOAD / J, xunits, d0, h0, w0, pd,
-                                             p.D, p.H, p.W);
+                load_halo_tile_async<HP, WP, TA>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, xdst, J * PLANE, t / J, NLOAD / J, xunits, d0, h0, w0,
+                                                 pd, p.D, p.H, p.W);
                 if (p.db && chunk == 0) {
                     for (int v = t / JO; v < zunits; v += zstep) {
                         const int wl = v % TW, hl = (v / TW) % TH, r = v / (TW * TH);
                         const uint4 val = *reinterpret_cast<const uint4*>(zdst + r * JO * WG_DZ_PLANE + (hl * TW + wl) * 16);
-                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+                        if constexpr (sizeof(TA) == 4) {
+                            const float* f = reinterpret_cast<const float*>(&val);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float2 f = __bfloat1622float2(h2[e]);
-                            dbacc[2 * e] += f.x;
-                            dbacc[2 * e + 1] += f.y;
+                            for (int e = 0; e < 4; ++e) dbacc[e] += f[e];
+                        } else {
+                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 f = __bfloat1622float2(h2[e]);
+                                dbacc[2 * e] += f.x;
+                                dbacc[2 * e + 1] += f.y;
+                            }
                         }
                     }
                 }
@@ -577,14 +596,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
         }
         if (p.db && chunk == 0) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(&s_db[jo * 8 + e], dbacc[e]);
+            for (int e = 0; e < EPU; ++e) atomicAdd(&s_db[jo * EPU + e], dbacc[e]);
             asm volatile("bar.sync 2, %0;" ::"n"(NLOAD) : "memory");
             if (t < p.NB) atomicAdd(p.db + cob * p.NB + t, s_db[t]);
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(128, p.NB, 1, 1);      // both operands MN-major
+            const uint32_t idesc = make_idesc<TA>(128, p.NB, 1, 1);       // both operands MN-major
             // A: LBO = next 8 voxels (next tile row), SBO = next 8 channels (next plane); B likewise on the dz slab
             const uint64_t ad = make_desc(0, WP * 16, PLANE), bd = make_desc(0, TW * 16, WG_DZ_PLANE);
             const uint32_t a_hi = (uint32_t)(ad >> 32), a_lo_c = (uint32_t)(ad & 0xFFFFFFFFu);
@@ -607,12 +626,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
                     for (int tp = 0; tp < tap9; ++tp) {
                         const uint32_t a0 = xs + s_tap9[tp];
                         const uint32_t tacc = tmem_base + tp * nb;
-                        // K step ks = voxel rows hl = 2ks, 2ks+1 (8 voxels each); offsets are immediates
-                        if (first) umma_bf16_c<false>(tacc, a0, a_hi, zs, b_hi, idesc);
-                        else umma_bf16_c<true>(tacc, a0, a_hi, zs, b_hi, idesc);
+                        // K step ks = KROWS voxel rows of the tile (8 voxels each); offsets are immediates
+                        if (first) umma_c<TA, false>(tacc, a0, a_hi, zs, b_hi, idesc);
+                        else umma_c<TA, true>(tacc, a0, a_hi, zs, b_hi, idesc);
 #pragma unroll
-                        for (int ks = 1; ks < TH / 2; ++ks)
-                            umma_bf16_c<true>(tacc, a0 + ks * 2 * WP, a_hi, zs + ks * 2 * TW, b_hi, idesc);
+                        for (int ks = 1; ks < TH / KROWS; ++ks)
+                            umma_c<TA, true>(tacc, a0 + ks * KROWS * WP, a_hi, zs + ks * KROWS * TW, b_hi, idesc);
                     }
                 }
                 umma_commit(&empty[buf]);
@@ -660,9 +679,9 @@ static bool wgrad_umma_shape(int Cin, int Cout, int& NB) {
 
 
 // layout parameters of the packed operand (pack.cu: batched packing of every weight of a model in one launch)
-bool umma_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC, int* NP) {
+bool umma_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC, int* NP, bool f32) {
     UmmaShape s;
-    if (!umma_shape(Cin, Cout, kd, kh, kw, s)) return false;
+    if (!umma_shape(Cin, Cout, kd, kh, kw, s, f32)) return false;
     *CC = s.CC; *NP = s.NP;
     return true;
 }
@@ -670,6 +689,119 @@ bool umma_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC, int* N
 }  // namespace b200em
 
 using namespace b200em;
+
+template <typename TA>
+static int launch_conv_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+                            void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
+                            int Cout, int kd, int kh, int kw, int relu, void* stream) {
+    constexpr bool F32 = sizeof(TA) == 4;
+    constexpr int EPU = 16 / (int)sizeof(TA);
+    B2_CHECK_ARG(x && w_packed && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma: bad arguments");
+    B2_CHECK_ARG((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv3d_umma: kernel dims must be 1 or 3");
+    UmmaShape s;
+    if (!umma_shape(Cin, Cout, kd, kh, kw, s, F32)) {
+        set_error("conv3d_umma: channel counts (%d -> %d) not supported by the tcgen05 path", Cin, Cout);
+        return 2;
+    }
+    B2_CHECK_ARG(x_ld % EPU == 0 && y_ld % EPU == 0 && aligned16(x) && aligned16(y), "conv3d_umma: activations must be 16-byte aligned with a pitch that keeps them so");
+    B2_CHECK_ARG(x_ld >= Cin && y_ld >= Cout, "conv3d_umma: pitch smaller than channel count");
+    ConvUmmaParams p;
+    p.x = x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.w = w_packed; p.bias = bias;
+    p.y = y; p.y_ld = y_ld; p.sums = sums;
+    p.dot_x = dot_x; p.dot_ld = dot_ld;
+    B2_CHECK_ARG(!dot_x || (sums && dot_ld % EPU == 0 && aligned16(dot_x) && dot_ld >= Cout), "conv3d_umma: dot_x needs sums, 16-byte alignment and pitch >= Cout");
+    p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.relu = relu;
+    // Depth slabs per work item: the shape admits R <= s.R; fewer slabs = more work items (the deep levels have fewer voxel
+    // tiles than SMs) but the weight block is streamed once per item.  Cost model per CTA (cycles): items per CTA x
+    // max(MMA issue, weight stream at ~48 B/clk from L2) + a fixed pipeline fill per item.
+    {
+        const int taps = kd * kh * kw;
+        const long long cols = (long long)N * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+        const int cta_cap = sm_count() / s.nblk > 0 ? sm_count() / s.nblk : 1;
+        const double mma_cyc = s.NP / 2 > 32 + s.NP / 4 ? s.NP / 2 : 32 + s.NP / 4;
+        const double wts = (double)taps * Cin * s.NP * 2 / 48.0;
+        double best = 1e300;
+        int best_r = s.R;
+        for (int R = s.R; R >= 1; R >>= 1) {
+            const long long items = cols * ((D + R - 1) / R);
+            const long long gx_ = items < cta_cap ? items : cta_cap;
+            const long long per_cta = (items + gx_ - 1) / gx_;
+            const double mma = (double)R * taps * (Cin / (2 * EPU)) * mma_cyc;
+            const double epi = (2 * R * s.NP <= 512) ? 0.0 : (double)R * (s.NP / 32) * 700.0;   // single accumulator set: the epilogue is not overlapped
+            const double cost = per_cta * ((mma > wts ? mma : wts) + epi + 4000.0 + 1500.0 * (R + kd - 1));
+            if (cost < best * 0.97) { best = cost; best_r = R; }
+        }
+        if (best_r != s.R) {
+            s.R = best_r;
+            s.acc_bufs = (2 * s.R * s.NP <= 512) ? 2 : 1;
+            s.a_bytes = (s.R + kd - 1) * (s.CC / EPU) * PLANE;
+            s.smem_bytes = 2 * s.a_bytes + NSTAGE * s.b_stage_bytes + s.NP * 4 * 3 + 16 * 8 + 16 + 27 * 4 + 128;
+        }
+    }
+    p.R = s.R; p.NP = s.NP; p.CC = s.CC; p.nchunks = Cin / s.CC; p.G = s.G; p.acc_bufs = s.acc_bufs;
+    p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + s.R - 1) / s.R;
+    p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
+    p.a_bytes = s.a_bytes; p.b_stage_bytes = s.b_stage_bytes;
+    long long gx = p.items < sm_count() / s.nblk ? p.items : sm_count() / s.nblk;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)s.nblk, 1);
+#define B2_UMMA_LAUNCH(R_, KC_)                                                                                             \
+    do {                                                                                                                    \
+        B2_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<TA, R_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM)); \
+        conv3d_umma_kernel<TA, R_, KC_><<<grid, THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                             \
+    } while (0)
+    const int kc = s.CC / (2 * EPU);            // MMA K steps per chunk (two 16-byte planes each)
+    if (s.R == 4 && kc == 2) B2_UMMA_LAUNCH(4, 2);
+    else if (s.R == 4) B2_UMMA_LAUNCH(4, 1);
+    else if (s.R == 2 && kc == 2) B2_UMMA_LAUNCH(2, 2);
+    else if (s.R == 2) B2_UMMA_LAUNCH(2, 1);
+    else if (kc == 2) B2_UMMA_LAUNCH(1, 2);
+    else B2_UMMA_LAUNCH(1, 1);
+#undef B2_UMMA_LAUNCH
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+
+template <typename TA>
+static int launch_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw,
+                             float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream) {
+    constexpr int EPU = 16 / (int)sizeof(TA);
+    constexpr int WG_R = WgR<TA>::value;
+    constexpr int J = 32 / EPU;
+    B2_CHECK_ARG(x && dz && dw && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_wgrad_umma: bad arguments");
+    B2_CHECK_ARG((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv3d_wgrad_umma: kernel dims must be 1 or 3");
+    int NB;
+    if (!wgrad_umma_shape(Cin, Cout, NB)) {
+        set_error("conv3d_wgrad_umma: channel counts (%d -> %d) not supported by the tcgen05 path", Cin, Cout);
+        return 2;
+    }
+    B2_CHECK_ARG(x_ld % EPU == 0 && dz_ld % EPU == 0 && aligned16(x) && aligned16(dz), "conv3d_wgrad_umma: activations must be 16-byte aligned with a pitch that keeps them so");
+    WgradUmmaParams p;
+    p.x = x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.dz = dz; p.dz_ld = dz_ld;
+    p.dw = dw; p.db = db;
+    p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
+    p.NB = NB; p.nco = Cout / NB;
+    p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + WG_R - 1) / WG_R;
+    p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
+    p.x_bytes = (WG_R + kd - 1) * J * PLANE;
+    p.dz_bytes = WG_R * (NB / EPU) * WG_DZ_PLANE;
+    p.pad_bytes = (4 - kd) * J * PLANE;          // slab r reads slices r .. r+3; WG_R + kd - 1 are loaded
+    { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    const int smem_bytes = 2 * p.x_bytes + p.pad_bytes + 2 * p.dz_bytes + NB * 4 + 8 * 8 + 16 + 9 * 4 + 128;
+    B2_CHECK_ARG(smem_bytes <= MAX_SMEM, "conv3d_wgrad_umma: shared memory budget exceeded");
+    B2_CUDA(cudaFuncSetAttribute(conv3d_wgrad_umma_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    const int pairs = (Cin / 32) * p.nco;
+    long long splits = sm_count() / pairs;
+    if (splits < 1) splits = 1;
+    if (splits > p.items) splits = p.items;
+    dim3 grid((unsigned)splits, (unsigned)pairs, 1);
+    conv3d_wgrad_umma_kernel<TA><<<grid, THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" {
 
@@ -697,71 +829,20 @@ int b200em_conv3d_umma_pack(const float* w, int Cout, int Cin, int kd, int kh, i
 int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
                        void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
                        int Cout, int kd, int kh, int kw, int relu, void* stream) {
-    B2_CHECK_ARG(x && w_packed && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma: bad arguments");
-    B2_CHECK_ARG((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv3d_umma: kernel dims must be 1 or 3");
+    return launch_conv_umma<__nv_bfloat16>(x, x_ld, in_scale_shift, w_packed, bias, y, y_ld, sums, dot_x, dot_ld, N, D, H, W, Cin, Cout, kd,
+                                           kh, kw, relu, stream);
+}
+
+int b200em_conv3d_umma_tf32_supported(int Cin, int Cout, int kd, int kh, int kw) {
     UmmaShape s;
-    if (!umma_shape(Cin, Cout, kd, kh, kw, s)) {
-        set_error("conv3d_umma: channel counts (%d -> %d) not supported by the tcgen05 path", Cin, Cout);
-        return 2;
-    }
-    B2_CHECK_ARG(x_ld % 8 == 0 && y_ld % 8 == 0 && aligned16(x) && aligned16(y), "conv3d_umma: activations must be 16-byte aligned with pitch % 8 == 0");
-    B2_CHECK_ARG(x_ld >= Cin && y_ld >= Cout, "conv3d_umma: pitch smaller than channel count");
-    ConvUmmaParams p;
-    p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.w = (const __nv_bfloat16*)w_packed; p.bias = bias;
-    p.y = (__nv_bfloat16*)y; p.y_ld = y_ld; p.sums = sums;
-    p.dot_x = (const __nv_bfloat16*)dot_x; p.dot_ld = dot_ld;
-    B2_CHECK_ARG(!dot_x || (sums && dot_ld % 8 == 0 && aligned16(dot_x) && dot_ld >= Cout), "conv3d_umma: dot_x needs sums, 16-byte alignment and pitch >= Cout");
-    p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.relu = relu;
-    // Depth slabs per work item: the shape admits R <= s.R; fewer slabs = more work items (the deep levels have fewer voxel
-    // tiles than SMs) but the weight block is streamed once per item.  Cost model per CTA (cycles): items per CTA x
-    // max(MMA issue, weight stream at ~48 B/clk from L2) + a fixed pipeline fill per item.
-    {
-        const int taps = kd * kh * kw;
-        const long long cols = (long long)N * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
-        const int cta_cap = sm_count() / s.nblk > 0 ? sm_count() / s.nblk : 1;
-        const double mma_cyc = s.NP / 2 > 32 + s.NP / 4 ? s.NP / 2 : 32 + s.NP / 4;
-        const double wts = (double)taps * Cin * s.NP * 2 / 48.0;
-        double best = 1e300;
-        int best_r = s.R;
-        for (int R = s.R; R >= 1; R >>= 1) {
-            const long long items = cols * ((D + R - 1) / R);
-            const long long gx_ = items < cta_cap ? items : cta_cap;
-            const long long per_cta = (items + gx_ - 1) / gx_;
-            const double mma = (double)R * taps * (Cin / 16) * mma_cyc;
-            const double epi = (2 * R * s.NP <= 512) ? 0.0 : (double)R * (s.NP / 32) * 700.0;   // single accumulator set: the epilogue is not overlapped
-            const double cost = per_cta * ((mma > wts ? mma : wts) + epi + 4000.0 + 1500.0 * (R + kd - 1));
-            if (cost < best * 0.97) { best = cost; best_r = R; }
-        }
-        if (best_r != s.R) {
-            s.R = best_r;
-            s.acc_bufs = (2 * s.R * s.NP <= 512) ? 2 : 1;
-            s.a_bytes = (s.R + kd - 1) * (s.CC / 8) * PLANE;
-            s.smem_bytes = 2 * s.a_bytes + NSTAGE * s.b_stage_bytes + s.NP * 4 * 3 + 16 * 8 + 16 + 27 * 4 + 128;
-        }
-    }
-    p.R = s.R; p.NP = s.NP; p.CC = s.CC; p.nchunks = Cin / s.CC; p.G = s.G; p.acc_bufs = s.acc_bufs;
-    p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + s.R - 1) / s.R;
-    p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
-    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
-    p.a_bytes = s.a_bytes; p.b_stage_bytes = s.b_stage_bytes;
-    long long gx = p.items < sm_count() / s.nblk ? p.items : sm_count() / s.nblk;
-    if (gx < 1) gx = 1;
-    dim3 grid((unsigned)gx, (unsigned)s.nblk, 1);
-#define B2_UMMA_LAUNCH(R_, KC_)                                                                                             \
-    do {                                                                                                                    \
-        B2_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<R_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));    \
-        conv3d_umma_kernel<R_, KC_><<<grid, THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                                \
-    } while (0)
-    const int kc = s.CC / 16;
-    if (s.R == 4 && kc == 2) B2_UMMA_LAUNCH(4, 2);
-    else if (s.R == 4) B2_UMMA_LAUNCH(4, 1);
-    else if (s.R == 2 && kc == 2) B2_UMMA_LAUNCH(2, 2);
-    else if (s.R == 2) B2_UMMA_LAUNCH(2, 1);
-    else if (kc == 2) B2_UMMA_LAUNCH(1, 2);
-    else B2_UMMA_LAUNCH(1, 1);
-#undef B2_UMMA_LAUNCH
-    B2_LAUNCH_CHECK();
-    return 0;
+    return umma_shape(Cin, Cout, kd, kh, kw, s, true) ? 1 : 0;
+}
+
+int b200em_conv3d_umma_tf32(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+                            void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
+                            int Cout, int kd, int kh, int kw, int relu, void* stream) {
+    return launch_conv_umma<float>(x, x_ld, in_scale_shift, w_packed, bias, y, y_ld, sums, dot_x, dot_ld, N, D, H, W, Cin, Cout, kd, kh, kw,
+                                   relu, stream);
 }
 
 int b200em_conv3d_wgrad_umma_supported(int Cin, int Cout, int kd, int kh, int kw) {
@@ -771,36 +852,12 @@ int b200em_conv3d_wgrad_umma_supported(int Cin, int Cout, int kd, int kh, int kw
 
 int b200em_conv3d_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw,
                              float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream) {
-    B2_CHECK_ARG(x && dz && dw && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_wgrad_umma: bad arguments");
-    B2_CHECK_ARG((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv3d_wgrad_umma: kernel dims must be 1 or 3");
-    int NB;
-    if (!wgrad_umma_shape(Cin, Cout, NB)) {
-        set_error("conv3d_wgrad_umma: channel counts (%d -> %d) not supported by the tcgen05 path", Cin, Cout);
-        return 2;
-    }
-    B2_CHECK_ARG(x_ld % 8 == 0 && dz_ld % 8 == 0 && aligned16(x) && aligned16(dz), "conv3d_wgrad_umma: activations must be 16-byte aligned with pitch % 8 == 0");
-    WgradUmmaParams p;
-    p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.dz = (const __nv_bfloat16*)dz; p.dz_ld = dz_ld;
-    p.dw = dw; p.db = db;
-    p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
-    p.NB = NB; p.nco = Cout / NB;
-    p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + WG_R - 1) / WG_R;
-    p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
-    B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
-    p.x_bytes = (WG_R + kd - 1) * 4 * PLANE;
-    p.dz_bytes = WG_R * (NB / 8) * WG_DZ_PLANE;
-    { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
-    const int smem_bytes = 2 * p.x_bytes + 4 * 4 * PLANE + 2 * p.dz_bytes + NB * 4 + 8 * 8 + 16 + 9 * 4 + 128;
-    B2_CHECK_ARG(smem_bytes <= MAX_SMEM, "conv3d_wgrad_umma: shared memory budget exceeded");
-    B2_CUDA(cudaFuncSetAttribute(conv3d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
-    const int pairs = (Cin / 32) * p.nco;
-    long long splits = sm_count() / pairs;
-    if (splits < 1) splits = 1;
-    if (splits > p.items) splits = p.items;
-    dim3 grid((unsigned)splits, (unsigned)pairs, 1);
-    conv3d_wgrad_umma_kernel<<<grid, THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
-    B2_LAUNCH_CHECK();
-    return 0;
+    return launch_wgrad_umma<__nv_bfloat16>(x, x_ld, in_scale_shift, dz, dz_ld, dw, db, N, D, H, W, Cin, Cout, kd, kh, kw, stream);
+}
+
+int b200em_conv3d_wgrad_umma_tf32(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw,
+                                  float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream) {
+    return launch_wgrad_umma<float>(x, x_ld, in_scale_shift, dz, dz_ld, dw, db, N, D, H, W, Cin, Cout, kd, kh, kw, stream);
 }
 
 }  // extern "C"

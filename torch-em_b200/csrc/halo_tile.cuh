@@ -55,12 +55,31 @@ __device__ __forceinline__ void load_halo_tile(const __nv_bfloat16* __restrict__
     }
 }
 
+// In-place norm apply on one 16-byte unit: 8 bf16 or 4 fp32 channels, scale * x + shift in fp32.
+template <typename T>
+__device__ __forceinline__ void affine_unit(uint4& val, const float* sc, const float* sh) {
+    if constexpr (sizeof(T) == 4) {
+        float* f = reinterpret_cast<float*>(&val);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+    } else {
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 f = __bfloat1622float2(h2[e]);
+            f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
+            f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+            h2[e] = __floats2bfloat162_rn(f.x, f.y);
+        }
+    }
+}
+
 // Asynchronous variant: every 16-byte unit of the thread is issued as one cp.async (LDGSTS, zero-filled when the voxel is
 // outside the volume) with no register staging, so ALL of a thread's units are in flight at once and the tile costs one
 // memory latency instead of one per register batch; the norm apply then runs as an in-place shared-memory pass over the
-// in-volume units this thread copied.  At most 32 units per thread.
-template <int HP_, int WP_>
-__device__ __forceinline__ void load_halo_tile_async(const __nv_bfloat16* __restrict__ xn, long long x_ld, const float* sc, const float* sh,
+// in-volume units this thread copied.  At most 32 units per thread.  T = __nv_bfloat16 (8 channels per unit) or float (4).
+template <int HP_, int WP_, typename T = __nv_bfloat16>
+__device__ __forceinline__ void load_halo_tile_async(const T* __restrict__ xn, long long x_ld, const float* sc, const float* sh,
                                                      bool affine, uint8_t* dst, int slice_stride_bytes, int v0, int step, int units,
                                                      int d0, int h0, int w0, int pd, int D, int H, int W) {
     uint32_t inb = 0;
@@ -71,7 +90,7 @@ __device__ __forceinline__ void load_halo_tile_async(const __nv_bfloat16* __rest
         const int gd = d0 + s - pd, gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
         const uint32_t off = (uint32_t)(s * slice_stride_bytes + (hp_ * WP_ + wp_) * 16);
         const bool in = gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;
-        const __nv_bfloat16* src = in ? xn + (((size_t)gd * H + gh) * W + gw) * x_ld : xn;
+        const T* src = in ? xn + (((size_t)gd * H + gh) * W + gw) * x_ld : xn;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst32 + off), "l"(src), "r"(in ? 16 : 0) : "memory");
         inb |= (in ? 1u : 0u) << i;
     }
@@ -83,14 +102,7 @@ __device__ __forceinline__ void load_halo_tile_async(const __nv_bfloat16* __rest
             const int wp_ = v % WP_, hp_ = (v / WP_) % HP_, s = v / (WP_ * HP_);
             uint4* q = reinterpret_cast<uint4*>(dst + s * slice_stride_bytes + (hp_ * WP_ + wp_) * 16);
             uint4 val = *q;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 f = __bfloat1622float2(h2[e]);
-                f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
-                f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
-                h2[e] = __floats2bfloat162_rn(f.x, f.y);
-            }
+            affine_unit<T>(val, sc, sh);
             *q = val;
         }
     }

@@ -16,7 +16,7 @@
 
 namespace b200em {
 
-bool umma_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC, int* NP);   // conv_umma.cu
+bool umma_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC, int* NP, bool f32);   // conv_umma.cu
 bool ds_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC);              // conv_umma_ds.cu
 
 __global__ void __launch_bounds__(256) pack_batch_kernel(const b200em_pack_job* __restrict__ jobs, int njobs) {
@@ -44,8 +44,24 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const b200em_pack_job* 
         tile[c][r] = w[((size_t)(co0 + c) * Cin + ci0) * taps + r];
     }
     __syncthreads();
-    __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(job.packed);
     const int Kc = dgrad ? Cout : Cin;                 // reduction channels of the packed operand
+    if (job.layout == B200EM_PACK_PLAIN_TF32) {
+        // fp32 operand of the TF32 path: [nblk][chunk (16 ch)][tap][plane j (4 ch)][NPb][4 fp32]; a tile holds two 4-channel units
+        float* __restrict__ outf = reinterpret_cast<float*>(job.packed);
+        const int NPb = job.NPb, nchunks = Kc / CC, J = CC / 4;
+        for (int u = threadIdx.x; u < 16 * taps; u += blockDim.x) {
+            const int nl = u % 8, half = (u / 8) % 2, tp = u / 16;
+            float4 v;
+            float* vf = reinterpret_cast<float*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) vf[e] = dgrad ? tile[4 * half + e][nl * taps + tp] : tile[nl][(4 * half + e) * taps + tp];
+            const int n_ = (dgrad ? ci0 : co0) + nl, k0 = (dgrad ? co0 : ci0) + 4 * half, t_ = dgrad ? taps - 1 - tp : tp;
+            const int nb = n_ / NPb, nn = n_ % NPb, chunk = k0 / CC, j = (k0 % CC) / 4;
+            *reinterpret_cast<float4*>(outf + ((((size_t)(nb * nchunks + chunk) * taps + t_) * J + j) * NPb + nn) * 4) = v;
+        }
+        return;
+    }
+    __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(job.packed);
     const int Nc = dgrad ? Cin : Cout;                 // output channels of the packed operand
     const int nchunks = Kc / CC, J = CC / 8;
     const int thw = job.kh * job.kw;
@@ -88,8 +104,8 @@ int b200em_pack_batch_prepare(b200em_pack_job* jobs, int njobs, int* total_block
                      "pack_batch_prepare: job %d: channels must be multiples of 8 and taps <= 27", i);
         const int n_ = j.dgrad ? j.Cin : j.Cout, k_ = j.dgrad ? j.Cout : j.Cin;   // operand's output / reduction channels
         bool ok;
-        if (j.layout == B200EM_PACK_PLAIN) {
-            ok = umma_pack_layout(k_, n_, j.kd, j.kh, j.kw, &j.CC, &j.NPb);
+        if (j.layout == B200EM_PACK_PLAIN || j.layout == B200EM_PACK_PLAIN_TF32) {
+            ok = umma_pack_layout(k_, n_, j.kd, j.kh, j.kw, &j.CC, &j.NPb, j.layout == B200EM_PACK_PLAIN_TF32);
         } else if (j.layout == B200EM_PACK_DEPTH_STACKED) {
             j.NPb = 0;
             ok = ds_pack_layout(k_, n_, j.kd, j.kh, j.kw, &j.CC);

@@ -152,6 +152,38 @@ __device__ __forceinline__ void umma_bf16_c(uint32_t tmem_d, uint32_t a_lo, uint
     }
 }
 
+// The same with TF32 operands (kind::tf32): A and B are 32-bit words of which the tensor core reads the upper 19 bits (fp32
+// activations and weights are fed as they are), K = 8 per instruction = two 16-byte core-matrix columns of 4 elements.
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32_c(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    if (ACC) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.eq.u32 p, 1, 1;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.u32 p, 1, 1;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+            : "memory");
+    }
+}
+
+// Operand-type dispatch of the issue loops: __nv_bfloat16 -> kind::f16 (K = 16), float -> kind::tf32 (K = 8).
+template <typename TA, bool ACC>
+__device__ __forceinline__ void umma_c(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    if constexpr (sizeof(TA) == 4) umma_tf32_c<ACC>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc);
+    else umma_bf16_c<ACC>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc);
+}
+
 // Shared-memory matrix descriptor, SWIZZLE_NONE ("interleave"), version 1 (Blackwell).
 // K-major operand: 8-row x 16-byte core matrices, each 128 contiguous bytes (row r of the core matrix at +16*r);
 //   lbo = byte distance between the two 16-byte K-chunks of one K=16 step, sbo = byte distance between 8-row groups.
@@ -168,6 +200,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::tf32: TF32 A and B (format code 2 at bits [7,10) and [10,13)), fp32 accumulator.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <typename TA>
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
+    return sizeof(TA) == 4 ? make_idesc_tf32(M, N, a_mn_major, b_mn_major) : make_idesc_bf16(M, N, a_mn_major, b_mn_major);
 }
 
 // TMEM -> registers: this warp's 32 lanes (lane field of taddr = 32 * (warp_id % 4)), 32 / 16 consecutive columns

@@ -34,6 +34,9 @@ from .._lib import call
 __all__ = ["Blocking", "predict_with_halo", "predict_with_halo_pipelined", "standardize"]
 
 MAX_BLOCKS_PER_LAUNCH = 16          # B200EM_MAX_TILE_BLOCKS
+# CUDA-event times (ms) of the last device-path call of worker 0: host -> device copy of the volume, the block loop (gather,
+# standardize, forward, scatter) and the device -> host copy of the result.  Read by bench.py; diagnostic only.
+last_timing = {}
 _RAW_CODES = {"uint8": 0, "int8": 1, "uint16": 2, "int16": 3, "int32": 4, "uint32": 5, "float16": 6, "float32": 7, "float64": 8}
 _SAME_BITS = {"uint16": "int16", "uint32": "int32"}      # dtypes torch cannot hold are shipped as their signed twin
 
@@ -170,7 +173,10 @@ def _device_worker(net, dev, worker_id, n_workers, vol_np, mask_np, blocks, bloc
     code = _RAW_CODES[str(vol_np.dtype)]
     ship = vol_np.view(_SAME_BITS[str(vol_np.dtype)]) if str(vol_np.dtype) in _SAME_BITS else vol_np
     with torch.cuda.device(dev), torch.no_grad(), autocast(dev):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
         vol = torch.from_numpy(ship).to(dev, non_blocking=True)                  # the volume: ONE host -> device copy
+        ev[1].record()
         C = vol.shape[0]
         D, H, W = _to3(vol.shape[1:], ndim, 1)
         spatial = tuple(vol.shape[1:])
@@ -216,8 +222,13 @@ def _device_worker(net, dev, worker_id, n_workers, vol_np, mask_np, blocks, bloc
                 call("b200em_scatter_blocks", _ptr(pred[k:]), Cp, bd, bh, bw, hd, hh, hw, _ints(obeg[k:k + n_]), _ints(oshp[k:k + n_]), n_,
                      _ptr(out_d), D, H, W, 0, Cp, _ptr(mask_d) if mask_d is not None else None, _stream(dev))
         host = torch.empty(out_d.shape, dtype=torch.float32, pin_memory=True)
+        ev[2].record()
         host.copy_(out_d, non_blocking=True)                                     # the result: ONE device -> host copy (pinned)
+        ev[3].record()
         torch.cuda.current_stream(dev).synchronize()
+        if worker_id == 0:
+            last_timing.update(h2d_ms=ev[0].elapsed_time(ev[1]), loop_ms=ev[1].elapsed_time(ev[2]), d2h_ms=ev[2].elapsed_time(ev[3]),
+                               blocks=len(mine), batch_size=batch_size)
     return host, mine
 
 
