@@ -56,7 +56,9 @@ KERNEL_OF = {"first:fwd": "conv3d_first_kernel", "first:wgrad": "conv3d_first_wg
              "ds:dgrad": "conv3d_umma_ds_kernel", "plain:fwd": "conv3d_umma_kernel", "plain:dgrad": "conv3d_umma_kernel",
              "thin:fwd": "conv3d_umma_kernel", "cs:wgrad": "conv3d_wgrad_cs_kernel", "umma:wgrad": "conv3d_wgrad_umma_kernel",
              "thin:wgrad": "conv3d_wgrad_umma_kernel", "direct:fwd": "conv3d_direct_kernel", "direct:dgrad": "conv3d_direct_kernel",
-             "direct:wgrad": "conv3d_wgrad_direct_kernel", "smallcin:wgrad": "conv3d_wgrad_smallcin_kernel"}
+             "direct:wgrad": "conv3d_wgrad_direct_kernel", "smallcin:wgrad": "conv3d_wgrad_smallcin_kernel",
+             "tf32:fwd": "conv3d_umma_kernel<float> (TF32)", "tf32:dgrad": "conv3d_umma_kernel<float> (TF32)",
+             "split3:wgrad": "split_bf16 + 3 x conv3d_wgrad_{cs,umma}_kernel (bf16 hi/lo)"}
 
 
 def synthetic_batch(batch, patch, seed, kind="dice", out_channels=2):

@@ -91,17 +91,15 @@ int b200em_conv3d_umma(const void* x, int64_t x_ld, const float* in_scale_shift,
                        void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
                        int Cout, int kd, int kh, int kw, int relu, void* stream);
 
-/* TF32 variants of the two entry points above: fp32 activations and fp32 packed weights (b200em_pack_batch with
+/* TF32 variant of the conv entry point above: fp32 activations and fp32 packed weights (b200em_pack_batch with
  * B200EM_PACK_PLAIN_TF32), fed to tcgen05.mma.kind::tf32, which reads the upper 19 bits of every operand word -- the arithmetic
  * torch / cuDNN use for fp32 convolutions by default (torch.backends.cudnn.allow_tf32; the reference's mixed_precision=False
- * path, default_trainer.py:132-142).  Same contracts, Cin % 16 == 0 (conv) resp. Cin % 32 == 0 (weight gradient). */
+ * path, default_trainer.py:132-142).  Same contract, Cin % 16 == 0.  (The fp32 weight gradient runs the bf16 weight-gradient
+ * kernels three times on split operands, see b200em_split_bf16.) */
 int b200em_conv3d_umma_tf32_supported(int Cin, int Cout, int kd, int kh, int kw);
 int b200em_conv3d_umma_tf32(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
                             void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
                             int Cout, int kd, int kh, int kw, int relu, void* stream);
-int b200em_conv3d_wgrad_umma_tf32(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld,
-                                  float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw,
-                                  void* stream);
 
 /* "depth-stacked" tcgen05 variant for 3 x kh x kw filters with few output channels (Cout <= 80) whose packed filter
  * fits in shared memory: the three depth taps share one operand fetch (N = 3*Cout) and land in the accumulators of
@@ -188,6 +186,12 @@ int b200em_norm_bwd_finalize(const float* dsums, const float* mean_rstd, const f
 int b200em_norm_bwd_apply(const void* g, int64_t g_ld, const void* x, int64_t x_ld, const float* coef,
                           const void* add, int64_t add_ld, void* out, int64_t out_ld, int dtype,
                           int N, int64_t S, int C, int relu_mask, void* stream);
+
+/* fp32 -> two bf16 tensors with hi + lo ~= x_hat (x_hat = scale*x + shift when in_scale_shift is given, else x): hi =
+ * bf16(x_hat), lo = bf16(x_hat - hi).  Lets the bf16 tensor-core weight-gradient kernels accumulate an fp32-class result as
+ * hi*hi + hi*lo + lo*hi (~16 mantissa bits).  x (N,S,C) with pitch x_ld; hi / lo contiguous (pitch C). */
+int b200em_split_bf16(const float* x, int64_t x_ld, const float* in_scale_shift, void* hi, void* lo, int N, int64_t S, int C,
+                      void* stream);
 
 /* ---- nn.MaxPool3d(factor) (unet.py:645, 316) -------------------------------------------------------------- */
 /* (D,H,W) are the INPUT dims; sums (nullable) [N][C][2] += stats of the pooled output. */

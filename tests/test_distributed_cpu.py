@@ -36,7 +36,7 @@ def _make_model():
     return net
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, min_chunk=32 << 20):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -49,7 +49,7 @@ def _worker(rank, world, port, out_dir):
             for p in net.parameters():
                 p.add_(1.0)
     tb.distributed.broadcast_parameters(net)
-    tb.distributed.sync_gradients(net)
+    tb.distributed.sync_gradients(net, min_chunk_bytes=min_chunk)
     opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
     x, t = _data(rank)
     sums = []
@@ -62,12 +62,20 @@ def _worker(rank, world, port, out_dir):
         opt.step()
         sums.append(tb.distributed.parameter_checksum(net))
     torch.save(sums, os.path.join(out_dir, f"sums{rank}.pt"))
+    torch.save(net.grad_sync.launched, os.path.join(out_dir, f"pieces{rank}.pt"))
     dist.destroy_process_group()
 
 
-def test_flat_allreduce_world2(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("min_chunk", [32 << 20, 1])
+def test_flat_allreduce_world2(tmp_path, min_chunk):
+    """min_chunk = 1 byte: every ready range of the flat buffer is exchanged as its own overlapped piece (base .. end, then one
+    encoder block at a time); the default merges them into one piece for this small model.  Same averaged gradients either way."""
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), min_chunk), nprocs=2, join=True)
+    assert torch.load(tmp_path / "pieces0.pt") == (3 if min_chunk == 1 else 1)       # depth 2: [base..end], enc.1, enc.0
     g0, g1 = torch.load(tmp_path / "grads0.pt"), torch.load(tmp_path / "grads1.pt")
     # single-process reference: mean of the two ranks' local gradients
     from oracle import dice as odice
@@ -82,3 +90,52 @@ def test_flat_allreduce_world2(tmp_path):
         np.testing.assert_allclose(g0[k].numpy(), 0.5 * (local[0][k] + local[1][k]).numpy(), rtol=1e-5, atol=1e-8, err_msg=k)
     s0, s1 = torch.load(tmp_path / "sums0.pt"), torch.load(tmp_path / "sums1.pt")
     assert s0 == s1                                               # replicas bit-identical after each optimizer step
+
+
+class _Patches(torch.utils.data.Dataset):
+    def __init__(self, n=8):
+        g = torch.Generator().manual_seed(0)
+        self.x = torch.randn((n, 1, 8, 16, 16), generator=g)
+        self.y = (torch.nn.functional.avg_pool3d(self.x, 3, 1, 1) > 0).float().repeat(1, 2, 1, 1, 1)
+
+    def __len__(self):
+        return len(self.x)
+
+    def __getitem__(self, i):
+        return self.x[i], self.y[i]
+
+
+def _emu_unet(**kw):
+    import torch_em_b200 as tb
+    from tests.emu_backend import TorchEmuBackend
+    torch.manual_seed(0)
+    net = tb.UNet3d(**kw)
+    net._backend_override = TorchEmuBackend()
+    return net
+
+
+def _trainer(**kw):
+    """The REAL torch_em.default_segmentation_trainer (imported through the stub finder), reference loss (ours has no CPU path)."""
+    sys.path.insert(0, ROOT)
+    from tests import ref_harness
+    te = ref_harness.import_torch_em()
+    return te.default_segmentation_trainer(loss=te.loss.DiceLoss(), metric=te.loss.DiceLoss(), logger=None, compile_model=False,
+                                           mixed_precision=False, **kw)
+
+
+def test_train_multi_gpu_launcher_world2_gloo(tmp_path):
+    """train_multi_gpu with the reference's argument list (multi_gpu_training.py:107-124), two gloo processes on CPUs, the real
+    default_segmentation_trainer inside: rank 0 writes the checkpoints, the weights moved."""
+    from tests import ref_harness
+    if ref_harness.reference_root() is None:
+        pytest.skip("reference package not available")
+    import torch_em_b200 as tb
+    tb.train_multi_gpu(
+        model_callable=_emu_unet, model_kwargs=dict(in_channels=1, out_channels=2, depth=2, initial_features=4, final_activation="Sigmoid"),
+        train_dataset_callable=_Patches, train_dataset_kwargs={}, val_dataset_callable=_Patches, val_dataset_kwargs=dict(n=4),
+        loader_kwargs=dict(batch_size=2, shuffle=True), iterations=4, trainer_callable=_trainer, world_size=2, backend="gloo",
+        name="mgpu", save_root=str(tmp_path))
+    ck = torch.load(tmp_path / "checkpoints" / "mgpu" / "latest.pt", map_location="cpu", weights_only=False)
+    assert ck["iteration"] == 4
+    ref = _emu_unet(in_channels=1, out_channels=2, depth=2, initial_features=4, final_activation="Sigmoid").state_dict()
+    assert any(not torch.equal(ck["model_state"][k], v) for k, v in ref.items())

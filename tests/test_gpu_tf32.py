@@ -91,7 +91,7 @@ def test_tf32_conv_forward_dgrad_wgrad(tf32, case):
         dw, db = torch.zeros_like(w).to(DEV), torch.zeros(Cout, device=DEV)
         B.wgrad(x.to(DEV), ss.to(DEV), dz.to(DEV), dw, db, k)
         torch.cuda.synchronize()
-        assert B.calls["tf32:wgrad"] == 1
+        assert B.calls["split3:wgrad"] == 1
         np.testing.assert_allclose(dw.cpu().numpy(), dw_ref.numpy(), rtol=tol, atol=tol * float(dw_ref.abs().max()))
         np.testing.assert_allclose(db.cpu().numpy(), db_ref.numpy(), rtol=1e-4, atol=1e-4 * float(db_ref.abs().max()))
 
@@ -139,7 +139,7 @@ def test_model_fp32_tf32_no_worse_than_reference_tf32(tf32, kw, shape):
     loss = tb.DiceLoss()(y, t.to(DEV))
     loss.backward()
     torch.cuda.synchronize()
-    assert B.calls.get("tf32:fwd", 0) > 0 and B.calls.get("tf32:dgrad", 0) > 0 and B.calls.get("tf32:wgrad", 0) > 0, dict(B.calls)
+    assert B.calls.get("tf32:fwd", 0) > 0 and B.calls.get("tf32:dgrad", 0) > 0 and B.calls.get("split3:wgrad", 0) > 0, dict(B.calls)
     assert y.dtype == torch.float32
 
     def rel(a, b):

@@ -428,10 +428,27 @@ class CudaBackend:
                 kw, _stream(x)))
             return
         if self.tf32_enabled() and x.dtype == torch.float32 and xld % 4 == 0 and zld % 4 == 0 and x.data_ptr() % 16 == 0 and \
-                dz.data_ptr() % 16 == 0 and _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw):
-            self._timed("tf32:wgrad", flops, lambda: call(
-                "b200em_conv3d_wgrad_umma_tf32", xp, xld, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cin, Cout, kd, kh,
-                kw, _stream(x)))
+                dz.data_ptr() % 16 == 0 and Cin % 8 == 0 and Cout % 8 == 0 and \
+                _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw):
+            # fp32 activations, TF32 allowed: the bf16 tensor-core weight-gradient kernels on split operands -- x_hat = hi + lo,
+            # dz = hi + lo, dW = hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-16 relative; more accurate than TF32's 10
+            # mantissa bits, at three bf16 passes)
+            S = D * H * W
+            xh = torch.empty((2, N, D, H, W, Cin), dtype=torch.bfloat16, device=x.device)
+            zh = torch.empty((2, N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+            call("b200em_split_bf16", xp, xld, _f32(in_ss), _ptr(xh[0]), _ptr(xh[1]), N, S, Cin, _stream(x))
+            call("b200em_split_bf16", zp, zld, None, _ptr(zh[0]), _ptr(zh[1]), N, S, Cout, _stream(x))
+
+            def three_passes():
+                calls, timing, self.timing = self.calls.copy(), self.timing, None
+                try:
+                    self.wgrad(xh[0], None, zh[0], dw, db, kernel)
+                    self.wgrad(xh[0], None, zh[1], dw, db, kernel)
+                    self.wgrad(xh[1], None, zh[0], dw, None, kernel)
+                finally:
+                    self.calls, self.timing = calls, timing    # the three bf16 passes count as ONE fp32 weight gradient
+
+            self._timed("split3:wgrad", flops, three_passes)
             return
         if Cin <= 4:
             self._timed("smallcin:wgrad", flops, lambda: call(

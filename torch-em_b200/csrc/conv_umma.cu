@@ -454,7 +454,11 @@ static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s, 
 // the (b,c) tap shift is again just a start-address offset of the descriptor.
 namespace {
 constexpr int WG_DZ_PLANE = TH * TW * 16;      // bytes per 16-byte-unit plane (8 bf16 / 4 fp32 channels) of a dz slab
-// depth slabs per work item: 2 with bf16 operands, 1 with fp32 (TF32) operands whose 32-channel chunk is 8 planes per slice
+// depth slabs per work item: 2 with bf16 operands, 1 with fp32 (TF32) operands whose 32-channel chunk is 8 planes per slice.
+// NOTE: only the bf16 instantiation is shipped.  With kind::tf32 and both operands MN-major (SWIZZLE_NONE) the accumulators came
+// back as exact zeros on B200 (tests/test_gpu_tf32.py history) -- the no-swizzle MN-major canonical layout of 32-bit operands
+// is not what this kernel assumes -- so the fp32 weight gradient runs as three bf16 MMAs on split operands instead
+// (backend.wgrad: x = hi + lo, dz = hi + lo, hi*hi + hi*lo + lo*hi; ~16 mantissa bits, more than TF32's 10).
 template <typename TA> struct WgR { static constexpr int value = sizeof(TA) == 4 ? 1 : 2; };
 }  // namespace
 
@@ -855,9 +859,5 @@ int b200em_conv3d_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_
     return launch_wgrad_umma<__nv_bfloat16>(x, x_ld, in_scale_shift, dz, dz_ld, dw, db, N, D, H, W, Cin, Cout, kd, kh, kw, stream);
 }
 
-int b200em_conv3d_wgrad_umma_tf32(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw,
-                                  float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream) {
-    return launch_wgrad_umma<float>(x, x_ld, in_scale_shift, dz, dz_ld, dw, db, N, D, H, W, Cin, Cout, kd, kh, kw, stream);
-}
 
 }  // extern "C"

@@ -215,6 +215,34 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ g, int64_t g_ld, con
     }
 }
 
+// fp32 -> (hi, lo) bf16 split of x_hat = scale*x + shift: hi = bf16(x_hat), lo = bf16(x_hat - hi)
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ ss, __nv_bfloat16* __restrict__ hi,
+                  __nv_bfloat16* __restrict__ lo, int64_t S, int C) {
+    const int64_t n = blockIdx.y;
+    const unsigned cvec = C / 4;
+    const int64_t total = S * cvec;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % cvec);
+        const int64_t vox = n * S + i / cvec;
+        const float4 v = *reinterpret_cast<const float4*>(x + vox * x_ld + cv * 4);
+        float f[4] = {v.x, v.y, v.z, v.w};
+        if (ss) {
+            const float* q = ss + ((size_t)n * C + cv * 4) * 2;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f[e] = fmaf(f[e], q[2 * e], q[2 * e + 1]);
+        }
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            h[e] = __float2bfloat16_rn(f[e]);
+            l[e] = __float2bfloat16_rn(f[e] - __bfloat162float(h[e]));
+        }
+        *reinterpret_cast<uint2*>(hi + vox * C + cv * 4) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + vox * C + cv * 4) = *reinterpret_cast<const uint2*>(l);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // max pool forward (+ statistics of the pooled output)
 // F2 = 1: factor (2,2,2) or (1,2,2) known at compile time (FDC = depth factor): the window loads are unrolled and in flight together
@@ -874,6 +902,16 @@ int b200em_norm_bwd_apply(const void* g, int64_t g_ld, const void* x, int64_t x_
                 (const T*)g, g_ld, (const T*)x, x_ld, coef, (const T*)add, add_ld, (T*)out, out_ld, S, C, relu_mask, total);
         }
     })
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_split_bf16(const float* x, int64_t x_ld, const float* in_scale_shift, void* hi, void* lo, int N, int64_t S, int C,
+                      void* stream) {
+    B2_CHECK_ARG(x && hi && lo && N > 0 && S > 0 && C > 0 && N <= 65535, "split_bf16: bad arguments");
+    B2_CHECK_ARG(C % 4 == 0 && x_ld % 4 == 0 && aligned16(x) && aligned16(hi) && aligned16(lo), "split_bf16: needs C % 4 == 0 and 16-byte aligned tensors");
+    split_bf16_kernel<<<dim3(flat_grid(S * (C / 4), 256, N), N), 256, 0, (cudaStream_t)stream>>>(x, x_ld, in_scale_shift, (__nv_bfloat16*)hi,
+                                                                                                (__nv_bfloat16*)lo, S, C);
     B2_LAUNCH_CHECK();
     return 0;
 }

@@ -404,10 +404,17 @@ class FlatGrads(dict):
         total = sum(p.numel() for p in P.values())
         dev = next(iter(P.values())).device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.offsets = {}
         off = 0
         for k, p in P.items():
             dict.__setitem__(self, k, self.flat[off:off + p.numel()].view(p.shape))
+            self.offsets[k] = (off, off + p.numel())
             off += p.numel()
+
+    def range_of(self, prefix):
+        """[lo, hi) of the parameters whose key starts with ``prefix`` (contiguous: state-dict order groups a block's tensors)."""
+        r = [v for k, v in self.offsets.items() if k.startswith(prefix)]
+        return (min(a for a, _ in r), max(b for _, b in r)) if r else None
 
     def __setitem__(self, k, v):
         self[k].copy_(v.reshape(self[k].shape))
@@ -416,12 +423,19 @@ class FlatGrads(dict):
         return self[k]
 
 
-def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_preds, packs):
+def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_preds, packs, sync=None):
     """grad_preds: list aligned with the predictions forward_pass returned (entries may be None for unused side outputs).
-    Returns {state-dict key: fp32 gradient} (a FlatGrads) for every parameter."""
+    Returns {state-dict key: fp32 gradient} (a FlatGrads) for every parameter.
+
+    sync (optional, data-parallel training): object with ``begin(flat)``, ``ready(lo, hi)`` and ``finish()``.  ``ready`` is called
+    as soon as a contiguous range of the flat gradient buffer is final, in descending address order -- first everything from the
+    base block to the end (base, decoder, samplers, heads: ~95 % of the parameters, done when the most expensive, shallow encoder
+    levels are still ahead), then one encoder block at a time -- so the gradient exchange overlaps the rest of the backward."""
     m = ctx.misc
     depth = plan.depth
     grads = FlatGrads(P)
+    if sync is not None:
+        sync.begin(grads.flat)
     preds = m["preds"]
     dec_outs = m["dec_outs"]
     dev = dec_outs[-1].device if dec_outs else preds[0].device
@@ -473,6 +487,8 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
         dz = g
     need_first_dx = plan.norm in AFFINE_NORMS          # the first norm's gamma/beta need the gradient w.r.t. its output
     d_p = _block_backward(B, plan, P, plan.base, ctx.blocks["base"], dz, depth > 0 or need_first_dx, grads, packs)
+    if sync is not None:
+        sync.ready(grads.range_of("base.")[0], grads.flat.numel())
     for l in reversed(range(depth)):
         spec = plan.enc[l]
         rec = ctx.blocks[spec.prefix]
@@ -490,4 +506,8 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
             sg = full
         B.maxpool_bwd(skip, d_p, sg, dz, f, 1)
         d_p = _block_backward(B, plan, P, spec, rec, dz, l > 0 or need_first_dx, grads, packs)
+        if sync is not None:
+            sync.ready(*grads.range_of(spec.prefix + "."))
+    if sync is not None:
+        sync.finish()
     return grads

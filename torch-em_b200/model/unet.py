@@ -215,9 +215,11 @@ class _UNetFunction(torch.autograd.Function):
         dev = preds[0].device
         with _device_ctx(dev):
             ctx.packs.refresh_dgrad(bf16=ctx.bf16)
-            grads = engine.backward_pass(B, model._plan, ctx.P, ctx.fctx, grad_preds, ctx.packs)
-            if model.grad_sync is not None:
-                model.grad_sync(grads.flat)      # ONE collective over the flat gradient buffer (distributed.py)
+            sync = model.grad_sync
+            chunked = sync is not None and hasattr(sync, "ready")
+            grads = engine.backward_pass(B, model._plan, ctx.P, ctx.fctx, grad_preds, ctx.packs, sync=sync if chunked else None)
+            if sync is not None and not chunked:
+                sync(grads.flat)                 # plain callable: one collective over the flat gradient buffer at the end
         ctx.fctx = None
         ctx.ran_backward = True
         out = [None, None, None]
