@@ -1,4 +1,4 @@
-"""One profiled train step of the bench workload (use under ncu with --profile-from-start off).
+"""One profiled train step of a bench workload (B200EM_CONFIG=cfg2|cfg3|cfg4, default cfg2) (use under ncu with --profile-from-start off).
 
     ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py
 """
@@ -11,21 +11,25 @@ import torch
 import bench
 import torch_em_b200 as tb
 
-batch = int(os.environ.get("B200EM_BATCH", bench.BATCH))
-patch = tuple(int(v) for v in os.environ.get("B200EM_PATCH", "128,128,128").split(","))
+cfg = bench.CONFIGS[os.environ.get("B200EM_CONFIG", "cfg2")]
+batch = int(os.environ.get("B200EM_BATCH", cfg["batch"]))
+patch = tuple(int(v) for v in os.environ["B200EM_PATCH"].split(",")) if "B200EM_PATCH" in os.environ else cfg["patch"]
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
-model = tb.UNet3d(**bench.MODEL_KW).to(dev)
-loss_fn = tb.DiceLoss()
+model = getattr(tb, cfg["model"])(**cfg["model_kw"]).to(dev)
+loss_fn = tb.AffinityLoss(bench.CREMI_OFFSETS, ignore_label=0) if cfg["loss"] == "affinity" else tb.DiceLoss()
+boundary = tb.BoundaryTransform(add_binary_target=True) if cfg["loss"] == "boundary" else None
 opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
-x, t = bench.synthetic_batch(batch, patch, 1)
+x, t = bench.synthetic_batch(batch, patch, 1, cfg["loss"], cfg["model_kw"]["out_channels"])
 x, t = x.to(dev), t.to(dev)
+bf16 = cfg["dtype"] == "bf16"
 
 
 def step():
     opt.zero_grad()
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        loss = loss_fn(model(x), t)
+    tt = boundary(t) if boundary is not None else t
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+        loss = loss_fn(model(x), tt)
     loss.backward()
     opt.step()
     return loss

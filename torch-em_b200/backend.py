@@ -427,16 +427,22 @@ class CudaBackend:
                 "b200em_conv3d_wgrad_umma", xp, xld, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cin, Cout, kd, kh,
                 kw, _stream(x)))
             return
-        if self.tf32_enabled() and x.dtype == torch.float32 and xld % 4 == 0 and zld % 4 == 0 and x.data_ptr() % 16 == 0 and \
-                dz.data_ptr() % 16 == 0 and Cin % 8 == 0 and Cout % 8 == 0 and \
-                _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw):
+        first_f32 = Cin == 1 and xld == 1 and self.use_ds and _lib.load().b200em_conv3d_first_supported(Cin, Cout, kd, kh, kw)
+        if self.tf32_enabled() and x.dtype == torch.float32 and zld % 4 == 0 and dz.data_ptr() % 16 == 0 and Cout % 8 == 0 and \
+                (first_f32 or (xld % 4 == 0 and x.data_ptr() % 16 == 0 and Cin % 8 == 0 and
+                               _lib.load().b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw))):
             # fp32 activations, TF32 allowed: the bf16 tensor-core weight-gradient kernels on split operands -- x_hat = hi + lo,
             # dz = hi + lo, dW = hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-16 relative; more accurate than TF32's 10
             # mantissa bits, at three bf16 passes)
             S = D * H * W
             xh = torch.empty((2, N, D, H, W, Cin), dtype=torch.bfloat16, device=x.device)
             zh = torch.empty((2, N, D, H, W, Cout), dtype=torch.bfloat16, device=x.device)
-            call("b200em_split_bf16", xp, xld, _f32(in_ss), _ptr(xh[0]), _ptr(xh[1]), N, S, Cin, _stream(x))
+            if first_f32:                                 # the 1-channel network input: a tiny tensor, split with torch ops
+                xa = x.float() if in_ss is None else x * in_ss[:, 0, 0].reshape(N, 1, 1, 1, 1) + in_ss[:, 0, 1].reshape(N, 1, 1, 1, 1)
+                xh[0].copy_(xa)
+                xh[1].copy_(xa - xh[0].float())
+            else:
+                call("b200em_split_bf16", xp, xld, _f32(in_ss), _ptr(xh[0]), _ptr(xh[1]), N, S, Cin, _stream(x))
             call("b200em_split_bf16", zp, zld, None, _ptr(zh[0]), _ptr(zh[1]), N, S, Cout, _stream(x))
 
             def three_passes():
