@@ -197,17 +197,22 @@ int b200em_split_bf16(const float* x, int64_t x_ld, const float* in_scale_shift,
 /* (D,H,W) are the INPUT dims; sums (nullable) [N][C][2] += stats of the pooled output. */
 int b200em_maxpool3d_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int dtype, int N, int D, int H, int W,
                          int C, int fd, int fh, int fw, float* sums, void* stream);
-/* out[hi] = ((hi is the first max of its window ? dp[window] : 0) [+ add[hi]]) * (relu_mask ? x[hi] > 0 : 1) */
+/* out[hi] = ((hi is the first max of its window ? dp[window] : 0) [+ a[hi]]) * (relu_mask ? x[hi] > 0 : 1), where
+ * a = add, or with coef (nullable; (c0,c1,c2) per (n,c), sample stride coef_nstride floats) a = c0*add + c1*x + c2: the norm
+ * backward of the consuming decoder block applied on the fly to its raw data gradient, so the skip gradient is never stored. */
 int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp_ld, const void* add, int64_t add_ld,
-                         void* out, int64_t out_ld, int dtype, int N, int D, int H, int W, int C,
-                         int fd, int fh, int fw, int relu_mask, void* stream);
+                         const float* coef, int64_t coef_nstride, void* out, int64_t out_ld, int dtype, int N, int D, int H, int W,
+                         int C, int fd, int fh, int fw, int relu_mask, void* stream);
 
 /* ---- F.interpolate(mode="trilinear", align_corners=False), integer scale (unet.py:456) --------------------- */
 /* (D,H,W) are the LOW-resolution dims. */
 int b200em_upsample_trilinear_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int dtype, int N, int D, int H,
                                   int W, int C, int fd, int fh, int fw, float* sums, void* stream);
-int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int dtype, int N, int D,
-                                  int H, int W, int C, int fd, int fh, int fw, void* stream);
+/* dx = transpose of the interpolation applied to dy, or with coef (nullable, as above) to c0*dy + c1*xcat + c2, xcat being the
+ * up-sampled tensor itself (the first half of the decoder block's input): the block's norm backward fused into the tile load. */
+int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, const void* xcat, int64_t xcat_ld, const float* coef,
+                                  int64_t coef_nstride, void* dx, int64_t dx_ld, int dtype, int N, int D, int H, int W, int C,
+                                  int fd, int fh, int fw, void* stream);
 
 /* ---- out_conv (1x1x1) + final activation (unet.py:202-205, 638, 162-172) ---------------------------------- */
 /* x NDHWC (Cin) -> out NCDHW fp32 (Cout): out = act(W x + b); w is (Cout,Cin) fp32 = the torch weight. */

@@ -119,7 +119,9 @@ class TorchEmuBackend:
         if sums is not None:
             self.channel_sums(y, sums)
 
-    def maxpool_bwd(self, x, dp, add, out, f, relu_mask):
+    def maxpool_bwd(self, x, dp, add, out, f, relu_mask, coef=None):
+        if coef is not None:
+            add = _bcast(coef[..., 0]) * add.float() + _bcast(coef[..., 1]) * x.float() + _bcast(coef[..., 2])
         with torch.enable_grad():
             xf = _ncdhw(x.float()).detach().clone().requires_grad_(True)
             r = F.max_pool3d(xf, kernel_size=list(f), stride=list(f))
@@ -137,7 +139,12 @@ class TorchEmuBackend:
         if sums is not None:
             self.channel_sums(y, sums)
 
-    def upsample_bwd(self, dy, dx, f):
+    def fused_up_bwd_ok(self, dy, f):
+        return True
+
+    def upsample_bwd(self, dy, dx, f, xcat=None, coef=None):
+        if coef is not None:
+            dy = _bcast(coef[..., 0]) * dy.float() + _bcast(coef[..., 1]) * xcat.float() + _bcast(coef[..., 2])
         with torch.enable_grad():
             z = torch.zeros(_ncdhw(dx).shape, dtype=torch.float32, requires_grad=True)
             r = F.interpolate(z, scale_factor=[float(s) for s in f], mode="trilinear", align_corners=False)

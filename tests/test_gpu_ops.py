@@ -173,6 +173,41 @@ def test_pool_and_upsample(B, dtype, f, C):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("f,shape", [((2, 2, 2), (2, 5, 9, 11)), ((1, 2, 2), (1, 3, 18, 9)), ((2, 2, 2), (1, 1, 1, 1))])
+@pytest.mark.parametrize("C", [16, 40])
+def test_fused_norm_backward_in_pool_and_upsample_backward(B, dtype, f, shape, C):
+    """The decoder block's first norm backward (d = c0 * g + c1 * x + c2 per (n, c)) applied on the fly by the tiled up-sampling
+    backward and by the max-pool backward, on channel SLICES of a 2C-wide concat buffer, vs the materialised form.  Odd tile
+    counts and a single-voxel volume exercise the clamped tile borders."""
+    N, D, H, W = shape
+    Dh, Hh, Wh = D * f[0], H * f[1], W * f[2]
+    g_cat = act((N, Dh, Hh, Wh, 2 * C), dtype, 21)
+    cat = act((N, Dh, Hh, Wh, 2 * C), dtype, 22, relu=True)
+    coef = torch.stack([1 + 0.2 * act((N, 2 * C), torch.float32, 23), 0.3 * act((N, 2 * C), torch.float32, 24),
+                        0.1 * act((N, 2 * C), torch.float32, 25)], -1).contiguous()
+    t = tol(dtype) if dtype == torch.float32 else dict(rtol=2e-2, atol=6e-2)
+    # up-sampling backward of the first C channels
+    dz_ref = torch.empty((N, D, H, W, C), dtype=dtype)
+    EMU.upsample_bwd(g_cat[..., :C], dz_ref, f, xcat=cat[..., :C], coef=coef[:, :C])
+    gd, cd, kd = g_cat.to(DEV), cat.to(DEV), coef.to(DEV)
+    assert B.fused_up_bwd_ok(gd[..., :C], f)
+    dz = torch.empty((N, D, H, W, C), dtype=dtype, device=DEV)
+    B.upsample_bwd(gd[..., :C], dz, f, xcat=cd[..., :C], coef=kd[:, :C])
+    close(dz, dz_ref, **t)
+    dz2_ref = torch.empty((N, D, H, W, C), dtype=dtype)
+    EMU.upsample_bwd(g_cat[..., :C], dz2_ref, f)
+    B.upsample_bwd(gd[..., :C], dz, f)                      # the tiled kernel without the fused transform
+    close(dz, dz2_ref, **t)
+    # max-pool backward of the skip half: pooled gradient + (c0 * g + c1 * skip + c2), ReLU mask of the skip
+    dp = act((N, D, H, W, C), dtype, 26)
+    o_ref = torch.empty((N, Dh, Hh, Wh, C), dtype=dtype)
+    EMU.maxpool_bwd(cat[..., C:], dp, g_cat[..., C:], o_ref, f, 1, coef=coef[:, C:])
+    o = torch.empty((N, Dh, Hh, Wh, C), dtype=dtype, device=DEV)
+    B.maxpool_bwd(cd[..., C:], dp.to(DEV), gd[..., C:], o, f, 1, coef=kd[:, C:])
+    close(o, o_ref, **t)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("act_name", [None, "Sigmoid", "ReLU", "Tanh"])
 @pytest.mark.parametrize("Cin,Cout", [(16, 2), (5, 3), (32, 12)])
 def test_head(B, dtype, act_name, Cin, Cout):

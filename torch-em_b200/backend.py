@@ -472,31 +472,53 @@ class CudaBackend:
     # ---- pool / upsample -------------------------------------------------------------------------------------
     def maxpool_fwd(self, x, y, f, sums):
         N, D, H, W, C = x.shape
+        assert tuple(y.shape[1:4]) == (D // f[0], H // f[1], W // f[2]), "maxpool_fwd: y must be x's shape floor-divided by the factors"
         xp, xld = _act(x)
         yp, yld = _act(y)
         call("b200em_maxpool3d_fwd", xp, xld, yp, yld, _dt(x), N, D, H, W, C, f[0], f[1], f[2], _f32(sums), _stream(x))
 
-    def maxpool_bwd(self, x, dp, add, out, f, relu_mask):
+    @staticmethod
+    def _coef(coef, C):
+        """(pointer, sample stride) of an (N, C, 3) fp32 coefficient view that may be a channel slice of a wider tensor."""
+        if coef is None:
+            return None, 0
+        assert coef.dtype == torch.float32 and coef.shape[1] == C and coef.shape[2] == 3 and coef.stride(2) == 1 and coef.stride(1) == 3
+        return _ptr(coef), coef.stride(0)
+
+    def maxpool_bwd(self, x, dp, add, out, f, relu_mask, coef=None):
+        """coef (N, C, 3): the added term is c0 * add + c1 * x + c2 (the consuming block's norm backward, fused)."""
         N, D, H, W, C = x.shape
         xp, xld = _act(x)
         dpp, dpld = _act(dp)
         ap, ald = _act(add) if add is not None else (None, 0)
         op, old = _act(out)
-        call("b200em_maxpool3d_bwd", xp, xld, dpp, dpld, ap, ald, op, old, _dt(x), N, D, H, W, C, f[0], f[1], f[2],
+        cp, cns = self._coef(coef, C)
+        call("b200em_maxpool3d_bwd", xp, xld, dpp, dpld, ap, ald, cp, cns, op, old, _dt(x), N, D, H, W, C, f[0], f[1], f[2],
              int(relu_mask), _stream(x))
 
     def upsample_fwd(self, x, y, f, sums):
         N, D, H, W, C = x.shape
+        assert tuple(y.shape[1:4]) == (D * f[0], H * f[1], W * f[2]), "upsample_fwd: y must be x's shape times the factors"
         xp, xld = _act(x)
         yp, yld = _act(y)
         call("b200em_upsample_trilinear_fwd", xp, xld, yp, yld, _dt(x), N, D, H, W, C, f[0], f[1], f[2], _f32(sums),
              _stream(x))
 
-    def upsample_bwd(self, dy, dx, f):
+    def fused_up_bwd_ok(self, dy, f):
+        """Whether upsample_bwd can apply the norm backward on the fly (tiled kernel: factors (1|2, 2, 2), 16-byte channel vectors)."""
+        vec = 8 if dy.dtype == torch.bfloat16 else 4
+        return f[0] <= 2 and f[1] == 2 and f[2] == 2 and dy.shape[4] % vec == 0 and dy.stride(3) % vec == 0 and dy.data_ptr() % 16 == 0
+
+    def upsample_bwd(self, dy, dx, f, xcat=None, coef=None):
+        """coef (N, C, 3) + xcat (the up-sampled tensor): the gradient that is transposed-interpolated is c0 * dy + c1 * xcat + c2."""
         N, D, H, W, C = dx.shape
+        assert tuple(dy.shape[1:4]) == (D * f[0], H * f[1], W * f[2]), "upsample_bwd: dy must be dx's shape times the factors"
         yp, yld = _act(dy)
         xp, xld = _act(dx)
-        call("b200em_upsample_trilinear_bwd", yp, yld, xp, xld, _dt(dx), N, D, H, W, C, f[0], f[1], f[2], _stream(dx))
+        cp, cns = self._coef(coef, C)
+        catp, catld = _act(xcat) if coef is not None else (None, 0)
+        call("b200em_upsample_trilinear_bwd", yp, yld, catp, catld, cp, cns, xp, xld, _dt(dx), N, D, H, W, C, f[0], f[1], f[2],
+             _stream(dx))
 
     # ---- head ------------------------------------------------------------------------------------------------
     def head_fwd(self, x, w, b, out, act):

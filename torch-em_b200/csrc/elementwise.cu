@@ -301,9 +301,13 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __r
 
 // max pool backward: one thread per (window, channel vector); first maximum in (d,h,w) scan order wins
 // (ATen max_pool3d_with_indices semantics).
+// coef (nullable, per (n, c): c0, c1, c2 with sample stride coef_nstride): the term added to every voxel is then
+// c0 * add + c1 * x + c2 -- the norm backward of the consuming decoder block applied to its raw data gradient `add` -- instead of
+// `add` itself, so the skip gradient is never materialised.
 template <typename T, int VEC>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const T* __restrict__ dp, int64_t dp_ld,
-                                   const T* __restrict__ add, int64_t add_ld, T* __restrict__ out, int64_t out_ld,
+                                   const T* __restrict__ add, int64_t add_ld, const float* __restrict__ coef, int64_t coef_nstride,
+                                   T* __restrict__ out, int64_t out_ld,
                                    int D, int H, int W, int C, int fd, int fh, int fw, int relu_mask, int64_t total) {
     const unsigned cvec = C / VEC;
     const int Do = D / fd, Ho = H / fh, Wo = W / fw;
@@ -337,8 +341,13 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const 
                 for (int c = 0; c < fw; ++c, ++pos) {
                     int64_t vi = n * Si + ((int64_t)(d_o * fd + a) * H + (ho * fh + b)) * W + (wo * fw + c);
                     float r[VEC], t[VEC], va[VEC];
-                    if (relu_mask) Vec<T, VEC>::load(x + vi * x_ld + cv * VEC, t);
+                    if (relu_mask || coef) Vec<T, VEC>::load(x + vi * x_ld + cv * VEC, t);
                     if (add) Vec<T, VEC>::load(add + vi * add_ld + cv * VEC, va);
+                    if (coef) {
+                        const float* cf = coef + n * coef_nstride + (size_t)cv * VEC * 3;
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) va[v] = fmaf(cf[3 * v], va[v], fmaf(cf[3 * v + 1], t[v], cf[3 * v + 2]));
+                    }
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         float q = (arg[v] == pos) ? gp[v] : 0.f;
@@ -776,6 +785,83 @@ upsample2_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, T* __restrict__ dx
     }
 }
 
+// Backward of the x2 up-sampling through a shared-memory tile, with the norm backward of the consuming block optionally fused
+// into the tile load:  dy_eff = coef ? c0 * dy + c1 * xcat + c2 : dy  (per (n, c) coefficients; xcat = the block's input, i.e. the
+// up-sampled tensor itself), then dx[i] = sum over the 4 (per axis) outputs around i with the clamped uniform weights
+// (.25, .75, .75, .25) -- clamping the output index reproduces the edge weights (1 instead of .75) exactly.
+// CTA = (LD x LH x 8) low-res voxels x 4 channel vectors; the (2LD+2) x (2LH+2) x 18 high-res tile is read ONCE from global
+// memory (the direct form read every value 8 times through L1), transformed, and kept in shared memory as T.
+template <typename T, int VEC, int FD>
+__global__ void __launch_bounds__(256)
+upsample2_bwd_tile_kernel(const T* __restrict__ dy, int64_t dy_ld, const T* __restrict__ xc, int64_t xc_ld,
+                          const float* __restrict__ coef, int64_t coef_nstride, T* __restrict__ dx, int64_t dx_ld, int D, int H, int W,
+                          int C, int tiles_h, int tiles_w) {
+    extern __shared__ __align__(16) uint8_t up_smem[];
+    constexpr int LD = FD == 2 ? 2 : 1, LH = FD == 2 ? 4 : 8, LW = 8, CV = 4;
+    constexpr int HD = FD == 2 ? 2 * LD + 2 : 1, HH = 2 * LH + 2, HW = 2 * LW + 2;
+    uint4* tile = reinterpret_cast<uint4*>(up_smem);                 // [HD][HH][HW][CV] 16-byte units
+    const int n = blockIdx.z;
+    const int cv0 = blockIdx.y * CV;                                 // first channel vector of this CTA
+    const int cvec = C / VEC;
+    int tb = blockIdx.x;
+    const int w0 = (tb % tiles_w) * LW; tb /= tiles_w;
+    const int h0 = (tb % tiles_h) * LH; tb /= tiles_h;
+    const int d0 = tb * LD;
+    const int Do = D * FD, Ho = H * 2, Wo = W * 2;
+    const T* gn = dy + (size_t)n * Do * Ho * Wo * dy_ld;
+    const T* xn = xc ? xc + (size_t)n * Do * Ho * Wo * xc_ld : nullptr;
+    // ---- load + transform: high-res voxel (od, oh, ow) = tile origin - 1 + local index, clamped into the volume
+    for (int u = threadIdx.x; u < HD * HH * HW * CV; u += 256) {
+        const int c = u % CV, lw = (u / CV) % HW, lh = (u / (CV * HW)) % HH, ld = u / (CV * HW * HH);
+        const int cv = cv0 + c;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (cv < cvec) {
+            const int od = FD == 2 ? min(max(2 * d0 - 1 + ld, 0), Do - 1) : d0;
+            const int oh = min(max(2 * h0 - 1 + lh, 0), Ho - 1), ow = min(max(2 * w0 - 1 + lw, 0), Wo - 1);
+            const size_t vox = ((size_t)od * Ho + oh) * Wo + ow;
+            float v[VEC];
+            Vec<T, VEC>::load(gn + vox * dy_ld + cv * VEC, v);
+            if (coef) {
+                float xv[VEC];
+                Vec<T, VEC>::load(xn + vox * xc_ld + cv * VEC, xv);
+                const float* cf = coef + (size_t)n * coef_nstride + (size_t)cv * VEC * 3;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) v[k] = fmaf(cf[3 * k], v[k], fmaf(cf[3 * k + 1], xv[k], cf[3 * k + 2]));
+            }
+            Vec<T, VEC>::store(reinterpret_cast<T*>(&val), v);
+        }
+        tile[u] = val;
+    }
+    __syncthreads();
+    // ---- gather: thread = (low-res voxel of the tile, channel vector)
+    const int c = threadIdx.x % CV, lv = threadIdx.x / CV;           // 64 voxels x 4 vectors
+    const int lw = lv % LW, lh = (lv / LW) % LH, ld = lv / (LW * LH);
+    const int w = w0 + lw, h = h0 + lh, d = d0 + ld, cv = cv0 + c;
+    if (w >= W || h >= H || d >= D || cv >= cvec) return;
+    float r[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) r[k] = 0.f;
+    constexpr float WT[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+#pragma unroll
+    for (int kd = 0; kd < (FD == 2 ? 4 : 1); ++kd) {
+#pragma unroll
+        for (int kh = 0; kh < 4; ++kh) {
+            const float wdh = (FD == 2 ? WT[kd] : 1.f) * WT[kh];
+            const uint4* row = tile + (((FD == 2 ? 2 * ld + kd : 0) * HH + 2 * lh + kh) * HW + 2 * lw) * CV + c;
+#pragma unroll
+            for (int kw = 0; kw < 4; ++kw) {
+                float t[VEC];
+                const uint4 q = row[kw * CV];
+                Vec<T, VEC>::load(reinterpret_cast<const T*>(&q), t);
+                const float wt = wdh * WT[kw];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) r[k] = fmaf(wt, t[k], r[k]);
+            }
+        }
+    }
+    Vec<T, VEC>::store(dx + ((size_t)n * D * H * W + ((size_t)d * H + h) * W + w) * dx_ld + cv * VEC, r);
+}
+
 static inline int flat_grid(int64_t total, int threads, int N = 1) {
     int64_t b = (total + threads - 1) / threads;
     int64_t cap = (int64_t)sm_count() * 16 / (N > 0 ? N : 1) + 1;
@@ -942,9 +1028,10 @@ int b200em_maxpool3d_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int
 }
 
 int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp_ld, const void* add, int64_t add_ld,
-                         void* out, int64_t out_ld, int dtype, int N, int D, int H, int W, int C, int fd, int fh, int fw,
-                         int relu_mask, void* stream) {
+                         const float* coef, int64_t coef_nstride, void* out, int64_t out_ld, int dtype, int N, int D, int H, int W,
+                         int C, int fd, int fh, int fw, int relu_mask, void* stream) {
     B2_CHECK_ARG(x && dp && out && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "maxpool3d_bwd: bad arguments");
+    B2_CHECK_ARG(!coef || add, "maxpool3d_bwd: coef needs the raw gradient in `add`");
     // voxels beyond the last full window are NOT written (the caller initialises them: they receive no pooled gradient)
     B2_CHECK_ARG(D >= fd && H >= fh && W >= fw, "maxpool3d_bwd: dims smaller than the window");
     B2_CHECK_ARG((int64_t)D * H * W * C < (1LL << 31) && N <= 65535, "maxpool3d_bwd: sample too large for 32-bit indexing");
@@ -954,11 +1041,13 @@ int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp
         if (can_vec<T>(C, {x_ld, dp_ld, add ? add_ld : (int64_t)V, out_ld}, {x, dp, add, out})) {
             int64_t total = So * (C / V);
             maxpool_bwd_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
-                (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, (T*)out, out_ld, D, H, W, C, fd, fh, fw, relu_mask, total);
+                (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, coef, coef_nstride, (T*)out, out_ld, D, H, W, C, fd, fh, fw,
+                relu_mask, total);
         } else {
             int64_t total = So * C;
             maxpool_bwd_kernel<T, 1><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
-                (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, (T*)out, out_ld, D, H, W, C, fd, fh, fw, relu_mask, total);
+                (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, coef, coef_nstride, (T*)out, out_ld, D, H, W, C, fd, fh, fw,
+                relu_mask, total);
         }
     })
     B2_LAUNCH_CHECK();
@@ -1004,15 +1093,34 @@ int b200em_upsample_trilinear_fwd(const void* x, int64_t x_ld, void* y, int64_t 
     return 0;
 }
 
-int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld, int dtype, int N, int D, int H,
+int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, const void* xcat, int64_t xcat_ld, const float* coef,
+                                  int64_t coef_nstride, void* dx, int64_t dx_ld, int dtype, int N, int D, int H,
                                   int W, int C, int fd, int fh, int fw, void* stream) {
     B2_CHECK_ARG(dy && dx && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "upsample_bwd: bad arguments");
+    B2_CHECK_ARG(!coef || xcat, "upsample_bwd: coef needs xcat");
     int64_t Si = (int64_t)D * H * W;
     B2_CHECK_ARG(Si * fd * fh * fw * C < (1LL << 31) && N <= 65535, "upsample_bwd: sample too large for 32-bit indexing");
     B2_DISPATCH_DTYPE(dtype, T, {
         constexpr int V = FullVec<T>::value;
         const int cvec_ = C / V;
-        if (can_vec<T>(C, {dy_ld, dx_ld}, {dy, dx}) && cvec_ <= 256 && 256 % cvec_ == 0 && fd <= 2 && fh == 2 && fw == 2) {
+        if (can_vec<T>(C, {dy_ld, dx_ld, coef ? xcat_ld : (int64_t)V}, {dy, dx, coef ? xcat : nullptr}) && fd <= 2 && fh == 2 && fw == 2) {
+            // tiled kernel: the high-res tile goes through shared memory once, the norm backward is applied on the way in
+            const int LDt = fd == 2 ? 2 : 1, LHt = fd == 2 ? 4 : 8;
+            const int th = (H + LHt - 1) / LHt, tw = (W + 7) / 8, td = (D + LDt - 1) / LDt;
+            dim3 grid((unsigned)(td * th * tw), (unsigned)((cvec_ + 3) / 4), (unsigned)N);
+            const int smem = (fd == 2 ? (2 * LDt + 2) : 1) * (2 * LHt + 2) * 18 * 4 * 16;
+            if (fd == 2) {
+                B2_CUDA(cudaFuncSetAttribute(upsample2_bwd_tile_kernel<T, V, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                upsample2_bwd_tile_kernel<T, V, 2><<<grid, 256, smem, (cudaStream_t)stream>>>(
+                    (const T*)dy, dy_ld, (const T*)xcat, xcat_ld, coef, coef_nstride, (T*)dx, dx_ld, D, H, W, C, th, tw);
+            } else {
+                upsample2_bwd_tile_kernel<T, V, 1><<<grid, 256, smem, (cudaStream_t)stream>>>(
+                    (const T*)dy, dy_ld, (const T*)xcat, xcat_ld, coef, coef_nstride, (T*)dx, dx_ld, D, H, W, C, th, tw);
+            }
+        } else if (coef) {
+            set_error("upsample_bwd: the fused norm backward needs 16-byte aligned channel vectors and factors (1|2, 2, 2)");
+            return 2;
+        } else if (can_vec<T>(C, {dy_ld, dx_ld}, {dy, dx}) && cvec_ <= 256 && 256 % cvec_ == 0 && fd <= 2 && fh == 2 && fw == 2) {
             const int th = (H + UP_BH - 1) / UP_BH, tw = (W + UP_BW - 1) / UP_BW, td = (D + UP_BD - 1) / UP_BD;
             dim3 grid((unsigned)(td * th * tw), 1, (unsigned)N);
             if (fd == 2)

@@ -355,9 +355,12 @@ def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act
     return preds, ctx
 
 
-def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs):
+def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs, lazy_dx=False):
     """dz2 = gradient w.r.t. the PRE-ReLU output of conv2 (i.e. already multiplied by [y2 > 0]).
-    Returns the gradient w.r.t. the block input (before any mask of the producer), or None."""
+    Returns the gradient w.r.t. the block input (before any mask of the producer), or None.
+    lazy_dx: return ``(g, coef)`` instead -- the raw data gradient of conv1 and the norm-backward coefficients with
+    d(input) = c0 * g + c1 * x_in + c2 -- so that the consumers (up-sampling backward, max-pool backward) apply the first norm's
+    backward on the fly and the block-input gradient is never written (coef is None without a norm: d(input) = g)."""
     norm = plan.norm
     c1, c2 = spec.conv1, spec.conv2
     x_in, y1 = rec["x_in"], rec["y1"]
@@ -366,13 +369,15 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
     dev = y1.device
     f32 = dict(dtype=torch.float32, device=dev)
 
-    def dgrad_and_norm_back(dz, conv, x, mr, mode, norm_key, out, relu_mask):
+    def dgrad_and_norm_back(dz, conv, x, mr, mode, norm_key, out, relu_mask, lazy=False):
         """g = dgrad(dz) (gradient w.r.t. the norm OUTPUT), then the norm backward (+ the producer's ReLU mask) -> out.
         The two norm-backward reductions (sum g, sum g*x) come out of the dgrad kernel's epilogue."""
         C = conv.cin
         g = torch.empty(x.shape, dtype=x.dtype, device=dev)
         if norm is None:
             B.conv(dz, None, packs[conv.key], None, g, None, conv.kernel, relu=False, dgrad=True)
+            if lazy:
+                return g, None
             if out is None:
                 return g
             B.norm_bwd_apply(g, x, None, None, out, relu_mask)
@@ -380,6 +385,8 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
         dsums = torch.zeros((N, C, 2), **f32)
         B.conv(dz, None, packs[conv.key], None, g, dsums, conv.kernel, relu=False, dgrad=True, dot_x=x)
         coef = _norm_backward_coef(B, plan, P, norm_key, dsums, mr, mode, S, C, grads)
+        if lazy:
+            return g, coef
         if out is None:
             out = torch.empty_like(g)
         B.norm_bwd_apply(g, x, coef, None, out, relu_mask)
@@ -392,7 +399,7 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
     B.wgrad(x_in, rec["ss1"], dz1, grads[c1.key + ".weight"], grads[c1.key + ".bias"], c1.kernel, aux=rec.get("aux1"))
     if not need_dx:
         return None
-    return dgrad_and_norm_back(dz1, c1, x_in, rec["mr1"], rec["m1"], spec.norm1_key, None, relu_mask=0)
+    return dgrad_and_norm_back(dz1, c1, x_in, rec["mr1"], rec["m1"], spec.norm1_key, None, relu_mask=0, lazy=lazy_dx)
 
 
 class FlatGrads(dict):
@@ -472,11 +479,23 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
         lvl = depth - 1 - i
         spec, samp = plan.dec[i], plan.samplers[i]
         C = samp.cout
-        d_cat = _block_backward(B, plan, P, spec, ctx.blocks[spec.prefix], dz, True, grads, packs)
-        skip_grads[lvl] = d_cat[..., C:]
+        rec = ctx.blocks[spec.prefix]
+        cat = rec["x_in"]
+        f = plan.scale_factors[lvl]
         x_low, zshape = m["sampler_in"][i]
         d_zlow = torch.empty(zshape, dtype=x_low.dtype, device=dev)
-        B.upsample_bwd(d_cat[..., :C], d_zlow, plan.scale_factors[lvl])
+        # The gradient w.r.t. the concat buffer is consumed twice -- [..., :C] by the up-sampling backward, [..., C:] (the skip)
+        # by the max-pool backward of the encoder -- and both kernels can apply the block's first norm backward while they load:
+        # d_cat = c0 * g + c1 * cat + c2 is then never written.  (Cropped skips, odd factors: materialise it as before.)
+        lazy = B.fused_up_bwd_ok(cat[..., :C], f) and m["enc_dims"][lvl] == m["dec_dims"][lvl]
+        if lazy:
+            g_cat, coef = _block_backward(B, plan, P, spec, rec, dz, True, grads, packs, lazy_dx=True)
+            skip_grads[lvl] = (g_cat[..., C:], None if coef is None else coef[:, C:])
+            B.upsample_bwd(g_cat[..., :C], d_zlow, f, xcat=cat[..., :C], coef=None if coef is None else coef[:, :C])
+        else:
+            d_cat = _block_backward(B, plan, P, spec, rec, dz, True, grads, packs)
+            skip_grads[lvl] = (d_cat[..., C:], None)
+            B.upsample_bwd(d_cat[..., :C], d_zlow, f)
         B.wgrad(x_low, None, d_zlow, grads[samp.key + ".weight"], grads[samp.key + ".bias"], samp.kernel)
         g = torch.empty_like(x_low)
         B.conv(d_zlow, None, packs[samp.key], None, g, None, samp.kernel, relu=False, dgrad=True)
@@ -495,7 +514,7 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
         skip = rec["y2"]
         dz = torch.empty(skip.shape, dtype=skip.dtype, device=dev)
         f = plan.scale_factors[l]
-        sg = skip_grads[l]
+        sg, sg_coef = skip_grads[l]
         dims, ddims = m["enc_dims"][l], m["dec_dims"][l]
         if ddims != dims:
             # check_shape=False with a non-divisible shape: the skip was centre-cropped (Decoder._crop), so its gradient is
@@ -504,7 +523,7 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
             full[(slice(None),) + _crop_slices(dims, ddims)] = sg
             B.norm_bwd_apply(full, skip, None, None, dz, 1)
             sg = full
-        B.maxpool_bwd(skip, d_p, sg, dz, f, 1)
+        B.maxpool_bwd(skip, d_p, sg, dz, f, 1, coef=sg_coef)
         d_p = _block_backward(B, plan, P, spec, rec, dz, l > 0 or need_first_dx, grads, packs)
         if sync is not None:
             sync.ready(*grads.range_of(spec.prefix + "."))
