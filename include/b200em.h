@@ -208,9 +208,11 @@ int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp
 /* (D,H,W) are the LOW-resolution dims. */
 int b200em_upsample_trilinear_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int dtype, int N, int D, int H,
                                   int W, int C, int fd, int fh, int fw, float* sums, void* stream);
-/* dx = transpose of the interpolation applied to dy, or with coef (nullable, as above) to c0*dy + c1*xcat + c2, xcat being the
- * up-sampled tensor itself (the first half of the decoder block's input): the block's norm backward fused into the tile load. */
-int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, const void* xcat, int64_t xcat_ld, const float* coef,
+/* dx = U^T dy (transpose of the interpolation), or with coef (nullable, as above) U^T (c0*dy + c1*up + c2) where up = U zlow is the
+ * up-sampled tensor itself (the first half of the decoder block's input): the block's norm backward fused in.  By linearity this
+ * is c0 U^T dy + c1 (U^T U) zlow + c2 U^T 1 -- a 3-tap-per-axis stencil on the LOW-resolution zlow and a constant -- so the
+ * high-resolution tensor is not read.  zlow: (N, D, H, W, C) with pitch zlow_ld. */
+int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, const void* zlow, int64_t zlow_ld, const float* coef,
                                   int64_t coef_nstride, void* dx, int64_t dx_ld, int dtype, int N, int D, int H, int W, int C,
                                   int fd, int fh, int fw, void* stream);
 

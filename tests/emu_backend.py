@@ -142,9 +142,10 @@ class TorchEmuBackend:
     def fused_up_bwd_ok(self, dy, f):
         return True
 
-    def upsample_bwd(self, dy, dx, f, xcat=None, coef=None):
+    def upsample_bwd(self, dy, dx, f, zlow=None, coef=None):
         if coef is not None:
-            dy = _bcast(coef[..., 0]) * dy.float() + _bcast(coef[..., 1]) * xcat.float() + _bcast(coef[..., 2])
+            up = F.interpolate(_ncdhw(zlow.float()), scale_factor=[float(s) for s in f], mode="trilinear", align_corners=False)
+            dy = _bcast(coef[..., 0]) * dy.float() + _bcast(coef[..., 1]) * up.permute(0, 2, 3, 4, 1) + _bcast(coef[..., 2])
         with torch.enable_grad():
             z = torch.zeros(_ncdhw(dx).shape, dtype=torch.float32, requires_grad=True)
             r = F.interpolate(z, scale_factor=[float(s) for s in f], mode="trilinear", align_corners=False)

@@ -505,19 +505,23 @@ class CudaBackend:
              _stream(x))
 
     def fused_up_bwd_ok(self, dy, f):
-        """Whether upsample_bwd can apply the norm backward on the fly (tiled kernel: factors (1|2, 2, 2), 16-byte channel vectors)."""
+        """Whether upsample_bwd can apply the norm backward on the fly (factors (1|2, 2, 2), 16-byte channel vectors whose count
+        divides 256)."""
         vec = 8 if dy.dtype == torch.bfloat16 else 4
-        return f[0] <= 2 and f[1] == 2 and f[2] == 2 and dy.shape[4] % vec == 0 and dy.stride(3) % vec == 0 and dy.data_ptr() % 16 == 0
+        C = dy.shape[4]
+        return f[0] <= 2 and f[1] == 2 and f[2] == 2 and C % vec == 0 and 256 % (C // vec) == 0 and dy.stride(3) % vec == 0 and \
+            dy.data_ptr() % 16 == 0
 
-    def upsample_bwd(self, dy, dx, f, xcat=None, coef=None):
-        """coef (N, C, 3) + xcat (the up-sampled tensor): the gradient that is transposed-interpolated is c0 * dy + c1 * xcat + c2."""
+    def upsample_bwd(self, dy, dx, f, zlow=None, coef=None):
+        """coef (N, C, 3) + zlow (the tensor that was up-sampled): the gradient that is transposed-interpolated is
+        c0 * dy + c1 * up(zlow) + c2 (the consuming block's norm backward, fused; the up-sampled tensor itself is not read)."""
         N, D, H, W, C = dx.shape
         assert tuple(dy.shape[1:4]) == (D * f[0], H * f[1], W * f[2]), "upsample_bwd: dy must be dx's shape times the factors"
         yp, yld = _act(dy)
         xp, xld = _act(dx)
         cp, cns = self._coef(coef, C)
-        catp, catld = _act(xcat) if coef is not None else (None, 0)
-        call("b200em_upsample_trilinear_bwd", yp, yld, catp, catld, cp, cns, xp, xld, _dt(dx), N, D, H, W, C, f[0], f[1], f[2],
+        zp, zld = _act(zlow) if coef is not None else (None, 0)
+        call("b200em_upsample_trilinear_bwd", yp, yld, zp, zld, cp, cns, xp, xld, _dt(dx), N, D, H, W, C, f[0], f[1], f[2],
              _stream(dx))
 
     # ---- head ------------------------------------------------------------------------------------------------

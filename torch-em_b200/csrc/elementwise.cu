@@ -335,6 +335,12 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const 
                 }
         float gp[VEC];
         Vec<T, VEC>::load(dp + vox * dp_ld + cv * VEC, gp);
+        float cf[VEC][3];
+        if (coef) {
+            const float* q = coef + n * coef_nstride + (size_t)cv * VEC * 3;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { cf[v][0] = q[3 * v]; cf[v][1] = q[3 * v + 1]; cf[v][2] = q[3 * v + 2]; }
+        }
         pos = 0;
         for (int a = 0; a < fd; ++a)
             for (int b = 0; b < fh; ++b)
@@ -344,9 +350,8 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const 
                     if (relu_mask || coef) Vec<T, VEC>::load(x + vi * x_ld + cv * VEC, t);
                     if (add) Vec<T, VEC>::load(add + vi * add_ld + cv * VEC, va);
                     if (coef) {
-                        const float* cf = coef + n * coef_nstride + (size_t)cv * VEC * 3;
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) va[v] = fmaf(cf[3 * v], va[v], fmaf(cf[3 * v + 1], t[v], cf[3 * v + 2]));
+                        for (int v = 0; v < VEC; ++v) va[v] = fmaf(cf[v][0], va[v], fmaf(cf[v][1], t[v], cf[v][2]));
                     }
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
@@ -731,7 +736,8 @@ upsample2_fwd_pair_kernel(const T* __restrict__ x, int64_t x_ld, T* __restrict__
 // a = (i == 0 ? 1 : .75), b = (i == n-1 ? 1 : .75) and the out-of-range taps dropped.  Separable: w, then h, then d.
 template <typename T, int VEC, int FD, int FH, int FW>
 __global__ void __launch_bounds__(256)
-upsample2_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, T* __restrict__ dx, int64_t dx_ld, int D, int H, int W, int C,
+upsample2_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, const T* __restrict__ zlow, int64_t zlow_ld,
+                     const float* __restrict__ coef, int64_t coef_nstride, T* __restrict__ dx, int64_t dx_ld, int D, int H, int W, int C,
                      int tiles_h, int tiles_w) {
     const int cvec = C / VEC;
     const int n = blockIdx.z;
@@ -781,85 +787,49 @@ upsample2_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, T* __restrict__ dx
                 }
             }
         }
+        if (coef) {
+            // Fused norm backward of the consuming block: the gradient that is transposed-interpolated is c0 * dy + c1 * up + c2
+            // with up = U z (the up-sampled tensor itself).  By linearity  U^T (c0 dy + c1 U z + c2) = c0 U^T dy + c1 (U^T U) z +
+            // c2 U^T 1:  U^T 1 = 2 per x2 axis (the four taps always sum to 2, edges included) and U^T U is a 3-tap stencil per
+            // axis on the LOW-resolution z -- so the high-resolution `up` tensor is not read at all.
+            auto uu = [&](int i, int n_, float& cm, float& c0_, float& cp) {        // per-axis coefficients on z[i-1], z[i], z[i+1]
+                const float t0 = tapw(i, n_, 0), t1 = tapw(i, n_, 1), t2 = tapw(i, n_, 2), t3 = tapw(i, n_, 3);
+                cm = t0 * 0.75f + (i > 0 ? t1 * 0.25f : 0.f);
+                c0_ = t0 * 0.25f + t1 * (i > 0 ? 0.75f : 1.f) + t2 * (i < n_ - 1 ? 0.75f : 1.f) + t3 * 0.25f;
+                cp = (i < n_ - 1 ? t2 * 0.25f : 0.f) + t3 * 0.75f;
+            };
+            float ad[3] = {0.f, 1.f, 0.f}, ah[3] = {0.f, 1.f, 0.f}, aw[3] = {0.f, 1.f, 0.f};
+            if (FD == 2) uu(d, D, ad[0], ad[1], ad[2]);
+            if (FH == 2) uu(h, H, ah[0], ah[1], ah[2]);
+            if (FW == 2) uu(w, W, aw[0], aw[1], aw[2]);
+            float sz[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sz[v] = 0.f;
+            const T* zn = zlow + (size_t)n * D * H * W * zlow_ld + cv * VEC;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (ad[a] == 0.f) continue;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    if (ah[b] == 0.f) continue;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (aw[c] == 0.f) continue;
+                        float t[VEC];
+                        Vec<T, VEC>::load(zn + (((size_t)(d + a - 1) * H + (h + b - 1)) * W + (w + c - 1)) * zlow_ld, t);
+                        const float wt = ad[a] * ah[b] * aw[c];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) sz[v] = fmaf(wt, t[v], sz[v]);
+                    }
+                }
+            }
+            const float* cf = coef + (size_t)n * coef_nstride + (size_t)cv * VEC * 3;
+            const float wsum = (FD == 2 ? 2.f : 1.f) * (FH == 2 ? 2.f : 1.f) * (FW == 2 ? 2.f : 1.f);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) r[v] = fmaf(cf[3 * v], r[v], fmaf(cf[3 * v + 1], sz[v], cf[3 * v + 2] * wsum));
+        }
         Vec<T, VEC>::store(xn + (((size_t)d * H + h) * W + w) * dx_ld + cv * VEC, r);
     }
-}
-
-// Backward of the x2 up-sampling through a shared-memory tile, with the norm backward of the consuming block optionally fused
-// into the tile load:  dy_eff = coef ? c0 * dy + c1 * xcat + c2 : dy  (per (n, c) coefficients; xcat = the block's input, i.e. the
-// up-sampled tensor itself), then dx[i] = sum over the 4 (per axis) outputs around i with the clamped uniform weights
-// (.25, .75, .75, .25) -- clamping the output index reproduces the edge weights (1 instead of .75) exactly.
-// CTA = (LD x LH x 8) low-res voxels x 4 channel vectors; the (2LD+2) x (2LH+2) x 18 high-res tile is read ONCE from global
-// memory (the direct form read every value 8 times through L1), transformed, and kept in shared memory as T.
-template <typename T, int VEC, int FD>
-__global__ void __launch_bounds__(256)
-upsample2_bwd_tile_kernel(const T* __restrict__ dy, int64_t dy_ld, const T* __restrict__ xc, int64_t xc_ld,
-                          const float* __restrict__ coef, int64_t coef_nstride, T* __restrict__ dx, int64_t dx_ld, int D, int H, int W,
-                          int C, int tiles_h, int tiles_w) {
-    extern __shared__ __align__(16) uint8_t up_smem[];
-    constexpr int LD = FD == 2 ? 2 : 1, LH = FD == 2 ? 4 : 8, LW = 8, CV = 4;
-    constexpr int HD = FD == 2 ? 2 * LD + 2 : 1, HH = 2 * LH + 2, HW = 2 * LW + 2;
-    uint4* tile = reinterpret_cast<uint4*>(up_smem);                 // [HD][HH][HW][CV] 16-byte units
-    const int n = blockIdx.z;
-    const int cv0 = blockIdx.y * CV;                                 // first channel vector of this CTA
-    const int cvec = C / VEC;
-    int tb = blockIdx.x;
-    const int w0 = (tb % tiles_w) * LW; tb /= tiles_w;
-    const int h0 = (tb % tiles_h) * LH; tb /= tiles_h;
-    const int d0 = tb * LD;
-    const int Do = D * FD, Ho = H * 2, Wo = W * 2;
-    const T* gn = dy + (size_t)n * Do * Ho * Wo * dy_ld;
-    const T* xn = xc ? xc + (size_t)n * Do * Ho * Wo * xc_ld : nullptr;
-    // ---- load + transform: high-res voxel (od, oh, ow) = tile origin - 1 + local index, clamped into the volume
-    for (int u = threadIdx.x; u < HD * HH * HW * CV; u += 256) {
-        const int c = u % CV, lw = (u / CV) % HW, lh = (u / (CV * HW)) % HH, ld = u / (CV * HW * HH);
-        const int cv = cv0 + c;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (cv < cvec) {
-            const int od = FD == 2 ? min(max(2 * d0 - 1 + ld, 0), Do - 1) : d0;
-            const int oh = min(max(2 * h0 - 1 + lh, 0), Ho - 1), ow = min(max(2 * w0 - 1 + lw, 0), Wo - 1);
-            const size_t vox = ((size_t)od * Ho + oh) * Wo + ow;
-            float v[VEC];
-            Vec<T, VEC>::load(gn + vox * dy_ld + cv * VEC, v);
-            if (coef) {
-                float xv[VEC];
-                Vec<T, VEC>::load(xn + vox * xc_ld + cv * VEC, xv);
-                const float* cf = coef + (size_t)n * coef_nstride + (size_t)cv * VEC * 3;
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) v[k] = fmaf(cf[3 * k], v[k], fmaf(cf[3 * k + 1], xv[k], cf[3 * k + 2]));
-            }
-            Vec<T, VEC>::store(reinterpret_cast<T*>(&val), v);
-        }
-        tile[u] = val;
-    }
-    __syncthreads();
-    // ---- gather: thread = (low-res voxel of the tile, channel vector)
-    const int c = threadIdx.x % CV, lv = threadIdx.x / CV;           // 64 voxels x 4 vectors
-    const int lw = lv % LW, lh = (lv / LW) % LH, ld = lv / (LW * LH);
-    const int w = w0 + lw, h = h0 + lh, d = d0 + ld, cv = cv0 + c;
-    if (w >= W || h >= H || d >= D || cv >= cvec) return;
-    float r[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) r[k] = 0.f;
-    constexpr float WT[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-#pragma unroll
-    for (int kd = 0; kd < (FD == 2 ? 4 : 1); ++kd) {
-#pragma unroll
-        for (int kh = 0; kh < 4; ++kh) {
-            const float wdh = (FD == 2 ? WT[kd] : 1.f) * WT[kh];
-            const uint4* row = tile + (((FD == 2 ? 2 * ld + kd : 0) * HH + 2 * lh + kh) * HW + 2 * lw) * CV + c;
-#pragma unroll
-            for (int kw = 0; kw < 4; ++kw) {
-                float t[VEC];
-                const uint4 q = row[kw * CV];
-                Vec<T, VEC>::load(reinterpret_cast<const T*>(&q), t);
-                const float wt = wdh * WT[kw];
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) r[k] = fmaf(wt, t[k], r[k]);
-            }
-        }
-    }
-    Vec<T, VEC>::store(dx + ((size_t)n * D * H * W + ((size_t)d * H + h) * W + w) * dx_ld + cv * VEC, r);
 }
 
 static inline int flat_grid(int64_t total, int threads, int N = 1) {
@@ -1093,40 +1063,29 @@ int b200em_upsample_trilinear_fwd(const void* x, int64_t x_ld, void* y, int64_t 
     return 0;
 }
 
-int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, const void* xcat, int64_t xcat_ld, const float* coef,
+int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, const void* zlow, int64_t zlow_ld, const float* coef,
                                   int64_t coef_nstride, void* dx, int64_t dx_ld, int dtype, int N, int D, int H,
                                   int W, int C, int fd, int fh, int fw, void* stream) {
     B2_CHECK_ARG(dy && dx && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "upsample_bwd: bad arguments");
-    B2_CHECK_ARG(!coef || xcat, "upsample_bwd: coef needs xcat");
+    B2_CHECK_ARG(!coef || zlow, "upsample_bwd: coef needs zlow");
     int64_t Si = (int64_t)D * H * W;
     B2_CHECK_ARG(Si * fd * fh * fw * C < (1LL << 31) && N <= 65535, "upsample_bwd: sample too large for 32-bit indexing");
     B2_DISPATCH_DTYPE(dtype, T, {
         constexpr int V = FullVec<T>::value;
         const int cvec_ = C / V;
-        if (can_vec<T>(C, {dy_ld, dx_ld, coef ? xcat_ld : (int64_t)V}, {dy, dx, coef ? xcat : nullptr}) && fd <= 2 && fh == 2 && fw == 2) {
-            // tiled kernel: the high-res tile goes through shared memory once, the norm backward is applied on the way in
-            const int LDt = fd == 2 ? 2 : 1, LHt = fd == 2 ? 4 : 8;
-            const int th = (H + LHt - 1) / LHt, tw = (W + 7) / 8, td = (D + LDt - 1) / LDt;
-            dim3 grid((unsigned)(td * th * tw), (unsigned)((cvec_ + 3) / 4), (unsigned)N);
-            const int smem = (fd == 2 ? (2 * LDt + 2) : 1) * (2 * LHt + 2) * 18 * 4 * 16;
-            if (fd == 2) {
-                B2_CUDA(cudaFuncSetAttribute(upsample2_bwd_tile_kernel<T, V, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                upsample2_bwd_tile_kernel<T, V, 2><<<grid, 256, smem, (cudaStream_t)stream>>>(
-                    (const T*)dy, dy_ld, (const T*)xcat, xcat_ld, coef, coef_nstride, (T*)dx, dx_ld, D, H, W, C, th, tw);
-            } else {
-                upsample2_bwd_tile_kernel<T, V, 1><<<grid, 256, smem, (cudaStream_t)stream>>>(
-                    (const T*)dy, dy_ld, (const T*)xcat, xcat_ld, coef, coef_nstride, (T*)dx, dx_ld, D, H, W, C, th, tw);
-            }
-        } else if (coef) {
-            set_error("upsample_bwd: the fused norm backward needs 16-byte aligned channel vectors and factors (1|2, 2, 2)");
-            return 2;
-        } else if (can_vec<T>(C, {dy_ld, dx_ld}, {dy, dx}) && cvec_ <= 256 && 256 % cvec_ == 0 && fd <= 2 && fh == 2 && fw == 2) {
+        if (can_vec<T>(C, {dy_ld, dx_ld, coef ? zlow_ld : (int64_t)V}, {dy, dx, coef ? zlow : nullptr}) && cvec_ <= 256 && 256 % cvec_ == 0 &&
+            fd <= 2 && fh == 2 && fw == 2) {
             const int th = (H + UP_BH - 1) / UP_BH, tw = (W + UP_BW - 1) / UP_BW, td = (D + UP_BD - 1) / UP_BD;
             dim3 grid((unsigned)(td * th * tw), 1, (unsigned)N);
             if (fd == 2)
-                upsample2_bwd_kernel<T, V, 2, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, th, tw);
+                upsample2_bwd_kernel<T, V, 2, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (const T*)zlow, zlow_ld, coef, coef_nstride,
+                                                                                        (T*)dx, dx_ld, D, H, W, C, th, tw);
             else
-                upsample2_bwd_kernel<T, V, 1, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, th, tw);
+                upsample2_bwd_kernel<T, V, 1, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (const T*)zlow, zlow_ld, coef, coef_nstride,
+                                                                                        (T*)dx, dx_ld, D, H, W, C, th, tw);
+        } else if (coef) {
+            set_error("upsample_bwd: the fused norm backward needs 16-byte aligned channel vectors (a power-of-two count of them) and factors (1|2, 2, 2)");
+            return 2;
         } else if (can_vec<T>(C, {dy_ld, dx_ld}, {dy, dx})) {
             int64_t total = Si * (C / V);
             upsample_bwd_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, fd, fh, fw, total);

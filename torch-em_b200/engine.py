@@ -329,7 +329,7 @@ def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act
         up = cat[..., :C]
         up_sums = torch.zeros((N, C, 2), dtype=torch.float32, device=dev) if norm is not None else None
         B.upsample_fwd(z_low, up, f, up_sums)
-        zlows.append((cur, z_low.shape))
+        zlows.append((cur, z_low))
         cat_sums = torch.cat([up_sums, skip_sums[lvl]], dim=1) if norm is not None else None
         out = torch.empty((N,) + dims + (spec.conv2.cout,), dtype=act_dtype, device=dev)
         _run_block(B, plan, P, bufs, spec, cat, cat_sums, out, False, ctx, packs, training)
@@ -482,16 +482,17 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
         rec = ctx.blocks[spec.prefix]
         cat = rec["x_in"]
         f = plan.scale_factors[lvl]
-        x_low, zshape = m["sampler_in"][i]
-        d_zlow = torch.empty(zshape, dtype=x_low.dtype, device=dev)
+        x_low, z_low = m["sampler_in"][i]
+        d_zlow = torch.empty(z_low.shape, dtype=x_low.dtype, device=dev)
         # The gradient w.r.t. the concat buffer is consumed twice -- [..., :C] by the up-sampling backward, [..., C:] (the skip)
-        # by the max-pool backward of the encoder -- and both kernels can apply the block's first norm backward while they load:
-        # d_cat = c0 * g + c1 * cat + c2 is then never written.  (Cropped skips, odd factors: materialise it as before.)
+        # by the max-pool backward of the encoder -- and both kernels apply the block's first norm backward themselves:
+        # d_cat = c0 * g + c1 * cat + c2 is then never written (the up-sampling backward does it on the low-resolution tensor by
+        # linearity, see b200em_upsample_trilinear_bwd).  Cropped skips, odd factors: materialise it as before.
         lazy = B.fused_up_bwd_ok(cat[..., :C], f) and m["enc_dims"][lvl] == m["dec_dims"][lvl]
         if lazy:
             g_cat, coef = _block_backward(B, plan, P, spec, rec, dz, True, grads, packs, lazy_dx=True)
             skip_grads[lvl] = (g_cat[..., C:], None if coef is None else coef[:, C:])
-            B.upsample_bwd(g_cat[..., :C], d_zlow, f, xcat=cat[..., :C], coef=None if coef is None else coef[:, :C])
+            B.upsample_bwd(g_cat[..., :C], d_zlow, f, zlow=z_low, coef=None if coef is None else coef[:, :C])
         else:
             d_cat = _block_backward(B, plan, P, spec, rec, dz, True, grads, packs)
             skip_grads[lvl] = (d_cat[..., C:], None)
