@@ -1,0 +1,21 @@
+#!/bin/bash
+# Collects the measured evidence of a round into gpurun_out/<tag>_*: run on the GPU box through gpurun, e.g.
+#   gpurun --timeout 3000 -- 'bash scripts/collect_profiles.sh r02'
+tag=${1:-r02}
+out=gpurun_out
+set -x
+python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_reference_cpu.json 2> $out/${tag}_bench_reference_cpu.err
+python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
+python bench.py --config cfg3 --steps 10 --warmup 3 --no-cpu-baseline > $out/${tag}_bench_cfg3.json 2> $out/${tag}_bench_cfg3.err
+python bench.py --config cfg4 --steps 5 --warmup 3 --no-cpu-baseline > $out/${tag}_bench_cfg4_n1.json 2> $out/${tag}_bench_cfg4_n1.err
+python bench.py --config cfg5 --steps 3 --warmup 2 > $out/${tag}_bench_cfg5.json 2> $out/${tag}_bench_cfg5.err
+python scripts/bench_layers.py > $out/${tag}_bench_layers.txt 2>&1
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches_train_step.csv python scripts/profile_step.py > $out/${tag}_prof_step.log 2>&1
+python scripts/summarize_launches.py $out/${tag}_launches_train_step.csv > $out/${tag}_launches_train_step_summary.txt
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches_predict.csv python scripts/profile_predict.py > $out/${tag}_prof_predict.log 2>&1
+python scripts/summarize_launches.py $out/${tag}_launches_predict.csv > $out/${tag}_launches_predict_summary.txt
+B200EM_CONFIG=cfg4 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches_cfg4.csv python scripts/profile_step.py > $out/${tag}_prof_cfg4.log 2>&1
+python scripts/summarize_launches.py $out/${tag}_launches_cfg4.csv > $out/${tag}_launches_cfg4_summary.txt
+ncu --set full --import-source on --clock-control none --profile-from-start off -f -o $out/${tag}_kernels python scripts/profile_kernels.py > $out/${tag}_prof_kernels.log 2>&1
+ncu -i $out/${tag}_kernels.ncu-rep --page raw --csv > $out/${tag}_kernels_raw.csv 2> /dev/null
+ls -la $out | tail -30

@@ -1,6 +1,6 @@
 """One launch of each hot kernel on its cfg2 L0 shape between cudaProfilerStart/Stop (for `ncu --set full`).
 
-    ncu --set full --import-source on --clock-control none --profile-from-start off -o gpurun_out/r01_kernels python scripts/profile_kernels.py
+    ncu --set full --import-source on --clock-control none --profile-from-start off -o gpurun_out/r02_kernels python scripts/profile_kernels.py
 """
 import os
 import sys
@@ -13,7 +13,7 @@ from torch_em_b200.backend import default_backend
 dev = "cuda:0"
 B = default_backend()
 N, S = 4, 128
-which = set((os.environ.get("KERNELS") or "ds_fwd,ds_dgrad,cs_wgrad,plain_fwd,upsample_fwd,upsample_bwd,maxpool_bwd,im2col").split(","))
+which = set((os.environ.get("KERNELS") or "ds_fwd,ds_dgrad,cs_wgrad,plain_fwd,plain_deep,tf32_fwd,upsample_fwd,upsample_bwd,maxpool_bwd,norm_bwd_apply").split(","))
 torch.manual_seed(0)
 x = torch.randn((N, S, S, S, 32), device=dev).bfloat16()
 dz = torch.randn((N, S, S, S, 32), device=dev).bfloat16()
@@ -37,6 +37,19 @@ cat = torch.empty((N, S, S, S, 64), device=dev, dtype=torch.bfloat16)
 dlo = torch.empty_like(lo)
 x1 = torch.randn((N, S, S, S, 1), device=dev).bfloat16()
 ss1 = torch.ones((N, 1, 2), device=dev)
+coef = torch.randn((N, 64, 3), device=dev)
+# deep level (L4 of cfg2: 512 -> 512 on 8^3) and the TF32 path (cfg4 L1: 128 -> 128 on 64^3, batch 1, fp32)
+x4 = torch.randn((N, 8, 8, 8, 512), device=dev).bfloat16()
+w4 = torch.randn((512, 512, 3, 3, 3), device=dev) * 0.01
+pk4 = B.pack(("prof", 512), w4)
+y4 = torch.empty_like(x4)
+torch.backends.cudnn.allow_tf32 = True
+xf = torch.randn((1, 64, 64, 64, 128), device=dev)
+wf = torch.randn((128, 128, 3, 3, 3), device=dev) * 0.03
+pkf = B.pack(("prof", "tf32"), wf)
+yf = torch.empty_like(xf)
+ssf = torch.ones((1, 128, 2), device=dev)
+sf = torch.zeros((1, 128, 2), device=dev)
 
 runs = {
     "ds_fwd": lambda: B.conv(x, ss, pk, b, y, sums, (3, 3, 3), True, False),
@@ -44,9 +57,11 @@ runs = {
     "cs_wgrad": lambda: B.wgrad(x, ss, dz, dw, db, (3, 3, 3)),
     "plain_fwd": lambda: B.conv(x2, ss2, pk2, torch.zeros(128, device=dev), y2, s2, (3, 3, 3), True, False),
     "upsample_fwd": lambda: B.upsample_fwd(lo, cat[..., :32], (2, 2, 2), sums),
-    "upsample_bwd": lambda: B.upsample_bwd(cat[..., :32], dlo, (2, 2, 2)),
-    "maxpool_bwd": lambda: B.maxpool_bwd(cat[..., 32:], lo, cat[..., :32], y, (2, 2, 2), 1),
-    "im2col": lambda: B.im2col(x1, ss1, (3, 3, 3), 32),
+    "plain_deep": lambda: B.conv(x4, None, pk4, torch.zeros(512, device=dev), y4, None, (3, 3, 3), True, False),
+    "tf32_fwd": lambda: B.conv(xf, ssf, pkf, torch.zeros(128, device=dev), yf, sf, (3, 3, 3), True, False),
+    "upsample_bwd": lambda: B.upsample_bwd(cat[..., :32], dlo, (2, 2, 2), zlow=lo, coef=coef[:, :32]),
+    "maxpool_bwd": lambda: B.maxpool_bwd(cat[..., 32:], lo, cat[..., :32], y, (2, 2, 2), 1, coef=coef[:, 32:]),
+    "norm_bwd_apply": lambda: B.norm_bwd_apply(g, x, coef[:, :32].contiguous(), None, y, 1),
 }
 for k, fn in runs.items():
     if k in which:

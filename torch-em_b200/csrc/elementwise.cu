@@ -313,6 +313,14 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const 
     const int Do = D / fd, Ho = H / fh, Wo = W / fw;
     const int64_t So = (int64_t)Do * Ho * Wo, Si = (int64_t)D * H * W;
     const int64_t n = blockIdx.y;
+    extern __shared__ __align__(16) float s_coef[];     // [channel vector][c0 | c1 | c2][VEC] of this sample when coef is given
+    if (coef) {
+        for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
+            const int c = i / 3, k = i % 3;
+            s_coef[((c / VEC) * 3 + k) * VEC + c % VEC] = coef[n * coef_nstride + i];
+        }
+        __syncthreads();
+    }
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
         int cv = (int)(i % cvec);
         const unsigned s = i / cvec;
@@ -335,12 +343,6 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const 
                 }
         float gp[VEC];
         Vec<T, VEC>::load(dp + vox * dp_ld + cv * VEC, gp);
-        float cf[VEC][3];
-        if (coef) {
-            const float* q = coef + n * coef_nstride + (size_t)cv * VEC * 3;
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) { cf[v][0] = q[3 * v]; cf[v][1] = q[3 * v + 1]; cf[v][2] = q[3 * v + 2]; }
-        }
         pos = 0;
         for (int a = 0; a < fd; ++a)
             for (int b = 0; b < fh; ++b)
@@ -350,8 +352,18 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const 
                     if (relu_mask || coef) Vec<T, VEC>::load(x + vi * x_ld + cv * VEC, t);
                     if (add) Vec<T, VEC>::load(add + vi * add_ld + cv * VEC, va);
                     if (coef) {
+                        // shared memory, read as 16-byte vectors: no extra registers across the window loop, no global loads in it
+                        float k0[VEC], k1[VEC], k2[VEC];
+                        Vec<float, VEC == 1 ? 1 : 4>::load(s_coef + (cv * 3 + 0) * VEC, *reinterpret_cast<float(*)[VEC == 1 ? 1 : 4]>(k0));
+                        Vec<float, VEC == 1 ? 1 : 4>::load(s_coef + (cv * 3 + 1) * VEC, *reinterpret_cast<float(*)[VEC == 1 ? 1 : 4]>(k1));
+                        Vec<float, VEC == 1 ? 1 : 4>::load(s_coef + (cv * 3 + 2) * VEC, *reinterpret_cast<float(*)[VEC == 1 ? 1 : 4]>(k2));
+                        if (VEC == 8) {
+                            Vec<float, 4>::load(s_coef + (cv * 3 + 0) * VEC + 4, *reinterpret_cast<float(*)[4]>(k0 + (VEC == 8 ? 4 : 0)));
+                            Vec<float, 4>::load(s_coef + (cv * 3 + 1) * VEC + 4, *reinterpret_cast<float(*)[4]>(k1 + (VEC == 8 ? 4 : 0)));
+                            Vec<float, 4>::load(s_coef + (cv * 3 + 2) * VEC + 4, *reinterpret_cast<float(*)[4]>(k2 + (VEC == 8 ? 4 : 0)));
+                        }
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) va[v] = fmaf(cf[v][0], va[v], fmaf(cf[v][1], t[v], cf[v][2]));
+                        for (int v = 0; v < VEC; ++v) va[v] = fmaf(k0[v], va[v], fmaf(k1[v], t[v], k2[v]));
                     }
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
@@ -736,8 +748,7 @@ upsample2_fwd_pair_kernel(const T* __restrict__ x, int64_t x_ld, T* __restrict__
 // a = (i == 0 ? 1 : .75), b = (i == n-1 ? 1 : .75) and the out-of-range taps dropped.  Separable: w, then h, then d.
 template <typename T, int VEC, int FD, int FH, int FW>
 __global__ void __launch_bounds__(256)
-upsample2_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, const T* __restrict__ zlow, int64_t zlow_ld,
-                     const float* __restrict__ coef, int64_t coef_nstride, T* __restrict__ dx, int64_t dx_ld, int D, int H, int W, int C,
+upsample2_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, T* __restrict__ dx, int64_t dx_ld, int D, int H, int W, int C,
                      int tiles_h, int tiles_w) {
     const int cvec = C / VEC;
     const int n = blockIdx.z;
@@ -787,48 +798,71 @@ upsample2_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, const T* __restric
                 }
             }
         }
-        if (coef) {
-            // Fused norm backward of the consuming block: the gradient that is transposed-interpolated is c0 * dy + c1 * up + c2
-            // with up = U z (the up-sampled tensor itself).  By linearity  U^T (c0 dy + c1 U z + c2) = c0 U^T dy + c1 (U^T U) z +
-            // c2 U^T 1:  U^T 1 = 2 per x2 axis (the four taps always sum to 2, edges included) and U^T U is a 3-tap stencil per
-            // axis on the LOW-resolution z -- so the high-resolution `up` tensor is not read at all.
-            auto uu = [&](int i, int n_, float& cm, float& c0_, float& cp) {        // per-axis coefficients on z[i-1], z[i], z[i+1]
-                const float t0 = tapw(i, n_, 0), t1 = tapw(i, n_, 1), t2 = tapw(i, n_, 2), t3 = tapw(i, n_, 3);
-                cm = t0 * 0.75f + (i > 0 ? t1 * 0.25f : 0.f);
-                c0_ = t0 * 0.25f + t1 * (i > 0 ? 0.75f : 1.f) + t2 * (i < n_ - 1 ? 0.75f : 1.f) + t3 * 0.25f;
-                cp = (i < n_ - 1 ? t2 * 0.25f : 0.f) + t3 * 0.75f;
-            };
-            float ad[3] = {0.f, 1.f, 0.f}, ah[3] = {0.f, 1.f, 0.f}, aw[3] = {0.f, 1.f, 0.f};
-            if (FD == 2) uu(d, D, ad[0], ad[1], ad[2]);
-            if (FH == 2) uu(h, H, ah[0], ah[1], ah[2]);
-            if (FW == 2) uu(w, W, aw[0], aw[1], aw[2]);
-            float sz[VEC];
+        Vec<T, VEC>::store(xn + (((size_t)d * H + h) * W + w) * dx_ld + cv * VEC, r);
+    }
+}
+
+// Fused norm backward of the block that consumes an up-sampled tensor, on the LOW-resolution side.  The gradient that has to be
+// transposed-interpolated is c0 * dy + c1 * up + c2 with up = U z (the up-sampled tensor itself); by linearity
+//   U^T (c0 dy + c1 U z + c2) = c0 U^T dy + c1 (U^T U) z + c2 U^T 1,
+// U^T 1 = 2 per x2 axis (the four taps always sum to 2, edges included) and U^T U is a 3-tap stencil per axis on z -- so the
+// high-resolution `up` tensor is never read: this kernel turns r = U^T dy (in place) into the result with one pass over the
+// low-resolution tensors.  One thread per (low-res voxel, channel vector).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+upsample2_bwd_norm_kernel(T* __restrict__ dx, int64_t dx_ld, const T* __restrict__ zlow, int64_t zlow_ld, const float* __restrict__ coef,
+                          int64_t coef_nstride, int D, int H, int W, int C, int fd, int64_t total) {
+    const unsigned cvec = C / VEC;
+    const int64_t n = blockIdx.y;
+    auto tapw = [](int i, int n_, int k) -> float {
+        if (k == 0) return i > 0 ? 0.25f : 0.f;
+        if (k == 1) return i > 0 ? 0.75f : 1.f;
+        if (k == 2) return i < n_ - 1 ? 0.75f : 1.f;
+        return i < n_ - 1 ? 0.25f : 0.f;
+    };
+    auto uu = [&](int i, int n_, float (&a)[3]) {        // per-axis coefficients of U^T U on z[i-1], z[i], z[i+1]
+        const float t0 = tapw(i, n_, 0), t1 = tapw(i, n_, 1), t2 = tapw(i, n_, 2), t3 = tapw(i, n_, 3);
+        a[0] = t0 * 0.75f + (i > 0 ? t1 * 0.25f : 0.f);
+        a[1] = t0 * 0.25f + t1 * (i > 0 ? 0.75f : 1.f) + t2 * (i < n_ - 1 ? 0.75f : 1.f) + t3 * 0.25f;
+        a[2] = (i < n_ - 1 ? t2 * 0.25f : 0.f) + t3 * 0.75f;
+    };
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
+        const int cv = (int)(i % cvec);
+        const unsigned s = i / cvec;
+        const int w = (int)(s % (unsigned)W), h = (int)((s / (unsigned)W) % (unsigned)H), d = (int)(s / (unsigned)(W * H));
+        float ad[3] = {0.f, 1.f, 0.f}, ah[3], aw[3];
+        if (fd == 2) uu(d, D, ad);
+        uu(h, H, ah);
+        uu(w, W, aw);
+        float sz[VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) sz[v] = 0.f;
-            const T* zn = zlow + (size_t)n * D * H * W * zlow_ld + cv * VEC;
+        for (int v = 0; v < VEC; ++v) sz[v] = 0.f;
+        const T* zn = zlow + (size_t)n * D * H * W * zlow_ld + cv * VEC;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                if (ad[a] == 0.f) continue;
+        for (int a = 0; a < 3; ++a) {
+            if (ad[a] == 0.f) continue;
 #pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    if (ah[b] == 0.f) continue;
+            for (int b = 0; b < 3; ++b) {
+                if (ah[b] == 0.f) continue;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (aw[c] == 0.f) continue;
-                        float t[VEC];
-                        Vec<T, VEC>::load(zn + (((size_t)(d + a - 1) * H + (h + b - 1)) * W + (w + c - 1)) * zlow_ld, t);
-                        const float wt = ad[a] * ah[b] * aw[c];
+                for (int c = 0; c < 3; ++c) {
+                    if (aw[c] == 0.f) continue;
+                    float t[VEC];
+                    Vec<T, VEC>::load(zn + (((size_t)(d + a - 1) * H + (h + b - 1)) * W + (w + c - 1)) * zlow_ld, t);
+                    const float wt = ad[a] * ah[b] * aw[c];
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) sz[v] = fmaf(wt, t[v], sz[v]);
-                    }
+                    for (int v = 0; v < VEC; ++v) sz[v] = fmaf(wt, t[v], sz[v]);
                 }
             }
-            const float* cf = coef + (size_t)n * coef_nstride + (size_t)cv * VEC * 3;
-            const float wsum = (FD == 2 ? 2.f : 1.f) * (FH == 2 ? 2.f : 1.f) * (FW == 2 ? 2.f : 1.f);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) r[v] = fmaf(cf[3 * v], r[v], fmaf(cf[3 * v + 1], sz[v], cf[3 * v + 2] * wsum));
         }
-        Vec<T, VEC>::store(xn + (((size_t)d * H + h) * W + w) * dx_ld + cv * VEC, r);
+        T* q = dx + ((size_t)n * D * H * W + s) * dx_ld + cv * VEC;
+        float r[VEC];
+        Vec<T, VEC>::load(q, r);
+        const float* cf = coef + (size_t)n * coef_nstride + (size_t)cv * VEC * 3;
+        const float wsum = (fd == 2 ? 2.f : 1.f) * 4.f;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = fmaf(cf[3 * v], r[v], fmaf(cf[3 * v + 1], sz[v], cf[3 * v + 2] * wsum));
+        Vec<T, VEC>::store(q, r);
     }
 }
 
@@ -1010,12 +1044,12 @@ int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp
         constexpr int V = FullVec<T>::value;
         if (can_vec<T>(C, {x_ld, dp_ld, add ? add_ld : (int64_t)V, out_ld}, {x, dp, add, out})) {
             int64_t total = So * (C / V);
-            maxpool_bwd_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
+            maxpool_bwd_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, coef ? C * 3 * sizeof(float) : 0, (cudaStream_t)stream>>>(
                 (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, coef, coef_nstride, (T*)out, out_ld, D, H, W, C, fd, fh, fw,
                 relu_mask, total);
         } else {
             int64_t total = So * C;
-            maxpool_bwd_kernel<T, 1><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
+            maxpool_bwd_kernel<T, 1><<<dim3(flat_grid(total, 256, N), N), 256, coef ? C * 3 * sizeof(float) : 0, (cudaStream_t)stream>>>(
                 (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, coef, coef_nstride, (T*)out, out_ld, D, H, W, C, fd, fh, fw,
                 relu_mask, total);
         }
@@ -1078,11 +1112,16 @@ int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, const void* zlo
             const int th = (H + UP_BH - 1) / UP_BH, tw = (W + UP_BW - 1) / UP_BW, td = (D + UP_BD - 1) / UP_BD;
             dim3 grid((unsigned)(td * th * tw), 1, (unsigned)N);
             if (fd == 2)
-                upsample2_bwd_kernel<T, V, 2, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (const T*)zlow, zlow_ld, coef, coef_nstride,
-                                                                                        (T*)dx, dx_ld, D, H, W, C, th, tw);
+                upsample2_bwd_kernel<T, V, 2, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, th, tw);
             else
-                upsample2_bwd_kernel<T, V, 1, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (const T*)zlow, zlow_ld, coef, coef_nstride,
-                                                                                        (T*)dx, dx_ld, D, H, W, C, th, tw);
+                upsample2_bwd_kernel<T, V, 1, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, th, tw);
+            if (coef) {
+                // NOTE: the intermediate U^T dy is rounded to the activation type once more than in the unfused form (bf16: 2^-9)
+                count_launch();
+                const int64_t total = Si * cvec_;
+                upsample2_bwd_norm_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
+                    (T*)dx, dx_ld, (const T*)zlow, zlow_ld, coef, coef_nstride, D, H, W, C, fd, total);
+            }
         } else if (coef) {
             set_error("upsample_bwd: the fused norm backward needs 16-byte aligned channel vectors (a power-of-two count of them) and factors (1|2, 2, 2)");
             return 2;
