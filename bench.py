@@ -50,7 +50,7 @@ CONFIGS = {
 MODEL_KW = CONFIGS["cfg2"]["model_kw"]
 BATCH, PATCH = CONFIGS["cfg2"]["batch"], CONFIGS["cfg2"]["patch"]
 METRIC = CONFIGS["cfg2"]["metric"]
-NCU_FULL_CSV = "profiles/r01_kernels_ncu_full.csv"
+NCU_FULL_CSV = "profiles/r02_kernels_ncu_full.csv"
 # backend launch label -> __global__ function it launches (csrc/)
 KERNEL_OF = {"first:fwd": "conv3d_first_kernel", "first:wgrad": "conv3d_first_wgrad_kernel", "ds:fwd": "conv3d_umma_ds_kernel",
              "ds:dgrad": "conv3d_umma_ds_kernel", "plain:fwd": "conv3d_umma_kernel", "plain:dgrad": "conv3d_umma_kernel",
@@ -388,8 +388,8 @@ def conv_roofline(fam, nroof, ms, tens_peak, peak_src):
     traffic = ncu_traffic(top)
     return {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": tens_peak, "unit": "TFLOP/s",
             "frac": achieved / tens_peak,
-            # per-launch DRAM bytes (read + write) of this kernel's LARGEST launch from the committed ncu --set full capture
-            # (not measured in this run); achieved / avg_launch_ms average over all of its launches
+            # per-launch DRAM bytes (read + write) of ONE representative launch of this kernel from the committed ncu --set full
+            # capture (shape in that file's first column; not measured in this run); achieved / avg_launch_ms average all launches
             "traffic": traffic, "traffic_source": NCU_FULL_CSV if traffic is not None else None,
             "launches_per_step": n // nroof, "avg_launch_ms": tot_ms / n, "share_of_step": tot_ms / nroof / ms,
             "peak_source": peak_src,
