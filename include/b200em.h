@@ -101,6 +101,27 @@ int b200em_conv3d_umma_tf32(const void* x, int64_t x_ld, const float* in_scale_s
                             void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
                             int Cout, int kd, int kh, int kw, int relu, void* stream);
 
+/* "h16" variant -- the DEFAULT tensor-core path of fp32 activations when TF32 convolutions are allowed.  IEEE fp16 has the same
+ * 11-bit significand as TF32 (and is rounded to nearest where kind::tf32 truncates), so feeding fp16 COPIES of the fp32
+ * operands to tcgen05.mma.kind::f16 with fp32 accumulation is TF32-class arithmetic at the bf16 rate (2x kind::tf32); fp16's
+ * narrow exponent is handled by an exact power-of-two scale per tensor (b200em_absmax_f32 / b200em_cvt_f16) that the kernel
+ * undoes on the fp32 accumulator.  Replaces nn.Conv3d forward / autograd dgrad / wgrad of the reference's mixed_precision=False
+ * path (unet.py:429-438, default_trainer.py:132-142).
+ *   x_f16: NDHWC fp16 copy of the (normalised) input, pitch x_ld; x_absmax: the DEVICE float its scale was derived from, or NULL
+ *   (unscaled);  w_packed: b200em_pack_batch image with B200EM_PACK_PLAIN_F16;  y / dot_x: fp32.  Otherwise as b200em_conv3d_umma
+ *   (same supported shapes: b200em_conv3d_umma_supported). */
+int b200em_conv3d_umma_h16(const void* x_f16, int64_t x_ld, const float* x_absmax, const void* w_packed, const float* bias, float* y,
+                           int64_t y_ld, float* sums, const float* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin, int Cout,
+                           int kd, int kh, int kw, int relu, void* stream);
+/* max |x| over an fp32 tensor of `rows` voxels x C channels with pitch x_ld, as an atomic max into *absmax (device, zeroed by
+ * the caller; non-negative floats order like their bit patterns).  colsum (nullable, C floats) += the per-channel sums of the
+ * same pass: the bias gradient sum(dz) from the fp32 values, as autograd computes it. */
+int b200em_absmax_f32(const float* x, int64_t x_ld, int64_t rows, int C, float* absmax, float* colsum, void* stream);
+/* out (N,S,C) fp16, contiguous = fp16(2^k * x_hat), x_hat = scale*x + shift when in_scale_shift is given (the fused norm apply),
+ * k derived on the device from *absmax (NULL: k = 0; see common.cuh h16_shift). */
+int b200em_cvt_f16(const float* x, int64_t x_ld, const float* in_scale_shift, const float* absmax, void* out, int N, int64_t S,
+                   int C, void* stream);
+
 /* "depth-stacked" tcgen05 variant for 3 x kh x kw filters with few output channels (Cout <= 80) whose packed filter
  * fits in shared memory: the three depth taps share one operand fetch (N = 3*Cout) and land in the accumulators of
  * three consecutive output slices (a ring of TMEM column blocks); every input slice is staged once per column of
@@ -122,6 +143,7 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
 #define B200EM_PACK_PLAIN 0          /* operand of b200em_conv3d_umma */
 #define B200EM_PACK_DEPTH_STACKED 1  /* operand of b200em_conv3d_umma_ds */
 #define B200EM_PACK_PLAIN_TF32 2     /* fp32 operand of b200em_conv3d_umma_tf32 (packed: Cout*Cin*taps fp32) */
+#define B200EM_PACK_PLAIN_F16 3      /* IEEE fp16 operand of b200em_conv3d_umma_h16 (the plain layout) */
 typedef struct b200em_pack_job {
     const float* w;    /* torch (Cout, Cin, kd, kh, kw) fp32, device */
     void* packed;      /* bf16 operand image, device */
@@ -159,6 +181,16 @@ int b200em_conv3d_wgrad_cs_supported(int Cin, int Cout, int kd, int kh, int kw);
 int b200em_conv3d_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld,
                            float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw,
                            void* stream);
+
+/* The two weight-gradient kernels above on IEEE fp16 operand copies of fp32 tensors (the h16 path, see b200em_conv3d_umma_h16):
+ * x_f16 = fp16(2^kx * x_hat) and dz_f16 = fp16(2^kz * dz) from b200em_cvt_f16 (the norm apply is already in x_f16), *_absmax
+ * the device floats the scales were derived from (NULL: unscaled); dw / db are accumulated in fp32 with the scales undone. */
+int b200em_conv3d_wgrad_umma_h16(const void* x_f16, int64_t x_ld, const float* x_absmax, const void* dz_f16, int64_t dz_ld,
+                                 const float* dz_absmax, float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd,
+                                 int kh, int kw, void* stream);
+int b200em_conv3d_wgrad_cs_h16(const void* x_f16, int64_t x_ld, const float* x_absmax, const void* dz_f16, int64_t dz_ld,
+                               const float* dz_absmax, float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd,
+                               int kh, int kw, void* stream);
 
 /* im2col of the first conv (thin K = taps*Cin): out (N,D,H,W,Kp) bf16 with out[vox][tap*Cin+ci] = x_hat[vox+tap][ci], zero in
  * the padding and for channels >= taps*Cin.  The conv is then a 1x1x1 conv with Kp input channels on the tcgen05 path. */

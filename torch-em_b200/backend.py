@@ -50,7 +50,16 @@ def _f32(t):
 class WeightPack:
     """Kernel-operand copies of one conv weight (derived data; the fp32 nn.Parameter stays the master)."""
     __slots__ = ("w_fwd_f32", "w_dgrad_f32", "f32_stale", "umma_fwd", "umma_dgrad", "cout", "cin", "kernel", "thin", "thin_kp",
-                 "ds_fwd", "ds_dgrad", "master", "tf32_fwd", "tf32_dgrad")
+                 "ds_fwd", "ds_dgrad", "master", "tf32_fwd", "tf32_dgrad", "h16_fwd", "h16_dgrad")
+
+
+class H16Operand:
+    """fp16 operand copy of an fp32 activation for the h16 path: ``t`` (N, D, H, W, C) float16, dense, = fp16(2^k * x_hat);
+    ``absmax`` the 1-element device tensor k is derived from on the device (None: k = 0, a normalised tensor)."""
+    __slots__ = ("t", "absmax")
+
+    def __init__(self, t, absmax):
+        self.t, self.absmax = t, absmax
 
 
 class _PackJob(ctypes.Structure):
@@ -62,7 +71,7 @@ class _PackJob(ctypes.Structure):
                 ("reserved", ctypes.c_int32 * 2)]
 
 
-PACK_PLAIN, PACK_DEPTH_STACKED, PACK_PLAIN_TF32 = 0, 1, 2
+PACK_PLAIN, PACK_DEPTH_STACKED, PACK_PLAIN_TF32, PACK_PLAIN_F16 = 0, 1, 2, 3
 
 
 class PackSet:
@@ -91,8 +100,9 @@ class PackSet:
         self.packs = {}
         self.device = None
         # table -> [(pack, attr, layout, elems)]: 0 / 1 = bf16 forward / data-gradient operands, 2 / 3 = the fp32 operands of the
-        # TF32 path (allocated and packed only when a pass really runs with fp32 activations and TF32 allowed)
-        plan = {0: [], 1: [], 2: [], 3: []}
+        # TF32 path, 4 / 5 = the fp16 operands of the h16 path (each allocated and packed only when a pass really runs with fp32
+        # activations on that path)
+        plan = {0: [], 1: [], 2: [], 3: [], 4: [], 5: []}
         for key, w in weights.items():
             if w.device.type != "cuda":
                 raise RuntimeError("b200em: parameters must live on a CUDA device (there is no CPU fallback for this path)")
@@ -105,6 +115,7 @@ class PackSet:
             pk.w_fwd_f32 = pk.w_dgrad_f32 = None
             pk.f32_stale = True
             pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.ds_fwd = pk.ds_dgrad = pk.tf32_fwd = pk.tf32_dgrad = None
+            pk.h16_fwd = pk.h16_dgrad = None
             pk.thin_kp = 0
             n = cout * cin * kd * kh * kw
             if B.use_umma:
@@ -121,6 +132,10 @@ class PackSet:
                     plan[2].append((pk, "tf32_fwd", PACK_PLAIN_TF32, n))
                 if lib.b200em_conv3d_umma_tf32_supported(cout, cin, kd, kh, kw):
                     plan[3].append((pk, "tf32_dgrad", PACK_PLAIN_TF32, n))
+                if lib.b200em_conv3d_umma_supported(cin, cout, kd, kh, kw):
+                    plan[4].append((pk, "h16_fwd", PACK_PLAIN_F16, n))
+                if lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
+                    plan[5].append((pk, "h16_dgrad", PACK_PLAIN_F16, n))
                 kp = -(-kd * kh * kw * cin // 32) * 32
                 first = B.use_ds and lib.b200em_conv3d_first_supported(cin, cout, kd, kh, kw)
                 if cin <= 4 and not first and lib.b200em_conv3d_umma_supported(kp, cout, 1, 1, 1):
@@ -136,7 +151,7 @@ class PackSet:
         if not plan:
             self.tables[d] = None
             return
-        dtype = torch.float32 if d >= 2 else torch.bfloat16
+        dtype = (torch.bfloat16, torch.float32, torch.float16)[d // 2]
         total = sum(-(-n // 8) * 8 for _, _, _, n in plan)
         flat = torch.empty(total, dtype=dtype, device=self.device)
         jobs = (_PackJob * len(plan))()
@@ -173,9 +188,11 @@ class PackSet:
         for pk in self.packs.values():
             pk.f32_stale = True
         if not bf16:
-            # fp32 activations: the TF32 tensor-core path when torch allows TF32 convolutions, else the exact direct kernels
-            # (their fp32 operands are packed lazily, f32_operands)
-            if self.B.tf32_enabled():
+            # fp32 activations: the h16 (default) or TF32 tensor-core path when torch allows TF32 convolutions, else the exact
+            # direct kernels (their fp32 operands are packed lazily, f32_operands)
+            if self.B.h16_enabled():
+                self._launch(4)
+            elif self.B.tf32_enabled():
                 self._launch(2)
             return
         self._launch(0)
@@ -186,6 +203,8 @@ class PackSet:
     def refresh_dgrad(self, bf16=True):
         if bf16:
             self._launch(1)
+        elif self.B.h16_enabled():
+            self._launch(5)
         elif self.B.tf32_enabled():
             self._launch(3)
 
@@ -207,9 +226,11 @@ class PackSet:
 class CudaBackend:
     name = "cuda"
 
-    def __init__(self, use_umma=True, use_ds=True, use_cs=True, use_tf32=None):
+    def __init__(self, use_umma=True, use_ds=True, use_cs=True, use_tf32=None, use_h16=True):
         self.use_umma = use_umma
         self.use_tf32 = use_tf32    # None: follow torch.backends.cudnn.allow_tf32 (True by default, like the reference's fp32 runs)
+        self.use_h16 = use_h16      # TF32-class arithmetic through fp16 operand copies at the bf16 MMA rate (False: kind::tf32 kernels)
+        self._h16_recent = []       # [(tensor, H16Operand)]: the last two un-normalised fp32 tensors converted (dz feeds wgrad AND dgrad)
         self.use_ds = use_ds and use_umma
         self.use_cs = use_cs and use_umma
         self.timing = None          # {family: [(start_event, end_event, work), ...]} while bench.py measures
@@ -245,6 +266,37 @@ class CudaBackend:
             return False
         return torch.backends.cudnn.allow_tf32 if self.use_tf32 is None else bool(self.use_tf32)
 
+    def h16_enabled(self):
+        """fp32 activations with TF32 allowed run as fp16 operand copies (same 11-bit significand as TF32, round-to-nearest, exact
+        power-of-two range scaling) on kind::f16 MMAs with fp32 accumulation: TF32-class results at twice the kind::tf32 rate."""
+        return bool(self.use_h16) and self.tf32_enabled()
+
+    def to_h16(self, x, in_ss, colsum=None):
+        """fp16 operand copy of the fp32 NDHWC view ``x``: fp16(scale * x + shift) for a normalised tensor (unit scale: no range
+        problem), else fp16(2^k * x) with k taken on the device from max |x| (gradients span any range).  Un-normalised tensors are
+        remembered by identity (the same dz object feeds the weight gradient and the data gradient back to back).
+        colsum (C floats, fp32): += the per-channel sums of x from the same pass (the bias gradient, from the fp32 values)."""
+        if in_ss is None:
+            for t, h in self._h16_recent:
+                if t is x:
+                    if colsum is not None:
+                        s2 = torch.zeros((x.shape[0], x.shape[4], 2), dtype=torch.float32, device=x.device)
+                        self.channel_sums(x, s2)
+                        colsum += s2[:, :, 0].sum(0)
+                    return h
+        N, D, H, W, C = x.shape
+        xp, xld = _act(x)
+        out = torch.empty((N, D, H, W, C), dtype=torch.float16, device=x.device)
+        am = None
+        if in_ss is None:
+            am = torch.zeros(1, dtype=torch.float32, device=x.device)
+            call("b200em_absmax_f32", xp, xld, N * D * H * W, C, _f32(am), _f32(colsum), _stream(x))
+        call("b200em_cvt_f16", xp, xld, _f32(in_ss), _f32(am), _ptr(out), N, D * H * W, C, _stream(x))
+        h = H16Operand(out, am)
+        if in_ss is None:
+            self._h16_recent = self._h16_recent[-1:] + [(x, h)]
+        return h
+
     # ---- weights ---------------------------------------------------------------------------------------------
     def pack_set(self, weights):
         """{key: conv weight} -> PackSet (all operand images of a model, one launch per direction)."""
@@ -256,8 +308,11 @@ class CudaBackend:
         ps.refresh_fwd()
         ps.refresh_dgrad()
         if self.tf32_enabled():
-            ps.refresh_fwd(bf16=False)
-            ps.refresh_dgrad(bf16=False)
+            ps._launch(2)
+            ps._launch(3)
+        if self.h16_enabled():
+            ps._launch(4)
+            ps._launch(5)
         return ps[key]
 
     def f32_operands(self, pk):
@@ -364,6 +419,16 @@ class CudaBackend:
                     "b200em_conv3d_umma", xp, xld, _f32(in_ss), _ptr(wu), _f32(b), yp, yld, _f32(sums), dp, dld, N, D, H, W, Cin,
                     Cout, kd, kh, kw, int(relu), _stream(x)))
                 return None
+        wh = pack.h16_dgrad if dgrad else pack.h16_fwd
+        if wh is not None and x.dtype == torch.float32 and self.h16_enabled() and xld % 4 == 0 and yld % 4 == 0 and \
+                x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
+            dp, dld = _act(dot_x) if dot_x is not None else (None, 0)
+            if dot_x is None or (dld % 4 == 0 and dot_x.data_ptr() % 16 == 0):
+                xh = self.to_h16(x, in_ss)
+                self._timed("h16:dgrad" if dgrad else "h16:fwd", flops, lambda: call(
+                    "b200em_conv3d_umma_h16", _ptr(xh.t), Cin, _f32(xh.absmax), _ptr(wh), _f32(b), yp, yld, _f32(sums), dp, dld, N, D,
+                    H, W, Cin, Cout, kd, kh, kw, int(relu), _stream(x)))
+                return None if dgrad else xh        # kept by the schedule for the weight gradient of the same conv
         wt = pack.tf32_dgrad if dgrad else pack.tf32_fwd
         if wt is not None and x.dtype == torch.float32 and self.tf32_enabled() and xld % 4 == 0 and yld % 4 == 0 and \
                 x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
@@ -427,6 +492,19 @@ class CudaBackend:
                 "b200em_conv3d_wgrad_umma", xp, xld, _f32(in_ss), zp, zld, _f32(dw), _f32(db), N, D, H, W, Cin, Cout, kd, kh,
                 kw, _stream(x)))
             return
+        if self.h16_enabled() and x.dtype == torch.float32 and xld % 4 == 0 and zld % 4 == 0 and x.data_ptr() % 16 == 0 and \
+                dz.data_ptr() % 16 == 0 and Cin % 8 == 0 and Cout % 8 == 0:
+            # fp32 activations, TF32 allowed: ONE pass of the tensor-core weight-gradient kernels on fp16 operand copies
+            lib = _lib.load()
+            fn = "b200em_conv3d_wgrad_cs_h16" if self.use_cs and lib.b200em_conv3d_wgrad_cs_supported(Cin, Cout, kd, kh, kw) else \
+                ("b200em_conv3d_wgrad_umma_h16" if lib.b200em_conv3d_wgrad_umma_supported(Cin, Cout, kd, kh, kw) else None)
+            if fn is not None:
+                xh = aux if isinstance(aux, H16Operand) else self.to_h16(x, in_ss)
+                zh = self.to_h16(dz, None, colsum=db)       # bias gradient from the fp32 dz, in the absmax pass
+                self._timed("h16:wgrad", flops, lambda: call(
+                    fn, _ptr(xh.t), Cin, _f32(xh.absmax), _ptr(zh.t), Cout, _f32(zh.absmax), _f32(dw), None, N, D, H, W, Cin, Cout,
+                    kd, kh, kw, _stream(x)))
+                return
         first_f32 = Cin == 1 and xld == 1 and self.use_ds and _lib.load().b200em_conv3d_first_supported(Cin, Cout, kd, kh, kw)
         if self.tf32_enabled() and x.dtype == torch.float32 and zld % 4 == 0 and dz.data_ptr() % 16 == 0 and Cout % 8 == 0 and \
                 (first_f32 or (xld % 4 == 0 and x.data_ptr() % 16 == 0 and Cin % 8 == 0 and
@@ -549,5 +627,6 @@ def default_backend():
     if _default is None:
         _lib.load()
         import os
-        _default = CudaBackend(use_ds=os.environ.get("B200EM_DS", "1") == "1", use_cs=os.environ.get("B200EM_CS", "1") == "1")
+        _default = CudaBackend(use_ds=os.environ.get("B200EM_DS", "1") == "1", use_cs=os.environ.get("B200EM_CS", "1") == "1",
+                               use_h16=os.environ.get("B200EM_H16", "1") == "1")
     return _default

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -47,7 +48,9 @@ int sm_count();
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
@@ -98,6 +101,20 @@ __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_c
 
 // Round a stored value the way the activation dtype would (bf16 statistics are taken on the rounded values).
 template <typename T> __device__ __forceinline__ float round_as(float v) { return to_f<T>(from_f<T>(v)); }
+
+// ---- power-of-two operand scaling of the h16 path ---------------------------------------------------------------
+// fp32 tensors without a bounded range (gradients, un-normalised activations) are multiplied by 2^k before they are rounded
+// to fp16, k chosen from the tensor's max |x| so that the largest element lands in [2^14, 2^15); the consuming kernel undoes
+// it (exactly) on the fp32 accumulator.  `absmax` is a DEVICE float written by b200em_absmax_f32 -- no host round trip.
+__device__ __forceinline__ int h16_shift(const float* absmax) {
+    if (!absmax) return 0;
+    const uint32_t b = __float_as_uint(*absmax) & 0x7fffffffu;
+    const int e = (int)(b >> 23) - 127;
+    if (b == 0 || e == 128) return 0;                  // all zeros, or inf / nan somewhere: leave the values alone
+    const int k = 14 - e;
+    return k < -100 ? -100 : (k > 100 ? 100 : k);
+}
+__device__ __forceinline__ float pow2i(int k) { return __uint_as_float((uint32_t)(k + 127) << 23); }
 
 // dispatch on dtype code
 #define B2_DISPATCH_DTYPE(dtype, T, ...)                                   \

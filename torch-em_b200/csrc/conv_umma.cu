@@ -50,6 +50,7 @@ struct ConvUmmaParams {
     void* y; long long y_ld;
     float* sums;
     const void* dot_x; long long dot_ld;   // non-null: sums = (sum y, sum y * dot_x) -- the norm-backward reductions
+    const float* x_absmax;                 // h16 path: device max |x| the fp16 operand was scaled by (common.cuh h16_shift), or null
     int N, D, H, W, Cin, Cout;
     int kd, kh, kw, relu;
     int R, NP, CC, nchunks, G, acc_bufs;
@@ -110,7 +111,9 @@ __device__ __forceinline__ void load_row(const T* __restrict__ src, bool valid, 
 
 // R_ = depth slabs per work item, KC_ = K=16 steps per channel chunk: compile-time so that the single-thread MMA issue
 // loop is straight-line code with immediate operand offsets (it bounds the small-N layers otherwise).
-template <typename TA, int R_, int KC_>
+// TA = operand type in shared memory (activations and packed weights), TO = type of y and dot_x in global memory:
+// (bf16, bf16), (float, float) = TF32, (__half, float) = the h16 path (fp32 tensors, fp16 operand copies).
+template <typename TA, typename TO, int R_, int KC_>
 __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int EPU = 16 / (int)sizeof(TA);       // channels per 16-byte unit: 8 (bf16) or 4 (fp32 / TF32)
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
         // ===================== epilogue (warps 0-3) =====================
         const int row = warp * 32 + lane;            // GEMM row = TMEM lane
         const int hl = row / TW, wl = row % TW;
+        const float osc = pow2i(-h16_shift(p.x_absmax));     // undo the power-of-two operand scaling (1 when there is none)
         uint32_t it = 0;
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
             int n, d0, h0, w0;
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
             const int rmax = min(p.R, p.D - d0);
             for (int r = 0; r < rmax; ++r) {
                 const int gd = d0 + r;
-                TA* yp = reinterpret_cast<TA*>(p.y) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.y_ld + nblk * p.NP;
+                TO* yp = reinterpret_cast<TO*>(p.y) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.y_ld + nblk * p.NP;
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * acc_cols + r * p.NP;
                 for (int cb = 0; cb < p.NP; cb += 32) {
                     if (p.NP - cb >= 32) {
@@ -298,16 +302,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         float v[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            float f = __uint_as_float(raw[i]) + s_bias[cb + i];
+                            float f = fmaf(__uint_as_float(raw[i]), osc, s_bias[cb + i]);
                             if (p.relu) f = fmaxf(f, 0.f);
-                            v[i] = round_as<TA>(f);
+                            v[i] = round_as<TO>(f);
                         }
-                        if (valid_hw) store_row<TA, 32>(yp + cb, v);
+                        if (valid_hw) store_row<TO, 32>(yp + cb, v);
                         if (p.sums) {
                             float s1[32], s2[32];
                             if (p.dot_x) {
-                                const TA* xq = reinterpret_cast<const TA*>(p.dot_x) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
-                                load_row<TA, 32>(xq, valid_hw, s2);
+                                const TO* xq = reinterpret_cast<const TO*>(p.dot_x) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
+                                load_row<TO, 32>(xq, valid_hw, s2);
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] *= s1[i]; }
                             } else {
@@ -326,16 +330,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            float f = __uint_as_float(raw[i]) + s_bias[cb + i];
+                            float f = fmaf(__uint_as_float(raw[i]), osc, s_bias[cb + i]);
                             if (p.relu) f = fmaxf(f, 0.f);
-                            v[i] = round_as<TA>(f);
+                            v[i] = round_as<TO>(f);
                         }
-                        if (valid_hw) store_row<TA, 16>(yp + cb, v);
+                        if (valid_hw) store_row<TO, 16>(yp + cb, v);
                         if (p.sums) {
                             float s1[16], s2[16];
                             if (p.dot_x) {
-                                const TA* xq = reinterpret_cast<const TA*>(p.dot_x) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
-                                load_row<TA, 16>(xq, valid_hw, s2);
+                                const TO* xq = reinterpret_cast<const TO*>(p.dot_x) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
+                                load_row<TO, 16>(xq, valid_hw, s2);
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] *= s1[i]; }
                             } else {
@@ -476,6 +480,8 @@ struct WgradUmmaParams {
     long long items;
     int x_bytes, dz_bytes;
     int debug;                                 // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 4 no MMAs, 8 no epilogue atomics
+    int fp16;                                  // 2-byte operands are IEEE fp16 (the h16 path of fp32 activations), not bf16
+    const float* x_absmax; const float* z_absmax;   // h16: device max |.| the operands were scaled by (common.cuh h16_shift), or null
 };
 
 template <typename TA>
@@ -582,6 +588,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
                             const float* f = reinterpret_cast<const float*>(&val);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) dbacc[e] += f[e];
+                        } else if (p.fp16) {
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&val);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 f = __half22float2(h2[e]);
+                                dbacc[2 * e] += f.x;
+                                dbacc[2 * e + 1] += f.y;
+                            }
                         } else {
                             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
 #pragma unroll
@@ -602,12 +616,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
 #pragma unroll
             for (int e = 0; e < EPU; ++e) atomicAdd(&s_db[jo * EPU + e], dbacc[e]);
             asm volatile("bar.sync 2, %0;" ::"n"(NLOAD) : "memory");
-            if (t < p.NB) atomicAdd(p.db + cob * p.NB + t, s_db[t]);
+            if (t < p.NB) atomicAdd(p.db + cob * p.NB + t, s_db[t] * pow2i(-h16_shift(p.z_absmax)));
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            const uint32_t idesc = make_idesc<TA>(128, p.NB, 1, 1);       // both operands MN-major
+            const uint32_t idesc = p.fp16 ? make_idesc_f16(128, p.NB, 1, 1) : make_idesc<TA>(128, p.NB, 1, 1);       // both operands MN-major
             // A: LBO = next 8 voxels (next tile row), SBO = next 8 channels (next plane); B likewise on the dz slab
             const uint64_t ad = make_desc(0, WP * 16, PLANE), bd = make_desc(0, TW * 16, WG_DZ_PLANE);
             const uint32_t a_hi = (uint32_t)(ad >> 32), a_lo_c = (uint32_t)(ad & 0xFFFFFFFFu);
@@ -648,6 +662,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
         tc_fence_after();
         const int a = warp;                              // depth tap of this warp's 32 lanes (a == 3: ignored rows)
         const int taps = p.kd * tap9;
+        const float osc = pow2i(-h16_shift(p.x_absmax) - h16_shift(p.z_absmax));
         if (a < p.kd && !(p.debug & 8)) {
             const int ci = chunk * 32 + lane;
             for (int tp = 0; tp < tap9; ++tp) {
@@ -659,7 +674,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int co = cob * p.NB + cb + i;
-                        atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * taps + tap, __uint_as_float(raw[i]));
+                        atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * taps + tap, __uint_as_float(raw[i]) * osc);
                     }
                 }
             }
@@ -694,12 +709,13 @@ bool umma_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC, int* N
 
 using namespace b200em;
 
-template <typename TA>
+template <typename TA, typename TO = TA>
 static int launch_conv_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
                             void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin,
-                            int Cout, int kd, int kh, int kw, int relu, void* stream) {
+                            int Cout, int kd, int kh, int kw, int relu, void* stream, const float* x_absmax = nullptr) {
     constexpr bool F32 = sizeof(TA) == 4;
     constexpr int EPU = 16 / (int)sizeof(TA);
+    constexpr int EPO = 16 / (int)sizeof(TO);
     B2_CHECK_ARG(x && w_packed && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma: bad arguments");
     B2_CHECK_ARG((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv3d_umma: kernel dims must be 1 or 3");
     UmmaShape s;
@@ -707,13 +723,13 @@ static int launch_conv_umma(const void* x, int64_t x_ld, const float* in_scale_s
         set_error("conv3d_umma: channel counts (%d -> %d) not supported by the tcgen05 path", Cin, Cout);
         return 2;
     }
-    B2_CHECK_ARG(x_ld % EPU == 0 && y_ld % EPU == 0 && aligned16(x) && aligned16(y), "conv3d_umma: activations must be 16-byte aligned with a pitch that keeps them so");
+    B2_CHECK_ARG(x_ld % EPU == 0 && y_ld % EPO == 0 && aligned16(x) && aligned16(y), "conv3d_umma: activations must be 16-byte aligned with a pitch that keeps them so");
     B2_CHECK_ARG(x_ld >= Cin && y_ld >= Cout, "conv3d_umma: pitch smaller than channel count");
     ConvUmmaParams p;
     p.x = x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.w = w_packed; p.bias = bias;
     p.y = y; p.y_ld = y_ld; p.sums = sums;
-    p.dot_x = dot_x; p.dot_ld = dot_ld;
-    B2_CHECK_ARG(!dot_x || (sums && dot_ld % EPU == 0 && aligned16(dot_x) && dot_ld >= Cout), "conv3d_umma: dot_x needs sums, 16-byte alignment and pitch >= Cout");
+    p.dot_x = dot_x; p.dot_ld = dot_ld; p.x_absmax = x_absmax;
+    B2_CHECK_ARG(!dot_x || (sums && dot_ld % EPO == 0 && aligned16(dot_x) && dot_ld >= Cout), "conv3d_umma: dot_x needs sums, 16-byte alignment and pitch >= Cout");
     p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.relu = relu;
     // Depth slabs per work item: the shape admits R <= s.R; fewer slabs = more work items (the deep levels have fewer voxel
     // tiles than SMs) but the weight block is streamed once per item.  Cost model per CTA (cycles): items per CTA x
@@ -752,8 +768,8 @@ static int launch_conv_umma(const void* x, int64_t x_ld, const float* in_scale_s
     dim3 grid((unsigned)gx, (unsigned)s.nblk, 1);
 #define B2_UMMA_LAUNCH(R_, KC_)                                                                                             \
     do {                                                                                                                    \
-        B2_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<TA, R_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM)); \
-        conv3d_umma_kernel<TA, R_, KC_><<<grid, THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                             \
+        B2_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<TA, TO, R_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM)); \
+        conv3d_umma_kernel<TA, TO, R_, KC_><<<grid, THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                             \
     } while (0)
     const int kc = s.CC / (2 * EPU);            // MMA K steps per chunk (two 16-byte planes each)
     if (s.R == 4 && kc == 2) B2_UMMA_LAUNCH(4, 2);
@@ -770,7 +786,8 @@ static int launch_conv_umma(const void* x, int64_t x_ld, const float* in_scale_s
 
 template <typename TA>
 static int launch_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw,
-                             float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream) {
+                             float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream, int fp16 = 0,
+                             const float* x_absmax = nullptr, const float* z_absmax = nullptr) {
     constexpr int EPU = 16 / (int)sizeof(TA);
     constexpr int WG_R = WgR<TA>::value;
     constexpr int J = 32 / EPU;
@@ -785,6 +802,8 @@ static int launch_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_
     WgradUmmaParams p;
     p.x = x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.dz = dz; p.dz_ld = dz_ld;
     p.dw = dw; p.db = db;
+    p.fp16 = fp16; p.x_absmax = x_absmax; p.z_absmax = z_absmax;
+    B2_CHECK_ARG(!fp16 || !in_scale_shift, "conv3d_wgrad_umma: fp16 operands take no fused norm apply (b200em_cvt_f16 applies it)");
     p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
     p.NB = NB; p.nco = Cout / NB;
     p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + WG_R - 1) / WG_R;
@@ -849,6 +868,13 @@ int b200em_conv3d_umma_tf32(const void* x, int64_t x_ld, const float* in_scale_s
                                    relu, stream);
 }
 
+int b200em_conv3d_umma_h16(const void* x_f16, int64_t x_ld, const float* x_absmax, const void* w_packed, const float* bias, float* y,
+                           int64_t y_ld, float* sums, const float* dot_x, int64_t dot_ld, int N, int D, int H, int W, int Cin, int Cout,
+                           int kd, int kh, int kw, int relu, void* stream) {
+    return launch_conv_umma<__half, float>(x_f16, x_ld, nullptr, w_packed, bias, y, y_ld, sums, dot_x, dot_ld, N, D, H, W, Cin, Cout, kd, kh,
+                                           kw, relu, stream, x_absmax);
+}
+
 int b200em_conv3d_wgrad_umma_supported(int Cin, int Cout, int kd, int kh, int kw) {
     int NB;
     return wgrad_umma_shape(Cin, Cout, NB) ? 1 : 0;
@@ -859,5 +885,11 @@ int b200em_conv3d_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_
     return launch_wgrad_umma<__nv_bfloat16>(x, x_ld, in_scale_shift, dz, dz_ld, dw, db, N, D, H, W, Cin, Cout, kd, kh, kw, stream);
 }
 
+int b200em_conv3d_wgrad_umma_h16(const void* x_f16, int64_t x_ld, const float* x_absmax, const void* dz_f16, int64_t dz_ld,
+                                 const float* dz_absmax, float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd,
+                                 int kh, int kw, void* stream) {
+    return launch_wgrad_umma<__nv_bfloat16>(x_f16, x_ld, nullptr, dz_f16, dz_ld, dw, db, N, D, H, W, Cin, Cout, kd, kh, kw, stream, 1,
+                                            x_absmax, dz_absmax);
+}
 
 }  // extern "C"

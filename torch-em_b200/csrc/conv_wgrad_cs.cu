@@ -55,6 +55,8 @@ struct WgradCsParams {
     long long items;
     int use_tma;                               // 1: tiles loaded by cp.async.bulk.tensor (tensor maps over x and dz), else cp.async
     int debug;                                 // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 4 no MMAs, 8 profile printf
+    int fp16;                                  // operands are IEEE fp16 (the h16 path of fp32 activations), not bf16
+    const float* x_absmax; const float* z_absmax;   // h16: device max |.| the operands were scaled by (common.cuh h16_shift), or null
 };
 
 __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const WgradCsParams p, const __grid_constant__ CUtensorMap tmx,
@@ -233,9 +235,10 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
                     for (int i = 1; i <= CS_TH; ++i) {
                         const uint4 val = *reinterpret_cast<const uint4*>(zdst + i * CS_ZROW);
                         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+                        const __half2* g2 = reinterpret_cast<const __half2*>(&val);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float2 f = __bfloat1622float2(h2[e]);
+                            const float2 f = p.fp16 ? __half22float2(g2[e]) : __bfloat1622float2(h2[e]);
                             dbacc[2 * e] += f.x;
                             dbacc[2 * e + 1] += f.y;
                         }
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
             for (int e = 0; e < 8; ++e) atomicAdd(&s_db[j * 8 + e], dbacc[e]);
             asm volatile("bar.sync 2, %0;" ::"n"(CS_NLW * 32) : "memory");
             const int t = threadIdx.x - 128;
-            if (t < CS_NB) atomicAdd(p.db + cob * CS_NB + t, s_db[t]);
+            if (t < CS_NB) atomicAdd(p.db + cob * CS_NB + t, s_db[t] * pow2i(-h16_shift(p.z_absmax)));
         }
         if (prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && w8 == 0)
             printf("[cs prof] loader warp 0: total %lld cyc, %lld stages: wait empty %lld, load %lld, norm/db/arrive %lld\n", clock64() - pf_t0,
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
     } else if (warp == CS_W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, N3, 1, 1);      // both operands MN-major
+            const uint32_t idesc = p.fp16 ? make_idesc_f16(128, N3, 1, 1) : make_idesc_bf16(128, N3, 1, 1);      // both operands MN-major
             // A: LBO = next 8 voxels (next tile row), SBO = next 8 channels (next plane; slices are consecutive planes)
             // B: LBO = next 8 voxels (next dz row), SBO = 128 B = next 8 output channels, and after four of them the next row
             const uint64_t ad = make_desc(0, CS_WP * 16, CS_PLANE), bd = make_desc(0, CS_ZROW, CS_TW * 16);
@@ -316,6 +319,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
         tc_fence_after();
         const int a = warp;                              // depth tap of this warp's 32 lanes (a == 3: ignored rows)
         const int taps = 27;
+        const float osc = pow2i(-h16_shift(p.x_absmax) - h16_shift(p.z_absmax));
         if (a < 3) {
             const int ci = chunk * 32 + lane;
             for (int c = 0; c < 3; ++c) {
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int co = cob * CS_NB + cb + i;
-                            atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * taps + tap, __uint_as_float(raw[i]));
+                            atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * taps + tap, __uint_as_float(raw[i]) * osc);
                         }
                     }
                 }
@@ -353,12 +357,9 @@ static bool wgrad_cs_shape(int Cin, int Cout, int kd, int kh, int kw) {
 
 using namespace b200em;
 
-extern "C" {
-
-int b200em_conv3d_wgrad_cs_supported(int Cin, int Cout, int kd, int kh, int kw) { return wgrad_cs_shape(Cin, Cout, kd, kh, kw) ? 1 : 0; }
-
-int b200em_conv3d_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw,
-                           float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream) {
+static int launch_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw,
+                           float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream, int fp16,
+                           const float* x_absmax, const float* z_absmax) {
     B2_CHECK_ARG(x && dz && dw && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_wgrad_cs: bad arguments");
     if (!wgrad_cs_shape(Cin, Cout, kd, kh, kw)) {
         set_error("conv3d_wgrad_cs: shape (%d -> %d, %dx%dx%d) not supported by the w-stacked tcgen05 weight gradient", Cin, Cout, kd, kh, kw);
@@ -370,6 +371,8 @@ int b200em_conv3d_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_sh
     WgradCsParams p;
     p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.dz = (const __nv_bfloat16*)dz; p.dz_ld = dz_ld;
     p.dw = dw; p.db = db;
+    p.fp16 = fp16; p.x_absmax = x_absmax; p.z_absmax = z_absmax;
+    B2_CHECK_ARG(!fp16 || !in_scale_shift, "conv3d_wgrad_cs: fp16 operands take no fused norm apply (b200em_cvt_f16 applies it)");
     p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
     p.nco = Cout / CS_NB;
     const int misc = CS_NB * 4 + (3 * CS_MAX_NS + 1) * 8 + 8 + 128;
@@ -435,10 +438,11 @@ int b200em_conv3d_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_sh
                 const cuuint64_t zdim[5] = {8, (cuuint64_t)W, (cuuint64_t)(Cout / 8), (cuuint64_t)H, (cuuint64_t)N * D};
                 const cuuint64_t zstr[4] = {(cuuint64_t)dz_ld * 2, 16, (cuuint64_t)W * dz_ld * 2, (cuuint64_t)H * W * dz_ld * 2};
                 const cuuint32_t zbox[5] = {8, (cuuint32_t)CS_TW, (cuuint32_t)(CS_NB / 8), (cuuint32_t)CS_HP, 1};
-                const CUresult r1 = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), xdim, xstr, xbox, estr,
+                const CUtensorMapDataType dt16 = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+                const CUresult r1 = encode(&tmx, dt16, 5, const_cast<void*>(x), xdim, xstr, xbox, estr,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                const CUresult r2 = encode(&tmz, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dz), zdim, zstr, zbox, estr,
+                const CUresult r2 = encode(&tmz, dt16, 5, const_cast<void*>(dz), zdim, zstr, zbox, estr,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) p.use_tma = 1;
@@ -448,6 +452,21 @@ int b200em_conv3d_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_sh
     conv3d_wgrad_cs_kernel<<<grid, CS_THREADS, smem_bytes, (cudaStream_t)stream>>>(p, tmx, tmz);
     B2_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" {
+
+int b200em_conv3d_wgrad_cs_supported(int Cin, int Cout, int kd, int kh, int kw) { return wgrad_cs_shape(Cin, Cout, kd, kh, kw) ? 1 : 0; }
+
+int b200em_conv3d_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw,
+                           float* db, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, void* stream) {
+    return launch_wgrad_cs(x, x_ld, in_scale_shift, dz, dz_ld, dw, db, N, D, H, W, Cin, Cout, kd, kh, kw, stream, 0, nullptr, nullptr);
+}
+
+int b200em_conv3d_wgrad_cs_h16(const void* x_f16, int64_t x_ld, const float* x_absmax, const void* dz_f16, int64_t dz_ld,
+                               const float* dz_absmax, float* dw, float* db, int N, int D, int H, int W, int Cin, int Cout, int kd,
+                               int kh, int kw, void* stream) {
+    return launch_wgrad_cs(x_f16, x_ld, nullptr, dz_f16, dz_ld, dw, db, N, D, H, W, Cin, Cout, kd, kh, kw, stream, 1, x_absmax, dz_absmax);
 }
 
 }  // extern "C"

@@ -243,6 +243,85 @@ split_bf16_kernel(const float* __restrict__ x, int64_t x_ld, const float* __rest
     }
 }
 
+// max |x| of an fp32 tensor (rows x C, pitch x_ld): one atomicMax per block on the bit pattern (non-negative floats order like
+// unsigned integers; a NaN ends up above +inf and switches the h16 scaling off, common.cuh h16_shift) -- and, in the same pass,
+// the per-channel sums (the bias gradient, taken from the fp32 values like autograd does, not from the fp16 copies).
+// Block = (bx channel vectors, by rows); a thread owns channel vectors tx, tx + bx, ... (at most 4).
+__global__ void __launch_bounds__(256)
+absmax_f32_kernel(const float* __restrict__ x, int64_t x_ld, int64_t rows, int C, unsigned* __restrict__ out, float* __restrict__ colsum) {
+    const int cvec = C / 4, bx = blockDim.x, by = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
+    unsigned m = 0;
+    float4 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t row = (int64_t)blockIdx.x * by + ty; row < rows; row += (int64_t)gridDim.x * by) {
+        const float* xr = x + row * x_ld;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cv = tx + k * bx;
+            if (cv < cvec) {
+                const float4 v = *reinterpret_cast<const float4*>(xr + cv * 4);
+                m = max(max(m, __float_as_uint(v.x) & 0x7fffffffu), __float_as_uint(v.y) & 0x7fffffffu);
+                m = max(max(m, __float_as_uint(v.z) & 0x7fffffffu), __float_as_uint(v.w) & 0x7fffffffu);
+                acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+            }
+        }
+    }
+    const int tid = ty * bx + tx;
+    __shared__ unsigned s_m;
+    extern __shared__ float s_col[];                       // [C] when colsum
+    if (tid == 0) s_m = 0u;
+    if (colsum)
+        for (int i = tid; i < C; i += bx * by) s_col[i] = 0.f;
+    __syncthreads();
+    if (m) atomicMax(&s_m, m);
+    if (colsum) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cv = tx + k * bx;
+            if (cv < cvec) {
+                atomicAdd(&s_col[cv * 4], acc[k].x); atomicAdd(&s_col[cv * 4 + 1], acc[k].y);
+                atomicAdd(&s_col[cv * 4 + 2], acc[k].z); atomicAdd(&s_col[cv * 4 + 3], acc[k].w);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && s_m) atomicMax(out, s_m);
+    if (colsum)
+        for (int i = tid; i < C; i += bx * by) atomicAdd(colsum + i, s_col[i]);
+}
+
+// fp32 -> fp16 operand copy of the h16 path: out = fp16(2^k * (scale*x + shift)), k from the device absmax (common.cuh)
+__global__ void __launch_bounds__(256)
+cvt_f16_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ ss, const float* __restrict__ absmax,
+               __half* __restrict__ out, int64_t S, int C) {
+    const int64_t n = blockIdx.y;
+    const unsigned cvec = C / 8;
+    const int64_t total = S * cvec;
+    const float mul = pow2i(h16_shift(absmax));
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % cvec);
+        const int64_t vox = n * S + i / cvec;
+        const float4 a = *reinterpret_cast<const float4*>(x + vox * x_ld + cv * 8);
+        const float4 b = *reinterpret_cast<const float4*>(x + vox * x_ld + cv * 8 + 4);
+        float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (ss) {
+            const float4* q = reinterpret_cast<const float4*>(ss + ((size_t)n * C + cv * 8) * 2);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 t = __ldg(q + e);
+                f[2 * e] = fmaf(f[2 * e], t.x, t.y);
+                f[2 * e + 1] = fmaf(f[2 * e + 1], t.z, t.w);
+            }
+        }
+        uint4 o;
+        __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e] * mul, f[2 * e + 1] * mul);
+        *reinterpret_cast<uint4*>(out + vox * C + cv * 8) = o;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // max pool forward (+ statistics of the pooled output)
 // F2 = 1: factor (2,2,2) or (1,2,2) known at compile time (FDC = depth factor): the window loads are unrolled and in flight together
@@ -1002,6 +1081,30 @@ int b200em_split_bf16(const float* x, int64_t x_ld, const float* in_scale_shift,
     B2_CHECK_ARG(C % 4 == 0 && x_ld % 4 == 0 && aligned16(x) && aligned16(hi) && aligned16(lo), "split_bf16: needs C % 4 == 0 and 16-byte aligned tensors");
     split_bf16_kernel<<<dim3(flat_grid(S * (C / 4), 256, N), N), 256, 0, (cudaStream_t)stream>>>(x, x_ld, in_scale_shift, (__nv_bfloat16*)hi,
                                                                                                 (__nv_bfloat16*)lo, S, C);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_absmax_f32(const float* x, int64_t x_ld, int64_t rows, int C, float* absmax, float* colsum, void* stream) {
+    B2_CHECK_ARG(x && absmax && rows > 0 && C > 0, "absmax_f32: bad arguments");
+    B2_CHECK_ARG(C % 4 == 0 && x_ld % 4 == 0 && aligned16(x) && C <= 4096, "absmax_f32: needs C % 4 == 0, C <= 4096 and a 16-byte aligned tensor");
+    const int cvec = C / 4;
+    const int bx = cvec < 256 ? cvec : 256;                   // a thread owns up to 4 channel vectors: cvec <= 1024
+    const int by = 256 / bx;
+    int64_t blocks = (rows + by - 1) / by;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    absmax_f32_kernel<<<(unsigned)blocks, dim3(bx, by), colsum ? C * sizeof(float) : 0, (cudaStream_t)stream>>>(
+        x, x_ld, rows, C, reinterpret_cast<unsigned*>(absmax), colsum);
+    B2_LAUNCH_CHECK();
+    return 0;
+}
+
+int b200em_cvt_f16(const float* x, int64_t x_ld, const float* in_scale_shift, const float* absmax, void* out, int N, int64_t S,
+                   int C, void* stream) {
+    B2_CHECK_ARG(x && out && N > 0 && S > 0 && C > 0 && N <= 65535, "cvt_f16: bad arguments");
+    B2_CHECK_ARG(C % 8 == 0 && x_ld % 4 == 0 && aligned16(x) && aligned16(out), "cvt_f16: needs C % 8 == 0 and 16-byte aligned tensors");
+    cvt_f16_kernel<<<dim3(flat_grid(S * (C / 8), 256, N), N), 256, 0, (cudaStream_t)stream>>>(x, x_ld, in_scale_shift, absmax, (__half*)out, S, C);
     B2_LAUNCH_CHECK();
     return 0;
 }

@@ -1,6 +1,9 @@
 // Haloed NDHWC tile -> shared memory in the tcgen05 SWIZZLE_NONE core-matrix layout (shared by the conv kernels).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <type_traits>
 #include <stdint.h>
 
 namespace b200em {
@@ -62,6 +65,15 @@ __device__ __forceinline__ void affine_unit(uint4& val, const float* sc, const f
         float* f = reinterpret_cast<float*>(&val);
 #pragma unroll
         for (int e = 0; e < 4; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+    } else if constexpr (std::is_same<T, __half>::value) {
+        __half2* h2 = reinterpret_cast<__half2*>(&val);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 f = __half22float2(h2[e]);
+            f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
+            f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+            h2[e] = __floats2half2_rn(f.x, f.y);
+        }
     } else {
         __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
 #pragma unroll

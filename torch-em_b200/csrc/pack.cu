@@ -7,7 +7,7 @@
 // costs less than the ~40 per-weight launches it replaces (the images are 2 bytes per weight element).
 //
 // Layouts (see conv_umma.cu / conv_umma_ds.cu):
-//   plain          [nblk][chunk][tap][plane j][NPb][8]
+//   plain          [nblk][chunk][tap][plane j][NPb][8]      (bf16, or IEEE fp16 for the h16 path: B200EM_PACK_PLAIN_F16)
 //   depth-stacked  [chunk][tap (b,c)][plane j][a*Nc + n][8]
 // dgrad = 1 packs the transposed, tap-flipped filter (the data gradient is a forward conv with it).
 // One block per (8 output channels x 8 input channels) tile of one job: the 8 x 8 x taps fp32 sub-filter is read as 8
@@ -68,16 +68,18 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const b200em_pack_job* 
     for (int u = threadIdx.x; u < 8 * taps; u += blockDim.x) {
         const int nl = u % 8, tp = u / 8;              // n within the tile, filter tap (torch order)
         __align__(16) __nv_bfloat16 v[8];
+        const bool f16 = job.layout == B200EM_PACK_PLAIN_F16;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             // forward: n = co, k = ci;  dgrad: n = ci, k = co
             const float f = dgrad ? tile[e][nl * taps + tp] : tile[nl][e * taps + tp];
-            v[e] = __float2bfloat16_rn(f);
+            if (f16) reinterpret_cast<__half*>(v)[e] = __float2half_rn(f);
+            else v[e] = __float2bfloat16_rn(f);
         }
         const int n_ = (dgrad ? ci0 : co0) + nl, k0 = dgrad ? co0 : ci0, t_ = dgrad ? taps - 1 - tp : tp;
         const int chunk = k0 / CC, j = (k0 % CC) / 8;
         size_t o;
-        if (job.layout == B200EM_PACK_PLAIN) {
+        if (job.layout == B200EM_PACK_PLAIN || f16) {
             const int NPb = job.NPb;
             const int nb = n_ / NPb, nn = n_ % NPb;
             o = ((((size_t)(nb * nchunks + chunk) * taps + t_) * J + j) * NPb + nn) * 8;
@@ -104,7 +106,7 @@ int b200em_pack_batch_prepare(b200em_pack_job* jobs, int njobs, int* total_block
                      "pack_batch_prepare: job %d: channels must be multiples of 8 and taps <= 27", i);
         const int n_ = j.dgrad ? j.Cin : j.Cout, k_ = j.dgrad ? j.Cout : j.Cin;   // operand's output / reduction channels
         bool ok;
-        if (j.layout == B200EM_PACK_PLAIN || j.layout == B200EM_PACK_PLAIN_TF32) {
+        if (j.layout == B200EM_PACK_PLAIN || j.layout == B200EM_PACK_PLAIN_TF32 || j.layout == B200EM_PACK_PLAIN_F16) {
             ok = umma_pack_layout(k_, n_, j.kd, j.kh, j.kw, &j.CC, &j.NPb, j.layout == B200EM_PACK_PLAIN_TF32);
         } else if (j.layout == B200EM_PACK_DEPTH_STACKED) {
             j.NPb = 0;

@@ -2,7 +2,10 @@
 // Inline PTX only -- no CUTLASS.  Everything here is cta_group::1 (one CTA per MMA).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 namespace b200em {
 namespace umma {
@@ -177,7 +180,8 @@ __device__ __forceinline__ void umma_tf32_c(uint32_t tmem_d, uint32_t a_lo, uint
     }
 }
 
-// Operand-type dispatch of the issue loops: __nv_bfloat16 -> kind::f16 (K = 16), float -> kind::tf32 (K = 8).
+// Operand-type dispatch of the issue loops: __nv_bfloat16 / __half -> kind::f16 (K = 16; the instruction descriptor names the
+// format), float -> kind::tf32 (K = 8).
 template <typename TA, bool ACC>
 __device__ __forceinline__ void umma_c(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
     if constexpr (sizeof(TA) == 4) umma_tf32_c<ACC>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc);
@@ -202,6 +206,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with IEEE fp16 A and B (format code 0): the "h16" path of fp32 activations -- fp16 carries the same 11-bit
+// significand as TF32 (the precision torch / cuDNN use for fp32 convolutions), at the bf16 MMA rate (twice kind::tf32).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
+    return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // kind::tf32: TF32 A and B (format code 2 at bits [7,10) and [10,13)), fp32 accumulator.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -209,7 +219,9 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
 }
 template <typename TA>
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
-    return sizeof(TA) == 4 ? make_idesc_tf32(M, N, a_mn_major, b_mn_major) : make_idesc_bf16(M, N, a_mn_major, b_mn_major);
+    return sizeof(TA) == 4 ? make_idesc_tf32(M, N, a_mn_major, b_mn_major)
+                           : (std::is_same<TA, __half>::value ? make_idesc_f16(M, N, a_mn_major, b_mn_major)
+                                                              : make_idesc_bf16(M, N, a_mn_major, b_mn_major));
 }
 
 // TMEM -> registers: this warp's 32 lanes (lane field of taddr = 32 * (warp_id % 4)), 32 / 16 consecutive columns

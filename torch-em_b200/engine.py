@@ -233,8 +233,8 @@ def _run_block(B, plan, P, bufs, spec: BlockSpec, x_in, sums_in, out, want_out_s
     sums2 = None
     if want_out_sums and norm is not None:
         sums2 = torch.zeros((N, c2.cout, 2), dtype=torch.float32, device=dev)
-    B.conv(y1, ss2, packs[c2.key], P[c2.key + ".bias"], out, sums2, c2.kernel, relu=True, dgrad=False)
-    rec.update(ss1=ss1, mr1=mr1, y1=y1, ss2=ss2, mr2=mr2, y2=out, aux1=aux1, m1=m1, m2=m2)
+    aux2 = B.conv(y1, ss2, packs[c2.key], P[c2.key + ".bias"], out, sums2, c2.kernel, relu=True, dgrad=False)
+    rec.update(ss1=ss1, mr1=mr1, y1=y1, ss2=ss2, mr2=mr2, y2=out, aux1=aux1, aux2=aux2, m1=m1, m2=m2)
     ctx.blocks[spec.prefix] = rec
     return sums2
 
@@ -393,7 +393,7 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
         return out
 
     # conv2
-    B.wgrad(y1, rec["ss2"], dz2, grads[c2.key + ".weight"], grads[c2.key + ".bias"], c2.kernel)
+    B.wgrad(y1, rec["ss2"], dz2, grads[c2.key + ".weight"], grads[c2.key + ".bias"], c2.kernel, aux=rec.get("aux2"))
     dz1 = dgrad_and_norm_back(dz2, c2, y1, rec["mr2"], rec["m2"], spec.norm2_key, torch.empty_like(y1), relu_mask=1)
     # conv1
     B.wgrad(x_in, rec["ss1"], dz1, grads[c1.key + ".weight"], grads[c1.key + ".bias"], c1.kernel, aux=rec.get("aux1"))
