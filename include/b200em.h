@@ -41,6 +41,13 @@ int b200em_device_info(int* sm_count, int* cc_major, int* cc_minor, int* umma_ok
 int64_t b200em_launch_count(void);
 void b200em_reset_launch_count(void);
 
+/* Registers a caller-owned scratch buffer for the CURRENT device (NULL, 0 unregisters).  It must be zero-filled when it is
+ * registered and must only be used by one stream at a time; kernels that use it restore it to all-zero before they finish.
+ * With a workspace the tcgen05 conv kernels split the reduction (input-channel chunks) of layers that have fewer output tiles
+ * than SMs over several CTAs (partial sums added into the workspace, the last CTA of a tile runs the epilogue); without one
+ * they run unsplit.  Recommended size: 64 MiB. */
+int b200em_set_workspace(void* workspace, int64_t bytes);
+
 /* ---- layout ------------------------------------------------------------------------------------------- */
 /* NCDHW fp32 network input -> NDHWC activations (replaces nothing in the reference: it keeps NCDHW). */
 int b200em_ncdhw_to_ndhwc(const float* x, void* y, int y_dtype, int64_t y_ld, int N, int C, int64_t S, void* stream);

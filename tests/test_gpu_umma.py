@@ -100,6 +100,49 @@ def test_umma_conv_forward_and_dgrad(B, case):
     np.testing.assert_allclose(d.cpu().numpy(), d_ref.numpy(), rtol=1e-2, atol=2e-2 * float(d_ref.abs().max()))
 
 
+@pytest.mark.parametrize("ks", ["1", "2", "3", "7"])
+@pytest.mark.parametrize("case", [(1, 4, 8, 8, 128, 256, (3, 3, 3)), (2, 6, 13, 9, 96, 48, (3, 3, 3)), (1, 2, 4, 4, 512, 128, (1, 3, 3)),
+                                  (1, 8, 8, 8, 256, 128, (1, 1, 1))])
+def test_plain_conv_split_k(case, ks, monkeypatch):
+    """Split-K of the plain kernel (layers with fewer output tiles than SMs): ks CTAs reduce disjoint Cin-chunk ranges of a tile
+    through the registered workspace, the last one runs the epilogue (bias, ReLU, statistics / norm-backward reductions).  Forced
+    factors incl. ones that do not divide the chunk count; the workspace must be all-zero again afterwards."""
+    from torch_em_b200.backend import CudaBackend
+    monkeypatch.setenv("B200EM_KSPLIT", ks)
+    B = CudaBackend(use_ds=False, use_cs=False)
+    N, D, H, W, Cin, Cout, k = case
+    x = rnd((N, D, H, W, Cin), 1).bfloat16()
+    w = rnd((Cout, Cin) + k, 2, scale=(Cin * k[0] * k[1] * k[2]) ** -0.5)
+    wq = w.bfloat16().float()
+    b = rnd((Cout,), 3)
+    ss = torch.stack([1 + 0.1 * rnd((N, Cin), 4), 0.1 * rnd((N, Cin), 5)], -1).contiguous()
+    pk = B.pack(("splitk-test", case), w.to(DEV))
+    xin = (x.float() * ss[:, None, None, None, :, 0] + ss[:, None, None, None, :, 1]).bfloat16()
+    y_ref = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16)
+    s_ref = torch.zeros((N, Cout, 2))
+    EMU.conv(xin, None, P(wq), b, y_ref, s_ref, k, True, False)
+    for _ in range(2):                               # twice: the second run sees the workspace the first one left behind
+        y = torch.empty((N, D, H, W, Cout), dtype=torch.bfloat16, device=DEV)
+        s = torch.zeros((N, Cout, 2), device=DEV)
+        B.conv(x.to(DEV), ss.to(DEV), pk, b.to(DEV), y, s, k, True, False)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(y.float().cpu().numpy(), y_ref.float().numpy(), rtol=1e-2, atol=1e-2)
+        np.testing.assert_allclose(s.cpu().numpy(), s_ref.numpy(), rtol=5e-3, atol=0.5)
+        assert not bool(B._workspaces[0].any()), "split-K must leave the workspace all-zero"
+    dz = rnd((N, D, H, W, Cout), 6).bfloat16()
+    g_ref = torch.empty((N, D, H, W, Cin), dtype=torch.bfloat16)
+    EMU.conv(dz, None, P(wq), None, g_ref, None, k, False, True)
+    d_ref = torch.zeros((N, Cin, 2))
+    EMU.channel_dot_sums(g_ref, x, d_ref)
+    g = torch.empty((N, D, H, W, Cin), dtype=torch.bfloat16, device=DEV)
+    d = torch.zeros((N, Cin, 2), device=DEV)
+    B.conv(dz.to(DEV), None, pk, None, g, d, k, False, True, dot_x=x.to(DEV))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(g.float().cpu().numpy(), g_ref.float().numpy(), rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(d.cpu().numpy(), d_ref.numpy(), rtol=1e-2, atol=2e-2 * float(d_ref.abs().max()))
+    assert not bool(B._workspaces[0].any())
+
+
 @pytest.mark.parametrize("tma", ["1", "0"])
 @pytest.mark.parametrize("case", [(2, 24, 48, 40, 64, 32, (3, 3, 3)), (2, 24, 48, 40, 32, 32, (3, 3, 3))])
 def test_dstacked_many_items_per_cta(case, tma, monkeypatch):

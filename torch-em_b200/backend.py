@@ -226,11 +226,13 @@ class PackSet:
 class CudaBackend:
     name = "cuda"
 
-    def __init__(self, use_umma=True, use_ds=True, use_cs=True, use_tf32=None, use_h16=True):
+    def __init__(self, use_umma=True, use_ds=True, use_cs=True, use_tf32=None, use_h16=True, use_splitk=True):
         self.use_umma = use_umma
         self.use_tf32 = use_tf32    # None: follow torch.backends.cudnn.allow_tf32 (True by default, like the reference's fp32 runs)
+        self.use_splitk = use_splitk
         self.use_h16 = use_h16      # TF32-class arithmetic through fp16 operand copies at the bf16 MMA rate (False: kind::tf32 kernels)
         self._h16_recent = []       # [(tensor, H16Operand)]: the last two un-normalised fp32 tensors converted (dz feeds wgrad AND dgrad)
+        self._workspaces = {}       # device index -> zero-filled scratch registered with the library (split-K partial sums)
         self.use_ds = use_ds and use_umma
         self.use_cs = use_cs and use_umma
         self.timing = None          # {family: [(start_event, end_event, work), ...]} while bench.py measures
@@ -265,6 +267,19 @@ class CudaBackend:
         if not self.use_umma:
             return False
         return torch.backends.cudnn.allow_tf32 if self.use_tf32 is None else bool(self.use_tf32)
+
+    WORKSPACE_BYTES = 65 << 20
+
+    def ensure_workspace(self, device):
+        """Registers (once per device) the zero-filled scratch the conv kernels use to split the reduction of layers with fewer
+        output tiles than SMs (b200em_set_workspace).  The kernels leave it all-zero; it is used by one stream at a time -- the
+        schedule runs every conv of a device on that device's current stream."""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in self._workspaces:
+            with torch.cuda.device(idx):
+                ws = torch.zeros(self.WORKSPACE_BYTES, dtype=torch.uint8, device=torch.device("cuda", idx))
+                call("b200em_set_workspace", _ptr(ws), ws.numel())
+            self._workspaces[idx] = ws
 
     def h16_enabled(self):
         """fp32 activations with TF32 allowed run as fp16 operand copies (same 11-bit significand as TF32, round-to-nearest, exact
@@ -384,6 +399,8 @@ class CudaBackend:
         xp, xld = _act(x)
         yp, yld = _act(y)
         assert _dt(x) == _dt(y)
+        if self.use_umma and self.use_splitk:
+            self.ensure_workspace(x.device)
         b = bias.detach() if bias is not None else None
         kd, kh, kw = kernel
         flops = 2.0 * N * D * H * W * Cin * Cout * kd * kh * kw
@@ -628,5 +645,5 @@ def default_backend():
         _lib.load()
         import os
         _default = CudaBackend(use_ds=os.environ.get("B200EM_DS", "1") == "1", use_cs=os.environ.get("B200EM_CS", "1") == "1",
-                               use_h16=os.environ.get("B200EM_H16", "1") == "1")
+                               use_h16=os.environ.get("B200EM_H16", "1") == "1", use_splitk=os.environ.get("B200EM_SPLITK", "1") == "1")
     return _default

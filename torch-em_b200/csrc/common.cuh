@@ -43,6 +43,9 @@ void count_launch(int n = 1);
     } while (0)
 
 int sm_count();
+// the caller-provided zero-initialised scratch of the current device (b200em_set_workspace), false if none is registered
+constexpr int WS_COUNTER_BYTES = 1 << 20;
+bool get_workspace(float** acc, int64_t* acc_floats, unsigned** counters, int* ncounters);
 
 // ---- scalar conversion ----------------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);

@@ -31,7 +31,7 @@ namespace {
 constexpr int TH = 16, TW = 8;             // voxel tile (h, w) = 128 GEMM rows
 constexpr int HP = TH + 2, WP = TW + 2;     // haloed tile
 constexpr int PLANE = HP * WP * 16 + 16;    // bytes per (slice, 8-channel group) plane; +16 staggers banks
-constexpr int NSTAGE = 4;                   // weight ring depth
+constexpr int NSTAGE = 4;                   // maximum weight ring depth (the launch picks p.nstage <= NSTAGE)
 constexpr int NLOAD = 256;                  // operand-loader threads (8 warps): the tile load is latency-bound, more threads = more bytes in flight
 constexpr int THREADS = 128 + NLOAD + 64;   // 4 epilogue warps | 8 loader warps | weight-loader warp | MMA warp
 constexpr int W_WLOAD = (128 + NLOAD) / 32, W_MMA = W_WLOAD + 1;
@@ -51,9 +51,11 @@ struct ConvUmmaParams {
     float* sums;
     const void* dot_x; long long dot_ld;   // non-null: sums = (sum y, sum y * dot_x) -- the norm-backward reductions
     const float* x_absmax;                 // h16 path: device max |x| the fp16 operand was scaled by (common.cuh h16_shift), or null
+    int ksplit;                            // > 1: gridDim.z CTAs share an output tile, each reducing a range of the Cin chunks (split-K)
+    float* ws_acc; unsigned* ws_cnt;       // split-K: zeroed fp32 partial sums [voxel][Cout] and per-(item, nblk) arrival counters
     int N, D, H, W, Cin, Cout;
     int kd, kh, kw, relu;
-    int R, NP, CC, nchunks, G, acc_bufs;
+    int R, NP, CC, nchunks, G, acc_bufs, nstage;
     int tiles_w, tiles_h, tiles_d;
     long long items;
     int a_bytes, b_stage_bytes;
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
     // carve: A[2] | B[NSTAGE] | bias[NP] | sums[2*NP] | barriers | tmem ptr
     uint8_t* smA = smem;
     uint8_t* smB = smA + 2 * p.a_bytes;
-    float* s_bias = reinterpret_cast<float*>(smB + NSTAGE * p.b_stage_bytes);
+    float* s_bias = reinterpret_cast<float*>(smB + p.nstage * p.b_stage_bytes);
     float* s_sums = s_bias + p.NP;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_sums + 2 * p.NP);
     uint64_t* a_full = bars;             // [2]   128 loader arrivals
@@ -134,6 +136,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = blockIdx.y;                    // NP-wide output-channel block
+    // split-K: this CTA reduces the Cin chunks [c_begin, c_end) of its tiles
+    const int c_begin = p.ksplit > 1 ? (int)((blockIdx.z * p.nchunks) / p.ksplit) : 0;
+    const int c_end = p.ksplit > 1 ? (int)(((blockIdx.z + 1) * p.nchunks) / p.ksplit) : p.nchunks;
     constexpr int J = KC_ * 2;                      // 8-channel planes per slice per chunk
     const int taps = p.kd * p.kh * p.kw;
     const int ngroups = taps / p.G;
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
             int n, d0, h0, w0;
             item_coords(p, item, n, d0, h0, w0);
-            for (int c = 0; c < p.nchunks; ++c, ++fill) {
+            for (int c = c_begin; c < c_end; ++c, ++fill) {
                 const int buf = fill & 1;
                 mbar_wait(&a_empty[buf], ((fill >> 1) & 1) ^ 1);
                 const int ch0 = c * p.CC + j * EPU;
@@ -200,14 +205,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
             const uint32_t bytes = (uint32_t)p.b_stage_bytes;
             const size_t tap_elems = (size_t)J * p.NP * 16;          // BYTES per (chunk, tap) block of the packed operand
             const uint8_t* wblk = reinterpret_cast<const uint8_t*>(p.w) + (size_t)nblk * p.nchunks * taps * tap_elems;
-            uint32_t cnt = 0;
+            int st = 0;
+            uint32_t ph = 0;                              // ring position and lap parity
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x)
-                for (int c = 0; c < p.nchunks; ++c)
-                    for (int g = 0; g < ngroups; ++g, ++cnt) {
-                        const int st = cnt % NSTAGE;
-                        mbar_wait(&b_empty[st], ((cnt / NSTAGE) & 1) ^ 1);
+                for (int c = c_begin; c < c_end; ++c)
+                    for (int g = 0; g < ngroups; ++g) {
+                        mbar_wait(&b_empty[st], ph ^ 1);
                         mbar_arrive_expect_tx(&b_full[st], bytes);
                         bulk_g2s(smB + st * p.b_stage_bytes, wblk + ((size_t)c * taps + (size_t)g * p.G) * tap_elems, bytes, &b_full[st]);
+                        if (++st == p.nstage) { st = 0; ph ^= 1; }
                     }
         }
     } else if (warp == W_MMA) {
@@ -224,7 +230,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
             constexpr uint32_t SLAB16 = J * (PLANE / 16), K16 = 2 * (PLANE / 16);
             const uint32_t np = (uint32_t)p.NP, b_tap16 = (uint32_t)(J * p.NP), bk16 = 2 * np;
             const uint32_t a_bytes16 = (uint32_t)(p.a_bytes >> 4), bstage16 = (uint32_t)(p.b_stage_bytes >> 4);
-            uint32_t fill = 0, cnt = 0, it = 0;
+            uint32_t fill = 0, it = 0;
+            int st = 0;
+            uint32_t ph = 0;                             // weight ring position and lap parity
             bool a_ok = false, b_ok = false;             // results of the early probes of the next a_full / b_full barriers
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
                 const int slot = (p.acc_bufs == 2) ? (it & 1) : 0;
@@ -234,26 +242,27 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                 uint32_t tcol[R_];
 #pragma unroll
                 for (int r = 0; r < R_; ++r) tcol[r] = tmem_base + slot * acc_cols + r * np;
-                for (int c = 0; c < p.nchunks; ++c, ++fill) {
+                for (int c = c_begin; c < c_end; ++c, ++fill) {
                     const int buf = fill & 1;
                     if (!a_ok) mbar_wait(&a_full[buf], (fill >> 1) & 1);
                     tc_fence_after();
                     a_ok = mbar_test_wait(&a_full[(fill + 1) & 1], ((fill + 1) >> 1) & 1);
                     const uint32_t abuf = a_lo_base + buf * a_bytes16;
-                    for (int g = 0; g < ngroups; ++g, ++cnt) {
-                        const int st = cnt % NSTAGE;
-                        if (!b_ok) mbar_wait(&b_full[st], (cnt / NSTAGE) & 1);
+                    for (int g = 0; g < ngroups; ++g) {
+                        if (!b_ok) mbar_wait(&b_full[st], ph);
                         tc_fence_after();
+                        const int st_n = st + 1 == p.nstage ? 0 : st + 1;
+                        const uint32_t ph_n = st_n == 0 ? ph ^ 1 : ph;
                         // early probe of the next weight stage: a probe costs ~200 cycles of latency even when the barrier is
                         // complete, so it is issued before this stage's MMAs and consumed after them
-                        b_ok = mbar_test_wait(&b_full[(cnt + 1) % NSTAGE], ((cnt + 1) / NSTAGE) & 1);
+                        b_ok = mbar_test_wait(&b_full[st_n], ph_n);
                         const uint32_t bst = b_lo_base + st * bstage16;
                         for (int tg = 0; tg < p.G; ++tg) {
                             const int tap = g * p.G + tg;
                             const uint32_t a0 = abuf + s_tap[tap];
                             const uint32_t b0 = bst + tg * b_tap16;
                             // slabs beyond the volume (d0 + r >= D) read zero-filled slices: computed, never stored
-                            if ((c | tap) == 0) {
+                            if (c == c_begin && tap == 0) {
 #pragma unroll
                                 for (int r = 0; r < R_; ++r) {
                                     umma_c<TA, false>(tcol[r], a0 + r * SLAB16, a_hi, b0, b_hi, idesc);
@@ -268,6 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                             }
                         }
                         umma_commit(&b_empty[st]);
+                        st = st_n; ph = ph_n;
                     }
                     umma_commit(&a_empty[buf]);
                 }
@@ -279,6 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
         const int row = warp * 32 + lane;            // GEMM row = TMEM lane
         const int hl = row / TW, wl = row % TW;
         const float osc = pow2i(-h16_shift(p.x_absmax));     // undo the power-of-two operand scaling (1 when there is none)
+        const bool split = p.ksplit > 1;
         uint32_t it = 0;
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
             int n, d0, h0, w0;
@@ -290,15 +301,65 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
             const int gh = h0 + hl, gw = w0 + wl;
             const bool valid_hw = gh < p.H && gw < p.W;
             const int rmax = min(p.R, p.D - d0);
+            if (split) {
+                // split-K, phase 1: add this CTA's partial accumulators into the fp32 workspace ([voxel][Cout], all zero between
+                // launches), release the TMEM slot, and count the arrival; only the LAST CTA of the tile goes on to the epilogue
+                // proper, reading the complete sums back from the workspace (and clearing them again).
+                for (int r = 0; r < rmax; ++r) {
+                    float* wrow = p.ws_acc + ((((size_t)n * p.D + d0 + r) * p.H + gh) * p.W + gw) * p.Cout + nblk * p.NP;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * acc_cols + r * p.NP;
+                    for (int cb = 0; cb < p.NP; cb += 16) {
+                        uint32_t raw[16];
+                        tmem_ld16(taddr + cb, raw);
+                        tmem_ld_wait();
+                        if (valid_hw) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + cb + 4 * q), "f"(__uint_as_float(raw[4 * q])),
+                                             "f"(__uint_as_float(raw[4 * q + 1])), "f"(__uint_as_float(raw[4 * q + 2])), "f"(__uint_as_float(raw[4 * q + 3]))
+                                             : "memory");
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[slot]);
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 0) {
+                    unsigned* cnt = p.ws_cnt + (size_t)item * gridDim.y + nblk;
+                    const unsigned old = atomicAdd(cnt, 1u);
+                    const bool last = old == (unsigned)p.ksplit - 1u;
+                    if (last) *cnt = 0u;                 // all arrivals are in: leave the counter zero for the next launch
+                    s_tmem[1] = last ? 1u : 0u;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const bool last = *reinterpret_cast<volatile uint32_t*>(&s_tmem[1]) != 0u;
+                asm volatile("bar.sync 1, 128;" ::: "memory");     // everybody has read the flag before the next item overwrites it
+                if (!last) continue;
+                __threadfence();
+            }
             for (int r = 0; r < rmax; ++r) {
                 const int gd = d0 + r;
-                TO* yp = reinterpret_cast<TO*>(p.y) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.y_ld + nblk * p.NP;
+                const size_t vox = (((size_t)n * p.D + gd) * p.H + gh) * p.W + gw;
+                TO* yp = reinterpret_cast<TO*>(p.y) + vox * p.y_ld + nblk * p.NP;
+                float* wrow = split ? p.ws_acc + vox * p.Cout + nblk * p.NP : nullptr;
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * acc_cols + r * p.NP;
                 for (int cb = 0; cb < p.NP; cb += 32) {
                     if (p.NP - cb >= 32) {
                         uint32_t raw[32];
-                        tmem_ld32(taddr + cb, raw);
-                        tmem_ld_wait();
+                        if (split) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 t4 = valid_hw ? __ldcg(reinterpret_cast<const float4*>(wrow + cb) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                raw[4 * q] = __float_as_uint(t4.x); raw[4 * q + 1] = __float_as_uint(t4.y);
+                                raw[4 * q + 2] = __float_as_uint(t4.z); raw[4 * q + 3] = __float_as_uint(t4.w);
+                                if (valid_hw) __stcg(reinterpret_cast<float4*>(wrow + cb) + q, make_float4(0.f, 0.f, 0.f, 0.f));
+                            }
+                        } else {
+                            tmem_ld32(taddr + cb, raw);
+                            tmem_ld_wait();
+                        }
                         float v[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -310,7 +371,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         if (p.sums) {
                             float s1[32], s2[32];
                             if (p.dot_x) {
-                                const TO* xq = reinterpret_cast<const TO*>(p.dot_x) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
+                                const TO* xq = reinterpret_cast<const TO*>(p.dot_x) + vox * p.dot_ld + nblk * p.NP + cb;
                                 load_row<TO, 32>(xq, valid_hw, s2);
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] *= s1[i]; }
@@ -325,8 +386,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         }
                     } else {   // 16-column tail (NP % 32 == 16)
                         uint32_t raw[16];
-                        tmem_ld16(taddr + cb, raw);
-                        tmem_ld_wait();
+                        if (split) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 t4 = valid_hw ? __ldcg(reinterpret_cast<const float4*>(wrow + cb) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                raw[4 * q] = __float_as_uint(t4.x); raw[4 * q + 1] = __float_as_uint(t4.y);
+                                raw[4 * q + 2] = __float_as_uint(t4.z); raw[4 * q + 3] = __float_as_uint(t4.w);
+                                if (valid_hw) __stcg(reinterpret_cast<float4*>(wrow + cb) + q, make_float4(0.f, 0.f, 0.f, 0.f));
+                            }
+                        } else {
+                            tmem_ld16(taddr + cb, raw);
+                            tmem_ld_wait();
+                        }
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -338,7 +409,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         if (p.sums) {
                             float s1[16], s2[16];
                             if (p.dot_x) {
-                                const TO* xq = reinterpret_cast<const TO*>(p.dot_x) + ((((size_t)n * p.D + gd) * p.H + gh) * p.W + gw) * p.dot_ld + nblk * p.NP + cb;
+                                const TO* xq = reinterpret_cast<const TO*>(p.dot_x) + vox * p.dot_ld + nblk * p.NP + cb;
                                 load_row<TO, 16>(xq, valid_hw, s2);
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) { s1[i] = valid_hw ? v[i] : 0.f; s2[i] *= s1[i]; }
@@ -356,9 +427,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[slot]);
+            if (!split) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[slot]);
+            }
             if (p.sums) {
                 // flush this item's per-channel partial sums (n may change with the next item)
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -415,8 +488,27 @@ __global__ void __launch_bounds__(256) pack_umma_weights_kernel(const float* __r
 }
 
 struct UmmaShape {
-    int CC, NP, nblk, R, G, acc_bufs, a_bytes, b_stage_bytes, smem_bytes;
+    int CC, NP, nblk, R, G, acc_bufs, nstage, a_bytes, b_stage_bytes, smem_bytes;
 };
+
+// Weight ring of a (R, NP, CC) configuration: G filter taps per stage and the ring depth.  The single issuing thread pays a fixed
+// ~500 cycles per stage hand-off (barrier probe, commit, fence), so a stage should carry well over 500 cycles of MMAs: three taps
+// per stage whenever >= 3 stages of them fit beside the two activation buffers, else one tap and four stages.
+static void umma_ring(UmmaShape& s, int taps, int kd, int planes_per_slice) {
+    const int fixed = s.NP * 4 * 3 + 16 * 8 + 16 + 27 * 4 + 128;
+    s.a_bytes = (s.R + kd - 1) * planes_per_slice * PLANE;
+    static const int g_env = [] { const char* e = getenv("B200EM_UMMA_G"); return e ? atoi(e) : 0; }();      // bring-up: force taps per stage
+    for (int G = (taps % 3 == 0 && g_env != 1) ? 3 : 1; G >= 1; G -= 2) {
+        s.G = G;
+        s.b_stage_bytes = G * planes_per_slice * s.NP * 16;
+        int ns = (MAX_SMEM - fixed - 2 * s.a_bytes) / s.b_stage_bytes;
+        if (ns > NSTAGE) ns = NSTAGE;
+        s.nstage = ns;
+        s.smem_bytes = 2 * s.a_bytes + ns * s.b_stage_bytes + fixed;
+        if (ns >= (G == 3 ? 3 : 2)) return;
+    }
+    s.smem_bytes = MAX_SMEM + 1;                        // does not fit
+}
 
 // Channel counts the tensor-core path takes; everything else goes to the direct kernel.
 static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s, bool f32 = false) {
@@ -430,15 +522,12 @@ static bool umma_shape(int Cin, int Cout, int kd, int kh, int kw, UmmaShape& s, 
     s.NP = (Cout % 128 == 0) ? 128 : Cout;
     s.nblk = Cout / s.NP;
     const int taps = kd * kh * kw;
-    s.G = (taps % 3 == 0 && s.NP <= 64) ? 3 : 1;
     const int J = s.CC / (f32 ? 4 : 8);
-    s.b_stage_bytes = s.G * J * s.NP * 16;
     for (int R = 4; R >= 1; R >>= 1) {
         if (R * s.NP > 512) continue;
         s.R = R;
         s.acc_bufs = (2 * R * s.NP <= 512) ? 2 : 1;
-        s.a_bytes = (R + kd - 1) * J * PLANE;
-        s.smem_bytes = 2 * s.a_bytes + NSTAGE * s.b_stage_bytes + s.NP * 4 * 3 + 16 * 8 + 16 + 27 * 4 + 128;
+        umma_ring(s, taps, kd, J);
         if (s.smem_bytes <= MAX_SMEM) return true;
     }
     return false;
@@ -731,41 +820,60 @@ static int launch_conv_umma(const void* x, int64_t x_ld, const float* in_scale_s
     p.dot_x = dot_x; p.dot_ld = dot_ld; p.x_absmax = x_absmax;
     B2_CHECK_ARG(!dot_x || (sums && dot_ld % EPO == 0 && aligned16(dot_x) && dot_ld >= Cout), "conv3d_umma: dot_x needs sums, 16-byte alignment and pitch >= Cout");
     p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw; p.relu = relu;
-    // Depth slabs per work item: the shape admits R <= s.R; fewer slabs = more work items (the deep levels have fewer voxel
-    // tiles than SMs) but the weight block is streamed once per item.  Cost model per CTA (cycles): items per CTA x
-    // max(MMA issue, weight stream at ~48 B/clk from L2) + a fixed pipeline fill per item.
+    // Depth slabs per work item and split-K factor.  The shape admits R <= s.R; fewer slabs = more work items (the deep levels
+    // have fewer voxel tiles than SMs) but the weight block is streamed once per item.  With a registered workspace
+    // (b200em_set_workspace) the Cin chunks of a tile can additionally be split over ks CTAs (partial sums through the workspace,
+    // the last CTA runs the epilogue).  Cost model per CTA (cycles): items per CTA x (max(MMA issue, weight stream at ~48 B/clk
+    // from L2) / ks + a fixed pipeline fill per item [+ the partial-sum round trip]).
+    int ksplit = 1;
+    float* ws_acc = nullptr;
+    unsigned* ws_cnt = nullptr;
     {
         const int taps = kd * kh * kw;
+        const int nchunks = Cin / s.CC;
         const long long cols = (long long)N * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
-        const int cta_cap = sm_count() / s.nblk > 0 ? sm_count() / s.nblk : 1;
+        int64_t ws_floats = 0;
+        int ncnt = 0;
+        const bool have_ws = get_workspace(&ws_acc, &ws_floats, &ws_cnt, &ncnt) && (int64_t)N * D * H * W * Cout <= ws_floats;
+        int ks_env = 0;                                  // bring-up / tests: B200EM_KSPLIT=k forces the factor (1 forbids the split)
+        { const char* e = getenv("B200EM_KSPLIT"); if (e) ks_env = atoi(e); }
         const double mma_cyc = s.NP / 2 > 32 + s.NP / 4 ? s.NP / 2 : 32 + s.NP / 4;
-        const double wts = (double)taps * Cin * s.NP * 2 / 48.0;
-        double best = 1e300;
-        int best_r = s.R;
+        const double wts = (double)taps * Cin * s.NP * sizeof(TA) / 48.0;
+        const int ks_only = ks_env > 0 ? (ks_env < nchunks ? ks_env : nchunks) : 0;
+        double best = 1e300, best_f = 1e300;             // best overall / best with the forced factor
+        int best_r = s.R, best_ks = 1, best_fr = 0;
         for (int R = s.R; R >= 1; R >>= 1) {
             const long long items = cols * ((D + R - 1) / R);
-            const long long gx_ = items < cta_cap ? items : cta_cap;
-            const long long per_cta = (items + gx_ - 1) / gx_;
-            const double mma = (double)R * taps * (Cin / (2 * EPU)) * mma_cyc;
-            const double epi = (2 * R * s.NP <= 512) ? 0.0 : (double)R * (s.NP / 32) * 700.0;   // single accumulator set: the epilogue is not overlapped
-            const double cost = per_cta * ((mma > wts ? mma : wts) + epi + 4000.0 + 1500.0 * (R + kd - 1));
-            if (cost < best * 0.97) { best = cost; best_r = R; }
+            for (int ks = 1; ks <= nchunks && ks <= 16; ++ks) {
+                if (ks > 1 && (!have_ws || items * s.nblk > ncnt || items * s.nblk * ks > sm_count())) break;
+                const int cta_cap = sm_count() / (s.nblk * ks) > 0 ? sm_count() / (s.nblk * ks) : 1;
+                const long long gx_ = items < cta_cap ? items : cta_cap;
+                const long long per_cta = (items + gx_ - 1) / gx_;
+                const double mma = (double)R * taps * (Cin / (2 * EPU)) * mma_cyc;
+                const double epi = (2 * R * s.NP <= 512) ? 0.0 : (double)R * (s.NP / 32) * 700.0;   // single accumulator set: the epilogue is not overlapped
+                const double part = ks > 1 ? (double)R * (s.NP / 32) * 1500.0 + 3000.0 : 0.0;      // partial sums out, arrival counter, sums back in
+                const double cost = per_cta * ((mma > wts ? mma : wts) / ks + epi + part + 4000.0 + 1500.0 * (R + kd - 1));
+                if (cost < best * 0.97) { best = cost; best_r = R; best_ks = ks; }
+                if (ks == ks_only && cost < best_f * 0.97) { best_f = cost; best_fr = R; }
+            }
         }
+        if (ks_only && best_fr) { best_r = best_fr; best_ks = ks_only; }
+        ksplit = best_ks;
         if (best_r != s.R) {
             s.R = best_r;
             s.acc_bufs = (2 * s.R * s.NP <= 512) ? 2 : 1;
-            s.a_bytes = (s.R + kd - 1) * (s.CC / EPU) * PLANE;
-            s.smem_bytes = 2 * s.a_bytes + NSTAGE * s.b_stage_bytes + s.NP * 4 * 3 + 16 * 8 + 16 + 27 * 4 + 128;
+            umma_ring(s, taps, kd, s.CC / EPU);
         }
     }
-    p.R = s.R; p.NP = s.NP; p.CC = s.CC; p.nchunks = Cin / s.CC; p.G = s.G; p.acc_bufs = s.acc_bufs;
+    p.ksplit = ksplit; p.ws_acc = ws_acc; p.ws_cnt = ws_cnt;
+    p.R = s.R; p.NP = s.NP; p.CC = s.CC; p.nchunks = Cin / s.CC; p.G = s.G; p.acc_bufs = s.acc_bufs; p.nstage = s.nstage;
     p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + s.R - 1) / s.R;
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
     B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
     p.a_bytes = s.a_bytes; p.b_stage_bytes = s.b_stage_bytes;
-    long long gx = p.items < sm_count() / s.nblk ? p.items : sm_count() / s.nblk;
+    long long gx = p.items < sm_count() / (s.nblk * ksplit) ? p.items : sm_count() / (s.nblk * ksplit);
     if (gx < 1) gx = 1;
-    dim3 grid((unsigned)gx, (unsigned)s.nblk, 1);
+    dim3 grid((unsigned)gx, (unsigned)s.nblk, (unsigned)ksplit);
 #define B2_UMMA_LAUNCH(R_, KC_)                                                                                             \
     do {                                                                                                                    \
         B2_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<TA, TO, R_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM)); \

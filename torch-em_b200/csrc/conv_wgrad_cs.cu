@@ -314,14 +314,19 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
                 printf("[cs prof] mma: total %lld cyc, %lld stages: wait full %lld\n", clock64() - pf_t0, pf_n, pf_w);
         }
     } else if (warp < 4) {
-        // ===================== epilogue: TMEM -> atomics into dW =====================
+        // ===================== epilogue: TMEM -> shared-memory transpose -> coalesced vector reductions into dW =====================
+        // dW is (Cout, Cin, 27) fp32: for one output channel the CTA's 32 input channels x 27 taps are 864 CONTIGUOUS floats.  A
+        // lane holds ONE input channel, so adding straight from the TMEM registers would scatter 4-byte atomics 108 bytes apart
+        // (one L2 transaction each: the deep, weight-heavy levels were bound by exactly that).  Instead the accumulators are
+        // transposed through the (now idle) operand ring -- every MMA has completed when acc_full fires, so the ring is free --
+        // and leave as 16-byte red.global.add.v4.f32 over contiguous memory.
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const int a = warp;                              // depth tap of this warp's 32 lanes (a == 3: ignored rows)
-        const int taps = 27;
+        constexpr int taps = 27, ROW = 32 * taps;        // floats per output channel of this CTA's (ci chunk, co block) tile
+        float* stage = reinterpret_cast<float*>(smem);   // [32 co][32 ci][27 taps] = 110,592 B <= (NS + 3) * CS_XSLOT + NS * CS_ZSLOT
         const float osc = pow2i(-h16_shift(p.x_absmax) - h16_shift(p.z_absmax));
         if (a < 3) {
-            const int ci = chunk * 32 + lane;
             for (int c = 0; c < 3; ++c) {
                 for (int bq = 0; bq < 3; ++bq) {             // N block b' = h shift of the dz rows: tap b = 2 - b'
                     const int tap = (a * 3 + (2 - bq)) * 3 + c;
@@ -330,13 +335,24 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
                         tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * N3 + bq * CS_NB + cb), raw);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int co = cob * CS_NB + cb + i;
-                            atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * taps + tap, __uint_as_float(raw[i]) * osc);
-                        }
+                        for (int i = 0; i < 16; ++i) stage[(cb + i) * ROW + lane * taps + tap] = __uint_as_float(raw[i]) * osc;   // lane stride 27 words: conflict-free
                     }
                 }
             }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int t = threadIdx.x;                       // 0..127
+        float* dwb = p.dw + ((size_t)(cob * CS_NB) * p.Cin + chunk * 32) * taps;
+        const size_t co_stride = (size_t)p.Cin * taps;
+        if ((reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
+            for (int i = t; i < CS_NB * (ROW / 4); i += 128) {
+                const int co = i / (ROW / 4), q = i % (ROW / 4);
+                const float4 v = *reinterpret_cast<const float4*>(stage + co * ROW + q * 4);
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dwb + co * co_stride + q * 4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                             : "memory");
+            }
+        } else {
+            for (int i = t; i < CS_NB * ROW; i += 128) atomicAdd(dwb + (i / ROW) * co_stride + i % ROW, stage[i]);
         }
     }
 
@@ -378,7 +394,7 @@ static int launch_wgrad_cs(const void* x, int64_t x_ld, const float* in_scale_sh
     const int misc = CS_NB * 4 + (3 * CS_MAX_NS + 1) * 8 + 8 + 128;
     int ns = (CS_MAX_SMEM - misc - 3 * CS_XSLOT) / (CS_XSLOT + CS_ZSLOT);
     if (ns > CS_MAX_NS) ns = CS_MAX_NS;
-    B2_CHECK_ARG(ns >= 4, "conv3d_wgrad_cs: shared memory budget exceeded");
+    B2_CHECK_ARG(ns >= 4 && (ns + 3) * CS_XSLOT + ns * CS_ZSLOT >= CS_NB * 32 * 27 * 4, "conv3d_wgrad_cs: shared memory budget exceeded");   // the ring doubles as the epilogue's transpose stage
     p.NS = ns;
     p.nlw = ns < CS_NLW ? ns : CS_NLW;
     const int smem_bytes = (ns + 3) * CS_XSLOT + ns * CS_ZSLOT + misc;

@@ -31,6 +31,24 @@ int sm_count() {
     return v;
 }
 
+// Caller-provided, all-zero scratch of the current device (b200em_set_workspace): the first WS_COUNTER_BYTES are tile counters, the
+// rest fp32 partial sums.  Kernels that use it leave it all-zero again (the last CTA of a tile clears what it read).
+namespace {
+struct Workspace { void* p; int64_t bytes; };
+Workspace g_ws[64];
+}
+bool get_workspace(float** acc, int64_t* acc_floats, unsigned** counters, int* ncounters) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    const Workspace w = g_ws[dev];
+    if (!w.p || w.bytes <= WS_COUNTER_BYTES) return false;
+    *counters = reinterpret_cast<unsigned*>(w.p);
+    *ncounters = WS_COUNTER_BYTES / 4;
+    *acc = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(w.p) + WS_COUNTER_BYTES);
+    *acc_floats = (w.bytes - WS_COUNTER_BYTES) / 4;
+    return true;
+}
+
 __global__ void memset_zero_kernel(uint4* __restrict__ p, int64_t n16, unsigned char* __restrict__ tail, int ntail) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = make_uint4(0, 0, 0, 0);
@@ -58,6 +76,17 @@ int b200em_device_info(int* sm_count_out, int* cc_major, int* cc_minor, int* umm
     if (cc_major) *cc_major = maj;
     if (cc_minor) *cc_minor = min;
     if (umma_ok) *umma_ok = (maj == 10) ? 1 : 0;
+    return 0;
+}
+
+int b200em_set_workspace(void* workspace, int64_t bytes) {
+    int dev = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CHECK_ARG(dev >= 0 && dev < 64, "set_workspace: device index out of range");
+    B2_CHECK_ARG((workspace == nullptr && bytes == 0) || (workspace && bytes > WS_COUNTER_BYTES && aligned16(workspace)),
+                 "set_workspace: needs a 16-byte aligned buffer larger than %d bytes (or NULL, 0 to unregister)", WS_COUNTER_BYTES);
+    g_ws[dev].p = workspace;
+    g_ws[dev].bytes = bytes;
     return 0;
 }
 
