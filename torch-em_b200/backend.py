@@ -223,6 +223,11 @@ class PackSet:
         return self.packs[key]
 
 
+# One scratch buffer per device for the whole process: the library keeps the raw pointer (b200em_set_workspace), so the tensor must
+# never be freed or replaced while any backend object may still launch kernels on that device.
+_WORKSPACES = {}
+
+
 class CudaBackend:
     name = "cuda"
 
@@ -232,7 +237,7 @@ class CudaBackend:
         self.use_splitk = use_splitk
         self.use_h16 = use_h16      # TF32-class arithmetic through fp16 operand copies at the bf16 MMA rate (False: kind::tf32 kernels)
         self._h16_recent = []       # [(tensor, H16Operand)]: the last two un-normalised fp32 tensors converted (dz feeds wgrad AND dgrad)
-        self._workspaces = {}       # device index -> zero-filled scratch registered with the library (split-K partial sums)
+        self._workspaces = _WORKSPACES   # device index -> zero-filled scratch registered with the library (split-K partial sums)
         self.use_ds = use_ds and use_umma
         self.use_cs = use_cs and use_umma
         self.timing = None          # {family: [(start_event, end_event, work), ...]} while bench.py measures
