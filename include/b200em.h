@@ -170,6 +170,10 @@ int b200em_pack_batch(const b200em_pack_job* jobs_device, int njobs, int total_b
 int b200em_conv3d_first_supported(int Cin, int Cout, int kd, int kh, int kw);
 int b200em_conv3d_first(const void* x, const float* in_scale_shift, const float* w, const float* bias, void* y, int64_t y_ld,
                         float* sums, int N, int D, int H, int W, int Cout, int relu, void* stream);
+/* fp32 variant (the h16 path): x (N,D,H,W,1) fp32, y fp32; the im2col image and the filter are rounded to IEEE fp16 (TF32's
+ * significand) in shared memory. */
+int b200em_conv3d_first_f32(const float* x, const float* in_scale_shift, const float* w, const float* bias, float* y, int64_t y_ld,
+                            float* sums, int N, int D, int H, int W, int Cout, int relu, void* stream);
 int b200em_conv3d_first_wgrad(const void* x, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw, float* db,
                               int N, int D, int H, int W, int Cout, void* stream);
 

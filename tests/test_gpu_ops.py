@@ -211,9 +211,9 @@ def test_fused_norm_backward_in_pool_and_upsample_backward(B, dtype, f, shape, C
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("act_name", [None, "Sigmoid", "ReLU", "Tanh"])
-@pytest.mark.parametrize("Cin,Cout", [(16, 2), (5, 3), (32, 12)])
+@pytest.mark.parametrize("Cin,Cout", [(16, 2), (5, 3), (32, 12), (32, 2), (64, 2), (128, 1), (64, 1)])
 def test_head(B, dtype, act_name, Cin, Cout):
-    N, D, H, W = 2, 3, 5, 9
+    N, D, H, W = (2, 3, 5, 9) if Cin < 64 else (2, 7, 13, 19)       # the wide heads: several warps per channel slice
     x = act((N, D, H, W, Cin), dtype, 1, relu=True)
     w = act((Cout, Cin, 1, 1, 1), torch.float32, 2, scale=0.3)
     b = act((Cout,), torch.float32, 3)

@@ -416,6 +416,13 @@ class CudaBackend:
                 "b200em_conv3d_first", xp, _f32(in_ss), _f32(pack.master), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cout,
                 int(relu), _stream(x)))
             return None
+        if (not dgrad) and self.use_ds and Cin == 1 and xld == 1 and x.dtype == torch.float32 and self.h16_enabled() and yld % 4 == 0 and \
+                y.data_ptr() % 16 == 0 and dot_x is None and _lib.load().b200em_conv3d_first_supported(Cin, Cout, kd, kh, kw):
+            # first conv with fp32 activations on the h16 path: the same kernel with an fp16 im2col image and fp32 output
+            self._timed("first:fwd", flops, lambda: call(
+                "b200em_conv3d_first_f32", xp, _f32(in_ss), _f32(pack.master), _f32(b), yp, yld, _f32(sums), N, D, H, W, Cout,
+                int(relu), _stream(x)))
+            return None
         if (not dgrad) and pack.thin is not None and x.dtype == torch.bfloat16 and yld % 8 == 0 and y.data_ptr() % 16 == 0:
             cols = self.im2col(x, in_ss, kernel, pack.thin_kp)
             assert dot_x is None

@@ -70,9 +70,9 @@ __device__ __forceinline__ void ds_coords(const ConvDsParams& p, long long item_
 // One NV-wide block of output channels of one output slice: bias, ReLU, bf16 store, statistics.
 // ACC: statistics go to per-thread accumulators (flushed once per work item); otherwise they are reduced over the
 // warp's 32 rows right away and added to the shared-memory sums.
-template <int NV, bool ACC>
+template <int NV, bool ACC, typename TO = __nv_bfloat16>
 __device__ __forceinline__ void ds_epilogue_block(uint32_t taddr, const float* __restrict__ bias_s, int relu, bool valid,
-                                                  __nv_bfloat16* __restrict__ yp, const uint4* xv, bool has_x, float* acc_s,
+                                                  TO* __restrict__ yp, const uint4* xv, bool has_x, float* acc_s,
                                                   float* acc_q, float* __restrict__ s_sums_blk, bool want_sums, int lane) {
     // xv: this row's dot_x values for these NV channels, already in registers (prefetched one slice ahead; zeros if !valid)
     uint32_t raw[NV];
@@ -83,16 +83,22 @@ __device__ __forceinline__ void ds_epilogue_block(uint32_t taddr, const float* _
     for (int i = 0; i < NV; ++i) {
         float f = __uint_as_float(raw[i]) + bias_s[i];
         if (relu) f = fmaxf(f, 0.f);
-        v[i] = __bfloat162float(__float2bfloat16_rn(f));
+        v[i] = round_as<TO>(f);
     }
     if (valid) {
+        if constexpr (sizeof(TO) == 4) {                 // fp32 activations (the first conv of the h16 path)
 #pragma unroll
-        for (int q = 0; q < NV / 8; ++q) {
-            uint4 o;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+            for (int q = 0; q < NV / 4; ++q)
+                *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
-            *reinterpret_cast<uint4*>(yp + 8 * q) = o;
+            for (int q = 0; q < NV / 8; ++q) {
+                uint4 o;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(yp + 8 * q) = o;
+            }
         }
     }
     if (!want_sums) return;
@@ -646,11 +652,11 @@ constexpr int F1_SCR = 3 * DS_HP * DS_WP;             // per-warp scratch: haloe
 }  // namespace
 
 struct ConvFirstParams {
-    const __nv_bfloat16* x;                           // (N, D, H, W, 1)
+    const void* x;                                    // (N, D, H, W, 1) bf16, or fp32 for the F32 instantiation
     const float* in_ss;                               // (N, 1, 2) or null
     const float* w;                                   // torch (Cout, 1, 3, 3, 3) fp32
     const float* bias;
-    __nv_bfloat16* y; long long y_ld;
+    void* y; long long y_ld;                          // bf16, or fp32 for the F32 instantiation
     float* sums;
     const __nv_bfloat16* dz; long long dz_ld;         // weight-gradient kernel only
     float* dw; float* db;
@@ -669,12 +675,15 @@ __device__ __forceinline__ void f1_coords(const ConvFirstParams& p, long long it
 
 // One loader warp builds the im2col image of one 128-voxel slab (output slice gd, tile origin h0, w0) at `dst`:
 // [k-group j][voxel m = 8*hl + wl][8 taps], tap k = (a*3 + b)*3 + c, k >= 27 zero.  scr = this warp's scratch.
+// F32: x is fp32 and the 16-bit im2col image is IEEE fp16 (the h16 path: same significand as TF32), else bf16 from bf16.
+template <bool F32 = false>
 __device__ __forceinline__ void f1_build_slab(const ConvFirstParams& p, int n, int gd, int h0, int w0, float sc, float sh,
                                               __nv_bfloat16* scr, uint8_t* dst, int lane) {
-    const __nv_bfloat16* xn = p.x + (size_t)n * p.D * p.H * p.W;
+    using TX = typename std::conditional<F32, float, __nv_bfloat16>::type;
+    const TX* xn = reinterpret_cast<const TX*>(p.x) + (size_t)n * p.D * p.H * p.W;
     // all of the lane's loads are issued before the first one is consumed (one global latency per slab, not 17)
     constexpr int NF = (F1_SCR + 31) / 32;
-    __nv_bfloat16 raw[NF];
+    TX raw[NF];
     bool inb[NF];
 #pragma unroll
     for (int q = 0; q < NF; ++q) {
@@ -682,12 +691,16 @@ __device__ __forceinline__ void f1_build_slab(const ConvFirstParams& p, int n, i
         const int wp_ = i % DS_WP, hp_ = (i / DS_WP) % DS_HP, a = i / (DS_WP * DS_HP);
         const int sd = gd + a - 1, gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
         inb[q] = i < F1_SCR && sd >= 0 && sd < p.D && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
-        raw[q] = inb[q] ? xn[((size_t)sd * p.H + gh) * p.W + gw] : __float2bfloat16_rn(0.f);
+        raw[q] = inb[q] ? xn[((size_t)sd * p.H + gh) * p.W + gw] : from_f<TX>(0.f);
     }
 #pragma unroll
     for (int q = 0; q < NF; ++q) {
         const int i = lane + 32 * q;
-        if (i < F1_SCR) scr[i] = __float2bfloat16_rn(inb[q] ? fmaf(__bfloat162float(raw[q]), sc, sh) : 0.f);
+        const float xh = inb[q] ? fmaf(to_f<TX>(raw[q]), sc, sh) : 0.f;
+        if (i < F1_SCR) {
+            if constexpr (F32) reinterpret_cast<__half*>(scr)[i] = __float2half_rn(xh);
+            else scr[i] = __float2bfloat16_rn(xh);
+        }
     }
     __syncwarp();
     const uint16_t* s16 = reinterpret_cast<const uint16_t*>(scr);
@@ -711,8 +724,9 @@ __device__ __forceinline__ void f1_build_slab(const ConvFirstParams& p, int n, i
     __syncwarp();                                     // scratch is reused by this warp's next slab
 }
 
-template <int CO>
+template <int CO, bool F32 = false>
 __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvFirstParams p) {
+    using TY = typename std::conditional<F32, float, __nv_bfloat16>::type;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int NA = (512 / CO) < DS_MAX_NA ? (512 / CO) : DS_MAX_NA;
     uint8_t* smA = smem;                                              // [F1_NS][F1_ASTAGE]
@@ -739,7 +753,9 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
     for (int i = threadIdx.x; i < 4 * CO * 8; i += F1_THREADS) {
         const int e = i % 8, co = (i / 8) % CO, j = i / (8 * CO);
         const int k = j * 8 + e;
-        reinterpret_cast<__nv_bfloat16*>(smB)[i] = __float2bfloat16_rn(k < 27 ? p.w[co * 27 + k] : 0.f);
+        const float wv = k < 27 ? p.w[co * 27 + k] : 0.f;
+        if constexpr (F32) reinterpret_cast<__half*>(smB)[i] = __float2half_rn(wv);
+        else reinterpret_cast<__nv_bfloat16*>(smB)[i] = __float2bfloat16_rn(wv);
     }
     for (int i = threadIdx.x; i < CO; i += F1_THREADS) {
         s_bias[i] = p.bias ? p.bias[i] : 0.f;
@@ -769,7 +785,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
                 if (++owner == F1_NLW) owner = 0;
                 if (!mine) continue;
                 mbar_wait(&a_empty[my_slot], my_phase);
-                f1_build_slab(p, n, d0 + od, h0, w0, sc, sh, scr, smA + my_slot * F1_ASTAGE, lane);
+                f1_build_slab<F32>(p, n, d0 + od, h0, w0, sc, sh, scr, smA + my_slot * F1_ASTAGE, lane);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) flag_store(&a_full[my_slot], my_lap);
@@ -778,7 +794,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
     } else if (warp == F1_W_MMA) {
         // ===================== MMA issuer: two K = 16 MMAs per slab =====================
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, CO);
+            constexpr uint32_t idesc = F32 ? make_idesc_f16(128, CO) : make_idesc_bf16(128, CO);
             const uint64_t ad = make_desc(0, 128 * 16, 128), bd = make_desc(0, (uint32_t)(CO * 16), 128);
             const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
             const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
@@ -828,22 +844,22 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
                 tc_fence_after();
                 const int gd = d0 + od;
                 const bool valid = valid_hw && gd < p.D;
-                __nv_bfloat16* yp = p.y + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld;
+                TY* yp = reinterpret_cast<TY*>(p.y) + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld;
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(r * CO);
                 if constexpr (CO == 16) {
-                    ds_epilogue_block<16, true>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
+                    ds_epilogue_block<16, true, TY>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
                 } else if constexpr (CO == 32) {
-                    ds_epilogue_block<16, true>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
-                    ds_epilogue_block<16, true>(taddr + 16, s_bias + 16, p.relu, valid, yp + 16, nullptr, false, acc_s + 16, acc_q + 16, s_sums,
-                                                ws, lane);
+                    ds_epilogue_block<16, true, TY>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
+                    ds_epilogue_block<16, true, TY>(taddr + 16, s_bias + 16, p.relu, valid, yp + 16, nullptr, false, acc_s + 16, acc_q + 16, s_sums,
+                                                    ws, lane);
                 } else {
-                    ds_epilogue_block<32, false>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
+                    ds_epilogue_block<32, false, TY>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
                     if constexpr (CO == 64)
-                        ds_epilogue_block<32, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, nullptr, false, acc_s, acc_q, s_sums + 64,
-                                                     ws, lane);
+                        ds_epilogue_block<32, false, TY>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, nullptr, false, acc_s, acc_q, s_sums + 64,
+                                                         ws, lane);
                     if constexpr (CO == 48)
-                        ds_epilogue_block<16, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, nullptr, false, acc_s, acc_q, s_sums + 64,
-                                                     ws, lane);
+                        ds_epilogue_block<16, false, TY>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, nullptr, false, acc_s, acc_q, s_sums + 64,
+                                                         ws, lane);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -1211,14 +1227,17 @@ static int first_setup(ConvFirstParams& p, int N, int D, int H, int W, int Cout,
     return 0;
 }
 
-int b200em_conv3d_first(const void* x, const float* in_scale_shift, const float* w, const float* bias, void* y, int64_t y_ld,
-                        float* sums, int N, int D, int H, int W, int Cout, int relu, void* stream) {
+}  // extern "C"
+
+template <bool F32>
+static int launch_conv_first(const void* x, const float* in_scale_shift, const float* w, const float* bias, void* y, int64_t y_ld,
+                             float* sums, int N, int D, int H, int W, int Cout, int relu, void* stream) {
     B2_CHECK_ARG(x && w && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_first: bad arguments");
     B2_CHECK_ARG(first_shape(1, Cout, 3, 3, 3), "conv3d_first: Cout %d not supported", Cout);
-    B2_CHECK_ARG(y_ld % 8 == 0 && aligned16(y) && y_ld >= Cout, "conv3d_first: output must be 16-byte aligned with pitch % 8 == 0");
+    B2_CHECK_ARG(y_ld % (F32 ? 4 : 8) == 0 && aligned16(y) && y_ld >= Cout, "conv3d_first: output must be 16-byte aligned with a pitch that keeps it so");
     ConvFirstParams p;
     memset(&p, 0, sizeof(p));
-    p.x = (const __nv_bfloat16*)x; p.in_ss = in_scale_shift; p.w = w; p.bias = bias; p.y = (__nv_bfloat16*)y; p.y_ld = y_ld;
+    p.x = x; p.in_ss = in_scale_shift; p.w = w; p.bias = bias; p.y = y; p.y_ld = y_ld;
     p.sums = sums; p.relu = relu;
     first_setup(p, N, D, H, W, Cout, sm_count());
     B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
@@ -1226,13 +1245,25 @@ int b200em_conv3d_first(const void* x, const float* in_scale_shift, const float*
     const int smem_bytes = F1_NS * F1_ASTAGE + 4 * Cout * 16 + ((F1_NLW * F1_SCR * 2 + 15) & ~15) + Cout * 12 + (2 * F1_NS + 2 * DS_MAX_NA) * 8 + 16 + 128;
 #define B2_F1(CO_)                                                                                                     \
     case CO_:                                                                                                          \
-        B2_CUDA(cudaFuncSetAttribute(conv3d_first_kernel<CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
-        conv3d_first_kernel<CO_><<<(unsigned)gx, F1_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);                     \
+        B2_CUDA(cudaFuncSetAttribute(conv3d_first_kernel<CO_, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
+        conv3d_first_kernel<CO_, F32><<<(unsigned)gx, F1_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);                \
         break;
     switch (Cout) { B2_F1(16) B2_F1(32) B2_F1(48) B2_F1(64) default: set_error("conv3d_first: Cout %d not instantiated", Cout); return 2; }
 #undef B2_F1
     B2_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" {
+
+int b200em_conv3d_first(const void* x, const float* in_scale_shift, const float* w, const float* bias, void* y, int64_t y_ld,
+                        float* sums, int N, int D, int H, int W, int Cout, int relu, void* stream) {
+    return launch_conv_first<false>(x, in_scale_shift, w, bias, y, y_ld, sums, N, D, H, W, Cout, relu, stream);
+}
+
+int b200em_conv3d_first_f32(const float* x, const float* in_scale_shift, const float* w, const float* bias, float* y, int64_t y_ld,
+                            float* sums, int N, int D, int H, int W, int Cout, int relu, void* stream) {
+    return launch_conv_first<true>(x, in_scale_shift, w, bias, y, y_ld, sums, N, D, H, W, Cout, relu, stream);
 }
 
 int b200em_conv3d_first_wgrad(const void* x, const float* in_scale_shift, const void* dz, int64_t dz_ld, float* dw, float* db, int N,
@@ -1242,7 +1273,7 @@ int b200em_conv3d_first_wgrad(const void* x, const float* in_scale_shift, const 
     B2_CHECK_ARG(dz_ld % 8 == 0 && aligned16(dz) && dz_ld >= Cout, "conv3d_first_wgrad: dz must be 16-byte aligned with pitch % 8 == 0");
     ConvFirstParams p;
     memset(&p, 0, sizeof(p));
-    p.x = (const __nv_bfloat16*)x; p.in_ss = in_scale_shift; p.dz = (const __nv_bfloat16*)dz; p.dz_ld = dz_ld; p.dw = dw; p.db = db;
+    p.x = x; p.in_ss = in_scale_shift; p.dz = (const __nv_bfloat16*)dz; p.dz_ld = dz_ld; p.dw = dw; p.db = db;
     first_setup(p, N, D, H, W, Cout, sm_count());
     B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
     const long long gx = p.items < sm_count() ? p.items : sm_count();

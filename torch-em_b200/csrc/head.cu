@@ -216,16 +216,21 @@ head_fwd_small_kernel(const T* __restrict__ x, int64_t x_ld, const float* __rest
     }
 }
 
+// cin_total = CIN * slices input channels: warp w of the grid handles channel slice (w % slices) of 32 consecutive voxels, so a
+// thread still owns one voxel x CIN channels (the dW partials fit in registers) and wider heads (Cin = 64, 128) take the same path.
 template <typename T, int CIN, int COUT>
 __global__ void __launch_bounds__(256, 2)
 head_bwd_small_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, const T* __restrict__ x, int64_t x_ld,
                       const float* __restrict__ w, T* __restrict__ dx, int64_t dx_ld, float* __restrict__ dw,
-                      float* __restrict__ db, int64_t S, int act, int relu_mask, int64_t total) {
+                      float* __restrict__ db, int64_t S, int act, int relu_mask, int64_t total, int cin_total) {
     constexpr int V = FullVec<T>::value;
-    __shared__ float red[8][COUT * CIN + COUT];
-    __shared__ float wr_s[COUT * CIN];               // filter in shared memory (broadcast reads): two blocks per SM fit the register file
+    constexpr int MAXC = 128;
+    __shared__ float red[COUT * MAXC + COUT];        // block-level dW | db partial sums
+    __shared__ float wr_s[COUT * MAXC];              // filter in shared memory (broadcast reads): two blocks per SM fit the register file
     float aw[COUT][CIN], ab[COUT];
-    for (int i = threadIdx.x; i < COUT * CIN; i += blockDim.x) wr_s[i] = w[i];
+    const int slices = cin_total / CIN;
+    for (int i = threadIdx.x; i < COUT * cin_total; i += blockDim.x) wr_s[i] = w[i];
+    for (int i = threadIdx.x; i < COUT * cin_total + COUT; i += blockDim.x) red[i] = 0.f;
 #pragma unroll
     for (int j = 0; j < COUT; ++j) {
         ab[j] = 0.f;
@@ -233,8 +238,11 @@ head_bwd_small_kernel(const float* __restrict__ grad_out, const float* __restric
         for (int c = 0; c < CIN; ++c) aw[j][c] = 0.f;
     }
     __syncthreads();
-    const float (*wr)[CIN] = reinterpret_cast<const float (*)[CIN]>(wr_s);
-    for (int64_t vox = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; vox < total; vox += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int sl = (int)(gwarp % slices);            // (gridDim.x * 8) % slices == 0: a warp keeps its slice over the grid-stride loop
+    const int c0 = sl * CIN;
+    for (int64_t vox = (gwarp / slices) * 32 + lane; vox < total; vox += (nwarps / slices) * 32) {
         const int64_t n = vox / S, s_ = vox % S;
         float dz[COUT];
 #pragma unroll
@@ -243,7 +251,7 @@ head_bwd_small_kernel(const float* __restrict__ grad_out, const float* __restric
             dz[j] = grad_out[o] * act_bwd(out[o], act);
             ab[j] += dz[j];
         }
-        const T* xp = x + vox * x_ld;
+        const T* xp = x + vox * x_ld + c0;
 #pragma unroll
         for (int c = 0; c < CIN; c += V) {
             float xv[V], r[V];
@@ -253,16 +261,15 @@ head_bwd_small_kernel(const float* __restrict__ grad_out, const float* __restric
                 float g = 0.f;
 #pragma unroll
                 for (int j = 0; j < COUT; ++j) {
-                    g = fmaf(wr[j][c + k], dz[j], g);
+                    g = fmaf(wr_s[j * cin_total + c0 + c + k], dz[j], g);
                     aw[j][c + k] = fmaf(dz[j], xv[k], aw[j][c + k]);
                 }
                 r[k] = (relu_mask && !(xv[k] > 0.f)) ? 0.f : g;
             }
-            if (dx) Vec<T, V>::store(dx + vox * dx_ld + c, r);
+            if (dx) Vec<T, V>::store(dx + vox * dx_ld + c0 + c, r);
         }
     }
-    // block reduction: warp shuffles, then one row per warp in shared memory, then COUT*CIN + COUT atomics per block
-    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    // block reduction: warp shuffles, one shared-memory atomic per warp and value, then COUT*cin_total + COUT atomics per block
 #pragma unroll
     for (int j = 0; j < COUT; ++j) {
 #pragma unroll
@@ -270,20 +277,17 @@ head_bwd_small_kernel(const float* __restrict__ grad_out, const float* __restric
             float a = aw[j][c];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) red[wi][j * CIN + c] = a;
+            if (lane == 0) atomicAdd(&red[j * cin_total + c0 + c], a);
         }
         float b = ab[j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
-        if (lane == 0) red[wi][COUT * CIN + j] = b;
+        if (lane == 0 && sl == 0) atomicAdd(&red[COUT * cin_total + j], b);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < COUT * CIN + COUT; i += blockDim.x) {
-        float a = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) a += red[q][i];
-        if (i < COUT * CIN) atomicAdd(dw + i, a);
-        else if (db) atomicAdd(db + (i - COUT * CIN), a);
+    for (int i = threadIdx.x; i < COUT * cin_total + COUT; i += blockDim.x) {
+        if (i < COUT * cin_total) atomicAdd(dw + i, red[i]);
+        else if (db) atomicAdd(db + (i - COUT * cin_total), red[i]);
     }
 }
 
@@ -291,6 +295,11 @@ template <typename T>
 static bool head_small_ok(const void* x, int64_t x_ld, const void* dx, int64_t dx_ld, int Cin, int Cout) {
     constexpr int V = FullVec<T>::value;
     return (Cin == 16 || Cin == 32) && (Cout == 1 || Cout == 2) && x_ld % V == 0 && aligned16(x) && (!dx || (dx_ld % V == 0 && aligned16(dx)));
+}
+// the backward kernel also takes Cin = 64 / 128 as 2 / 4 channel slices of 32
+template <typename T>
+static bool head_bwd_small_ok(const void* x, int64_t x_ld, const void* dx, int64_t dx_ld, int Cin, int Cout) {
+    return head_small_ok<T>(x, x_ld, dx, dx_ld, (Cin == 64 || Cin == 128) ? 32 : Cin, Cout);
 }
 
 }  // namespace b200em
@@ -338,9 +347,9 @@ static void launch_head_bwd_small(unsigned blocks, cudaStream_t st, const float*
                                   int Cout, int act, int relu_mask, int64_t total) {
 #define B2_HEAD_BWD_SMALL(CI, CO)                                                                                             \
     head_bwd_small_kernel<T, CI, CO><<<blocks, 256, 0, st>>>(grad_out, out, (const T*)x, x_ld, w, (T*)dx, dx_ld, dw, db, S, act, \
-                                                             relu_mask, total)
-    if (Cin == 32 && Cout == 2) B2_HEAD_BWD_SMALL(32, 2);
-    else if (Cin == 32) B2_HEAD_BWD_SMALL(32, 1);
+                                                             relu_mask, total, Cin)
+    if (Cin % 32 == 0 && Cout == 2) B2_HEAD_BWD_SMALL(32, 2);
+    else if (Cin % 32 == 0) B2_HEAD_BWD_SMALL(32, 1);
     else if (Cout == 2) B2_HEAD_BWD_SMALL(16, 2);
     else B2_HEAD_BWD_SMALL(16, 1);
 #undef B2_HEAD_BWD_SMALL
@@ -383,8 +392,8 @@ int b200em_head_bwd(const float* grad_out, const float* out, const void* x, int6
     {
         bool done = false;
         B2_DISPATCH_DTYPE(dtype, T, {
-            if (head_small_ok<T>(x, x_ld, dx, dx_ld, Cin, Cout)) {
-                launch_head_bwd_small<T>((unsigned)blocks, (cudaStream_t)stream, grad_out, out, x, x_ld, w, dx, dx_ld, dw, db, S, Cin, Cout,
+            if (head_bwd_small_ok<T>(x, x_ld, dx, dx_ld, Cin, Cout)) {
+                launch_head_bwd_small<T>((unsigned)(blocks / 4 * 4 > 0 ? blocks / 4 * 4 : 4), (cudaStream_t)stream, grad_out, out, x, x_ld, w, dx, dx_ld, dw, db, S, Cin, Cout,
                                          act, relu_mask, total);
                 done = true;
             }
