@@ -91,6 +91,20 @@ template <> struct Vec<__nv_bfloat16, 8> {
         *reinterpret_cast<uint4*>(p) = t;
     }
 };
+template <> struct Vec<__nv_bfloat16, 4> {           // 8-byte accesses: half a 16-byte unit per thread (register-heavy stencils)
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+        uint2 t;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+        h[0] = __floats2bfloat162_rn(v[0], v[1]);
+        h[1] = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = t;
+    }
+};
 template <> struct Vec<__nv_bfloat16, 1> {
     static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); }
     static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[1]) { *p = __float2bfloat16_rn(v[0]); }
