@@ -125,9 +125,10 @@ int b200em_conv3d_umma_h16(const void* x_f16, int64_t x_ld, const float* x_absma
  * same pass: the bias gradient sum(dz) from the fp32 values, as autograd computes it. */
 int b200em_absmax_f32(const float* x, int64_t x_ld, int64_t rows, int C, float* absmax, float* colsum, void* stream);
 /* out (N,S,C) fp16, contiguous = fp16(2^k * x_hat), x_hat = scale*x + shift when in_scale_shift is given (the fused norm apply),
- * k derived on the device from *absmax (NULL: k = 0; see common.cuh h16_shift). */
-int b200em_cvt_f16(const float* x, int64_t x_ld, const float* in_scale_shift, const float* absmax, void* out, int N, int64_t S,
-                   int C, void* stream);
+ * k derived on the device from *absmax (NULL: k = 0; see common.cuh h16_shift).  colsum (nullable, C floats, C <= 2048) += the
+ * per-channel sums of x in the same pass (the bias gradient sum(dz), from the fp32 values). */
+int b200em_cvt_f16(const float* x, int64_t x_ld, const float* in_scale_shift, const float* absmax, void* out, float* colsum, int N,
+                   int64_t S, int C, void* stream);
 
 /* "depth-stacked" tcgen05 variant for 3 x kh x kw filters with few output channels (Cout <= 80) whose packed filter
  * fits in shared memory: the three depth taps share one operand fetch (N = 3*Cout) and land in the accumulators of
@@ -225,10 +226,12 @@ int b200em_affine_apply(const void* x, int64_t x_ld, const float* scale_shift, v
 /* Backward coefficients: dx = coef0*g + coef1*x + coef2 per (n,c); dgamma/dbeta (nullable) accumulated. */
 int b200em_norm_bwd_finalize(const float* dsums, const float* mean_rstd, const float* gamma, int N, int C,
                              int64_t S, int groups, float* coef, float* dgamma, float* dbeta, void* stream);
-/* out = (coef0*g + coef1*x + coef2 [+ add]) * (relu_mask ? x > 0 : 1).  coef == NULL means out = g [+ add]. */
+/* out = (coef0*g + coef1*x + coef2 [+ add]) * (relu_mask ? x > 0 : 1).  coef == NULL means out = g [+ add].
+ * absmax (nullable, here and in b200em_maxpool3d_bwd / b200em_head_bwd): device float, zeroed by the caller, raised to max |out|
+ * with atomicMax -- the h16 path derives the fp16 operand scale of a gradient tensor from it without another pass over it. */
 int b200em_norm_bwd_apply(const void* g, int64_t g_ld, const void* x, int64_t x_ld, const float* coef,
                           const void* add, int64_t add_ld, void* out, int64_t out_ld, int dtype,
-                          int N, int64_t S, int C, int relu_mask, void* stream);
+                          int N, int64_t S, int C, int relu_mask, float* absmax, void* stream);
 
 /* fp32 -> two bf16 tensors with hi + lo ~= x_hat (x_hat = scale*x + shift when in_scale_shift is given, else x): hi =
  * bf16(x_hat), lo = bf16(x_hat - hi).  Lets the bf16 tensor-core weight-gradient kernels accumulate an fp32-class result as
@@ -245,7 +248,7 @@ int b200em_maxpool3d_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int
  * backward of the consuming decoder block applied on the fly to its raw data gradient, so the skip gradient is never stored. */
 int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp_ld, const void* add, int64_t add_ld,
                          const float* coef, int64_t coef_nstride, void* out, int64_t out_ld, int dtype, int N, int D, int H, int W,
-                         int C, int fd, int fh, int fw, int relu_mask, void* stream);
+                         int C, int fd, int fh, int fw, int relu_mask, float* absmax, void* stream);
 
 /* ---- F.interpolate(mode="trilinear", align_corners=False), integer scale (unet.py:456) --------------------- */
 /* (D,H,W) are the LOW-resolution dims. */
@@ -267,7 +270,7 @@ int b200em_head_fwd(const void* x, int64_t x_ld, int dtype, const float* w, cons
  * output of the last conv block, unet.py:437); dw (Cout,Cin) and db (Cout) accumulated. */
 int b200em_head_bwd(const float* grad_out, const float* out, const void* x, int64_t x_ld, int dtype, const float* w,
                     void* dx, int64_t dx_ld, float* dw, float* db, int N, int64_t S, int Cin, int Cout, int act,
-                    int relu_mask, void* stream);
+                    int relu_mask, float* absmax, void* stream);
 
 /* ---- DiceLoss [+ ApplyAndRemoveMask("multiply")]  (loss/dice.py:34-93, loss/wrapper.py:84-87,129-152) ------- */
 /* pred (N,C,S) fp32 or bf16; target fp32 with sample stride target_nstride (elements): channel c of sample n at

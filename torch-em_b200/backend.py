@@ -237,6 +237,7 @@ class CudaBackend:
         self.use_splitk = use_splitk
         self.use_h16 = use_h16      # TF32-class arithmetic through fp16 operand copies at the bf16 MMA rate (False: kind::tf32 kernels)
         self._h16_recent = []       # [(tensor, H16Operand)]: the last two un-normalised fp32 tensors converted (dz feeds wgrad AND dgrad)
+        self._absmax_known = []     # [(fp32 tensor, its device max |.|)] written by the producing kernel, consumed by to_h16
         self._workspaces = _WORKSPACES   # device index -> zero-filled scratch registered with the library (split-K partial sums)
         self.use_ds = use_ds and use_umma
         self.use_cs = use_cs and use_umma
@@ -291,6 +292,14 @@ class CudaBackend:
         power-of-two range scaling) on kind::f16 MMAs with fp32 accumulation: TF32-class results at twice the kind::tf32 rate."""
         return bool(self.use_h16) and self.tf32_enabled()
 
+    def _want_absmax(self, out):
+        """Device word for max |out| of a gradient tensor the h16 path will convert next (None when it will not)."""
+        if out is None or out.dtype != torch.float32 or not self.h16_enabled() or out.shape[4] % 8:
+            return None
+        am = torch.zeros(1, dtype=torch.float32, device=out.device)
+        self._absmax_known = [e for e in self._absmax_known if e[0] is not out][-3:] + [(out, am)]   # a rewrite supersedes
+        return am
+
     def to_h16(self, x, in_ss, colsum=None):
         """fp16 operand copy of the fp32 NDHWC view ``x``: fp16(scale * x + shift) for a normalised tensor (unit scale: no range
         problem), else fp16(2^k * x) with k taken on the device from max |x| (gradients span any range).  Un-normalised tensors are
@@ -309,9 +318,20 @@ class CudaBackend:
         out = torch.empty((N, D, H, W, C), dtype=torch.float16, device=x.device)
         am = None
         if in_ss is None:
-            am = torch.zeros(1, dtype=torch.float32, device=x.device)
-            call("b200em_absmax_f32", xp, xld, N * D * H * W, C, _f32(am), _f32(colsum), _stream(x))
-        call("b200em_cvt_f16", xp, xld, _f32(in_ss), _f32(am), _ptr(out), N, D * H * W, C, _stream(x))
+            # max |x| already came out of the kernel that produced x (norm / max-pool / head backward), else one more pass
+            for i, (t, a) in enumerate(self._absmax_known):
+                if t is x:
+                    am = a
+                    del self._absmax_known[i]
+                    break
+            if am is None:
+                am = torch.zeros(1, dtype=torch.float32, device=x.device)
+                call("b200em_absmax_f32", xp, xld, N * D * H * W, C, _f32(am), None, _stream(x))
+        call("b200em_cvt_f16", xp, xld, _f32(in_ss), _f32(am), _ptr(out), _f32(colsum) if C <= 8192 else None, N, D * H * W, C, _stream(x))
+        if colsum is not None and C > 8192:
+            s2 = torch.zeros((N, C, 2), dtype=torch.float32, device=x.device)
+            self.channel_sums(x, s2)
+            colsum += s2[:, :, 0].sum(0)
         h = H16Operand(out, am)
         if in_ss is None:
             self._h16_recent = self._h16_recent[-1:] + [(x, h)]
@@ -393,7 +413,7 @@ class CudaBackend:
         ap, ald = _act(add) if add is not None else (None, 0)
         op, old = _act(out)
         call("b200em_norm_bwd_apply", gp, gld, xp, xld, _f32(coef), ap, ald, op, old, _dt(g), N, D * H * W, C,
-             int(relu_mask), _stream(g))
+             int(relu_mask), _f32(self._want_absmax(out)), _stream(g))
 
     # ---- convolution -----------------------------------------------------------------------------------------
     def conv(self, x, in_ss, pack, bias, y, sums, kernel, relu, dgrad, dot_x=None):
@@ -601,7 +621,7 @@ class CudaBackend:
         op, old = _act(out)
         cp, cns = self._coef(coef, C)
         call("b200em_maxpool3d_bwd", xp, xld, dpp, dpld, ap, ald, cp, cns, op, old, _dt(x), N, D, H, W, C, f[0], f[1], f[2],
-             int(relu_mask), _stream(x))
+             int(relu_mask), _f32(self._want_absmax(out)), _stream(x))
 
     def upsample_fwd(self, x, y, f, sums):
         N, D, H, W, C = x.shape
@@ -645,7 +665,7 @@ class CudaBackend:
         xp, xld = _act(x)
         dxp, dxld = _act(dx) if dx is not None else (None, 0)
         call("b200em_head_bwd", _f32(grad_out), _f32(out), xp, xld, _dt(x), _f32(w.detach().reshape(Cout, Cin)), dxp, dxld,
-             _f32(dw), _f32(db), N, D * H * W, Cin, Cout, ACT[act], int(relu_mask), _stream(x))
+             _f32(dw), _f32(db), N, D * H * W, Cin, Cout, ACT[act], int(relu_mask), _f32(self._want_absmax(dx)), _stream(x))
 
 
 _default = None

@@ -133,6 +133,15 @@ __device__ __forceinline__ int h16_shift(const float* absmax) {
 }
 __device__ __forceinline__ float pow2i(int k) { return __uint_as_float((uint32_t)(k + 127) << 23); }
 
+// running max |v| of a thread (as the bit pattern) -> one atomicMax per warp into the device absmax word (nullable)
+__device__ __forceinline__ unsigned absmax_acc(unsigned am, float v) { return max(am, __float_as_uint(v) & 0x7fffffffu); }
+__device__ __forceinline__ void absmax_flush(unsigned am, float* absmax) {
+    if (!absmax) return;
+    am = __reduce_max_sync(0xffffffffu, am);
+    // thousands of warps target ONE word: look first (a stale read only costs a redundant atomic), so that all but the first few skip it
+    if ((threadIdx.x & 31) == 0 && am > *reinterpret_cast<volatile unsigned*>(absmax)) atomicMax(reinterpret_cast<unsigned*>(absmax), am);
+}
+
 // dispatch on dtype code
 #define B2_DISPATCH_DTYPE(dtype, T, ...)                                   \
     if ((dtype) == B200EM_F32) { using T = float; __VA_ARGS__ }            \

@@ -191,9 +191,10 @@ template <typename T, int VEC>
 __global__ void norm_bwd_apply_kernel(const T* __restrict__ g, int64_t g_ld, const T* __restrict__ x, int64_t x_ld,
                                       const float* __restrict__ coef, const T* __restrict__ add, int64_t add_ld,
                                       T* __restrict__ out, int64_t out_ld, int64_t S, int C, int relu_mask,
-                                      int64_t total) {
+                                      int64_t total, float* __restrict__ absmax) {
     const unsigned cvec = C / VEC;
     const int64_t n = blockIdx.y;
+    unsigned am = 0;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
         int cv = (int)(i % cvec);
         int64_t vox = n * S + i / cvec;
@@ -212,9 +213,11 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ g, int64_t g_ld, con
             if (add) t += va[k];
             if (relu_mask && !(vx[k] > 0.f)) t = 0.f;
             r[k] = t;
+            am = absmax_acc(am, t);
         }
         Vec<T, VEC>::store(out + vox * out_ld + cv * VEC, r);
     }
+    absmax_flush(am, absmax);
 }
 
 // fp32 -> (hi, lo) bf16 split of x_hat = scale*x + shift: hi = bf16(x_hat), lo = bf16(x_hat - hi)
@@ -293,34 +296,59 @@ absmax_f32_kernel(const float* __restrict__ x, int64_t x_ld, int64_t rows, int C
         for (int i = tid; i < C; i += bx * by) atomicAdd(colsum + i, s_col[i]);
 }
 
-// fp32 -> fp16 operand copy of the h16 path: out = fp16(2^k * (scale*x + shift)), k from the device absmax (common.cuh)
+// fp32 -> fp16 operand copy of the h16 path: out = fp16(2^k * (scale*x + shift)), k from the device absmax (common.cuh).
+// Block = (bx 8-channel vectors, by voxels): a thread keeps its channels over the loop, so the per-channel sums of x (the bias
+// gradient sum(dz), wanted from the fp32 values like autograd computes it) accumulate in registers in the same pass.
 __global__ void __launch_bounds__(256)
 cvt_f16_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ ss, const float* __restrict__ absmax,
-               __half* __restrict__ out, int64_t S, int C) {
+               __half* __restrict__ out, float* __restrict__ colsum, int64_t S, int C) {
     const int64_t n = blockIdx.y;
-    const unsigned cvec = C / 8;
-    const int64_t total = S * cvec;
+    const int cvec = C / 8, bx = blockDim.x, by = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
     const float mul = pow2i(h16_shift(absmax));
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % cvec);
-        const int64_t vox = n * S + i / cvec;
-        const float4 a = *reinterpret_cast<const float4*>(x + vox * x_ld + cv * 8);
-        const float4 b = *reinterpret_cast<const float4*>(x + vox * x_ld + cv * 8 + 4);
-        float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        if (ss) {
-            const float4* q = reinterpret_cast<const float4*>(ss + ((size_t)n * C + cv * 8) * 2);
+    extern __shared__ float s_col[];                   // [C] when colsum
+    if (colsum) {
+        for (int i = ty * bx + tx; i < C; i += bx * by) s_col[i] = 0.f;
+        __syncthreads();
+    }
+    for (int cv = tx; cv < cvec; cv += bx) {
+        float sc[8], sh[8], acc[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float4 t = __ldg(q + e);
-                f[2 * e] = fmaf(f[2 * e], t.x, t.y);
-                f[2 * e + 1] = fmaf(f[2 * e + 1], t.z, t.w);
+        for (int e = 0; e < 8; ++e) { sc[e] = 1.f; sh[e] = 0.f; acc[e] = 0.f; }
+        if (ss) {
+            const float* q = ss + ((size_t)n * C + cv * 8) * 2;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
+        }
+        const int64_t vstep = (int64_t)gridDim.x * by;
+        for (int64_t v0 = (int64_t)blockIdx.x * by + ty; v0 < S; v0 += 2 * vstep) {
+            // two voxels per iteration: four 16-byte loads in flight per thread
+            const int64_t v1 = v0 + vstep;
+            const bool two = v1 < S;
+            const float* p0 = x + (n * S + v0) * x_ld + cv * 8;
+            const float* p1 = x + (n * S + (two ? v1 : v0)) * x_ld + cv * 8;
+            const float4 a0 = *reinterpret_cast<const float4*>(p0), b0 = *reinterpret_cast<const float4*>(p0 + 4);
+            const float4 a1 = *reinterpret_cast<const float4*>(p1), b1 = *reinterpret_cast<const float4*>(p1 + 4);
+            float f[2][8] = {{a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w}, {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w}};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { acc[e] += f[u][e]; f[u][e] = fmaf(f[u][e], sc[e], sh[e]); }
+                uint4 o;
+                __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[u][2 * e] * mul, f[u][2 * e + 1] * mul);
+                *reinterpret_cast<uint4*>(out + (n * S + (u ? v1 : v0)) * C + cv * 8) = o;
             }
         }
-        uint4 o;
-        __half2* h = reinterpret_cast<__half2*>(&o);
+        if (colsum) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e] * mul, f[2 * e + 1] * mul);
-        *reinterpret_cast<uint4*>(out + vox * C + cv * 8) = o;
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_col[cv * 8 + e], acc[e]);
+        }
+    }
+    if (colsum) {
+        __syncthreads();
+        for (int i = ty * bx + tx; i < C; i += bx * by) atomicAdd(colsum + i, s_col[i]);
     }
 }
 
@@ -389,7 +417,8 @@ template <typename T, int VEC>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const T* __restrict__ dp, int64_t dp_ld,
                                    const T* __restrict__ add, int64_t add_ld, const float* __restrict__ coef, int64_t coef_nstride,
                                    T* __restrict__ out, int64_t out_ld,
-                                   int D, int H, int W, int C, int fd, int fh, int fw, int relu_mask, int64_t total) {
+                                   int D, int H, int W, int C, int fd, int fh, int fw, int relu_mask, int64_t total, float* __restrict__ absmax) {
+    unsigned am = 0;
     const unsigned cvec = C / VEC;
     const int Do = D / fd, Ho = H / fh, Wo = W / fw;
     const int64_t So = (int64_t)Do * Ho * Wo, Si = (int64_t)D * H * W;
@@ -452,10 +481,12 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const 
                         if (add) q += va[v];
                         if (relu_mask && !(t[v] > 0.f)) q = 0.f;
                         r[v] = q;
+                        am = absmax_acc(am, q);
                     }
                     Vec<T, VEC>::store(out + vi * out_ld + cv * VEC, r);
                 }
     }
+    absmax_flush(am, absmax);
 }
 
 // Max-pool backward for the windows the U-Net uses, (2|1, 2, 2), known at compile time: one thread per (window, channel vector)
@@ -477,8 +508,9 @@ template <typename T, int VEC, int FD>
 __global__ void __launch_bounds__(256)
 maxpool2_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const T* __restrict__ dp, int64_t dp_ld, const T* __restrict__ add, int64_t add_ld,
                     const float* __restrict__ coef, int64_t coef_nstride, T* __restrict__ out, int64_t out_ld, int D, int H, int W, int C,
-                    int relu_mask, unsigned total) {
+                    int relu_mask, unsigned total, float* __restrict__ absmax) {
     static_assert(VEC * sizeof(T) == 16, "16-byte channel vectors");
+    unsigned am = 0;
     constexpr int NW = FD * 4;
     const unsigned cvec = C / VEC;
     const int Ho = H / 2, Wo = W / 2;
@@ -546,10 +578,12 @@ maxpool2_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const T* __restrict__
                 if (add) g += coef ? fmaf(k0[v], va[v], fmaf(k1[v], t[v], k2[v])) : va[v];
                 if (relu_mask && !(t[v] > 0.f)) g = 0.f;
                 r[v] = g;
+                am = absmax_acc(am, g);
             }
             Vec<T, VEC>::store(reinterpret_cast<T*>(ob + (vox[q] * ol + cvo)), r);
         }
     }
+    absmax_flush(am, absmax);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1445,7 +1479,7 @@ int b200em_affine_apply(const void* x, int64_t x_ld, const float* scale_shift, v
 
 int b200em_norm_bwd_apply(const void* g, int64_t g_ld, const void* x, int64_t x_ld, const float* coef, const void* add,
                           int64_t add_ld, void* out, int64_t out_ld, int dtype, int N, int64_t S, int C, int relu_mask,
-                          void* stream) {
+                          float* absmax, void* stream) {
     B2_CHECK_ARG(g && out && N > 0 && C > 0 && S > 0 && g_ld >= C && out_ld >= C, "norm_bwd_apply: bad arguments");
     B2_CHECK_ARG(S * C < (1LL << 31) && N <= 65535, "norm_bwd_apply: sample too large for 32-bit indexing");
     B2_CHECK_ARG(S * C < (1LL << 31) && N <= 65535, "norm_bwd_apply: sample too large for 32-bit indexing");
@@ -1455,11 +1489,11 @@ int b200em_norm_bwd_apply(const void* g, int64_t g_ld, const void* x, int64_t x_
         if (can_vec<T>(C, {g_ld, x ? x_ld : (int64_t)V, add ? add_ld : (int64_t)V, out_ld}, {g, x, add, out})) {
             int64_t total = S * (C / V);
             norm_bwd_apply_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
-                (const T*)g, g_ld, (const T*)x, x_ld, coef, (const T*)add, add_ld, (T*)out, out_ld, S, C, relu_mask, total);
+                (const T*)g, g_ld, (const T*)x, x_ld, coef, (const T*)add, add_ld, (T*)out, out_ld, S, C, relu_mask, total, absmax);
         } else {
             int64_t total = S * C;
             norm_bwd_apply_kernel<T, 1><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
-                (const T*)g, g_ld, (const T*)x, x_ld, coef, (const T*)add, add_ld, (T*)out, out_ld, S, C, relu_mask, total);
+                (const T*)g, g_ld, (const T*)x, x_ld, coef, (const T*)add, add_ld, (T*)out, out_ld, S, C, relu_mask, total, absmax);
         }
     })
     B2_LAUNCH_CHECK();
@@ -1491,11 +1525,21 @@ int b200em_absmax_f32(const float* x, int64_t x_ld, int64_t rows, int C, float* 
     return 0;
 }
 
-int b200em_cvt_f16(const float* x, int64_t x_ld, const float* in_scale_shift, const float* absmax, void* out, int N, int64_t S,
-                   int C, void* stream) {
+int b200em_cvt_f16(const float* x, int64_t x_ld, const float* in_scale_shift, const float* absmax, void* out, float* colsum, int N,
+                   int64_t S, int C, void* stream) {
     B2_CHECK_ARG(x && out && N > 0 && S > 0 && C > 0 && N <= 65535, "cvt_f16: bad arguments");
     B2_CHECK_ARG(C % 8 == 0 && x_ld % 4 == 0 && aligned16(x) && aligned16(out), "cvt_f16: needs C % 8 == 0 and 16-byte aligned tensors");
-    cvt_f16_kernel<<<dim3(flat_grid(S * (C / 8), 256, N), N), 256, 0, (cudaStream_t)stream>>>(x, x_ld, in_scale_shift, absmax, (__half*)out, S, C);
+    B2_CHECK_ARG(!colsum || C <= 8192, "cvt_f16: colsum needs C <= 8192");
+    const int cvec = C / 8;
+    int bx = 1;
+    while (bx < cvec && bx < 256) bx <<= 1;           // power of two: 256 / bx voxels per block pass
+    const int by = 256 / bx;
+    int64_t blocks = (S + by - 1) / by;
+    int64_t cap = (int64_t)sm_count() * 16 / N + 1;
+    if (colsum && cap > (int64_t)sm_count() * 8 / N + 1) cap = (int64_t)sm_count() * 8 / N + 1;   // every block ends with C atomics
+    if (blocks > cap) blocks = cap;
+    cvt_f16_kernel<<<dim3((unsigned)blocks, N), dim3(bx, by), colsum ? C * sizeof(float) : 0, (cudaStream_t)stream>>>(
+        x, x_ld, in_scale_shift, absmax, (__half*)out, colsum, S, C);
     B2_LAUNCH_CHECK();
     return 0;
 }
@@ -1527,7 +1571,7 @@ int b200em_maxpool3d_fwd(const void* x, int64_t x_ld, void* y, int64_t y_ld, int
 
 int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp_ld, const void* add, int64_t add_ld,
                          const float* coef, int64_t coef_nstride, void* out, int64_t out_ld, int dtype, int N, int D, int H, int W,
-                         int C, int fd, int fh, int fw, int relu_mask, void* stream) {
+                         int C, int fd, int fh, int fw, int relu_mask, float* absmax, void* stream) {
     B2_CHECK_ARG(x && dp && out && N > 0 && C > 0 && fd > 0 && fh > 0 && fw > 0, "maxpool3d_bwd: bad arguments");
     B2_CHECK_ARG(!coef || add, "maxpool3d_bwd: coef needs the raw gradient in `add`");
     // voxels beyond the last full window are NOT written (the caller initialises them: they receive no pooled gradient)
@@ -1545,20 +1589,20 @@ int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp
             const size_t sm = coef ? C * 3 * sizeof(float) : 0;
             if (fd == 2)
                 maxpool2_bwd_kernel<T, V, 2><<<grid, 256, sm, (cudaStream_t)stream>>>((const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, coef, coef_nstride,
-                                                                                      (T*)out, out_ld, D, H, W, C, relu_mask, (unsigned)total);
+                                                                                      (T*)out, out_ld, D, H, W, C, relu_mask, (unsigned)total, absmax);
             else
                 maxpool2_bwd_kernel<T, V, 1><<<grid, 256, sm, (cudaStream_t)stream>>>((const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, coef, coef_nstride,
-                                                                                      (T*)out, out_ld, D, H, W, C, relu_mask, (unsigned)total);
+                                                                                      (T*)out, out_ld, D, H, W, C, relu_mask, (unsigned)total, absmax);
         } else if (can_vec<T>(C, {x_ld, dp_ld, add ? add_ld : (int64_t)V, out_ld}, {x, dp, add, out})) {
             int64_t total = So * (C / V);
             maxpool_bwd_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, coef ? C * 3 * sizeof(float) : 0, (cudaStream_t)stream>>>(
                 (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, coef, coef_nstride, (T*)out, out_ld, D, H, W, C, fd, fh, fw,
-                relu_mask, total);
+                relu_mask, total, absmax);
         } else {
             int64_t total = So * C;
             maxpool_bwd_kernel<T, 1><<<dim3(flat_grid(total, 256, N), N), 256, coef ? C * 3 * sizeof(float) : 0, (cudaStream_t)stream>>>(
                 (const T*)x, x_ld, (const T*)dp, dp_ld, (const T*)add, add_ld, coef, coef_nstride, (T*)out, out_ld, D, H, W, C, fd, fh, fw,
-                relu_mask, total);
+                relu_mask, total, absmax);
         }
     })
     B2_LAUNCH_CHECK();

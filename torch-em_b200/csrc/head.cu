@@ -222,7 +222,8 @@ template <typename T, int CIN, int COUT>
 __global__ void __launch_bounds__(256, 2)
 head_bwd_small_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, const T* __restrict__ x, int64_t x_ld,
                       const float* __restrict__ w, T* __restrict__ dx, int64_t dx_ld, float* __restrict__ dw,
-                      float* __restrict__ db, int64_t S, int act, int relu_mask, int64_t total, int cin_total) {
+                      float* __restrict__ db, int64_t S, int act, int relu_mask, int64_t total, int cin_total, float* __restrict__ absmax) {
+    unsigned am = 0;
     constexpr int V = FullVec<T>::value;
     constexpr int MAXC = 128;
     __shared__ float red[COUT * MAXC + COUT];        // block-level dW | db partial sums
@@ -265,10 +266,12 @@ head_bwd_small_kernel(const float* __restrict__ grad_out, const float* __restric
                     aw[j][c + k] = fmaf(dz[j], xv[k], aw[j][c + k]);
                 }
                 r[k] = (relu_mask && !(xv[k] > 0.f)) ? 0.f : g;
+                am = absmax_acc(am, r[k]);
             }
             if (dx) Vec<T, V>::store(dx + vox * dx_ld + c0 + c, r);
         }
     }
+    absmax_flush(am, absmax);
     // block reduction: warp shuffles, one shared-memory atomic per warp and value, then COUT*cin_total + COUT atomics per block
 #pragma unroll
     for (int j = 0; j < COUT; ++j) {
@@ -344,10 +347,10 @@ static void launch_head_fwd_small(unsigned blocks, cudaStream_t st, const void* 
 template <typename T>
 static void launch_head_bwd_small(unsigned blocks, cudaStream_t st, const float* grad_out, const float* out, const void* x,
                                   int64_t x_ld, const float* w, void* dx, int64_t dx_ld, float* dw, float* db, int64_t S, int Cin,
-                                  int Cout, int act, int relu_mask, int64_t total) {
+                                  int Cout, int act, int relu_mask, int64_t total, float* absmax) {
 #define B2_HEAD_BWD_SMALL(CI, CO)                                                                                             \
     head_bwd_small_kernel<T, CI, CO><<<blocks, 256, 0, st>>>(grad_out, out, (const T*)x, x_ld, w, (T*)dx, dx_ld, dw, db, S, act, \
-                                                             relu_mask, total, Cin)
+                                                             relu_mask, total, Cin, absmax)
     if (Cin % 32 == 0 && Cout == 2) B2_HEAD_BWD_SMALL(32, 2);
     else if (Cin % 32 == 0) B2_HEAD_BWD_SMALL(32, 1);
     else if (Cout == 2) B2_HEAD_BWD_SMALL(16, 2);
@@ -380,7 +383,7 @@ int b200em_head_fwd(const void* x, int64_t x_ld, int dtype, const float* w, cons
 
 int b200em_head_bwd(const float* grad_out, const float* out, const void* x, int64_t x_ld, int dtype, const float* w,
                     void* dx, int64_t dx_ld, float* dw, float* db, int N, int64_t S, int Cin, int Cout, int act,
-                    int relu_mask, void* stream) {
+                    int relu_mask, float* absmax, void* stream) {
     B2_CHECK_ARG(grad_out && out && x && w && dw && N > 0 && S > 0 && Cin > 0 && Cout > 0 && x_ld >= Cin, "head_bwd: bad arguments");
     B2_CHECK_ARG(!dx || dx_ld >= Cin, "head_bwd: dx pitch smaller than Cin");
     B2_CHECK_ARG(act >= 0 && act <= 3, "head_bwd: unknown activation code %d", act);
@@ -394,7 +397,7 @@ int b200em_head_bwd(const float* grad_out, const float* out, const void* x, int6
         B2_DISPATCH_DTYPE(dtype, T, {
             if (head_bwd_small_ok<T>(x, x_ld, dx, dx_ld, Cin, Cout)) {
                 launch_head_bwd_small<T>((unsigned)(blocks / 4 * 4 > 0 ? blocks / 4 * 4 : 4), (cudaStream_t)stream, grad_out, out, x, x_ld, w, dx, dx_ld, dw, db, S, Cin, Cout,
-                                         act, relu_mask, total);
+                                         act, relu_mask, total, absmax);
                 done = true;
             }
         })
@@ -411,6 +414,8 @@ int b200em_head_bwd(const float* grad_out, const float* out, const void* x, int6
         })
         B2_LAUNCH_CHECK();
     }
+    // the generic kernel does not track max |dx|: one more pass where the caller asked for it (fp32 heads wider than 128 channels)
+    if (absmax && dx && dtype == B200EM_F32) return b200em_absmax_f32((const float*)dx, dx_ld, total, Cin, absmax, nullptr, stream);
     return 0;
 }
 

@@ -19,8 +19,12 @@ namespace b200em {
 bool umma_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC, int* NP, bool f32);   // conv_umma.cu
 bool ds_pack_layout(int Cin, int Cout, int kd, int kh, int kw, int* CC);              // conv_umma_ds.cu
 
+// ci channels per block tile: 32 (every layer but the first few: 3.4 KB contiguous per output channel row, 27 loads in flight per
+// thread) or 8; b200em_pack_batch_prepare and the kernel agree through this function
+__host__ __device__ inline int pack_tile_ci(int Cin, int layout) { return (Cin % 32 == 0 && layout != B200EM_PACK_PLAIN_TF32) ? 32 : 8; }
+
 __global__ void __launch_bounds__(256) pack_batch_kernel(const b200em_pack_job* __restrict__ jobs, int njobs) {
-    __shared__ float tile[8][8 * 27];
+    __shared__ float tile[8][32 * 27 + 1];             // +1: rows of 864 words would all start in the same bank
     __shared__ b200em_pack_job job;
     if (threadIdx.x == 0) {
         // jobs are sorted by block_begin: last job whose first block is <= blockIdx.x
@@ -34,14 +38,26 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const b200em_pack_job* 
     __syncthreads();
     const int Cout = job.Cout, Cin = job.Cin, dgrad = job.dgrad, CC = job.CC;
     const int taps = job.kd * job.kh * job.kw;
+    const int TCI = pack_tile_ci(Cin, job.layout);
     const int local = (int)blockIdx.x - job.block_begin;
-    const int tiles_ci = Cin / 8;
-    const int co0 = (local / tiles_ci) * 8, ci0 = (local % tiles_ci) * 8;
+    const int tiles_ci = Cin / TCI;
+    const int co0 = (local / tiles_ci) * 8, ci0 = (local % tiles_ci) * TCI;
     const float* __restrict__ w = job.w;
-    const int run = 8 * taps;                          // floats per output channel in this tile (contiguous in w)
-    for (int i = threadIdx.x; i < 8 * run; i += blockDim.x) {
-        const int c = i / run, r = i % run;
-        tile[c][r] = w[((size_t)(co0 + c) * Cin + ci0) * taps + r];
+    const int run = TCI * taps;                        // floats per output channel in this tile (contiguous in w)
+    if (TCI == 32) {
+        // one warp per output-channel row, 16-byte loads (the row is 32 * taps * 4 bytes from a 16-byte aligned start), no divisions
+        const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(w + ((size_t)(co0 + c) * Cin + ci0) * taps);
+        for (int q = lane; q < run / 4; q += 32) {
+            const float4 v = __ldg(src + q);
+            float* d = &tile[c][4 * q];
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < 8 * run; i += blockDim.x) {
+            const int c = i / run, r = i % run;
+            tile[c][r] = w[((size_t)(co0 + c) * Cin + ci0) * taps + r];
+        }
     }
     __syncthreads();
     const int Kc = dgrad ? Cout : Cin;                 // reduction channels of the packed operand
@@ -65,18 +81,27 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const b200em_pack_job* 
     const int Nc = dgrad ? Cin : Cout;                 // output channels of the packed operand
     const int nchunks = Kc / CC, J = CC / 8;
     const int thw = job.kh * job.kw;
-    for (int u = threadIdx.x; u < 8 * taps; u += blockDim.x) {
-        const int nl = u % 8, tp = u / 8;              // n within the tile, filter tap (torch order)
+    const bool f16 = job.layout == B200EM_PACK_PLAIN_F16;
+    // 16-byte units (8 reduction channels of one operand row n and tap): forward n = co (8 rows) x TCI/8 ci groups, data gradient
+    // n = ci (TCI rows) x the tile's one co group; consecutive threads take consecutive n (adjacent 16-byte units of the image)
+    const int nrows = dgrad ? TCI : 8, kgroups = dgrad ? 1 : TCI / 8;
+    for (int u = threadIdx.x; u < nrows * kgroups * taps; u += blockDim.x) {
+        int nl, kg = 0, tp;                            // (rows x k-groups) per tap is 32 or 8: shifts, no divisions
+        if (TCI == 32) {
+            tp = u >> 5;
+            if (dgrad) nl = u & 31; else { nl = u & 7; kg = (u >> 3) & 3; }
+        } else {
+            nl = u & 7; tp = u >> 3;
+        }
         __align__(16) __nv_bfloat16 v[8];
-        const bool f16 = job.layout == B200EM_PACK_PLAIN_F16;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             // forward: n = co, k = ci;  dgrad: n = ci, k = co
-            const float f = dgrad ? tile[e][nl * taps + tp] : tile[nl][e * taps + tp];
+            const float f = dgrad ? tile[e][nl * taps + tp] : tile[nl][(kg * 8 + e) * taps + tp];
             if (f16) reinterpret_cast<__half*>(v)[e] = __float2half_rn(f);
             else v[e] = __float2bfloat16_rn(f);
         }
-        const int n_ = (dgrad ? ci0 : co0) + nl, k0 = dgrad ? co0 : ci0, t_ = dgrad ? taps - 1 - tp : tp;
+        const int n_ = (dgrad ? ci0 : co0) + nl, k0 = dgrad ? co0 : ci0 + kg * 8, t_ = dgrad ? taps - 1 - tp : tp;
         const int chunk = k0 / CC, j = (k0 % CC) / 8;
         size_t o;
         if (job.layout == B200EM_PACK_PLAIN || f16) {
@@ -102,6 +127,7 @@ int b200em_pack_batch_prepare(b200em_pack_job* jobs, int njobs, int* total_block
     int blocks = 0;
     for (int i = 0; i < njobs; ++i) {
         b200em_pack_job& j = jobs[i];
+        B2_CHECK_ARG(aligned16(j.w) && aligned16(j.packed), "pack_batch_prepare: job %d: weight and image must be 16-byte aligned", i);
         B2_CHECK_ARG(j.Cout > 0 && j.Cin > 0 && j.Cout % 8 == 0 && j.Cin % 8 == 0 && j.kd * j.kh * j.kw <= 27,
                      "pack_batch_prepare: job %d: channels must be multiples of 8 and taps <= 27", i);
         const int n_ = j.dgrad ? j.Cin : j.Cout, k_ = j.dgrad ? j.Cout : j.Cin;   // operand's output / reduction channels
@@ -121,7 +147,7 @@ int b200em_pack_batch_prepare(b200em_pack_job* jobs, int njobs, int* total_block
             return 2;
         }
         j.block_begin = blocks;
-        blocks += (j.Cout / 8) * (j.Cin / 8);
+        blocks += (j.Cout / 8) * (j.Cin / pack_tile_ci(j.Cin, j.layout));
     }
     *total_blocks = blocks;
     return 0;
