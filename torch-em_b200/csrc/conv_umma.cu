@@ -51,6 +51,7 @@ struct ConvUmmaParams {
     float* sums;
     const void* dot_x; long long dot_ld;   // non-null: sums = (sum y, sum y * dot_x) -- the norm-backward reductions
     const float* x_absmax;                 // h16 path: device max |x| the fp16 operand was scaled by (common.cuh h16_shift), or null
+    int prefetch;                          // bring-up switch (env B200EM_PREFETCH=0): no L1 prefetch of the dot_x rows
     int ksplit;                            // > 1: gridDim.z CTAs share an output tile, each reducing a range of the Cin chunks (split-K)
     float* ws_acc; unsigned* ws_cnt;       // split-K: zeroed fp32 partial sums [voxel][Cout] and per-(item, nblk) arrival counters
     int N, D, H, W, Cin, Cout;
@@ -115,6 +116,8 @@ __device__ __forceinline__ void load_row(const T* __restrict__ src, bool valid, 
 // loop is straight-line code with immediate operand offsets (it bounds the small-N layers otherwise).
 // TA = operand type in shared memory (activations and packed weights), TO = type of y and dot_x in global memory:
 // (bf16, bf16), (float, float) = TF32, (__half, float) = the h16 path (fp32 tensors, fp16 operand copies).
+// (448 threads = 14 warps put 4 warps on two of the SM's four sub-partitions, each with 16 K registers: 128 registers per thread
+// is the hardware limit for this block size, whatever __maxnreg__ says -- a launch with 144 fails.)
 template <typename TA, typename TO, int R_, int KC_>
 __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -339,6 +342,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                 if (!last) continue;
                 __threadfence();
             }
+            // norm-backward reductions (data gradient): the dot_x row of a 32-column block is PREFETCHED into L1 one block ahead --
+            // loaded only after the accumulators have arrived it would expose one global-memory latency per block and the epilogue,
+            // not the MMAs, would bound the layer (fp32 rows are 128 bytes per thread).  A prefetch instruction, not a register
+            // prefetch: the epilogue is at the register limit.
+            const bool pre = p.dot_x != nullptr && p.sums != nullptr && valid_hw && p.prefetch;
+            auto prefetch_x = [&](int r_, int cb_) {
+                const size_t vox_ = (((size_t)n * p.D + d0 + r_) * p.H + gh) * p.W + gw;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const TO*>(p.dot_x) + vox_ * p.dot_ld + nblk * p.NP + cb_));
+            };
+            if (pre && rmax > 0) prefetch_x(0, 0);
             for (int r = 0; r < rmax; ++r) {
                 const int gd = d0 + r;
                 const size_t vox = (((size_t)n * p.D + gd) * p.H + gh) * p.W + gw;
@@ -371,6 +384,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                         if (p.sums) {
                             float s1[32], s2[32];
                             if (p.dot_x) {
+                                if (pre) {               // next block of this item (same slab, or the first block of the next slab)
+                                    if (cb + 32 < p.NP) prefetch_x(r, cb + 32);
+                                    else if (r + 1 < rmax) prefetch_x(r + 1, 0);
+                                }
                                 const TO* xq = reinterpret_cast<const TO*>(p.dot_x) + vox * p.dot_ld + nblk * p.NP + cb;
                                 load_row<TO, 32>(xq, valid_hw, s2);
 #pragma unroll
@@ -866,6 +883,7 @@ static int launch_conv_umma(const void* x, int64_t x_ld, const float* in_scale_s
         }
     }
     p.ksplit = ksplit; p.ws_acc = ws_acc; p.ws_cnt = ws_cnt;
+    { const char* e = getenv("B200EM_PREFETCH"); p.prefetch = e ? atoi(e) : 1; }
     p.R = s.R; p.NP = s.NP; p.CC = s.CC; p.nchunks = Cin / s.CC; p.G = s.G; p.acc_bufs = s.acc_bufs; p.nstage = s.nstage;
     p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + s.R - 1) / s.R;
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
