@@ -10,6 +10,8 @@ python bench.py --config cfg3 --steps 10 --warmup 3 --no-cpu-baseline > $out/${t
 python bench.py --config cfg4 --steps 5 --warmup 3 --no-cpu-baseline > $out/${tag}_bench_cfg4_n1.json 2> $out/${tag}_bench_cfg4_n1.err
 python bench.py --config cfg5 --steps 3 --warmup 2 > $out/${tag}_bench_cfg5.json 2> $out/${tag}_bench_cfg5.err
 python scripts/bench_layers.py > $out/${tag}_bench_layers.txt 2>&1
+python scripts/bench_layers.py --config cfg4 > $out/${tag}_bench_layers_cfg4.txt 2>&1
+python scripts/bench_elementwise.py > $out/${tag}_bench_elementwise.txt 2>&1
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches_train_step.csv python scripts/profile_step.py > $out/${tag}_prof_step.log 2>&1
 python scripts/summarize_launches.py $out/${tag}_launches_train_step.csv > $out/${tag}_launches_train_step_summary.txt
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches_predict.csv python scripts/profile_predict.py > $out/${tag}_prof_predict.log 2>&1
@@ -18,4 +20,9 @@ B200EM_CONFIG=cfg4 ncu --profile-from-start off --metrics gpu__time_duration.sum
 python scripts/summarize_launches.py $out/${tag}_launches_cfg4.csv > $out/${tag}_launches_cfg4_summary.txt
 ncu --set full --import-source on --clock-control none --profile-from-start off -f -o $out/${tag}_kernels python scripts/profile_kernels.py > $out/${tag}_prof_kernels.log 2>&1
 ncu -i $out/${tag}_kernels.ncu-rep --page raw --csv > $out/${tag}_kernels_raw.csv 2> /dev/null
+python scripts/reduce_ncu_raw.py $out/${tag}_kernels_raw.csv $out/${tag}_kernels_ncu_full.csv
+rm -f $out/${tag}_kernels.ncu-rep
+# compute-sanitizer over the tcgen05 kernel tests (memcheck + racecheck): small cases, bounded
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_umma.py -x -q -k "(test_umma_conv_forward_and_dgrad or test_umma_wgrad) and case2 or (test_plain_conv_split_k and 3-case1)" > $out/${tag}_sanitizer_memcheck.log 2>&1
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_umma.py -x -q -k "(test_umma_conv_forward_and_dgrad or test_umma_wgrad) and case2" > $out/${tag}_sanitizer_racecheck.log 2>&1
 ls -la $out | tail -30

@@ -13,7 +13,8 @@ from torch_em_b200.backend import default_backend
 dev = "cuda:0"
 B = default_backend()
 N, S = 4, 128
-which = set((os.environ.get("KERNELS") or "ds_fwd,ds_dgrad,cs_wgrad,plain_fwd,plain_deep,tf32_fwd,upsample_fwd,upsample_bwd,maxpool_bwd,norm_bwd_apply").split(","))
+which = set((os.environ.get("KERNELS") or "ds_fwd,ds_dgrad,cs_wgrad,plain_fwd,plain_deep,h16_fwd,h16_dgrad,h16_wgrad,tf32_fwd,upsample_fwd,upsample_bwd,maxpool_bwd,"
+                                          "norm_bwd_apply,cvt_f16,pack").split(","))
 torch.manual_seed(0)
 x = torch.randn((N, S, S, S, 32), device=dev).bfloat16()
 dz = torch.randn((N, S, S, S, 32), device=dev).bfloat16()
@@ -38,7 +39,7 @@ dlo = torch.empty_like(lo)
 x1 = torch.randn((N, S, S, S, 1), device=dev).bfloat16()
 ss1 = torch.ones((N, 1, 2), device=dev)
 coef = torch.randn((N, 64, 3), device=dev)
-# deep level (L4 of cfg2: 512 -> 512 on 8^3) and the TF32 path (cfg4 L1: 128 -> 128 on 64^3, batch 1, fp32)
+# deep level (L4 of cfg2: 512 -> 512 on 8^3, split-K) and the fp32 paths (cfg4 L1: 128 -> 128 on 64^3, batch 1): h16 (default) / TF32
 x4 = torch.randn((N, 8, 8, 8, 512), device=dev).bfloat16()
 w4 = torch.randn((512, 512, 3, 3, 3), device=dev) * 0.01
 pk4 = B.pack(("prof", 512), w4)
@@ -47,7 +48,15 @@ torch.backends.cudnn.allow_tf32 = True
 xf = torch.randn((1, 64, 64, 64, 128), device=dev)
 wf = torch.randn((128, 128, 3, 3, 3), device=dev) * 0.03
 pkf = B.pack(("prof", "tf32"), wf)
+from torch_em_b200.backend import CudaBackend
+B32 = CudaBackend(use_h16=False)
 yf = torch.empty_like(xf)
+dzf = torch.randn((1, 64, 64, 64, 128), device=dev) * 1e-6
+gf = torch.empty_like(xf)
+dsf = torch.zeros((1, 128, 2), device=dev)
+dwf = torch.zeros_like(wf)
+dbf = torch.zeros(128, device=dev)
+ps_big = B.pack_set({"big": torch.randn((512, 512, 3, 3, 3), device=dev) * 0.01})
 ssf = torch.ones((1, 128, 2), device=dev)
 sf = torch.zeros((1, 128, 2), device=dev)
 
@@ -58,7 +67,12 @@ runs = {
     "plain_fwd": lambda: B.conv(x2, ss2, pk2, torch.zeros(128, device=dev), y2, s2, (3, 3, 3), True, False),
     "upsample_fwd": lambda: B.upsample_fwd(lo, cat[..., :32], (2, 2, 2), sums),
     "plain_deep": lambda: B.conv(x4, None, pk4, torch.zeros(512, device=dev), y4, None, (3, 3, 3), True, False),
-    "tf32_fwd": lambda: B.conv(xf, ssf, pkf, torch.zeros(128, device=dev), yf, sf, (3, 3, 3), True, False),
+    "h16_fwd": lambda: B.conv(xf, ssf, pkf, torch.zeros(128, device=dev), yf, sf, (3, 3, 3), True, False),
+    "h16_dgrad": lambda: B.conv(dzf, None, pkf, None, gf, dsf, (3, 3, 3), False, True, dot_x=xf),
+    "h16_wgrad": lambda: B.wgrad(xf, ssf, dzf, dwf, dbf, (3, 3, 3)),
+    "tf32_fwd": lambda: B32.conv(xf, ssf, pkf, torch.zeros(128, device=dev), yf, sf, (3, 3, 3), True, False),
+    "cvt_f16": lambda: B.to_h16(xf, ssf),
+    "pack": lambda: ps_big.refresh_fwd(),
     "upsample_bwd": lambda: B.upsample_bwd(cat[..., :32], dlo, (2, 2, 2), zlow=lo, coef=coef[:, :32]),
     "maxpool_bwd": lambda: B.maxpool_bwd(cat[..., 32:], lo, cat[..., :32], y, (2, 2, 2), 1, coef=coef[:, 32:]),
     "norm_bwd_apply": lambda: B.norm_bwd_apply(g, x, coef[:, :32].contiguous(), None, y, 1),
