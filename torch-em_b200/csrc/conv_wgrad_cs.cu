@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
         if (prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && w8 == 0)
             printf("[cs prof] loader warp 0: total %lld cyc, %lld stages: wait empty %lld, load %lld, norm/db/arrive %lld\n", clock64() - pf_t0,
                    pf_n, pf_wait, pf_load, pf_rest);
+        asm volatile("bar.sync 4, %0;" ::"n"(CS_THREADS) : "memory");      // ring hand-over to the epilogue (see there)
     } else if (warp == CS_W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
@@ -313,6 +314,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
             if (prof && blockIdx.x == 0 && blockIdx.y == 0)
                 printf("[cs prof] mma: total %lld cyc, %lld stages: wait full %lld\n", clock64() - pf_t0, pf_n, pf_w);
         }
+        __syncwarp();
+        asm volatile("bar.sync 4, %0;" ::"n"(CS_THREADS) : "memory");
     } else if (warp < 4) {
         // ===================== epilogue: TMEM -> shared-memory transpose -> coalesced vector reductions into dW =====================
         // dW is (Cout, Cin, 27) fp32: for one output channel the CTA's 32 input channels x 27 taps are 864 CONTIGUOUS floats.  A
@@ -322,6 +325,10 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
         // and leave as 16-byte red.global.add.v4.f32 over contiguous memory.
         mbar_wait(acc_full, 0);
         tc_fence_after();
+        // acc_full (tcgen05.commit of the last MMA) already orders every loader write and every tensor-core read of the ring before
+        // this point; the CTA-wide barrier states the same hand-over in terms compute-sanitizer's racecheck understands (the loader
+        // and MMA warps arrive when their loops end -- nobody waits for long)
+        asm volatile("bar.sync 4, %0;" ::"n"(CS_THREADS) : "memory");
         const int a = warp;                              // depth tap of this warp's 32 lanes (a == 3: ignored rows)
         constexpr int taps = 27, ROW = 32 * taps;        // floats per output channel of this CTA's (ci chunk, co block) tile
         float* stage = reinterpret_cast<float*>(smem);   // [32 co][32 ci][27 taps] = 110,592 B <= (NS + 3) * CS_XSLOT + NS * CS_ZSLOT
@@ -344,6 +351,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv3d_wgrad_cs_kernel(const Wg
         const int t = threadIdx.x;                       // 0..127
         float* dwb = p.dw + ((size_t)(cob * CS_NB) * p.Cin + chunk * 32) * taps;
         const size_t co_stride = (size_t)p.Cin * taps;
+        // (fire-and-forget reductions also where this CTA is the tile's only contributor: a read-add-write of the 110 KB tile is a
+        // chain of dependent round trips per thread and measured 3x slower on the 2048 -> 2048 layer)
         if ((reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
             for (int i = t; i < CS_NB * (ROW / 4); i += 128) {
                 const int co = i / (ROW / 4), q = i % (ROW / 4);
