@@ -197,6 +197,11 @@ WG_CASES = [
     (1, 21, 20, 11, 64, 64, (3, 1, 3)),
     (2, 24, 48, 40, 64, 32, (3, 3, 3)),
     (1, 9, 33, 17, 96, 64, (3, 3, 3)),
+    # 1x1x1 filters (the up-sampler convs): 64 / 128 input channels per CTA instead of 32 (M rows = channels of one slice)
+    (2, 5, 20, 13, 64, 32, (1, 1, 1)),
+    (1, 7, 17, 9, 128, 64, (1, 1, 1)),
+    (2, 3, 8, 8, 512, 256, (1, 1, 1)),
+    (1, 9, 33, 17, 192, 48, (1, 1, 1)),
 ]
 
 

@@ -586,6 +586,8 @@ struct WgradUmmaParams {
     long long items;
     int x_bytes, dz_bytes;
     int debug;                                 // bring-up switches (env B200EM_DEBUG): 1 no operand loads, 4 no MMAs, 8 no epilogue atomics
+    int CH;                                    // input channels per CTA: 32 (M rows = 4 depth slices x 32 channels: the depth taps), or for
+                                               // 1x1x1 filters 32 / 64 / 128 (M rows = 128 / CH slices x CH channels, rows [0, CH) useful)
     int fp16;                                  // 2-byte operands are IEEE fp16 (the h16 path of fp32 activations), not bf16
     const float* x_absmax; const float* z_absmax;   // h16: device max |.| the operands were scaled by (common.cuh h16_shift), or null
 };
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
     extern __shared__ __align__(128) uint8_t smem[];
     // carve: X[2] | pad slices | DZ[2] | db sums[NB] | barriers | tmem ptr
     constexpr int EPU = 16 / (int)sizeof(TA);                  // channels per 16-byte unit
-    constexpr int J = 32 / EPU;                                // 32-channel chunk = 4 (bf16) or 8 (fp32) planes per slice
+    const int J = p.CH / EPU;                                  // planes per slice: a 32-channel chunk = 4 (bf16) or 8 (fp32); up to 16 for 1x1x1 filters
     constexpr int WG_R = WgR<TA>::value;
     constexpr int KROWS = sizeof(TA) == 4 ? 1 : 2;             // tile rows (8 voxels each) per MMA K step: K = 8 (tf32) or 16
     const int nslices = WG_R + p.kd - 1;
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
             coords(item, n, d0, h0, w0);
             const int buf = fill & 1;
             mbar_wait(&empty[buf], ((fill >> 1) & 1) ^ 1);
-            const int ch0 = chunk * 32 + j * EPU;
+            const int ch0 = chunk * p.CH + j * EPU;
             if (p.in_ss && n != cur_n) {           // scale/shift of this thread's channels: reload only when the sample changes
                 const float* q = p.in_ss + ((size_t)n * p.Cin + ch0) * 2;
 #pragma unroll
@@ -769,10 +771,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_wgrad_umma_kernel(const Wgr
         const int a = warp;                              // depth tap of this warp's 32 lanes (a == 3: ignored rows)
         const int taps = p.kd * tap9;
         const float osc = pow2i(-h16_shift(p.x_absmax) - h16_shift(p.z_absmax));
-        if (a < p.kd && !(p.debug & 8)) {
-            const int ci = chunk * 32 + lane;
+        // rows [32 a, 32 a + 32): depth tap a of the CTA's 32 channels -- or, for a 1x1x1 filter, channels [32 a, 32 a + 32) of its CH
+        const bool wide = p.CH > 32;
+        if ((wide ? 32 * a < p.CH : a < p.kd) && !(p.debug & 8)) {
+            const int ci = wide ? chunk * p.CH + 32 * a + lane : chunk * 32 + lane;
             for (int tp = 0; tp < tap9; ++tp) {
-                const int tap = a * tap9 + tp;
+                const int tap = wide ? 0 : a * tap9 + tp;
                 for (int cb = 0; cb < p.NB; cb += 16) {
                     uint32_t raw[16];
                     tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + tp * p.NB + cb, raw);
@@ -916,7 +920,6 @@ static int launch_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_
                              const float* x_absmax = nullptr, const float* z_absmax = nullptr) {
     constexpr int EPU = 16 / (int)sizeof(TA);
     constexpr int WG_R = WgR<TA>::value;
-    constexpr int J = 32 / EPU;
     B2_CHECK_ARG(x && dz && dw && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_wgrad_umma: bad arguments");
     B2_CHECK_ARG((kd == 1 || kd == 3) && (kh == 1 || kh == 3) && (kw == 1 || kw == 3), "conv3d_wgrad_umma: kernel dims must be 1 or 3");
     int NB;
@@ -935,14 +938,21 @@ static int launch_wgrad_umma(const void* x, int64_t x_ld, const float* in_scale_
     p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_d = (D + WG_R - 1) / WG_R;
     p.items = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
     B2_CHECK_ARG(p.items < (1LL << 31), "conv: too many work items for 32-bit indexing");
+    // 1x1x1 filters (the up-sampler convs): there are no depth taps to stack along M, so the 128 MMA rows hold up to 128 input
+    // channels of ONE slice instead of 32 channels of four -- 4x fewer CTAs per layer (each re-reads the dz tile), 4x the split over
+    // voxel tiles (these layers are a serial chain of small tile loads per CTA), up to all rows useful instead of a quarter
+    p.CH = 32;
+    if (kd == 1 && kh == 1 && kw == 1 && sizeof(TA) == 2 && !getenv("B200EM_WG_NARROW")) p.CH = Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : 32);
+    const int J = p.CH / EPU;
+    const int span = p.CH > 32 ? 128 / p.CH : 4;  // slices an MMA's 128 rows span
     p.x_bytes = (WG_R + kd - 1) * J * PLANE;
     p.dz_bytes = WG_R * (NB / EPU) * WG_DZ_PLANE;
-    p.pad_bytes = (4 - kd) * J * PLANE;          // slab r reads slices r .. r+3; WG_R + kd - 1 are loaded
+    p.pad_bytes = (span - kd) * J * PLANE;       // slab r reads slices r .. r + span - 1; WG_R + kd - 1 are loaded
     { const char* e = getenv("B200EM_DEBUG"); p.debug = e ? atoi(e) : 0; }
     const int smem_bytes = 2 * p.x_bytes + p.pad_bytes + 2 * p.dz_bytes + NB * 4 + 8 * 8 + 16 + 9 * 4 + 128;
     B2_CHECK_ARG(smem_bytes <= MAX_SMEM, "conv3d_wgrad_umma: shared memory budget exceeded");
     B2_CUDA(cudaFuncSetAttribute(conv3d_wgrad_umma_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
-    const int pairs = (Cin / 32) * p.nco;
+    const int pairs = (Cin / p.CH) * p.nco;
     long long splits = sm_count() / pairs;
     if (splits < 1) splits = 1;
     if (splits > p.items) splits = p.items;
