@@ -182,3 +182,66 @@ def _model_fp32_vs_reference_tf32(B, kw, shape, path, seed):
             bad.append((k, e_o, e_r))
     assert not bad, bad
     return (tot_o / tot_r) ** 0.5
+
+
+def test_h16_range_scaling_edge_cases(tf32):
+    """The fp16 operand copies of the h16 path: an all-zero gradient (max |x| = 0: no scale) gives exactly zero, gradients far below
+    and activations far above fp16's range survive through the power-of-two scale, and a non-finite value switches the scale off
+    and propagates like it does in fp32."""
+    from torch_em_b200.backend import CudaBackend
+    B = CudaBackend()
+    N, D, H, W, Cin, Cout, k = 1, 4, 16, 8, 32, 64, (3, 3, 3)
+    w = rnd((Cout, Cin) + k, 2, scale=(Cin * 27) ** -0.5)
+    pk = B.pack(("h16-edge",), w.to(DEV))
+    x = rnd((N, D, H, W, Cin), 1)
+    for scale in (0.0, 1e-30, 1e-12, 1e6, 1e20):
+        dz = (rnd((N, D, H, W, Cout), 6) * scale)
+        g_ref = torch.empty((N, D, H, W, Cin))
+        EMU.conv(dz, None, P(w), None, g_ref, None, k, False, True)
+        dw_ref, db_ref = torch.zeros_like(w), torch.zeros(Cout)
+        EMU.wgrad(x, None, dz, dw_ref, db_ref, k)
+        dzd = dz.to(DEV)
+        g = torch.empty((N, D, H, W, Cin), device=DEV)
+        dw, db = torch.zeros_like(w).to(DEV), torch.zeros(Cout, device=DEV)
+        B.calls.clear()
+        B.wgrad(x.to(DEV), None, dzd, dw, db, k)
+        B.conv(dzd, None, pk, None, g, None, k, False, True)
+        torch.cuda.synchronize()
+        assert B.calls["h16:wgrad"] == 1 and B.calls["h16:dgrad"] == 1
+        for got, ref in ((g, g_ref), (dw, dw_ref), (db, db_ref)):
+            assert bool(torch.isfinite(got).all())
+            if scale == 0.0:
+                assert float(got.abs().max()) == 0.0
+            else:
+                np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=3e-3, atol=3e-3 * float(ref.abs().max()))
+    # un-normalised activations beyond fp16's largest finite value (65504): the forward operand is range-scaled as well
+    xb = x * 3e5
+    y_ref = torch.empty((N, D, H, W, Cout))
+    EMU.conv(xb, None, P(w), None, y_ref, None, k, False, False)
+    y = torch.empty((N, D, H, W, Cout), device=DEV)
+    B.conv(xb.to(DEV), None, pk, None, y, None, k, False, False)
+    np.testing.assert_allclose(y.cpu().numpy(), y_ref.numpy(), rtol=3e-3, atol=3e-3 * float(y_ref.abs().max()))
+    # a NaN in the gradient reaches the outputs (as it would in fp32), everything else stays finite-or-NaN, nothing traps
+    dz = rnd((N, D, H, W, Cout), 6)
+    dz[0, 1, 2, 3, 4] = float("nan")
+    g = torch.empty((N, D, H, W, Cin), device=DEV)
+    B.conv(dz.to(DEV), None, pk, None, g, None, k, False, True)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(g[0, 1, 2, 3]).any()) and bool(torch.isfinite(g[0, 3, 12, 6]).all())
+
+
+def test_h16_prediction_matches_exact_fp32(tf32):
+    """Inference without autocast (predict_with_halo's default, prediction.py:252-275) takes the h16 path when TF32 is allowed: same
+    prediction as the exact-fp32 kernels to TF32-class accuracy."""
+    torch.manual_seed(3)
+    net = tb.UNet3d(1, 2, depth=3, initial_features=32, final_activation="Sigmoid").to(DEV).eval()
+    x = torch.randn(1, 1, 32, 48, 40, device=DEV)
+    from torch_em_b200.backend import default_backend
+    B = default_backend()
+    with torch.no_grad():
+        B.calls.clear()
+        y16 = net(x)
+        assert B.calls.get("h16:fwd", 0) > 0 and not any(k_.startswith("tf32") for k_ in B.calls), dict(B.calls)
+        torch.backends.cudnn.allow_tf32 = False
+        y32 = net(x)
+    assert float((y16 - y32).abs().max()) < 5e-3 and float((y16 - y32).norm() / y32.norm()) < 1e-3
