@@ -374,9 +374,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
                             tmem_ld_wait();
                         }
                         float v[32];
+                        if (p.bias) {                    // 16-byte shared-memory loads, none for the data gradient (no bias)
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cb + 4 * q);
+                                v[4 * q] = b4.x; v[4 * q + 1] = b4.y; v[4 * q + 2] = b4.z; v[4 * q + 3] = b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                        }
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            float f = fmaf(__uint_as_float(raw[i]), osc, s_bias[cb + i]);
+                            float f = fmaf(__uint_as_float(raw[i]), osc, v[i]);
                             if (p.relu) f = fmaxf(f, 0.f);
                             v[i] = round_as<TO>(f);
                         }

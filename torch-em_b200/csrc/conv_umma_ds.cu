@@ -78,10 +78,22 @@ __device__ __forceinline__ void ds_epilogue_block(uint32_t taddr, const float* _
     uint32_t raw[NV];
     if constexpr (NV == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
     tmem_ld_wait();
+    // bias: 16-byte shared-memory loads (or none at all for the data gradient).  The kernel runs at the shared-memory bandwidth
+    // limit -- the tensor core's operand fetch takes ~half of it -- and one 4-byte broadcast load per column was ~9 % of the rest.
     float v[NV];
+    if (bias_s) {
+#pragma unroll
+        for (int q = 0; q < NV / 4; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 4 * q);
+            v[4 * q] = b4.x; v[4 * q + 1] = b4.y; v[4 * q + 2] = b4.z; v[4 * q + 3] = b4.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        float f = __uint_as_float(raw[i]) + bias_s[i];
+        float f = __uint_as_float(raw[i]) + v[i];
         if (relu) f = fmaxf(f, 0.f);
         v[i] = round_as<TO>(f);
     }
@@ -547,7 +559,8 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                 const bool valid = valid_hw && gd < p.D;
                 __nv_bfloat16* yp = p.y + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld + col0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(blk * CO + col0);
-                const float* s_biasg = s_bias + col0;
+                const float* s_biasg = p.bias ? s_bias + col0 : nullptr;
+                const float* const s_bias0 = p.bias ? s_bias : nullptr;     // (an absent bias costs no shared-memory loads)
                 float* s_sumsg = s_sums + 2 * col0;
                 if (p.debug & 2) {
                 } else if constexpr (CPT == 16) {
@@ -555,17 +568,17 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                 } else if constexpr (CPT == 32) {
                     // two 16-column passes: half the live registers of one 32-column pass (the 64 statistics accumulators stay)
                     ds_epilogue_block<16, true>(taddr, s_biasg, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sumsg, ws, lane);
-                    ds_epilogue_block<16, true>(taddr + 16, s_biasg + 16, p.relu, valid, yp + 16, xcur + 2, has_x, acc_s + 16, acc_q + 16,
+                    ds_epilogue_block<16, true>(taddr + 16, s_biasg ? s_biasg + 16 : nullptr, p.relu, valid, yp + 16, xcur + 2, has_x, acc_s + 16, acc_q + 16,
                                                 s_sumsg, ws, lane);
                 } else {
-                    ds_epilogue_block<32, false>(taddr, s_bias, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sums, ws, lane);
+                    ds_epilogue_block<32, false>(taddr, s_bias0, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sums, ws, lane);
                     if constexpr (CO == 48)
-                        ds_epilogue_block<16, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
+                        ds_epilogue_block<16, false>(taddr + 32, s_bias0 ? s_bias0 + 32 : nullptr, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
                                                      s_sums + 64, ws, lane);
                     if constexpr (CO == 80) {
-                        ds_epilogue_block<32, false>(taddr + 32, s_bias + 32, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
+                        ds_epilogue_block<32, false>(taddr + 32, s_bias0 ? s_bias0 + 32 : nullptr, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
                                                      s_sums + 64, ws, lane);
-                        ds_epilogue_block<16, false>(taddr + 64, s_bias + 64, p.relu, valid, yp + 64, xcur + 8, has_x, acc_s, acc_q,
+                        ds_epilogue_block<16, false>(taddr + 64, s_bias0 ? s_bias0 + 64 : nullptr, p.relu, valid, yp + 64, xcur + 8, has_x, acc_s, acc_q,
                                                      s_sums + 128, ws, lane);
                     }
                 }
