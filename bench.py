@@ -59,7 +59,7 @@ KERNEL_OF = {"first:fwd": "conv3d_first_kernel", "first:wgrad": "conv3d_first_wg
              "direct:wgrad": "conv3d_wgrad_direct_kernel", "smallcin:wgrad": "conv3d_wgrad_smallcin_kernel",
              "tf32:fwd": "conv3d_umma_kernel<float> (TF32)", "tf32:dgrad": "conv3d_umma_kernel<float> (TF32)",
              "split3:wgrad": "split_bf16 + 3 x conv3d_wgrad_{cs,umma}_kernel (bf16 hi/lo)",
-             "h16:fwd": "conv3d_umma_kernel<half,float> (h16)", "h16:dgrad": "conv3d_umma_kernel<half,float> (h16)",
+             "h16:fwd": "conv3d_umma_kernel<__half, float", "h16:dgrad": "conv3d_umma_kernel<__half, float",     # (substrings of the ncu names)
              "h16:wgrad": "conv3d_wgrad_{cs,umma}_kernel (h16: fp16 operands)"}
 
 
