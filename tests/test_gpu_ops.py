@@ -211,7 +211,7 @@ def test_fused_norm_backward_in_pool_and_upsample_backward(B, dtype, f, shape, C
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("act_name", [None, "Sigmoid", "ReLU", "Tanh"])
-@pytest.mark.parametrize("Cin,Cout", [(16, 2), (5, 3), (32, 12), (32, 2), (64, 2), (128, 1), (64, 1)])
+@pytest.mark.parametrize("Cin,Cout", [(16, 2), (5, 3), (32, 12), (32, 2), (64, 2), (128, 1), (64, 1), (32, 3), (64, 12), (128, 8), (32, 6), (64, 4)])
 def test_head(B, dtype, act_name, Cin, Cout):
     N, D, H, W = (2, 3, 5, 9) if Cin < 64 else (2, 7, 13, 19)       # the wide heads: several warps per channel slice
     x = act((N, D, H, W, Cin), dtype, 1, relu=True)

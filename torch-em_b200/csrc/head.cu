@@ -294,6 +294,144 @@ head_bwd_small_kernel(const float* __restrict__ grad_out, const float* __restric
     }
 }
 
+// ---- mid-size heads (Cout = 3 .. 12: affinity / multi-class outputs on the first feature level) ---------------------------------
+// The filter of such a head (e.g. 12 x 32) and its dW partials do not fit one thread's registers, so a voxel is shared by several
+// threads: FORWARD by groups of JG output channels (warp-uniform group: a warp reads 32 consecutive voxels' full x rows --
+// coalesced, the other groups' warps hit L1 -- and writes JG coalesced NCDHW rows), BACKWARD by 8-channel slices of x (lane =
+// 8 voxels x 4 slices: contiguous 64 / 128 bytes per voxel; a thread keeps COUT x 8 dW partials and produces dx for its 8
+// channels from all COUT output gradients, so no cross-thread reduction is needed in the loop).
+template <typename T, int COUT, int JG>
+__global__ void __launch_bounds__(256)
+head_fwd_mid_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ w, const float* __restrict__ bias,
+                    float* __restrict__ out, int64_t S, int Cin, int act, int64_t total) {
+    constexpr int V = FullVec<T>::value, NG = COUT / JG, MAXC = 128;
+    __shared__ float w_s[COUT * MAXC];
+    for (int i = threadIdx.x; i < COUT * Cin; i += blockDim.x) w_s[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int jg = (int)(gwarp % NG);                  // (gridDim.x * 8) % NG == 0: a warp keeps its group
+    float br[JG];
+#pragma unroll
+    for (int j = 0; j < JG; ++j) br[j] = bias ? bias[jg * JG + j] : 0.f;
+    for (int64_t vox = (gwarp / NG) * 32 + lane; vox < total; vox += (nwarps / NG) * 32) {
+        const int64_t n = vox / S, s_ = vox % S;
+        const T* xp = x + vox * x_ld;
+        float acc[JG];
+#pragma unroll
+        for (int j = 0; j < JG; ++j) acc[j] = br[j];
+        for (int c = 0; c < Cin; c += V) {
+            float xv[V];
+            Vec<T, V>::load(xp + c, xv);
+#pragma unroll
+            for (int j = 0; j < JG; ++j) {
+                const float* wr = w_s + (jg * JG + j) * Cin + c;     // warp-uniform address: broadcast
+#pragma unroll
+                for (int k = 0; k < V; k += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wr + k);
+                    acc[j] = fmaf(w4.x, xv[k], acc[j]); acc[j] = fmaf(w4.y, xv[k + 1], acc[j]);
+                    acc[j] = fmaf(w4.z, xv[k + 2], acc[j]); acc[j] = fmaf(w4.w, xv[k + 3], acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < JG; ++j) out[((size_t)n * COUT + jg * JG + j) * S + s_] = act_fwd(acc[j], act);
+    }
+}
+
+// (Tried and slower on the 12-channel affinity head: splitting the output channels over two lane halves to halve the registers --
+// 2.6 ms; loading the output gradients once per voxel, coalesced, and handing them out by shuffles -- 1.9 ms; this form: 1.5 ms.
+// The loop is bound by the latency of its loads at 8 resident warps per SM.)
+template <typename T, int COUT>
+__global__ void __launch_bounds__(128, COUT > 8 ? 2 : 3)
+head_bwd_mid_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, const T* __restrict__ x, int64_t x_ld,
+                    const float* __restrict__ w, T* __restrict__ dx, int64_t dx_ld, float* __restrict__ dw, float* __restrict__ db,
+                    int64_t S, int act, int relu_mask, int64_t total, int Cin, float* __restrict__ absmax) {
+    constexpr int MAXC = 128;
+    __shared__ float red[COUT * MAXC + COUT];          // block-level dW | db partial sums
+    __shared__ float w_s[COUT * MAXC];                 // filter, transposed to [c][COUT]: a thread reads its 8 channels' weights
+    const int nsl = Cin / 8;                           // 8-channel slices of x: 4 (Cin = 32), 8, 16; a warp covers 32 / nsl voxels
+    for (int i = threadIdx.x; i < COUT * Cin; i += blockDim.x) w_s[(i % Cin) * COUT + i / Cin] = w[i];
+    for (int i = threadIdx.x; i < COUT * Cin + COUT; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int sl = lane % nsl, vl = lane / nsl, vpw = 32 / nsl;      // slice, voxel within the warp, voxels per warp
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float aw[COUT][8], ab[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+        ab[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) aw[j][c] = 0.f;
+    }
+    unsigned am = 0;
+    for (int64_t vox = gwarp * vpw + vl; vox < total; vox += nwarps * vpw) {
+        const int64_t n = vox / S, s_ = vox % S;
+        float dz[COUT];
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) {
+            const size_t o = ((size_t)n * COUT + j) * S + s_;
+            dz[j] = grad_out[o] * act_bwd(out[o], act);
+            ab[j] += dz[j];
+        }
+        float xv[8], r[8];
+        const T* xp = x + vox * x_ld + sl * 8;
+        if constexpr (sizeof(T) == 2) {
+            Vec<T, 8>::load(xp, xv);
+        } else {
+            Vec<T, 4>::load(xp, *reinterpret_cast<float(*)[4]>(xv));
+            Vec<T, 4>::load(xp + 4, *reinterpret_cast<float(*)[4]>(xv + 4));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float* wk = w_s + (sl * 8 + k) * COUT;
+            float g = 0.f;
+#pragma unroll
+            for (int j = 0; j < COUT; ++j) {
+                g = fmaf(wk[j], dz[j], g);
+                aw[j][k] = fmaf(dz[j], xv[k], aw[j][k]);
+            }
+            r[k] = (relu_mask && !(xv[k] > 0.f)) ? 0.f : g;
+            am = absmax_acc(am, r[k]);
+        }
+        if (dx) {
+            T* dp = dx + vox * dx_ld + sl * 8;
+            if constexpr (sizeof(T) == 2) {
+                Vec<T, 8>::store(dp, r);
+            } else {
+                Vec<T, 4>::store(dp, *reinterpret_cast<float(*)[4]>(r));
+                Vec<T, 4>::store(dp + 4, *reinterpret_cast<float(*)[4]>(r + 4));
+            }
+        }
+    }
+    absmax_flush(am, absmax);
+    // reduce over the lanes that share a slice (the voxel bits of the lane index); the bias gradient is taken from slice 0's lanes
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float a = aw[j][c];
+            for (int o = 16; o >= nsl; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (vl == 0) atomicAdd(&red[j * Cin + sl * 8 + c], a);
+        }
+        float b = ab[j];
+        for (int o = 16; o >= nsl; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) atomicAdd(&red[COUT * Cin + j], b);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * Cin + COUT; i += blockDim.x) {
+        if (i < COUT * Cin) atomicAdd(dw + i, red[i]);
+        else if (db) atomicAdd(db + (i - COUT * Cin), red[i]);
+    }
+}
+
+template <typename T>
+static bool head_mid_ok(const void* x, int64_t x_ld, const void* dx, int64_t dx_ld, int Cin, int Cout) {
+    constexpr int V = FullVec<T>::value;
+    return (Cin == 32 || Cin == 64 || Cin == 128) && (Cout == 3 || Cout == 4 || Cout == 6 || Cout == 8 || Cout == 12) && x_ld % V == 0 &&
+           aligned16(x) && (!dx || (dx_ld % V == 0 && aligned16(dx)));
+}
+
 template <typename T>
 static bool head_small_ok(const void* x, int64_t x_ld, const void* dx, int64_t dx_ld, int Cin, int Cout) {
     constexpr int V = FullVec<T>::value;
@@ -358,6 +496,37 @@ static void launch_head_bwd_small(unsigned blocks, cudaStream_t st, const float*
 #undef B2_HEAD_BWD_SMALL
 }
 
+template <typename T>
+static void launch_head_fwd_mid(int64_t blocks, cudaStream_t st, const void* x, int64_t x_ld, const float* w, const float* bias, float* out,
+                                int64_t S, int Cin, int Cout, int act, int64_t total) {
+    // warps = voxel groups x output-channel groups of 3 (or 4): a block count divisible by 3 and 4 keeps a warp's group fixed
+    unsigned bl = (unsigned)(((blocks * (Cout % 3 == 0 ? Cout / 3 : Cout / 4)) + 11) / 12 * 12);
+    const unsigned cap_ = (unsigned)sm_count() * 16 / 12 * 12;
+    if (bl > cap_) bl = cap_;
+#define B2_HEAD_FWD_MID(CO, JG) head_fwd_mid_kernel<T, CO, JG><<<bl, 256, 0, st>>>((const T*)x, x_ld, w, bias, out, S, Cin, act, total)
+    if (Cout == 12) B2_HEAD_FWD_MID(12, 3);
+    else if (Cout == 6) B2_HEAD_FWD_MID(6, 3);
+    else if (Cout == 3) B2_HEAD_FWD_MID(3, 3);
+    else if (Cout == 8) B2_HEAD_FWD_MID(8, 4);
+    else B2_HEAD_FWD_MID(4, 4);
+#undef B2_HEAD_FWD_MID
+}
+
+template <typename T>
+static void launch_head_bwd_mid(cudaStream_t st, const float* grad_out, const float* out, const void* x, int64_t x_ld, const float* w, void* dx,
+                                int64_t dx_ld, float* dw, float* db, int64_t S, int Cin, int Cout, int act, int relu_mask, int64_t total,
+                                float* absmax) {
+    const unsigned bl = (unsigned)sm_count() * (Cout > 8 ? 2 : 3);      // resident blocks of 128 threads per SM, grid-stride
+#define B2_HEAD_BWD_MID(CO) \
+    head_bwd_mid_kernel<T, CO><<<bl, 128, 0, st>>>(grad_out, out, (const T*)x, x_ld, w, (T*)dx, dx_ld, dw, db, S, act, relu_mask, total, Cin, absmax)
+    if (Cout == 12) B2_HEAD_BWD_MID(12);
+    else if (Cout == 8) B2_HEAD_BWD_MID(8);
+    else if (Cout == 6) B2_HEAD_BWD_MID(6);
+    else if (Cout == 4) B2_HEAD_BWD_MID(4);
+    else B2_HEAD_BWD_MID(3);
+#undef B2_HEAD_BWD_MID
+}
+
 extern "C" {
 
 int b200em_head_fwd(const void* x, int64_t x_ld, int dtype, const float* w, const float* bias, float* out, int N,
@@ -372,6 +541,8 @@ int b200em_head_fwd(const void* x, int64_t x_ld, int dtype, const float* w, cons
         constexpr int V = FullVec<T>::value;
         if (head_small_ok<T>(x, x_ld, nullptr, 0, Cin, Cout)) {
             launch_head_fwd_small<T>((unsigned)blocks, (cudaStream_t)stream, x, x_ld, w, bias, out, S, Cin, Cout, act, total);
+        } else if (head_mid_ok<T>(x, x_ld, nullptr, 0, Cin, Cout)) {
+            launch_head_fwd_mid<T>(blocks, (cudaStream_t)stream, x, x_ld, w, bias, out, S, Cin, Cout, act, total);
         } else if (Cin % V == 0 && x_ld % V == 0 && aligned16(x))
             head_fwd_kernel<T, V><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, w, bias, out, S, Cin, Cout, act, total);
         else
@@ -395,7 +566,10 @@ int b200em_head_bwd(const float* grad_out, const float* out, const void* x, int6
     {
         bool done = false;
         B2_DISPATCH_DTYPE(dtype, T, {
-            if (head_bwd_small_ok<T>(x, x_ld, dx, dx_ld, Cin, Cout)) {
+            if (head_mid_ok<T>(x, x_ld, dx, dx_ld, Cin, Cout)) {
+                launch_head_bwd_mid<T>((cudaStream_t)stream, grad_out, out, x, x_ld, w, dx, dx_ld, dw, db, S, Cin, Cout, act, relu_mask, total, absmax);
+                done = true;
+            } else if (head_bwd_small_ok<T>(x, x_ld, dx, dx_ld, Cin, Cout)) {
                 launch_head_bwd_small<T>((unsigned)(blocks / 4 * 4 > 0 ? blocks / 4 * 4 : 4), (cudaStream_t)stream, grad_out, out, x, x_ld, w, dx, dx_ld, dw, db, S, Cin, Cout,
                                          act, relu_mask, total, absmax);
                 done = true;
