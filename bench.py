@@ -546,7 +546,11 @@ def run_ours(args):
         "config": {"workload": workload_name(cfg, batch, patch),
                    "e2e": "per step: H2D of the batch (pinned, side stream, overlapped with the previous step) + train step + loss.item()",
                    "global_batch": batch * world, "parallelism": f"dp{world}", "l2": "inputs and activations larger than L2 (no flush needed)",
-                   "conv_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12},
+                   "conv_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
+                   "precision": ("bf16 autocast: bf16 activations and operands, fp32 accumulation / statistics / parameters" if bf16 else
+                                 "fp32 activations, statistics, parameters and gradients; convolutions TF32-class, as torch / cuDNN run fp32 "
+                                 "convolutions by default (allow_tf32=True, what the reference arm uses): fp16 operand copies (TF32's 11-bit "
+                                 "significand, exact power-of-two range scaling per tensor), fp32 accumulation")},
         "e2e": {"value": e2e, "unit": "voxels/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": xh.numel() * xh.element_size() + th.numel() * th.element_size(), "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
