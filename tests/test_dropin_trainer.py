@@ -163,6 +163,20 @@ def test_real_trainer_gpu_bf16(tmp_path, compile_model):
 
 
 @pytest.mark.gpu
+def test_real_trainer_gpu_default_mixed_precision_fp16(tmp_path):
+    """``mixed_precision=True`` with the trainer's DEFAULT dtype (float16 + GradScaler, default_trainer.py:132-142): the model
+    serves fp16 autocast on the h16 path (fp32 activations, fp16 tensor-core operands), the scaler stays enabled and works."""
+    dev = "cuda:0"
+    LOSS_LOG.clear()
+    tb.reset_launch_count()
+    trainer, folder = _run_trainer(tmp_path, dev, RecordingDiceLoss(), tb.DiceLoss(), compile_model=False, mixed_precision=True)
+    loss_vals = list(LOSS_LOG)
+    assert tb.launch_count() > 100, "the CUDA kernels of libb200em did not run"
+    assert trainer.scaler.is_enabled()
+    assert all(v == v for v in loss_vals) and loss_vals[-1] < loss_vals[0], loss_vals
+
+
+@pytest.mark.gpu
 def test_real_trainer_gpu_fp32_matches_reference_model_trajectory(tmp_path):
     """Same seed, same data order, fp32: the reference UNet3d + DiceLoss and ours must produce the same loss curve
     through the same real trainer (rtol 2e-3 over 10 AdamW steps, the bound of tests/test_gpu_unet.py)."""

@@ -86,11 +86,42 @@ def test_bf16_autocast_no_worse_than_reference_autocast(norm):
     assert r[len(r) // 2] <= 1.1, ("median error ratio vs reference autocast", r[len(r) // 2])
 
 
-def test_fp16_autocast_is_refused():
-    net = tb.UNet3d(1, 1, depth=1, initial_features=4).to(DEV)
+def test_fp16_autocast_runs_on_the_h16_path():
+    """torch.autocast(float16) + GradScaler -- the reference trainer's DEFAULT mixed precision (default_trainer.py:132-142) -- is
+    served by the h16 path: fp32 activations, fp16 tensor-core operands with range scaling (so the scaler's 65536x loss scale is
+    harmless), fp32 outputs and gradients.  At least fp16-autocast accuracy: checked against the fp32 oracle at TF32-class
+    tolerance, whatever allow_tf32 says (it is False in this test suite)."""
+    from oracle import dice as odice
+    from oracle import unet as ounet
+    from torch_em_b200.backend import default_backend
+    torch.manual_seed(5)
+    kw = dict(in_channels=1, out_channels=2, depth=2, initial_features=32, final_activation="Sigmoid")
+    net = tb.UNet3d(**kw).to(DEV)
+    x = torch.randn(1, 1, 16, 32, 32)
+    t = (torch.nn.functional.avg_pool3d(torch.randn(1, 2, 16, 32, 32), 5, 1, 2) > 0).float()
+    B = default_backend()
+    B.calls.clear()
+    scaler = torch.amp.GradScaler("cuda")
     with torch.autocast("cuda", dtype=torch.float16):
-        with pytest.raises(NotImplementedError, match="bfloat16"):
-            net(torch.zeros(1, 1, 8, 8, 8, device=DEV))
+        y = net(x.to(DEV))
+        loss = tb.DiceLoss()(y, t.to(DEV))
+    scaler.scale(loss).backward()
+    torch.cuda.synchronize()
+    assert y.dtype == torch.float32
+    assert B.calls.get("h16:fwd", 0) > 0 and B.calls.get("h16:dgrad", 0) > 0 and B.calls.get("h16:wgrad", 0) > 0, dict(B.calls)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    y_ref = ounet.unet3d_forward(x, sd, [2, 2], final_activation="Sigmoid")
+    l_ref = odice.dice_loss(y_ref, t)
+    l_ref.backward()
+    assert float((y.detach().cpu() - y_ref.detach()).norm() / y_ref.detach().norm()) < 2e-3
+    assert abs(loss.item() - l_ref.item()) < 2e-3 * abs(l_ref.item())
+    s_ = scaler.get_scale()
+    g = torch.cat([p.grad.flatten().cpu() / s_ for p in net.parameters()])
+    gref = torch.cat([sd[k].grad.flatten() for k, _ in net.named_parameters()])
+    assert bool(torch.isfinite(g).all())
+    assert float(torch.dot(g, gref) / (g.norm() * gref.norm())) > 0.99
+    assert float((g - gref).norm() / gref.norm()) < 0.15
+    assert not B.h16_enabled()                       # the forcing ends with the node (allow_tf32 is False here)
 
 
 def test_train_steps_reduce_loss_and_match_oracle_trajectory():

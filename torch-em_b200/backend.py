@@ -236,6 +236,7 @@ class CudaBackend:
         self.use_tf32 = use_tf32    # None: follow torch.backends.cudnn.allow_tf32 (True by default, like the reference's fp32 runs)
         self.use_splitk = use_splitk
         self.use_h16 = use_h16      # TF32-class arithmetic through fp16 operand copies at the bf16 MMA rate (False: kind::tf32 kernels)
+        self._force_h16 = False     # fp16 autocast in effect (forcing_h16)
         self._h16_recent = []       # [(tensor, H16Operand)]: the last two un-normalised fp32 tensors converted (dz feeds wgrad AND dgrad)
         self._absmax_known = []     # [(fp32 tensor, its device max |.|)] written by the producing kernel, consumed by to_h16
         self._workspaces = _WORKSPACES   # device index -> zero-filled scratch registered with the library (split-K partial sums)
@@ -290,7 +291,25 @@ class CudaBackend:
     def h16_enabled(self):
         """fp32 activations with TF32 allowed run as fp16 operand copies (same 11-bit significand as TF32, round-to-nearest, exact
         power-of-two range scaling) on kind::f16 MMAs with fp32 accumulation: TF32-class results at twice the kind::tf32 rate."""
+        if self._force_h16 and self.use_umma:
+            return True                      # fp16 autocast: half-precision operands are what the caller asked for
         return bool(self.use_h16) and self.tf32_enabled()
+
+    def forcing_h16(self, on=True):
+        """Context manager: run fp32 activations on the h16 path whatever ``allow_tf32`` says -- how the model serves
+        ``torch.autocast(float16)`` (the reference trainer's default mixed precision): fp32 activations and accumulation, fp16
+        tensor-core operands, i.e. at least the precision fp16 autocast would give."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            was = self._force_h16
+            self._force_h16 = bool(on) or was
+            try:
+                yield
+            finally:
+                self._force_h16 = was
+        return ctx()
 
     def _want_absmax(self, out):
         """Device word for max |out| of a gradient tensor the h16 path will convert next (None when it will not)."""

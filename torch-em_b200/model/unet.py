@@ -165,6 +165,13 @@ class _LazyPacks:
         pass
 
 
+def _forcing_h16(B, on):
+    """backend.forcing_h16(on) where the backend has one (the emulation backend of the CPU tests does not)."""
+    import contextlib
+    f = getattr(B, "forcing_h16", None)
+    return f(on) if f is not None else contextlib.nullcontext()
+
+
 class _UNetFunction(torch.autograd.Function):
     """The whole network as one autograd node: forward_pass / backward_pass are explicit kernel schedules."""
 
@@ -178,9 +185,14 @@ class _UNetFunction(torch.autograd.Function):
         # 2-D models hold Conv2d-shaped weights (Cout, Cin, kh, kw): the kernels see them as (Cout, Cin, 1, kh, kw) views
         P = {k: (v.unsqueeze(2) if v.dim() == 4 else v) for k, v in zip(names, params)}
         B = model._backend()
+        # fp16 autocast (the reference trainer's default mixed precision, default_trainer.py:132-142): fp32 activations with fp16
+        # tensor-core operands -- the h16 path, forced on for this node's forward and backward
+        fp16 = act_dtype == torch.float16
+        if fp16:
+            act_dtype = torch.float32
         bf16 = act_dtype == torch.bfloat16
         two_d = model._dim == 2
-        with _device_ctx(x.device):
+        with _device_ctx(x.device), _forcing_h16(B, fp16):
             packs = model._packs(B, P)
             packs.refresh_fwd({k[:-len(".weight")]: v for k, v in P.items() if v.dim() == 5}, bf16=bf16)
             bufs = dict(model.named_buffers())
@@ -188,7 +200,7 @@ class _UNetFunction(torch.autograd.Function):
                                               bufs=bufs, training=model.training)
         if two_d:
             preds = [p.squeeze(2) for p in preds]
-        ctx.model, ctx.P, ctx.packs, ctx.bf16 = model, P, packs, bf16
+        ctx.model, ctx.P, ctx.packs, ctx.bf16, ctx.fp16 = model, P, packs, bf16, fp16
         ctx.shapes = [tuple(v.shape) for v in params]
         ctx.fctx = fctx if any(ctx.needs_input_grad) else None   # no_grad / eval inference keeps nothing
         ctx.ran_backward = False
@@ -213,7 +225,7 @@ class _UNetFunction(torch.autograd.Function):
         ctx.fctx.misc["preds"] = preds
         B = model._backend()
         dev = preds[0].device
-        with _device_ctx(dev):
+        with _device_ctx(dev), _forcing_h16(B, ctx.fp16):
             ctx.packs.refresh_dgrad(bf16=ctx.bf16)
             sync = model.grad_sync
             chunked = sync is not None and hasattr(sync, "ready")
@@ -403,11 +415,11 @@ class _UNetCommon(nn.Module):
             return self.compute_dtype
         if torch.is_autocast_enabled(x.device.type):
             dt = torch.get_autocast_dtype(x.device.type)
-            if dt == torch.float16:
+            if dt == torch.float16 and not hasattr(self._backend(), "forcing_h16"):
                 raise NotImplementedError(
-                    "fp16 autocast (+GradScaler) is not supported by the B200 path; pass "
+                    "fp16 autocast (+GradScaler) is not supported by this backend; pass "
                     "mixed_precision_dtype='bfloat16' (or mixed_precision=False) to default_segmentation_trainer")
-            return dt
+            return dt            # float16: served as fp32 activations with fp16 tensor-core operands (_UNetFunction.forward)
         return torch.float32
 
     @torch.compiler.disable
