@@ -179,18 +179,18 @@ affinity_dice_sums_kernel(const TP* __restrict__ pred, const long long* __restri
                           OffsetTable offs, AffRule rule, float* __restrict__ sums) {
     __shared__ float sh[3][8];
     const int n = blockIdx.y;
-    const int64_t S = (int64_t)D * H * W;
+    const unsigned S = (unsigned)D * H * W;                 // 32-bit voxel indices within a sample (checked by the launcher)
     const long long* lab = labels + (size_t)n * S;
     const int noff = offs.n;
     long long lp[AD_PER_THREAD];
     int pd[AD_PER_THREAD], ph[AD_PER_THREAD], pw[AD_PER_THREAD];
-    const int64_t base = (int64_t)blockIdx.x * AD_CHUNK + threadIdx.x;
+    const unsigned base = blockIdx.x * (unsigned)AD_CHUNK + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < AD_PER_THREAD; ++k) {
-        const int64_t s = base + (int64_t)k * 256;
+        const unsigned s = base + (unsigned)k * 256u;
         if (s < S) {
             lp[k] = lab[s];
-            pw[k] = (int)(s % W); ph[k] = (int)((s / W) % H); pd[k] = (int)(s / ((int64_t)W * H));
+            pw[k] = (int)(s % (unsigned)W); ph[k] = (int)((s / (unsigned)W) % (unsigned)H); pd[k] = (int)(s / ((unsigned)W * (unsigned)H));
         } else {
             lp[k] = 0; pw[k] = ph[k] = pd[k] = 0;
         }
@@ -200,7 +200,7 @@ affinity_dice_sums_kernel(const TP* __restrict__ pred, const long long* __restri
         float a_pt = 0.f, a_pp = 0.f, a_tt = 0.f;
 #pragma unroll
         for (int k = 0; k < AD_PER_THREAD; ++k) {
-            const int64_t s = base + (int64_t)k * 256;
+            const unsigned s = base + (unsigned)k * 256u;
             if (s < S) {
                 float t, m;
                 aff_eval(lab, lp[k], pd[k], ph[k], pw[k], D, H, W, offs.d[c], offs.h[c], offs.w[c], rule, t, m);
@@ -235,19 +235,19 @@ affinity_dice_bwd_kernel(const TP* __restrict__ pred, const long long* __restric
                          OffsetTable offs, AffRule rule, const float* __restrict__ coef, const float* __restrict__ gout,
                          TG* __restrict__ grad) {
     const int n = blockIdx.y;
-    const int64_t S = (int64_t)D * H * W;
+    const unsigned S = (unsigned)D * H * W;                 // 32-bit voxel indices within a sample (checked by the launcher)
     const long long* lab = labels + (size_t)n * S;
     const int noff = offs.n;
     const float go = gout[0];
     long long lp[AD_PER_THREAD];
     int pd[AD_PER_THREAD], ph[AD_PER_THREAD], pw[AD_PER_THREAD];
-    const int64_t base = (int64_t)blockIdx.x * AD_CHUNK + threadIdx.x;
+    const unsigned base = blockIdx.x * (unsigned)AD_CHUNK + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < AD_PER_THREAD; ++k) {
-        const int64_t s = base + (int64_t)k * 256;
+        const unsigned s = base + (unsigned)k * 256u;
         if (s < S) {
             lp[k] = lab[s];
-            pw[k] = (int)(s % W); ph[k] = (int)((s / W) % H); pd[k] = (int)(s / ((int64_t)W * H));
+            pw[k] = (int)(s % (unsigned)W); ph[k] = (int)((s / (unsigned)W) % (unsigned)H); pd[k] = (int)(s / ((unsigned)W * (unsigned)H));
         } else {
             lp[k] = 0; pw[k] = ph[k] = pd[k] = 0;
         }
@@ -258,7 +258,7 @@ affinity_dice_bwd_kernel(const TP* __restrict__ pred, const long long* __restric
         TG* g = grad + ((size_t)n * noff + c) * S;
 #pragma unroll
         for (int k = 0; k < AD_PER_THREAD; ++k) {
-            const int64_t s = base + (int64_t)k * 256;
+            const unsigned s = base + (unsigned)k * 256u;
             if (s < S) {
                 float t, m;
                 aff_eval(lab, lp[k], pd[k], ph[k], pw[k], D, H, W, offs.d[c], offs.h[c], offs.w[c], rule, t, m);
@@ -351,6 +351,7 @@ int b200em_affinity_dice_sums(const void* pred, int pred_dtype, const int64_t* l
     if (fill_offsets(t, offsets, n_off)) return 1;
     AffRule r{has_ignore, (long long)ignore_label, include_ignore_transitions};
     int64_t S = (int64_t)D * H * W;
+    B2_CHECK_ARG(S < (1LL << 31), "affinity_dice_sums: sample too large for 32-bit voxel indices");
     dim3 grid((unsigned)((S + AD_CHUNK - 1) / AD_CHUNK), (unsigned)N);
     B2_DISPATCH_DTYPE(pred_dtype, TP, {
         affinity_dice_sums_kernel<TP><<<grid, 256, 0, (cudaStream_t)stream>>>((const TP*)pred, (const long long*)labels, D, H, W, t, r, sums);
@@ -368,6 +369,7 @@ int b200em_affinity_dice_bwd(const void* pred, int pred_dtype, const int64_t* la
     if (fill_offsets(t, offsets, n_off)) return 1;
     AffRule r{has_ignore, (long long)ignore_label, include_ignore_transitions};
     int64_t S = (int64_t)D * H * W;
+    B2_CHECK_ARG(S < (1LL << 31), "affinity_dice_bwd: sample too large for 32-bit voxel indices");
     dim3 grid((unsigned)((S + AD_CHUNK - 1) / AD_CHUNK), (unsigned)N);
     B2_DISPATCH_DTYPE(pred_dtype, TP, {
         B2_DISPATCH_DTYPE(grad_dtype, TG, {
