@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256)
 head_fwd_mid_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ out, int64_t S, int Cin, int act, int64_t total) {
     constexpr int V = FullVec<T>::value, NG = COUT / JG, MAXC = 128;
-    __shared__ float w_s[COUT * MAXC];
+    __shared__ __align__(16) float w_s[COUT * MAXC];
     for (int i = threadIdx.x; i < COUT * Cin; i += blockDim.x) w_s[i] = w[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -504,7 +504,10 @@ static void launch_head_fwd_mid(int64_t blocks, cudaStream_t st, const void* x, 
     const unsigned cap_ = (unsigned)sm_count() * 16 / 12 * 12;
     if (bl > cap_) bl = cap_;
 #define B2_HEAD_FWD_MID(CO, JG) head_fwd_mid_kernel<T, CO, JG><<<bl, 256, 0, st>>>((const T*)x, x_ld, w, bias, out, S, Cin, act, total)
-    if (Cout == 12) B2_HEAD_FWD_MID(12, 3);
+    if (Cout <= 2) {
+        bl = (unsigned)(blocks < (int64_t)sm_count() * 16 ? blocks : (int64_t)sm_count() * 16);
+        if (Cout == 2) B2_HEAD_FWD_MID(2, 2); else B2_HEAD_FWD_MID(1, 1);
+    } else if (Cout == 12) B2_HEAD_FWD_MID(12, 3);
     else if (Cout == 6) B2_HEAD_FWD_MID(6, 3);
     else if (Cout == 3) B2_HEAD_FWD_MID(3, 3);
     else if (Cout == 8) B2_HEAD_FWD_MID(8, 4);
@@ -541,7 +544,9 @@ int b200em_head_fwd(const void* x, int64_t x_ld, int dtype, const float* w, cons
         constexpr int V = FullVec<T>::value;
         if (head_small_ok<T>(x, x_ld, nullptr, 0, Cin, Cout)) {
             launch_head_fwd_small<T>((unsigned)blocks, (cudaStream_t)stream, x, x_ld, w, bias, out, S, Cin, Cout, act, total);
-        } else if (head_mid_ok<T>(x, x_ld, nullptr, 0, Cin, Cout)) {
+        } else if (head_mid_ok<T>(x, x_ld, nullptr, 0, Cin, Cout) || head_bwd_small_ok<T>(x, x_ld, nullptr, 0, Cin, Cout)) {
+            // (the second condition: 1 / 2 output channels on 64 / 128 input channels -- too wide for the register-resident filter
+            // of the small kernel, served by the shared-memory-filter kernel with one channel group)
             launch_head_fwd_mid<T>(blocks, (cudaStream_t)stream, x, x_ld, w, bias, out, S, Cin, Cout, act, total);
         } else if (Cin % V == 0 && x_ld % V == 0 && aligned16(x))
             head_fwd_kernel<T, V><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, w, bias, out, S, Cin, Cout, act, total);
