@@ -652,11 +652,12 @@ class CudaBackend:
 
     def fused_up_bwd_ok(self, dy, f):
         """Whether upsample_bwd can apply the norm backward on the fly (factors (1|2, 2, 2), 16-byte channel vectors whose count
-        divides 256)."""
+        divides 256, samples below 4 GiB)."""
         vec = 8 if dy.dtype == torch.bfloat16 else 4
         C = dy.shape[4]
+        per_sample_bytes = dy.shape[1] * dy.shape[2] * dy.shape[3] * dy.stride(3) * dy.element_size()
         return f[0] <= 2 and f[1] == 2 and f[2] == 2 and C % vec == 0 and 256 % (C // vec) == 0 and dy.stride(3) % vec == 0 and \
-            dy.data_ptr() % 16 == 0
+            dy.data_ptr() % 16 == 0 and per_sample_bytes < 2 ** 32        # (the kernel addresses a sample with 32-bit byte offsets)
 
     def upsample_bwd(self, dy, dx, f, zlow=None, coef=None):
         """coef (N, C, 3) + zlow (the tensor that was up-sampled): the gradient that is transposed-interpolated is

@@ -746,213 +746,7 @@ im2col_taps_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Trilinear x2 / x1 per axis (the only factors the U-Net uses), specialised: one thread per LOW-resolution voxel and
-// 8-channel vector produces its fd*fh*fw outputs from the 3x3x3 neighbourhood with separable constant weights
-// (align_corners=False, scale 2:  out[2i] = .25 x[i-1] + .75 x[i] (x[0] at i = 0),  out[2i+1] = .75 x[i] + .25 x[i+1]
-// (x[n-1] at i = n-1)); 27 loads per 8 outputs instead of 64, index arithmetic once per 8 outputs.
-// Block = 2 x 4 x 8 low-res voxels x (C/VEC) vectors so neighbouring rows hit L1.
-namespace {
-constexpr int UP_BD = 2, UP_BH = 4, UP_BW = 8;
-}
-
-template <typename T, int VEC, int FD, int FH, int FW>
-__global__ void __launch_bounds__(256)
-upsample2_fwd_kernel(const T* __restrict__ x, int64_t x_ld, T* __restrict__ y, int64_t y_ld, int D, int H, int W, int C,
-                     float* __restrict__ sums, int tiles_h, int tiles_w) {
-    __shared__ float red[256 * 2];
-    const int cvec = C / VEC;
-    const int n = blockIdx.z;
-    int tb = blockIdx.x;
-    const int w0 = (tb % tiles_w) * UP_BW; tb /= tiles_w;
-    const int h0 = (tb % tiles_h) * UP_BH; tb /= tiles_h;
-    const int d0 = tb * UP_BD;
-    const int Do = D * FD, Ho = H * FH, Wo = W * FW;
-    const T* xn = x + (size_t)n * D * H * W * x_ld;
-    T* yn = y + (size_t)n * Do * Ho * Wo * y_ld;
-    const int vpb = 256 / cvec;                         // voxels handled per pass by this block (cvec divides 256)
-    const int cv = threadIdx.x % cvec;
-    float acc[VEC][2];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v][0] = acc[v][1] = 0.f;
-    for (int lv = threadIdx.x / cvec; lv < UP_BD * UP_BH * UP_BW; lv += vpb) {
-        const int w = w0 + lv % UP_BW, h = h0 + (lv / UP_BW) % UP_BH, d = d0 + lv / (UP_BW * UP_BH);
-        if (w >= W || h >= H || d >= D) continue;
-        // neighbourhood with clamped indices
-        float nb[3][3][3][VEC];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (FD == 1 && a != 1) continue;
-            const int dd = min(max(d + a - 1, 0), D - 1);
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                if (FH == 1 && b != 1) continue;
-                const int hh = min(max(h + b - 1, 0), H - 1);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (FW == 1 && c != 1) continue;
-                    const int ww = min(max(w + c - 1, 0), W - 1);
-                    Vec<T, VEC>::load(xn + (((size_t)dd * H + hh) * W + ww) * x_ld + cv * VEC, nb[a][b][c]);
-                }
-            }
-        }
-        // weights of (x[i-1], x[i], x[i+1]) for the two outputs of each axis; edge outputs are exact copies
-        auto wts = [](int i, int n_, int o, float& wm, float& w0_, float& wp) {
-            if (o == 0) { wm = i > 0 ? 0.25f : 0.f; w0_ = i > 0 ? 0.75f : 1.f; wp = 0.f; }
-            else { wm = 0.f; w0_ = i < n_ - 1 ? 0.75f : 1.f; wp = i < n_ - 1 ? 0.25f : 0.f; }
-        };
-#pragma unroll
-        for (int od = 0; od < FD; ++od) {
-            float dm = 0.f, dc = 1.f, dp = 0.f;
-            if (FD == 2) wts(d, D, od, dm, dc, dp);
-#pragma unroll
-            for (int oh = 0; oh < FH; ++oh) {
-                float hm = 0.f, hc = 1.f, hp = 0.f;
-                if (FH == 2) wts(h, H, oh, hm, hc, hp);
-#pragma unroll
-                for (int ow = 0; ow < FW; ++ow) {
-                    float wm = 0.f, wc = 1.f, wp = 0.f;
-                    if (FW == 2) wts(w, W, ow, wm, wc, wp);
-                    float r[VEC];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) r[v] = 0.f;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        if (FD == 1 && a != 1) continue;
-                        const float wa = a == 0 ? dm : (a == 1 ? dc : dp);
-#pragma unroll
-                        for (int b = 0; b < 3; ++b) {
-                            if (FH == 1 && b != 1) continue;
-                            const float wab = wa * (b == 0 ? hm : (b == 1 ? hc : hp));
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                if (FW == 1 && c != 1) continue;
-                                const float wt = wab * (c == 0 ? wm : (c == 1 ? wc : wp));
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) r[v] = fmaf(wt, nb[a][b][c][v], r[v]);
-                            }
-                        }
-                    }
-                    const size_t ovox = ((size_t)(d * FD + od) * Ho + (h * FH + oh)) * Wo + (w * FW + ow);
-                    Vec<T, VEC>::store(yn + ovox * y_ld + cv * VEC, r);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const float q = round_as<T>(r[v]);
-                        acc[v][0] += q; acc[v][1] += q * q;
-                    }
-                }
-            }
-        }
-    }
-    if (sums) {
-        // block reduce per channel: threads with the same cv hold partial sums
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            red[threadIdx.x * 2] = acc[v][0];
-            red[threadIdx.x * 2 + 1] = acc[v][1];
-            __syncthreads();
-            if ((int)threadIdx.x < cvec) {
-                float s1 = 0.f, s2 = 0.f;
-                for (int j = threadIdx.x; j < 256; j += cvec) { s1 += red[j * 2]; s2 += red[j * 2 + 1]; }
-                atomicAdd(sums + ((size_t)n * C + threadIdx.x * VEC + v) * 2, s1);
-                atomicAdd(sums + ((size_t)n * C + threadIdx.x * VEC + v) * 2 + 1, s2);
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// Forward, output-centric variant (the one launched for factors (2|1, 2, 2)): one thread per (output d, output h, LOW-res
-// w, 8-channel vector) produces the two outputs along w.  With clamped neighbour indices the weights are uniform
-// (out[2i] = .25 x[i-1] + .75 x[i], out[2i+1] = .75 x[i] + .25 x[i+1]; the clamp turns the edge samples into the exact
-// copies align_corners=False prescribes), so the 2 (d) x 2 (h) x 3 (w) neighbourhood is folded into three running
-// vectors as it is loaded: 12 loads, 24 accumulators, no 27-vector register tile.  HBM-bound: reads hit L1/L2.
-template <typename T, int VEC, int FD>
-__global__ void __launch_bounds__(256)
-upsample2_fwd_pair_kernel(const T* __restrict__ x, int64_t x_ld, T* __restrict__ y, int64_t y_ld, int D, int H, int W, int C,
-                          float* __restrict__ sums, unsigned total) {
-    __shared__ float red[256 * 2];
-    const int cvec = C / VEC;
-    const int n = blockIdx.y;
-    const int Do = D * FD, Ho = H * 2, Wo = W * 2;
-    const T* xn = x + (size_t)n * D * H * W * x_ld;
-    T* yn = y + (size_t)n * Do * Ho * Wo * y_ld;
-    float acc[VEC][2];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v][0] = acc[v][1] = 0.f;
-    // blockDim.x * gridDim.x is a multiple of cvec, so a thread keeps its channel vector over the grid-stride loop
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        unsigned t = idx;
-        const int cv = (int)(t % (unsigned)cvec); t /= (unsigned)cvec;
-        const int w = (int)(t % (unsigned)W); t /= (unsigned)W;
-        const int oh = (int)(t % (unsigned)Ho); t /= (unsigned)Ho;
-        const int od = (int)t;
-        // the two source rows along d and h and their weights
-        int d_a, d_b; float wd_a, wd_b;
-        if (FD == 2) {
-            const int i = od >> 1;
-            if (od & 1) { d_a = i; d_b = min(i + 1, D - 1); wd_a = 0.75f; wd_b = 0.25f; }
-            else { d_a = max(i - 1, 0); d_b = i; wd_a = 0.25f; wd_b = 0.75f; }
-        } else { d_a = d_b = od; wd_a = 1.f; wd_b = 0.f; }
-        int h_a, h_b; float wh_a, wh_b;
-        {
-            const int i = oh >> 1;
-            if (oh & 1) { h_a = i; h_b = min(i + 1, H - 1); wh_a = 0.75f; wh_b = 0.25f; }
-            else { h_a = max(i - 1, 0); h_b = i; wh_a = 0.25f; wh_b = 0.75f; }
-        }
-        const int wm = max(w - 1, 0), wp = min(w + 1, W - 1);
-        float am[VEC], a0[VEC], ap[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) am[v] = a0[v] = ap[v] = 0.f;
-#pragma unroll
-        for (int q = 0; q < (FD == 2 ? 4 : 2); ++q) {
-            const int dd = (q & 2) ? d_b : d_a, hh = (q & 1) ? h_b : h_a;
-            const float wt = ((q & 2) ? wd_b : wd_a) * ((q & 1) ? wh_b : wh_a);
-            const T* row = xn + ((size_t)dd * H + hh) * W * x_ld + cv * VEC;
-            float r[VEC];
-            Vec<T, VEC>::load(row + (size_t)wm * x_ld, r);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) am[v] = fmaf(wt, r[v], am[v]);
-            Vec<T, VEC>::load(row + (size_t)w * x_ld, r);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) a0[v] = fmaf(wt, r[v], a0[v]);
-            Vec<T, VEC>::load(row + (size_t)wp * x_ld, r);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) ap[v] = fmaf(wt, r[v], ap[v]);
-        }
-        float lo[VEC], hi[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            lo[v] = fmaf(0.25f, am[v], 0.75f * a0[v]);
-            hi[v] = fmaf(0.25f, ap[v], 0.75f * a0[v]);
-        }
-        T* yo = yn + (((size_t)od * Ho + oh) * Wo + 2 * w) * y_ld + cv * VEC;
-        Vec<T, VEC>::store(yo, lo);
-        Vec<T, VEC>::store(yo + y_ld, hi);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const float q0 = round_as<T>(lo[v]), q1 = round_as<T>(hi[v]);
-            acc[v][0] += q0 + q1;
-            acc[v][1] += q0 * q0 + q1 * q1;
-        }
-    }
-    if (sums) {
-        const int cvt = threadIdx.x % cvec;          // blockDim.x % cvec == 0
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            red[threadIdx.x * 2] = acc[v][0];
-            red[threadIdx.x * 2 + 1] = acc[v][1];
-            __syncthreads();
-            if ((int)threadIdx.x < cvec) {
-                float s1 = 0.f, s2 = 0.f;
-                for (int j = threadIdx.x; j < 256; j += cvec) { s1 += red[j * 2]; s2 += red[j * 2 + 1]; }
-                atomicAdd(sums + ((size_t)n * C + cvt * VEC + v) * 2, s1);
-                atomicAdd(sums + ((size_t)n * C + cvt * VEC + v) * 2 + 1, s2);
-            }
-            __syncthreads();
-        }
-    }
-}
-
+// Trilinear x2 / x1 per axis (the only factors the U-Net uses), specialised.
 // Forward, block variant (the one launched for factors (2|1, 2, 2) with 4-channel vectors): one thread per LOW-resolution voxel
 // and 4 channels produces its FD x 2 x 2 outputs, separably -- with clamped neighbour indices the weights are uniform, so per
 // depth slice the 3 x 3 neighbourhood goes w-pass (3 rows -> 3 x 2) and h-pass (-> 2 x 2), and the d-pass combines three such
@@ -1084,64 +878,6 @@ upsample2_fwd_block_kernel(const T* __restrict__ x, int64_t x_ld, T* __restrict_
             }
             __syncthreads();
         }
-    }
-}
-
-// Backward (transpose of the same weights): dx[i] = .25 g[2i-1] + a g[2i] + b g[2i+1] + .25 g[2i+2] per axis with
-// a = (i == 0 ? 1 : .75), b = (i == n-1 ? 1 : .75) and the out-of-range taps dropped.  Separable: w, then h, then d.
-template <typename T, int VEC, int FD, int FH, int FW>
-__global__ void __launch_bounds__(256)
-upsample2_bwd_kernel(const T* __restrict__ dy, int64_t dy_ld, T* __restrict__ dx, int64_t dx_ld, int D, int H, int W, int C,
-                     int tiles_h, int tiles_w) {
-    const int cvec = C / VEC;
-    const int n = blockIdx.z;
-    int tb = blockIdx.x;
-    const int w0 = (tb % tiles_w) * UP_BW; tb /= tiles_w;
-    const int h0 = (tb % tiles_h) * UP_BH; tb /= tiles_h;
-    const int d0 = tb * UP_BD;
-    const int Do = D * FD, Ho = H * FH, Wo = W * FW;
-    const T* gn = dy + (size_t)n * Do * Ho * Wo * dy_ld;
-    T* xn = dx + (size_t)n * D * H * W * dx_ld;
-    const int vpb = 256 / cvec;
-    const int cv = threadIdx.x % cvec;
-    // taps of one axis: output index o = f*i + k - 1 (k = 0..3) for f = 2, o = i for f = 1
-    auto tapw = [](int i, int n_, int k) -> float {
-        if (k == 0) return i > 0 ? 0.25f : 0.f;
-        if (k == 1) return i > 0 ? 0.75f : 1.f;
-        if (k == 2) return i < n_ - 1 ? 0.75f : 1.f;
-        return i < n_ - 1 ? 0.25f : 0.f;
-    };
-    for (int lv = threadIdx.x / cvec; lv < UP_BD * UP_BH * UP_BW; lv += vpb) {
-        const int w = w0 + lv % UP_BW, h = h0 + (lv / UP_BW) % UP_BH, d = d0 + lv / (UP_BW * UP_BH);
-        if (w >= W || h >= H || d >= D) continue;
-        float r[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) r[v] = 0.f;
-#pragma unroll
-        for (int kd = 0; kd < (FD == 2 ? 4 : 1); ++kd) {
-            const float wd = FD == 2 ? tapw(d, D, kd) : 1.f;
-            if (wd == 0.f) continue;
-            const int od = FD == 2 ? 2 * d + kd - 1 : d;
-#pragma unroll
-            for (int kh = 0; kh < (FH == 2 ? 4 : 1); ++kh) {
-                const float wh = FH == 2 ? tapw(h, H, kh) : 1.f;
-                if (wh == 0.f) continue;
-                const int oh = FH == 2 ? 2 * h + kh - 1 : h;
-                const T* row = gn + (((size_t)od * Ho + oh) * Wo) * dy_ld + cv * VEC;
-#pragma unroll
-                for (int kw = 0; kw < (FW == 2 ? 4 : 1); ++kw) {
-                    const float ww = FW == 2 ? tapw(w, W, kw) : 1.f;
-                    if (ww == 0.f) continue;
-                    const int ow = FW == 2 ? 2 * w + kw - 1 : w;
-                    float t[VEC];
-                    Vec<T, VEC>::load(row + (size_t)ow * dy_ld, t);
-                    const float wt = wd * wh * ww;
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) r[v] = fmaf(wt, t[v], r[v]);
-                }
-            }
-        }
-        Vec<T, VEC>::store(xn + (((size_t)d * H + h) * W + w) * dx_ld + cv * VEC, r);
     }
 }
 
@@ -1303,70 +1039,6 @@ upsample2_bwd_block_kernel(const T* __restrict__ dy, int64_t dy_ld, const T* __r
                 Vec<T, VEC>::store(reinterpret_cast<T*>(xb + ((unsigned)dd * xslice + (unsigned)hh * xrow + (unsigned)ww * xl + cvo)), v);
             }
         }
-    }
-}
-
-// Fused norm backward of the block that consumes an up-sampled tensor, on the LOW-resolution side.  The gradient that has to be
-// transposed-interpolated is c0 * dy + c1 * up + c2 with up = U z (the up-sampled tensor itself); by linearity
-//   U^T (c0 dy + c1 U z + c2) = c0 U^T dy + c1 (U^T U) z + c2 U^T 1,
-// U^T 1 = 2 per x2 axis (the four taps always sum to 2, edges included) and U^T U is a 3-tap stencil per axis on z -- so the
-// high-resolution `up` tensor is never read: this kernel turns r = U^T dy (in place) into the result with one pass over the
-// low-resolution tensors.  One thread per (low-res voxel, channel vector).
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256)
-upsample2_bwd_norm_kernel(T* __restrict__ dx, int64_t dx_ld, const T* __restrict__ zlow, int64_t zlow_ld, const float* __restrict__ coef,
-                          int64_t coef_nstride, int D, int H, int W, int C, int fd, int64_t total) {
-    const unsigned cvec = C / VEC;
-    const int64_t n = blockIdx.y;
-    auto tapw = [](int i, int n_, int k) -> float {
-        if (k == 0) return i > 0 ? 0.25f : 0.f;
-        if (k == 1) return i > 0 ? 0.75f : 1.f;
-        if (k == 2) return i < n_ - 1 ? 0.75f : 1.f;
-        return i < n_ - 1 ? 0.25f : 0.f;
-    };
-    auto uu = [&](int i, int n_, float (&a)[3]) {        // per-axis coefficients of U^T U on z[i-1], z[i], z[i+1]
-        const float t0 = tapw(i, n_, 0), t1 = tapw(i, n_, 1), t2 = tapw(i, n_, 2), t3 = tapw(i, n_, 3);
-        a[0] = t0 * 0.75f + (i > 0 ? t1 * 0.25f : 0.f);
-        a[1] = t0 * 0.25f + t1 * (i > 0 ? 0.75f : 1.f) + t2 * (i < n_ - 1 ? 0.75f : 1.f) + t3 * 0.25f;
-        a[2] = (i < n_ - 1 ? t2 * 0.25f : 0.f) + t3 * 0.75f;
-    };
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
-        const int cv = (int)(i % cvec);
-        const unsigned s = i / cvec;
-        const int w = (int)(s % (unsigned)W), h = (int)((s / (unsigned)W) % (unsigned)H), d = (int)(s / (unsigned)(W * H));
-        float ad[3] = {0.f, 1.f, 0.f}, ah[3], aw[3];
-        if (fd == 2) uu(d, D, ad);
-        uu(h, H, ah);
-        uu(w, W, aw);
-        float sz[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) sz[v] = 0.f;
-        const T* zn = zlow + (size_t)n * D * H * W * zlow_ld + cv * VEC;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (ad[a] == 0.f) continue;
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                if (ah[b] == 0.f) continue;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (aw[c] == 0.f) continue;
-                    float t[VEC];
-                    Vec<T, VEC>::load(zn + (((size_t)(d + a - 1) * H + (h + b - 1)) * W + (w + c - 1)) * zlow_ld, t);
-                    const float wt = ad[a] * ah[b] * aw[c];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) sz[v] = fmaf(wt, t[v], sz[v]);
-                }
-            }
-        }
-        T* q = dx + ((size_t)n * D * H * W + s) * dx_ld + cv * VEC;
-        float r[VEC];
-        Vec<T, VEC>::load(q, r);
-        const float* cf = coef + (size_t)n * coef_nstride + (size_t)cv * VEC * 3;
-        const float wsum = (fd == 2 ? 2.f : 1.f) * 4.f;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) r[v] = fmaf(cf[3 * v], r[v], fmaf(cf[3 * v + 1], sz[v], cf[3 * v + 2] * wsum));
-        Vec<T, VEC>::store(q, r);
     }
 }
 
@@ -1583,7 +1255,7 @@ int b200em_maxpool3d_bwd(const void* x, int64_t x_ld, const void* dp, int64_t dp
         const int64_t si_ = (int64_t)D * H * W;
         const int64_t ldmax = std::max(std::max(x_ld, out_ld), std::max(add ? add_ld : (int64_t)0, dp_ld));
         if (can_vec<T>(C, {x_ld, dp_ld, add ? add_ld : (int64_t)V, out_ld}, {x, dp, add, out}) && fd <= 2 && fh == 2 && fw == 2 &&
-            si_ * ldmax * (int64_t)sizeof(T) < (1LL << 32) && D % fd == 0 && H % 2 == 0 && W % 2 == 0 && !getenv("B200EM_POOL_OLD")) {
+            si_ * ldmax * (int64_t)sizeof(T) < (1LL << 32) && D % fd == 0 && H % 2 == 0 && W % 2 == 0) {
             int64_t total = So * (C / V);
             const dim3 grid(flat_grid(total, 256, N), N);
             const size_t sm = coef ? C * 3 * sizeof(float) : 0;
@@ -1618,7 +1290,7 @@ int b200em_upsample_trilinear_fwd(const void* x, int64_t x_ld, void* y, int64_t 
         const int cvec_ = C / V;
         const int64_t totv = (int64_t)D * H * W * cvec_, so_bytes = So * y_ld * (int64_t)sizeof(T);
         if (can_vec<T>(C, {x_ld, y_ld}, {x, y}) && cvec_ <= 256 && 256 % cvec_ == 0 && fd <= 2 && fh == 2 && fw == 2 && totv < (1LL << 31) &&
-            so_bytes < (1LL << 32) && (int64_t)D * H * W * x_ld * (int64_t)sizeof(T) < (1LL << 32) && N <= 65535 && !getenv("B200EM_UP_PAIR")) {
+            so_bytes < (1LL << 32) && (int64_t)D * H * W * x_ld * (int64_t)sizeof(T) < (1LL << 32) && N <= 65535) {
             // >= 4 low-resolution voxels (32 outputs) per thread: the per-block statistics reduction and its atomics amortise
             // few, long-lived blocks: every block ends with 2 * C atomics on the same N * C * 2 statistics words
             int64_t blocks = (totv + 256 * 4 - 1) / (256 * 4);
@@ -1630,26 +1302,6 @@ int b200em_upsample_trilinear_fwd(const void* x, int64_t x_ld, void* y, int64_t 
                 upsample2_fwd_block_kernel<T, V, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, (unsigned)totv);
             else
                 upsample2_fwd_block_kernel<T, V, 1><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, (unsigned)totv);
-        } else if (can_vec<T>(C, {x_ld, y_ld}, {x, y}) && cvec_ <= 256 && 256 % cvec_ == 0 && fd <= 2 && fh == 2 && fw == 2) {
-            const int64_t tot = (int64_t)D * fd * H * 2 * W * cvec_;
-            if (tot < (1LL << 31) && N <= 65535) {
-                // >= 16 outputs pairs per thread: the per-block statistics reduction and its atomics amortise
-                int64_t blocks = (tot + 256 * 16 - 1) / (256 * 16);
-                const int64_t cap = (int64_t)sm_count() * 8;
-                if (blocks > cap) blocks = cap;
-                dim3 grid((unsigned)blocks, (unsigned)N, 1);
-                if (fd == 2)
-                    upsample2_fwd_pair_kernel<T, V, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, (unsigned)tot);
-                else
-                    upsample2_fwd_pair_kernel<T, V, 1><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, (unsigned)tot);
-            } else {
-                const int th = (H + UP_BH - 1) / UP_BH, tw = (W + UP_BW - 1) / UP_BW, td = (D + UP_BD - 1) / UP_BD;
-                dim3 grid((unsigned)(td * th * tw), 1, (unsigned)N);
-                if (fd == 2)
-                    upsample2_fwd_kernel<T, V, 2, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, th, tw);
-                else
-                    upsample2_fwd_kernel<T, V, 1, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, sums, th, tw);
-            }
         } else if (can_vec<T>(C, {x_ld, y_ld}, {x, y})) {
             Launch2D l = make_launch(C / V, So, N);
             upsample_fwd_kernel<T, V><<<l.grid, l.block, 0, (cudaStream_t)stream>>>((const T*)x, x_ld, (T*)y, y_ld, D, H, W, C, fd, fh, fw, sums);
@@ -1677,7 +1329,7 @@ int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, const void* zlo
             const int nd = fd == 2 ? 2 : 1;
             const int64_t totb = (int64_t)((D + nd - 1) / nd) * ((H + 1) / 2) * ((W + 1) / 2) * cvec_;
             if (Si * fd * 4 * dy_ld * (int64_t)sizeof(T) < (1LL << 32) && Si * dx_ld * (int64_t)sizeof(T) < (1LL << 32) &&
-                (!coef || Si * zlow_ld * (int64_t)sizeof(T) < (1LL << 32)) && !getenv("B200EM_UP_OLD")) {
+                (!coef || Si * zlow_ld * (int64_t)sizeof(T) < (1LL << 32))) {
                 int64_t blocks = (totb + 127) / 128;
                 const int64_t cap = (int64_t)sm_count() * 16;
                 if (blocks > cap) blocks = cap;
@@ -1691,19 +1343,13 @@ int b200em_upsample_trilinear_bwd(const void* dy, int64_t dy_ld, const void* zlo
                 B2_LAUNCH_CHECK();
                 return 0;
             }
-            const int th = (H + UP_BH - 1) / UP_BH, tw = (W + UP_BW - 1) / UP_BW, td = (D + UP_BD - 1) / UP_BD;
-            dim3 grid((unsigned)(td * th * tw), 1, (unsigned)N);
-            if (fd == 2)
-                upsample2_bwd_kernel<T, V, 2, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, th, tw);
-            else
-                upsample2_bwd_kernel<T, V, 1, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, th, tw);
             if (coef) {
-                // NOTE: the intermediate U^T dy is rounded to the activation type once more than in the unfused form (bf16: 2^-9)
-                count_launch();
-                const int64_t total = Si * cvec_;
-                upsample2_bwd_norm_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>(
-                    (T*)dx, dx_ld, (const T*)zlow, zlow_ld, coef, coef_nstride, D, H, W, C, fd, total);
+                set_error("upsample_bwd: the fused norm backward needs tensors below 4 GiB per sample (32-bit byte offsets)");
+                return 2;
             }
+            // (larger samples: the generic kernel below)
+            int64_t total = Si * (C / V);
+            upsample_bwd_kernel<T, V><<<dim3(flat_grid(total, 256, N), N), 256, 0, (cudaStream_t)stream>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, D, H, W, C, fd, fh, fw, total);
         } else if (coef) {
             set_error("upsample_bwd: the fused norm backward needs 16-byte aligned channel vectors (a power-of-two count of them) and factors (1|2, 2, 2)");
             return 2;
