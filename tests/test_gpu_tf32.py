@@ -245,3 +245,42 @@ def test_h16_prediction_matches_exact_fp32(tf32):
         torch.backends.cudnn.allow_tf32 = False
         y32 = net(x)
     assert float((y16 - y32).abs().max()) < 5e-3 and float((y16 - y32).norm() / y32.norm()) < 1e-3
+
+
+def test_h16_training_trajectory_tracks_exact_fp32(tf32):
+    """Fifteen AdamW steps of the same net on the same batch: the h16 path (default fp32 mode), the kind::tf32 kernels and the
+    exact-fp32 CUDA-core kernels must descend along the same loss curve (TF32-class rounding only perturbs it)."""
+    from torch_em_b200.backend import default_backend
+    B = default_backend()
+    kw = dict(in_channels=1, out_channels=2, depth=2, initial_features=32, final_activation="Sigmoid")
+    torch.manual_seed(7)
+    x = torch.randn(2, 1, 16, 32, 32, device=DEV)
+    t = (torch.nn.functional.avg_pool3d(torch.randn(2, 2, 16, 32, 32), 5, 1, 2) > 0).float().to(DEV)
+    curves = {}
+    was = B.use_h16
+    try:
+        for mode in ("exact", "h16", "tf32"):
+            torch.backends.cudnn.allow_tf32 = mode != "exact"
+            B.use_h16 = mode == "h16"
+            torch.manual_seed(0)
+            net = tb.UNet3d(**kw).to(DEV)
+            opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+            B.calls.clear()
+            losses = []
+            for _ in range(15):
+                opt.zero_grad()
+                loss = tb.DiceLoss()(net(x), t)
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+            want = {"exact": "direct:", "h16": "h16:", "tf32": "tf32:"}[mode]
+            assert any(k.startswith(want) for k in B.calls), (mode, dict(B.calls))
+            curves[mode] = losses
+    finally:
+        B.use_h16 = was
+    ex = np.array(curves["exact"])
+    assert ex[-1] < ex[0] - 0.02, ex                                  # it trains
+    # (a training trajectory amplifies any rounding difference: the TF32-class curves wander ~0.5 % around the exact one)
+    dev = {mode: float(np.max(np.abs(np.array(curves[mode]) - ex) / ex)) for mode in ("h16", "tf32")}
+    assert dev["h16"] < 2e-2 and dev["tf32"] < 2e-2, dev
+    assert dev["h16"] <= 3.0 * dev["tf32"] + 5e-3, dev
