@@ -60,7 +60,7 @@ KERNEL_OF = {"first:fwd": "conv3d_first_kernel", "first:wgrad": "conv3d_first_wg
              "tf32:fwd": "conv3d_umma_kernel<float> (TF32)", "tf32:dgrad": "conv3d_umma_kernel<float> (TF32)",
              "split3:wgrad": "split_bf16 + 3 x conv3d_wgrad_{cs,umma}_kernel (bf16 hi/lo)",
              "h16:fwd": "conv3d_umma_kernel<__half, float", "h16:dgrad": "conv3d_umma_kernel<__half, float",     # (substrings of the ncu names)
-             "h16:wgrad": "conv3d_wgrad_{cs,umma}_kernel (h16: fp16 operands)"}
+             "h16:wgrad": "conv3d_wgrad_{cs,umma}_kernel (h16: fp16 operands)", "h16ds:fwd": "conv3d_umma_ds_kernel"}
 
 
 def synthetic_batch(batch, patch, seed, kind="dice", out_channels=2):
@@ -521,7 +521,7 @@ def run_ours(args):
     if bf16:
         tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-    elif any(k.startswith("h16:") for k in fam):
+    elif any(k.startswith("h16") for k in fam):
         tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "measured sustained 16-bit tensor rate (fp32 activations run the h16 path: fp16 operand copies, kind::f16 MMAs, fp32 accumulate)"
     else:

@@ -143,6 +143,12 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
                           void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W,
                           int Cin, int Cout, int kd, int kh, int kw, int relu, void* stream);
 
+/* h16 variant of the depth-stacked kernel (forward convs of fp32 activations whose input is normalised, i.e. needs no range
+ * scale): x_f16 from b200em_cvt_f16 with the norm apply in it, w_packed with B200EM_PACK_DEPTH_STACKED_F16, fp32 output and
+ * statistics.  No dot_x: the fp32 data gradients take b200em_conv3d_umma_h16. */
+int b200em_conv3d_umma_ds_h16(const void* x_f16, int64_t x_ld, const void* w_packed, const float* bias, float* y, int64_t y_ld, float* sums,
+                              int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int relu, void* stream);
+
 /* Batched packing: the bf16 operand images of EVERY conv weight of a model in one launch (csrc/pack.cu).  The fp32
  * nn.Parameter (unet.py:431,435,453) stays the master; the images are rebuilt at the start of every forward / backward pass,
  * so no in-place parameter update can leave a stale operand behind.  The caller fills w, packed (Cout*Cin*taps bf16, 16-byte
@@ -152,6 +158,7 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
 #define B200EM_PACK_DEPTH_STACKED 1  /* operand of b200em_conv3d_umma_ds */
 #define B200EM_PACK_PLAIN_TF32 2     /* fp32 operand of b200em_conv3d_umma_tf32 (packed: Cout*Cin*taps fp32) */
 #define B200EM_PACK_PLAIN_F16 3      /* IEEE fp16 operand of b200em_conv3d_umma_h16 (the plain layout) */
+#define B200EM_PACK_DEPTH_STACKED_F16 4   /* IEEE fp16 operand of b200em_conv3d_umma_ds_h16 (the depth-stacked layout) */
 typedef struct b200em_pack_job {
     const float* w;    /* torch (Cout, Cin, kd, kh, kw) fp32, device */
     void* packed;      /* bf16 operand image, device */

@@ -50,7 +50,7 @@ def _f32(t):
 class WeightPack:
     """Kernel-operand copies of one conv weight (derived data; the fp32 nn.Parameter stays the master)."""
     __slots__ = ("w_fwd_f32", "w_dgrad_f32", "f32_stale", "umma_fwd", "umma_dgrad", "cout", "cin", "kernel", "thin", "thin_kp",
-                 "ds_fwd", "ds_dgrad", "master", "tf32_fwd", "tf32_dgrad", "h16_fwd", "h16_dgrad")
+                 "ds_fwd", "ds_dgrad", "master", "tf32_fwd", "tf32_dgrad", "h16_fwd", "h16_dgrad", "h16_ds_fwd")
 
 
 class H16Operand:
@@ -71,7 +71,7 @@ class _PackJob(ctypes.Structure):
                 ("reserved", ctypes.c_int32 * 2)]
 
 
-PACK_PLAIN, PACK_DEPTH_STACKED, PACK_PLAIN_TF32, PACK_PLAIN_F16 = 0, 1, 2, 3
+PACK_PLAIN, PACK_DEPTH_STACKED, PACK_PLAIN_TF32, PACK_PLAIN_F16, PACK_DEPTH_STACKED_F16 = 0, 1, 2, 3, 4
 
 
 class PackSet:
@@ -115,7 +115,7 @@ class PackSet:
             pk.w_fwd_f32 = pk.w_dgrad_f32 = None
             pk.f32_stale = True
             pk.umma_fwd = pk.umma_dgrad = pk.thin = pk.ds_fwd = pk.ds_dgrad = pk.tf32_fwd = pk.tf32_dgrad = None
-            pk.h16_fwd = pk.h16_dgrad = None
+            pk.h16_fwd = pk.h16_dgrad = pk.h16_ds_fwd = None
             pk.thin_kp = 0
             n = cout * cin * kd * kh * kw
             if B.use_umma:
@@ -134,6 +134,8 @@ class PackSet:
                     plan[3].append((pk, "tf32_dgrad", PACK_PLAIN_TF32, n))
                 if lib.b200em_conv3d_umma_supported(cin, cout, kd, kh, kw):
                     plan[4].append((pk, "h16_fwd", PACK_PLAIN_F16, n))
+                if B.use_ds and lib.b200em_conv3d_umma_ds_supported(cin, cout, kd, kh, kw):
+                    plan[4].append((pk, "h16_ds_fwd", PACK_DEPTH_STACKED_F16, n))     # forward only: the depth-stacked kernel, fp32 out
                 if lib.b200em_conv3d_umma_supported(cout, cin, kd, kh, kw):
                     plan[5].append((pk, "h16_dgrad", PACK_PLAIN_F16, n))
                 kp = -(-kd * kh * kw * cin // 32) * 32
@@ -493,6 +495,12 @@ class CudaBackend:
             dp, dld = _act(dot_x) if dot_x is not None else (None, 0)
             if dot_x is None or (dld % 4 == 0 and dot_x.data_ptr() % 16 == 0):
                 xh = self.to_h16(x, in_ss)
+                if (not dgrad) and pack.h16_ds_fwd is not None and xh.absmax is None and dot_x is None and self.use_ds:
+                    # few output channels, normalised (unscaled) input: the depth-stacked kernel on the fp16 copy, fp32 output
+                    self._timed("h16ds:fwd", flops, lambda: call(
+                        "b200em_conv3d_umma_ds_h16", _ptr(xh.t), Cin, _ptr(pack.h16_ds_fwd), _f32(b), yp, yld, _f32(sums), N, D, H, W,
+                        Cin, Cout, kd, kh, kw, int(relu), _stream(x)))
+                    return xh
                 self._timed("h16:dgrad" if dgrad else "h16:fwd", flops, lambda: call(
                     "b200em_conv3d_umma_h16", _ptr(xh.t), Cin, _f32(xh.absmax), _ptr(wh), _f32(b), yp, yld, _f32(sums), dp, dld, N, D,
                     H, W, Cin, Cout, kd, kh, kw, int(relu), _stream(x)))

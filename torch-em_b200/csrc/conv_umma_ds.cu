@@ -44,7 +44,8 @@ struct ConvDsParams {
     const float* in_ss;
     const __nv_bfloat16* w;
     const float* bias;
-    __nv_bfloat16* y; long long y_ld;
+    void* y; long long y_ld;                        // bf16, or fp32 for the h16 instantiation (TO = float)
+    int fp16;                                       // operands (x, w) are IEEE fp16: the h16 path of fp32 activations (in_ss, dot_x unused)
     float* sums;
     const __nv_bfloat16* dot_x; long long dot_ld;   // non-null: sums = (sum y, sum y * dot_x) -- the norm-backward reductions
     int N, D, H, W, Cin, Cout;
@@ -200,7 +201,7 @@ template <int CO> struct DsRoles {
     static constexpr int CPT = SPLIT ? CO / 2 : CO;        // output columns per epilogue thread
 };
 
-template <int CO, int KC_>
+template <int CO, int KC_, typename TO = __nv_bfloat16>
 __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel(const ConvDsParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     using RL = DsRoles<CO>;
@@ -373,7 +374,9 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
     } else if (warp == DS_W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            const uint32_t idesc1 = make_idesc_bf16(128, CO), idesc2 = make_idesc_bf16(128, 2 * CO), idesc3 = make_idesc_bf16(128, N3);
+            const uint32_t idesc1 = p.fp16 ? make_idesc_f16(128, CO) : make_idesc_bf16(128, CO),
+                           idesc2 = p.fp16 ? make_idesc_f16(128, 2 * CO) : make_idesc_bf16(128, 2 * CO),
+                           idesc3 = p.fp16 ? make_idesc_f16(128, N3) : make_idesc_bf16(128, N3);
             const uint64_t ad = make_desc(0, DS_PLANE, DS_WP * 16), bd = make_desc(0, (uint32_t)(N3 * 16), 128);
             const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
             const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
@@ -557,28 +560,28 @@ __global__ void __launch_bounds__(DsRoles<CO>::THREADS, 1) conv3d_umma_ds_kernel
                 tc_fence_after();
                 const int gd = d0 + od;
                 const bool valid = valid_hw && gd < p.D;
-                __nv_bfloat16* yp = p.y + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld + col0;
+                TO* yp = reinterpret_cast<TO*>(p.y) + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld + col0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(blk * CO + col0);
                 const float* s_biasg = p.bias ? s_bias + col0 : nullptr;
                 const float* const s_bias0 = p.bias ? s_bias : nullptr;     // (an absent bias costs no shared-memory loads)
                 float* s_sumsg = s_sums + 2 * col0;
                 if (p.debug & 2) {
                 } else if constexpr (CPT == 16) {
-                    ds_epilogue_block<16, true>(taddr, s_biasg, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sumsg, ws, lane);
+                    ds_epilogue_block<16, true, TO>(taddr, s_biasg, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sumsg, ws, lane);
                 } else if constexpr (CPT == 32) {
                     // two 16-column passes: half the live registers of one 32-column pass (the 64 statistics accumulators stay)
-                    ds_epilogue_block<16, true>(taddr, s_biasg, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sumsg, ws, lane);
-                    ds_epilogue_block<16, true>(taddr + 16, s_biasg ? s_biasg + 16 : nullptr, p.relu, valid, yp + 16, xcur + 2, has_x, acc_s + 16, acc_q + 16,
+                    ds_epilogue_block<16, true, TO>(taddr, s_biasg, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sumsg, ws, lane);
+                    ds_epilogue_block<16, true, TO>(taddr + 16, s_biasg ? s_biasg + 16 : nullptr, p.relu, valid, yp + 16, xcur + 2, has_x, acc_s + 16, acc_q + 16,
                                                 s_sumsg, ws, lane);
                 } else {
-                    ds_epilogue_block<32, false>(taddr, s_bias0, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sums, ws, lane);
+                    ds_epilogue_block<32, false, TO>(taddr, s_bias0, p.relu, valid, yp, xcur, has_x, acc_s, acc_q, s_sums, ws, lane);
                     if constexpr (CO == 48)
-                        ds_epilogue_block<16, false>(taddr + 32, s_bias0 ? s_bias0 + 32 : nullptr, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
+                        ds_epilogue_block<16, false, TO>(taddr + 32, s_bias0 ? s_bias0 + 32 : nullptr, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
                                                      s_sums + 64, ws, lane);
                     if constexpr (CO == 80) {
-                        ds_epilogue_block<32, false>(taddr + 32, s_bias0 ? s_bias0 + 32 : nullptr, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
+                        ds_epilogue_block<32, false, TO>(taddr + 32, s_bias0 ? s_bias0 + 32 : nullptr, p.relu, valid, yp + 32, xcur + 4, has_x, acc_s, acc_q,
                                                      s_sums + 64, ws, lane);
-                        ds_epilogue_block<16, false>(taddr + 64, s_bias0 ? s_bias0 + 64 : nullptr, p.relu, valid, yp + 64, xcur + 8, has_x, acc_s, acc_q,
+                        ds_epilogue_block<16, false, TO>(taddr + 64, s_bias0 ? s_bias0 + 64 : nullptr, p.relu, valid, yp + 64, xcur + 8, has_x, acc_s, acc_q,
                                                      s_sums + 128, ws, lane);
                     }
                 }
@@ -1139,23 +1142,30 @@ int b200em_conv3d_umma_ds_pack(const float* w, int Cout, int Cin, int kd, int kh
     return 0;
 }
 
-int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+}  // extern "C"
+
+// TO = __nv_bfloat16: bf16 activations in and out.  TO = float: the h16 path -- fp16 operand copies in, fp32 out (no fused norm
+// apply: b200em_cvt_f16 did it; no dot_x: the fp32 data gradients take the plain kernel).
+template <typename TO>
+static int launch_conv_ds(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
                           void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W,
                           int Cin, int Cout, int kd, int kh, int kw, int relu, void* stream) {
+    constexpr bool H16 = sizeof(TO) == 4;
+    B2_CHECK_ARG(!H16 || (!in_scale_shift && !dot_x), "conv3d_umma_ds_h16: takes neither a fused norm apply nor dot_x");
     B2_CHECK_ARG(x && w_packed && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_umma_ds: bad arguments");
     DsShape s;
     if (!ds_shape(Cin, Cout, kd, kh, kw, s, dot_x != nullptr)) {
         set_error("conv3d_umma_ds: shape (%d -> %d, %dx%dx%d) not supported by the depth-stacked tcgen05 path", Cin, Cout, kd, kh, kw);
         return 2;
     }
-    B2_CHECK_ARG(x_ld % 8 == 0 && y_ld % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(w_packed),
+    B2_CHECK_ARG(x_ld % 8 == 0 && y_ld % (H16 ? 4 : 8) == 0 && aligned16(x) && aligned16(y) && aligned16(w_packed),
                  "conv3d_umma_ds: activations must be 16-byte aligned with pitch % 8 == 0");
     B2_CHECK_ARG(x_ld >= Cin && y_ld >= Cout, "conv3d_umma_ds: pitch smaller than channel count");
     B2_CHECK_ARG((long long)H * W * x_ld < (1LL << 31), "conv3d_umma_ds: slice too large for 32-bit in-slice offsets");
     B2_CHECK_ARG(!dot_x || (sums && dot_ld % 8 == 0 && aligned16(dot_x) && dot_ld >= Cout), "conv3d_umma_ds: dot_x needs sums, 16-byte alignment and pitch >= Cout");
     ConvDsParams p;
     p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.in_ss = in_scale_shift; p.w = (const __nv_bfloat16*)w_packed; p.bias = bias;
-    p.y = (__nv_bfloat16*)y; p.y_ld = y_ld; p.sums = sums; p.dot_x = (const __nv_bfloat16*)dot_x; p.dot_ld = dot_ld;
+    p.y = y; p.y_ld = y_ld; p.fp16 = H16 ? 1 : 0; p.sums = sums; p.dot_x = (const __nv_bfloat16*)dot_x; p.dot_ld = dot_ld;
     p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.relu = relu;
     p.CC = s.CC; p.nchunks = Cin / s.CC; p.NS = s.NS; p.wbytes = s.wbytes; p.xdepth = s.xdepth;
     { const int nlw_max = (Cout == 64 || Cout == 32) ? 6 : 8; p.nlw = s.NS < nlw_max ? s.NS : nlw_max; }
@@ -1196,7 +1206,7 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
                                             (cuuint64_t)D * H * W * x_ld * 2};
                 const cuuint32_t box[5] = {8, (cuuint32_t)DS_WP, (cuuint32_t)DS_HP, 1, 1};
                 const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-                const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                const CUresult r = encode(&tmap, H16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r == CUDA_SUCCESS) p.use_tma = 1;
@@ -1206,11 +1216,11 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
 #define B2_DS_LAUNCH(CO_)                                                                                                          \
     case CO_:                                                                                                                      \
         if (s.CC == 32) {                                                                                                          \
-            B2_CUDA(cudaFuncSetAttribute(conv3d_umma_ds_kernel<CO_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
-            conv3d_umma_ds_kernel<CO_, 2><<<(unsigned)gx, DsRoles<CO_>::THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p, tmap);                    \
+            B2_CUDA(cudaFuncSetAttribute(conv3d_umma_ds_kernel<CO_, 2, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
+            conv3d_umma_ds_kernel<CO_, 2, TO><<<(unsigned)gx, DsRoles<CO_>::THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p, tmap);                    \
         } else {                                                                                                                   \
-            B2_CUDA(cudaFuncSetAttribute(conv3d_umma_ds_kernel<CO_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
-            conv3d_umma_ds_kernel<CO_, 1><<<(unsigned)gx, DsRoles<CO_>::THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p, tmap);                    \
+            B2_CUDA(cudaFuncSetAttribute(conv3d_umma_ds_kernel<CO_, 1, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
+            conv3d_umma_ds_kernel<CO_, 1, TO><<<(unsigned)gx, DsRoles<CO_>::THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p, tmap);                    \
         }                                                                                                                          \
         break;
     switch (Cout) {
@@ -1226,6 +1236,20 @@ int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shi
 #undef B2_DS_LAUNCH
     B2_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" {
+
+int b200em_conv3d_umma_ds(const void* x, int64_t x_ld, const float* in_scale_shift, const void* w_packed, const float* bias,
+                          void* y, int64_t y_ld, float* sums, const void* dot_x, int64_t dot_ld, int N, int D, int H, int W,
+                          int Cin, int Cout, int kd, int kh, int kw, int relu, void* stream) {
+    return launch_conv_ds<__nv_bfloat16>(x, x_ld, in_scale_shift, w_packed, bias, y, y_ld, sums, dot_x, dot_ld, N, D, H, W, Cin, Cout, kd, kh, kw,
+                                         relu, stream);
+}
+
+int b200em_conv3d_umma_ds_h16(const void* x_f16, int64_t x_ld, const void* w_packed, const float* bias, float* y, int64_t y_ld, float* sums,
+                              int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int relu, void* stream) {
+    return launch_conv_ds<float>(x_f16, x_ld, nullptr, w_packed, bias, y, y_ld, sums, nullptr, 0, N, D, H, W, Cin, Cout, kd, kh, kw, relu, stream);
 }
 
 int b200em_conv3d_first_supported(int Cin, int Cout, int kd, int kh, int kw) { return first_shape(Cin, Cout, kd, kh, kw) ? 1 : 0; }

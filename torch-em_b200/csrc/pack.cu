@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const b200em_pack_job* 
     const int Nc = dgrad ? Cin : Cout;                 // output channels of the packed operand
     const int nchunks = Kc / CC, J = CC / 8;
     const int thw = job.kh * job.kw;
-    const bool f16 = job.layout == B200EM_PACK_PLAIN_F16;
+    const bool f16 = job.layout == B200EM_PACK_PLAIN_F16 || job.layout == B200EM_PACK_DEPTH_STACKED_F16;
     // 16-byte units (8 reduction channels of one operand row n and tap): forward n = co (8 rows) x TCI/8 ci groups, data gradient
     // n = ci (TCI rows) x the tile's one co group; consecutive threads take consecutive n (adjacent 16-byte units of the image)
     const int nrows = dgrad ? TCI : 8, kgroups = dgrad ? 1 : TCI / 8;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const b200em_pack_job* 
         const int n_ = (dgrad ? ci0 : co0) + nl, k0 = dgrad ? co0 : ci0 + kg * 8, t_ = dgrad ? taps - 1 - tp : tp;
         const int chunk = k0 / CC, j = (k0 % CC) / 8;
         size_t o;
-        if (job.layout == B200EM_PACK_PLAIN || f16) {
+        if (job.layout == B200EM_PACK_PLAIN || job.layout == B200EM_PACK_PLAIN_F16) {
             const int NPb = job.NPb;
             const int nb = n_ / NPb, nn = n_ % NPb;
             o = ((((size_t)(nb * nchunks + chunk) * taps + t_) * J + j) * NPb + nn) * 8;
@@ -134,7 +134,7 @@ int b200em_pack_batch_prepare(b200em_pack_job* jobs, int njobs, int* total_block
         bool ok;
         if (j.layout == B200EM_PACK_PLAIN || j.layout == B200EM_PACK_PLAIN_TF32 || j.layout == B200EM_PACK_PLAIN_F16) {
             ok = umma_pack_layout(k_, n_, j.kd, j.kh, j.kw, &j.CC, &j.NPb, j.layout == B200EM_PACK_PLAIN_TF32);
-        } else if (j.layout == B200EM_PACK_DEPTH_STACKED) {
+        } else if (j.layout == B200EM_PACK_DEPTH_STACKED || j.layout == B200EM_PACK_DEPTH_STACKED_F16) {
             j.NPb = 0;
             ok = ds_pack_layout(k_, n_, j.kd, j.kh, j.kw, &j.CC);
         } else {
