@@ -614,9 +614,9 @@ def run_reference_cfg5(args):
 
 def run_ours_cfg5(args):
     """Tiled prediction of a 512^3 volume (64 blocks of 128^3 + halo 32 -> 192^3 network inputs).  A "step" is one whole-volume
-    prediction through the public API from a HOST numpy array to a HOST numpy array (one H2D of the volume, one D2H of the
-    result inside the timed region); ``value`` = the same with the volume already on the device, measured by timing the
-    device work only (CUDA events around the block loop)."""
+    prediction through the public API from a HOST numpy array to a HOST numpy array (the H2D of the volume and the D2H of the
+    result inside the timed region, overlapped with the block loop on side streams); ``value`` = the device work only (CUDA
+    events on the compute stream from the arrival of the first batch's rows to the last scatter)."""
     import numpy as np
     import torch
     import torch_em_b200 as tb
@@ -676,7 +676,9 @@ def run_ours_cfg5(args):
                                f"block {bs} halo {halo} ({cfg['label']})",
                    "kept_fraction_of_computed_voxels": kept_frac, "blocks": int(np.prod([-(-s // b_) for s, b_ in zip(shape, bs)])),
                    "value": "block loop on the device (gather, standardize, forward, scatter), volume and output resident in HBM",
-                   "e2e": "host numpy volume -> predict_with_halo -> host numpy result: one H2D, the block loop, one D2H",
+                   "e2e": "host numpy volume -> predict_with_halo -> host numpy result; the volume goes up in row ranges ahead of the blocks "
+                          "that read them and finished output rows go down behind them (side streams): h2d_ms / d2h_ms are the "
+                          "EXPOSED parts (first batch's rows up, last rows down)",
                    "l2": "volume, activations and output larger than L2",
                    "conv_tflop_per_step": conv_flops / 1e12, "conv_ms_per_step": conv_ms},
         "e2e": {"value": n_vox / sec_e2e, "unit": "voxels/s", "ms_per_step": sec_e2e * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -152,6 +152,31 @@ def test_device_path_raw_dtypes(dtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("overlap", ["1", "0"])
+@pytest.mark.parametrize("order", ["ascending", "descending", "shuffled", "partial"])
+def test_device_path_transfer_overlap(monkeypatch, overlap, order):
+    """The volume goes up in row ranges ahead of the batches that read them and finished output rows go down behind them
+    (side streams).  Whatever the block order (iter_list) -- ascending overlaps, anything else degrades to up-front / at-the-end
+    copies -- the result is the reference's; several row slabs, truncated last blocks, a mask and a batch of 3."""
+    monkeypatch.setenv("B200EM_PREDICT_OVERLAP", overlap)
+    rng = np.random.default_rng(11)
+    vol = (rng.random((50, 22, 26)) * 100).astype("float32")
+    mask = np.ones(vol.shape, dtype=bool)
+    mask[18:31, :, 5:20] = False
+    mask[16:24, 0:16, 0:16] = False                       # block 8 has an empty inner mask: skipped
+    net, cpu = TinyNet().to("cuda:0"), TinyNet()
+    block_shape, halo = (8, 16, 16), (3, 2, 4)
+    n_blocks = 7 * 2 * 2
+    ids = {"ascending": None, "descending": list(range(n_blocks))[::-1], "shuffled": [int(i) for i in rng.permutation(n_blocks)],
+           "partial": [3, 4, 17, 9, 27]}[order]
+    ref = opred.predict_with_halo(vol, np_net(cpu), block_shape, halo, n_out=2, mask=mask, iter_list=ids, preprocess=opred.standardize)
+    out = predict_with_halo_pipelined(vol, net, [0], block_shape, halo, mask=mask, iter_list=ids, preprocess=standardize, batch_size=3)
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4)
+    from torch_em_b200.util import prediction as P
+    assert P.last_timing["overlap"] == (overlap == "1")
+
+
+@pytest.mark.gpu
 def test_device_path_2d_and_channels():
     class Net2d(torch.nn.Module):
         out_channels = 3

@@ -22,6 +22,7 @@ and inputs that do not fit the device (lazy hdf5 / zarr datasets larger than the
 reference's own per-block host loop, restated, around the same device model.
 """
 import ctypes
+import os
 from concurrent import futures
 from copy import deepcopy
 from typing import Any, Callable, List, Optional, Sequence, Tuple, Union
@@ -164,19 +165,53 @@ def _to3(v, ndim, fill):
     return [fill] * (3 - ndim) + [int(x) for x in v]
 
 
+def _copy_rows(dst, src, lo, hi):
+    """Rows [lo, hi) of the first spatial axis of a (C, rows, ...) array, one contiguous piece per channel (plain memcpys: a
+    strided tensor copy between host and device would go through temporaries)."""
+    for c in range(dst.shape[0]):
+        dst[c, lo:hi].copy_(src[c, lo:hi], non_blocking=True)
+
+
 def _device_worker(net, dev, worker_id, n_workers, vol_np, mask_np, blocks, block_ids, block_shape, halo, ndim, with_channels,
                    standardize_blocks, prediction_function, batch_size, autocast, n_out_hint):
-    """All blocks of one device: returns (host result (C_out, *spatial) float32 pinned tensor, processed block ids)."""
+    """All blocks of one device: returns (host result (C_out, *spatial) float32 pinned tensor, processed block ids).
+
+    The transfers ride on two side streams.  The volume goes up in row ranges of its first spatial axis, always ahead of the batch
+    that needs them (a haloed block reads rows [begin - halo, begin + block_shape + halo) clipped to the volume: the reflect
+    padding of prediction.py:98-142 mirrors the CLIPPED data), so that only the rows of the first batch are waited for; finished
+    output rows -- those below the first row of every block still to come -- go down while later blocks are computed, so that
+    only the last rows' copy is exposed.  ``B200EM_PREDICT_OVERLAP=0`` restores one copy up, the loop, one copy down."""
     mine = [b for b in block_ids if b % n_workers == worker_id]
     if not mine:
         return None, []
     code = _RAW_CODES[str(vol_np.dtype)]
     ship = vol_np.view(_SAME_BITS[str(vol_np.dtype)]) if str(vol_np.dtype) in _SAME_BITS else vol_np
+    overlap = os.environ.get("B200EM_PREDICT_OVERLAP", "1") != "0"
     with torch.cuda.device(dev), torch.no_grad(), autocast(dev):
+        main = torch.cuda.current_stream(dev)
+        up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        vol = torch.from_numpy(ship).to(dev, non_blocking=True)                  # the volume: ONE host -> device copy
-        ev[1].record()
+        ship_t = torch.from_numpy(ship)
+        vol = torch.empty(ship_t.shape, dtype=ship_t.dtype, device=dev)
+        vol.record_stream(up)
+        up.wait_stream(main)                                                     # the allocation may recycle memory still in use on main
+        rows = vol.shape[1]
+        uploaded = 0
+
+        def upload(hi):
+            """Rows [uploaded, hi) of the volume, host -> device on the side stream; the compute stream waits for them."""
+            nonlocal uploaded
+            hi = min(rows, hi)
+            if hi <= uploaded:
+                return
+            with torch.cuda.stream(up):
+                _copy_rows(vol, ship_t, uploaded, hi)
+                done = torch.cuda.Event()
+                done.record(up)
+            main.wait_event(done)
+            uploaded = hi
+
         C = vol.shape[0]
         D, H, W = _to3(vol.shape[1:], ndim, 1)
         spatial = tuple(vol.shape[1:])
@@ -191,10 +226,22 @@ def _device_worker(net, dev, worker_id, n_workers, vol_np, mask_np, blocks, bloc
                 return None, []
         bd, bh, bw = _to3([bs + 2 * ha for bs, ha in zip(block_shape, halo)], ndim, 1)
         hd, hh, hw = _to3(halo, ndim, 0)
-        out_d = None
-        for s in range(0, len(mine), batch_size):
-            ids = mine[s:s + batch_size]
+        batches = [mine[s:s + batch_size] for s in range(0, len(mine), batch_size)]
+        need = [max(blocks[i].begin[0] + block_shape[0] + halo[0] for i in ids) for ids in batches]    # volume rows a batch reads
+        # output rows no later batch writes: the smallest first row of the blocks still to come
+        tail, ready = rows, []
+        for ids in reversed(batches):
+            ready.append(tail)
+            tail = min(tail, min(blocks[i].begin[0] for i in ids))
+        ready.reverse()
+        step_rows = -(-rows // len(batches))                                     # spread the upload evenly over the batches
+        upload(need[0] if overlap else rows)
+        ev[1].record()
+        out_d = host = None
+        copied = 0
+        for s, ids in enumerate(batches):
             nb = len(ids)
+            upload(need[s])
             begins = [_to3([b - ha for b, ha in zip(blocks[i].begin, halo)], ndim, 0) for i in ids]
             inp = torch.empty((nb, C, bd, bh, bw), dtype=torch.float32, device=dev)
             stats = torch.zeros((nb, 2), dtype=torch.float64, device=dev) if standardize_blocks else None
@@ -215,20 +262,32 @@ def _device_worker(net, dev, worker_id, n_workers, vol_np, mask_np, blocks, bloc
                 raise ValueError(f"predict_with_halo: the model changed the spatial shape {tuple(x.shape[2:])} -> {tuple(pred.shape[2:])}")
             if out_d is None:
                 out_d = torch.zeros((Cp,) + spatial, dtype=torch.float32, device=dev)
+                out_d.record_stream(down)
+                host = torch.empty(out_d.shape, dtype=torch.float32, pin_memory=True)
             obeg = [_to3(blocks[i].begin, ndim, 0) for i in ids]
             oshp = [_to3(blocks[i].shape, ndim, 1) for i in ids]
             for k in range(0, nb, MAX_BLOCKS_PER_LAUNCH):
                 n_ = min(MAX_BLOCKS_PER_LAUNCH, nb - k)
                 call("b200em_scatter_blocks", _ptr(pred[k:]), Cp, bd, bh, bw, hd, hh, hw, _ints(obeg[k:k + n_]), _ints(oshp[k:k + n_]), n_,
                      _ptr(out_d), D, H, W, 0, Cp, _ptr(mask_d) if mask_d is not None else None, _stream(dev))
-        host = torch.empty(out_d.shape, dtype=torch.float32, pin_memory=True)
-        ev[2].record()
-        host.copy_(out_d, non_blocking=True)                                     # the result: ONE device -> host copy (pinned)
+            last = s + 1 == len(batches)
+            if last:
+                ev[2].record()
+            if overlap or last:
+                hi = rows if last else ready[s]
+                if hi > copied:                                                  # finished output rows go down behind this batch
+                    down.wait_stream(main)
+                    with torch.cuda.stream(down):
+                        _copy_rows(host, out_d, copied, hi)
+                    copied = hi
+            if not last:                                                         # the next batches' rows go up while this one computes
+                upload(max(need[s + 1], uploaded + step_rows))
+        main.wait_stream(down)
         ev[3].record()
-        torch.cuda.current_stream(dev).synchronize()
+        main.synchronize()
         if worker_id == 0:
             last_timing.update(h2d_ms=ev[0].elapsed_time(ev[1]), loop_ms=ev[1].elapsed_time(ev[2]), d2h_ms=ev[2].elapsed_time(ev[3]),
-                               blocks=len(mine), batch_size=batch_size)
+                               blocks=len(mine), batch_size=batch_size, overlap=overlap)
     return host, mine
 
 
