@@ -17,7 +17,9 @@
 // norm), warps 4-11 operand loaders (global -> [scale*x+shift of the preceding norm] -> shared; padding is written as
 // zeros, i.e. in normalised space like the reference), warp 12 weight loader (one elected thread), warp 13 MMA issuer
 // (one elected thread).  All hand-offs are mbarriers; the accumulator hand-off is tcgen05.commit.
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -30,7 +32,8 @@ using namespace umma;
 namespace {
 constexpr int TH = 16, TW = 8;             // voxel tile (h, w) = 128 GEMM rows
 constexpr int HP = TH + 2, WP = TW + 2;     // haloed tile
-constexpr int PLANE = HP * WP * 16 + 16;    // bytes per (slice, 8-channel group) plane; +16 staggers banks
+constexpr int PLANE = HP * WP * 16 + 16;    // bytes per (slice, 8-channel group) plane; +16 staggers banks (cp.async loaders)
+constexpr int PLANE_TMA = 2944;             // the same plane padded to a multiple of 128 B: destination of one tiled TMA load
 constexpr int NSTAGE = 4;                   // maximum weight ring depth (the launch picks p.nstage <= NSTAGE)
 constexpr int NLOAD = 256;                  // operand-loader threads (8 warps): the tile load is latency-bound, more threads = more bytes in flight
 constexpr int THREADS = 128 + NLOAD + 64;   // 4 epilogue warps | 8 loader warps | weight-loader warp | MMA warp
@@ -52,6 +55,7 @@ struct ConvUmmaParams {
     const void* dot_x; long long dot_ld;   // non-null: sums = (sum y, sum y * dot_x) -- the norm-backward reductions
     const float* x_absmax;                 // h16 path: device max |x| the fp16 operand was scaled by (common.cuh h16_shift), or null
     int prefetch;                          // bring-up switch (env B200EM_PREFETCH=0): no L1 prefetch of the dot_x rows
+    int use_tma;                           // 1 (the TMA_ instantiation): the haloed tile planes are loaded by cp.async.bulk.tensor
     int ksplit;                            // > 1: gridDim.z CTAs share an output tile, each reducing a range of the Cin chunks (split-K)
     float* ws_acc; unsigned* ws_cnt;       // split-K: zeroed fp32 partial sums [voxel][Cout] and per-(item, nblk) arrival counters
     int N, D, H, W, Cin, Cout;
@@ -118,10 +122,15 @@ __device__ __forceinline__ void load_row(const T* __restrict__ src, bool valid, 
 // (bf16, bf16), (float, float) = TF32, (__half, float) = the h16 path (fp32 tensors, fp16 operand copies).
 // (448 threads = 14 warps put 4 warps on two of the SM's four sub-partitions, each with 16 K registers: 128 registers per thread
 // is the hardware limit for this block size, whatever __maxnreg__ says -- a launch with 144 fails.)
-template <typename TA, typename TO, int R_, int KC_>
-__global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaParams p) {
+// TMA_: the operand tile arrives by tiled TMA loads (one per slice and 16-byte channel plane, halo zero-filled by the TMA unit)
+// into planes of PLANE_TMA bytes; the loader warps only run the in-place norm apply.  A cp.async (LDGSTS) tile load writes shared
+// memory sector by sector as the data returns -- measured 38 shared-memory wavefronts per warp instruction, ~15 % of the
+// shared-memory pipe the tensor core's operand fetch saturates anyway; the TMA unit writes whole lines.
+template <typename TA, typename TO, int R_, int KC_, bool TMA_>
+__global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int EPU = 16 / (int)sizeof(TA);       // channels per 16-byte unit: 8 (bf16) or 4 (fp32 / TF32)
+    constexpr int PL = TMA_ ? PLANE_TMA : PLANE;    // bytes per (slice, 16-byte channel plane)
     // carve: A[2] | B[NSTAGE] | bias[NP] | sums[2*NP] | barriers | tmem ptr
     uint8_t* smA = smem;
     uint8_t* smB = smA + 2 * p.a_bytes;
@@ -134,7 +143,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
     uint64_t* b_empty = bars + 4 + NSTAGE;
     uint64_t* acc_full = bars + 4 + 2 * NSTAGE;   // [2] tcgen05.commit
     uint64_t* acc_empty = acc_full + 2;           // [2] 128 epilogue arrivals
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* t_full = acc_empty + 2;             // [2] TMA tile loads (expect_tx)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_full + 2);
     uint32_t* s_tap = s_tmem + 2;                   // [27] operand start offset of each tap, in 16-byte units
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -154,14 +164,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], NLOAD / 32); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); mbar_init(&t_full[i], 1); }
         fence_mbar_init();
     }
     if (warp == W_MMA) tmem_alloc(s_tmem, tmem_cols);
     if (threadIdx.x < taps) {
         const int tap = threadIdx.x;
         const int a = tap / (p.kh * p.kw), b = (tap / p.kw) % p.kh, cc = tap % p.kw;
-        s_tap[tap] = (uint32_t)((a * J * PLANE + ((b + 1 - ph) * WP + (cc + 1 - pw)) * 16) >> 4);
+        s_tap[tap] = (uint32_t)((a * J * PL + ((b + 1 - ph) * WP + (cc + 1 - pw)) * 16) >> 4);
     }
     for (int i = threadIdx.x; i < p.NP; i += THREADS) {
         const int co = nblk * p.NP + i;
@@ -177,9 +187,69 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
     if (warp >= 4 && warp < W_WLOAD) {
         // ===================== operand loaders =====================
         const int t = threadIdx.x - 128;             // 0..NLOAD-1
+        uint32_t fill = 0;
+        if constexpr (TMA_) {
+            // One elected thread issues the tile: a tiled TMA load per (slice, plane), box (EPU ch, 10 w, 18 h, 1 d, 1 n) -> [hp][wp][16 B];
+            // coordinates outside the volume (the halo, slices before 0 / beyond D) are zero-filled by the TMA unit.  Every loader
+            // warp then owns the (slice, plane) pairs w8, w8 + 8, ... (8 % J == 0: its plane j, hence its scale / shift registers,
+            // is fixed) for the in-place norm apply: a lane takes voxels lane, lane + 32, ... of a plane, so the eight lanes of a
+            // 16-byte shared-memory phase touch one 128-byte line.
+            const int w8 = t >> 5;
+            const int j = w8 % J;
+            const int npairs = nslices * J;
+            const uint32_t tile_bytes = (uint32_t)(npairs * HP * WP * 16);
+            for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+                int n, d0, h0, w0;
+                item_coords(p, item, n, d0, h0, w0);
+                for (int c = c_begin; c < c_end; ++c, ++fill) {
+                    const int buf = fill & 1;
+                    uint8_t* abuf = smA + buf * p.a_bytes;
+                    if (w8 == 0) mbar_wait(&a_empty[buf], ((fill >> 1) & 1) ^ 1);      // the whole warp waits: no divergent spinning
+                    if (t == 0) {
+                        mbar_arrive_expect_tx(&t_full[buf], tile_bytes);
+                        const uint32_t bar32 = smem_u32(&t_full[buf]);
+                        for (int s = 0; s < nslices; ++s)
+#pragma unroll
+                            for (int jj = 0; jj < J; ++jj)
+                                asm volatile(
+                                    "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::
+                                        "r"(smem_u32(abuf + (s * J + jj) * PL)),
+                                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c * p.CC + jj * EPU), "r"(w0 - 1), "r"(h0 - 1), "r"(d0 + s - pd), "r"(n), "r"(bar32)
+                                    : "memory");
+                    }
+                    __syncwarp();
+                    mbar_wait(&t_full[buf], (fill >> 1) & 1);
+                    if (p.in_ss) {
+                        float sc[EPU], sh[EPU];
+                        const float* q = p.in_ss + ((size_t)n * p.Cin + c * p.CC + j * EPU) * 2;
+#pragma unroll
+                        for (int e = 0; e < EPU; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
+                        for (int pr = w8; pr < npairs; pr += NLOAD / 32) {
+                            const int gd = d0 + pr / J - pd;
+                            if (gd < 0 || gd >= p.D) continue;
+                            uint8_t* pl = abuf + pr * PL;
+#pragma unroll
+                            for (int i = 0; i < (HP * WP + 31) / 32; ++i) {
+                                const int v = lane + 32 * i;
+                                const int hp_ = v / WP, wp_ = v % WP;
+                                const int gh = h0 + hp_ - 1, gw = w0 + wp_ - 1;
+                                if (v < HP * WP && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
+                                    uint4* qd = reinterpret_cast<uint4*>(pl + v * 16);
+                                    uint4 val = *qd;
+                                    affine_unit<TA>(val, sc, sh);
+                                    *qd = val;
+                                }
+                            }
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[buf]);
+                }
+            }
+        } else {
         const int j = t % J;                         // fixed 8-channel group of this thread (128 % J == 0)
         const int units = nslices * HP * WP;         // voxels of the haloed tile per chunk
-        uint32_t fill = 0;
         for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
             int n, d0, h0, w0;
             item_coords(p, item, n, d0, h0, w0);
@@ -193,14 +263,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
 #pragma unroll
                     for (int e = 0; e < EPU; ++e) { sc[e] = q[2 * e]; sh[e] = q[2 * e + 1]; }
                 }
-                uint8_t* dstbase = smA + buf * p.a_bytes + j * PLANE;
+                uint8_t* dstbase = smA + buf * p.a_bytes + j * PL;
                 const TA* xn = reinterpret_cast<const TA*>(p.x) + (size_t)n * p.D * p.H * p.W * p.x_ld + ch0;
-                load_halo_tile_async<HP, WP, TA>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * PLANE, t / J, NLOAD / J, units, d0, h0, w0, pd,
+                load_halo_tile_async<HP, WP, TA>(xn, p.x_ld, sc, sh, p.in_ss != nullptr, dstbase, J * PL, t / J, NLOAD / J, units, d0, h0, w0, pd,
                                p.D, p.H, p.W);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[buf]);
             }
+        }
         }
     } else if (warp == W_WLOAD) {
         // ===================== weight loader =====================
@@ -226,11 +297,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3d_umma_kernel(const ConvUmmaP
         // body is R_*KC_ MMAs whose operand offsets are immediates.
         if (elect_one()) {
             const uint32_t idesc = make_idesc<TA>(128, p.NP);
-            const uint64_t ad = make_desc(0, PLANE, WP * 16), bd = make_desc(0, (uint32_t)(p.NP * 16), 128);
+            const uint64_t ad = make_desc(0, PL, WP * 16), bd = make_desc(0, (uint32_t)(p.NP * 16), 128);
             const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
             const uint32_t a_lo_base = (uint32_t)(ad & 0xFFFFFFFFu) + (smem_u32(smA) >> 4);
             const uint32_t b_lo_base = (uint32_t)(bd & 0xFFFFFFFFu) + (smem_u32(smB) >> 4);
-            constexpr uint32_t SLAB16 = J * (PLANE / 16), K16 = 2 * (PLANE / 16);
+            constexpr uint32_t SLAB16 = J * (PL / 16), K16 = 2 * (PL / 16);
             const uint32_t np = (uint32_t)p.NP, b_tap16 = (uint32_t)(J * p.NP), bk16 = 2 * np;
             const uint32_t a_bytes16 = (uint32_t)(p.a_bytes >> 4), bstage16 = (uint32_t)(p.b_stage_bytes >> 4);
             uint32_t fill = 0, it = 0;
@@ -522,8 +593,8 @@ struct UmmaShape {
 // ~500 cycles per stage hand-off (barrier probe, commit, fence), so a stage should carry well over 500 cycles of MMAs: three taps
 // per stage whenever >= 3 stages of them fit beside the two activation buffers, else one tap and four stages.
 static void umma_ring(UmmaShape& s, int taps, int kd, int planes_per_slice) {
-    const int fixed = s.NP * 4 * 3 + 16 * 8 + 16 + 27 * 4 + 128;
-    s.a_bytes = (s.R + kd - 1) * planes_per_slice * PLANE;
+    const int fixed = s.NP * 4 * 3 + 18 * 8 + 16 + 27 * 4 + 128;
+    s.a_bytes = (s.R + kd - 1) * planes_per_slice * PLANE_TMA;     // sized for the TMA planes (the cp.async planes are smaller)
     static const int g_env = [] { const char* e = getenv("B200EM_UMMA_G"); return e ? atoi(e) : 0; }();      // bring-up: force taps per stage
     for (int G = (taps % 3 == 0 && g_env != 1) ? 3 : 1; G >= 1; G -= 2) {
         s.G = G;
@@ -906,10 +977,45 @@ static int launch_conv_umma(const void* x, int64_t x_ld, const float* in_scale_s
     long long gx = p.items < sm_count() / (s.nblk * ksplit) ? p.items : sm_count() / (s.nblk * ksplit);
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)s.nblk, (unsigned)ksplit);
-#define B2_UMMA_LAUNCH(R_, KC_)                                                                                             \
-    do {                                                                                                                    \
-        B2_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<TA, TO, R_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM)); \
-        conv3d_umma_kernel<TA, TO, R_, KC_><<<grid, THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p);                             \
+    // tiled tensor map over x: dims (C, W, H, D, N), box (one 16-byte channel unit, 10, 18, 1, 1) -> one TMA load per (slice, plane)
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    p.use_tma = 0;
+    {
+        static const bool tma_env = [] { const char* e = getenv("B200EM_UMMA_TMA"); return !(e && atoi(e) == 0); }();
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static const EncodeFn encode = [] {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+                return (EncodeFn)fn;
+            (void)cudaGetLastError();
+            return (EncodeFn) nullptr;
+        }();
+        if (tma_env && encode) {
+            const cuuint64_t esz = sizeof(TA);
+            const cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+            const cuuint64_t gstr[4] = {(cuuint64_t)x_ld * esz, (cuuint64_t)W * x_ld * esz, (cuuint64_t)H * W * x_ld * esz,
+                                        (cuuint64_t)D * H * W * x_ld * esz};
+            const cuuint32_t box[5] = {(cuuint32_t)EPU, (cuuint32_t)WP, (cuuint32_t)HP, 1, 1};
+            const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            const CUtensorMapDataType dt = F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                               : (std::is_same<TA, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+            const CUresult r = encode(&tmap, dt, 5, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) p.use_tma = 1;
+        }
+    }
+#define B2_UMMA_LAUNCH_(R_, KC_, TMA_)                                                                                             \
+    do {                                                                                                                           \
+        B2_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<TA, TO, R_, KC_, TMA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM)); \
+        conv3d_umma_kernel<TA, TO, R_, KC_, TMA_><<<grid, THREADS, s.smem_bytes, (cudaStream_t)stream>>>(p, tmap);                       \
+    } while (0)
+#define B2_UMMA_LAUNCH(R_, KC_)                                                                                                    \
+    do {                                                                                                                           \
+        if (p.use_tma) B2_UMMA_LAUNCH_(R_, KC_, true);                                                                             \
+        else B2_UMMA_LAUNCH_(R_, KC_, false);                                                                                      \
     } while (0)
     const int kc = s.CC / (2 * EPU);            // MMA K steps per chunk (two 16-byte planes each)
     if (s.R == 4 && kc == 2) B2_UMMA_LAUNCH(4, 2);
@@ -918,6 +1024,7 @@ static int launch_conv_umma(const void* x, int64_t x_ld, const float* in_scale_s
     else if (s.R == 2) B2_UMMA_LAUNCH(2, 1);
     else if (kc == 2) B2_UMMA_LAUNCH(1, 2);
     else B2_UMMA_LAUNCH(1, 1);
+#undef B2_UMMA_LAUNCH_
 #undef B2_UMMA_LAUNCH
     B2_LAUNCH_CHECK();
     return 0;
