@@ -1,6 +1,8 @@
 // Network head: out_conv (1x1x1 nn.Conv3d, unet.py:638,202-203) + final activation (unet.py:162-172,204-205),
 // fused with the NDHWC -> NCDHW layout change, forward and backward.  HBM-bound (AI ~ 2-9 FLOP/B):
 // one pass over x, one coalesced write of the fp32 NCDHW prediction.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200em {
@@ -425,6 +427,191 @@ head_bwd_mid_kernel(const float* __restrict__ grad_out, const float* __restrict_
     }
 }
 
+// ---- mid-size head backward, shared-memory staged (Cin = 32: the affinity head of cfg3) ------------------------------------------
+// The register form above keeps 8 warps per SM (252 registers) with ~1.3 KB of loads in flight per warp: ~10 KB per SM against the
+// ~30 KB that HBM's bandwidth x latency product asks for -- it runs at 1.1 TB/s whatever its instruction mix (packed FMAs, a
+// shared-memory filter and a software-pipelined variant all measured the same or worse).  Here the operands of a 128-voxel tile
+// (12 + 12 planar rows of the output gradient / output, the x rows) are staged by cp.async through a three-deep shared-memory
+// ring, so ~40 KB per block are in flight independently of the registers, and the arithmetic reads shared memory: the dW
+// partials (96 registers) stay thread-private as before, the FMAs are packed (fma.rn.f32x2 over channel pairs), the filter is
+// read as 16-byte broadcast loads and the activation derivative is branch-free.
+constexpr int HBT_TV = 128, HBT_NST = 3, HBT_CIN = 32;
+template <typename T, int COUT> struct HbtSmem {
+    static constexpr int JP = (COUT + 1) / 2;
+    static constexpr int go_bytes = 2 * COUT * HBT_TV * 4, x_bytes = HBT_TV * HBT_CIN * (int)sizeof(T);
+    static constexpr int stage_bytes = go_bytes + x_bytes;
+    static constexpr int WSL = 4 * JP + 1;           // float4 per 8-channel slice of the filter, +1: the four slices of a quarter-warp read distinct banks
+    static constexpr int w_bytes = (HBT_CIN / 8) * WSL * 16, red_bytes = (COUT * HBT_CIN + COUT) * 4;
+    static constexpr int total = HBT_NST * stage_bytes + w_bytes + red_bytes;
+};
+
+template <typename T, int COUT>
+__global__ void __launch_bounds__(128, 2)
+head_bwd_mid_tiled_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, const T* __restrict__ x, int64_t x_ld,
+                          const float* __restrict__ w, T* __restrict__ dx, int64_t dx_ld, float* __restrict__ dw, float* __restrict__ db,
+                          int64_t S, int act, int relu_mask, int N, float* __restrict__ absmax) {
+    using L = HbtSmem<T, COUT>;
+    constexpr int JP = L::JP, TV = HBT_TV, Cin = HBT_CIN;
+    constexpr int XCH = Cin * (int)sizeof(T) / 16;     // 16-byte chunks of one x row
+    extern __shared__ __align__(16) uint8_t hb_smem[];
+    float4* w_s = reinterpret_cast<float4*>(hb_smem + HBT_NST * L::stage_bytes);   // [channel pair][output pair] (w[2jp][2cp..], w[2jp+1][2cp..])
+    float* red = reinterpret_cast<float*>(hb_smem + HBT_NST * L::stage_bytes + L::w_bytes);
+    for (int i = threadIdx.x; i < (Cin / 2) * JP; i += blockDim.x) {
+        const int cp = i / JP, j0 = 2 * (i % JP), j1 = j0 + 1;
+        w_s[(cp / 4) * L::WSL + (cp % 4) * JP + i % JP] = make_float4(w[j0 * Cin + 2 * cp], w[j0 * Cin + 2 * cp + 1], j1 < COUT ? w[j1 * Cin + 2 * cp] : 0.f,
+                                                                      j1 < COUT ? w[j1 * Cin + 2 * cp + 1] : 0.f);
+    }
+    for (int i = threadIdx.x; i < COUT * Cin + COUT; i += blockDim.x) red[i] = 0.f;
+    const int tps = (int)((S + TV - 1) / TV);           // tiles per sample: a tile never straddles two samples
+    const int ntiles = N * tps;
+    const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(hb_smem));
+
+    auto issue = [&](int tile, int stage) {
+        if (tile < ntiles) {
+            const int n = tile / tps;
+            const int64_t s0 = (int64_t)(tile % tps) * TV;
+            const int vcnt = (int)min((int64_t)TV, S - s0);                          // multiple of 4 (S % 4 == 0)
+            const uint32_t sb = smem0 + stage * L::stage_bytes;
+            for (int i = threadIdx.x; i < 2 * COUT * (TV / 4); i += 128) {           // planar rows: [array][j][TV] fp32
+                const int ch = i % (TV / 4), row = i / (TV / 4), j = row % COUT;
+                const float* src = (row < COUT ? grad_out : out) + ((size_t)n * COUT + j) * S + s0 + 4 * ch;
+                const bool in = 4 * ch < vcnt;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sb + (uint32_t)(row * TV + 4 * ch) * 4), "l"(in ? src : grad_out),
+                             "r"(in ? 16 : 0)
+                             : "memory");
+            }
+            const T* xt = x + ((size_t)n * S + s0) * x_ld;
+            for (int i = threadIdx.x; i < TV * XCH; i += 128) {                      // x rows: [voxel][Cin]
+                const int v = i / XCH, q = i % XCH;
+                const bool in = v < vcnt;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sb + (uint32_t)(L::go_bytes + i * 16)),
+                             "l"(in ? reinterpret_cast<const uint8_t*>(xt + (size_t)v * x_ld) + q * 16 : reinterpret_cast<const uint8_t*>(x)),
+                             "r"(in ? 16 : 0)
+                             : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = lane & 3, vl = lane >> 2;            // 8-channel slice of x, voxel within the warp
+    const float a0 = (act == B200EM_ACT_SIGMOID) ? 0.f : 1.f, a1 = (act == B200EM_ACT_SIGMOID) ? 1.f : 0.f,
+                a2 = (act == B200EM_ACT_SIGMOID || act == B200EM_ACT_TANH) ? -1.f : 0.f;
+    const bool step = act == B200EM_ACT_RELU;
+    float2 aw[COUT][4];
+    float ab[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+        ab[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) aw[j][c] = make_float2(0.f, 0.f);
+    }
+    unsigned am = 0;
+    const float4* wsl = w_s + sl * L::WSL;
+#pragma unroll
+    for (int k = 0; k < HBT_NST - 1; ++k) issue(blockIdx.x + k * gridDim.x, k);
+    int stage = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        { const int ps = stage + HBT_NST - 1; issue(tile + (HBT_NST - 1) * gridDim.x, ps >= HBT_NST ? ps - HBT_NST : ps); }
+        asm volatile("cp.async.wait_group %0;" ::"n"(HBT_NST - 1) : "memory");
+        __syncthreads();
+        const int n = tile / tps;
+        const int64_t s0 = (int64_t)(tile % tps) * TV;
+        const int vcnt = (int)min((int64_t)TV, S - s0);
+        const uint8_t* sb = hb_smem + stage * L::stage_bytes;
+        const float* g_s = reinterpret_cast<const float*>(sb);
+        const float* o_s = g_s + COUT * TV;
+#pragma unroll 1
+        for (int pass = 0; pass < TV / 64; ++pass) {
+            // two voxels per thread and pass (v, v + 8): one filter read from shared memory serves both
+            const int vb = pass * 64 + warp * 16;
+            if (vb >= vcnt) break;                       // warp-uniform; zero-filled voxels beyond vcnt contribute nothing and are not stored
+            float dz[2][2 * JP], xv[2][8], r[2][8];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int v = vb + 8 * u + vl;
+#pragma unroll
+                for (int j = 0; j < COUT; ++j) {
+                    const float o_ = o_s[j * TV + v];
+                    float d = fmaf(o_, fmaf(a2, o_, a1), a0);
+                    d = step ? (o_ > 0.f ? 1.f : 0.f) : d;
+                    dz[u][j] = g_s[j * TV + v] * d;
+                    ab[j] += dz[u][j];
+                }
+                if (COUT & 1) dz[u][2 * JP - 1] = 0.f;
+                const T* xs = reinterpret_cast<const T*>(sb + L::go_bytes) + v * Cin + sl * 8;
+                if constexpr (sizeof(T) == 2) {
+                    Vec<T, 8>::load(xs, xv[u]);
+                } else {
+                    Vec<T, 4>::load(xs, *reinterpret_cast<float(*)[4]>(xv[u]));
+                    Vec<T, 4>::load(xs + 4, *reinterpret_cast<float(*)[4]>(xv[u] + 4));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float2 x2[2] = {make_float2(xv[0][2 * c], xv[0][2 * c + 1]), make_float2(xv[1][2 * c], xv[1][2 * c + 1])};
+                float2 g[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                for (int jp = 0; jp < JP; ++jp) {
+                    const float4 w4 = wsl[c * JP + jp];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float2 d0 = make_float2(dz[u][2 * jp], dz[u][2 * jp]), d1 = make_float2(dz[u][2 * jp + 1], dz[u][2 * jp + 1]);
+                        g[u] = __ffma2_rn(make_float2(w4.x, w4.y), d0, g[u]);
+                        aw[2 * jp][c] = __ffma2_rn(d0, x2[u], aw[2 * jp][c]);
+                        if (2 * jp + 1 < COUT) {
+                            g[u] = __ffma2_rn(make_float2(w4.z, w4.w), d1, g[u]);
+                            aw[2 * jp + 1][c] = __ffma2_rn(d1, x2[u], aw[2 * jp + 1][c]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    r[u][2 * c] = (relu_mask && !(x2[u].x > 0.f)) ? 0.f : g[u].x;
+                    r[u][2 * c + 1] = (relu_mask && !(x2[u].y > 0.f)) ? 0.f : g[u].y;
+                    am = absmax_acc(am, r[u][2 * c]);
+                    am = absmax_acc(am, r[u][2 * c + 1]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int v = vb + 8 * u + vl;
+                if (dx && v < vcnt) {
+                    T* dp = dx + ((size_t)n * S + s0 + v) * dx_ld + sl * 8;
+                    if constexpr (sizeof(T) == 2) {
+                        Vec<T, 8>::store(dp, r[u]);
+                    } else {
+                        Vec<T, 4>::store(dp, *reinterpret_cast<float(*)[4]>(r[u]));
+                        Vec<T, 4>::store(dp + 4, *reinterpret_cast<float(*)[4]>(r[u] + 4));
+                    }
+                }
+            }
+        }
+        __syncthreads();                                 // the stage is free for the load issued by the next iteration
+        if (++stage == HBT_NST) stage = 0;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    absmax_flush(am, absmax);
+    // reduce over the lanes that share a slice (the voxel bits of the lane index); the bias gradient is taken from slice 0's lanes
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float a = (c & 1) ? aw[j][c >> 1].y : aw[j][c >> 1].x;
+            for (int o = 16; o >= 4; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (vl == 0) atomicAdd(&red[j * Cin + sl * 8 + c], a);
+        }
+        float b = ab[j];
+        for (int o = 16; o >= 4; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) atomicAdd(&red[COUT * Cin + j], b);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * Cin + COUT; i += blockDim.x) {
+        if (i < COUT * Cin) atomicAdd(dw + i, red[i]);
+        else if (db) atomicAdd(db + (i - COUT * Cin), red[i]);
+    }
+}
+
 template <typename T>
 static bool head_mid_ok(const void* x, int64_t x_ld, const void* dx, int64_t dx_ld, int Cin, int Cout) {
     constexpr int V = FullVec<T>::value;
@@ -517,8 +704,27 @@ static void launch_head_fwd_mid(int64_t blocks, cudaStream_t st, const void* x, 
 
 template <typename T>
 static void launch_head_bwd_mid(cudaStream_t st, const float* grad_out, const float* out, const void* x, int64_t x_ld, const float* w, void* dx,
-                                int64_t dx_ld, float* dw, float* db, int64_t S, int Cin, int Cout, int act, int relu_mask, int64_t total,
+                                int64_t dx_ld, float* dw, float* db, int N, int64_t S, int Cin, int Cout, int act, int relu_mask, int64_t total,
                                 float* absmax) {
+    // shared-memory staged form: 32 input channels, planar rows that can be copied in 16-byte pieces
+    static const bool tiled_env = [] { const char* e = getenv("B200EM_HEAD_TILED"); return !(e && atoi(e) == 0); }();
+    if (tiled_env && Cin == HBT_CIN && S % 4 == 0 && aligned16(grad_out) && aligned16(out) && (N * ((S + HBT_TV - 1) / HBT_TV)) < (1LL << 31)) {
+        const long long ntiles = (long long)N * ((S + HBT_TV - 1) / HBT_TV);
+        const unsigned bl = (unsigned)(ntiles < 2LL * sm_count() ? ntiles : 2LL * sm_count());
+#define B2_HEAD_BWD_TILED(CO)                                                                                                              \
+    do {                                                                                                                                   \
+        cudaFuncSetAttribute(head_bwd_mid_tiled_kernel<T, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, HbtSmem<T, CO>::total);         \
+        head_bwd_mid_tiled_kernel<T, CO><<<bl, 128, HbtSmem<T, CO>::total, st>>>(grad_out, out, (const T*)x, x_ld, w, (T*)dx, dx_ld, dw, db, S, \
+                                                                                  act, relu_mask, N, absmax);                             \
+    } while (0)
+        if (Cout == 12) B2_HEAD_BWD_TILED(12);
+        else if (Cout == 8) B2_HEAD_BWD_TILED(8);
+        else if (Cout == 6) B2_HEAD_BWD_TILED(6);
+        else if (Cout == 4) B2_HEAD_BWD_TILED(4);
+        else B2_HEAD_BWD_TILED(3);
+#undef B2_HEAD_BWD_TILED
+        return;
+    }
     const unsigned bl = (unsigned)sm_count() * (Cout > 8 ? 2 : 3);      // resident blocks of 128 threads per SM, grid-stride
 #define B2_HEAD_BWD_MID(CO) \
     head_bwd_mid_kernel<T, CO><<<bl, 128, 0, st>>>(grad_out, out, (const T*)x, x_ld, w, (T*)dx, dx_ld, dw, db, S, act, relu_mask, total, Cin, absmax)
@@ -572,7 +778,7 @@ int b200em_head_bwd(const float* grad_out, const float* out, const void* x, int6
         bool done = false;
         B2_DISPATCH_DTYPE(dtype, T, {
             if (head_mid_ok<T>(x, x_ld, dx, dx_ld, Cin, Cout)) {
-                launch_head_bwd_mid<T>((cudaStream_t)stream, grad_out, out, x, x_ld, w, dx, dx_ld, dw, db, S, Cin, Cout, act, relu_mask, total, absmax);
+                launch_head_bwd_mid<T>((cudaStream_t)stream, grad_out, out, x, x_ld, w, dx, dx_ld, dw, db, N, S, Cin, Cout, act, relu_mask, total, absmax);
                 done = true;
             } else if (head_bwd_small_ok<T>(x, x_ld, dx, dx_ld, Cin, Cout)) {
                 launch_head_bwd_small<T>((unsigned)(blocks / 4 * 4 > 0 ? blocks / 4 * 4 : 4), (cudaStream_t)stream, grad_out, out, x, x_ld, w, dx, dx_ld, dw, db, S, Cin, Cout,
