@@ -427,6 +427,92 @@ head_bwd_mid_kernel(const float* __restrict__ grad_out, const float* __restrict_
     }
 }
 
+constexpr int HBT_TV = 128, HBT_NST = 3, HBT_CIN = 32;      // staged head kernels: voxels per tile, ring depth, input channels
+
+// ---- mid-size head forward, shared-memory staged (Cin = 32) -------------------------------------------------------------------------
+// The group form above reads every x row once per output-channel group through L1 with 64-byte lane strides (16 cache lines per
+// warp load): ncu shows it bound by L1 throughput (79 %) at 1.7 TB/s.  Here the x rows of a 128-voxel tile arrive ONCE by cp.async
+// (three-deep ring, rows padded to 80 / 144 bytes so that a quarter-warp's 16-byte reads hit distinct banks), a thread owns a
+// voxel and all COUT outputs, the filter is read as 16-byte broadcasts and the FMAs are packed over channel pairs.
+template <typename T> struct HftSmem {
+    static constexpr int row_bytes = HBT_CIN * (int)sizeof(T) + 16;
+    static constexpr int stage_bytes = HBT_TV * row_bytes;
+};
+
+template <typename T, int COUT>
+__global__ void __launch_bounds__(128, 4)
+head_fwd_mid_tiled_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ w, const float* __restrict__ bias,
+                          float* __restrict__ out, int64_t S, int act, int N) {
+    using L = HftSmem<T>;
+    constexpr int TV = HBT_TV, Cin = HBT_CIN, XCH = Cin * (int)sizeof(T) / 16;
+    extern __shared__ __align__(16) uint8_t hf_smem[];
+    float4* w_s = reinterpret_cast<float4*>(hf_smem + HBT_NST * L::stage_bytes);     // [j][Cin / 4]
+    for (int i = threadIdx.x; i < COUT * Cin / 4; i += blockDim.x) w_s[i] = reinterpret_cast<const float4*>(w)[i];
+    const int tps = (int)((S + TV - 1) / TV);
+    const int ntiles = N * tps;
+    const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(hf_smem));
+    auto issue = [&](int tile, int stage) {
+        if (tile < ntiles) {
+            const int n = tile / tps;
+            const int64_t s0 = (int64_t)(tile % tps) * TV;
+            const int vcnt = (int)min((int64_t)TV, S - s0);
+            const T* xt = x + ((size_t)n * S + s0) * x_ld;
+            const uint32_t sb = smem0 + stage * L::stage_bytes;
+            for (int i = threadIdx.x; i < TV * XCH; i += 128) {
+                const int v = i / XCH, q = i % XCH;
+                const bool in = v < vcnt;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sb + (uint32_t)(v * L::row_bytes + q * 16)),
+                             "l"(in ? reinterpret_cast<const uint8_t*>(xt + (size_t)v * x_ld) + q * 16 : reinterpret_cast<const uint8_t*>(x)),
+                             "r"(in ? 16 : 0)
+                             : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float br[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) br[j] = bias ? bias[j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < HBT_NST - 1; ++k) issue(blockIdx.x + k * gridDim.x, k);
+    int stage = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        { const int ps = stage + HBT_NST - 1; issue(tile + (HBT_NST - 1) * gridDim.x, ps >= HBT_NST ? ps - HBT_NST : ps); }
+        asm volatile("cp.async.wait_group %0;" ::"n"(HBT_NST - 1) : "memory");
+        __syncthreads();
+        const int n = tile / tps;
+        const int64_t s0 = (int64_t)(tile % tps) * TV;
+        const int vcnt = (int)min((int64_t)TV, S - s0);
+        const int v = threadIdx.x;
+        float2 x2[Cin / 2];
+        {
+            const T* xs = reinterpret_cast<const T*>(hf_smem + stage * L::stage_bytes + v * L::row_bytes);
+            constexpr int V = FullVec<T>::value;
+#pragma unroll
+            for (int c = 0; c < Cin; c += V) {
+                float t[V];
+                Vec<T, V>::load(xs + c, t);
+#pragma unroll
+                for (int e = 0; e < V; e += 2) x2[(c + e) / 2] = make_float2(t[e], t[e + 1]);
+            }
+        }
+        float* op = out + (size_t)n * COUT * S + s0 + v;
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) {
+            float2 a = make_float2(br[j], 0.f);
+#pragma unroll
+            for (int q = 0; q < Cin / 4; ++q) {
+                const float4 w4 = w_s[j * (Cin / 4) + q];
+                a = __ffma2_rn(make_float2(w4.x, w4.y), x2[2 * q], a);
+                a = __ffma2_rn(make_float2(w4.z, w4.w), x2[2 * q + 1], a);
+            }
+            if (v < vcnt) op[(size_t)j * S] = act_fwd(a.x + a.y, act);
+        }
+        __syncthreads();
+        if (++stage == HBT_NST) stage = 0;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // ---- mid-size head backward, shared-memory staged (Cin = 32: the affinity head of cfg3) ------------------------------------------
 // The register form above keeps 8 warps per SM (252 registers) with ~1.3 KB of loads in flight per warp: ~10 KB per SM against the
 // ~30 KB that HBM's bandwidth x latency product asks for -- it runs at 1.1 TB/s whatever its instruction mix (packed FMAs, a
@@ -435,7 +521,6 @@ head_bwd_mid_kernel(const float* __restrict__ grad_out, const float* __restrict_
 // ring, so ~40 KB per block are in flight independently of the registers, and the arithmetic reads shared memory: the dW
 // partials (96 registers) stay thread-private as before, the FMAs are packed (fma.rn.f32x2 over channel pairs), the filter is
 // read as 16-byte broadcast loads and the activation derivative is branch-free.
-constexpr int HBT_TV = 128, HBT_NST = 3, HBT_CIN = 32;
 template <typename T, int COUT> struct HbtSmem {
     static constexpr int JP = (COUT + 1) / 2;
     static constexpr int go_bytes = 2 * COUT * HBT_TV * 4, x_bytes = HBT_TV * HBT_CIN * (int)sizeof(T);
@@ -686,6 +771,21 @@ static void launch_head_bwd_small(unsigned blocks, cudaStream_t st, const float*
 template <typename T>
 static void launch_head_fwd_mid(int64_t blocks, cudaStream_t st, const void* x, int64_t x_ld, const float* w, const float* bias, float* out,
                                 int64_t S, int Cin, int Cout, int act, int64_t total) {
+    static const bool tiled_env = [] { const char* e = getenv("B200EM_HEAD_TILED"); return !(e && atoi(e) == 0); }();
+    // (measured on (2, 64, 256, 256) x 32 channels, bf16: 12 outputs 548 -> 422 us; 8 outputs 298 vs 307, 4 outputs 155 vs 200: the group form keeps those)
+    if (tiled_env && Cin == HBT_CIN && Cout > 8 && aligned16(w) && total / S * ((S + HBT_TV - 1) / HBT_TV) < (1LL << 31)) {
+        const int N = (int)(total / S);
+        const long long ntiles = (long long)N * ((S + HBT_TV - 1) / HBT_TV);
+        const unsigned blt = (unsigned)(ntiles < 4LL * sm_count() ? ntiles : 4LL * sm_count());
+#define B2_HEAD_FWD_TILED(CO)                                                                                                         \
+    do {                                                                                                                              \
+        const int smem = HBT_NST * HftSmem<T>::stage_bytes + CO * HBT_CIN * 4;                                                         \
+        cudaFuncSetAttribute(head_fwd_mid_tiled_kernel<T, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                     \
+        head_fwd_mid_tiled_kernel<T, CO><<<blt, 128, smem, st>>>((const T*)x, x_ld, w, bias, out, S, act, N);                          \
+    } while (0)
+        if (Cout == 12) { B2_HEAD_FWD_TILED(12); return; }
+#undef B2_HEAD_FWD_TILED
+    }
     // warps = voxel groups x output-channel groups of 3 (or 4): a block count divisible by 3 and 4 keeps a warp's group fixed
     unsigned bl = (unsigned)(((blocks * (Cout % 3 == 0 ? Cout / 3 : Cout / 4)) + 11) / 12 * 12);
     const unsigned cap_ = (unsigned)sm_count() * 16 / 12 * 12;
