@@ -16,6 +16,9 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control no
 python scripts/summarize_launches.py $out/${tag}_launches_train_step.csv > $out/${tag}_launches_train_step_summary.txt
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches_predict.csv python scripts/profile_predict.py > $out/${tag}_prof_predict.log 2>&1
 python scripts/summarize_launches.py $out/${tag}_launches_predict.csv > $out/${tag}_launches_predict_summary.txt
+B200EM_CONFIG=cfg3 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches_cfg3.csv python scripts/profile_step.py > $out/${tag}_prof_cfg3.log 2>&1
+python scripts/summarize_launches.py $out/${tag}_launches_cfg3.csv > $out/${tag}_launches_cfg3_summary.txt
+python scripts/bench_head.py > $out/${tag}_bench_head.txt 2>&1
 B200EM_CONFIG=cfg4 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches_cfg4.csv python scripts/profile_step.py > $out/${tag}_prof_cfg4.log 2>&1
 python scripts/summarize_launches.py $out/${tag}_launches_cfg4.csv > $out/${tag}_launches_cfg4_summary.txt
 ncu --set full --import-source on --clock-control none --profile-from-start off -f -o $out/${tag}_kernels python scripts/profile_kernels.py > $out/${tag}_prof_kernels.log 2>&1

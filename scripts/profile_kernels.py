@@ -13,7 +13,7 @@ from torch_em_b200.backend import default_backend
 dev = "cuda:0"
 B = default_backend()
 N, S = 4, 128
-which = set((os.environ.get("KERNELS") or "ds_fwd,ds_dgrad,cs_wgrad,plain_fwd,plain_deep,h16_fwd,h16_dgrad,h16_wgrad,tf32_fwd,upsample_fwd,upsample_bwd,maxpool_bwd,"
+which = set((os.environ.get("KERNELS") or "ds_fwd,ds_dgrad,cs_wgrad,plain_fwd,plain_dgrad,plain_deep,head_mid_fwd,head_mid_bwd,h16_fwd,h16_dgrad,h16_wgrad,tf32_fwd,upsample_fwd,upsample_bwd,maxpool_bwd,"
                                           "norm_bwd_apply,cvt_f16,pack").split(","))
 torch.manual_seed(0)
 x = torch.randn((N, S, S, S, 32), device=dev).bfloat16()
@@ -60,7 +60,22 @@ ps_big = B.pack_set({"big": torch.randn((512, 512, 3, 3, 3), device=dev) * 0.01}
 ssf = torch.ones((1, 128, 2), device=dev)
 sf = torch.zeros((1, 128, 2), device=dev)
 
+dz2 = torch.randn_like(x2)
+g2 = torch.empty_like(x2)
+# cfg3's affinity head: 32 -> 12 channels on (2, 64, 256, 256)
+xh = torch.randn((2, 64, 256, 256, 32), device=dev).bfloat16()
+wh = torch.randn((12, 32, 1, 1, 1), device=dev) * 0.2
+bh = torch.zeros(12, device=dev)
+oh = torch.empty((2, 12, 64, 256, 256), device=dev)
+gh = torch.randn_like(oh)
+dxh = torch.empty_like(xh)
+dwh = torch.zeros((12, 32), device=dev)
+dbh = torch.zeros(12, device=dev)
+
 runs = {
+    "plain_dgrad": lambda: B.conv(dz2, None, pk2, None, g2, s2, (3, 3, 3), False, True, dot_x=x2),
+    "head_mid_fwd": lambda: B.head_fwd(xh, wh, bh, oh, "Sigmoid"),
+    "head_mid_bwd": lambda: B.head_bwd(gh, oh, xh, wh, dxh, dwh, dbh, "Sigmoid", True),
     "ds_fwd": lambda: B.conv(x, ss, pk, b, y, sums, (3, 3, 3), True, False),
     "ds_dgrad": lambda: B.conv(dz, None, pk, None, g, sums, (3, 3, 3), False, True, dot_x=x),
     "cs_wgrad": lambda: B.wgrad(x, ss, dz, dw, db, (3, 3, 3)),
