@@ -740,8 +740,14 @@ __device__ __forceinline__ void f1_build_slab(const ConvFirstParams& p, int n, i
     __syncwarp();                                     // scratch is reused by this warp's next slab
 }
 
-template <int CO, bool F32 = false>
-__global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvFirstParams p) {
+// EG = epilogue warp groups: with EG = 2 the warps w and w + 4 share a TMEM lane quarter and split the CO output columns.  One
+// warp's chain of ~330 dependent instructions per slab (TMEM load, bias, ReLU, rounding, statistics, store) is what bounds the
+// kernel with EG = 1 (ncu source page: the loader warps sit in their a_empty wait); two groups halve it, the eight loader warps stay.
+template <int CO, bool F32 = false, int EG = 1, int NLW = F1_NLW>
+__global__ void __launch_bounds__(EG * 128 + NLW * 32 + 32, 1) conv3d_first_kernel(const ConvFirstParams p) {
+    // (EG = 2: 17 warps put five on one SM sub-partition = 96 registers per thread and 32 bytes of spills; seven loader warps instead
+    // -- 128 registers, no spills -- measured 412 us against 300: the loaders' round robin wants NLW == the ring depth)
+    constexpr int W_LOAD0 = 4 * EG, W_MMA = 4 * EG + NLW;
     using TY = typename std::conditional<F32, float, __nv_bfloat16>::type;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int NA = (512 / CO) < DS_MAX_NA ? (512 / CO) : DS_MAX_NA;
@@ -764,16 +770,16 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
         for (int i = 0; i < NA; ++i) { mbar_init(&acc_full[i], 1); flag_init(&acc_empty[i]); }    // acc_empty: plain completion counters
         fence_mbar_init();
     }
-    if (warp == F1_W_MMA) tmem_alloc(s_tmem, 512);
+    if (warp == W_MMA) tmem_alloc(s_tmem, 512);
     // weight operand straight from the fp32 parameter: B[k-group j][co][8 taps], taps >= 27 zero
-    for (int i = threadIdx.x; i < 4 * CO * 8; i += F1_THREADS) {
+    for (int i = threadIdx.x; i < 4 * CO * 8; i += blockDim.x) {
         const int e = i % 8, co = (i / 8) % CO, j = i / (8 * CO);
         const int k = j * 8 + e;
         const float wv = k < 27 ? p.w[co * 27 + k] : 0.f;
         if constexpr (F32) reinterpret_cast<__half*>(smB)[i] = __float2half_rn(wv);
         else reinterpret_cast<__nv_bfloat16*>(smB)[i] = __float2bfloat16_rn(wv);
     }
-    for (int i = threadIdx.x; i < CO; i += F1_THREADS) {
+    for (int i = threadIdx.x; i < CO; i += blockDim.x) {
         s_bias[i] = p.bias ? p.bias[i] : 0.f;
         s_sums[2 * i] = 0.f;
         s_sums[2 * i + 1] = 0.f;
@@ -784,9 +790,9 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp >= 4 && warp < F1_W_MMA) {
+    if (warp >= W_LOAD0 && warp < W_MMA) {
         // ===================== loaders: warp w8 builds every 8th slab =====================
-        const int w8 = warp - 4;
+        const int w8 = warp - W_LOAD0;
         __nv_bfloat16* scr = s_scr + w8 * F1_SCR;
         uint32_t slot = 0, phase = 1, lap = 1;
         int owner = 0;
@@ -798,7 +804,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
                 const uint32_t my_slot = slot, my_phase = phase, my_lap = lap;
                 const bool mine = owner == w8;
                 if (++slot == F1_NS) { slot = 0; phase ^= 1; ++lap; }
-                if (++owner == F1_NLW) owner = 0;
+                if (++owner == NLW) owner = 0;
                 if (!mine) continue;
                 mbar_wait(&a_empty[my_slot], my_phase);
                 f1_build_slab<F32>(p, n, d0 + od, h0, w0, sc, sh, scr, smA + my_slot * F1_ASTAGE, lane);
@@ -807,7 +813,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
                 if (lane == 0) flag_store(&a_full[my_slot], my_lap);
             }
         }
-    } else if (warp == F1_W_MMA) {
+    } else if (warp == W_MMA) {
         // ===================== MMA issuer: two K = 16 MMAs per slab =====================
         if (elect_one()) {
             constexpr uint32_t idesc = F32 ? make_idesc_f16(128, CO) : make_idesc_bf16(128, CO);
@@ -819,7 +825,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
             int r = 0;
             for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
                 for (int od = 0; od < DR; ++od) {
-                    if (started >= (uint32_t)NA) counter_wait_ge(&acc_empty[r], 4u * (started / (uint32_t)NA));
+                    if (started >= (uint32_t)NA) counter_wait_ge(&acc_empty[r], 4u * EG * (started / (uint32_t)NA));
                     ++started;
                     flag_wait_eq(&a_full[slot], lap);
                     tc_fence_after();
@@ -835,13 +841,14 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
             }
         }
     } else {
-        // ===================== epilogue (warps 0-3) =====================
-        const int row = warp * 32 + lane;
+        // ===================== epilogue (warps 0 .. 4 * EG - 1) =====================
+        const int wq = warp & 3, grp = warp >> 2;     // TMEM lane quarter of the warp, column group
+        const int row = wq * 32 + lane;
         const int hl = row / DS_TW, wl = row % DS_TW;
-        constexpr bool kAcc = CO <= 32;
-        constexpr int NAcc = kAcc ? CO : 1;
-        constexpr int CPT = CO;                       // one column group: every epilogue thread owns all CO columns
-        const int col0 = 0, grp = 0;
+        constexpr int CPT = CO / EG;                  // columns per epilogue thread
+        constexpr bool kAcc = CPT <= 32 && CO <= 32;
+        constexpr int NAcc = kAcc ? CPT : 1;
+        const int col0 = grp * CPT;
         float acc_s[NAcc], acc_q[NAcc];
 #pragma unroll
         for (int i = 0; i < NAcc; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
@@ -861,9 +868,9 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
                 const int gd = d0 + od;
                 const bool valid = valid_hw && gd < p.D;
                 TY* yp = reinterpret_cast<TY*>(p.y) + (vox0 + (size_t)(gd < p.D ? od : 0) * hw) * p.y_ld;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(r * CO);
-                if constexpr (CO == 16) {
-                    ds_epilogue_block<16, true, TY>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
+                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(r * CO + col0);
+                if constexpr (CPT == 16) {
+                    ds_epilogue_block<16, true, TY>(taddr, s_bias + col0, p.relu, valid, yp + col0, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
                 } else if constexpr (CO == 32) {
                     ds_epilogue_block<16, true, TY>(taddr, s_bias, p.relu, valid, yp, nullptr, false, acc_s, acc_q, s_sums, ws, lane);
                     ds_epilogue_block<16, true, TY>(taddr + 16, s_bias + 16, p.relu, valid, yp + 16, nullptr, false, acc_s + 16, acc_q + 16, s_sums,
@@ -902,7 +909,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv3d_first_kernel(const ConvF
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == F1_W_MMA) {
+    if (warp == W_MMA) {
         __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -1285,6 +1292,13 @@ static int launch_conv_first(const void* x, const float* in_scale_shift, const f
         B2_CUDA(cudaFuncSetAttribute(conv3d_first_kernel<CO_, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM)); \
         conv3d_first_kernel<CO_, F32><<<(unsigned)gx, F1_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);                \
         break;
+    static const bool eg1 = [] { const char* e = getenv("B200EM_FIRST_EG"); return e && atoi(e) == 1; }();
+    if (Cout == 32 && !F32 && !eg1) {         // the bf16 nets of width 32: two epilogue warp groups of 16 columns each (369 -> 300 us on (4, 128^3))
+        B2_CUDA(cudaFuncSetAttribute(conv3d_first_kernel<32, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_SMEM));
+        conv3d_first_kernel<32, false, 2><<<(unsigned)gx, 2 * 128 + F1_NLW * 32 + 32, smem_bytes, (cudaStream_t)stream>>>(p);
+        B2_LAUNCH_CHECK();
+        return 0;
+    }
     switch (Cout) { B2_F1(16) B2_F1(32) B2_F1(48) B2_F1(64) default: set_error("conv3d_first: Cout %d not instantiated", Cout); return 2; }
 #undef B2_F1
     B2_LAUNCH_CHECK();
