@@ -100,15 +100,17 @@ def test_umma_conv_forward_and_dgrad(B, case):
     np.testing.assert_allclose(d.cpu().numpy(), d_ref.numpy(), rtol=1e-2, atol=2e-2 * float(d_ref.abs().max()))
 
 
+@pytest.mark.parametrize("tma", ["1", "0"])
 @pytest.mark.parametrize("ks", ["1", "2", "3", "7"])
 @pytest.mark.parametrize("case", [(1, 4, 8, 8, 128, 256, (3, 3, 3)), (2, 6, 13, 9, 96, 48, (3, 3, 3)), (1, 2, 4, 4, 512, 128, (1, 3, 3)),
                                   (1, 8, 8, 8, 256, 128, (1, 1, 1))])
-def test_plain_conv_split_k(case, ks, monkeypatch):
+def test_plain_conv_split_k(case, ks, tma, monkeypatch):
     """Split-K of the plain kernel (layers with fewer output tiles than SMs): ks CTAs reduce disjoint Cin-chunk ranges of a tile
     through the registered workspace, the last one runs the epilogue (bias, ReLU, statistics / norm-backward reductions).  Forced
     factors incl. ones that do not divide the chunk count; the workspace must be all-zero again afterwards."""
     from torch_em_b200.backend import CudaBackend
     monkeypatch.setenv("B200EM_KSPLIT", ks)
+    monkeypatch.setenv("B200EM_UMMA_TMA", tma)       # "0": the cp.async fallback of the plain kernel's tile loader
     B = CudaBackend(use_ds=False, use_cs=False)
     N, D, H, W, Cin, Cout, k = case
     x = rnd((N, D, H, W, Cin), 1).bfloat16()

@@ -982,7 +982,8 @@ static int launch_conv_umma(const void* x, int64_t x_ld, const float* in_scale_s
     memset(&tmap, 0, sizeof(tmap));
     p.use_tma = 0;
     {
-        static const bool tma_env = [] { const char* e = getenv("B200EM_UMMA_TMA"); return !(e && atoi(e) == 0); }();
+        const char* tma_e = getenv("B200EM_UMMA_TMA");      // "0": the cp.async fallback of the tile loader (read per launch: tests switch it)
+        const bool tma_env = !(tma_e && atoi(tma_e) == 0);
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
         static const EncodeFn encode = [] {
