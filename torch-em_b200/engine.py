@@ -141,12 +141,36 @@ def _groups(norm, c):
     return min(32, c) if norm == "GroupNorm" else c
 
 
+class _ZeroArena:
+    """Zero-initialised fp32 scratch of one pass (the per-(n, c) statistics the kernels accumulate into): views of a few large
+    buffers, each zero-filled by ONE launch, instead of one ``torch.zeros`` -- one fill kernel -- per norm layer (42 per cfg2 step)."""
+    CHUNK = 1 << 16                                      # floats per buffer (256 KB)
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+        self.used = 0
+
+    def zeros(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        need = (n + 63) & ~63                            # 256-byte granules keep every view 16-byte aligned
+        if self.buf is None or self.used + need > self.buf.numel():
+            self.buf = torch.zeros(max(self.CHUNK, need), dtype=torch.float32, device=self.device)
+            self.used = 0
+        v = self.buf[self.used:self.used + n].view(shape)
+        self.used += need
+        return v
+
+
 class _Ctx:
     """Everything the backward pass needs from one forward pass."""
 
     def __init__(self):
         self.blocks = {}
         self.misc = {}
+        self.arena = None
 
 
 def _norm_forward(B, plan, P, bufs, key, sums, S, C, training):
@@ -226,13 +250,13 @@ def _run_block(B, plan, P, bufs, spec: BlockSpec, x_in, sums_in, out, want_out_s
     if norm is not None:
         ss1, mr1, m1 = _norm_forward(B, plan, P, bufs, spec.norm1_key, sums_in, S, c1.cin, training)
     y1 = torch.empty((N, D, H, W, c1.cout), dtype=x_in.dtype, device=dev)
-    sums1 = torch.zeros((N, c1.cout, 2), dtype=torch.float32, device=dev) if norm is not None else None
+    sums1 = ctx.arena.zeros((N, c1.cout, 2)) if norm is not None else None
     aux1 = B.conv(x_in, ss1, packs[c1.key], P[c1.key + ".bias"], y1, sums1, c1.kernel, relu=True, dgrad=False)
     if norm is not None:
         ss2, mr2, m2 = _norm_forward(B, plan, P, bufs, spec.norm2_key, sums1, S, c2.cin, training)
     sums2 = None
     if want_out_sums and norm is not None:
-        sums2 = torch.zeros((N, c2.cout, 2), dtype=torch.float32, device=dev)
+        sums2 = ctx.arena.zeros((N, c2.cout, 2))
     aux2 = B.conv(y1, ss2, packs[c2.key], P[c2.key + ".bias"], out, sums2, c2.kernel, relu=True, dgrad=False)
     rec.update(ss1=ss1, mr1=mr1, y1=y1, ss2=ss2, mr2=mr2, y2=out, aux1=aux1, aux2=aux2, m1=m1, m2=m2)
     ctx.blocks[spec.prefix] = rec
@@ -263,6 +287,7 @@ def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act
     norm = plan.norm
     bufs = bufs or {}
     ctx = _Ctx()
+    ctx.arena = _ZeroArena(dev)
     x = x.contiguous()
     if x.dtype != torch.float32:
         x = x.float()
@@ -272,7 +297,7 @@ def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act
     cur = a
     cur_sums = None
     if norm is not None:
-        cur_sums = torch.zeros((N, Cin, 2), dtype=torch.float32, device=dev)
+        cur_sums = ctx.arena.zeros((N, Cin, 2))
         B.channel_sums(a, cur_sums)
     dims = (D, H, W)
     # spatial dims on the way down (floor division, like nn.MaxPool3d) and on the way up (x factor): they differ from the
@@ -300,14 +325,14 @@ def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act
             sl = _crop_slices(dims, dec_dims[l])
             cat[..., C:].copy_(skip[(slice(None),) + sl])
             if norm is not None:
-                s2 = torch.zeros((N, C, 2), dtype=torch.float32, device=dev)
+                s2 = ctx.arena.zeros((N, C, 2))
                 B.channel_sums(cat[..., C:], s2)
         cats.append(cat)
         skip_sums.append(s2)
         skips_full.append(skip)
         f = plan.scale_factors[l]
         pooled = torch.empty((N,) + enc_dims[l + 1] + (C,), dtype=act_dtype, device=dev)
-        psums = torch.zeros((N, C, 2), dtype=torch.float32, device=dev) if norm is not None else None
+        psums = ctx.arena.zeros((N, C, 2)) if norm is not None else None
         B.maxpool_fwd(skip, pooled, f, psums)
         cur, cur_sums = pooled, psums
     spec = plan.base
@@ -327,7 +352,7 @@ def forward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], x: torch.Tensor, act
         dims = dec_dims[lvl]
         cat = cats[lvl]
         up = cat[..., :C]
-        up_sums = torch.zeros((N, C, 2), dtype=torch.float32, device=dev) if norm is not None else None
+        up_sums = ctx.arena.zeros((N, C, 2)) if norm is not None else None
         B.upsample_fwd(z_low, up, f, up_sums)
         zlows.append((cur, z_low))
         cat_sums = torch.cat([up_sums, skip_sums[lvl]], dim=1) if norm is not None else None
@@ -382,7 +407,7 @@ def _block_backward(B, plan, P, spec: BlockSpec, rec, dz2, need_dx, grads, packs
                 return g
             B.norm_bwd_apply(g, x, None, None, out, relu_mask)
             return out
-        dsums = torch.zeros((N, C, 2), **f32)
+        dsums = grads.arena.zeros((N, C, 2))
         B.conv(dz, None, packs[conv.key], None, g, dsums, conv.kernel, relu=False, dgrad=True, dot_x=x)
         coef = _norm_backward_coef(B, plan, P, norm_key, dsums, mr, mode, S, C, grads)
         if lazy:
@@ -446,6 +471,7 @@ def backward_pass(B, plan: Plan, P: Dict[str, torch.Tensor], ctx: _Ctx, grad_pre
     preds = m["preds"]
     dec_outs = m["dec_outs"]
     dev = dec_outs[-1].device if dec_outs else preds[0].device
+    grads.arena = _ZeroArena(dev)                        # zero-initialised reduction scratch of this backward pass
     if torch.is_tensor(grad_preds):
         grad_preds = [grad_preds]
 
