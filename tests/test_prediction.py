@@ -177,6 +177,23 @@ def test_device_path_transfer_overlap(monkeypatch, overlap, order):
 
 
 @pytest.mark.gpu
+def test_device_path_two_devices():
+    """``gpu_ids=[0, 1]``: block i runs on device i % 2 (prediction.py:249-250), one replica, one thread and one pair of transfer
+    streams per device; the two partial results are merged on the host.  Skipped on a one-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(12)
+    vol = (rng.random((40, 22, 26)) * 100).astype("float32")
+    net, cpu = TinyNet().to("cuda:0"), TinyNet()
+    block_shape, halo = (8, 16, 16), (3, 2, 4)
+    ref = opred.predict_with_halo(vol, np_net(cpu), block_shape, halo, n_out=2)
+    out = predict_with_halo(vol, net, [0, 1], block_shape, halo)
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4)
+    out = predict_with_halo_pipelined(vol, net, ["cuda:1", "cuda:0"], block_shape, halo, batch_size=2)
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
 def test_device_path_2d_and_channels():
     class Net2d(torch.nn.Module):
         out_channels = 3
