@@ -28,18 +28,30 @@ struct AffRule {
     int include_ignore_transitions;
 };
 
+// The neighbour of voxel (d, h, w) at an offset: whether it lies inside the volume, and its linear index (the voxel's own index s
+// when it does not, so that the label load below is unconditional and always in bounds).
+__device__ __forceinline__ bool aff_neighbour(int d, int h, int w, int D, int H, int W, int od, int oh, int ow, unsigned s, unsigned& q) {
+    const int qd = d + od, qh = h + oh, qw = w + ow;
+    const bool inb = qd >= 0 && qd < D && qh >= 0 && qh < H && qw >= 0 && qw < W;
+    q = inb ? ((unsigned)qd * (unsigned)H + (unsigned)qh) * (unsigned)W + (unsigned)qw : s;
+    return inb;
+}
+
+// AffinityTransform's rule (label.py:277-327 / the brute force of test_label_transforms.py:5-55) on the two labels, branch-free:
+// the loads of several voxels can then be issued together instead of one memory latency per voxel and channel.
+__device__ __forceinline__ void aff_rule(long long lp, long long lq, bool inb, const AffRule& r, float& disaff, float& msk) {
+    const int k = r.has_ignore ? (int)(lp == r.ignore_label) + (int)(lq == r.ignore_label) : 0;
+    const bool off = !inb || k == 2 || (k == 1 && !r.include_ignore_transitions);     // masked out: (1, 0)
+    const bool trans = k == 1 && r.include_ignore_transitions;                          // transition to the ignore label: (1, 1)
+    disaff = (off || trans || lp != lq) ? 1.f : 0.f;
+    msk = off ? 0.f : 1.f;
+}
+
 __device__ __forceinline__ void aff_eval(const long long* __restrict__ lab, long long lp, int d, int h, int w, int D, int H,
                                          int W, int od, int oh, int ow, const AffRule& r, float& disaff, float& msk) {
-    const int qd = d + od, qh = h + oh, qw = w + ow;
-    if (qd < 0 || qd >= D || qh < 0 || qh >= H || qw < 0 || qw >= W) { disaff = 1.f; msk = 0.f; return; }
-    const long long lq = lab[((size_t)qd * H + qh) * W + qw];
-    if (r.has_ignore) {
-        const int k = (lp == r.ignore_label) + (lq == r.ignore_label);
-        if (k == 2 || (k == 1 && !r.include_ignore_transitions)) { disaff = 1.f; msk = 0.f; return; }
-        if (k == 1) { disaff = 1.f; msk = 1.f; return; }
-    }
-    disaff = lp != lq ? 1.f : 0.f;
-    msk = 1.f;
+    unsigned q;
+    const bool inb = aff_neighbour(d, h, w, D, H, W, od, oh, ow, ((unsigned)d * (unsigned)H + (unsigned)h) * (unsigned)W + (unsigned)w, q);
+    aff_rule(lp, lab[q], inb, r, disaff, msk);
 }
 
 // out (N, channels, D,H,W): [fg?][n disaff][fg-mask?][n masks]
@@ -198,13 +210,27 @@ affinity_dice_sums_kernel(const TP* __restrict__ pred, const long long* __restri
     for (int c = 0; c < noff; ++c) {
         const TP* p = pred + ((size_t)n * noff + c) * S;
         float a_pt = 0.f, a_pp = 0.f, a_tt = 0.f;
+        // all loads of the thread's voxels first (16 independent requests), then the arithmetic
+        const int od = offs.d[c], oh = offs.h[c], ow = offs.w[c];
+        long long lq[AD_PER_THREAD];
+        TP pv[AD_PER_THREAD];
+        bool inb[AD_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < AD_PER_THREAD; ++k) {
+            const unsigned s = base + (unsigned)k * 256u;
+            const unsigned ss = s < S ? s : 0u;
+            unsigned q;
+            inb[k] = aff_neighbour(pd[k], ph[k], pw[k], D, H, W, od, oh, ow, ss, q);
+            lq[k] = lab[q];
+            pv[k] = p[ss];
+        }
 #pragma unroll
         for (int k = 0; k < AD_PER_THREAD; ++k) {
             const unsigned s = base + (unsigned)k * 256u;
             if (s < S) {
                 float t, m;
-                aff_eval(lab, lp[k], pd[k], ph[k], pw[k], D, H, W, offs.d[c], offs.h[c], offs.w[c], rule, t, m);
-                const float pm = to_f<TP>(p[s]) * m, tm = t * m;
+                aff_rule(lp[k], lq[k], inb[k], rule, t, m);
+                const float pm = to_f<TP>(pv[k]) * m, tm = t * m;
                 a_pt = fmaf(pm, tm, a_pt);
                 a_pp = fmaf(pm, pm, a_pp);
                 a_tt = fmaf(tm, tm, a_tt);
@@ -256,13 +282,26 @@ affinity_dice_bwd_kernel(const TP* __restrict__ pred, const long long* __restric
         const float A = coef[2 * c] * go, B = coef[2 * c + 1] * go;
         const TP* p = pred + ((size_t)n * noff + c) * S;
         TG* g = grad + ((size_t)n * noff + c) * S;
+        const int od = offs.d[c], oh = offs.h[c], ow = offs.w[c];
+        long long lq[AD_PER_THREAD];
+        TP pv[AD_PER_THREAD];
+        bool inb[AD_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < AD_PER_THREAD; ++k) {          // all loads first (16 independent requests per thread)
+            const unsigned s = base + (unsigned)k * 256u;
+            const unsigned ss = s < S ? s : 0u;
+            unsigned q;
+            inb[k] = aff_neighbour(pd[k], ph[k], pw[k], D, H, W, od, oh, ow, ss, q);
+            lq[k] = lab[q];
+            pv[k] = p[ss];
+        }
 #pragma unroll
         for (int k = 0; k < AD_PER_THREAD; ++k) {
             const unsigned s = base + (unsigned)k * 256u;
             if (s < S) {
                 float t, m;
-                aff_eval(lab, lp[k], pd[k], ph[k], pw[k], D, H, W, offs.d[c], offs.h[c], offs.w[c], rule, t, m);
-                g[s] = from_f<TG>((A * t + B * to_f<TP>(p[s])) * m * m);
+                aff_rule(lp[k], lq[k], inb[k], rule, t, m);
+                g[s] = from_f<TG>((A * t + B * to_f<TP>(pv[k])) * m * m);
             }
         }
     }
