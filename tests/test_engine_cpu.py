@@ -131,3 +131,18 @@ def test_autograd_contract(golden_dir):
     y.clamp_(0.1, 0.9)
     with pytest.raises(RuntimeError, match="modified by an inplace operation"):
         y.sum().backward()
+
+
+def test_zero_arena_views_are_zero_disjoint_and_aligned():
+    """engine._ZeroArena: the per-pass reduction scratch -- zero-initialised, 16-byte aligned, non-overlapping views; a request
+    larger than what is left of (or than) a chunk opens a new buffer."""
+    import torch
+    from torch_em_b200.engine import _ZeroArena
+    ar = _ZeroArena(torch.device("cpu"))
+    views = [ar.zeros((4, 32, 2)), ar.zeros((3, 5, 2)), ar.zeros((1, 1, 2)), ar.zeros((2, _ZeroArena.CHUNK)), ar.zeros((4, 512, 2))]
+    for i, v in enumerate(views):
+        assert v.dtype == torch.float32 and v.is_contiguous() and float(v.abs().sum()) == 0.0
+        assert v.data_ptr() % 16 == 0
+        v.fill_(float(i + 1))
+    for i, v in enumerate(views):                       # nobody wrote into somebody else's view
+        assert bool((v == float(i + 1)).all())
